@@ -1,0 +1,205 @@
+/*
+ * pepper_b200.h -- C-ABI of the B200-native PEPPER hot path (libpepper_b200.so).
+ *
+ * Plain pointers and sizes only; no C++/torch types. Every entry point returns 0 on success and a negative
+ * PV_E* code on failure; pv_last_error() then holds a message (thread-local). Nothing here ever falls back
+ * to the CPU: without a CUDA device every compute entry point fails with PV_ENODEVICE.
+ *
+ * What each entry point replaces in the reference (/root/reference, paths relative to it):
+ *
+ *   pv_summary_*            RegionalSummaryGenerator::{ctor, generate_max_insert_summary, generate_summary}
+ *                           pepper_variant/modules/cpp/region_summary.cpp:9-17, 69-96, 568-916 as bound in
+ *                           pepper_variant/modules/cpp/pybind_api.h:55-62 and called from
+ *                           pepper_variant/modules/python/AlignmentSummarizer.py:220-238
+ *   PvReadBatch             type_read / CigarOp (read.h:60-108, cigar.h:30-53): packed SoA instead of AoS
+ *   PvCandidates            vector<CandidateImageSummary> (region_summary.h:88-111)
+ *   pv_lstm_*               pepper_variant TransducerGRU.forward (modules/python/models/simple_model.py:48-82)
+ *                           as driven by predict_distributed_gpu.py:57-69 (weights: ModelHander.py:18-44)
+ *   pv_gru_*                pepper (polisher) TransducerGRU.forward (pepper/modules/python/models/simple_model.py:27-42)
+ *                           and the sliding-window loop predict_distributed_gpu.py:63-96
+ */
+#ifndef PEPPER_B200_H
+#define PEPPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_OK           0
+#define PV_EINVAL      -1   /* bad argument / inconsistent batch */
+#define PV_ENODEVICE   -2   /* no CUDA device / wrong architecture (needs sm_100) */
+#define PV_ECUDA       -3   /* CUDA runtime error (message has the detail) */
+#define PV_EOVERFLOW   -4   /* more candidates than the caller-provided capacity (count is still returned) */
+#define PV_ENOMEM      -5
+
+#define PV_WINDOW       33  /* candidate_window_size + 1 rows (Options.py:8, region_summary.cpp:831) */
+#define PV_FEATURES     26  /* ImageSizeOptions.IMAGE_HEIGHT (Options.py:6) */
+#define PV_ALLELE_BYTES 64  /* "<type digit><bases>", at most 61 bytes (region_summary.cpp:461,511), NUL padded */
+
+/* CIGAR op codes (cigar.h:15-28 == BAM). cigar[] entries are BAM-encoded: (length << 4) | op. */
+enum { PV_CIGAR_MATCH = 0, PV_CIGAR_INS = 1, PV_CIGAR_DEL = 2, PV_CIGAR_REF_SKIP = 3, PV_CIGAR_SOFT_CLIP = 4,
+       PV_CIGAR_HARD_CLIP = 5, PV_CIGAR_PAD = 6, PV_CIGAR_EQUAL = 7, PV_CIGAR_DIFF = 8 };
+
+/*
+ * Packed read batch: the reads of n_regions regions, grouped by region (region_read_begin[r] ..
+ * region_read_begin[r+1]). All arrays live in the SAME memory space (all host for *_host entry points, all
+ * device for the others). Invariants checked by pv_batch_validate():
+ *   read_base_off[i] % 16 == 0; read_base_off[i] + read_len[i] <= n_bases; cigar ranges inside n_ops;
+ *   region_ref_end >= region_ref_start; region_ref_len[r] >= ref_end-ref_start+1; region_ref_off[r] + region_ref_len[r] <= n_ref;
+ *   reads per region <= 32767 (window values must fit int16).
+ */
+typedef struct PvReadBatch {
+    int64_t n_reads, n_bases, n_ops, n_ref;
+    int32_t n_regions;
+    /* per read */
+    const int64_t*  read_pos;         /* type_read.pos: reference position of the first aligned base */
+    const int64_t*  read_base_off;    /* offset of the read's first base in bases[]/quals[] (16-byte aligned) */
+    const int32_t*  read_len;         /* type_read.sequence.length() */
+    const int64_t*  read_cigar_off;   /* offset of the read's first op in cigar[] */
+    const int32_t*  read_n_ops;
+    const uint8_t*  read_flags;       /* bit0: type_read.flags.is_reverse */
+    const uint8_t*  read_mapq;        /* type_read.mapping_quality clipped to [0,255]; 0 = skipped (region_summary.cpp:619) */
+    /* per base / per op */
+    const uint8_t*  bases;            /* type_read.sequence bytes as given (any byte value) */
+    const uint8_t*  quals;            /* type_read.base_qualities (0..255) */
+    const uint32_t* cigar;
+    /* per region */
+    const int64_t*  region_ref_start; /* RegionalSummaryGenerator ctor region_start (inclusive) */
+    const int64_t*  region_ref_end;   /* region_end (inclusive) */
+    const int64_t*  region_cand_start;/* generate_summary candidate_region_start */
+    const int64_t*  region_cand_end;  /* candidate_region_end (inclusive) */
+    const int64_t*  region_ref_off;   /* offset of the region's reference_sequence in ref[] */
+    const int64_t*  region_ref_len;   /* reference_sequence.length() (>= ref_end-ref_start+1; deletion alleles are
+                                         reference substrings truncated at this length, region_summary.cpp:500) */
+    const int64_t*  region_read_begin;/* n_regions + 1 entries */
+    const uint8_t*  ref;              /* reference bytes as given; region r owns region_ref_len[r] bytes */
+} PvReadBatch;
+
+/* The ten scalars of generate_summary (region_summary.h:191-201), same order, same double compares. */
+typedef struct PvThresholds {
+    double min_snp_baseq, min_indel_baseq;
+    double snp_freq, insert_freq, delete_freq;
+    double min_coverage;
+    double snp_candidate_freq, indel_candidate_freq;
+    double candidate_support;
+    int32_t skip_indels;
+    int32_t _pad;
+} PvThresholds;
+
+/*
+ * Candidate output, caller-allocated for `capacity` candidates, ordered like the reference emits them
+ * (region ascending, position ascending, allele in std::set<std::string> order; region_summary.cpp:669-670).
+ */
+typedef struct PvCandidates {
+    int64_t  capacity;
+    int16_t* windows;     /* [capacity][33][26] CandidateImageSummary.image_matrix (values as C++ int, fit int16) */
+    int64_t* position;    /* CandidateImageSummary.position */
+    int32_t* region;      /* index of the region in the batch (gives .contig) */
+    int32_t* depth;       /* CandidateImageSummary.depth (<=125) */
+    int32_t* frequency;   /* CandidateImageSummary.candidate_frequency[0] (<=125) */
+    uint8_t* allele;      /* [capacity][PV_ALLELE_BYTES] CandidateImageSummary.candidates[0] */
+    uint8_t* allele_len;  /* strlen of the above */
+} PvCandidates;
+
+const char* pv_version(void);
+const char* pv_last_error(void);
+/* number of usable CUDA devices (sm_100); 0 when none. Never fails. */
+int pv_device_count(void);
+
+/* Host-side consistency check of a HOST-resident batch. */
+int pv_batch_validate(const PvReadBatch* host_batch);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Summary: device-resident interface. `stream` is a cudaStream_t passed as void*.
+ * pv_summary_workspace_bytes: bytes of scratch pv_summary_regions needs for this batch shape.
+ * pv_summary_regions: everything asynchronous on `stream`; *n_candidates_dev (device int64) receives the
+ *   number of candidates found. If it exceeds out->capacity only the first `capacity` (in reference order)
+ *   are stored; the host wrapper reports PV_EOVERFLOW.
+ * dense_image_dev (optional, may be NULL): int16 [total_positions][26] clamped image_matrix of every region
+ *   back to back (debug / parity hook for region_summary.cpp:598-654).
+ * ------------------------------------------------------------------------------------------------------- */
+int64_t pv_summary_workspace_bytes(int64_t n_reads, int64_t n_ops, int32_t n_regions, int64_t total_positions,
+                                   int64_t capacity);
+int pv_summary_regions(const PvReadBatch* batch_dev_ptrs, const int64_t* region_len_host, int64_t total_positions,
+                       const PvThresholds* thr, int32_t window, int32_t features,
+                       const PvCandidates* out_dev_ptrs, int64_t* n_candidates_dev,
+                       void* workspace_dev, int64_t workspace_bytes, int16_t* dense_image_dev, void* stream);
+
+/* Summary: host-buffer convenience (what the pybind RegionalSummaryGenerator and bench e2e call).
+ * Copies the batch to the current device, runs pv_summary_regions, copies the candidates back.
+ * out_host arrays are host memory with `capacity` slots; *n_candidates receives the true count. */
+int pv_summary_regions_host(const PvReadBatch* host_batch, const PvThresholds* thr, int32_t window, int32_t features,
+                            const PvCandidates* out_host, int64_t* n_candidates, int16_t* dense_image_host);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Model M-A: pepper_variant TransducerGRU (2x biLSTM-256 + 5x SELU MLP + softmax(3)).
+ * Weights are the fp32 tensors of the checkpoint's model_state_dict (train_distributed.py:36-42), row-major,
+ * PyTorch layouts; [2] = {forward, reverse}.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct PvLstmWeights {
+    const float* enc_w_ih[2];   /* [1024][26]  encoder.weight_ih_l0(_reverse), gate rows i,f,g,o */
+    const float* enc_w_hh[2];   /* [1024][256] */
+    const float* enc_b_ih[2];   /* [1024] */
+    const float* enc_b_hh[2];   /* [1024] */
+    const float* dec_w_ih[2];   /* [1024][512] */
+    const float* dec_w_hh[2];   /* [1024][256] */
+    const float* dec_b_ih[2];
+    const float* dec_b_hh[2];
+    const float* lin_w[5];      /* linear_1 [512][16896], linear_2..5 [512][512] */
+    const float* lin_b[5];      /* [512] */
+    const float* out_w;         /* output_layer_type [3][512] */
+    const float* out_b;         /* [3] */
+} PvLstmWeights;
+
+typedef struct PvLstmModel PvLstmModel;
+int pv_lstm_create(const PvLstmWeights* host_weights, PvLstmModel** model);
+void pv_lstm_destroy(PvLstmModel* model);
+int64_t pv_lstm_workspace_bytes(int64_t max_windows);
+/* windows_dev int16 [n][33][26]; probs_dev float [n][3] (softmax); argmax_dev uint8 [n] (may be NULL).
+ * wrap_int8 != 0 reproduces the reference pipeline's int8 HDF5 round trip (DataStore.py:68,
+ * dataloader_predict.py:90): the value fed to the network is (int8_t)window value. */
+int pv_lstm_infer(PvLstmModel* model, const int16_t* windows_dev, int64_t n, int32_t wrap_int8,
+                  float* probs_dev, uint8_t* argmax_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+/* host-buffer convenience: H2D, infer (in chunks), D2H */
+int pv_lstm_infer_host(PvLstmModel* model, const int16_t* windows_host, int64_t n, int32_t wrap_int8,
+                       float* probs_host, uint8_t* argmax_host);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Model M-B: pepper (polisher) TransducerGRU (2x biGRU-128 + Linear(256,5)), T = 100 positions, 10 features.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct PvGruWeights {
+    const float* enc_w_ih[2];   /* [384][10]  gru_encoder.weight_ih_l0(_reverse), gate rows r,z,n */
+    const float* enc_w_hh[2];   /* [384][128] */
+    const float* enc_b_ih[2];   /* [384] */
+    const float* enc_b_hh[2];
+    const float* dec_w_ih[2];   /* [384][256] */
+    const float* dec_w_hh[2];   /* [384][128] */
+    const float* dec_b_ih[2];
+    const float* dec_b_hh[2];
+    const float* dense_w;       /* dense1 [5][256] */
+    const float* dense_b;       /* [5] */
+} PvGruWeights;
+
+typedef struct PvGruModel PvGruModel;
+int pv_gru_create(const PvGruWeights* host_weights, PvGruModel** model);
+void pv_gru_destroy(PvGruModel* model);
+int64_t pv_gru_workspace_bytes(int64_t max_batch, int32_t seq_len);
+/* One TransducerGRU.forward: images_dev uint8 [n][seq_len][10] (raw 0..254 counts cast to float, no
+ * normalisation; predict_distributed_gpu.py:60), hidden_dev float [n][2][128] read as h0 and overwritten with
+ * the decoder's h_n; logits_dev float [n][seq_len][5]. */
+int pv_gru_forward(PvGruModel* model, const uint8_t* images_dev, int64_t n, int32_t seq_len, float* hidden_dev,
+                   float* logits_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+/* The polisher's chunk loop (predict_distributed_gpu.py:63-96): images_dev uint8 [n][chunk_len][10]; windows of
+ * `window` positions every `stride`; hidden carried between windows; softmax summed over overlaps into
+ * prob_sum_dev float [n][chunk_len][5]; labels_dev uint8 [n][chunk_len] = argmax. */
+int pv_gru_predict_chunks(PvGruModel* model, const uint8_t* images_dev, int64_t n, int32_t chunk_len, int32_t window,
+                          int32_t stride, float* prob_sum_dev, uint8_t* labels_dev, void* workspace_dev,
+                          int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEPPER_B200_H */

@@ -1,0 +1,236 @@
+"""Packed SoA read batch -- the host side of ``PvReadBatch`` (include/pepper_b200.h).
+
+Replaces the AoS ``list[type_read]`` the reference hands across pybind
+(/root/reference/pepper_variant/modules/cpp/read.h:60-108, cigar.h:30-53): one byte per base, one byte per
+quality, BAM-encoded CIGAR words, per-read headers, per-region headers. Reads of a region are contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+
+_READ_FIELDS = [("read_pos", np.int64), ("read_base_off", np.int64), ("read_len", np.int32),
+                ("read_cigar_off", np.int64), ("read_n_ops", np.int32), ("read_flags", np.uint8),
+                ("read_mapq", np.uint8)]
+_REGION_FIELDS = [("region_ref_start", np.int64), ("region_ref_end", np.int64), ("region_cand_start", np.int64),
+                  ("region_cand_end", np.int64), ("region_ref_off", np.int64), ("region_ref_len", np.int64)]
+
+
+class PvReadBatchStruct(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64), ("n_ref", C.c_int64),
+                ("n_regions", C.c_int32),
+                ("read_pos", C.c_void_p), ("read_base_off", C.c_void_p), ("read_len", C.c_void_p),
+                ("read_cigar_off", C.c_void_p), ("read_n_ops", C.c_void_p), ("read_flags", C.c_void_p),
+                ("read_mapq", C.c_void_p),
+                ("bases", C.c_void_p), ("quals", C.c_void_p), ("cigar", C.c_void_p),
+                ("region_ref_start", C.c_void_p), ("region_ref_end", C.c_void_p), ("region_cand_start", C.c_void_p),
+                ("region_cand_end", C.c_void_p), ("region_ref_off", C.c_void_p), ("region_ref_len", C.c_void_p),
+                ("region_read_begin", C.c_void_p),
+                ("ref", C.c_void_p)]
+
+
+ARRAY_NAMES = [n for n, _ in _READ_FIELDS] + ["bases", "quals", "cigar"] + [n for n, _ in _REGION_FIELDS] + \
+              ["region_read_begin", "ref"]
+
+
+@dataclass
+class ReadBatch:
+    """Host-resident packed batch (numpy arrays, C-contiguous)."""
+    read_pos: np.ndarray
+    read_base_off: np.ndarray
+    read_len: np.ndarray
+    read_cigar_off: np.ndarray
+    read_n_ops: np.ndarray
+    read_flags: np.ndarray
+    read_mapq: np.ndarray
+    bases: np.ndarray
+    quals: np.ndarray
+    cigar: np.ndarray
+    region_ref_start: np.ndarray
+    region_ref_end: np.ndarray
+    region_cand_start: np.ndarray
+    region_cand_end: np.ndarray
+    region_ref_off: np.ndarray
+    region_ref_len: np.ndarray
+    region_read_begin: np.ndarray
+    ref: np.ndarray
+    contigs: List[str] = field(default_factory=list)
+
+    # ---- shape helpers -------------------------------------------------------------------------------------
+    @property
+    def n_reads(self) -> int:
+        return int(self.read_pos.shape[0])
+
+    @property
+    def n_regions(self) -> int:
+        return int(self.region_ref_start.shape[0])
+
+    @property
+    def n_bases(self) -> int:
+        return int(self.bases.shape[0])
+
+    @property
+    def n_ops(self) -> int:
+        return int(self.cigar.shape[0])
+
+    @property
+    def region_len(self) -> np.ndarray:
+        return (self.region_ref_end - self.region_ref_start + 1).astype(np.int64)
+
+    @property
+    def total_positions(self) -> int:
+        return int(self.region_len.sum())
+
+    @property
+    def candidate_bp(self) -> int:
+        """Reference positions of the candidate regions (the unit of the Mbp/s metric)."""
+        return int((self.region_cand_end - self.region_cand_start + 1).sum())
+
+    def algorithmic_bytes(self, n_candidates: int) -> int:
+        """2*N_bases + 4*N_ops + 32*N_reads + L + K*(33*26*2 + 32)."""
+        real_bases = int(self.read_len.astype(np.int64).sum())
+        return 2 * real_bases + 4 * self.n_ops + 32 * self.n_reads + self.total_positions + \
+            n_candidates * (33 * 26 * 2 + 32)
+
+    def as_struct(self, arrays=None) -> PvReadBatchStruct:
+        """ctypes view. ``arrays`` may map names to integer (device) pointers instead of the numpy arrays."""
+        s = PvReadBatchStruct()
+        s.n_reads, s.n_bases, s.n_ops, s.n_ref = self.n_reads, self.n_bases, self.n_ops, int(self.ref.shape[0])
+        s.n_regions = self.n_regions
+        for name in ARRAY_NAMES:
+            if arrays is not None:
+                setattr(s, name, int(arrays[name]))
+            else:
+                a = getattr(self, name)
+                assert a.flags["C_CONTIGUOUS"], name
+                setattr(s, name, a.ctypes.data)
+        return s
+
+    def region_slice(self, r: int) -> "ReadBatch":
+        """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""
+        return select_regions(self, [r])
+
+
+def select_regions(batch: ReadBatch, regions: Sequence[int]) -> ReadBatch:
+    """Re-pack the given regions (in the given order) into a fresh batch."""
+    parts = {n: [] for n in ARRAY_NAMES}
+    b_cur = o_cur = f_cur = r_cur = 0
+    read_begin = [0]
+    contigs = []
+    for r in regions:
+        lo, hi = int(batch.region_read_begin[r]), int(batch.region_read_begin[r + 1])
+        L = int(batch.region_ref_len[r])
+        fo = int(batch.region_ref_off[r])
+        parts["ref"].append(batch.ref[fo:fo + L])
+        parts["region_ref_len"].append(np.array([L], np.int64))
+        for n in ("region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end"):
+            parts[n].append(getattr(batch, n)[r:r + 1])
+        parts["region_ref_off"].append(np.array([f_cur], np.int64))
+        f_cur += L
+        if batch.contigs:
+            contigs.append(batch.contigs[r])
+        if hi > lo:
+            bo = batch.read_base_off[lo:hi]
+            ln = batch.read_len[lo:hi].astype(np.int64)
+            b_lo, b_hi = int(bo.min()), int((bo + ((ln + 15) & ~15)).max())
+            b_hi = min(b_hi, batch.n_bases)
+            co = batch.read_cigar_off[lo:hi]
+            c_lo, c_hi = int(co.min()), int((co + batch.read_n_ops[lo:hi]).max())
+            parts["bases"].append(batch.bases[b_lo:b_hi])
+            parts["quals"].append(batch.quals[b_lo:b_hi])
+            parts["cigar"].append(batch.cigar[c_lo:c_hi])
+            parts["read_base_off"].append(bo - b_lo + b_cur)
+            parts["read_cigar_off"].append(co - c_lo + o_cur)
+            pad = (-(b_hi - b_lo)) % 16
+            if pad:
+                parts["bases"].append(np.zeros(pad, np.uint8))
+                parts["quals"].append(np.zeros(pad, np.uint8))
+            b_cur += b_hi - b_lo + pad
+            o_cur += c_hi - c_lo
+            for n in ("read_pos", "read_len", "read_n_ops", "read_flags", "read_mapq"):
+                parts[n].append(getattr(batch, n)[lo:hi])
+        r_cur += hi - lo
+        read_begin.append(r_cur)
+    dt = dict(_READ_FIELDS + _REGION_FIELDS)
+    dt.update(bases=np.uint8, quals=np.uint8, cigar=np.uint32, ref=np.uint8, region_read_begin=np.int64)
+    out = {}
+    for n in ARRAY_NAMES:
+        if n == "region_read_begin":
+            out[n] = np.asarray(read_begin, np.int64)
+        else:
+            out[n] = np.ascontiguousarray(np.concatenate(parts[n]).astype(dt[n], copy=False)) if parts[n] \
+                else np.zeros(0, dt[n])
+    return ReadBatch(contigs=contigs, **out)
+
+
+@dataclass
+class Region:
+    """One call of AlignmentSummarizer.create_summary: the generator ctor args + the candidate interval."""
+    contig: str
+    ref_start: int
+    ref_end: int
+    reference: bytes
+    cand_start: int
+    cand_end: int
+    reads: list     # objects with .pos .sequence .base_qualities .cigar_tuples(.cigar_op/.cigar_len) .flags.is_reverse .mapping_quality
+
+
+def pack_regions(regions: Sequence[Region]) -> ReadBatch:
+    """Pack reference-style read objects (``type_read`` duck type, pybind_api.h:208-221) into a ReadBatch."""
+    rp, bo, rl, co, no, fl, mq = [], [], [], [], [], [], []
+    bases, quals, cig, refs = [], [], [], []
+    rs, re_, cs, ce, ro, rln, rb = [], [], [], [], [], [], [0]
+    b_cur = o_cur = f_cur = 0
+    for reg in regions:
+        ref = reg.reference.encode() if isinstance(reg.reference, str) else bytes(reg.reference)
+        L = reg.ref_end - reg.ref_start + 1
+        if L <= 0:
+            raise ValueError("region_end < region_start")
+        if len(ref) < L:
+            raise ValueError("reference_sequence shorter than region_end - region_start + 1")
+        if len(reg.reads) > 32767:
+            raise ValueError("more than 32767 reads in a region: window values would not fit int16")
+        refs.append(np.frombuffer(ref, np.uint8))
+        rs.append(reg.ref_start); re_.append(reg.ref_end); cs.append(reg.cand_start); ce.append(reg.cand_end)
+        ro.append(f_cur); rln.append(len(ref)); f_cur += len(ref)
+        for rd in reg.reads:
+            seq = rd.sequence.encode("latin-1") if isinstance(rd.sequence, str) else bytes(rd.sequence)
+            q = np.asarray(rd.base_qualities, dtype=np.int64)
+            if q.shape[0] != len(seq):
+                raise ValueError("base_qualities and sequence differ in length")
+            if q.size and (q.min() < 0 or q.max() > 255):
+                raise ValueError("base quality outside [0, 255]")
+            ops = rd.cigar_tuples
+            words = np.empty(len(ops), np.uint32)
+            for k, op in enumerate(ops):
+                o, l = (op.cigar_op, op.cigar_len) if hasattr(op, "cigar_op") else op
+                if not (0 <= o <= 15) or not (0 <= l < (1 << 28)):
+                    raise ValueError("bad CIGAR op")
+                words[k] = (l << 4) | o
+            n = len(seq)
+            pad = (-n) % 16
+            rp.append(int(rd.pos)); bo.append(b_cur); rl.append(n); co.append(o_cur); no.append(len(ops))
+            fl.append(1 if rd.flags.is_reverse else 0)
+            mq.append(min(255, max(0, int(rd.mapping_quality))))
+            bases.append(np.frombuffer(seq + b"\0" * pad, np.uint8))
+            quals.append(np.concatenate([q.astype(np.uint8), np.zeros(pad, np.uint8)]))
+            cig.append(words)
+            b_cur += n + pad; o_cur += len(ops)
+        rb.append(len(rp))
+
+    def cat(parts, dt):
+        return np.ascontiguousarray(np.concatenate(parts).astype(dt, copy=False)) if parts else np.zeros(0, dt)
+
+    return ReadBatch(
+        read_pos=np.asarray(rp, np.int64), read_base_off=np.asarray(bo, np.int64), read_len=np.asarray(rl, np.int32),
+        read_cigar_off=np.asarray(co, np.int64), read_n_ops=np.asarray(no, np.int32),
+        read_flags=np.asarray(fl, np.uint8), read_mapq=np.asarray(mq, np.uint8),
+        bases=cat(bases, np.uint8), quals=cat(quals, np.uint8), cigar=cat(cig, np.uint32),
+        region_ref_start=np.asarray(rs, np.int64), region_ref_end=np.asarray(re_, np.int64),
+        region_cand_start=np.asarray(cs, np.int64), region_cand_end=np.asarray(ce, np.int64),
+        region_ref_off=np.asarray(ro, np.int64), region_ref_len=np.asarray(rln, np.int64),
+        region_read_begin=np.asarray(rb, np.int64),
+        ref=cat(refs, np.uint8), contigs=[r.contig for r in regions])
