@@ -1,0 +1,203 @@
+// C-ABI plumbing of libpepper_b200.so: error state, device checks, batch validation and the host-buffer
+// convenience entry point for the summary path (include/pepper_b200.h).
+#include "common.cuh"
+#include <mutex>
+#include <vector>
+
+namespace pv {
+
+char* err_buf() {
+    static thread_local char buf[1024] = {0};
+    return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(err_buf(), 1024, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(PV_ENODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    int dev = 0;
+    PV_CUDA_CHECK(cudaGetDevice(&dev));
+    int major = 0;
+    PV_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return set_error(PV_ENODEVICE, "device %d has compute capability %d.x; kernels are built for sm_100a only", dev, major);
+    return PV_OK;
+}
+
+int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+// grow-only device buffers reused across host-wrapper calls (one set per process; one process per GPU)
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return PV_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); return set_error(PV_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return PV_OK;
+    }
+};
+
+}  // namespace pv
+
+extern "C" const char* pv_version(void) { return "pepper_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* pv_last_error(void) { return pv::err_buf(); }
+
+extern "C" int pv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+extern "C" int pv_batch_validate(const PvReadBatch* b) {
+    if (!b) return pv::set_error(PV_EINVAL, "null batch");
+    if (b->n_reads < 0 || b->n_bases < 0 || b->n_ops < 0 || b->n_regions < 0 || b->n_ref < 0)
+        return pv::set_error(PV_EINVAL, "negative size");
+    if (b->n_regions == 0) return PV_OK;
+    if (!b->region_read_begin || b->region_read_begin[0] != 0 || b->region_read_begin[b->n_regions] != b->n_reads)
+        return pv::set_error(PV_EINVAL, "region_read_begin must start at 0 and end at n_reads");
+    for (int32_t r = 0; r < b->n_regions; r++) {
+        const int64_t L = b->region_ref_end[r] - b->region_ref_start[r] + 1;
+        if (L <= 0) return pv::set_error(PV_EINVAL, "region %d: region_end < region_start", r);
+        if (L > 0x7fffffffll) return pv::set_error(PV_EINVAL, "region %d longer than 2^31", r);
+        if (b->region_ref_len[r] < L) return pv::set_error(PV_EINVAL, "region %d: reference_sequence shorter than the region", r);
+        if (b->region_ref_off[r] < 0 || b->region_ref_off[r] + b->region_ref_len[r] > b->n_ref)
+            return pv::set_error(PV_EINVAL, "region %d: reference outside ref[]", r);
+        const int64_t n = b->region_read_begin[r + 1] - b->region_read_begin[r];
+        if (n < 0) return pv::set_error(PV_EINVAL, "region_read_begin not monotone at region %d", r);
+        if (n > 32767) return pv::set_error(PV_EINVAL, "region %d has %lld reads; more than 32767 would not fit the int16 windows", r, (long long)n);
+    }
+    for (int64_t i = 0; i < b->n_reads; i++) {
+        if (b->read_base_off[i] < 0 || (b->read_base_off[i] & 15) || b->read_len[i] < 0 ||
+            b->read_base_off[i] + b->read_len[i] > b->n_bases)
+            return pv::set_error(PV_EINVAL, "read %lld: bases outside bases[] or not 16-byte aligned", (long long)i);
+        if (b->read_cigar_off[i] < 0 || b->read_n_ops[i] < 0 || b->read_cigar_off[i] + b->read_n_ops[i] > b->n_ops)
+            return pv::set_error(PV_EINVAL, "read %lld: cigar outside cigar[]", (long long)i);
+        int64_t tot = 0;
+        const uint32_t* c = b->cigar + b->read_cigar_off[i];
+        for (int32_t k = 0; k < b->read_n_ops[i]; k++) tot += (int64_t)(c[k] >> 4);
+        if (tot > 0x3fffffffll) return pv::set_error(PV_EINVAL, "read %lld: CIGAR longer than 2^30", (long long)i);
+    }
+    return PV_OK;
+}
+
+namespace {
+
+struct HostCtx {
+    std::mutex mu;
+    pv::DevBuf arr[18];      // batch arrays in PvReadBatch order
+    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense;
+    cudaStream_t stream = nullptr;
+};
+HostCtx& host_ctx() { static HostCtx c; return c; }
+
+}  // namespace
+
+extern "C" int pv_summary_status_offset(void);
+
+extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds* thr, int32_t window, int32_t features,
+                                       const PvCandidates* out, int64_t* n_candidates, int16_t* dense_image_host) {
+    if (!hb || !thr || !out || !n_candidates) return pv::set_error(PV_EINVAL, "null argument");
+    *n_candidates = 0;
+    if (int rc = pv_batch_validate(hb)) return rc;
+    if (int rc = pv::require_device()) return rc;
+    if (hb->n_regions == 0) return PV_OK;
+    HostCtx& h = host_ctx();
+    std::lock_guard<std::mutex> lock(h.mu);
+    if (!h.stream) PV_CUDA_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    cudaStream_t st = h.stream;
+
+    std::vector<int64_t> rlen(hb->n_regions);
+    int64_t total = 0;
+    for (int32_t r = 0; r < hb->n_regions; r++) { rlen[r] = hb->region_ref_end[r] - hb->region_ref_start[r] + 1; total += rlen[r]; }
+
+    const void* src[18] = {hb->read_pos, hb->read_base_off, hb->read_len, hb->read_cigar_off, hb->read_n_ops, hb->read_flags,
+                           hb->read_mapq, hb->bases, hb->quals, hb->cigar, hb->region_ref_start, hb->region_ref_end,
+                           hb->region_cand_start, hb->region_cand_end, hb->region_ref_off, hb->region_ref_len,
+                           hb->region_read_begin, hb->ref};
+    const size_t bytes[18] = {(size_t)hb->n_reads * 8, (size_t)hb->n_reads * 8, (size_t)hb->n_reads * 4, (size_t)hb->n_reads * 8,
+                              (size_t)hb->n_reads * 4, (size_t)hb->n_reads, (size_t)hb->n_reads, (size_t)hb->n_bases,
+                              (size_t)hb->n_bases, (size_t)hb->n_ops * 4, (size_t)hb->n_regions * 8, (size_t)hb->n_regions * 8,
+                              (size_t)hb->n_regions * 8, (size_t)hb->n_regions * 8, (size_t)hb->n_regions * 8,
+                              (size_t)hb->n_regions * 8, (size_t)(hb->n_regions + 1) * 8, (size_t)hb->n_ref};
+    for (int i = 0; i < 18; i++) {
+        if (int rc = h.arr[i].reserve(bytes[i] + 16)) return rc;
+        if (bytes[i]) PV_CUDA_CHECK(cudaMemcpyAsync(h.arr[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
+    }
+    PvReadBatch db = *hb;
+    db.read_pos = (const int64_t*)h.arr[0].p; db.read_base_off = (const int64_t*)h.arr[1].p; db.read_len = (const int32_t*)h.arr[2].p;
+    db.read_cigar_off = (const int64_t*)h.arr[3].p; db.read_n_ops = (const int32_t*)h.arr[4].p; db.read_flags = (const uint8_t*)h.arr[5].p;
+    db.read_mapq = (const uint8_t*)h.arr[6].p; db.bases = (const uint8_t*)h.arr[7].p; db.quals = (const uint8_t*)h.arr[8].p;
+    db.cigar = (const uint32_t*)h.arr[9].p; db.region_ref_start = (const int64_t*)h.arr[10].p; db.region_ref_end = (const int64_t*)h.arr[11].p;
+    db.region_cand_start = (const int64_t*)h.arr[12].p; db.region_cand_end = (const int64_t*)h.arr[13].p;
+    db.region_ref_off = (const int64_t*)h.arr[14].p; db.region_ref_len = (const int64_t*)h.arr[15].p;
+    db.region_read_begin = (const int64_t*)h.arr[16].p; db.ref = (const uint8_t*)h.arr[17].p;
+
+    const int64_t cap = out->capacity > 0 ? out->capacity : 1;
+    const int64_t ws_bytes = pv_summary_workspace_bytes(hb->n_reads, hb->n_ops, hb->n_regions, total, cap);
+    if (int rc = h.ws.reserve((size_t)ws_bytes)) return rc;
+    if (int rc = h.win.reserve((size_t)cap * PV_WINDOW * PV_FEATURES * 2)) return rc;
+    if (int rc = h.pos.reserve((size_t)cap * 8)) return rc;
+    if (int rc = h.reg.reserve((size_t)cap * 4)) return rc;
+    if (int rc = h.dep.reserve((size_t)cap * 4)) return rc;
+    if (int rc = h.frq.reserve((size_t)cap * 4)) return rc;
+    if (int rc = h.al.reserve((size_t)cap * PV_ALLELE_BYTES)) return rc;
+    if (int rc = h.aln.reserve((size_t)cap)) return rc;
+    if (int rc = h.cnt.reserve(64)) return rc;
+    int16_t* dense_dev = nullptr;
+    if (dense_image_host) {
+        if (int rc = h.dense.reserve((size_t)total * PV_FEATURES * 2)) return rc;
+        dense_dev = (int16_t*)h.dense.p;
+    }
+    PvCandidates dout;
+    dout.capacity = cap; dout.windows = (int16_t*)h.win.p; dout.position = (int64_t*)h.pos.p; dout.region = (int32_t*)h.reg.p;
+    dout.depth = (int32_t*)h.dep.p; dout.frequency = (int32_t*)h.frq.p; dout.allele = (uint8_t*)h.al.p; dout.allele_len = (uint8_t*)h.aln.p;
+
+    if (int rc = pv_summary_regions(&db, rlen.data(), total, thr, window, features, &dout, (int64_t*)h.cnt.p, h.ws.p,
+                                    (int64_t)h.ws.cap, dense_dev, st)) return rc;
+    int64_t found = 0; int32_t status = 0;
+    PV_CUDA_CHECK(cudaMemcpyAsync(&found, h.cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PV_CUDA_CHECK(cudaMemcpyAsync(&status, (const uint8_t*)h.ws.p + pv_summary_status_offset(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PV_CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_candidates = found;
+    if (status & 8) return pv::set_error(PV_ECUDA, "internal inconsistency in the allele event pass (status %d)", status);
+    if (status & 3) return pv::set_error(PV_EOVERFLOW, "site/event scratch overflow (status %d): raise the candidate capacity", status);
+    const int64_t n = found < out->capacity ? found : out->capacity;
+    if (n > 0) {
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->windows, dout.windows, (size_t)n * PV_WINDOW * PV_FEATURES * 2, cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->position, dout.position, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->region, dout.region, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->depth, dout.depth, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->frequency, dout.frequency, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->allele, dout.allele, (size_t)n * PV_ALLELE_BYTES, cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(out->allele_len, dout.allele_len, (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    if (dense_image_host)
+        PV_CUDA_CHECK(cudaMemcpyAsync(dense_image_host, dense_dev, (size_t)total * PV_FEATURES * 2, cudaMemcpyDeviceToHost, st));
+    PV_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (found > out->capacity)
+        return pv::set_error(PV_EOVERFLOW, "%lld candidates found but capacity is %lld", (long long)found, (long long)out->capacity);
+    return PV_OK;
+}

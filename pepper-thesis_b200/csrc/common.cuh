@@ -1,0 +1,43 @@
+// Shared host/device helpers of libpepper_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "pepper_b200.h"
+
+namespace pv {
+
+// thread-local last-error message (pv_last_error)
+char* err_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define PV_CUDA_CHECK(expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return pv::set_error(PV_ECUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,     \
+                                 cudaGetErrorString(e_));                                          \
+    } while (0)
+
+// 0 when a usable sm_100 device is current, else PV_ENODEVICE with the message set.
+int require_device();
+int sm_count();
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over a caller-provided workspace
+struct Arena {
+    uint8_t* base; int64_t size; int64_t cur;
+    Arena(void* p, int64_t n) : base((uint8_t*)p), size(n), cur(0) {}
+    template <typename T> T* take(int64_t count) {
+        cur = align_up(cur, 256);
+        T* p = (T*)(base ? base + cur : nullptr);
+        cur += count * (int64_t)sizeof(T);
+        return p;
+    }
+    bool ok() const { return cur <= size; }
+};
+
+}  // namespace pv

@@ -1,0 +1,839 @@
+// Pileup summary on sm_100a: the B200-native replacement of RegionalSummaryGenerator::generate_summary
+// (/root/reference/pepper_variant/modules/cpp/region_summary.cpp:337-916, inference mode).
+//
+// Kernel chain (all on one stream, no host synchronisation):
+//   K0 cigar_prefix_kernel   warp per read: exclusive prefix of (reference advance, read advance) per CIGAR op,
+//                            with the REF_SKIP/PAD -> SOFT_CLIP fall-through of region_summary.cpp:556-561.
+//   K1 pileup_tile_kernel    CTA per tile of P reference positions of one region. Phase A walks every read that
+//                            overlaps the tile (warp per read, 32 ops per step, aligned bases flattened across
+//                            the lanes) and accumulates the per-position counters in SHARED memory with 32-bit
+//                            atomics on words that pack the forward strand in the low half and the reverse
+//                            strand in the high half. Phase B turns the counters into the clamped int16
+//                            image rows (flushed to HBM), evaluates the site thresholds in fp64 exactly like
+//                            :634-646 and registers candidate sites. Phase C re-walks only the CIGAR ops (no
+//                            bases) and records the insert/delete alleles of the registered sites.
+//   K2 site_allele_kernel    warp per site: exact de-duplication of the recorded alleles (byte-wise compares, no
+//                            hashing), per-allele filters of :682-712, one candidate record per survivor with a
+//                            64-bit order key (position, type, allele rank).
+//   cub radix sort           of the candidate keys -> the reference's emission order (:669-670).
+//   K3 emit_window_kernel    warp per candidate in sorted order: 33x26 int16 window from the dense image with
+//                            the centre-row / deletion-span overrides of :848-905, plus position/depth/... .
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <vector>
+
+namespace {
+
+constexpr int NC = 14;           // packed 32-bit counter words per position
+constexpr int K1_THREADS = 512;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int MAX_PPT = 8;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
+constexpr int LIST_CAP = 1024;   // overlapping-read list entries per round
+constexpr int WIN_ELEMS = PV_WINDOW * PV_FEATURES;   // 858
+
+enum { C_REF = 0, C_BASE = 1 /* +0..6 = A C G T I D * */, C_COVSNP = 8, C_INSDEL = 9, C_SNP = 10 /* +0..3 = A C G T */ };
+enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_COUNT = 8 };
+enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8 };
+enum { PF_SITE = 1, PF_SNP = 2, PF_INS = 4, PF_DEL = 8, PF_OTHER = 16 };
+
+struct SiteRec {
+    int64_t gpos;          // dense position index (region-major)
+    int32_t region;
+    int32_t local;         // position - region_ref_start
+    int32_t cov;
+    int32_t flags;         // PF_*
+    int32_t ev_off;        // first event slot
+    int32_t n_ev;          // events this site will receive
+    int32_t fill;          // atomic cursor (phase C)
+    uint16_t snp[8];       // "1A","1C","1G","1T" x {fwd, rev}
+    int32_t pad;
+};
+
+struct Event {             // one recorded allele observation
+    int64_t ptr;           // byte offset of the allele's first byte in bases[] (type 1,2) or ref[] (type 3)
+    uint32_t info;         // type | rev << 2 | elen << 8
+    uint32_t pad;
+};
+
+struct CandRec {
+    int64_t ptr;           // allele bytes (see Event); for dense SNP alleles: the byte itself
+    int32_t site;
+    uint32_t info;         // type | dense_snp << 2 | elen << 8
+    int32_t nf, nr;
+};
+
+struct SumParams {
+    PvReadBatch b;
+    const int64_t* pos_off;       // [n_regions + 1] dense position offset of each region
+    const int32_t* tile_region;   // [n_tiles]
+    const int32_t* tile_start;    // [n_tiles] first region-relative position of the tile
+    int32_t P;                    // tile size
+    int32_t* op_ref;              // [n_ops] reference advance before the op (relative to read_pos)
+    int32_t* op_ri;               // [n_ops] read index before the op
+    int32_t* read_span;           // [n_reads] total reference advance
+    int16_t* img;                 // [total_positions][26]
+    SiteRec* sites; int32_t site_cap;
+    Event* events; int32_t ev_cap;
+    CandRec* cands; unsigned long long* cand_key; int32_t cand_cap;
+    int32_t* ctr;                 // CTR_*
+    int32_t qthr;                 // ceil(min_snp_baseq): q >= min_snp_baseq  <=>  q >= qthr for integer q
+    PvThresholds t;
+};
+
+__device__ __forceinline__ bool valid_ref(uint8_t c) {          // check_ref_base, region_summary.cpp:193-199
+    c |= 0x20; return c == 'a' || c == 'c' || c == 'g' || c == 't';
+}
+__device__ __forceinline__ uint8_t upc(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+__device__ __forceinline__ int base_class(uint8_t b) {          // get_feature_index, :201-230 (0..6 = A C G T I D *)
+    switch (upc(b)) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+                      case 'I': return 4; case 'D': return 5; default: return 6; }
+}
+__device__ __forceinline__ int ref_value(uint8_t b) {           // get_reference_feature_value, :165-172
+    switch (upc(b)) { case 'A': return 1; case 'C': return 2; case 'G': return 3; case 'T': return 4; default: return 5; }
+}
+__device__ __forceinline__ int acgt_code(uint8_t b) {           // upper-case only: dense SNP allele slot
+    return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1;
+}
+__device__ __forceinline__ bool is_match_op(int op) { return op == 0 || op == 7 || op == 8; }
+__device__ __forceinline__ int min125(int v) { return v < 125 ? v : 125; }
+
+// first k in [0, n) with a[k] >= key (n if none); a non-decreasing; all 32 lanes cooperate (32-ary search)
+__device__ int warp_lower_bound(const int32_t* __restrict__ a, int n, int64_t key, int lane) {
+    int lo = 0, hi = n;
+    while (hi > lo) {
+        const int len = hi - lo;
+        const int step = (len + 31) >> 5;
+        int idx = lo + (lane + 1) * step - 1;
+        if (idx > hi - 1) idx = hi - 1;
+        const bool pred = (int64_t)a[idx] >= key;
+        const unsigned m = __ballot_sync(0xffffffffu, pred);
+        if (m == 0) return hi;
+        const int l = __ffs(m) - 1;
+        const int nlo = lo + l * step;
+        int nhi = lo + (l + 1) * step - 1;
+        if (nhi > hi - 1) nhi = hi - 1;
+        if (step == 1) return nlo;
+        lo = nlo; hi = nhi;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K0
+// ------------------------------------------------------------------------------------------------------------
+__global__ void cigar_prefix_kernel(PvReadBatch b, int32_t* __restrict__ op_ref, int32_t* __restrict__ op_ri,
+                                    int32_t* __restrict__ read_span) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < b.n_reads; r += n_warps) {
+        const int64_t co = b.read_cigar_off[r];
+        const int n_ops = b.read_n_ops[r];
+        int ref_run = 0, ri_run = 0;
+        for (int k0 = 0; k0 < n_ops; k0 += 32) {
+            const int k = k0 + lane;
+            const uint32_t w = k < n_ops ? b.cigar[co + k] : 0u;
+            const int op = (int)(w & 15u), len = (int)(w >> 4);
+            // :357-563 -- what each op adds to ref_position / read_index (REF_SKIP and PAD also advance the read)
+            const int ra = (is_match_op(op) || op == 2 || op == 3 || op == 6) ? len : 0;
+            const int qa = (is_match_op(op) || op == 1 || op == 4 || op == 3 || op == 6) ? len : 0;
+            int sr = ra, sq = qa;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int tr = __shfl_up_sync(0xffffffffu, sr, d), tq = __shfl_up_sync(0xffffffffu, sq, d);
+                if (lane >= d) { sr += tr; sq += tq; }
+            }
+            if (k < n_ops) { op_ref[co + k] = ref_run + sr - ra; op_ri[co + k] = ri_run + sq - qa; }
+            ref_run += __shfl_sync(0xffffffffu, sr, 31);
+            ri_run += __shfl_sync(0xffffffffu, sq, 31);
+        }
+        if (lane == 0) read_span[r] = ref_run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------------------
+struct TileCtx {
+    uint32_t* cnt;        // [NC][P] shared
+    uint8_t* ref_s;       // [P] shared: reference bytes of the tile
+    uint8_t* pflag;       // [P] shared: PF_* of each tile position (phase B onwards)
+    int32_t* site_slot;   // [P] shared (aliases cnt after phase B): site index or -1
+    int32_t* scratch;     // this warp's [4][32] shared scratch
+    int P;
+    int n_valid;          // positions of the tile that exist in the region
+    int region;
+    int64_t t_lo;         // first tile position, relative to region_ref_start
+    int64_t L;            // region length
+    int64_t ref_len;      // reference_sequence.length()
+    int64_t ref_off;      // offset of the region's reference in ref[]
+};
+
+__device__ __forceinline__ void record_event(const SumParams& p, int s, int type, int rev, int elen, int64_t ptr) {
+    SiteRec* sr = &p.sites[s];
+    const int slot = atomicAdd(&sr->fill, 1);
+    if (slot < sr->n_ev) {
+        const int idx = sr->ev_off + slot;
+        if (idx < p.ev_cap) {
+            Event e; e.ptr = ptr; e.info = (uint32_t)type | ((uint32_t)rev << 2) | ((uint32_t)elen << 8); e.pad = 0;
+            p.events[idx] = e;
+        }
+    } else {
+        atomicOr(&p.ctr[CTR_STATUS], ST_INTERNAL);
+    }
+}
+
+// Walks the CIGAR ops of one read that can touch the tile (whole warp).
+//   MODE 0: accumulate counters (populate_summary_matrix, :337-566)
+//   MODE 1: record insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and
+//           :507-535, needed only where the site thresholds passed)
+template <int MODE>
+__device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int lane) {
+    const PvReadBatch& b = p.b;
+    const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];   // read start, region-relative
+    const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;          // tile, inclusive, region-relative
+    const int64_t co = b.read_cigar_off[r];
+    const int n_ops = b.read_n_ops[r];
+    const int read_len = b.read_len[r];
+    const int64_t bo = b.read_base_off[r];
+    const uint32_t rev = b.read_flags[r] & 1u;
+    const uint32_t strand_inc = rev ? 0x10000u : 1u;
+    const int32_t* oref = p.op_ref + co;
+    const int32_t* ori_a = p.op_ri + co;
+    const uint8_t* quals = b.quals + bo;
+    const uint8_t* bases = b.bases + bo;
+
+    // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] with a_k <= min(t_hi + 1, L - 1) (an op that starts
+    // beyond ref_end is never reached, :355) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
+    int k_lo = warp_lower_bound(oref, n_ops, t_lo - rel, lane) - 1;
+    if (k_lo < 0) k_lo = 0;
+    const int64_t a_max = (t_hi + 1 < c.L - 1) ? t_hi + 1 : c.L - 1;
+    const int k_hi = warp_lower_bound(oref, n_ops, a_max - rel + 1, lane);
+
+    int32_t* s_pref = c.scratch;            // [33] exclusive prefix of clipped match lengths (uses [0..32])
+    int32_t* s_ri0 = c.scratch + 40;        // read index of the first clipped base
+    int32_t* s_p0 = c.scratch + 72;         // tile-local position of the first clipped base
+    int32_t* s_last = c.scratch + 104;      // clipped index of the anchor base that skips REF (or < 0)
+
+    for (int kb = k_lo; kb < k_hi; kb += 32) {
+        const int k = kb + lane;
+        const bool have = k < k_hi;
+        const uint32_t w = have ? b.cigar[co + k] : 0u;
+        const int op = have ? (int)(w & 15u) : 15;
+        const int len = (int)(w >> 4);
+        const int64_t a = have ? rel + (int64_t)oref[k] : 0;
+        const int ori = have ? ori_a[k] : 0;
+        int m_cnt = 0, m_ri0 = 0, m_p0 = 0, m_last = -1;
+
+        if (have && a <= c.L - 1) {
+            if (is_match_op(op)) {
+                if (MODE == 0) {
+                    int64_t i_lo = t_lo - a; if (i_lo < 0) i_lo = 0;
+                    int64_t i_hi = t_hi - a; if (i_hi > len - 1) i_hi = len - 1;
+                    if (i_hi > (int64_t)read_len - 1 - ori) i_hi = (int64_t)read_len - 1 - ori;
+                    if (i_hi >= i_lo) {
+                        m_cnt = (int)(i_hi - i_lo + 1);
+                        m_ri0 = ori + (int)i_lo;
+                        m_p0 = (int)(a + i_lo - t_lo);
+                        if (k != n_ops - 1) {                                   // anchor rule, :381-391
+                            const int nop = (int)(b.cigar[co + k + 1] & 15u);
+                            if (nop == 1 || nop == 2) m_last = (int)((int64_t)len - 1 - i_lo);
+                        }
+                    }
+                }
+            } else if (op == 1) {                                               // IN, :431-490
+                const int64_t o = a - 1;
+                if (o >= t_lo && o <= t_hi && ori >= 1 && ori - 1 < read_len) {
+                    const int ol = (int)(o - t_lo);
+                    bool go = true;
+                    int s = -1;
+                    if (MODE == 1) { s = c.site_slot[ol]; go = s >= 0 && (c.pflag[ol] & PF_INS); }
+                    if (go) {
+                        const int64_t n = (int64_t)len + 1;                      // :442
+                        int64_t elen = n;                                        // substr truncation, :439
+                        if ((int64_t)ori - 1 + elen > read_len) elen = (int64_t)read_len - (ori - 1);
+                        int64_t bq = 0;
+                        for (int64_t i = ori - 1; i < ori - 1 + n && i < read_len; i++) bq += quals[i];   // :448-450
+                        const bool pass = (double)bq >= p.t.min_indel_baseq * (double)n;
+                        if (MODE == 0) {
+                            if (pass && (int)quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COVSNP * c.P + ol], 1u);   // :453-454
+                            if (1 + elen <= 61 && pass) {                        // :461-464
+                                if (valid_ref(c.ref_s[ol])) atomicAdd(&c.cnt[(C_BASE + 4) * c.P + ol], strand_inc);
+                                atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
+                            }
+                        } else if (1 + elen <= 61 && pass) {
+                            record_event(p, s, 2, (int)rev, (int)elen, bo + ori - 1);
+                        }
+                    }
+                }
+            } else if (op == 2) {                                               // DEL, :491-555
+                const int64_t o = a - 1;
+                if (o >= t_lo && o <= t_hi) {
+                    const int ol = (int)(o - t_lo);
+                    int64_t elen = (int64_t)len + 1;                             // substr truncation, :500
+                    if (o + elen > c.ref_len) elen = c.ref_len - o;
+                    if (MODE == 0) {
+                        if (valid_ref(c.ref_s[ol])) atomicAdd(&c.cnt[(C_BASE + 5) * c.P + ol], strand_inc);   // :497
+                        if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);                 // :511-512
+                    } else {
+                        const int s = c.site_slot[ol];
+                        if (s >= 0 && (c.pflag[ol] & PF_DEL) && 1 + elen <= 61)
+                            record_event(p, s, 3, (int)rev, (int)elen, c.ref_off + o);
+                    }
+                }
+                if (MODE == 0) {                                                 // :542-552
+                    int64_t i_lo = t_lo - a; if (i_lo < 0) i_lo = 0;
+                    int64_t i_hi = t_hi - a; if (i_hi > len - 1) i_hi = len - 1;
+                    for (int64_t i = i_lo; i <= i_hi; i++) {
+                        const int pl = (int)(a + i - t_lo);
+                        if (valid_ref(c.ref_s[pl])) atomicAdd(&c.cnt[(C_BASE + 6) * c.P + pl], strand_inc);
+                    }
+                }
+            }
+        }
+
+        if (MODE == 0) {
+            // flatten the clipped match bases of these 32 ops across the lanes
+            int incl = m_cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total > 0) {
+                __syncwarp();
+                s_pref[lane] = incl - m_cnt;
+                if (lane == 31) s_pref[32] = total;
+                s_ri0[lane] = m_ri0; s_p0[lane] = m_p0; s_last[lane] = m_last;
+                __syncwarp();
+                for (int j0 = 0; j0 < total; j0 += 128) {
+                    int idx[4], pl[4]; bool skip_ref[4], act[4];
+                    uint8_t bb[4], qq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = j0 + u * 32 + lane;
+                        act[u] = j < total;
+                        int s = 0;
+                        if (act[u]) {
+#pragma unroll
+                            for (int step = 16; step >= 1; step >>= 1)
+                                if (s_pref[s + step] <= j) s += step;
+                            const int i = j - s_pref[s];
+                            idx[u] = s_ri0[s] + i; pl[u] = s_p0[s] + i; skip_ref[u] = (i == s_last[s]);
+                        } else { idx[u] = 0; pl[u] = 0; skip_ref[u] = false; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        bb[u] = act[u] ? __ldg(bases + idx[u]) : (uint8_t)0;
+                        qq[u] = act[u] ? __ldg(quals + idx[u]) : (uint8_t)0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (act[u] && (int)qq[u] >= p.qthr) {                    // :378
+                            const uint8_t rb = c.ref_s[pl[u]];
+                            const bool mism = rb != bb[u];                      // raw compare, :394
+                            atomicAdd(&c.cnt[C_COVSNP * c.P + pl[u]], mism ? 0x10001u : 1u);   // coverage (+ snp_count)
+                            if (!skip_ref[u]) atomicAdd(&c.cnt[C_REF * c.P + pl[u]], strand_inc);
+                            if (valid_ref(rb)) atomicAdd(&c.cnt[(C_BASE + base_class(bb[u])) * c.P + pl[u]], strand_inc);
+                            if (mism) {
+                                const int code = acgt_code(bb[u]);
+                                if (code >= 0) atomicAdd(&c.cnt[(C_SNP + code) * c.P + pl[u]], strand_inc);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// SNP alleles whose byte is not an upper-case A/C/G/T (":398 candidate_string = '1' + alt" keeps the raw byte): rare,
+// recorded after the fact for registered sites only. One thread per read.
+__device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, int64_t r) {
+    const PvReadBatch& b = p.b;
+    if (b.read_mapq[r] == 0) return;
+    const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
+    const int64_t x = c.t_lo + ol - rel;                 // reference offset inside the read
+    if (x < 0 || x >= (int64_t)p.read_span[r]) return;
+    const int64_t co = b.read_cigar_off[r];
+    const int n_ops = b.read_n_ops[r];
+    const int32_t* oref = p.op_ref + co;
+    int lo = 0, hi = n_ops;                              // upper_bound: first k with op_ref[k] > x
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)oref[mid] <= x) lo = mid + 1; else hi = mid; }
+    const int k = lo - 1;
+    if (k < 0) return;
+    const uint32_t w = b.cigar[co + k];
+    if (!is_match_op((int)(w & 15u))) return;
+    const int64_t i = x - oref[k];
+    if (i >= (int64_t)(w >> 4)) return;
+    const int64_t idx = (int64_t)p.op_ri[co + k] + i;
+    if (idx >= b.read_len[r]) return;
+    const int64_t bo = b.read_base_off[r];
+    const uint8_t base = b.bases[bo + idx];
+    if ((int)b.quals[bo + idx] < p.qthr) return;
+    if (base == c.ref_s[ol] || acgt_code(base) >= 0) return;
+    record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
+}
+
+template <int MODE>
+__device__ void for_each_overlapping_read(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next) {
+    const PvReadBatch& b = p.b;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
+    const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;
+    for (int64_t base = rb; base < re; base += LIST_CAP) {
+        if (tid == 0) { *s_n = 0; *s_next = 0; }
+        __syncthreads();
+        const int64_t end = base + LIST_CAP < re ? base + LIST_CAP : re;
+        for (int64_t r = base + tid; r < end; r += blockDim.x) {
+            if (b.read_mapq[r] == 0) continue;                                   // :619
+            const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
+            const int64_t span = p.read_span[r];
+            // touched positions: aligned/deleted [rel, rel+span-1] and insert/delete anchors [rel-1, rel+span-1]
+            if (rel - 1 > t_hi || rel + span - 1 < t_lo) continue;
+            s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
+        }
+        __syncthreads();
+        const int n = *s_n;
+        while (true) {
+            int i = 0;
+            if (lane == 0) i = atomicAdd(s_next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n) break;
+            walk_read<MODE>(p, c, base + s_list[i], lane);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int32_t s_list[LIST_CAP];
+    __shared__ int s_n, s_next, s_any_events, s_any_other;
+
+    const PvReadBatch& b = p.b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = p.P;
+
+    TileCtx c;
+    c.P = P;
+    c.cnt = (uint32_t*)smem;
+    c.site_slot = (int32_t*)smem;                                     // aliases cnt row 0 after phase B
+    c.scratch = (int32_t*)(smem + (size_t)NC * P * 4) + warp * 136;
+    c.ref_s = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4;
+    c.pflag = c.ref_s + P;
+    c.region = p.tile_region[blockIdx.x];
+    c.t_lo = p.tile_start[blockIdx.x];
+    c.L = b.region_ref_end[c.region] - b.region_ref_start[c.region] + 1;
+    c.ref_len = b.region_ref_len[c.region];
+    c.ref_off = b.region_ref_off[c.region];
+    c.n_valid = (int)((c.L - c.t_lo) < P ? (c.L - c.t_lo) : P);
+    const int64_t gbase = p.pos_off[c.region] + c.t_lo;
+
+    for (int i = tid; i < NC * P; i += K1_THREADS) c.cnt[i] = 0;
+    for (int i = tid; i < P; i += K1_THREADS) {
+        c.ref_s[i] = i < c.n_valid ? b.ref[c.ref_off + c.t_lo + i] : (uint8_t)'N';
+        c.pflag[i] = 0;
+    }
+    if (tid == 0) { s_any_events = 0; s_any_other = 0; }
+    __syncthreads();
+
+    // ---- phase A: accumulate -----------------------------------------------------------------------------------
+    for_each_overlapping_read<0>(p, c, s_list, &s_n, &s_next);
+
+    // ---- phase B: image rows, site thresholds ---------------------------------------------------------------------
+    int my_site[MAX_PPT];
+#pragma unroll
+    for (int u = 0; u < MAX_PPT; u++) {
+        my_site[u] = -1;
+        const int i = tid + u * K1_THREADS;
+        if (i < c.n_valid) {
+            uint32_t w[NC];
+#pragma unroll
+            for (int k = 0; k < NC; k++) w[k] = c.cnt[k * P + i];
+            const uint8_t rb = c.ref_s[i];
+            int row[PV_FEATURES];
+#pragma unroll
+            for (int f = 0; f < PV_FEATURES; f++) row[f] = 0;
+            row[0] = ref_value(rb);                                             // :174-191
+            row[4] = -(int)(w[C_REF] & 0xffffu);
+            row[15] = -(int)(w[C_REF] >> 16);
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                row[8 + k] = -(int)(w[C_BASE + k] & 0xffffu);
+                row[19 + k] = -(int)(w[C_BASE + k] >> 16);
+            }
+#pragma unroll
+            for (int f = 11; f < 25; f++) row[f] = row[f] < -125 ? -125 : row[f];   // :648-653 (all values <= 0 here)
+            uint32_t* dst = (uint32_t*)(p.img + (gbase + i) * PV_FEATURES);
+#pragma unroll
+            for (int f = 0; f < PV_FEATURES; f += 2)
+                dst[f >> 1] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
+
+            const int cov = (int)(w[C_COVSNP] & 0xffffu), snp = (int)(w[C_COVSNP] >> 16);
+            const int ins = (int)(w[C_INSDEL] & 0xffffu), del = (int)(w[C_INSDEL] >> 16);
+            const double cv = (double)cov > 1.0 ? (double)cov : 1.0;             // :635-637
+            const double sf = (double)snp / cv, inf = (double)ins / cv, df = (double)del / cv;
+            const bool ps = sf >= p.t.snp_freq, pi = inf >= p.t.insert_freq, pd = df >= p.t.delete_freq;
+            const int64_t pos = b.region_ref_start[c.region] + c.t_lo + i;
+            if ((ps || pi || pd) && pos >= b.region_cand_start[c.region] && pos <= b.region_cand_end[c.region] &&
+                (double)cov >= p.t.min_coverage) {                              // :639-645
+                int flags = PF_SITE | (ps ? PF_SNP : 0) | (pi ? PF_INS : 0) | (pd ? PF_DEL : 0);
+                int dense = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) dense += (int)(w[C_SNP + k] & 0xffffu) + (int)(w[C_SNP + k] >> 16);
+                const int n_other = ps ? snp - dense : 0;
+                if (n_other > 0) flags |= PF_OTHER;
+                const int n_ev = (pi ? ins : 0) + (pd ? del : 0) + n_other;
+                const int s = atomicAdd(&p.ctr[CTR_SITES], 1);
+                if (s < p.site_cap) {
+                    int ev_off = 0;
+                    if (n_ev > 0) {
+                        ev_off = atomicAdd(&p.ctr[CTR_EVENTS], n_ev);
+                        if ((int64_t)ev_off + n_ev > p.ev_cap) atomicOr(&p.ctr[CTR_STATUS], ST_EVENT_OVF);
+                        s_any_events = 1;
+                        if (n_other > 0) s_any_other = 1;
+                    }
+                    SiteRec sr;
+                    sr.gpos = gbase + i; sr.region = c.region; sr.local = (int32_t)(c.t_lo + i); sr.cov = cov;
+                    sr.flags = flags; sr.ev_off = ev_off; sr.n_ev = n_ev; sr.fill = 0; sr.pad = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        sr.snp[2 * k] = (uint16_t)(w[C_SNP + k] & 0xffffu);
+                        sr.snp[2 * k + 1] = (uint16_t)(w[C_SNP + k] >> 16);
+                    }
+                    p.sites[s] = sr;
+                    my_site[u] = s;
+                    c.pflag[i] = (uint8_t)flags;
+                } else {
+                    atomicOr(&p.ctr[CTR_STATUS], ST_SITE_OVF);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_any_events) return;
+
+    // ---- phase C: allele events of the registered sites -----------------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < MAX_PPT; u++) {
+        const int i = tid + u * K1_THREADS;
+        if (i < P) c.site_slot[i] = my_site[u];
+    }
+    __threadfence();      // site records (n_ev, ev_off) are read back through global memory by record_event
+    __syncthreads();
+    for_each_overlapping_read<1>(p, c, s_list, &s_n, &s_next);
+    if (s_any_other) {
+        const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
+        for (int i = 0; i < c.n_valid; i++) {
+            if (!(c.pflag[i] & PF_OTHER)) continue;
+            for (int64_t r = rb + tid; r < re; r += K1_THREADS) record_other_snp(p, c, i, r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t* event_bytes(const SumParams& p, const Event& e) {
+    return ((e.info & 3u) == 3u ? p.b.ref : p.b.bases) + e.ptr;
+}
+
+// std::string order of "<type><bytes>": <0 if x < y, 0 if equal
+__device__ int cmp_event(const SumParams& p, const Event& x, const Event& y) {
+    const int tx = (int)(x.info & 3u), ty = (int)(y.info & 3u);
+    if (tx != ty) return tx < ty ? -1 : 1;
+    const int lx = (int)(x.info >> 8), ly = (int)(y.info >> 8);
+    const uint8_t* sx = event_bytes(p, x);
+    const uint8_t* sy = event_bytes(p, y);
+    const int m = lx < ly ? lx : ly;
+    for (int i = 0; i < m; i++) {
+        const uint8_t a = sx[i], c = sy[i];
+        if (a != c) return a < c ? -1 : 1;
+    }
+    return lx == ly ? 0 : (lx < ly ? -1 : 1);
+}
+
+__device__ void try_emit(const SumParams& p, const SiteRec& sr, int s, int type, bool dense, int elen, int64_t ptr,
+                         int nf, int nr, uint32_t sub) {
+    const int depth = min125(sr.cov);                                           // :682
+    const int ad = nf + nr;
+    if ((double)ad < p.t.candidate_support) return;                             // :693
+    const double cf = (double)ad / ((double)depth > 1.0 ? (double)depth : 1.0); // :689
+    if (type != 1 && cf < p.t.indel_candidate_freq) return;                     // :697
+    if (type == 1 && cf < p.t.snp_candidate_freq) return;                       // :700
+    if (type != 1 && p.t.skip_indels) return;                                   // :704
+    if (!(sr.flags & (1 << type))) return;                                      // :708-712
+    const int slot = atomicAdd(&p.ctr[CTR_CANDS], 1);
+    if (slot >= p.cand_cap) { atomicOr(&p.ctr[CTR_STATUS], ST_CAND_OVF); return; }
+    CandRec cr; cr.ptr = ptr; cr.site = s; cr.info = (uint32_t)type | (dense ? 4u : 0u) | ((uint32_t)elen << 8);
+    cr.nf = nf; cr.nr = nr;
+    p.cands[slot] = cr;
+    p.cand_key[slot] = ((unsigned long long)sr.gpos << 24) | ((unsigned long long)type << 22) | (unsigned long long)sub;
+}
+
+__global__ void site_allele_kernel(const SumParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    int n_sites = p.ctr[CTR_SITES];
+    if (n_sites > p.site_cap) n_sites = p.site_cap;
+    for (int s = warp; s < n_sites; s += n_warps) {
+        const SiteRec sr = p.sites[s];
+        if ((sr.flags & PF_SNP) && lane < 4) {                                  // dense "1A" "1C" "1G" "1T"
+            const int nf = sr.snp[2 * lane], nr = sr.snp[2 * lane + 1];
+            if (nf + nr > 0) {
+                const uint8_t byte = (uint8_t)("ACGT"[lane]);
+                try_emit(p, sr, s, 1, true, 1, (int64_t)byte, nf, nr, (uint32_t)byte);
+            }
+        }
+        const int n = sr.n_ev;
+        if (n <= 0 || (int64_t)sr.ev_off + n > p.ev_cap) continue;
+        if (sr.fill != n && lane == 0) atomicOr(&p.ctr[CTR_STATUS], ST_INTERNAL);
+        const Event* ev = p.events + sr.ev_off;
+        for (int i = lane; i < n; i += 32) {
+            const Event ei = ev[i];
+            int less = 0, nf = 0, nr = 0; bool dup = false;
+            for (int j = 0; j < n; j++) {
+                const Event ej = ev[j];
+                const int cc = (j == i) ? 0 : cmp_event(p, ej, ei);
+                if (cc < 0) less++;
+                else if (cc == 0) { if (j < i) dup = true; if ((ej.info >> 2) & 1u) nr++; else nf++; }
+            }
+            if (dup) continue;
+            const int type = (int)(ei.info & 3u);
+            const uint32_t sub = type == 1 ? (uint32_t)(*event_bytes(p, ei)) : (uint32_t)less;
+            try_emit(p, sr, s, type, false, (int)(ei.info >> 8), ei.ptr, nf, nr, sub);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t* v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+
+__global__ void emit_window_kernel(const SumParams p, const uint32_t* __restrict__ order, PvCandidates out,
+                                   int64_t* n_candidates) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int found = p.ctr[CTR_CANDS];
+    int n = found < p.cand_cap ? found : p.cand_cap;
+    if (n > out.capacity) n = (int)out.capacity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_candidates = found;
+    for (int i = warp; i < n; i += n_warps) {
+        const CandRec cr = p.cands[order[i]];
+        const SiteRec sr = p.sites[cr.site];
+        const int type = (int)(cr.info & 3u), elen = (int)(cr.info >> 8);
+        const bool dense = (cr.info & 4u) != 0;
+        const int64_t L = p.b.region_ref_end[sr.region] - p.b.region_ref_start[sr.region] + 1;
+        const int64_t gbase = p.pos_off[sr.region];
+        const int64_t o = sr.local;
+        const uint8_t rb = p.b.ref[p.b.region_ref_off[sr.region] + o];
+        const bool rv = valid_ref(rb);
+        const uint8_t* src = dense ? nullptr : ((type == 3 ? p.b.ref : p.b.bases) + cr.ptr);
+        const uint8_t a0 = dense ? (uint8_t)cr.ptr : src[0];
+        const int nf = min125(cr.nf), nr = min125(cr.nr);
+        int end_index = 16 + elen - 1; if (end_index > 31) end_index = 31;      // :885
+        const int cls = base_class(a0);
+        int16_t* w = out.windows + (int64_t)i * WIN_ELEMS;
+        for (int e = lane; e < WIN_ELEMS; e += 32) {
+            const int row = e / PV_FEATURES, f = e - row * PV_FEATURES;
+            const int64_t q = o - 16 + row;
+            int v = (q < 0 || q >= L) ? 0 : (int)p.img[(gbase + q) * PV_FEATURES + f];   // :833-841 (row L is all zero)
+            if (row == 16) {
+                if (type == 1) {                                                // :853-860
+                    if (f == 1) v = ref_value(a0); else if (f == 5) v = nf; else if (f == 16) v = nr;
+                    else if (rv && (f == 8 + cls || f == 19 + cls)) v = -v;
+                } else if (type == 2) {                                         // :868-875
+                    if (f == 2) v = min125(elen); else if (f == 6) v = nf; else if (f == 17) v = nr;
+                    else if (rv && (f == 12 || f == 23)) v = -v;
+                } else {                                                        // :883-892
+                    if (f == 3) v = min125(elen); else if (f == 7) v = nf; else if (f == 18) v = nr;
+                    else if (rv && (f == 13 || f == 24)) v = -v;
+                }
+            } else if (type == 3 && row >= 17 && row <= end_index) {            // :896-904
+                if (f == 3) v = min125(elen); else if (f == 7) v = nf; else if (f == 18) v = nr;
+                else if (rv && (f == 14 || f == 25)) v = -v;
+            }
+            w[e] = (int16_t)v;
+        }
+        for (int e = lane; e < PV_ALLELE_BYTES; e += 32) {
+            uint8_t ch = 0;
+            if (e == 0) ch = (uint8_t)('0' + type);
+            else if (e - 1 < elen) ch = dense ? a0 : src[e - 1];
+            out.allele[(int64_t)i * PV_ALLELE_BYTES + e] = ch;
+        }
+        if (lane == 0) {
+            out.position[i] = p.b.region_ref_start[sr.region] + o;
+            out.region[i] = sr.region;
+            out.depth[i] = min125(sr.cov);
+            out.frequency[i] = min125(cr.nf + cr.nr);
+            out.allele_len[i] = (uint8_t)(1 + elen);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct Plan {
+    int P; int64_t n_tiles;
+    int64_t site_cap, ev_cap, cand_cap;
+    size_t sort_tmp;
+};
+
+int choose_tile(int64_t total_positions, int32_t n_regions) {
+    // large tiles amortise the per-(tile, read) set-up; small batches need enough CTAs to cover the 148 SMs
+    const int sms = 148;
+    int P = 2048;
+    while (P > 512 && (total_positions / P + n_regions) < 2 * sms) P >>= 1;
+    return P;
+}
+
+size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4 + 2 * (size_t)P + 16; }
+
+Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
+    Plan pl;
+    pl.P = choose_tile(total_positions, n_regions);
+    pl.n_tiles = total_positions / pl.P + n_regions + 1;     // upper bound
+    pl.cand_cap = capacity < 1 ? 1 : capacity;
+    pl.site_cap = 4 * pl.cand_cap + 4096;
+    if (pl.site_cap > total_positions) pl.site_cap = total_positions > 0 ? total_positions : 1;
+    pl.ev_cap = n_ops + (1 << 20);
+    if (pl.ev_cap > 0x7fffff00ll) pl.ev_cap = 0x7fffff00ll;
+    if (pl.cand_cap > 0x7fffff00ll) pl.cand_cap = 0x7fffff00ll;
+    if (pl.site_cap > 0x7fffff00ll) pl.site_cap = 0x7fffff00ll;
+    pl.sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, pl.sort_tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)pl.cand_cap, 0, 64, (cudaStream_t)0);
+    return pl;
+}
+
+struct WsLayout {
+    int64_t* pos_off; int32_t* tile_region; int32_t* tile_start;
+    int32_t* op_ref; int32_t* op_ri; int32_t* read_span;
+    int16_t* img; SiteRec* sites; Event* events; CandRec* cands;
+    unsigned long long* key_in; unsigned long long* key_out; uint32_t* val_in; uint32_t* val_out;
+    void* sort_tmp; int32_t* ctr;
+    int64_t bytes;
+};
+
+WsLayout carve(void* base, int64_t size, const Plan& pl, int64_t n_reads, int64_t n_ops, int32_t n_regions,
+               int64_t total_positions, bool need_img) {
+    pv::Arena a(base, size);
+    WsLayout w;
+    w.ctr = a.take<int32_t>(CTR_COUNT);
+    w.pos_off = a.take<int64_t>(n_regions + 1);
+    w.tile_region = a.take<int32_t>(pl.n_tiles);
+    w.tile_start = a.take<int32_t>(pl.n_tiles);
+    w.op_ref = a.take<int32_t>(n_ops);
+    w.op_ri = a.take<int32_t>(n_ops);
+    w.read_span = a.take<int32_t>(n_reads);
+    w.img = need_img ? a.take<int16_t>(total_positions * PV_FEATURES) : nullptr;
+    w.sites = a.take<SiteRec>(pl.site_cap);
+    w.events = a.take<Event>(pl.ev_cap);
+    w.cands = a.take<CandRec>(pl.cand_cap);
+    w.key_in = a.take<unsigned long long>(pl.cand_cap);
+    w.key_out = a.take<unsigned long long>(pl.cand_cap);
+    w.val_in = a.take<uint32_t>(pl.cand_cap);
+    w.val_out = a.take<uint32_t>(pl.cand_cap);
+    w.sort_tmp = a.take<uint8_t>((int64_t)pl.sort_tmp);
+    w.bytes = pv::align_up(a.cur, 256);
+    return w;
+}
+
+}  // namespace
+
+extern "C" int64_t pv_summary_workspace_bytes(int64_t n_reads, int64_t n_ops, int32_t n_regions,
+                                              int64_t total_positions, int64_t capacity) {
+    const Plan pl = make_plan(n_ops, n_regions, total_positions, capacity);
+    return carve(nullptr, 0, pl, n_reads, n_ops, n_regions, total_positions, true).bytes;
+}
+
+extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* region_len_host, int64_t total_positions,
+                                  const PvThresholds* thr, int32_t window, int32_t features,
+                                  const PvCandidates* out, int64_t* n_candidates_dev, void* workspace_dev,
+                                  int64_t workspace_bytes, int16_t* dense_image_dev, void* stream_) {
+    if (!batch || !thr || !out || !n_candidates_dev || !region_len_host) return pv::set_error(PV_EINVAL, "null argument");
+    if (window != PV_WINDOW - 1 || features != PV_FEATURES)
+        return pv::set_error(PV_EINVAL, "only candidate_window_size=32, feature_size=26 are built (got %d, %d)", window, features);
+    if (!(thr->min_snp_baseq == thr->min_snp_baseq) || !(thr->min_indel_baseq == thr->min_indel_baseq))
+        return pv::set_error(PV_EINVAL, "NaN base-quality threshold");
+    if (int rc = pv::require_device()) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const PvReadBatch& b = *batch;
+    if (b.n_regions <= 0) {
+        PV_CUDA_CHECK(cudaMemsetAsync(n_candidates_dev, 0, sizeof(int64_t), stream));
+        return PV_OK;
+    }
+    const Plan pl = make_plan(b.n_ops, b.n_regions, total_positions, out->capacity);
+    const WsLayout w = carve(workspace_dev, workspace_bytes, pl, b.n_reads, b.n_ops, b.n_regions, total_positions,
+                             dense_image_dev == nullptr);
+    if (w.bytes > workspace_bytes)
+        return pv::set_error(PV_EINVAL, "workspace too small: need %lld bytes, got %lld", (long long)w.bytes, (long long)workspace_bytes);
+
+    // host-side planning: dense position offsets and the tile table
+    std::vector<int64_t> pos_off(b.n_regions + 1, 0);
+    std::vector<int32_t> t_region, t_start;
+    for (int32_t r = 0; r < b.n_regions; r++) {
+        const int64_t L = region_len_host[r];
+        if (L <= 0 || L > 0x7fffffffll) return pv::set_error(PV_EINVAL, "region %d has length %lld", r, (long long)L);
+        pos_off[r + 1] = pos_off[r] + L;
+        for (int64_t s = 0; s < L; s += pl.P) { t_region.push_back(r); t_start.push_back((int32_t)s); }
+    }
+    if (pos_off[b.n_regions] != total_positions) return pv::set_error(PV_EINVAL, "total_positions does not match region lengths");
+    if (total_positions >= (1ll << 40)) return pv::set_error(PV_EINVAL, "too many positions in one batch");
+    const int64_t n_tiles = (int64_t)t_region.size();
+    if (n_tiles > pl.n_tiles) return pv::set_error(PV_EINVAL, "internal: tile bound");
+    PV_CUDA_CHECK(cudaMemcpyAsync(w.pos_off, pos_off.data(), pos_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    PV_CUDA_CHECK(cudaMemcpyAsync(w.tile_region, t_region.data(), n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    PV_CUDA_CHECK(cudaMemcpyAsync(w.tile_start, t_start.data(), n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    PV_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_COUNT * sizeof(int32_t), stream));
+    PV_CUDA_CHECK(cudaMemsetAsync(w.key_in, 0xff, pl.cand_cap * sizeof(unsigned long long), stream));
+
+    SumParams p;
+    p.b = b; p.pos_off = w.pos_off; p.tile_region = w.tile_region; p.tile_start = w.tile_start; p.P = pl.P;
+    p.op_ref = w.op_ref; p.op_ri = w.op_ri; p.read_span = w.read_span;
+    p.img = dense_image_dev ? dense_image_dev : w.img;
+    p.sites = w.sites; p.site_cap = (int32_t)pl.site_cap; p.events = w.events; p.ev_cap = (int32_t)pl.ev_cap;
+    p.cands = w.cands; p.cand_key = w.key_in; p.cand_cap = (int32_t)pl.cand_cap; p.ctr = w.ctr;
+    double q = thr->min_snp_baseq; int qi = 0;
+    if (q > 256.0) qi = 256; else if (q > 0.0) { qi = (int)q; if ((double)qi < q) qi++; }
+    p.qthr = qi;
+    p.t = *thr;
+
+    const int sms = pv::sm_count();
+    if (b.n_reads > 0) {
+        int64_t blocks = (b.n_reads + 7) / 8;            // 8 warps per 256-thread block
+        if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+        cigar_prefix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b, w.op_ref, w.op_ri, w.read_span);
+        PV_CUDA_CHECK(cudaGetLastError());
+    }
+    const size_t smem = k1_smem_bytes(pl.P);
+    PV_CUDA_CHECK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pileup_tile_kernel<<<(unsigned)n_tiles, K1_THREADS, smem, stream>>>(p);
+    PV_CUDA_CHECK(cudaGetLastError());
+
+    site_allele_kernel<<<sms * 8, 256, 0, stream>>>(p);
+    PV_CUDA_CHECK(cudaGetLastError());
+
+    iota_kernel<<<(unsigned)((pl.cand_cap + 255) / 256), 256, 0, stream>>>(w.val_in, (int)pl.cand_cap);
+    PV_CUDA_CHECK(cudaGetLastError());
+    size_t tmp = pl.sort_tmp;
+    PV_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.sort_tmp, tmp, (const unsigned long long*)w.key_in, w.key_out,
+                                                  (const uint32_t*)w.val_in, w.val_out, (int)pl.cand_cap, 0, 64, stream));
+    int64_t eblocks = (pl.cand_cap + 7) / 8;
+    if (eblocks > (int64_t)sms * 16) eblocks = (int64_t)sms * 16;
+    emit_window_kernel<<<(unsigned)eblocks, 256, 0, stream>>>(p, w.val_out, *out, n_candidates_dev);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+// status word of the last pv_summary_regions on this workspace (device int32 at the start of the workspace)
+extern "C" int pv_summary_status_offset(void) { return CTR_STATUS * (int)sizeof(int32_t); }

@@ -1,0 +1,108 @@
+"""GPU parity: the CUDA summary path (through the C-ABI, host-buffer entry point) against the CPU oracles."""
+import numpy as np
+import pytest
+
+import helpers as H
+import pyoracle as O
+from pepper_thesis_b200 import capi, synth
+from pepper_thesis_b200.read_batch import select_regions
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle(b, r, thr):
+    return O.ref_summary(b, r, thr) if O.have_ref() else O.port_summary(b, r, thr)
+
+
+def gpu_region_dict(out, r):
+    d = out.trimmed()
+    m = d["region"] == r
+    idx = np.nonzero(m)[0]
+    return dict(position=d["position"][m], depth=d["depth"][m], frequency=d["frequency"][m], images=d["images"][m],
+                alleles=[d["alleles"][i] for i in idx])
+
+
+@pytest.mark.parametrize("name", sorted(H.KATS))
+def test_kat(name):
+    b = H.KATS[name]()
+    out, dense = capi.summary_regions_host(b, H.R9, want_dense=True)
+    p = O.port_summary(b, 0, H.R9, want_dense=True)
+    assert np.array_equal(dense.astype(np.int32), p["dense"]), "dense image"
+    H.assert_same(oracle(b, 0, H.R9), gpu_region_dict(out, 0), name)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_fuzz(seed):
+    b = H.fuzz_region(seed)
+    thr = H.fuzz_thresholds(seed)
+    out, dense = capi.summary_regions_host(b, thr, want_dense=True)
+    p = O.port_summary(b, 0, thr, want_dense=True)
+    bad = np.argwhere(dense.astype(np.int32) != p["dense"])
+    assert bad.size == 0, "dense image differs first at %s" % bad[0].tolist()
+    H.assert_same(oracle(b, 0, thr), gpu_region_dict(out, 0), "fuzz %d" % seed)
+
+
+@pytest.mark.parametrize("seed", range(60, 70))
+def test_fuzz_reference_n(seed):
+    """Non-ACGT reference bases: the reference C++ is undefined there (vector[-1]); compare with the port."""
+    b = H.fuzz_region(seed, ref_n=True)
+    thr = H.fuzz_thresholds(seed)
+    out = capi.summary_regions_host(b, thr)
+    H.assert_same(O.port_summary(b, 0, thr), gpu_region_dict(out, 0), "fuzz-N %d" % seed)
+
+
+@pytest.mark.parametrize("profile,cov", [("ont_r9", 30.0), ("ont_r9", 50.0), ("ont_r10", 40.0), ("hifi", 35.0)])
+def test_synthetic_regions(profile, cov):
+    """Several 100 kbp regions in one batch (incl. the first and last region of the contig)."""
+    b = synth.generate(profile, 450000, cov, seed=5)
+    thr = synth.PROFILES[profile].thresholds
+    out, dense = capi.summary_regions_host(b, thr, want_dense=True)
+    off = 0
+    for r in range(b.n_regions):
+        sub = select_regions(b, [r])
+        p = O.port_summary(sub, 0, thr, want_dense=True)
+        L = p["dense"].shape[0]
+        assert np.array_equal(dense[off:off + L].astype(np.int32), p["dense"]), "dense region %d" % r
+        off += L
+        H.assert_same(oracle(sub, 0, thr), gpu_region_dict(out, r), "%s region %d" % (profile, r))
+    assert out.count > 100
+
+
+def test_many_fuzz_regions_one_batch():
+    from pepper_thesis_b200.read_batch import ReadBatch
+    bs = [H.fuzz_region(s, L=300 + 37 * (s % 5)) for s in range(100, 140)]
+    import numpy as np
+    from pepper_thesis_b200 import read_batch as rb
+    # concatenate single-region batches
+    parts = {n: [] for n in rb.ARRAY_NAMES}
+    b_cur = o_cur = f_cur = r_cur = 0
+    rbeg = [0]
+    for b in bs:
+        for n in ("read_pos", "read_len", "read_n_ops", "read_flags", "read_mapq", "bases", "quals", "cigar", "ref",
+                  "region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end", "region_ref_len"):
+            parts[n].append(getattr(b, n))
+        parts["read_base_off"].append(b.read_base_off + b_cur)
+        parts["read_cigar_off"].append(b.read_cigar_off + o_cur)
+        parts["region_ref_off"].append(b.region_ref_off + f_cur)
+        b_cur += b.n_bases; o_cur += b.n_ops; f_cur += b.ref.shape[0]; r_cur += b.n_reads
+        rbeg.append(r_cur)
+    arrs = {n: np.ascontiguousarray(np.concatenate(parts[n])) for n in rb.ARRAY_NAMES if n != "region_read_begin"}
+    big = ReadBatch(region_read_begin=np.asarray(rbeg, np.int64), contigs=["fz"] * len(bs), **arrs)
+    out = capi.summary_regions_host(big, H.R9)
+    for r, b in enumerate(bs):
+        H.assert_same(oracle(b, 0, H.R9), gpu_region_dict(out, r), "batch region %d" % r)
+
+
+def test_candidate_overflow_is_reported():
+    b = H.kat_refskip()
+    with pytest.raises(capi.PvError) as e:
+        capi.summary_regions_host(b, H.R9, capacity=3)
+    assert e.value.code == capi.PV_EOVERFLOW
+
+
+def test_empty_region_and_mapq0():
+    b = H.one_region("ACGT" * 25, [H.Read(0, "ACGT" * 25, [(0, 100)], mapq=0)])
+    out = capi.summary_regions_host(b, H.R9)
+    assert out.count == 0
+    b = H.one_region("ACGT" * 25, [])
+    assert capi.summary_regions_host(b, H.R9).count == 0
