@@ -1,0 +1,88 @@
+// Helpers shared by the two recurrent models (tensor maps, bf16 packing, activations, GEMM launch).
+#pragma once
+#include "common.cuh"
+#include "tc_gemm.cuh"
+#include <vector>
+
+namespace {
+
+constexpr int MAX_CHUNK = 8192;     // windows per pass
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// bf16 tensor [rows][slots][chan] (chan contiguous), box = 64 chan x 1 slot x 128 rows, 128-byte swizzle
+int make_map3(CUtensorMap* m, const void* base, int64_t rows, int64_t slots, int64_t chan, int64_t row_stride_elems) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return pv::set_error(PV_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dim[3] = {(cuuint64_t)chan, (cuuint64_t)slots, (cuuint64_t)rows};
+    cuuint64_t stride[2] = {(cuuint64_t)chan * 2, (cuuint64_t)row_stride_elems * 2};
+    cuuint32_t box[3] = {(cuuint32_t)tc::BLOCK_K, 1, (cuuint32_t)tc::BLOCK_M};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pv::set_error(PV_ECUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+    return PV_OK;
+}
+// bf16 weight matrix [rows][k] (k contiguous), box = 64 k x 256 rows
+int make_map2(CUtensorMap* m, const void* base, int64_t rows, int64_t k) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return pv::set_error(PV_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t stride[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)tc::BLOCK_N};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pv::set_error(PV_ECUDA, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+    return PV_OK;
+}
+
+uint16_t f2bf(float f) {                 // round-to-nearest-even float -> bf16 bits
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+
+template <class Epi>
+int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const tc::GemmShape& g, const Epi& epi,
+                int sms, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        PV_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles = g.m_blks * g.n_blks * g.dirs;
+    const int grid = tiles < sms ? tiles : sms;
+    tc::gemm_kernel<Epi><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a0, a1, w, g, epi);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+template <typename Tv>
+int upload(Tv** dst, const void* src, size_t bytes) {
+    PV_CUDA_CHECK(cudaMalloc((void**)dst, bytes));
+    PV_CUDA_CHECK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return PV_OK;
+}
+
+
+}  // namespace

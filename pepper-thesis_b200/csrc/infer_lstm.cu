@@ -1,0 +1,368 @@
+// Model M-A on sm_100a: pepper_variant TransducerGRU.forward
+// (/root/reference/pepper_variant/modules/python/models/simple_model.py:48-82): biLSTM(26->256) -> biLSTM(512->256)
+// -> flatten(33*512) -> 5 x (Linear + SELU) -> Linear(512->3) -> softmax, batch_first, h0 = c0 = 0, eval mode.
+//
+// Every dense product runs on the tcgen05/TMA GEMM core (tc_gemm.cuh):
+//   * one launch per time step advances BOTH directions of a layer: A = [h_{t-1} | x_t] (two tensor maps),
+//     W = [W_hh | W_ih] re-ordered so a 256-column tile holds i,f,g,o of 64 hidden units; the LSTM cell
+//     (sigmoid/tanh, c update, h = o*tanh(c)) is the GEMM epilogue, h_t is written as bf16 straight into the
+//     layer output [B][T+2][512] where the next step (and the next layer) TMA-loads it from;
+//   * the encoder input (raw int16 counts) is split exactly into bf16 hi + lo parts (|x| < 2^16 exact) and W_ih into
+//     a bf16 high part + bf16 remainder, so the input projection keeps ~16 mantissa bits even on unnormalised,
+//     deep-coverage counts;
+//   * the MLP runs the same kernel with a bias+SELU epilogue; the 512->3 head, softmax and argmax are one small kernel.
+#include "common.cuh"
+#include "tc_gemm.cuh"
+#include "infer_common.cuh"
+#include <cmath>
+#include <vector>
+
+namespace {
+
+constexpr int T = PV_WINDOW;        // 33 time steps
+constexpr int F = PV_FEATURES;      // 26 input features
+constexpr int H = 256;              // hidden size of both LSTMs
+constexpr int C = 2 * H;            // channels of a layer output
+constexpr int S = T + 2;            // slots per window in a layer output (slot t+1 = time t; 0 and T+1 unused here)
+constexpr int XK = 128;             // encoder input, two k blocks: [x_hi(26) x_lo(26) 0(12)] [x_hi(26) 0(38)]
+constexpr int ENC_K = H + XK;       // 384
+constexpr int DEC_K = H + C;        // 768
+constexpr int LIN = 512;
+constexpr int FLAT = T * C;         // 16896
+
+// ---- epilogues ---------------------------------------------------------------------------------------------
+struct LstmEpilogue {
+    const float* bias;        // [dirs][n_blks][4 gates][64]  (b_ih + b_hh, tile order)
+    float* c_state;           // [M][2][H] fp32
+    __nv_bfloat16* out;       // [M][S][C]
+    int n_blks;
+    int out_slot[2];
+    int first;                // c_{t-1} == 0
+
+    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr) const {
+        const float* b = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ch++) {
+            float ai[16], af[16], ag[16], ao[16];
+            tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ai);
+            tc::tmem_ld16(taddr + 1 * 64 + ch * 16, af);
+            tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ag);
+            tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ao);
+            tc::tmem_ld_wait();
+            if (ok) {
+                float* cp = c_state + ((size_t)row * 2 + dir) * H + n_blk * 64 + ch * 16;
+                float c[16];
+                if (first) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) c[i] = 0.f;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(cp + i); c[i] = v.x; c[i + 1] = v.y; c[i + 2] = v.z; c[i + 3] = v.w; }
+                }
+                __align__(16) __nv_bfloat16 hb[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int j = ch * 16 + i;
+                    const float ig = sigmoid_f(ai[i] + __ldg(b + 0 * 64 + j));
+                    const float fg = sigmoid_f(af[i] + __ldg(b + 1 * 64 + j));
+                    const float gg = tanh_f(ag[i] + __ldg(b + 2 * 64 + j));
+                    const float og = sigmoid_f(ao[i] + __ldg(b + 3 * 64 + j));
+                    c[i] = fg * c[i] + ig * gg;
+                    hb[i] = __float2bfloat16_rn(og * tanh_f(c[i]));
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *(float4*)(cp + i) = make_float4(c[i], c[i + 1], c[i + 2], c[i + 3]);
+                __nv_bfloat16* op = out + ((size_t)row * S + out_slot[dir]) * C + dir * H + n_blk * 64 + ch * 16;
+                *(uint4*)op = *(const uint4*)hb;
+                *(uint4*)(op + 8) = *(const uint4*)(hb + 8);
+            }
+        }
+    }
+};
+
+struct SeluEpilogue {
+    const float* bias;        // [N]
+    __nv_bfloat16* out;       // [M][ldo]
+    int ldo;
+
+    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr) const {
+        (void)dir;
+        const float alpha = 1.6732632423543772f, lambda = 1.0507009873554805f;
+#pragma unroll 1
+        for (int ch = 0; ch < 16; ch++) {
+            float a[16];
+            tc::tmem_ld16(taddr + ch * 16, a);
+            tc::tmem_ld_wait();
+            if (ok) {
+                const int col = n_blk * tc::BLOCK_N + ch * 16;
+                __align__(16) __nv_bfloat16 hb[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float x = a[i] + __ldg(bias + col + i);
+                    hb[i] = __float2bfloat16_rn(lambda * (x > 0.f ? x : alpha * (__expf(x) - 1.f)));
+                }
+                __nv_bfloat16* op = out + (size_t)row * ldo + col;
+                *(uint4*)op = *(const uint4*)hb;
+                *(uint4*)(op + 8) = *(const uint4*)(hb + 8);
+            }
+        }
+    }
+};
+
+// ---- small kernels -----------------------------------------------------------------------------------------
+// windows int16 [n][33][26] -> xhl bf16 [n][33][128]: cols 0..25 = x_hi, 26..51 = x_lo (x == x_hi + x_lo exactly; both
+// meet bf16(W_ih)), cols 64..89 = x_hi again (meets the bf16 remainder of W_ih), rest 0
+__global__ void prep_input_kernel(const int16_t* __restrict__ win, __nv_bfloat16* __restrict__ xhl, int64_t n, int wrap_int8) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over n*33*64
+    if (i >= n * T * XK) return;
+    const int col = (int)(i % XK);
+    const int64_t rt = i / XK;
+    float v = 0.f;
+    const int f = col < 2 * F ? (col < F ? col : col - F) : (col >= 64 && col < 64 + F ? col - 64 : -1);
+    if (f >= 0) {
+        int x = win[rt * F + f];
+        if (wrap_int8) x = (int)(int8_t)x;                                  // DataStore.py:68 int8 round trip
+        const float xf = (float)x;
+        const float hi = __bfloat162float(__float2bfloat16_rn(xf));
+        v = (col >= F && col < 2 * F) ? xf - hi : hi;
+    }
+    xhl[i] = __float2bfloat16_rn(v);
+}
+
+// output_layer_type (512 -> 3) + softmax + argmax; one warp per window
+__global__ void head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                            float* __restrict__ probs, uint8_t* __restrict__ argmax, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < LIN; k += 32) {
+        const float v = __bfloat162float(x[row * LIN + k]);
+        s0 += v * w[k]; s1 += v * w[LIN + k]; s2 += v * w[2 * LIN + k];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) {
+        s0 += b[0]; s1 += b[1]; s2 += b[2];
+        const float m = fmaxf(s0, fmaxf(s1, s2));
+        const float e0 = expf(s0 - m), e1 = expf(s1 - m), e2 = expf(s2 - m);
+        const float inv = 1.f / (e0 + e1 + e2);
+        probs[row * 3 + 0] = e0 * inv; probs[row * 3 + 1] = e1 * inv; probs[row * 3 + 2] = e2 * inv;
+        if (argmax) argmax[row] = (uint8_t)(s1 > s0 ? (s2 > s1 ? 2 : 1) : (s2 > s0 ? 2 : 0));   // first maximum wins (torch.argmax)
+    }
+}
+
+}  // namespace
+
+struct PvLstmModel {
+    __nv_bfloat16 *enc_w, *dec_w, *lin_w[5];
+    float *enc_b, *dec_b, *lin_b[5], *out_w, *out_b;
+    CUtensorMap map_enc_w, map_dec_w, map_lin_w[5];
+    int device;
+    int sms;
+    // host-wrapper buffers
+    void* ws; int64_t ws_bytes;
+    int16_t* win_dev; float* probs_dev; uint8_t* arg_dev; int64_t io_cap;
+    cudaStream_t stream;
+};
+
+namespace {
+
+struct Ws {
+    __nv_bfloat16 *xhl, *enc_out, *dec_out, *act0, *act1;
+    float* c_state;
+    int64_t bytes;
+};
+
+Ws carve_ws(void* base, int64_t size, int64_t chunk) {
+    pv::Arena a(base, size);
+    Ws w;
+    w.xhl = a.take<__nv_bfloat16>(chunk * T * XK);
+    w.enc_out = a.take<__nv_bfloat16>(chunk * S * C);
+    w.dec_out = a.take<__nv_bfloat16>(chunk * S * C);
+    w.act0 = a.take<__nv_bfloat16>(chunk * LIN);
+    w.act1 = a.take<__nv_bfloat16>(chunk * LIN);
+    w.c_state = a.take<float>(chunk * 2 * H);
+    w.bytes = pv::align_up(a.cur, 256);
+    return w;
+}
+
+int64_t chunk_for(int64_t n) {
+    int64_t c = (n + 127) / 128 * 128;
+    if (c < 128) c = 128;
+    return c < MAX_CHUNK ? c : MAX_CHUNK;
+}
+
+// pack one LSTM layer: rows in tile order (dir, n_blk, gate, j) <- PyTorch row gate*256 + n_blk*64 + j
+void pack_lstm(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2], const float* const b_hh[2],
+               int in_dim, int k_total, bool hi_lo, std::vector<uint16_t>& w, std::vector<float>& b) {
+    w.assign((size_t)2 * 4 * H * k_total, 0);
+    b.assign((size_t)2 * 4 * H, 0.f);
+    for (int dir = 0; dir < 2; dir++)
+        for (int nb = 0; nb < 4; nb++)
+            for (int gate = 0; gate < 4; gate++)
+                for (int j = 0; j < 64; j++) {
+                    const int src = gate * H + nb * 64 + j;
+                    const size_t dst = ((size_t)(dir * 4 + nb) * 4 + gate) * 64 + j;
+                    uint16_t* wr = &w[dst * k_total];
+                    for (int k = 0; k < H; k++) wr[k] = f2bf(w_hh[dir][(size_t)src * H + k]);
+                    for (int k = 0; k < in_dim; k++) {
+                        const float wv = w_ih[dir][(size_t)src * in_dim + k];
+                        const uint16_t v = f2bf(wv);
+                        wr[H + k] = v;
+                        if (hi_lo) { wr[H + in_dim + k] = v; wr[H + 64 + k] = f2bf(wv - bf2f(v)); }
+                    }
+                    b[dst] = b_ih[dir][src] + b_hh[dir][src];
+                }
+}
+
+}  // namespace
+
+extern "C" int pv_lstm_create(const PvLstmWeights* hw, PvLstmModel** out) {
+    if (!hw || !out) return pv::set_error(PV_EINVAL, "null argument");
+    if (int rc = pv::require_device()) return rc;
+    PvLstmModel* m = new PvLstmModel();
+    memset(m, 0, sizeof(*m));
+    cudaGetDevice(&m->device);
+    m->sms = pv::sm_count();
+    std::vector<uint16_t> w; std::vector<float> b;
+    pack_lstm(hw->enc_w_ih, hw->enc_w_hh, hw->enc_b_ih, hw->enc_b_hh, F, ENC_K, true, w, b);
+    if (int rc = upload(&m->enc_w, w.data(), w.size() * 2)) return rc;
+    if (int rc = upload(&m->enc_b, b.data(), b.size() * 4)) return rc;
+    pack_lstm(hw->dec_w_ih, hw->dec_w_hh, hw->dec_b_ih, hw->dec_b_hh, C, DEC_K, false, w, b);
+    if (int rc = upload(&m->dec_w, w.data(), w.size() * 2)) return rc;
+    if (int rc = upload(&m->dec_b, b.data(), b.size() * 4)) return rc;
+    for (int l = 0; l < 5; l++) {
+        const int k = l == 0 ? FLAT : LIN;
+        w.resize((size_t)LIN * k);
+        for (size_t i = 0; i < w.size(); i++) w[i] = f2bf(hw->lin_w[l][i]);
+        if (int rc = upload(&m->lin_w[l], w.data(), w.size() * 2)) return rc;
+        if (int rc = upload(&m->lin_b[l], hw->lin_b[l], LIN * 4)) return rc;
+        if (int rc = make_map2(&m->map_lin_w[l], m->lin_w[l], LIN, k)) return rc;
+    }
+    if (int rc = upload(&m->out_w, hw->out_w, 3 * LIN * 4)) return rc;
+    if (int rc = upload(&m->out_b, hw->out_b, 3 * 4)) return rc;
+    if (int rc = make_map2(&m->map_enc_w, m->enc_w, 2 * 4 * H, ENC_K)) return rc;
+    if (int rc = make_map2(&m->map_dec_w, m->dec_w, 2 * 4 * H, DEC_K)) return rc;
+    *out = m;
+    return PV_OK;
+}
+
+extern "C" void pv_lstm_destroy(PvLstmModel* m) {
+    if (!m) return;
+    cudaFree(m->enc_w); cudaFree(m->dec_w); cudaFree(m->enc_b); cudaFree(m->dec_b);
+    for (int l = 0; l < 5; l++) { cudaFree(m->lin_w[l]); cudaFree(m->lin_b[l]); }
+    cudaFree(m->out_w); cudaFree(m->out_b);
+    if (m->ws) cudaFree(m->ws);
+    if (m->win_dev) cudaFree(m->win_dev);
+    if (m->probs_dev) cudaFree(m->probs_dev);
+    if (m->arg_dev) cudaFree(m->arg_dev);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int64_t pv_lstm_workspace_bytes(int64_t max_windows) {
+    return carve_ws(nullptr, 0, chunk_for(max_windows)).bytes;
+}
+
+extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, int32_t wrap_int8, float* probs,
+                             uint8_t* argmax, void* workspace, int64_t workspace_bytes, void* stream_) {
+    if (!m || !windows || !probs || !workspace) return pv::set_error(PV_EINVAL, "null argument");
+    if (n <= 0) return PV_OK;
+    cudaStream_t st = (cudaStream_t)stream_;
+    // the largest chunk the workspace can hold
+    int64_t chunk = chunk_for(n);
+    while (chunk > 128 && carve_ws(nullptr, 0, chunk).bytes > workspace_bytes) chunk -= 128;
+    const Ws w = carve_ws(workspace, workspace_bytes, chunk);
+    if (w.bytes > workspace_bytes) return pv::set_error(PV_EINVAL, "workspace too small: need at least %lld bytes", (long long)w.bytes);
+
+    CUtensorMap map_x, map_enc, map_dec, map_flat, map_act0, map_act1;
+    if (int rc = make_map3(&map_x, w.xhl, chunk, T, XK, (int64_t)T * XK)) return rc;
+    if (int rc = make_map3(&map_enc, w.enc_out, chunk, S, C, (int64_t)S * C)) return rc;
+    if (int rc = make_map3(&map_dec, w.dec_out, chunk, S, C, (int64_t)S * C)) return rc;
+    // linear_1 reads the decoder output of a window as one row of 33*512 channels starting at slot 1
+    if (int rc = make_map3(&map_flat, w.dec_out + C, chunk, 1, FLAT, (int64_t)S * C)) return rc;
+    if (int rc = make_map3(&map_act0, w.act0, chunk, 1, LIN, LIN)) return rc;
+    if (int rc = make_map3(&map_act1, w.act1, chunk, 1, LIN, LIN)) return rc;
+
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t nb = n - off < chunk ? n - off : chunk;
+        const int64_t elems = nb * T * XK;
+        prep_input_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(windows + off * T * F, w.xhl, nb, wrap_int8);
+        PV_CUDA_CHECK(cudaGetLastError());
+
+        tc::GemmShape g;
+        memset(&g, 0, sizeof(g));
+        g.M = (int)nb; g.m_blks = (int)((nb + 127) / 128); g.n_blks = 4; g.dirs = 2;
+        g.w_row[0] = 0; g.w_row[1] = 4 * H;
+        g.a0_col[0] = 0; g.a0_col[1] = H;
+        for (int layer = 0; layer < 2; layer++) {
+            LstmEpilogue e;
+            e.bias = layer == 0 ? m->enc_b : m->dec_b;
+            e.c_state = w.c_state;
+            e.out = layer == 0 ? w.enc_out : w.dec_out;
+            e.n_blks = 4;
+            g.kb1 = layer == 0 ? XK / tc::BLOCK_K : C / tc::BLOCK_K;
+            for (int s = 0; s < T; s++) {
+                const int tf = s, tb = T - 1 - s;               // time handled by the forward / reverse direction
+                e.first = s == 0;
+                e.out_slot[0] = tf + 1; e.out_slot[1] = tb + 1;
+                g.kb0 = s == 0 ? 0 : H / tc::BLOCK_K;           // h_{-1} == 0: skip the recurrent k blocks
+                g.w_kb_off = s == 0 ? H / tc::BLOCK_K : 0;
+                g.a0_slot[0] = tf; g.a0_slot[1] = tb + 2;       // slot of h_{t-1} (forward) / h_{t+1} (reverse)
+                if (layer == 0) { g.a1_slot[0] = tf; g.a1_slot[1] = tb; g.a1_col[0] = g.a1_col[1] = 0; }
+                else { g.a1_slot[0] = tf + 1; g.a1_slot[1] = tb + 1; g.a1_col[0] = g.a1_col[1] = 0; }
+                if (int rc = launch_gemm(layer == 0 ? map_enc : map_dec, layer == 0 ? map_x : map_enc,
+                                         layer == 0 ? m->map_enc_w : m->map_dec_w, g, e, m->sms, st)) return rc;
+            }
+        }
+        // MLP
+        tc::GemmShape gl;
+        memset(&gl, 0, sizeof(gl));
+        gl.M = (int)nb; gl.m_blks = g.m_blks; gl.n_blks = LIN / tc::BLOCK_N; gl.dirs = 1;
+        for (int l = 0; l < 5; l++) {
+            SeluEpilogue e;
+            e.bias = m->lin_b[l]; e.out = (l & 1) ? w.act1 : w.act0; e.ldo = LIN;
+            gl.kb0 = 0; gl.kb1 = (l == 0 ? FLAT : LIN) / tc::BLOCK_K;
+            const CUtensorMap& a = l == 0 ? map_flat : ((l & 1) ? map_act0 : map_act1);
+            if (int rc = launch_gemm(a, a, m->map_lin_w[l], gl, e, m->sms, st)) return rc;
+        }
+        head_kernel<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(w.act0, m->out_w, m->out_b, probs + off * 3,
+                                                                        argmax ? argmax + off : nullptr, nb);
+        PV_CUDA_CHECK(cudaGetLastError());
+    }
+    return PV_OK;
+}
+
+extern "C" int pv_lstm_infer_host(PvLstmModel* m, const int16_t* windows_host, int64_t n, int32_t wrap_int8,
+                                  float* probs_host, uint8_t* argmax_host) {
+    if (!m || !windows_host || !probs_host) return pv::set_error(PV_EINVAL, "null argument");
+    if (n <= 0) return PV_OK;
+    if (int rc = pv::require_device()) return rc;
+    if (!m->stream) PV_CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    const int64_t need = pv_lstm_workspace_bytes(n);
+    if (need > m->ws_bytes) {
+        if (m->ws) cudaFree(m->ws);
+        m->ws = nullptr; m->ws_bytes = 0;
+        PV_CUDA_CHECK(cudaMalloc(&m->ws, (size_t)need));
+        m->ws_bytes = need;
+    }
+    if (n > m->io_cap) {
+        if (m->win_dev) cudaFree(m->win_dev);
+        if (m->probs_dev) cudaFree(m->probs_dev);
+        if (m->arg_dev) cudaFree(m->arg_dev);
+        m->io_cap = 0;
+        PV_CUDA_CHECK(cudaMalloc((void**)&m->win_dev, (size_t)n * T * F * 2));
+        PV_CUDA_CHECK(cudaMalloc((void**)&m->probs_dev, (size_t)n * 3 * 4));
+        PV_CUDA_CHECK(cudaMalloc((void**)&m->arg_dev, (size_t)n));
+        m->io_cap = n;
+    }
+    PV_CUDA_CHECK(cudaMemcpyAsync(m->win_dev, windows_host, (size_t)n * T * F * 2, cudaMemcpyHostToDevice, m->stream));
+    if (int rc = pv_lstm_infer(m, m->win_dev, n, wrap_int8, m->probs_dev, m->arg_dev, m->ws, m->ws_bytes, m->stream)) return rc;
+    PV_CUDA_CHECK(cudaMemcpyAsync(probs_host, m->probs_dev, (size_t)n * 12, cudaMemcpyDeviceToHost, m->stream));
+    if (argmax_host) PV_CUDA_CHECK(cudaMemcpyAsync(argmax_host, m->arg_dev, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    PV_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return PV_OK;
+}

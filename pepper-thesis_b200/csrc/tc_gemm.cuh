@@ -1,0 +1,239 @@
+// Hand-written tcgen05 + TMA GEMM core for sm_100a with pluggable fused epilogues.
+//
+//   D[M, N] = A[M, K] * W[N, K]^T        bf16 operands (K-major, 128-byte swizzle), fp32 accumulators in TMEM
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0   TMA producer   cp.async.bulk.tensor (UTMALDG) A/W tiles -> 4-stage shared-memory ring (full/empty mbarriers)
+//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UTCHMMA), 128x256x16 per
+//                           instruction, accumulating into one of two 256-column TMEM stages; tcgen05.commit frees
+//                           the smem stage / publishes the accumulator
+//   warp 2   TMEM allocator (512 columns)
+//   warps 4-7 epilogue      tcgen05.ld (LDTM) 32 lanes x 16 columns per call -> registers -> fused epilogue -> HBM,
+//                           overlapping the next tile's MMAs through the second TMEM stage
+//
+// The A operand is the K-concatenation of up to two tensors (A0 then A1), each addressed through its own 3-D
+// tensor map [rows][slot][channels]: this is how a recurrent step computes  [h_{t-1} | x_t] * [W_hh | W_ih]^T
+// in ONE pass (input projection fused with the recurrent product, nothing materialised in HBM).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int W_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane_base + i), columns col..col+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::f16: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- problem description -----------------------------------------------------------------------------------
+struct GemmShape {
+    int M;            // rows (windows)
+    int m_blks;       // ceil(M / 128)
+    int n_blks;       // N / 256 per direction
+    int dirs;         // 1 or 2 independent directions (own W rows, own slots)
+    int kb0, kb1;     // 64-wide k blocks taken from A0 then from A1
+    int a0_col[2];    // first channel of A0 per direction
+    int a0_slot[2];   // slot (time index) of A0 per direction
+    int a1_col[2];
+    int a1_slot[2];
+    int w_row[2];     // first W row per direction
+    int w_kb_off;     // first W k block (non-zero when the h block is skipped because h == 0)
+};
+
+// Epilogue functor interface:
+//   __device__ void operator()(int dir, int n_blk, int row, bool row_ok, uint32_t taddr /* lane base + stage col */)
+// called by the 128 epilogue threads; it must read its 256 accumulator columns with tmem_ld16 + tmem_ld_wait.
+
+template <class Epilogue>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+            const __grid_constant__ CUtensorMap tmW, const GemmShape g, const Epilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_w = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = g.m_blks * g.n_blks * g.dirs;
+    const int kbt = g.kb0 + g.kb1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int dir = tile % g.dirs;
+                const int n_blk = (tile / g.dirs) % g.n_blks;
+                const int m_blk = tile / (g.dirs * g.n_blks);
+                for (int kb = 0; kb < kbt; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    if (kb < g.kb0)
+                        tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA0, &full_bar[stage],
+                                    g.a0_col[dir] + kb * BLOCK_K, g.a0_slot[dir], m_blk * BLOCK_M);
+                    else
+                        tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA1, &full_bar[stage],
+                                    g.a1_col[dir] + (kb - g.kb0) * BLOCK_K, g.a1_slot[dir], m_blk * BLOCK_M);
+                    // W columns: A0's k blocks first, then A1's (the host packs [W_hh | W_ih] that way)
+                    tma_load_2d(smem_w + stage * W_STAGE_BYTES, &tmW, &full_bar[stage],
+                                (g.w_kb_off + kb) * BLOCK_K, g.w_row[dir] + n_blk * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < kbt; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_w + stage * W_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16),
+                                  idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int dir = tile % g.dirs;
+            const int n_blk = (tile / g.dirs) % g.n_blks;
+            const int m_blk = tile / (g.dirs * g.n_blks);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            epi(dir, n_blk, row, row < g.M, taddr);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+}  // namespace tc

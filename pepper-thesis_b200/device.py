@@ -1,0 +1,84 @@
+"""Device-resident hand-off: torch tensors own the HBM, the C-ABI gets raw pointers and the current CUDA stream.
+
+PyTorch is plumbing only (allocation, streams, H2D/D2H); every kernel is in libpepper_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .read_batch import ARRAY_NAMES, ReadBatch
+
+_TORCH_DT = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
+             np.dtype(np.uint32): torch.int32}
+
+
+def _to_torch(a: np.ndarray) -> torch.Tensor:
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return torch.from_numpy(a)
+
+
+class DeviceBatch:
+    """A ReadBatch whose arrays live in HBM (``PvReadBatch`` with device pointers)."""
+
+    def __init__(self, host: ReadBatch, device: torch.device | str = "cuda", non_blocking: bool = True):
+        self.host = host
+        self.device = torch.device(device)
+        self.t = {}
+        for name in ARRAY_NAMES:
+            a = getattr(host, name)
+            src = _to_torch(a) if a.size else torch.zeros(1, dtype=_TORCH_DT[np.dtype(a.dtype)])
+            self.t[name] = src.to(self.device, non_blocking=non_blocking)
+        self.region_len = np.ascontiguousarray(host.region_len)
+        self.total_positions = int(self.region_len.sum())
+        self.struct = host.as_struct({n: self.t[n].data_ptr() for n in ARRAY_NAMES})
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
+
+
+class SummaryWorkspace:
+    """Caller-allocated outputs + scratch of ``pv_summary_regions`` (reused across calls of the same shape)."""
+
+    def __init__(self, n_reads, n_ops, n_regions, total_positions, capacity, device="cuda", want_dense=False):
+        lib = capi.load()
+        self.capacity = int(capacity)
+        dev = torch.device(device)
+        ws_bytes = int(lib.pv_summary_workspace_bytes(n_reads, n_ops, n_regions, total_positions, capacity))
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.windows = torch.empty((capacity, capi.PV_WINDOW, capi.PV_FEATURES), dtype=torch.int16, device=dev)
+        self.position = torch.empty(capacity, dtype=torch.int64, device=dev)
+        self.region = torch.empty(capacity, dtype=torch.int32, device=dev)
+        self.depth = torch.empty(capacity, dtype=torch.int32, device=dev)
+        self.frequency = torch.empty(capacity, dtype=torch.int32, device=dev)
+        self.allele = torch.empty((capacity, capi.PV_ALLELE_BYTES), dtype=torch.uint8, device=dev)
+        self.allele_len = torch.empty(capacity, dtype=torch.uint8, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.dense = torch.empty((total_positions, capi.PV_FEATURES), dtype=torch.int16, device=dev) if want_dense else None
+        self.out = capi.PvCandidatesStruct(capacity, self.windows.data_ptr(), self.position.data_ptr(),
+                                           self.region.data_ptr(), self.depth.data_ptr(), self.frequency.data_ptr(),
+                                           self.allele.data_ptr(), self.allele_len.data_ptr())
+
+    @classmethod
+    def for_batch(cls, db: DeviceBatch, capacity: int, want_dense=False) -> "SummaryWorkspace":
+        h = db.host
+        return cls(h.n_reads, h.n_ops, h.n_regions, db.total_positions, capacity, db.device, want_dense)
+
+    def status(self) -> int:
+        return int(self.ws[12:16].view(torch.int32).item())
+
+
+def summary_regions(db: DeviceBatch, thr, ws: SummaryWorkspace, window: int = 32, features: int = 26):
+    """Launch the summary kernel chain on the current stream (asynchronous; no host sync)."""
+    lib = capi.load()
+    t = capi.thresholds_struct(thr)
+    stream = torch.cuda.current_stream(db.device).cuda_stream
+    rc = lib.pv_summary_regions(C.byref(db.struct), db.region_len.ctypes.data, db.total_positions, C.byref(t), window,
+                                features, C.byref(ws.out), ws.count.data_ptr(), ws.ws.data_ptr(), ws.ws.numel(),
+                                ws.dense.data_ptr() if ws.dense is not None else None, C.c_void_p(stream))
+    capi.check(rc)

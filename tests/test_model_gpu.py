@@ -1,0 +1,141 @@
+"""GPU parity of the two TransducerGRU models (tcgen05 path) against the fp32 CPU restatement and the goldens made
+from the real reference modules. Tolerances (BASELINE.json north_star): outputs within 1e-2, identical argmax on
+>= 99.99 % of positions (ties closer than the tolerance are not counted as disagreements)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import model_port as MP
+from pepper_thesis_b200 import models
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-2
+
+
+def _variant(seed=0):
+    m = models.TransducerGRU(26, 1, 256, 28, 3, True)
+    sd = MP.variant_state_dict(seed)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def _argmax_agreement(a, b, tol):
+    """fraction of rows whose argmax agrees, not counting rows where the oracle's top two are within tol"""
+    aa, bb = a.argmax(-1), b.argmax(-1)
+    top2 = np.sort(b, axis=-1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > tol
+    return float(((aa == bb) | ~clear).mean()), float((aa == bb).mean())
+
+
+def test_variant_golden():
+    g = np.load(os.path.join(GOLD, "model_variant.npz"))
+    m, sd = _variant(0)
+    y = m(torch.from_numpy(g["x"]), False).numpy()
+    ref = g["probs"] if abs(sum(float(v.double().sum()) for v in sd.values()) - float(g["w_sum"])) < 1e-6 else \
+        MP.variant_forward(sd, torch.from_numpy(g["x"].astype(np.float32))).numpy()
+    assert np.abs(y - ref).max() < TOL, np.abs(y - ref).max()
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000])
+def test_variant_vs_port_sizes(n):
+    m, sd = _variant(1)
+    g = torch.Generator().manual_seed(n)
+    x = -torch.randint(0, 50, (n, 33, 26), generator=g)
+    x[:, :, 0] = torch.randint(1, 6, (n, 33), generator=g)
+    y = m(x, False).numpy()
+    ref = MP.variant_forward(sd, x.float()).numpy()
+    err = np.abs(y - ref).max()
+    print("variant n=%d max prob err %.2e" % (n, err))
+    assert err < TOL, err
+    agree, raw = _argmax_agreement(y, ref, TOL)
+    assert agree >= 0.9999, (agree, raw)
+    assert np.allclose(y.sum(-1), 1.0, atol=1e-5)
+
+
+def test_variant_deep_coverage_and_wrap():
+    """Values beyond +-127: exact hi/lo bf16 split (wrap off) and the reference pipeline's int8 round trip (wrap on)."""
+    m, sd = _variant(2)
+    g = torch.Generator().manual_seed(7)
+    x = -torch.randint(0, 3000, (200, 33, 26), generator=g)
+    y = m(x, False).numpy()
+    ref = MP.variant_forward(sd, x.float()).numpy()
+    assert np.abs(y - ref).max() < TOL
+    probs, arg = m.infer_windows(x.to(torch.int16).cuda(), wrap_int8=True)
+    xw = x.to(torch.int16).numpy().astype(np.int8).astype(np.float32)      # DataStore.py:68 / dataloader_predict.py:90
+    refw = MP.variant_forward(sd, torch.from_numpy(xw)).numpy()
+    assert np.abs(probs.cpu().numpy() - refw).max() < TOL
+    assert (arg.cpu().numpy() == probs.cpu().numpy().argmax(-1)).all()
+
+
+def test_variant_large_batch_chunks():
+    m, sd = _variant(3)
+    g = torch.Generator().manual_seed(11)
+    n = 9000                                                   # > one 8192-window pass
+    x = -torch.randint(0, 40, (n, 33, 26), generator=g)
+    y = m(x, False).numpy()
+    idx = np.r_[0:64, 8150:8250, n - 64:n]
+    ref = MP.variant_forward(sd, x[idx].float()).numpy()
+    assert np.abs(y[idx] - ref).max() < TOL
+
+
+def test_variant_checkpoint_contract(tmp_path):
+    sd = MP.variant_state_dict(5)
+    ck = {"model_state_dict": {"module." + k: v for k, v in sd.items()}, "model_optimizer": {}, "hidden_size": 256,
+          "gru_layers": 1, "epochs": 3}
+    path = str(tmp_path / "ckpt.pkl")
+    torch.save(ck, path)
+    m, hs, gl, ep = models.ModelHandler.load_simple_model_for_training(path, 26, 28, 3)
+    assert (hs, gl, ep) == (256, 1, 3)
+    x = -torch.randint(0, 30, (16, 33, 26))
+    assert np.abs(m(x, False).numpy() - MP.variant_forward(sd, x.float()).numpy()).max() < TOL
+
+
+def _polisher(seed=0):
+    m = models.PolisherTransducerGRU(1, 10, 1, 128, 5, True)
+    sd = MP.polisher_state_dict(seed)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def test_polisher_golden():
+    g = np.load(os.path.join(GOLD, "model_polisher.npz"))
+    m, sd = _polisher(0)
+    logits, hf = m(torch.from_numpy(g["x"]), torch.from_numpy(g["h"]))
+    if abs(sum(float(v.double().sum()) for v in sd.values()) - float(g["w_sum"])) < 1e-6:
+        rl, rh = g["logits"], g["h_final"]
+    else:
+        a, b = MP.polisher_forward(sd, torch.from_numpy(g["x"].astype(np.float32)), torch.from_numpy(g["h"]))
+        rl, rh = a.numpy(), b.numpy()
+    assert np.abs(logits.numpy() - rl).max() < TOL, np.abs(logits.numpy() - rl).max()
+    assert np.abs(hf.numpy() - rh).max() < TOL
+
+
+@pytest.mark.parametrize("n", [3, 130, 600])
+def test_polisher_vs_port(n):
+    m, sd = _polisher(1)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randint(0, 255, (n, 100, 10), generator=g)
+    h = torch.randn(n, 2, 128, generator=g) * 0.5
+    logits, hf = m(x, h)
+    rl, rh = MP.polisher_forward(sd, x.float(), h)
+    print("polisher n=%d max logit err %.2e hidden err %.2e" % (n, (logits - rl).abs().max(), (hf - rh).abs().max()))
+    assert (logits - rl).abs().max() < TOL, (logits - rl).abs().max()
+    assert (hf - rh).abs().max() < TOL
+    agree, raw = _argmax_agreement(logits.numpy(), rl.numpy(), TOL)
+    assert agree >= 0.9999, (agree, raw)
+
+
+def test_polisher_chunk_loop():
+    """1000-position chunks, 100-wide windows every 50, hidden carried, softmax summed (predict_distributed_gpu.py:63-96)."""
+    m, sd = _polisher(2)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 255, (20, 1000, 10), generator=g)
+    acc, labels = m.predict_chunks(x, 100, 50)
+    racc, rlab = MP.polisher_predict_chunks(sd, x, 100, 50)
+    assert (acc.cpu() - racc).abs().max() < 2 * TOL
+    agree, raw = _argmax_agreement(acc.cpu().numpy(), racc.numpy(), 2 * TOL)
+    assert agree >= 0.9999, (agree, raw)
+    assert (labels.cpu().numpy() == acc.cpu().numpy().argmax(-1)).all()
