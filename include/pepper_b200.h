@@ -109,6 +109,20 @@ const char* pv_last_error(void);
 /* number of usable CUDA devices (sm_100); 0 when none. Never fails. */
 int pv_device_count(void);
 
+/* Launch accounting and optional CUDA-event profiling of the library's own kernels (used by bench.py for
+ * `gpu_launches` and the per-kernel roofline). Families, in order: 0 summary cigar prefix, 1 summary pileup tile,
+ * 2 summary site alleles, 3 summary key sort, 4 summary window emit, 5 LSTM input prep, 6 LSTM encoder steps,
+ * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc. */
+#define PV_PROFILE_FAMILIES 11
+void pv_profile_enable(int on);
+int pv_profile_collect(double* ms_by_family, int64_t* launches_by_family);
+void pv_profile_reset(void);
+int64_t pv_launch_count(void);
+
+/* byte offset, inside the summary workspace, of the int32 status word of the last pv_summary_regions call
+ * (bit0 site scratch overflow, bit1 allele-event scratch overflow, bit2 candidate capacity overflow, bit3 internal). */
+int pv_summary_status_offset(void);
+
 /* Host-side consistency check of a HOST-resident batch. */
 int pv_batch_validate(const PvReadBatch* host_batch);
 
@@ -116,8 +130,8 @@ int pv_batch_validate(const PvReadBatch* host_batch);
  * Summary: device-resident interface. `stream` is a cudaStream_t passed as void*.
  * pv_summary_workspace_bytes: bytes of scratch pv_summary_regions needs for this batch shape.
  * pv_summary_regions: everything asynchronous on `stream`; *n_candidates_dev (device int64) receives the
- *   number of candidates found. If it exceeds out->capacity only the first `capacity` (in reference order)
- *   are stored; the host wrapper reports PV_EOVERFLOW.
+ *   number of candidates found. If it exceeds out->capacity an unspecified subset of `capacity` candidates is
+ *   stored (still sorted); the host wrapper reports PV_EOVERFLOW and the caller retries with a larger capacity.
  * dense_image_dev (optional, may be NULL): int16 [total_positions][26] clamped image_matrix of every region
  *   back to back (debug / parity hook for region_summary.cpp:598-654).
  * ------------------------------------------------------------------------------------------------------- */

@@ -128,3 +128,30 @@ def polisher_predict_chunks(sd, images, window=100, stride=50):
         logits, hidden = polisher_forward(sd, images[:, i:i + window].float(), hidden)
         acc[:, i:i + window] += torch.softmax(logits, dim=2)
     return acc, acc.argmax(dim=2)
+
+
+class TorchVariantModule(nn.Module):
+    """nn.Module re-declaration of the variant TransducerGRU (simple_model.py:6-82) on the stock PyTorch operators
+    (nn.LSTM / nn.Linear / nn.SELU / nn.Softmax) -- used ONLY as the CPU baseline of bench.py, where the reference's
+    own module cannot be imported (its tree is absent on the GPU box)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        self.encoder = nn.LSTM(26, 256, num_layers=1, bidirectional=True, batch_first=True)
+        self.decoder = nn.LSTM(512, 256, num_layers=1, bidirectional=True, batch_first=True)
+        self.activation = nn.SELU()
+        self.linear_1 = nn.Linear(512 * 33, 512)
+        self.linear_2 = nn.Linear(512, 512)
+        self.linear_3 = nn.Linear(512, 512)
+        self.linear_4 = nn.Linear(512, 512)
+        self.linear_5 = nn.Linear(512, 512)
+        self.output_layer_type = nn.Linear(512, 3)
+        self.load_state_dict(sd)
+
+    def forward(self, x):
+        x, _ = self.encoder(x)
+        x, _ = self.decoder(x)
+        x = torch.flatten(x, start_dim=1, end_dim=2)
+        for lin in (self.linear_1, self.linear_2, self.linear_3, self.linear_4, self.linear_5):
+            x = self.activation(lin(x))
+        return torch.softmax(self.output_layer_type(x), dim=1)

@@ -19,7 +19,8 @@ PV_WINDOW, PV_FEATURES, PV_ALLELE_BYTES = 33, 26, 64
 PV_EOVERFLOW = -4
 
 # every symbol include/pepper_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_batch_validate", "pv_summary_workspace_bytes",
+EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_profile_enable", "pv_profile_collect",
+           "pv_profile_reset", "pv_launch_count", "pv_summary_status_offset", "pv_batch_validate", "pv_summary_workspace_bytes",
            "pv_summary_regions", "pv_summary_regions_host", "pv_lstm_create", "pv_lstm_destroy",
            "pv_lstm_workspace_bytes", "pv_lstm_infer", "pv_lstm_infer_host", "pv_gru_create", "pv_gru_destroy",
            "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks"]
@@ -72,6 +73,11 @@ def load() -> C.CDLL:
         lib.pv_last_error.restype = C.c_char_p
         lib.pv_device_count.restype = C.c_int
         lib.pv_batch_validate.argtypes = [C.POINTER(PvReadBatchStruct)]
+        lib.pv_profile_enable.argtypes = [C.c_int]
+        lib.pv_profile_enable.restype = None
+        lib.pv_profile_collect.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pv_profile_reset.restype = None
+        lib.pv_launch_count.restype = C.c_int64
         lib.pv_summary_workspace_bytes.restype = C.c_int64
         lib.pv_summary_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64]
         lib.pv_summary_regions.argtypes = [C.POINTER(PvReadBatchStruct), C.c_void_p, C.c_int64,
@@ -102,6 +108,18 @@ def load() -> C.CDLL:
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib = lib
     return _lib
+
+
+FAMILIES = ["sum_cigar_prefix", "sum_pileup_tile", "sum_site_alleles", "sum_key_sort", "sum_emit_windows",
+            "lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head", "gru_steps", "gru_misc"]
+
+
+def profile_collect():
+    """{family: (total ms, launches)} since the last profile_reset (waits for the recorded events)."""
+    ms = (C.c_double * len(FAMILIES))()
+    ln = (C.c_int64 * len(FAMILIES))()
+    load().pv_profile_collect(ms, ln)
+    return {f: (float(ms[i]), int(ln[i])) for i, f in enumerate(FAMILIES)}
 
 
 def check(rc: int):

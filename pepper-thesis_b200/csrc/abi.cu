@@ -40,6 +40,46 @@ int sm_count() {
     return n > 0 ? n : 148;
 }
 
+// ---- launch counting / profiling -----------------------------------------------------------------------------------
+namespace {
+struct ProfRec { int fam; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_open, g_prof_done;
+std::vector<cudaEvent_t> g_prof_pool;
+int64_t g_launches[FAM_COUNT] = {0};
+double g_ms[FAM_COUNT] = {0};
+int64_t g_prof_launches[FAM_COUNT] = {0};
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+
+void prof_begin(int fam, cudaStream_t stream) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    if (!g_prof_on) return;
+    ProfRec r; r.fam = fam; r.a = prof_event(); r.b = nullptr;
+    cudaEventRecord(r.a, stream);
+    g_prof_open.push_back(r);
+}
+
+void prof_end(int fam, cudaStream_t stream, int launches) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    g_launches[fam] += launches;
+    if (!g_prof_on) return;
+    for (size_t i = g_prof_open.size(); i-- > 0;)
+        if (g_prof_open[i].fam == fam) {
+            ProfRec r = g_prof_open[i];
+            g_prof_open.erase(g_prof_open.begin() + i);
+            r.b = prof_event();
+            cudaEventRecord(r.b, stream);
+            g_prof_done.push_back(r);
+            g_prof_launches[fam] += launches;
+            break;
+        }
+}
+
 // grow-only device buffers reused across host-wrapper calls (one set per process; one process per GPU)
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -59,6 +99,38 @@ struct DevBuf {
 
 extern "C" const char* pv_version(void) { return "pepper_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* pv_last_error(void) { return pv::err_buf(); }
+
+extern "C" void pv_profile_enable(int on) {
+    std::lock_guard<std::mutex> l(pv::g_prof_mu);
+    pv::g_prof_on = on != 0;
+}
+
+// Waits for the recorded events, adds their elapsed times to the per-family totals and returns the totals since the
+// last pv_profile_reset: ms[FAM_COUNT], launches[FAM_COUNT] (profiled launches only). Returns the family count.
+extern "C" int pv_profile_collect(double* ms, int64_t* launches) {
+    std::lock_guard<std::mutex> l(pv::g_prof_mu);
+    for (auto& r : pv::g_prof_done) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) pv::g_ms[r.fam] += t;
+        pv::g_prof_pool.push_back(r.a); pv::g_prof_pool.push_back(r.b);
+    }
+    pv::g_prof_done.clear();
+    for (int i = 0; i < pv::FAM_COUNT; i++) { if (ms) ms[i] = pv::g_ms[i]; if (launches) launches[i] = pv::g_prof_launches[i]; }
+    return pv::FAM_COUNT;
+}
+
+extern "C" void pv_profile_reset(void) {
+    std::lock_guard<std::mutex> l(pv::g_prof_mu);
+    for (int i = 0; i < pv::FAM_COUNT; i++) { pv::g_ms[i] = 0; pv::g_prof_launches[i] = 0; }
+}
+
+// kernels launched by this library since load (all families)
+extern "C" int64_t pv_launch_count(void) {
+    std::lock_guard<std::mutex> l(pv::g_prof_mu);
+    int64_t n = 0;
+    for (int i = 0; i < pv::FAM_COUNT; i++) n += pv::g_launches[i];
+    return n;
+}
 
 extern "C" int pv_device_count(void) {
     int n = 0;

@@ -25,6 +25,13 @@ int set_error(int code, const char* fmt, ...);
 int require_device();
 int sm_count();
 
+// kernel families for launch counting and optional CUDA-event profiling (pv_profile_*)
+enum Family { FAM_SUM_PREFIX = 0, FAM_SUM_TILE, FAM_SUM_ALLELE, FAM_SUM_SORT, FAM_SUM_EMIT, FAM_LSTM_PREP, FAM_LSTM_ENC,
+              FAM_LSTM_DEC, FAM_LSTM_MLP, FAM_GRU_STEP, FAM_GRU_MISC, FAM_COUNT };
+// brackets `launches` kernel launches of one family on `stream`; records events only while profiling is enabled
+void prof_begin(int fam, cudaStream_t stream);
+void prof_end(int fam, cudaStream_t stream, int launches);
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // bump allocator over a caller-provided workspace

@@ -230,8 +230,10 @@ int gru_forward_chunk(PvGruModel* m, const GruWs& w, const CUtensorMap& map_x, c
                       float* h_state, cudaStream_t st) {
     const int S = T + 2;
     const int64_t elems = nb * T * GXK;
+    pv::prof_begin(pv::FAM_GRU_MISC, st);
     gru_prep_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(images, img_row_stride, t0, w.xin, nb, T);
     PV_CUDA_CHECK(cudaGetLastError());
+    pv::prof_end(pv::FAM_GRU_MISC, st, 1);
     tc::GemmShape g;
     memset(&g, 0, sizeof(g));
     g.M = (int)nb; g.m_blks = (int)((nb + 127) / 128); g.n_blks = 2; g.dirs = 2;
@@ -245,6 +247,7 @@ int gru_forward_chunk(PvGruModel* m, const GruWs& w, const CUtensorMap& map_x, c
         GruEpilogue e;
         e.bias = layer == 0 ? m->enc_b : m->dec_b; e.h_state = h_state; e.out = out; e.n_blks = 2; e.S = S;
         g.kb1 = layer == 0 ? 1 : GC / tc::BLOCK_K;
+        pv::prof_begin(pv::FAM_GRU_STEP, st);
         for (int s = 0; s < T; s++) {
             const int tf = s, tb = T - 1 - s;
             e.out_slot[0] = tf + 1; e.out_slot[1] = tb + 1;
@@ -255,6 +258,7 @@ int gru_forward_chunk(PvGruModel* m, const GruWs& w, const CUtensorMap& map_x, c
             if (int rc = launch_gemm(layer == 0 ? map_enc : map_dec, layer == 0 ? map_x : map_enc,
                                      layer == 0 ? m->map_enc_w : m->map_dec_w, g, e, m->sms, st)) return rc;
         }
+        pv::prof_end(pv::FAM_GRU_STEP, st, T + 1);
     }
     return PV_OK;
 }

@@ -290,8 +290,10 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t nb = n - off < chunk ? n - off : chunk;
         const int64_t elems = nb * T * XK;
+        pv::prof_begin(pv::FAM_LSTM_PREP, st);
         prep_input_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(windows + off * T * F, w.xhl, nb, wrap_int8);
         PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_LSTM_PREP, st, 1);
 
         tc::GemmShape g;
         memset(&g, 0, sizeof(g));
@@ -305,6 +307,7 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
             e.out = layer == 0 ? w.enc_out : w.dec_out;
             e.n_blks = 4;
             g.kb1 = layer == 0 ? XK / tc::BLOCK_K : C / tc::BLOCK_K;
+            pv::prof_begin(layer == 0 ? pv::FAM_LSTM_ENC : pv::FAM_LSTM_DEC, st);
             for (int s = 0; s < T; s++) {
                 const int tf = s, tb = T - 1 - s;               // time handled by the forward / reverse direction
                 e.first = s == 0;
@@ -317,8 +320,10 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
                 if (int rc = launch_gemm(layer == 0 ? map_enc : map_dec, layer == 0 ? map_x : map_enc,
                                          layer == 0 ? m->map_enc_w : m->map_dec_w, g, e, m->sms, st)) return rc;
             }
+            pv::prof_end(layer == 0 ? pv::FAM_LSTM_ENC : pv::FAM_LSTM_DEC, st, T);
         }
         // MLP
+        pv::prof_begin(pv::FAM_LSTM_MLP, st);
         tc::GemmShape gl;
         memset(&gl, 0, sizeof(gl));
         gl.M = (int)nb; gl.m_blks = g.m_blks; gl.n_blks = LIN / tc::BLOCK_N; gl.dirs = 1;
@@ -332,6 +337,7 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
         head_kernel<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(w.act0, m->out_w, m->out_b, probs + off * 3,
                                                                         argmax ? argmax + off : nullptr, nb);
         PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_LSTM_MLP, st, 6);
     }
     return PV_OK;
 }

@@ -812,26 +812,36 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     if (b.n_reads > 0) {
         int64_t blocks = (b.n_reads + 7) / 8;            // 8 warps per 256-thread block
         if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+        pv::prof_begin(pv::FAM_SUM_PREFIX, stream);
         cigar_prefix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b, w.op_ref, w.op_ri, w.read_span);
         PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_SUM_PREFIX, stream, 1);
     }
     const size_t smem = k1_smem_bytes(pl.P);
     PV_CUDA_CHECK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pv::prof_begin(pv::FAM_SUM_TILE, stream);
     pileup_tile_kernel<<<(unsigned)n_tiles, K1_THREADS, smem, stream>>>(p);
     PV_CUDA_CHECK(cudaGetLastError());
+    pv::prof_end(pv::FAM_SUM_TILE, stream, 1);
 
+    pv::prof_begin(pv::FAM_SUM_ALLELE, stream);
     site_allele_kernel<<<sms * 8, 256, 0, stream>>>(p);
     PV_CUDA_CHECK(cudaGetLastError());
+    pv::prof_end(pv::FAM_SUM_ALLELE, stream, 1);
 
+    pv::prof_begin(pv::FAM_SUM_SORT, stream);
     iota_kernel<<<(unsigned)((pl.cand_cap + 255) / 256), 256, 0, stream>>>(w.val_in, (int)pl.cand_cap);
     PV_CUDA_CHECK(cudaGetLastError());
     size_t tmp = pl.sort_tmp;
     PV_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.sort_tmp, tmp, (const unsigned long long*)w.key_in, w.key_out,
                                                   (const uint32_t*)w.val_in, w.val_out, (int)pl.cand_cap, 0, 64, stream));
+    pv::prof_end(pv::FAM_SUM_SORT, stream, 11);     // iota + histogram + exclusive sum + 8 onesweep passes
     int64_t eblocks = (pl.cand_cap + 7) / 8;
     if (eblocks > (int64_t)sms * 16) eblocks = (int64_t)sms * 16;
+    pv::prof_begin(pv::FAM_SUM_EMIT, stream);
     emit_window_kernel<<<(unsigned)eblocks, 256, 0, stream>>>(p, w.val_out, *out, n_candidates_dev);
     PV_CUDA_CHECK(cudaGetLastError());
+    pv::prof_end(pv::FAM_SUM_EMIT, stream, 1);
     return PV_OK;
 }
 

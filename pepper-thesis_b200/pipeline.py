@@ -1,0 +1,167 @@
+"""Region-sharded hot path: pileup summary -> candidate windows -> TransducerGRU inference, all on the GPU.
+
+Mirrors what `pepper_variant call_variant` does between reading the BAM and writing predictions
+(/root/reference/pepper_variant/modules/python/ImageGenerationUI.py:191-260 make_images +
+/root/reference/pepper_variant/modules/python/models/predict_distributed_gpu.py:48-70 run_inference) without the HDF5
+round trip: the int16 windows the summary kernels emit are consumed in place by the inference kernels.
+
+Multi-GPU: regions are independent. Rank r of N takes the contiguous block
+``shard_regions(n_regions, r, N)``; there is NO data-path collective, only a host-side gather of the small result
+records (``gather_to_rank0``), exactly like the reference concatenates per-process outputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import device as dev
+from .read_batch import ReadBatch
+
+
+def shard_regions(n_regions: int, rank: int, world: int):
+    """Contiguous block of regions for ``rank`` (block sizes differ by at most one)."""
+    base, rem = divmod(n_regions, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class Predictions:
+    """SoA form of ``list[CandidateImagePrediction]`` (region_summary.h:114-136) for a set of regions."""
+    region: np.ndarray        # int32 [K] region index (global)
+    position: np.ndarray      # int64 [K]
+    depth: np.ndarray         # int32 [K]
+    frequency: np.ndarray     # int32 [K]
+    allele: np.ndarray        # uint8 [K, 64]
+    allele_len: np.ndarray    # uint8 [K]
+    probs: np.ndarray         # float32 [K, 3]  prediction_type (softmax)
+    genotype: np.ndarray      # uint8 [K] argmax
+
+    def __len__(self):
+        return int(self.position.shape[0])
+
+    def alleles(self):
+        return [bytes(self.allele[i, :self.allele_len[i]]) for i in range(len(self))]
+
+    @staticmethod
+    def empty():
+        return Predictions(np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                           np.zeros((0, 64), np.uint8), np.zeros(0, np.uint8), np.zeros((0, 3), np.float32),
+                           np.zeros(0, np.uint8))
+
+    @staticmethod
+    def concat(parts: List["Predictions"]) -> "Predictions":
+        parts = [p for p in parts if p is not None]
+        if not parts:
+            return Predictions.empty()
+        return Predictions(*[np.concatenate([getattr(p, f) for p in parts]) for f in
+                             ("region", "position", "depth", "frequency", "allele", "allele_len", "probs", "genotype")])
+
+    def sorted(self) -> "Predictions":
+        """(region, position) order; within a position the emission order is kept (stable)."""
+        order = np.lexsort((self.position, self.region))
+        return Predictions(*[getattr(self, f)[order] for f in
+                             ("region", "position", "depth", "frequency", "allele", "allele_len", "probs", "genotype")])
+
+
+def merge_results(parts: List[Predictions]) -> Predictions:
+    """Host-side gather step: concatenate per-rank (or per-group) results and restore (region, position) order."""
+    return Predictions.concat(parts).sorted()
+
+
+def gather_to_rank0(local: Predictions, group=None) -> Optional[Predictions]:
+    """Gather the per-rank result records on rank 0 (torch.distributed, any backend; host objects, no device collective)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(local, gathered, dst=0, group=group)
+    return merge_results(gathered) if rank == 0 else None
+
+
+class HotPath:
+    """summary + inference for batches of regions on one GPU."""
+
+    def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
+                 wrap_int8: bool = True):
+        self.model = model
+        self.thr = thresholds
+        self.device = torch.device(device)
+        self.group_regions = group_regions
+        self.cand_per_kbp = candidates_per_kbp
+        self.wrap_int8 = wrap_int8
+        self._ws = None
+        self._ws_key = None
+        self.copy_stream = None
+        self.last_launches = 0
+
+    def _workspace(self, db: dev.DeviceBatch):
+        h = db.host
+        cap = max(4096, int(db.total_positions / 1000.0 * self.cand_per_kbp))
+        key = (h.n_reads, h.n_ops, h.n_regions, db.total_positions, cap)
+        if self._ws is None or any(a < b for a, b in zip(self._ws_key, key)):
+            grow = tuple(int(max(a, b) * 1.05) + 16 for a, b in zip(self._ws_key or key, key))
+            self._ws = dev.SummaryWorkspace(grow[0], grow[1], grow[2], grow[3], grow[4], self.device)
+            self._ws_key = grow
+        return self._ws
+
+    def run_device(self, db: dev.DeviceBatch, region_offset: int = 0, to_host: bool = True):
+        """One group of regions already in HBM. Returns Predictions (host) or a dict of device tensors."""
+        while True:
+            ws = self._workspace(db)
+            dev.summary_regions(db, self.thr, ws)
+            k = int(ws.count.item())                        # the one host sync: inference grid sizes need K
+            st = ws.status()
+            if st & 8:
+                raise RuntimeError("internal inconsistency in the allele event pass")
+            if k > ws.capacity or (st & 7):
+                self.cand_per_kbp *= 2.0 * max(1.0, k / max(1, ws.capacity))
+                self._ws = None
+                continue
+            break
+        probs, arg = self.model.infer_windows(ws.windows[:k], wrap_int8=self.wrap_int8)
+        # kernels launched: K0 K1 K2 iota + 10 cub sort passes + K3 = 15; prep + 66 steps + 5 MLP + head = 73 per 8192 windows
+        self.last_launches = 15 + 73 * max(1, (k + 8191) // 8192)
+        if not to_host:
+            return dict(count=k, region=ws.region[:k] + region_offset, position=ws.position[:k], depth=ws.depth[:k],
+                        frequency=ws.frequency[:k], allele=ws.allele[:k], allele_len=ws.allele_len[:k], probs=probs,
+                        genotype=arg)
+        return Predictions((ws.region[:k] + region_offset).cpu().numpy(), ws.position[:k].cpu().numpy(),
+                           ws.depth[:k].cpu().numpy(), ws.frequency[:k].cpu().numpy(), ws.allele[:k].cpu().numpy(),
+                           ws.allele_len[:k].cpu().numpy(), probs.cpu().numpy(), arg.cpu().numpy())
+
+    def run_host(self, batch: ReadBatch, region_offset: int = 0) -> Predictions:
+        """Host buffers in, host results out: regions are processed in groups; the H2D copy of group i+1 (on a side
+        stream, from pinned memory when the batch is pinned) overlaps the kernels of group i."""
+        n = batch.n_regions
+        if n == 0:
+            return Predictions.empty()
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(self.device)
+        groups = [(r0, min(n, r0 + self.group_regions)) for r0 in range(0, n, self.group_regions)]
+        main = torch.cuda.current_stream(self.device)
+
+        def upload(g):
+            with torch.cuda.stream(self.copy_stream):
+                db = dev.DeviceBatch(batch.region_range_view(*g), self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            return db, ev
+
+        out, launches = [], 0
+        nxt = upload(groups[0])
+        for i, g in enumerate(groups):
+            db, ev = nxt
+            main.wait_event(ev)
+            if i + 1 < len(groups):
+                nxt = upload(groups[i + 1])
+            out.append(self.run_device(db, region_offset + g[0]))
+            for t in db.t.values():
+                t.record_stream(main)
+            launches += self.last_launches
+        self.last_launches = launches
+        return Predictions.concat(out)

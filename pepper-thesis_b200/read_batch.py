@@ -109,6 +109,32 @@ class ReadBatch:
                 setattr(s, name, a.ctypes.data)
         return s
 
+    def region_range_view(self, r0: int, r1: int) -> "ReadBatch":
+        """Regions [r0, r1) as a batch whose big arrays (bases, quals, cigar, ref) are VIEWS of this batch (no copy);
+        only the small per-read / per-region offset arrays are rebuilt. Requires the layout pack_regions / synth
+        produce: reads, bases, ops and reference of consecutive regions stored consecutively."""
+        rb, re_ = int(self.region_read_begin[r0]), int(self.region_read_begin[r1])
+        f_lo = int(self.region_ref_off[r0])
+        f_hi = int(self.region_ref_off[r1 - 1] + self.region_ref_len[r1 - 1])
+        if re_ > rb:
+            b_lo = int(self.read_base_off[rb])
+            b_hi = int(self.read_base_off[re_ - 1]) + ((int(self.read_len[re_ - 1]) + 15) & ~15)
+            b_hi = min(b_hi, self.n_bases)
+            c_lo = int(self.read_cigar_off[rb])
+            c_hi = int(self.read_cigar_off[re_ - 1] + self.read_n_ops[re_ - 1])
+        else:
+            b_lo = b_hi = c_lo = c_hi = 0
+        return ReadBatch(
+            read_pos=self.read_pos[rb:re_], read_base_off=self.read_base_off[rb:re_] - b_lo, read_len=self.read_len[rb:re_],
+            read_cigar_off=self.read_cigar_off[rb:re_] - c_lo, read_n_ops=self.read_n_ops[rb:re_],
+            read_flags=self.read_flags[rb:re_], read_mapq=self.read_mapq[rb:re_],
+            bases=self.bases[b_lo:b_hi], quals=self.quals[b_lo:b_hi], cigar=self.cigar[c_lo:c_hi],
+            region_ref_start=self.region_ref_start[r0:r1], region_ref_end=self.region_ref_end[r0:r1],
+            region_cand_start=self.region_cand_start[r0:r1], region_cand_end=self.region_cand_end[r0:r1],
+            region_ref_off=self.region_ref_off[r0:r1] - f_lo, region_ref_len=self.region_ref_len[r0:r1],
+            region_read_begin=self.region_read_begin[r0:r1 + 1] - rb, ref=self.ref[f_lo:f_hi],
+            contigs=self.contigs[r0:r1] if self.contigs else [])
+
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""
         return select_regions(self, [r])
