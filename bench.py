@@ -179,7 +179,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pepper_thesis_b200 import capi, device as dev, models, pipeline, synth
-    from pepper_thesis_b200 import build
+    from pepper_thesis_b200 import nativebuild as build
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -1,7 +1,7 @@
 """pepper-thesis_b200: B200-native (sm_100a) pileup-summary + recurrent-inference hot path of PEPPER r0.8.
 
 Sub-modules (imported lazily; nothing here touches CUDA at import time):
-  build        compile every native artefact in-tree (nvcc / gcc / g++)
+  nativebuild  compile every native artefact in-tree (nvcc / gcc / g++)
   read_batch   packed SoA read batch (host side of include/pepper_b200.h PvReadBatch)
   synth        seeded synthetic pileups
   capi         ctypes binding of the C-ABI library libpepper_b200.so

@@ -66,7 +66,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise PvError(-2, "libpepper_b200.so is not built (run `python -m pepper_thesis_b200.build`); "
+            raise PvError(-2, "libpepper_b200.so is not built (run `python -m pepper_thesis_b200.nativebuild`); "
                               "there is no CPU fallback")
         lib = C.CDLL(LIB_PATH)
         lib.pv_version.restype = C.c_char_p

@@ -33,7 +33,7 @@ class _Sizes(C.Structure):
 def _lib():
     global _LIB
     if _LIB is None:
-        from . import build
+        from . import nativebuild as build
         path = build.build_synth()
         _LIB = C.CDLL(path)
         _LIB.pv_synth_count.argtypes = [C.POINTER(_Cfg), C.c_int64, C.c_int64, C.c_int, C.POINTER(_Sizes)]

@@ -16,6 +16,6 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Build every native artefact once per session (no-op when up to date)."""
-    from pepper_thesis_b200 import build
+    from pepper_thesis_b200 import nativebuild as build
     build.build_all()
     yield

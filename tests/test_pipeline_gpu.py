@@ -1,0 +1,73 @@
+"""GPU: summary -> inference pipeline (device-resident and host-buffer entry points) against the oracles, and
+size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import model_port as MP
+import pyoracle as O
+from pepper_thesis_b200 import device as dev, models, pipeline, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _hot_path(profile, wrap=False, group=3):
+    sd = models.random_variant_state_dict(0)
+    model = models.TransducerGRU().load_state_dict(sd)
+    return pipeline.HotPath(model, synth.PROFILES[profile].thresholds, "cuda", group_regions=group, wrap_int8=wrap), sd
+
+
+def test_pipeline_matches_oracles_end_to_end():
+    b = synth.generate("ont_r9", 520000, 25.0, seed=21)          # 6 regions, groups of 3 -> two uploads
+    hp, sd = _hot_path("ont_r9")
+    pred = hp.run_host(b)
+    thr = synth.PROFILES["ont_r9"].thresholds
+    pos, alle, imgs = [], [], []
+    for r in range(b.n_regions):
+        o = O.ref_summary(b, r, thr) if O.have_ref() else O.port_summary(b, r, thr)
+        pos.append(np.asarray(o["position"])); alle += list(o["alleles"]); imgs.append(np.asarray(o["images"]))
+    pos = np.concatenate(pos); imgs = np.concatenate(imgs)
+    assert np.array_equal(pred.position, pos) and pred.alleles() == alle
+    want = MP.variant_forward(sd, torch.from_numpy(imgs.astype(np.float32))).numpy()
+    assert np.abs(pred.probs - want).max() < 1e-2
+    assert (pred.genotype == pred.probs.argmax(-1)).all()
+    assert (np.diff(pred.region) >= 0).all()
+
+
+def test_grouping_and_sharding_do_not_change_results():
+    """Property at a larger size: any grouping of regions, and any rank sharding + merge, gives identical records."""
+    b = synth.generate("hifi", 1300000, 20.0, seed=22)            # 13 regions
+    hp1, _ = _hot_path("hifi", group=13)
+    hp2, _ = _hot_path("hifi", group=4)
+    a, c = hp1.run_host(b), hp2.run_host(b)
+    assert np.array_equal(a.position, c.position) and a.alleles() == c.alleles() and np.array_equal(a.probs, c.probs)
+    parts = []
+    for rank in range(3):
+        lo, hi = pipeline.shard_regions(b.n_regions, rank, 3)
+        parts.append(hp2.run_host(b.region_range_view(lo, hi), region_offset=lo))
+    m = pipeline.merge_results(parts[::-1])
+    assert np.array_equal(m.region, a.region) and np.array_equal(m.position, a.position) and m.alleles() == a.alleles()
+    assert np.abs(m.probs - a.probs).max() < 1e-6
+
+
+def test_int8_wrap_mode_matches_reference_pipeline():
+    b = H.kat_clamp()                                             # 300x coverage: features reach -300
+    hp, sd = _hot_path("ont_r9", wrap=True, group=1)
+    pred = hp.run_host(b)
+    o = O.port_summary(b, 0, H.R9)
+    x = o["images"].astype(np.int8).astype(np.float32)            # DataStore.py:68 + dataloader_predict.py:90
+    want = MP.variant_forward(sd, torch.from_numpy(x)).numpy()
+    assert np.abs(pred.probs - want).max() < 1e-2
+
+
+def test_device_resident_api_and_counts():
+    b = synth.generate("ont_r10", 200000, 40.0, seed=23)
+    hp, _ = _hot_path("ont_r10")
+    db = dev.DeviceBatch(b)
+    out = hp.run_device(db, to_host=False)
+    assert out["probs"].is_cuda and out["probs"].shape == (out["count"], 3)
+    s = out["probs"].sum(1)
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-5)
+    pred = hp.run_device(db)
+    assert len(pred) == out["count"] and (np.diff(pred.position[pred.region == 0]) >= 0).all()
