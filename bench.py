@@ -215,10 +215,7 @@ def run_ours(args):
     input_bytes = sum(d.h2d_bytes for d in resident)
 
     def step_resident():
-        k = 0
-        for d, g in zip(resident, groups):
-            k += hp.run_device(d, g[0], to_host=False)["count"]
-        return k
+        return hp.run_device(resident, [g[0] for g in groups], to_host=False)["count"]
 
     def barrier():
         torch.cuda.synchronize()

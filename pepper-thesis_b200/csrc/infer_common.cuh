@@ -59,8 +59,20 @@ uint16_t f2bf(float f) {                 // round-to-nearest-even float -> bf16 
 
 float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
 
+// Gate non-linearities on the MUFU tanh unit (tanh.approx.f32, max relative error 2^-11 -- an order of magnitude
+// below the bf16 rounding of the MMA operands): 1 MUFU op per activation instead of ex2 + rcp.
+// -DPV_EXACT_ACT switches to exp/divide based forms.
+#ifdef PV_EXACT_ACT
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+#else
+__device__ __forceinline__ float tanh_f(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_f(0.5f * x), 0.5f); }
+#endif
+__device__ __forceinline__ void ld16(const float* p, float* v) {     // 64 contiguous, 16-byte aligned bytes
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) { const float4 t = __ldg((const float4*)(p + i)); v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }
+}
 
 template <class Epi>
 int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const tc::GemmShape& g, const Epi& epi,

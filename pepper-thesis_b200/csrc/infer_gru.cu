@@ -31,28 +31,30 @@ struct GruEpilogue {
     int n_blks, S;
     int out_slot[2];
 
-    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr) const {
+    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr, int half) const {
         const float* b = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ch++) {
+        for (int cc = 0; cc < 2; cc++) {
+            const int ch = half * 2 + cc;
             float ar[16], az[16], ah[16], ax[16];
             tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ar);
             tc::tmem_ld16(taddr + 1 * 64 + ch * 16, az);
             tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ah);
             tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ax);
+            float br[16], bz[16], bh[16], bx[16], h[16];
+            ld16(b + 0 * 64 + ch * 16, br); ld16(b + 1 * 64 + ch * 16, bz);
+            ld16(b + 2 * 64 + ch * 16, bh); ld16(b + 3 * 64 + ch * 16, bx);
+            float* hp = h_state + ((size_t)(ok ? row : 0) * 2 + dir) * GH + n_blk * 64 + ch * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(hp + i); h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w; }
             tc::tmem_ld_wait();
             if (ok) {
-                float* hp = h_state + ((size_t)row * 2 + dir) * GH + n_blk * 64 + ch * 16;
-                float h[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(hp + i); h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w; }
                 __align__(16) __nv_bfloat16 hb[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const int j = ch * 16 + i;
-                    const float r = sigmoid_f(ar[i] + __ldg(b + 0 * 64 + j));
-                    const float z = sigmoid_f(az[i] + __ldg(b + 1 * 64 + j));
-                    const float n = tanh_f(ax[i] + __ldg(b + 3 * 64 + j) + r * (ah[i] + __ldg(b + 2 * 64 + j)));
+                    const float r = sigmoid_f(ar[i] + br[i]);
+                    const float z = sigmoid_f(az[i] + bz[i]);
+                    const float n = tanh_f(ax[i] + bx[i] + r * (ah[i] + bh[i]));
                     h[i] = (1.f - z) * n + z * h[i];
                     hb[i] = __float2bfloat16_rn(h[i]);
                 }

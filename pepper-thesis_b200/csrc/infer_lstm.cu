@@ -39,34 +39,37 @@ struct LstmEpilogue {
     int out_slot[2];
     int first;                // c_{t-1} == 0
 
-    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr) const {
+    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr, int half) const {
         const float* b = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ch++) {
+        for (int cc = 0; cc < 2; cc++) {
+            const int ch = half * 2 + cc;                      // 16 hidden units per chunk
             float ai[16], af[16], ag[16], ao[16];
             tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ai);
             tc::tmem_ld16(taddr + 1 * 64 + ch * 16, af);
             tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ag);
             tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ao);
+            // global loads issued before the TMEM wait so their latency overlaps it
+            float bi[16], bf[16], bg[16], bo[16], c[16];
+            ld16(b + 0 * 64 + ch * 16, bi); ld16(b + 1 * 64 + ch * 16, bf);
+            ld16(b + 2 * 64 + ch * 16, bg); ld16(b + 3 * 64 + ch * 16, bo);
+            float* cp = c_state + ((size_t)(ok ? row : 0) * 2 + dir) * H + n_blk * 64 + ch * 16;
+            if (first) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) c[i] = 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(cp + i); c[i] = v.x; c[i + 1] = v.y; c[i + 2] = v.z; c[i + 3] = v.w; }
+            }
             tc::tmem_ld_wait();
             if (ok) {
-                float* cp = c_state + ((size_t)row * 2 + dir) * H + n_blk * 64 + ch * 16;
-                float c[16];
-                if (first) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) c[i] = 0.f;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(cp + i); c[i] = v.x; c[i + 1] = v.y; c[i + 2] = v.z; c[i + 3] = v.w; }
-                }
                 __align__(16) __nv_bfloat16 hb[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const int j = ch * 16 + i;
-                    const float ig = sigmoid_f(ai[i] + __ldg(b + 0 * 64 + j));
-                    const float fg = sigmoid_f(af[i] + __ldg(b + 1 * 64 + j));
-                    const float gg = tanh_f(ag[i] + __ldg(b + 2 * 64 + j));
-                    const float og = sigmoid_f(ao[i] + __ldg(b + 3 * 64 + j));
+                    const float ig = sigmoid_f(ai[i] + bi[i]);
+                    const float fg = sigmoid_f(af[i] + bf[i]);
+                    const float gg = tanh_f(ag[i] + bg[i]);
+                    const float og = sigmoid_f(ao[i] + bo[i]);
                     c[i] = fg * c[i] + ig * gg;
                     hb[i] = __float2bfloat16_rn(og * tanh_f(c[i]));
                 }
@@ -85,20 +88,21 @@ struct SeluEpilogue {
     __nv_bfloat16* out;       // [M][ldo]
     int ldo;
 
-    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr) const {
+    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr, int half) const {
         (void)dir;
         const float alpha = 1.6732632423543772f, lambda = 1.0507009873554805f;
 #pragma unroll 1
-        for (int ch = 0; ch < 16; ch++) {
-            float a[16];
+        for (int ch = half * 8; ch < half * 8 + 8; ch++) {
+            float a[16], bb[16];
             tc::tmem_ld16(taddr + ch * 16, a);
+            const int col = n_blk * tc::BLOCK_N + ch * 16;
+            ld16(bias + col, bb);
             tc::tmem_ld_wait();
             if (ok) {
-                const int col = n_blk * tc::BLOCK_N + ch * 16;
                 __align__(16) __nv_bfloat16 hb[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float x = a[i] + __ldg(bias + col + i);
+                    const float x = a[i] + bb[i];
                     hb[i] = __float2bfloat16_rn(lambda * (x > 0.f ? x : alpha * (__expf(x) - 1.f)));
                 }
                 __nv_bfloat16* op = out + (size_t)row * ldo + col;

@@ -8,8 +8,9 @@
 //                           instruction, accumulating into one of two 256-column TMEM stages; tcgen05.commit frees
 //                           the smem stage / publishes the accumulator
 //   warp 2   TMEM allocator (512 columns)
-//   warps 4-7 epilogue      tcgen05.ld (LDTM) 32 lanes x 16 columns per call -> registers -> fused epilogue -> HBM,
-//                           overlapping the next tile's MMAs through the second TMEM stage
+//   warps 4-11 epilogue     tcgen05.ld (LDTM) 32 lanes x 16 columns per call -> registers -> fused epilogue -> HBM,
+//                           overlapping the next tile's MMAs through the second TMEM stage; two warps per TMEM lane
+//                           quarter (warp % 4), each taking half of the tile's columns
 //
 // The A operand is the K-concatenation of up to two tensors (A0 then A1), each addressed through its own 3-D
 // tensor map [rows][slot][channels]: this is how a recurrent step computes  [h_{t-1} | x_t] * [W_hh | W_ih]^T
@@ -31,7 +32,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int W_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;                      // 4 control warps + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -125,8 +126,9 @@ struct GemmShape {
 };
 
 // Epilogue functor interface:
-//   __device__ void operator()(int dir, int n_blk, int row, bool row_ok, uint32_t taddr /* lane base + stage col */)
-// called by the 128 epilogue threads; it must read its 256 accumulator columns with tmem_ld16 + tmem_ld_wait.
+//   __device__ void operator()(int dir, int n_blk, int row, bool row_ok, uint32_t taddr /* lane base + stage col */, int half)
+// called by the 256 epilogue threads (two per accumulator row, half = 0/1); each call reads its half of the 256
+// accumulator columns with tmem_ld16 + tmem_ld_wait.
 
 template <class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -152,7 +154,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -225,7 +227,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             tc_fence_after();
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epi(dir, n_blk, row, row < g.M, taddr);
+            epi(dir, n_blk, row, row < g.M, taddr, (warp - 4) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -84,21 +84,28 @@ def gather_to_rank0(local: Predictions, group=None) -> Optional[Predictions]:
 
 
 class HotPath:
-    """summary + inference for batches of regions on one GPU."""
+    """summary + inference for batches of regions on one GPU.
+
+    Regions are summarised in groups of ``group_regions`` (bounded scratch, H2D of the next group overlaps the
+    kernels of the current one); the int16 windows of consecutive groups are accumulated in HBM and the model runs
+    on full passes of ``infer_batch`` windows, so the tensor-core kernels always see full waves of tiles.
+    """
 
     def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
-                 wrap_int8: bool = True):
+                 wrap_int8: bool = True, infer_batch: int = 8192):
         self.model = model
         self.thr = thresholds
         self.device = torch.device(device)
         self.group_regions = group_regions
         self.cand_per_kbp = candidates_per_kbp
         self.wrap_int8 = wrap_int8
+        self.infer_batch = infer_batch
         self._ws = None
         self._ws_key = None
+        self._acc = None
         self.copy_stream = None
-        self.last_launches = 0
 
+    # ---- summary of one group -----------------------------------------------------------------------------------------
     def _workspace(self, db: dev.DeviceBatch):
         h = db.host
         cap = max(4096, int(db.total_positions / 1000.0 * self.cand_per_kbp))
@@ -109,12 +116,13 @@ class HotPath:
             self._ws_key = grow
         return self._ws
 
-    def run_device(self, db: dev.DeviceBatch, region_offset: int = 0, to_host: bool = True):
-        """One group of regions already in HBM. Returns Predictions (host) or a dict of device tensors."""
+    def summarize(self, db: dev.DeviceBatch):
+        """Summary kernel chain on one group; returns (workspace, K). The one host sync of the pipeline: K sizes the
+        inference launches."""
         while True:
             ws = self._workspace(db)
             dev.summary_regions(db, self.thr, ws)
-            k = int(ws.count.item())                        # the one host sync: inference grid sizes need K
+            k = int(ws.count.item())
             st = ws.status()
             if st & 8:
                 raise RuntimeError("internal inconsistency in the allele event pass")
@@ -122,21 +130,83 @@ class HotPath:
                 self.cand_per_kbp *= 2.0 * max(1.0, k / max(1, ws.capacity))
                 self._ws = None
                 continue
-            break
-        probs, arg = self.model.infer_windows(ws.windows[:k], wrap_int8=self.wrap_int8)
-        # kernels launched: K0 K1 K2 iota + 10 cub sort passes + K3 = 15; prep + 66 steps + 5 MLP + head = 73 per 8192 windows
-        self.last_launches = 15 + 73 * max(1, (k + 8191) // 8192)
+            return ws, k
+
+    # ---- accumulate windows, infer in full passes -----------------------------------------------------------------------
+    class _Run:
+        def __init__(self):
+            self.meta = []          # per group: dict of small device tensors
+            self.probs = []
+            self.arg = []
+            self.n_acc = 0
+            self.total = 0
+
+    def _acc_buffer(self, need, keep=0):
+        if self._acc is None or self._acc.shape[0] < need:
+            new = torch.empty((int(need * 1.25) + 1024, 33, 26), dtype=torch.int16, device=self.device)
+            if keep:
+                new[:keep].copy_(self._acc[:keep])
+            self._acc = new
+        return self._acc
+
+    def _push(self, run, ws, k, region_offset):
+        if k == 0:
+            return
+        acc = self._acc_buffer(run.n_acc + k, keep=run.n_acc)
+        acc[run.n_acc:run.n_acc + k].copy_(ws.windows[:k])
+        run.meta.append(dict(region=ws.region[:k] + region_offset, position=ws.position[:k].clone(),
+                             depth=ws.depth[:k].clone(), frequency=ws.frequency[:k].clone(),
+                             allele=ws.allele[:k].clone(), allele_len=ws.allele_len[:k].clone()))
+        run.n_acc += k
+        run.total += k
+        self._drain(run, final=False)
+
+    def _drain(self, run, final):
+        b = self.infer_batch
+        while run.n_acc >= b or (final and run.n_acc > 0):
+            m = b if run.n_acc >= b else run.n_acc
+            probs, arg = self.model.infer_windows(self._acc[:m], wrap_int8=self.wrap_int8)
+            run.probs.append(probs)
+            run.arg.append(arg)
+            rest = run.n_acc - m
+            if rest:
+                self._acc[:rest].copy_(self._acc[m:m + rest].clone() if rest > m else self._acc[m:m + rest])
+            run.n_acc = rest
+
+    def _finish(self, run, to_host):
+        self._drain(run, final=True)
+        if run.total == 0:
+            return Predictions.empty() if to_host else dict(count=0)
+        cat = {k: torch.cat([m[k] for m in run.meta]) for k in run.meta[0]}
+        probs, arg = torch.cat(run.probs), torch.cat(run.arg)
         if not to_host:
-            return dict(count=k, region=ws.region[:k] + region_offset, position=ws.position[:k], depth=ws.depth[:k],
-                        frequency=ws.frequency[:k], allele=ws.allele[:k], allele_len=ws.allele_len[:k], probs=probs,
-                        genotype=arg)
-        return Predictions((ws.region[:k] + region_offset).cpu().numpy(), ws.position[:k].cpu().numpy(),
-                           ws.depth[:k].cpu().numpy(), ws.frequency[:k].cpu().numpy(), ws.allele[:k].cpu().numpy(),
-                           ws.allele_len[:k].cpu().numpy(), probs.cpu().numpy(), arg.cpu().numpy())
+            return dict(count=run.total, probs=probs, genotype=arg, **cat)
+        return Predictions(cat["region"].cpu().numpy(), cat["position"].cpu().numpy(), cat["depth"].cpu().numpy(),
+                           cat["frequency"].cpu().numpy(), cat["allele"].cpu().numpy(), cat["allele_len"].cpu().numpy(),
+                           probs.cpu().numpy(), arg.cpu().numpy())
+
+    # ---- public entry points --------------------------------------------------------------------------------------------
+    def run_device(self, dbs, region_offsets=None, to_host: bool = True):
+        """Groups of regions already resident in HBM (one DeviceBatch or a list of them)."""
+        if isinstance(dbs, dev.DeviceBatch):
+            dbs = [dbs]
+        if region_offsets is None:
+            region_offsets, o = [], 0
+            for d in dbs:
+                region_offsets.append(o)
+                o += d.host.n_regions
+        elif isinstance(region_offsets, int):
+            region_offsets = [region_offsets]
+        run = HotPath._Run()
+        self._acc_buffer(self.infer_batch * 2)
+        for d, off in zip(dbs, region_offsets):
+            ws, k = self.summarize(d)
+            self._push(run, ws, k, off)
+        return self._finish(run, to_host)
 
     def run_host(self, batch: ReadBatch, region_offset: int = 0) -> Predictions:
-        """Host buffers in, host results out: regions are processed in groups; the H2D copy of group i+1 (on a side
-        stream, from pinned memory when the batch is pinned) overlaps the kernels of group i."""
+        """Host buffers in, host results out: the H2D copy of group i+1 (side stream, truly asynchronous when the batch
+        lives in pinned memory) overlaps the kernels of group i."""
         n = batch.n_regions
         if n == 0:
             return Predictions.empty()
@@ -152,16 +222,16 @@ class HotPath:
                 ev.record(self.copy_stream)
             return db, ev
 
-        out, launches = [], 0
+        run = HotPath._Run()
+        self._acc_buffer(self.infer_batch * 2)
         nxt = upload(groups[0])
         for i, g in enumerate(groups):
             db, ev = nxt
             main.wait_event(ev)
             if i + 1 < len(groups):
                 nxt = upload(groups[i + 1])
-            out.append(self.run_device(db, region_offset + g[0]))
+            ws, k = self.summarize(db)
+            self._push(run, ws, k, region_offset + g[0])
             for t in db.t.values():
                 t.record_stream(main)
-            launches += self.last_launches
-        self.last_launches = launches
-        return Predictions.concat(out)
+        return self._finish(run, True)
