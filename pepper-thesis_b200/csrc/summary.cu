@@ -24,14 +24,27 @@
 
 namespace {
 
-constexpr int NC = 14;           // packed 32-bit counter words per position
-constexpr int K1_THREADS = 512;
+constexpr int NC = 16;           // packed 32-bit counter words per position
+constexpr int K1_THREADS = 384;
 constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int MAX_PPT = 8;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
-constexpr int LIST_CAP = 1024;   // overlapping-read list entries per round
+constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
+constexpr int P_MAX = 1408;      // 2 CTAs per SM: 16 words x 1408 positions = 88 KB of counters each
+constexpr int UNITS_PER_READ = 8;// a read's ops inside the tile are split into at most this many work units
+constexpr int LIST_CAP = 1024;    // work units per round
+constexpr int UNIT_OPS = 96;     // preferred CIGAR ops per work unit (3 warp steps)
 constexpr int WIN_ELEMS = PV_WINDOW * PV_FEATURES;   // 858
 
-enum { C_REF = 0, C_BASE = 1 /* +0..6 = A C G T I D * */, C_COVSNP = 8, C_INSDEL = 9, C_SNP = 10 /* +0..3 = A C G T */ };
+// Counter words (forward strand in the low 16 bits, reverse strand in the high 16 bits unless noted). The common
+// case -- an aligned base that passes the quality threshold and equals the reference byte -- costs ONE atomic (C_T);
+// everything the reference derives from it (coverage, REFF/REFR, the base's own feature) is reconstructed at flush:
+//   coverage = T_f + T_r + bump      REF = T - SKIP      BASE[class(ref)] = T - DEV      BASE[c != class(ref)] = CLS[c]
+enum { C_T = 0,        // aligned bases with q >= min_snp_baseq
+       C_SKIP = 1,     // ... of which anchor an insert/delete (no REFF/REFR decrement, :381-391)
+       C_DEV = 2,      // ... of which have a base class different from the (valid) reference base's class
+       C_CLS = 3,      // +0..6 = A C G T I D *: explicit class counts (deviating bases, insert/delete anchors, deleted spans)
+       C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count
+       C_INSDEL = 11,  // low: insert_count; high: delete_count
+       C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
 enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_COUNT = 8 };
 enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8 };
 enum { PF_SITE = 1, PF_SNP = 2, PF_INS = 4, PF_DEL = 8, PF_OTHER = 16 };
@@ -157,6 +170,7 @@ __global__ void cigar_prefix_kernel(PvReadBatch b, int32_t* __restrict__ op_ref,
 struct TileCtx {
     uint32_t* cnt;        // [NC][P] shared
     uint8_t* ref_s;       // [P] shared: reference bytes of the tile
+    uint8_t* rcls;        // [P] shared: class 0..3 of the reference base, 0xff when it is not A/C/G/T (any case)
     uint8_t* pflag;       // [P] shared: PF_* of each tile position (phase B onwards)
     int32_t* site_slot;   // [P] shared (aliases cnt after phase B): site index or -1
     int32_t* scratch;     // this warp's [4][32] shared scratch
@@ -183,12 +197,12 @@ __device__ __forceinline__ void record_event(const SumParams& p, int s, int type
     }
 }
 
-// Walks the CIGAR ops of one read that can touch the tile (whole warp).
+// Walks CIGAR ops [k_begin, k_end) of one read (whole warp): one work unit of the tile.
 //   MODE 0: accumulate counters (populate_summary_matrix, :337-566)
 //   MODE 1: record insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and
 //           :507-535, needed only where the site thresholds passed)
 template <int MODE>
-__device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int lane) {
+__device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
     const PvReadBatch& b = p.b;
     const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];   // read start, region-relative
     const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;          // tile, inclusive, region-relative
@@ -202,13 +216,7 @@ __device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int l
     const int32_t* ori_a = p.op_ri + co;
     const uint8_t* quals = b.quals + bo;
     const uint8_t* bases = b.bases + bo;
-
-    // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] with a_k <= min(t_hi + 1, L - 1) (an op that starts
-    // beyond ref_end is never reached, :355) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
-    int k_lo = warp_lower_bound(oref, n_ops, t_lo - rel, lane) - 1;
-    if (k_lo < 0) k_lo = 0;
-    const int64_t a_max = (t_hi + 1 < c.L - 1) ? t_hi + 1 : c.L - 1;
-    const int k_hi = warp_lower_bound(oref, n_ops, a_max - rel + 1, lane);
+    const int k_lo = k_begin, k_hi = k_end;
 
     int32_t* s_pref = c.scratch;            // [33] exclusive prefix of clipped match lengths (uses [0..32])
     int32_t* s_ri0 = c.scratch + 40;        // read index of the first clipped base
@@ -256,9 +264,9 @@ __device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int l
                         for (int64_t i = ori - 1; i < ori - 1 + n && i < read_len; i++) bq += quals[i];   // :448-450
                         const bool pass = (double)bq >= p.t.min_indel_baseq * (double)n;
                         if (MODE == 0) {
-                            if (pass && (int)quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COVSNP * c.P + ol], 1u);   // :453-454
+                            if (pass && (int)quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
                             if (1 + elen <= 61 && pass) {                        // :461-464
-                                if (valid_ref(c.ref_s[ol])) atomicAdd(&c.cnt[(C_BASE + 4) * c.P + ol], strand_inc);
+                                if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], strand_inc);
                                 atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
                             }
                         } else if (1 + elen <= 61 && pass) {
@@ -273,7 +281,7 @@ __device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int l
                     int64_t elen = (int64_t)len + 1;                             // substr truncation, :500
                     if (o + elen > c.ref_len) elen = c.ref_len - o;
                     if (MODE == 0) {
-                        if (valid_ref(c.ref_s[ol])) atomicAdd(&c.cnt[(C_BASE + 5) * c.P + ol], strand_inc);   // :497
+                        if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 5) * c.P + ol], strand_inc);   // :497
                         if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);                 // :511-512
                     } else {
                         const int s = c.site_slot[ol];
@@ -286,7 +294,7 @@ __device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int l
                     int64_t i_hi = t_hi - a; if (i_hi > len - 1) i_hi = len - 1;
                     for (int64_t i = i_lo; i <= i_hi; i++) {
                         const int pl = (int)(a + i - t_lo);
-                        if (valid_ref(c.ref_s[pl])) atomicAdd(&c.cnt[(C_BASE + 6) * c.P + pl], strand_inc);
+                        if (c.rcls[pl] != 0xff) atomicAdd(&c.cnt[(C_CLS + 6) * c.P + pl], strand_inc);
                     }
                 }
             }
@@ -302,25 +310,32 @@ __device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int l
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (total > 0) {
+                // ops that contribute bases are compacted into the scratch arrays; item j of the flattened sequence
+                // belongs to compacted op  s(j) = #{ops whose first item <= j} - 1, evaluated per block of 32 items
+                // with one warp OR-reduction instead of a per-lane search
+                const int pref = incl - m_cnt;                              // first flattened item of this lane's op
+                const unsigned nz = __ballot_sync(0xffffffffu, m_cnt > 0);
+                const int rank = __popc(nz & ((1u << lane) - 1u));
                 __syncwarp();
-                s_pref[lane] = incl - m_cnt;
-                if (lane == 31) s_pref[32] = total;
-                s_ri0[lane] = m_ri0; s_p0[lane] = m_p0; s_last[lane] = m_last;
+                if (m_cnt > 0) { s_pref[rank] = pref; s_ri0[rank] = m_ri0; s_p0[rank] = m_p0; s_last[rank] = m_last; }
                 __syncwarp();
+                int s_first = 0;                                            // compacted op that holds item j0
                 for (int j0 = 0; j0 < total; j0 += 128) {
                     int idx[4], pl[4]; bool skip_ref[4], act[4];
                     uint8_t bb[4], qq[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int j = j0 + u * 32 + lane;
+                        const int jb = j0 + u * 32;
+                        const int sl = pref - jb;                           // ops starting inside (jb, jb + 32]
+                        const unsigned bit = (m_cnt > 0 && sl >= 1 && sl <= 32) ? (1u << (sl - 1)) : 0u;
+                        const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
+                        const int sidx = s_first + __popc(mask & ((1u << lane) - 1u));
+                        s_first += __popc(mask);
+                        const int j = jb + lane;
                         act[u] = j < total;
-                        int s = 0;
                         if (act[u]) {
-#pragma unroll
-                            for (int step = 16; step >= 1; step >>= 1)
-                                if (s_pref[s + step] <= j) s += step;
-                            const int i = j - s_pref[s];
-                            idx[u] = s_ri0[s] + i; pl[u] = s_p0[s] + i; skip_ref[u] = (i == s_last[s]);
+                            const int i = j - s_pref[sidx];
+                            idx[u] = s_ri0[sidx] + i; pl[u] = s_p0[sidx] + i; skip_ref[u] = (i == s_last[sidx]);
                         } else { idx[u] = 0; pl[u] = 0; skip_ref[u] = false; }
                     }
 #pragma unroll
@@ -332,11 +347,18 @@ __device__ void walk_read(const SumParams& p, const TileCtx& c, int64_t r, int l
                     for (int u = 0; u < 4; u++) {
                         if (act[u] && (int)qq[u] >= p.qthr) {                    // :378
                             const uint8_t rb = c.ref_s[pl[u]];
-                            const bool mism = rb != bb[u];                      // raw compare, :394
-                            atomicAdd(&c.cnt[C_COVSNP * c.P + pl[u]], mism ? 0x10001u : 1u);   // coverage (+ snp_count)
-                            if (!skip_ref[u]) atomicAdd(&c.cnt[C_REF * c.P + pl[u]], strand_inc);
-                            if (valid_ref(rb)) atomicAdd(&c.cnt[(C_BASE + base_class(bb[u])) * c.P + pl[u]], strand_inc);
-                            if (mism) {
+                            atomicAdd(&c.cnt[C_T * c.P + pl[u]], strand_inc);    // coverage, REF and the base's own class
+                            if (skip_ref[u]) atomicAdd(&c.cnt[C_SKIP * c.P + pl[u]], strand_inc);
+                            if (rb != bb[u]) {                                  // raw compare, :394 (rare path)
+                                atomicAdd(&c.cnt[C_COV2 * c.P + pl[u]], 0x10000u);   // snp_count
+                                const int rc = c.rcls[pl[u]];
+                                if (rc != 0xff) {
+                                    const int cb = base_class(bb[u]);
+                                    if (cb != rc) {
+                                        atomicAdd(&c.cnt[C_DEV * c.P + pl[u]], strand_inc);
+                                        atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl[u]], strand_inc);
+                                    }
+                                }
                                 const int code = acgt_code(bb[u]);
                                 if (code >= 0) atomicAdd(&c.cnt[(C_SNP + code) * c.P + pl[u]], strand_inc);
                             }
@@ -376,23 +398,70 @@ __device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, i
     record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
 }
 
+// first k in [0, n) with a[k] >= key (n if none); one thread
+__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int n, int64_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+struct WorkUnit { int32_t read; int32_t k_begin; int32_t k_end; };   // read index relative to the round's first read
+
+// Builds the tile's work list (a thread per read finds the read's op range inside the tile and cuts it into units of
+// about UNIT_OPS ops) and lets the warps pull units from it.
 template <int MODE>
-__device__ void for_each_overlapping_read(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next) {
+__device__ void for_each_unit(const SumParams& p, const TileCtx& c, WorkUnit* s_list, int* s_n, int* s_next) {
     const PvReadBatch& b = p.b;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
     const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;
-    for (int64_t base = rb; base < re; base += LIST_CAP) {
+    // how many reads touch the tile decides the granularity: normally ONE round with several units per read
+    if (tid == 0) *s_n = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int64_t r = rb + tid; r < re; r += blockDim.x) {
+        if (b.read_mapq[r] == 0) continue;
+        const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
+        if (rel - 1 > t_hi || rel + (int64_t)p.read_span[r] - 1 < t_lo) continue;
+        mine++;
+    }
+    if (mine) atomicAdd(s_n, mine);
+    __syncthreads();
+    const int n_ov = *s_n;
+    __syncthreads();
+    const bool single = n_ov <= LIST_CAP;
+    int budget = 1;
+    if (single && n_ov > 0) { budget = LIST_CAP / n_ov; if (budget > UNITS_PER_READ) budget = UNITS_PER_READ; }
+    const int64_t round_reads = single ? (re - rb > 0 ? re - rb : 1) : LIST_CAP;
+    for (int64_t base = rb; base < re; base += round_reads) {
         if (tid == 0) { *s_n = 0; *s_next = 0; }
         __syncthreads();
-        const int64_t end = base + LIST_CAP < re ? base + LIST_CAP : re;
+        const int64_t end = base + round_reads < re ? base + round_reads : re;
         for (int64_t r = base + tid; r < end; r += blockDim.x) {
             if (b.read_mapq[r] == 0) continue;                                   // :619
             const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
             const int64_t span = p.read_span[r];
             // touched positions: aligned/deleted [rel, rel+span-1] and insert/delete anchors [rel-1, rel+span-1]
             if (rel - 1 > t_hi || rel + span - 1 < t_lo) continue;
-            s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
+            // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] <= min(t_hi + 1, L - 1) (an op that starts beyond
+            // ref_end is never reached, :355) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
+            const int32_t* oref = p.op_ref + b.read_cigar_off[r];
+            const int n_ops = b.read_n_ops[r];
+            int k_lo = lower_bound_i32(oref, n_ops, t_lo - rel) - 1;
+            if (k_lo < 0) k_lo = 0;
+            const int64_t a_max = (t_hi + 1 < c.L - 1) ? t_hi + 1 : c.L - 1;
+            const int k_hi = lower_bound_i32(oref, n_ops, a_max - rel + 1);
+            const int n_k = k_hi - k_lo;
+            if (n_k <= 0) continue;
+            int per = UNIT_OPS;
+            if ((n_k + per - 1) / per > budget) per = ((n_k + budget - 1) / budget + 31) & ~31;
+            const int n_units = (n_k + per - 1) / per;
+            const int at = atomicAdd(s_n, n_units);
+            for (int u = 0; u < n_units; u++) {
+                WorkUnit w; w.read = (int32_t)(r - base); w.k_begin = k_lo + u * per;
+                w.k_end = (k_lo + (u + 1) * per < k_hi) ? k_lo + (u + 1) * per : k_hi;
+                s_list[at + u] = w;
+            }
         }
         __syncthreads();
         const int n = *s_n;
@@ -401,15 +470,16 @@ __device__ void for_each_overlapping_read(const SumParams& p, const TileCtx& c, 
             if (lane == 0) i = atomicAdd(s_next, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
-            walk_read<MODE>(p, c, base + s_list[i], lane);
+            const WorkUnit w = s_list[i];
+            walk_unit<MODE>(p, c, base + w.read, w.k_begin, w.k_end, lane);
         }
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumParams p) {
+__global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int32_t s_list[LIST_CAP];
+    __shared__ WorkUnit s_list[LIST_CAP];
     __shared__ int s_n, s_next, s_any_events, s_any_other;
 
     const PvReadBatch& b = p.b;
@@ -423,6 +493,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumPar
     c.scratch = (int32_t*)(smem + (size_t)NC * P * 4) + warp * 136;
     c.ref_s = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4;
     c.pflag = c.ref_s + P;
+    c.rcls = c.pflag + P;
     c.region = p.tile_region[blockIdx.x];
     c.t_lo = p.tile_start[blockIdx.x];
     c.L = b.region_ref_end[c.region] - b.region_ref_start[c.region] + 1;
@@ -433,14 +504,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumPar
 
     for (int i = tid; i < NC * P; i += K1_THREADS) c.cnt[i] = 0;
     for (int i = tid; i < P; i += K1_THREADS) {
-        c.ref_s[i] = i < c.n_valid ? b.ref[c.ref_off + c.t_lo + i] : (uint8_t)'N';
+        const uint8_t rbyte = i < c.n_valid ? b.ref[c.ref_off + c.t_lo + i] : (uint8_t)'N';
+        c.ref_s[i] = rbyte;
+        c.rcls[i] = valid_ref(rbyte) ? (uint8_t)base_class(rbyte) : (uint8_t)0xff;
         c.pflag[i] = 0;
     }
     if (tid == 0) { s_any_events = 0; s_any_other = 0; }
     __syncthreads();
 
     // ---- phase A: accumulate -----------------------------------------------------------------------------------
-    for_each_overlapping_read<0>(p, c, s_list, &s_n, &s_next);
+    for_each_unit<0>(p, c, s_list, &s_n, &s_next);
 
     // ---- phase B: image rows, site thresholds ---------------------------------------------------------------------
     int my_site[MAX_PPT];
@@ -457,12 +530,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumPar
 #pragma unroll
             for (int f = 0; f < PV_FEATURES; f++) row[f] = 0;
             row[0] = ref_value(rb);                                             // :174-191
-            row[4] = -(int)(w[C_REF] & 0xffffu);
-            row[15] = -(int)(w[C_REF] >> 16);
+            const int tf = (int)(w[C_T] & 0xffffu), tr = (int)(w[C_T] >> 16);
+            row[4] = -(tf - (int)(w[C_SKIP] & 0xffffu));                         // REFF = T - SKIP
+            row[15] = -(tr - (int)(w[C_SKIP] >> 16));
+            const int rc = c.rcls[i];
 #pragma unroll
             for (int k = 0; k < 7; k++) {
-                row[8 + k] = -(int)(w[C_BASE + k] & 0xffffu);
-                row[19 + k] = -(int)(w[C_BASE + k] >> 16);
+                int f = (int)(w[C_CLS + k] & 0xffffu), r = (int)(w[C_CLS + k] >> 16);
+                if (k == rc) { f += tf - (int)(w[C_DEV] & 0xffffu); r += tr - (int)(w[C_DEV] >> 16); }   // BASE[class(ref)] = T - DEV
+                row[8 + k] = rc == 0xff ? 0 : -f;
+                row[19 + k] = rc == 0xff ? 0 : -r;
             }
 #pragma unroll
             for (int f = 11; f < 25; f++) row[f] = row[f] < -125 ? -125 : row[f];   // :648-653 (all values <= 0 here)
@@ -471,7 +548,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumPar
             for (int f = 0; f < PV_FEATURES; f += 2)
                 dst[f >> 1] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
 
-            const int cov = (int)(w[C_COVSNP] & 0xffffu), snp = (int)(w[C_COVSNP] >> 16);
+            const int cov = tf + tr + (int)(w[C_COV2] & 0xffffu), snp = (int)(w[C_COV2] >> 16);
             const int ins = (int)(w[C_INSDEL] & 0xffffu), del = (int)(w[C_INSDEL] >> 16);
             const double cv = (double)cov > 1.0 ? (double)cov : 1.0;             // :635-637
             const double sf = (double)snp / cv, inf = (double)ins / cv, df = (double)del / cv;
@@ -523,7 +600,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) pileup_tile_kernel(const SumPar
     }
     __threadfence();      // site records (n_ev, ev_off) are read back through global memory by record_event
     __syncthreads();
-    for_each_overlapping_read<1>(p, c, s_list, &s_n, &s_next);
+    for_each_unit<1>(p, c, s_list, &s_n, &s_next);
     if (s_any_other) {
         const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
         for (int i = 0; i < c.n_valid; i++) {
@@ -691,12 +768,12 @@ struct Plan {
 int choose_tile(int64_t total_positions, int32_t n_regions) {
     // large tiles amortise the per-(tile, read) set-up; small batches need enough CTAs to cover the 148 SMs
     const int sms = 148;
-    int P = 2048;
-    while (P > 512 && (total_positions / P + n_regions) < 2 * sms) P >>= 1;
+    int P = P_MAX;
+    while (P > 352 && (total_positions / P + n_regions) < 4 * sms) P >>= 1;
     return P;
 }
 
-size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4 + 2 * (size_t)P + 16; }
+size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4 + 3 * (size_t)P + 16; }
 
 Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
     Plan pl;
