@@ -171,6 +171,7 @@ struct TileCtx {
     uint32_t* cnt;        // [NC][P] shared
     uint8_t* ref_s;       // [P] shared: reference bytes of the tile
     uint8_t* rcls;        // [P] shared: class 0..3 of the reference base, 0xff when it is not A/C/G/T (any case)
+    uint8_t* lut;         // [256] shared: base byte -> class 0..6 | 8 if the byte is an upper-case A/C/G/T
     uint8_t* pflag;       // [P] shared: PF_* of each tile position (phase B onwards)
     int32_t* site_slot;   // [P] shared (aliases cnt after phase B): site index or -1
     int32_t* scratch;     // this warp's [4][32] shared scratch
@@ -204,8 +205,11 @@ __device__ __forceinline__ void record_event(const SumParams& p, int s, int type
 template <int MODE>
 __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
     const PvReadBatch& b = p.b;
-    const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];   // read start, region-relative
-    const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;          // tile, inclusive, region-relative
+    // everything below is in TILE-LOCAL int32 coordinates: position 0 = first position of the tile
+    const int64_t rel_t = b.read_pos[r] - b.region_ref_start[c.region] - c.t_lo;   // read start relative to the tile
+    const int nv = c.n_valid;                                                     // tile = [0, nv)
+    const int64_t l_end64 = c.L - 1 - c.t_lo;                                     // last region position, tile-local
+    const int l_end = l_end64 > (1 << 30) ? (1 << 30) : (int)l_end64;
     const int64_t co = b.read_cigar_off[r];
     const int n_ops = b.read_n_ops[r];
     const int read_len = b.read_len[r];
@@ -229,39 +233,42 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
         const uint32_t w = have ? b.cigar[co + k] : 0u;
         const int op = have ? (int)(w & 15u) : 15;
         const int len = (int)(w >> 4);
-        const int64_t a = have ? rel + (int64_t)oref[k] : 0;
+        int64_t a64 = have ? rel_t + (int64_t)oref[k] : 0;                        // op start, tile-local
+        if (a64 > (1 << 30)) a64 = (1 << 30);
+        if (a64 < -(1 << 30)) a64 = -(1 << 30);
+        const int a = (int)a64;
         const int ori = have ? ori_a[k] : 0;
         int m_cnt = 0, m_ri0 = 0, m_p0 = 0, m_last = -1;
 
-        if (have && a <= c.L - 1) {
+        if (have && a <= l_end) {                                               // an op starting beyond ref_end is never reached (:355)
             if (is_match_op(op)) {
                 if (MODE == 0) {
-                    int64_t i_lo = t_lo - a; if (i_lo < 0) i_lo = 0;
-                    int64_t i_hi = t_hi - a; if (i_hi > len - 1) i_hi = len - 1;
-                    if (i_hi > (int64_t)read_len - 1 - ori) i_hi = (int64_t)read_len - 1 - ori;
+                    const int i_lo = a < 0 ? -a : 0;
+                    int i_hi = nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
+                    if (i_hi > read_len - 1 - ori) i_hi = read_len - 1 - ori;
                     if (i_hi >= i_lo) {
-                        m_cnt = (int)(i_hi - i_lo + 1);
-                        m_ri0 = ori + (int)i_lo;
-                        m_p0 = (int)(a + i_lo - t_lo);
+                        m_cnt = i_hi - i_lo + 1;
+                        m_ri0 = ori + i_lo;
+                        m_p0 = a + i_lo;
                         if (k != n_ops - 1) {                                   // anchor rule, :381-391
                             const int nop = (int)(b.cigar[co + k + 1] & 15u);
-                            if (nop == 1 || nop == 2) m_last = (int)((int64_t)len - 1 - i_lo);
+                            if (nop == 1 || nop == 2) m_last = len - 1 - i_lo;
                         }
                     }
                 }
             } else if (op == 1) {                                               // IN, :431-490
-                const int64_t o = a - 1;
-                if (o >= t_lo && o <= t_hi && ori >= 1 && ori - 1 < read_len) {
-                    const int ol = (int)(o - t_lo);
+                const int ol = a - 1;
+                if (ol >= 0 && ol < nv && ori >= 1 && ori - 1 < read_len) {
                     bool go = true;
                     int s = -1;
                     if (MODE == 1) { s = c.site_slot[ol]; go = s >= 0 && (c.pflag[ol] & PF_INS); }
                     if (go) {
-                        const int64_t n = (int64_t)len + 1;                      // :442
-                        int64_t elen = n;                                        // substr truncation, :439
-                        if ((int64_t)ori - 1 + elen > read_len) elen = (int64_t)read_len - (ori - 1);
+                        const int n = len + 1;                                   // :442
+                        int elen = n;                                            // substr truncation, :439
+                        if (elen > read_len - (ori - 1)) elen = read_len - (ori - 1);
                         int64_t bq = 0;
-                        for (int64_t i = ori - 1; i < ori - 1 + n && i < read_len; i++) bq += quals[i];   // :448-450
+                        const int i_end = ori - 1 + n < read_len ? ori - 1 + n : read_len;
+                        for (int i = ori - 1; i < i_end; i++) bq += quals[i];     // :448-450
                         const bool pass = (double)bq >= p.t.min_indel_baseq * (double)n;
                         if (MODE == 0) {
                             if (pass && (int)quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
@@ -270,30 +277,30 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
                                 atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
                             }
                         } else if (1 + elen <= 61 && pass) {
-                            record_event(p, s, 2, (int)rev, (int)elen, bo + ori - 1);
+                            record_event(p, s, 2, (int)rev, elen, bo + ori - 1);
                         }
                     }
                 }
             } else if (op == 2) {                                               // DEL, :491-555
-                const int64_t o = a - 1;
-                if (o >= t_lo && o <= t_hi) {
-                    const int ol = (int)(o - t_lo);
-                    int64_t elen = (int64_t)len + 1;                             // substr truncation, :500
-                    if (o + elen > c.ref_len) elen = c.ref_len - o;
+                const int ol = a - 1;
+                if (ol >= 0 && ol < nv) {
+                    const int64_t rem = c.ref_len - c.t_lo - ol;                 // reference bytes from the anchor on
+                    int elen = len + 1;                                          // substr truncation, :500
+                    if ((int64_t)elen > rem) elen = (int)rem;
                     if (MODE == 0) {
                         if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 5) * c.P + ol], strand_inc);   // :497
-                        if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);                 // :511-512
+                        if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);            // :511-512
                     } else {
                         const int s = c.site_slot[ol];
                         if (s >= 0 && (c.pflag[ol] & PF_DEL) && 1 + elen <= 61)
-                            record_event(p, s, 3, (int)rev, (int)elen, c.ref_off + o);
+                            record_event(p, s, 3, (int)rev, elen, c.ref_off + c.t_lo + ol);
                     }
                 }
                 if (MODE == 0) {                                                 // :542-552
-                    int64_t i_lo = t_lo - a; if (i_lo < 0) i_lo = 0;
-                    int64_t i_hi = t_hi - a; if (i_hi > len - 1) i_hi = len - 1;
-                    for (int64_t i = i_lo; i <= i_hi; i++) {
-                        const int pl = (int)(a + i - t_lo);
+                    const int i_lo = a < 0 ? -a : 0;
+                    int i_hi = nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
+                    for (int i = i_lo; i <= i_hi; i++) {
+                        const int pl = a + i;
                         if (c.rcls[pl] != 0xff) atomicAdd(&c.cnt[(C_CLS + 6) * c.P + pl], strand_inc);
                     }
                 }
@@ -352,15 +359,13 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
                             if (rb != bb[u]) {                                  // raw compare, :394 (rare path)
                                 atomicAdd(&c.cnt[C_COV2 * c.P + pl[u]], 0x10000u);   // snp_count
                                 const int rc = c.rcls[pl[u]];
-                                if (rc != 0xff) {
-                                    const int cb = base_class(bb[u]);
-                                    if (cb != rc) {
-                                        atomicAdd(&c.cnt[C_DEV * c.P + pl[u]], strand_inc);
-                                        atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl[u]], strand_inc);
-                                    }
+                                const int lu = c.lut[bb[u]];                    // class | dense-allele flag << 3
+                                const int cb = lu & 7;
+                                if (rc != 0xff && cb != rc) {
+                                    atomicAdd(&c.cnt[C_DEV * c.P + pl[u]], strand_inc);
+                                    atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl[u]], strand_inc);
                                 }
-                                const int code = acgt_code(bb[u]);
-                                if (code >= 0) atomicAdd(&c.cnt[(C_SNP + code) * c.P + pl[u]], strand_inc);
+                                if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl[u]], strand_inc);
                             }
                         }
                     }
@@ -494,6 +499,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
     c.ref_s = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4;
     c.pflag = c.ref_s + P;
     c.rcls = c.pflag + P;
+    c.lut = c.rcls + P;
+    if (tid < 256) c.lut[tid] = (uint8_t)(base_class((uint8_t)tid) | (acgt_code((uint8_t)tid) >= 0 ? 8 : 0));
     c.region = p.tile_region[blockIdx.x];
     c.t_lo = p.tile_start[blockIdx.x];
     c.L = b.region_ref_end[c.region] - b.region_ref_start[c.region] + 1;
@@ -773,7 +780,7 @@ int choose_tile(int64_t total_positions, int32_t n_regions) {
     return P;
 }
 
-size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4 + 3 * (size_t)P + 16; }
+size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4 + 3 * (size_t)P + 256 + 16; }
 
 Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
     Plan pl;
