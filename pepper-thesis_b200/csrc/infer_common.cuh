@@ -78,13 +78,14 @@ template <class Epi>
 int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const tc::GemmShape& g, const Epi& epi,
                 int sms, cudaStream_t st) {
     static bool attr_done = false;
+    constexpr int smem = tc::smem_bytes<Epi>();
     if (!attr_done) {
-        PV_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        PV_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
     const int tiles = g.m_blks * g.n_blks * g.dirs;
     const int grid = tiles < sms ? tiles : sms;
-    tc::gemm_kernel<Epi><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a0, a1, w, g, epi);
+    tc::gemm_kernel<Epi><<<grid, tc::THREADS, smem, st>>>(a0, a1, w, g, epi);
     PV_CUDA_CHECK(cudaGetLastError());
     return PV_OK;
 }

@@ -25,44 +25,73 @@ constexpr int GDEC_K = GH + GC;     // 384
 constexpr int GCLS = 5;
 
 struct GruEpilogue {
+    static constexpr int kStages = 3;
+    static constexpr int kBiasBytes = 2 * 2 * 4 * 64 * 4;                  // whole layer: [dir][n_blk][gate][64] fp32
+    static constexpr int kStateBytes = tc::EPI_THREADS * 2 * 64;
+    static constexpr int kSmemBytes = kBiasBytes + 2 * kStateBytes;
+
     const float* bias;        // [dirs][n_blks][4][64]: b_ir+b_hr, b_iz+b_hz, b_hn, b_in
     float* h_state;           // [M][2][GH] fp32, read as h_{t-1}, overwritten with h_t
     __nv_bfloat16* out;       // [M][S][GC]
     int n_blks, S;
     int out_slot[2];
 
-    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr, int half) const {
-        const float* b = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+    __device__ void setup(uint8_t* scratch, int te) const {
+        float4* sb = (float4*)scratch;
+        const float4* gb = (const float4*)bias;
+        for (int i = te; i < kBiasBytes / 16; i += tc::EPI_THREADS) sb[i] = __ldg(gb + i);
+    }
+    __device__ void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te) const {
+        if (!ok) return;
+        uint8_t* dst = scratch + kBiasBytes + buf * kStateBytes;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const float* hp = h_state + ((size_t)row * 2 + dir) * GH + n_blk * 64 + (half * 2 + cc) * 16;
+#pragma unroll
+            for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, hp + j * 4);
+        }
+    }
+    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te) const {
+        const float* sb = (const float*)scratch + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+        const uint8_t* hst = scratch + kBiasBytes + buf * kStateBytes;
 #pragma unroll 1
         for (int cc = 0; cc < 2; cc++) {
             const int ch = half * 2 + cc;
-            float ar[16], az[16], ah[16], ax[16];
+            float ar[16], az[16], ah[16], ax[16], h[16];
             tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ar);
             tc::tmem_ld16(taddr + 1 * 64 + ch * 16, az);
             tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ah);
             tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ax);
-            float br[16], bz[16], bh[16], bx[16], h[16];
-            ld16(b + 0 * 64 + ch * 16, br); ld16(b + 1 * 64 + ch * 16, bz);
-            ld16(b + 2 * 64 + ch * 16, bh); ld16(b + 3 * 64 + ch * 16, bx);
-            float* hp = h_state + ((size_t)(ok ? row : 0) * 2 + dir) * GH + n_blk * 64 + ch * 16;
+            if (ok) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(hp + i); h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w; }
+                for (int j = 0; j < 4; j++) {
+                    const float4 v = *(const float4*)(hst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16);
+                    h[4 * j] = v.x; h[4 * j + 1] = v.y; h[4 * j + 2] = v.z; h[4 * j + 3] = v.w;
+                }
+            }
             tc::tmem_ld_wait();
             if (ok) {
-                __align__(16) __nv_bfloat16 hb[16];
+                const float* br = sb + 0 * 64 + ch * 16; const float* bz = sb + 1 * 64 + ch * 16;
+                const float* bh = sb + 2 * 64 + ch * 16; const float* bx = sb + 3 * 64 + ch * 16;
+                uint32_t hp[8];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float r = sigmoid_f(ar[i] + br[i]);
-                    const float z = sigmoid_f(az[i] + bz[i]);
-                    const float n = tanh_f(ax[i] + bx[i] + r * (ah[i] + bh[i]));
-                    h[i] = (1.f - z) * n + z * h[i];
-                    hb[i] = __float2bfloat16_rn(h[i]);
+                for (int i = 0; i < 16; i += 2) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const float r = sigmoid_f(ar[i + e] + br[i + e]);
+                        const float z = sigmoid_f(az[i + e] + bz[i + e]);
+                        const float n = tanh_f(ax[i + e] + bx[i + e] + r * (ah[i + e] + bh[i + e]));
+                        h[i + e] = (1.f - z) * n + z * h[i + e];
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(h[i], h[i + 1]);
+                    hp[i >> 1] = *(const uint32_t*)&h2;
                 }
+                float* hg = h_state + ((size_t)row * 2 + dir) * GH + n_blk * 64 + ch * 16;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) *(float4*)(hp + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
-                __nv_bfloat16* op = out + ((size_t)row * S + out_slot[dir]) * GC + dir * GH + n_blk * 64 + ch * 16;
-                *(uint4*)op = *(const uint4*)hb;
-                *(uint4*)(op + 8) = *(const uint4*)(hb + 8);
+                for (int i = 0; i < 16; i += 4) *(float4*)(hg + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+                __nv_bfloat16* op = out + ((size_t)row * S + (dir ? out_slot[1] : out_slot[0])) * GC + dir * GH + n_blk * 64 + ch * 16;
+                *(uint4*)op = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *(uint4*)(op + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
             }
         }
     }

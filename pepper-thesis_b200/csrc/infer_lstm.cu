@@ -15,6 +15,7 @@
 #include "tc_gemm.cuh"
 #include "infer_common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -32,63 +33,99 @@ constexpr int FLAT = T * C;         // 16896
 
 // ---- epilogues ---------------------------------------------------------------------------------------------
 struct LstmEpilogue {
+    static constexpr int kStages = 3;
+    static constexpr int kBiasBytes = 2 * 4 * 4 * 64 * 4;                  // whole layer: [dir][n_blk][gate][64] fp32
+    static constexpr int kStateBytes = tc::EPI_THREADS * 2 * 64;           // one tile: 256 threads x 2 chunks x 16 fp32
+    static constexpr int kSmemBytes = kBiasBytes + 2 * kStateBytes;        // biases + double-buffered c tile
+
     const float* bias;        // [dirs][n_blks][4 gates][64]  (b_ih + b_hh, tile order)
     float* c_state;           // [M][2][H] fp32
     __nv_bfloat16* out;       // [M][S][C]
     int n_blks;
     int out_slot[2];
     int first;                // c_{t-1} == 0
+    int debug;                // PV_DEBUG_EPI: 1 = skip the cell math (timing experiments only)
 
-    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr, int half) const {
-        const float* b = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+    __device__ void setup(uint8_t* scratch, int te) const {
+        float4* sb = (float4*)scratch;
+        const float4* gb = (const float4*)bias;
+        for (int i = te; i < kBiasBytes / 16; i += tc::EPI_THREADS) sb[i] = __ldg(gb + i);
+    }
+    // thread te keeps its 2 x 64 bytes of a tile at [(cc*4 + j) * 256 + te] 16-byte slots: conflict-free both ways
+    __device__ void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te) const {
+        if (first || !ok) return;
+        uint8_t* dst = scratch + kBiasBytes + buf * kStateBytes;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const float* cp = c_state + ((size_t)row * 2 + dir) * H + n_blk * 64 + (half * 2 + cc) * 16;
+#pragma unroll
+            for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, cp + j * 4);
+        }
+    }
+    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te) const {
+        const float* sb = (const float*)scratch + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+        const uint8_t* cst = scratch + kBiasBytes + buf * kStateBytes;
 #pragma unroll 1
         for (int cc = 0; cc < 2; cc++) {
             const int ch = half * 2 + cc;                      // 16 hidden units per chunk
-            float ai[16], af[16], ag[16], ao[16];
+            float ai[16], af[16], ag[16], ao[16], c[16];
             tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ai);
             tc::tmem_ld16(taddr + 1 * 64 + ch * 16, af);
             tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ag);
             tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ao);
-            // global loads issued before the TMEM wait so their latency overlaps it
-            float bi[16], bf[16], bg[16], bo[16], c[16];
-            ld16(b + 0 * 64 + ch * 16, bi); ld16(b + 1 * 64 + ch * 16, bf);
-            ld16(b + 2 * 64 + ch * 16, bg); ld16(b + 3 * 64 + ch * 16, bo);
-            float* cp = c_state + ((size_t)(ok ? row : 0) * 2 + dir) * H + n_blk * 64 + ch * 16;
-            if (first) {
+            if (first || !ok) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) c[i] = 0.f;
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) { const float4 v = *(const float4*)(cp + i); c[i] = v.x; c[i + 1] = v.y; c[i + 2] = v.z; c[i + 3] = v.w; }
+                for (int j = 0; j < 4; j++) {
+                    const float4 v = *(const float4*)(cst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16);
+                    c[4 * j] = v.x; c[4 * j + 1] = v.y; c[4 * j + 2] = v.z; c[4 * j + 3] = v.w;
+                }
             }
             tc::tmem_ld_wait();
+            if (debug) continue;
             if (ok) {
-                __align__(16) __nv_bfloat16 hb[16];
+                const float* bi = sb + 0 * 64 + ch * 16; const float* bf = sb + 1 * 64 + ch * 16;
+                const float* bg = sb + 2 * 64 + ch * 16; const float* bo = sb + 3 * 64 + ch * 16;
+                uint32_t hp[8];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float ig = sigmoid_f(ai[i] + bi[i]);
-                    const float fg = sigmoid_f(af[i] + bf[i]);
-                    const float gg = tanh_f(ag[i] + bg[i]);
-                    const float og = sigmoid_f(ao[i] + bo[i]);
-                    c[i] = fg * c[i] + ig * gg;
-                    hb[i] = __float2bfloat16_rn(og * tanh_f(c[i]));
+                for (int i = 0; i < 16; i += 2) {
+                    float hv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const float ig = sigmoid_f(ai[i + e] + bi[i + e]);
+                        const float fg = sigmoid_f(af[i + e] + bf[i + e]);
+                        const float gg = tanh_f(ag[i + e] + bg[i + e]);
+                        const float og = sigmoid_f(ao[i + e] + bo[i + e]);
+                        c[i + e] = fg * c[i + e] + ig * gg;
+                        hv[e] = og * tanh_f(c[i + e]);
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(hv[0], hv[1]);
+                    hp[i >> 1] = *(const uint32_t*)&h2;
                 }
+                float* cp = c_state + ((size_t)row * 2 + dir) * H + n_blk * 64 + ch * 16;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) *(float4*)(cp + i) = make_float4(c[i], c[i + 1], c[i + 2], c[i + 3]);
-                __nv_bfloat16* op = out + ((size_t)row * S + out_slot[dir]) * C + dir * H + n_blk * 64 + ch * 16;
-                *(uint4*)op = *(const uint4*)hb;
-                *(uint4*)(op + 8) = *(const uint4*)(hb + 8);
+                __nv_bfloat16* op = out + ((size_t)row * S + (dir ? out_slot[1] : out_slot[0])) * C + dir * H + n_blk * 64 + ch * 16;
+                *(uint4*)op = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *(uint4*)(op + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
             }
         }
     }
 };
 
 struct SeluEpilogue {
+    static constexpr int kStages = 4;
+    static constexpr int kSmemBytes = 0;
+    __device__ void setup(uint8_t*, int) const {}
+    __device__ void prefetch(uint8_t*, int, int, int, int, bool, int, int) const {}
+
     const float* bias;        // [N]
     __nv_bfloat16* out;       // [M][ldo]
     int ldo;
 
-    __device__ void operator()(int dir, int n_blk, int row, bool ok, uint32_t taddr, int half) const {
+    __device__ void operator()(uint8_t*, int, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int) const {
         (void)dir;
         const float alpha = 1.6732632423543772f, lambda = 1.0507009873554805f;
 #pragma unroll 1
@@ -99,15 +136,17 @@ struct SeluEpilogue {
             ld16(bias + col, bb);
             tc::tmem_ld_wait();
             if (ok) {
-                __align__(16) __nv_bfloat16 hb[16];
+                uint32_t hp[8];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float x = a[i] + bb[i];
-                    hb[i] = __float2bfloat16_rn(lambda * (x > 0.f ? x : alpha * (__expf(x) - 1.f)));
+                for (int i = 0; i < 16; i += 2) {
+                    const float x0 = a[i] + bb[i], x1 = a[i + 1] + bb[i + 1];
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(lambda * (x0 > 0.f ? x0 : alpha * (__expf(x0) - 1.f)),
+                                                                    lambda * (x1 > 0.f ? x1 : alpha * (__expf(x1) - 1.f)));
+                    hp[i >> 1] = *(const uint32_t*)&h2;
                 }
                 __nv_bfloat16* op = out + (size_t)row * ldo + col;
-                *(uint4*)op = *(const uint4*)hb;
-                *(uint4*)(op + 8) = *(const uint4*)(hb + 8);
+                *(uint4*)op = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *(uint4*)(op + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
             }
         }
     }
@@ -310,6 +349,7 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
             e.c_state = w.c_state;
             e.out = layer == 0 ? w.enc_out : w.dec_out;
             e.n_blks = 4;
+            { static int dbg = -1; if (dbg < 0) { const char* v = getenv("PV_DEBUG_EPI"); dbg = v ? atoi(v) : 0; } e.debug = dbg; }
             g.kb1 = layer == 0 ? XK / tc::BLOCK_K : C / tc::BLOCK_K;
             pv::prof_begin(layer == 0 ? pv::FAM_LSTM_ENC : pv::FAM_LSTM_DEC, st);
             for (int s = 0; s < T; s++) {

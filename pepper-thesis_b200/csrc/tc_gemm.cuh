@@ -27,11 +27,14 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int W_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int EPI_THREADS = 256;
+// dynamic shared memory of gemm_kernel<Epilogue>: operand ring + alignment slack + barriers + epilogue scratch
+template <class Epilogue> constexpr int smem_bytes() {
+    return Epilogue::kStages * STAGE_BYTES + 1024 + 256 + Epilogue::kSmemBytes;
+}
 constexpr int THREADS = 384;                      // 4 control warps + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 
@@ -99,6 +102,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS) and its group fences; used to prefetch per-tile epilogue state
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -125,10 +136,13 @@ struct GemmShape {
     int w_kb_off;     // first W k block (non-zero when the h block is skipped because h == 0)
 };
 
-// Epilogue functor interface:
-//   __device__ void operator()(int dir, int n_blk, int row, bool row_ok, uint32_t taddr /* lane base + stage col */, int half)
-// called by the 256 epilogue threads (two per accumulator row, half = 0/1); each call reads its half of the 256
-// accumulator columns with tmem_ld16 + tmem_ld_wait.
+// Epilogue functor interface (called by the 256 epilogue threads, two per accumulator row, half = 0/1, te = 0..255):
+//   static constexpr int kStages, kSmemBytes            operand ring depth, bytes of epilogue scratch in shared memory
+//   void setup(uint8_t* scratch, int te)                once per kernel (e.g. biases -> shared memory)
+//   void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te)
+//                                                       cp.async the NEXT tile's per-row state into buffer `buf`
+//   void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te)
+//                                                       reads its half of the 256 accumulator columns (tmem_ld16)
 
 template <class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -137,8 +151,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
+    constexpr int STAGES = Epilogue::kStages;
     uint8_t* smem_w = smem + STAGES * A_STAGE_BYTES;
     uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint8_t* epi_scratch = smem + STAGES * STAGE_BYTES + 256;
     uint64_t* full_bar = bars;                 // [STAGES]
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -176,13 +192,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     if (kb < g.kb0)
                         tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA0, &full_bar[stage],
-                                    g.a0_col[dir] + kb * BLOCK_K, g.a0_slot[dir], m_blk * BLOCK_M);
+                                    (dir ? g.a0_col[1] : g.a0_col[0]) + kb * BLOCK_K, (dir ? g.a0_slot[1] : g.a0_slot[0]), m_blk * BLOCK_M);
                     else
                         tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA1, &full_bar[stage],
-                                    g.a1_col[dir] + (kb - g.kb0) * BLOCK_K, g.a1_slot[dir], m_blk * BLOCK_M);
+                                    (dir ? g.a1_col[1] : g.a1_col[0]) + (kb - g.kb0) * BLOCK_K, (dir ? g.a1_slot[1] : g.a1_slot[0]), m_blk * BLOCK_M);
                     // W columns: A0's k blocks first, then A1's (the host packs [W_hh | W_ih] that way)
                     tma_load_2d(smem_w + stage * W_STAGE_BYTES, &tmW, &full_bar[stage],
-                                (g.w_kb_off + kb) * BLOCK_K, g.w_row[dir] + n_blk * BLOCK_N);
+                                (g.w_kb_off + kb) * BLOCK_K, (dir ? g.w_row[1] : g.w_row[0]) + n_blk * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -216,22 +232,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;
+        const int te = threadIdx.x - 128;
+        epi.setup(epi_scratch, te);
+        epi_barrier();
         int it = 0;
+        if ((int)blockIdx.x < n_tiles) {                       // state of the first tile
+            const int tile = blockIdx.x;
+            const int row = (tile / (g.dirs * g.n_blks)) * BLOCK_M + q * 32 + lane;
+            epi.prefetch(epi_scratch, 0, tile % g.dirs, (tile / g.dirs) % g.n_blks, row, row < g.M, half, te);
+        }
+        cp_async_commit();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
             const int dir = tile % g.dirs;
             const int n_blk = (tile / g.dirs) % g.n_blks;
             const int m_blk = tile / (g.dirs * g.n_blks);
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int nxt = tile + gridDim.x;
+            if (nxt < n_tiles) {                               // next tile's state: lands while this tile is computed
+                const int nrow = (nxt / (g.dirs * g.n_blks)) * BLOCK_M + q * 32 + lane;
+                epi.prefetch(epi_scratch, acc ^ 1, nxt % g.dirs, (nxt / g.dirs) % g.n_blks, nrow, nrow < g.M, half, te);
+            }
+            cp_async_commit();
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            cp_async_wait<1>();                                // everything but the group just committed has landed
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epi(dir, n_blk, row, row < g.M, taddr, (warp - 4) >> 2);
+            epi(epi_scratch, acc, dir, n_blk, row, row < g.M, taddr, half, te);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
+        cp_async_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
