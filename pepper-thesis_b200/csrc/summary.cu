@@ -32,6 +32,8 @@ constexpr int P_MAX = 1408;      // 2 CTAs per SM: 16 words x 1408 positions = 8
 constexpr int UNITS_PER_READ = 8;// a read's ops inside the tile are split into at most this many work units
 constexpr int LIST_CAP = 1024;    // work units per round
 constexpr int UNIT_OPS = 96;     // preferred CIGAR ops per work unit (3 warp steps)
+constexpr int SUB = 15;          // bases per lane sub-run (odd: conflict-free shared-memory banks along a run)
+constexpr int WARP_SCRATCH = 168;// ints of per-warp scratch
 constexpr int WIN_ELEMS = PV_WINDOW * PV_FEATURES;   // 858
 
 // Counter words (forward strand in the low 16 bits, reverse strand in the high 16 bits unless noted). The common
@@ -222,10 +224,11 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
     const uint8_t* bases = b.bases + bo;
     const int k_lo = k_begin, k_hi = k_end;
 
-    int32_t* s_pref = c.scratch;            // [33] exclusive prefix of clipped match lengths (uses [0..32])
+    int32_t* s_pref = c.scratch;            // [33] first sub-run of each compacted op
     int32_t* s_ri0 = c.scratch + 40;        // read index of the first clipped base
     int32_t* s_p0 = c.scratch + 72;         // tile-local position of the first clipped base
     int32_t* s_last = c.scratch + 104;      // clipped index of the anchor base that skips REF (or < 0)
+    int32_t* s_cnt = c.scratch + 136;       // clipped match length
 
     for (int kb = k_lo; kb < k_hi; kb += 32) {
         const int k = kb + lane;
@@ -308,8 +311,13 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
         }
 
         if (MODE == 0) {
-            // flatten the clipped match bases of these 32 ops across the lanes
-            int incl = m_cnt;
+            // The clipped match runs of these 32 ops are cut into sub-runs of at most SUB bases; each lane takes ONE sub-run
+            // (contiguous read bases AND contiguous reference positions, so no CIGAR logic in the inner loop): five aligned
+            // 32-bit loads + funnel shifts fetch its bases / qualities / reference bytes, then a fully unrolled loop issues
+            // one predicated shared-memory atomic per passing base. SUB is odd, so lanes walking one long run hit 32
+            // different banks. Mismatches (a few per cent) are collected in a bit mask and handled after the loop.
+            const int n_sub = (m_cnt + SUB - 1) / SUB;
+            int incl = n_sub;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -317,56 +325,72 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (total > 0) {
-                // ops that contribute bases are compacted into the scratch arrays; item j of the flattened sequence
-                // belongs to compacted op  s(j) = #{ops whose first item <= j} - 1, evaluated per block of 32 items
-                // with one warp OR-reduction instead of a per-lane search
-                const int pref = incl - m_cnt;                              // first flattened item of this lane's op
-                const unsigned nz = __ballot_sync(0xffffffffu, m_cnt > 0);
+                const int pref = incl - n_sub;                              // first sub-run of this lane's op
+                const unsigned nz = __ballot_sync(0xffffffffu, n_sub > 0);
                 const int rank = __popc(nz & ((1u << lane) - 1u));
                 __syncwarp();
-                if (m_cnt > 0) { s_pref[rank] = pref; s_ri0[rank] = m_ri0; s_p0[rank] = m_p0; s_last[rank] = m_last; }
+                if (n_sub > 0) { s_pref[rank] = pref; s_ri0[rank] = m_ri0; s_p0[rank] = m_p0; s_last[rank] = m_last; s_cnt[rank] = m_cnt; }
                 __syncwarp();
-                int s_first = 0;                                            // compacted op that holds item j0
-                for (int j0 = 0; j0 < total; j0 += 128) {
-                    int idx[4], pl[4]; bool skip_ref[4], act[4];
-                    uint8_t bb[4], qq[4];
+                const int padded = (read_len + 15) & ~15;                   // reads are stored padded to 16 bytes
+                int s_first = 0;                                            // compacted op that holds sub-run jb
+                for (int jb = 0; jb < total; jb += 32) {
+                    // sub-run v belongs to compacted op  #{ops whose first sub-run <= v} - 1: one warp OR-reduction per block
+                    const int sl = pref - jb;                               // ops starting inside (jb, jb + 32]
+                    const unsigned bit = (n_sub > 0 && sl >= 1 && sl <= 32) ? (1u << (sl - 1)) : 0u;
+                    const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
+                    const int sidx = s_first + __popc(mask & ((1u << lane) - 1u));
+                    s_first += __popc(mask);
+                    const int v = jb + lane;
+                    if (v < total) {
+                        const int off = (v - s_pref[sidx]) * SUB;
+                        int cnt = s_cnt[sidx] - off; if (cnt > SUB) cnt = SUB;
+                        const int ri = s_ri0[sidx] + off;                   // first read base of the sub-run
+                        const int pos = s_p0[sidx] + off;                   // its tile-local reference position
+                        const int skip_i = s_last[sidx] - off;              // anchor base (no REF decrement) if in [0, cnt)
+                        const int off4 = ri & ~3;
+                        const uint32_t* gb = (const uint32_t*)(bases + off4);
+                        const uint32_t* gq = (const uint32_t*)(quals + off4);
+                        const uint32_t* sr = (const uint32_t*)(c.ref_s + (pos & ~3));
+                        uint32_t wb[5], wq[5], wr[5];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int jb = j0 + u * 32;
-                        const int sl = pref - jb;                           // ops starting inside (jb, jb + 32]
-                        const unsigned bit = (m_cnt > 0 && sl >= 1 && sl <= 32) ? (1u << (sl - 1)) : 0u;
-                        const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
-                        const int sidx = s_first + __popc(mask & ((1u << lane) - 1u));
-                        s_first += __popc(mask);
-                        const int j = jb + lane;
-                        act[u] = j < total;
-                        if (act[u]) {
-                            const int i = j - s_pref[sidx];
-                            idx[u] = s_ri0[sidx] + i; pl[u] = s_p0[sidx] + i; skip_ref[u] = (i == s_last[sidx]);
-                        } else { idx[u] = 0; pl[u] = 0; skip_ref[u] = false; }
-                    }
+                        for (int j = 0; j < 5; j++) {
+                            const bool in = off4 + 4 * j < padded;
+                            wb[j] = in ? __ldg(gb + j) : 0u;
+                            wq[j] = in ? __ldg(gq + j) : 0u;
+                            wr[j] = sr[j];
+                        }
+                        const int sh = (ri & 3) * 8, shr = (pos & 3) * 8;
+                        uint32_t vq[4], vx[4];                              // qualities; bases XOR reference (0 = raw match)
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        bb[u] = act[u] ? __ldg(bases + idx[u]) : (uint8_t)0;
-                        qq[u] = act[u] ? __ldg(quals + idx[u]) : (uint8_t)0;
-                    }
+                        for (int j = 0; j < 4; j++) {
+                            vq[j] = __funnelshift_r(wq[j], wq[j + 1], sh);
+                            vx[j] = __funnelshift_r(wb[j], wb[j + 1], sh) ^ __funnelshift_r(wr[j], wr[j + 1], shr);
+                        }
+                        uint32_t* tcnt = &c.cnt[C_T * c.P + pos];
+                        uint32_t mm = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (act[u] && (int)qq[u] >= p.qthr) {                    // :378
-                            const uint8_t rb = c.ref_s[pl[u]];
-                            atomicAdd(&c.cnt[C_T * c.P + pl[u]], strand_inc);    // coverage, REF and the base's own class
-                            if (skip_ref[u]) atomicAdd(&c.cnt[C_SKIP * c.P + pl[u]], strand_inc);
-                            if (rb != bb[u]) {                                  // raw compare, :394 (rare path)
-                                atomicAdd(&c.cnt[C_COV2 * c.P + pl[u]], 0x10000u);   // snp_count
-                                const int rc = c.rcls[pl[u]];
-                                const int lu = c.lut[bb[u]];                    // class | dense-allele flag << 3
-                                const int cb = lu & 7;
-                                if (rc != 0xff && cb != rc) {
-                                    atomicAdd(&c.cnt[C_DEV * c.P + pl[u]], strand_inc);
-                                    atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl[u]], strand_inc);
-                                }
-                                if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl[u]], strand_inc);
+                        for (int i = 0; i < SUB; i++) {
+                            const int q = (int)((vq[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+                            if (i < cnt && q >= p.qthr) {                        // :378
+                                atomicAdd(tcnt + i, strand_inc);                 // coverage, REF and the base's own class
+                                if ((vx[i >> 2] >> ((i & 3) * 8)) & 0xffu) mm |= 1u << i;   // raw compare, :394
                             }
+                        }
+                        if (skip_i >= 0 && skip_i < cnt && (int)__ldg(quals + ri + skip_i) >= p.qthr)
+                            atomicAdd(&c.cnt[C_SKIP * c.P + pos + skip_i], strand_inc);
+                        while (mm) {                                             // mismatching bases (rare path)
+                            const int i = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const int pl = pos + i;
+                            atomicAdd(&c.cnt[C_COV2 * c.P + pl], 0x10000u);      // snp_count
+                            const int rc = c.rcls[pl];
+                            const int lu = c.lut[__ldg(bases + ri + i)];         // class | dense-allele flag << 3
+                            const int cb = lu & 7;
+                            if (rc != 0xff && cb != rc) {
+                                atomicAdd(&c.cnt[C_DEV * c.P + pl], strand_inc);
+                                atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl], strand_inc);
+                            }
+                            if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl], strand_inc);
                         }
                     }
                 }
@@ -495,9 +519,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
     c.P = P;
     c.cnt = (uint32_t*)smem;
     c.site_slot = (int32_t*)smem;                                     // aliases cnt row 0 after phase B
-    c.scratch = (int32_t*)(smem + (size_t)NC * P * 4) + warp * 136;
-    c.ref_s = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4;
-    c.pflag = c.ref_s + P;
+    c.scratch = (int32_t*)(smem + (size_t)NC * P * 4) + warp * WARP_SCRATCH;
+    c.ref_s = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4;   // P + 32 bytes (word loads overrun)
+    c.pflag = c.ref_s + P + 32;
     c.rcls = c.pflag + P;
     c.lut = c.rcls + P;
     if (tid < 256) c.lut[tid] = (uint8_t)(base_class((uint8_t)tid) | (acgt_code((uint8_t)tid) >= 0 ? 8 : 0));
@@ -510,6 +534,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
     const int64_t gbase = p.pos_off[c.region] + c.t_lo;
 
     for (int i = tid; i < NC * P; i += K1_THREADS) c.cnt[i] = 0;
+    if (tid < 32) c.ref_s[P + tid] = 0;
     for (int i = tid; i < P; i += K1_THREADS) {
         const uint8_t rbyte = i < c.n_valid ? b.ref[c.ref_off + c.t_lo + i] : (uint8_t)'N';
         c.ref_s[i] = rbyte;
@@ -780,7 +805,7 @@ int choose_tile(int64_t total_positions, int32_t n_regions) {
     return P;
 }
 
-size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * 136 * 4 + 3 * (size_t)P + 256 + 16; }
+size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4 + 3 * (size_t)P + 32 + 256 + 16; }
 
 Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
     Plan pl;
