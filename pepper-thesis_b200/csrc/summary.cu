@@ -269,9 +269,23 @@ __device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k
                         const int n = len + 1;                                   // :442
                         int elen = n;                                            // substr truncation, :439
                         if (elen > read_len - (ori - 1)) elen = read_len - (ori - 1);
-                        int64_t bq = 0;
+                        int64_t bq = 0;                                          // sum of the n qualities, :448-450
                         const int i_end = ori - 1 + n < read_len ? ori - 1 + n : read_len;
-                        for (int i = ori - 1; i < i_end; i++) bq += quals[i];     // :448-450
+                        if (i_end - (ori - 1) <= 8) {                            // short insert: three independent word loads
+                            const int i0 = ori - 1, o4 = i0 & ~3, m = i_end - i0;
+                            const uint32_t* gq = (const uint32_t*)(quals + o4);
+                            const int pad_end = (read_len + 15) & ~15;           // reads are stored padded to 16 bytes
+                            const uint32_t w0 = __ldg(gq), w1 = o4 + 4 < pad_end ? __ldg(gq + 1) : 0u,
+                                           w2 = o4 + 8 < pad_end ? __ldg(gq + 2) : 0u;
+                            const int sh = (i0 & 3) * 8;
+                            uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+                            if (m <= 4) { hi = 0; lo &= m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u); }
+                            else hi &= m == 8 ? 0xffffffffu : ((1u << (8 * (m - 4))) - 1u);
+                            const uint32_t s2 = (lo & 0x00ff00ffu) + ((lo >> 8) & 0x00ff00ffu) + (hi & 0x00ff00ffu) + ((hi >> 8) & 0x00ff00ffu);
+                            bq = (int64_t)((s2 & 0xffffu) + (s2 >> 16));
+                        } else {
+                            for (int i = ori - 1; i < i_end; i++) bq += quals[i];
+                        }
                         const bool pass = (double)bq >= p.t.min_indel_baseq * (double)n;
                         if (MODE == 0) {
                             if (pass && (int)quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
@@ -428,10 +442,29 @@ __device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, i
 }
 
 // first k in [0, n) with a[k] >= key (n if none); one thread
+// op_ref grows almost linearly with the op index, so the probe alternates between an interpolated guess and plain
+// bisection (the latter keeps the worst case logarithmic); typically 3-5 dependent loads instead of ~14
 __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int n, int64_t key) {
     int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)a[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
+    if (n == 0 || (int64_t)a[0] >= key) return 0;
+    if ((int64_t)a[n - 1] < key) return n;
+    int64_t alo = a[0], ahi = a[n - 1];                 // invariant: a[lo] < key <= a[hi - 1] with lo < hi - 1 possible
+    hi = n - 1;                                         // answer in (lo, hi]
+    bool interp = true;
+    while (hi - lo > 1) {
+        int mid;
+        if (interp && ahi > alo) {
+            mid = lo + (int)(((key - alo) * (int64_t)(hi - lo)) / (ahi - alo));
+            if (mid <= lo) mid = lo + 1;
+            if (mid >= hi) mid = hi - 1;
+        } else {
+            mid = (lo + hi) >> 1;
+        }
+        interp = !interp;
+        const int64_t am = a[mid];
+        if (am < key) { lo = mid; alo = am; } else { hi = mid; ahi = am; }
+    }
+    return hi;
 }
 
 struct WorkUnit { int32_t read; int32_t k_begin; int32_t k_end; };   // read index relative to the round's first read
