@@ -6,7 +6,7 @@
 
 namespace {
 
-constexpr int MAX_CHUNK = 8192;     // windows per pass
+constexpr int MAX_CHUNK = 32768;    // windows per pass: many tiles per CTA per launch amortise pipeline fill/drain
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -63,8 +63,10 @@ float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u,
 // below the bf16 rounding of the MMA operands): 1 MUFU op per activation instead of ex2 + rcp.
 // -DPV_EXACT_ACT switches to exp/divide based forms.
 #ifdef PV_EXACT_ACT
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+__device__ __forceinline__ float ex2_f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_f(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_f(1.f + ex2_f(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_f(float x) { return fmaf(2.f, rcp_f(1.f + ex2_f(-2.8853900817779268f * x)), -1.f); }
 #else
 __device__ __forceinline__ float tanh_f(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_f(0.5f * x), 0.5f); }

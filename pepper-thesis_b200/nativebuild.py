@@ -60,7 +60,8 @@ def build_lib(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
         if force or _newer(o, [s] + headers()):
-            _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+            extra = os.environ.get("PV_NVCC_FLAGS", "").split()
+            _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", *extra,
                   "-I", INC, "-I", CSRC, "-c", s, "-o", o], verbose)
         objs.append(o)
     _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"], verbose)

@@ -92,7 +92,7 @@ class HotPath:
     """
 
     def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
-                 wrap_int8: bool = True, infer_batch: int = 8192):
+                 wrap_int8: bool = True, infer_batch: int = 32768):
         self.model = model
         self.thr = thresholds
         self.device = torch.device(device)
