@@ -76,6 +76,12 @@ typedef struct PvReadBatch {
                                          reference substrings truncated at this length, region_summary.cpp:500) */
     const int64_t*  region_read_begin;/* n_regions + 1 entries */
     const uint8_t*  ref;              /* reference bytes as given; region r owns region_ref_len[r] bytes */
+    /* Optional wire format for HOST batches: the BAM-native 4-bit packing of `bases` (nt16 codes of
+     * "=ACMGRSVTWYHKDBN", base i in byte i/2, even i in the high nibble; n_bases/2 bytes). When non-NULL the host entry
+     * points upload this instead of `bases` (which may then be NULL) and expand it on the device (pv_unpack_bases4);
+     * only valid when every base is one of those 16 upper-case letters (what BAM_handler::get_reads produces,
+     * bam_handler.cpp:213). Ignored (may be NULL) for device-resident batches. */
+    const uint8_t*  bases4;
 } PvReadBatch;
 
 /* The ten scalars of generate_summary (region_summary.h:191-201), same order, same double compares. */
@@ -122,6 +128,11 @@ int64_t pv_launch_count(void);
 /* byte offset, inside the summary workspace, of the int32 status word of the last pv_summary_regions call
  * (bit0 site scratch overflow, bit1 allele-event scratch overflow, bit2 candidate capacity overflow, bit3 internal). */
 int pv_summary_status_offset(void);
+
+/* Device: expand 4-bit packed bases (see PvReadBatch.bases4) into one byte per base; n_bases must be a multiple of 16. */
+int pv_unpack_bases4(const uint8_t* packed_dev, int64_t n_bases, uint8_t* bases_dev, void* stream);
+/* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
+int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 
 /* Host-side consistency check of a HOST-resident batch. */
 int pv_batch_validate(const PvReadBatch* host_batch);

@@ -2,6 +2,7 @@
 // convenience entry point for the summary path (include/pepper_b200.h).
 #include "common.cuh"
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace pv {
@@ -147,6 +148,8 @@ extern "C" int pv_batch_validate(const PvReadBatch* b) {
     if (!b) return pv::set_error(PV_EINVAL, "null batch");
     if (b->n_reads < 0 || b->n_bases < 0 || b->n_ops < 0 || b->n_regions < 0 || b->n_ref < 0)
         return pv::set_error(PV_EINVAL, "negative size");
+    if (b->bases4 && (b->n_bases & 15)) return pv::set_error(PV_EINVAL, "bases4 needs n_bases to be a multiple of 16");
+    if (!b->bases4 && !b->bases && b->n_bases) return pv::set_error(PV_EINVAL, "neither bases nor bases4 given");
     if (b->n_regions == 0) return PV_OK;
     if (!b->region_read_begin || b->region_read_begin[0] != 0 || b->region_read_begin[b->n_regions] != b->n_reads)
         return pv::set_error(PV_EINVAL, "region_read_begin must start at 0 and end at n_reads");
@@ -177,10 +180,29 @@ extern "C" int pv_batch_validate(const PvReadBatch* b) {
 
 namespace {
 
+// 4-bit -> 8-bit bases: a 256-entry shared-memory table maps one packed byte to its two ASCII letters
+__global__ void unpack_bases4_kernel(const uint8_t* __restrict__ packed, int64_t n_vec, uint8_t* __restrict__ bases) {
+    __shared__ uint16_t lut[256];
+    const char* nt16 = "=ACMGRSVTWYHKDBN";
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (uint16_t)((uint8_t)nt16[i >> 4] | ((uint16_t)(uint8_t)nt16[i & 15] << 8));
+    __syncthreads();
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 in = __ldg((const uint2*)packed + v);                       // 8 packed bytes = 16 bases
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = j < 2 ? in.x : in.y;
+            const uint32_t b0 = (w >> ((j & 1) * 16)) & 0xffu, b1 = (w >> ((j & 1) * 16 + 8)) & 0xffu;
+            o[j] = (uint32_t)lut[b0] | ((uint32_t)lut[b1] << 16);
+        }
+        ((uint4*)bases)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 struct HostCtx {
     std::mutex mu;
     pv::DevBuf arr[18];      // batch arrays in PvReadBatch order
-    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense;
+    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense, packed;
     cudaStream_t stream = nullptr;
 };
 HostCtx& host_ctx() { static HostCtx c; return c; }
@@ -188,6 +210,45 @@ HostCtx& host_ctx() { static HostCtx c; return c; }
 }  // namespace
 
 extern "C" int pv_summary_status_offset(void);
+
+extern "C" int pv_unpack_bases4(const uint8_t* packed_dev, int64_t n_bases, uint8_t* bases_dev, void* stream) {
+    if (!packed_dev || !bases_dev || n_bases < 0 || (n_bases & 15)) return pv::set_error(PV_EINVAL, "pv_unpack_bases4: bad arguments (n_bases must be a multiple of 16)");
+    if (n_bases == 0) return PV_OK;
+    if (int rc = pv::require_device()) return rc;
+    const int64_t n_vec = n_bases / 16;
+    int64_t blocks = (n_vec + 255) / 256;
+    const int64_t cap = (int64_t)pv::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    unpack_bases4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed_dev, n_vec, bases_dev);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_pack_bases4(const uint8_t* bases, int64_t n_bases, uint8_t* packed, int32_t threads) {
+    if (!bases || !packed || n_bases < 0 || (n_bases & 1)) return pv::set_error(PV_EINVAL, "pv_pack_bases4: bad arguments");
+    uint8_t code[256];
+    memset(code, 0xff, sizeof(code));
+    const char* nt16 = "=ACMGRSVTWYHKDBN";
+    for (int i = 0; i < 16; i++) code[(uint8_t)nt16[i]] = (uint8_t)i;
+    code[0] = 0;                                            // padding
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    std::vector<int> bad((size_t)threads, 0);
+    std::vector<std::thread> pool;
+    const int64_t n_out = n_bases / 2, per = (n_out + threads - 1) / threads;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t]() {
+            const int64_t lo = t * per, hi = lo + per < n_out ? lo + per : n_out;
+            for (int64_t i = lo; i < hi; i++) {
+                const uint8_t a = code[bases[2 * i]], c = code[bases[2 * i + 1]];
+                if ((a | c) & 0xf0) bad[(size_t)t] = 1;
+                packed[i] = (uint8_t)((a << 4) | (c & 15));
+            }
+        });
+    for (auto& th : pool) th.join();
+    for (int v : bad) if (v) return pv::set_error(PV_EINVAL, "pv_pack_bases4: a base is outside the nt16 alphabet");
+    return PV_OK;
+}
 
 extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds* thr, int32_t window, int32_t features,
                                        const PvCandidates* out, int64_t* n_candidates, int16_t* dense_image_host) {
@@ -216,9 +277,16 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
                               (size_t)hb->n_regions * 8, (size_t)(hb->n_regions + 1) * 8, (size_t)hb->n_ref};
     for (int i = 0; i < 18; i++) {
         if (int rc = h.arr[i].reserve(bytes[i] + 16)) return rc;
+        if (i == 7 && hb->bases4 && hb->n_bases) {          // bases travel 4-bit packed and are expanded on the device
+            if (int rc = h.packed.reserve((size_t)hb->n_bases / 2 + 16)) return rc;
+            PV_CUDA_CHECK(cudaMemcpyAsync(h.packed.p, hb->bases4, (size_t)hb->n_bases / 2, cudaMemcpyHostToDevice, st));
+            if (int rc = pv_unpack_bases4((const uint8_t*)h.packed.p, hb->n_bases, (uint8_t*)h.arr[7].p, st)) return rc;
+            continue;
+        }
         if (bytes[i]) PV_CUDA_CHECK(cudaMemcpyAsync(h.arr[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
     }
     PvReadBatch db = *hb;
+    db.bases4 = nullptr;
     db.read_pos = (const int64_t*)h.arr[0].p; db.read_base_off = (const int64_t*)h.arr[1].p; db.read_len = (const int32_t*)h.arr[2].p;
     db.read_cigar_off = (const int64_t*)h.arr[3].p; db.read_n_ops = (const int32_t*)h.arr[4].p; db.read_flags = (const uint8_t*)h.arr[5].p;
     db.read_mapq = (const uint8_t*)h.arr[6].p; db.bases = (const uint8_t*)h.arr[7].p; db.quals = (const uint8_t*)h.arr[8].p;

@@ -29,8 +29,17 @@ class DeviceBatch:
         self.host = host
         self.device = torch.device(device)
         self.t = {}
+        self.packed = None
         for name in ARRAY_NAMES:
             a = getattr(host, name)
+            if name == "bases" and host.bases4 is not None and a.size:
+                # bases travel in the BAM-native 4-bit form and are expanded on the device (pv_unpack_bases4)
+                self.packed = _to_torch(host.bases4).to(self.device, non_blocking=non_blocking)
+                out = torch.empty(a.size, dtype=torch.uint8, device=self.device)
+                capi.check(capi.load().pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), a.size, C.c_void_p(out.data_ptr()),
+                                                        C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+                self.t[name] = out
+                continue
             src = _to_torch(a) if a.size else torch.zeros(1, dtype=_TORCH_DT[np.dtype(a.dtype)])
             self.t[name] = src.to(self.device, non_blocking=non_blocking)
         self.region_len = np.ascontiguousarray(host.region_len)
@@ -39,7 +48,10 @@ class DeviceBatch:
 
     @property
     def h2d_bytes(self) -> int:
-        return int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
+        n = int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
+        if self.packed is not None:
+            n -= self.host.bases.nbytes - self.host.bases4.nbytes
+        return n
 
 
 class SummaryWorkspace:

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -29,7 +29,7 @@ class PvReadBatchStruct(C.Structure):
                 ("region_ref_start", C.c_void_p), ("region_ref_end", C.c_void_p), ("region_cand_start", C.c_void_p),
                 ("region_cand_end", C.c_void_p), ("region_ref_off", C.c_void_p), ("region_ref_len", C.c_void_p),
                 ("region_read_begin", C.c_void_p),
-                ("ref", C.c_void_p)]
+                ("ref", C.c_void_p), ("bases4", C.c_void_p)]
 
 
 ARRAY_NAMES = [n for n, _ in _READ_FIELDS] + ["bases", "quals", "cigar"] + [n for n, _ in _REGION_FIELDS] + \
@@ -58,6 +58,7 @@ class ReadBatch:
     region_read_begin: np.ndarray
     ref: np.ndarray
     contigs: List[str] = field(default_factory=list)
+    bases4: Optional[np.ndarray] = None      # optional BAM-native 4-bit packing of `bases` (n_bases / 2 bytes)
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -107,7 +108,23 @@ class ReadBatch:
                 a = getattr(self, name)
                 assert a.flags["C_CONTIGUOUS"], name
                 setattr(s, name, a.ctypes.data)
+        s.bases4 = self.bases4.ctypes.data if (arrays is None and self.bases4 is not None) else None
         return s
+
+    def pack_bases4(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the 4-bit wire form of the bases (raises if a base is outside the BAM nt16 alphabet)."""
+        from . import capi
+        import os
+        lib = capi.load()
+        if pinned:
+            import torch
+            self._bases4_owner = torch.empty(max(1, self.n_bases // 2), dtype=torch.uint8, pin_memory=True)
+            out = self._bases4_owner.numpy()[:self.n_bases // 2]
+        else:
+            out = np.empty(self.n_bases // 2, np.uint8)
+        capi.check(lib.pv_pack_bases4(self.bases.ctypes.data, self.n_bases, out.ctypes.data, threads or min(32, os.cpu_count() or 1)))
+        self.bases4 = out
+        return self
 
     def region_range_view(self, r0: int, r1: int) -> "ReadBatch":
         """Regions [r0, r1) as a batch whose big arrays (bases, quals, cigar, ref) are VIEWS of this batch (no copy);
@@ -133,7 +150,8 @@ class ReadBatch:
             region_cand_start=self.region_cand_start[r0:r1], region_cand_end=self.region_cand_end[r0:r1],
             region_ref_off=self.region_ref_off[r0:r1] - f_lo, region_ref_len=self.region_ref_len[r0:r1],
             region_read_begin=self.region_read_begin[r0:r1 + 1] - rb, ref=self.ref[f_lo:f_hi],
-            contigs=self.contigs[r0:r1] if self.contigs else [])
+            contigs=self.contigs[r0:r1] if self.contigs else [],
+            bases4=self.bases4[b_lo // 2:b_hi // 2] if self.bases4 is not None else None)
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

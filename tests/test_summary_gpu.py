@@ -106,3 +106,26 @@ def test_empty_region_and_mapq0():
     assert out.count == 0
     b = H.one_region("ACGT" * 25, [])
     assert capi.summary_regions_host(b, H.R9).count == 0
+
+
+def test_bases4_wire_format_equals_byte_format():
+    """BAM-native 4-bit bases uploaded and expanded on the device give the same candidates as byte bases."""
+    b = synth.generate("ont_r9", 300000, 20.0, seed=8)
+    thr = synth.PROFILES["ont_r9"].thresholds
+    a = capi.summary_regions_host(b, thr).trimmed()
+    b.pack_bases4()
+    assert b.bases4.nbytes * 2 == b.bases.nbytes
+    c = capi.summary_regions_host(b, thr).trimmed()
+    H.assert_same(a, c, "bases4")
+    assert np.array_equal(a["region"], c["region"])
+    from pepper_thesis_b200 import device as dev
+    import torch
+    db = dev.DeviceBatch(b.region_range_view(1, 3))
+    torch.cuda.synchronize()
+    assert np.array_equal(db.t["bases"].cpu().numpy()[:100000], np.where(b.region_range_view(1, 3).bases[:100000] == 0, ord("="), b.region_range_view(1, 3).bases[:100000]))
+
+
+def test_pack_bases4_rejects_other_bytes():
+    b = H.fuzz_region(3)          # contains lower-case / odd bytes
+    with pytest.raises(capi.PvError):
+        b.pack_bases4()
