@@ -136,6 +136,8 @@ __device__ int warp_lower_bound(const int32_t* __restrict__ a, int n, int64_t ke
 // ------------------------------------------------------------------------------------------------------------
 // K0
 // ------------------------------------------------------------------------------------------------------------
+// Each lane takes FOUR consecutive ops (one 16-byte load, two 16-byte stores), so a warp step covers 128 ops with a
+// single pair of shuffle scans. Ops are indexed from the 16-byte aligned slot at or below the read's first op.
 __global__ void cigar_prefix_kernel(PvReadBatch b, int32_t* __restrict__ op_ref, int32_t* __restrict__ op_ri,
                                     int32_t* __restrict__ read_span) {
     const int lane = threadIdx.x & 31;
@@ -144,23 +146,50 @@ __global__ void cigar_prefix_kernel(PvReadBatch b, int32_t* __restrict__ op_ref,
     for (int64_t r = warp; r < b.n_reads; r += n_warps) {
         const int64_t co = b.read_cigar_off[r];
         const int n_ops = b.read_n_ops[r];
+        const int64_t co_al = co & ~(int64_t)3;                 // aligned slot; ops before `co` belong to the previous read
+        const int skip = (int)(co - co_al);
+        const int n_slots = skip + n_ops;
         int ref_run = 0, ri_run = 0;
-        for (int k0 = 0; k0 < n_ops; k0 += 32) {
-            const int k = k0 + lane;
-            const uint32_t w = k < n_ops ? b.cigar[co + k] : 0u;
-            const int op = (int)(w & 15u), len = (int)(w >> 4);
-            // :357-563 -- what each op adds to ref_position / read_index (REF_SKIP and PAD also advance the read)
-            const int ra = (is_match_op(op) || op == 2 || op == 3 || op == 6) ? len : 0;
-            const int qa = (is_match_op(op) || op == 1 || op == 4 || op == 3 || op == 6) ? len : 0;
-            int sr = ra, sq = qa;
+        for (int k0 = 0; k0 < n_slots; k0 += 128) {
+            const int k = k0 + lane * 4;                        // first slot of this lane
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (k + 3 < n_slots && co_al + k + 3 < b.n_ops) w = __ldg((const uint4*)(b.cigar + co_al + k));
+            else {
+                if (k + 0 < n_slots) w.x = b.cigar[co_al + k + 0];
+                if (k + 1 < n_slots) w.y = b.cigar[co_al + k + 1];
+                if (k + 2 < n_slots) w.z = b.cigar[co_al + k + 2];
+            }
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            int ra[4], qa[4], sr = 0, sq = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool mine = k + j >= skip && k + j < n_slots;
+                const int op = (int)(ws[j] & 15u), len = (int)(ws[j] >> 4);
+                // :357-563 -- what each op adds to ref_position / read_index (REF_SKIP and PAD also advance the read)
+                ra[j] = (mine && (is_match_op(op) || op == 2 || op == 3 || op == 6)) ? len : 0;
+                qa[j] = (mine && (is_match_op(op) || op == 1 || op == 4 || op == 3 || op == 6)) ? len : 0;
+                sr += ra[j]; sq += qa[j];
+            }
+            int ir = sr, iq = sq;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int tr = __shfl_up_sync(0xffffffffu, sr, d), tq = __shfl_up_sync(0xffffffffu, sq, d);
-                if (lane >= d) { sr += tr; sq += tq; }
+                const int tr = __shfl_up_sync(0xffffffffu, ir, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
+                if (lane >= d) { ir += tr; iq += tq; }
             }
-            if (k < n_ops) { op_ref[co + k] = ref_run + sr - ra; op_ri[co + k] = ri_run + sq - qa; }
-            ref_run += __shfl_sync(0xffffffffu, sr, 31);
-            ri_run += __shfl_sync(0xffffffffu, sq, 31);
+            int pr = ref_run + ir - sr, pq = ri_run + iq - sq;  // prefix before this lane's first slot
+            int o_r[4], o_q[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { o_r[j] = pr; o_q[j] = pq; pr += ra[j]; pq += qa[j]; }
+            if (k >= skip && k + 3 < n_slots) {
+                *(int4*)(op_ref + co_al + k) = make_int4(o_r[0], o_r[1], o_r[2], o_r[3]);
+                *(int4*)(op_ri + co_al + k) = make_int4(o_q[0], o_q[1], o_q[2], o_q[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (k + j >= skip && k + j < n_slots) { op_ref[co_al + k + j] = o_r[j]; op_ri[co_al + k + j] = o_q[j]; }
+            }
+            ref_run += __shfl_sync(0xffffffffu, ir, 31);
+            ri_run += __shfl_sync(0xffffffffu, iq, 31);
         }
         if (lane == 0) read_span[r] = ref_run;
     }
@@ -975,8 +1004,10 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     iota_kernel<<<(unsigned)((pl.cand_cap + 255) / 256), 256, 0, stream>>>(w.val_in, (int)pl.cand_cap);
     PV_CUDA_CHECK(cudaGetLastError());
     size_t tmp = pl.sort_tmp;
+    int key_bits = 25;                                    // 24 low bits (type, allele rank) + the position bits in use
+    while (key_bits < 64 && (total_positions >> (key_bits - 24)) != 0) key_bits++;
     PV_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.sort_tmp, tmp, (const unsigned long long*)w.key_in, w.key_out,
-                                                  (const uint32_t*)w.val_in, w.val_out, (int)pl.cand_cap, 0, 64, stream));
+                                                  (const uint32_t*)w.val_in, w.val_out, (int)pl.cand_cap, 0, key_bits, stream));
     pv::prof_end(pv::FAM_SUM_SORT, stream, 11);     // iota + histogram + exclusive sum + 8 onesweep passes
     int64_t eblocks = (pl.cand_cap + 7) / 8;
     if (eblocks > (int64_t)sms * 16) eblocks = (int64_t)sms * 16;

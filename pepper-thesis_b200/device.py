@@ -25,26 +25,38 @@ def _to_torch(a: np.ndarray) -> torch.Tensor:
 class DeviceBatch:
     """A ReadBatch whose arrays live in HBM (``PvReadBatch`` with device pointers)."""
 
-    def __init__(self, host: ReadBatch, device: torch.device | str = "cuda", non_blocking: bool = True):
+    def __init__(self, host: ReadBatch, device: torch.device | str = "cuda", non_blocking: bool = True,
+                 defer_unpack: bool = False):
         self.host = host
         self.device = torch.device(device)
         self.t = {}
         self.packed = None
+        self._unpacked = True
         for name in ARRAY_NAMES:
             a = getattr(host, name)
             if name == "bases" and host.bases4 is not None and a.size:
                 # bases travel in the BAM-native 4-bit form and are expanded on the device (pv_unpack_bases4)
                 self.packed = _to_torch(host.bases4).to(self.device, non_blocking=non_blocking)
-                out = torch.empty(a.size, dtype=torch.uint8, device=self.device)
-                capi.check(capi.load().pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), a.size, C.c_void_p(out.data_ptr()),
-                                                        C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
-                self.t[name] = out
+                self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
+                self._unpacked = False
+                if not defer_unpack:
+                    self.unpack()
                 continue
             src = _to_torch(a) if a.size else torch.zeros(1, dtype=_TORCH_DT[np.dtype(a.dtype)])
             self.t[name] = src.to(self.device, non_blocking=non_blocking)
         self.region_len = np.ascontiguousarray(host.region_len)
         self.total_positions = int(self.region_len.sum())
         self.struct = host.as_struct({n: self.t[n].data_ptr() for n in ARRAY_NAMES})
+
+    def unpack(self):
+        """Expand the 4-bit bases on the CURRENT stream (a copy stream should only carry copies: the caller runs this
+        on the compute stream after waiting for the upload)."""
+        if self._unpacked:
+            return
+        out = self.t["bases"]
+        capi.check(capi.load().pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        self._unpacked = True
 
     @property
     def h2d_bytes(self) -> int:

@@ -102,35 +102,61 @@ class HotPath:
         self.infer_batch = infer_batch
         self._ws = None
         self._ws_key = None
+        self._host_counts = None
         self._acc = None
         self.copy_stream = None
 
     # ---- summary of one group -----------------------------------------------------------------------------------------
-    def _workspace(self, db: dev.DeviceBatch):
+    # Two workspaces alternate: the kernels of group i+1 are already queued when the host waits (on an event, not on the
+    # whole stream) for the candidate count of group i, so the GPU never idles on the one host round trip per group.
+    def _key(self, db: dev.DeviceBatch):
         h = db.host
         cap = max(4096, int(db.total_positions / 1000.0 * self.cand_per_kbp))
-        key = (h.n_reads, h.n_ops, h.n_regions, db.total_positions, cap)
-        if self._ws is None or any(a < b for a, b in zip(self._ws_key, key)):
-            grow = tuple(int(max(a, b) * 1.05) + 16 for a, b in zip(self._ws_key or key, key))
-            self._ws = dev.SummaryWorkspace(grow[0], grow[1], grow[2], grow[3], grow[4], self.device)
-            self._ws_key = grow
-        return self._ws
+        return (h.n_reads, h.n_ops, h.n_regions, db.total_positions, cap)
 
-    def summarize(self, db: dev.DeviceBatch):
-        """Summary kernel chain on one group; returns (workspace, K). The one host sync of the pipeline: K sizes the
-        inference launches."""
+    def _ensure_workspaces(self, db: dev.DeviceBatch):
+        key = self._key(db)
+        if self._ws is None or any(a < b for a, b in zip(self._ws_key, key)):
+            torch.cuda.current_stream(self.device).synchronize()
+            grow = tuple(int(max(a, b) * 1.05) + 16 for a, b in zip(self._ws_key or key, key))
+            self._ws = [dev.SummaryWorkspace(grow[0], grow[1], grow[2], grow[3], grow[4], self.device) for _ in range(2)]
+            self._ws_key = grow
+            self._host_counts = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+            return True
+        return False
+
+    def _launch_summary(self, db: dev.DeviceBatch, slot: int):
+        ws = self._ws[slot]
+        dev.summary_regions(db, self.thr, ws)
+        hc = self._host_counts[slot]
+        hc[0:1].copy_(ws.count, non_blocking=True)
+        hc[1:2].copy_(ws.ws[12:16].view(torch.int32), non_blocking=True)       # status word
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return dict(db=db, slot=slot, ev=ev, ws=ws, hc=hc)      # keeps its workspace alive even if the pool is regrown
+
+    def _collect_summary(self, h):
+        """Waits for the summary of one group; returns (workspace, K). Re-runs the group with a larger candidate
+        capacity when it overflowed (rare)."""
+        h["ev"].synchronize()
+        k, st = int(h["hc"][0]), int(h["hc"][1])
+        ws = h["ws"]
         while True:
-            ws = self._workspace(db)
-            dev.summary_regions(db, self.thr, ws)
-            k = int(ws.count.item())
-            st = ws.status()
             if st & 8:
                 raise RuntimeError("internal inconsistency in the allele event pass")
-            if k > ws.capacity or (st & 7):
-                self.cand_per_kbp *= 2.0 * max(1.0, k / max(1, ws.capacity))
-                self._ws = None
-                continue
-            return ws, k
+            if k <= ws.capacity and not (st & 7):
+                return ws, k
+            self.cand_per_kbp *= 2.0 * max(1.0, k / max(1, ws.capacity))
+            self._ws = None
+            self._ensure_workspaces(h["db"])
+            ws = self._ws[h["slot"]]
+            dev.summary_regions(h["db"], self.thr, ws)
+            k, st = int(ws.count.item()), ws.status()
+
+    def summarize(self, db: dev.DeviceBatch):
+        """Summary kernel chain on one group (synchronous form); returns (workspace, K)."""
+        self._ensure_workspaces(db)
+        return self._collect_summary(self._launch_summary(db, 0))
 
     # ---- accumulate windows, infer in full passes -----------------------------------------------------------------------
     class _Run:
@@ -199,9 +225,17 @@ class HotPath:
             region_offsets = [region_offsets]
         run = HotPath._Run()
         self._acc_buffer(self.infer_batch * 2)
-        for d, off in zip(dbs, region_offsets):
-            ws, k = self.summarize(d)
-            self._push(run, ws, k, off)
+        pending = None
+        for i, (d, off) in enumerate(zip(dbs, region_offsets)):
+            self._ensure_workspaces(d)            # a regrown pool leaves the pending group's own workspace untouched
+            h = self._launch_summary(d, i & 1)
+            if pending is not None:
+                ws, k = self._collect_summary(pending[0])
+                self._push(run, ws, k, pending[1])
+            pending = (h, off)
+        if pending is not None:
+            ws, k = self._collect_summary(pending[0])
+            self._push(run, ws, k, pending[1])
         return self._finish(run, to_host)
 
     def run_host(self, batch: ReadBatch, region_offset: int = 0) -> Predictions:
@@ -217,7 +251,7 @@ class HotPath:
 
         def upload(g):
             with torch.cuda.stream(self.copy_stream):
-                db = dev.DeviceBatch(batch.region_range_view(*g), self.device, non_blocking=True)
+                db = dev.DeviceBatch(batch.region_range_view(*g), self.device, non_blocking=True, defer_unpack=True)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
             return db, ev
@@ -230,8 +264,13 @@ class HotPath:
             main.wait_event(ev)
             if i + 1 < len(groups):
                 nxt = upload(groups[i + 1])
+            db.unpack()                           # 4-bit bases -> bytes, on the compute stream
+            # this path is bound by the H2D copies, so the simple synchronous form is used: the host waits for the group's
+            # candidate count before queueing more (measured: queueing further ahead slows the copies down)
             ws, k = self.summarize(db)
             self._push(run, ws, k, region_offset + g[0])
             for t in db.t.values():
                 t.record_stream(main)
+            if db.packed is not None:
+                db.packed.record_stream(main)
         return self._finish(run, True)
