@@ -39,7 +39,8 @@ struct LstmEpilogue {
     static constexpr int kSmemBytes = kBiasBytes + 2 * kStateBytes;        // biases + double-buffered c tile
 
     const float* bias;        // [dirs][n_blks][4 gates][64]  (b_ih + b_hh, tile order)
-    float* c_state;           // [M][2][H] fp32
+    float* c_state;           // cell state, fp32, private TILE layout [m_blk][dir][n_blk][half][chunk][j][row 0..127][4]:
+                              // every warp-wide 16-byte load/store of the epilogue touches 512 contiguous bytes
     __nv_bfloat16* out;       // [M][S][C]
     int n_blks;
     int out_slot[2];
@@ -52,15 +53,17 @@ struct LstmEpilogue {
         for (int i = te; i < kBiasBytes / 16; i += tc::EPI_THREADS) sb[i] = __ldg(gb + i);
     }
     // thread te keeps its 2 x 64 bytes of a tile at [(cc*4 + j) * 256 + te] 16-byte slots: conflict-free both ways
+    __device__ __forceinline__ float* c_ptr(int dir, int n_blk, int row, int half, int cc, int j) const {
+        const size_t tile = ((size_t)(row >> 7) * 2 + dir) * n_blks + n_blk;
+        return c_state + ((((tile * 2 + half) * 2 + cc) * 4 + j) * 128 + (row & 127)) * 4;
+    }
     __device__ void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te) const {
         if (first || !ok) return;
         uint8_t* dst = scratch + kBiasBytes + buf * kStateBytes;
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const float* cp = c_state + ((size_t)row * 2 + dir) * H + n_blk * 64 + (half * 2 + cc) * 16;
+        for (int cc = 0; cc < 2; cc++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, cp + j * 4);
-        }
+            for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, c_ptr(dir, n_blk, row, half, cc, j));
     }
     __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te) const {
         const float* sb = (const float*)scratch + (size_t)((dir * n_blks + n_blk) * 4) * 64;
@@ -69,10 +72,15 @@ struct LstmEpilogue {
         for (int cc = 0; cc < 2; cc++) {
             const int ch = half * 2 + cc;                      // 16 hidden units per chunk
             float ai[16], af[16], ag[16], ao[16], c[16];
-            tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ai);
-            tc::tmem_ld16(taddr + 1 * 64 + ch * 16, af);
-            tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ag);
-            tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ao);
+            if (debug != 3) {
+                tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ai);
+                tc::tmem_ld16(taddr + 1 * 64 + ch * 16, af);
+                tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ag);
+                tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ao);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) { ai[i] = 0.1f * i; af[i] = 0.2f; ag[i] = -0.1f * i; ao[i] = 0.3f; }
+            }
             if (first || !ok) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) c[i] = 0.f;
@@ -84,29 +92,40 @@ struct LstmEpilogue {
                 }
             }
             tc::tmem_ld_wait();
-            if (debug) continue;
+            if (debug == 1) continue;
             if (ok) {
                 const float* bi = sb + 0 * 64 + ch * 16; const float* bf = sb + 1 * 64 + ch * 16;
                 const float* bg = sb + 2 * 64 + ch * 16; const float* bo = sb + 3 * 64 + ch * 16;
+                // stage-wise over the 16 cells (not cell by cell): every stage is 16 independent instructions, so the MUFU
+                // and FMA pipes stay full instead of waiting on one cell's dependency chain
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    ai[i] = 0.5f * (ai[i] + bi[i]); af[i] = 0.5f * (af[i] + bf[i]);
+                    ag[i] = ag[i] + bg[i];          ao[i] = 0.5f * (ao[i] + bo[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) ai[i] = tanh_f(ai[i]);
+#pragma unroll
+                for (int i = 0; i < 16; i++) af[i] = tanh_f(af[i]);
+#pragma unroll
+                for (int i = 0; i < 16; i++) ag[i] = tanh_f(ag[i]);
+#pragma unroll
+                for (int i = 0; i < 16; i++) ao[i] = tanh_f(ao[i]);
+#pragma unroll
+                for (int i = 0; i < 16; i++)                    // sigmoid(x) = 0.5 tanh(x/2) + 0.5
+                    c[i] = fmaf(fmaf(0.5f, af[i], 0.5f), c[i], fmaf(0.5f, ai[i], 0.5f) * ag[i]);
+#pragma unroll
+                for (int i = 0; i < 16; i++) ag[i] = tanh_f(c[i]);
                 uint32_t hp[8];
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    float hv[2];
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const float ig = sigmoid_f(ai[i + e] + bi[i + e]);
-                        const float fg = sigmoid_f(af[i + e] + bf[i + e]);
-                        const float gg = tanh_f(ag[i + e] + bg[i + e]);
-                        const float og = sigmoid_f(ao[i + e] + bo[i + e]);
-                        c[i + e] = fg * c[i + e] + ig * gg;
-                        hv[e] = og * tanh_f(c[i + e]);
-                    }
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(hv[0], hv[1]);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(0.5f, ao[i], 0.5f) * ag[i], fmaf(0.5f, ao[i + 1], 0.5f) * ag[i + 1]);
                     hp[i >> 1] = *(const uint32_t*)&h2;
                 }
-                float* cp = c_state + ((size_t)row * 2 + dir) * H + n_blk * 64 + ch * 16;
+                if (debug == 2 && hp[0] != 0x12345678u) continue;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) *(float4*)(cp + i) = make_float4(c[i], c[i + 1], c[i + 2], c[i + 3]);
+                for (int j = 0; j < 4; j++)
+                    *(float4*)c_ptr(dir, n_blk, row, half, cc, j) = make_float4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
                 __nv_bfloat16* op = out + ((size_t)row * S + (dir ? out_slot[1] : out_slot[0])) * C + dir * H + n_blk * 64 + ch * 16;
                 *(uint4*)op = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 *(uint4*)(op + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
@@ -199,6 +218,11 @@ __global__ void head_kernel(const __nv_bfloat16* __restrict__ x, const float* __
 
 }  // namespace
 
+#ifdef PV_TRACE
+long long* pv_trace_buffer = nullptr;
+extern "C" long long* pv_trace_ptr(void) { return pv_trace_buffer; }
+#endif
+
 struct PvLstmModel {
     __nv_bfloat16 *enc_w, *dec_w, *lin_w[5];
     float *enc_b, *dec_b, *lin_b[5], *out_w, *out_b;
@@ -227,7 +251,7 @@ Ws carve_ws(void* base, int64_t size, int64_t chunk) {
     w.dec_out = a.take<__nv_bfloat16>(chunk * S * C);
     w.act0 = a.take<__nv_bfloat16>(chunk * LIN);
     w.act1 = a.take<__nv_bfloat16>(chunk * LIN);
-    w.c_state = a.take<float>(chunk * 2 * H);
+    w.c_state = a.take<float>(((chunk + 127) / 128 * 128) * 2 * H);
     w.bytes = pv::align_up(a.cur, 256);
     return w;
 }
@@ -343,6 +367,9 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
         g.M = (int)nb; g.m_blks = (int)((nb + 127) / 128); g.n_blks = 4; g.dirs = 2;
         g.w_row[0] = 0; g.w_row[1] = 4 * H;
         g.a0_col[0] = 0; g.a0_col[1] = H;
+#ifdef PV_TRACE
+        { static long long* tr = nullptr; if (!tr) { cudaMalloc((void**)&tr, 3 * 16 * 8 * 8); } g.trace = tr; pv_trace_buffer = tr; }
+#endif
         for (int layer = 0; layer < 2; layer++) {
             LstmEpilogue e;
             e.bias = layer == 0 ? m->enc_b : m->dec_b;

@@ -134,7 +134,14 @@ struct GemmShape {
     int a1_slot[2];
     int w_row[2];     // first W row per direction
     int w_kb_off;     // first W k block (non-zero when the h block is skipped because h == 0)
+    long long* trace; // optional (debug builds with -DPV_TRACE): CTA 0 records [role][tile][event] SM-clock stamps here
 };
+
+#ifdef PV_TRACE
+#define PV_TR(role, it, ev) do { if (g.trace && blockIdx.x == 0 && (it) < 16) g.trace[((role) * 16 + (it)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define PV_TR(role, it, ev) do { } while (0)
+#endif
 
 // Epilogue functor interface (called by the 256 epilogue threads, two per accumulator row, half = 0/1, te = 0..255):
 //   static constexpr int kStages, kSmemBytes            operand ring depth, bytes of epilogue scratch in shared memory
@@ -182,11 +189,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int stage = 0; uint32_t phase = 0; int itp = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, itp++) {
                 const int dir = tile % g.dirs;
                 const int n_blk = (tile / g.dirs) % g.n_blks;
                 const int m_blk = tile / (g.dirs * g.n_blks);
+                PV_TR(0, itp, 0);
                 for (int kb = 0; kb < kbt; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -201,6 +209,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                                 (g.w_kb_off + kb) * BLOCK_K, (dir ? g.w_row[1] : g.w_row[0]) + n_blk * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                PV_TR(0, itp, 1);
             }
         }
     } else if (warp == 1) {
@@ -211,7 +220,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                PV_TR(1, it, 0);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                PV_TR(1, it, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
                 for (int kb = 0; kb < kbt; kb++) {
@@ -227,6 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);                  // accumulator complete
+                PV_TR(1, it, 2);
             }
         }
     } else if (warp >= 4) {
@@ -255,12 +267,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 epi.prefetch(epi_scratch, acc ^ 1, nxt % g.dirs, (nxt / g.dirs) % g.n_blks, nrow, nrow < g.M, half, te);
             }
             cp_async_commit();
+            if (te == 0) PV_TR(2, it, 0);
             mbar_wait(&tfull_bar[acc], acc_phase);
+            if (te == 0) PV_TR(2, it, 1);
             tc_fence_after();
             cp_async_wait<1>();                                // everything but the group just committed has landed
+            if (te == 0) PV_TR(2, it, 2);
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             epi(epi_scratch, acc, dir, n_blk, row, row < g.M, taddr, half, te);
+            if (te == 0) PV_TR(2, it, 3);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
