@@ -36,13 +36,13 @@ int make_map3(CUtensorMap* m, const void* base, int64_t rows, int64_t slots, int
     if (r != CUDA_SUCCESS) return pv::set_error(PV_ECUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
     return PV_OK;
 }
-// bf16 weight matrix [rows][k] (k contiguous), box = 64 k x 256 rows
+// bf16 weight matrix [rows][k] (k contiguous), box = 64 k x (256 / CLUSTER) rows: one CTA's multicast slice of a W tile
 int make_map2(CUtensorMap* m, const void* base, int64_t rows, int64_t k) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return pv::set_error(PV_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
     cuuint64_t stride[1] = {(cuuint64_t)k * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)tc::BLOCK_N};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)tc::W_SLICE_ROWS};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -85,10 +85,20 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
         PV_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    const int tiles = g.m_blks * g.n_blks * g.dirs;
-    const int grid = tiles < sms ? tiles : sms;
-    tc::gemm_kernel<Epi><<<grid, tc::THREADS, smem, st>>>(a0, a1, w, g, epi);
-    PV_CUDA_CHECK(cudaGetLastError());
+    const int groups = ((g.m_blks + tc::CLUSTER - 1) / tc::CLUSTER) * g.n_blks * g.dirs;
+    int clusters = sms / tc::CLUSTER;
+    if (clusters > groups) clusters = groups;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(clusters * tc::CLUSTER));
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tc::CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::gemm_kernel<Epi>, a0, a1, w, g, epi));
     return PV_OK;
 }
 

@@ -31,6 +31,12 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int W_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
 constexpr int EPI_THREADS = 256;
+// Thread-block cluster along M: the CLUSTER CTAs of a cluster work on CLUSTER consecutive row tiles of the SAME
+// (direction, column tile), so they need the same W tile: each CTA TMA-loads 1/CLUSTER of it and MULTICASTS the slice
+// into the shared memory of all of them. L2->SM operand traffic per CTA drops from 48 KB to 16 + 32/CLUSTER KB per
+// k block (the kernel is bound by exactly that traffic).
+constexpr int CLUSTER = 2;
+constexpr int W_SLICE_ROWS = BLOCK_N / CLUSTER;
 // dynamic shared memory of gemm_kernel<Epilogue>: operand ring + alignment slack + barriers + epilogue scratch
 template <class Epilogue> constexpr int smem_bytes() {
     return Epilogue::kStages * STAGE_BYTES + 1024 + 256 + Epilogue::kSmemBytes;
@@ -72,6 +78,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset in every CTA of `mask`, and completes on the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -86,6 +103,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (when the MMAs issued so far retire) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -154,7 +176,7 @@ struct GemmShape {
 template <class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-            const __grid_constant__ CUtensorMap tmW, const GemmShape g, const Epilogue epi) {
+            const __grid_constant__ CUtensorMap tmW /* box = 64 k x W_SLICE_ROWS rows */, const GemmShape g, const Epilogue epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -169,20 +191,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = g.m_blks * g.n_blks * g.dirs;
+    // work item = a GROUP of CLUSTER consecutive row tiles with the same (column tile, direction); the cluster's CTA r
+    // takes row tile  m_grp * CLUSTER + r  (possibly beyond M at the ragged end: loads are zero-filled, stores skipped)
+    const int crank = (int)cluster_ctarank();
+    const int cluster_id = (int)blockIdx.x / CLUSTER, n_clusters = (int)gridDim.x / CLUSTER;
+    const int m_grps = (g.m_blks + CLUSTER - 1) / CLUSTER;
+    const int n_tiles = m_grps * g.n_blks * g.dirs;             // groups
     const int kbt = g.kb0 + g.kb1;
+    constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmW);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // a stage may be refilled only when ALL CTAs of the cluster have consumed it (peers multicast into it)
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
         for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                        // every CTA's barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -190,10 +220,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0; int itp = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, itp++) {
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, itp++) {
                 const int dir = tile % g.dirs;
                 const int n_blk = (tile / g.dirs) % g.n_blks;
-                const int m_blk = tile / (g.dirs * g.n_blks);
+                const int m_blk = (tile / (g.dirs * g.n_blks)) * CLUSTER + crank;
                 PV_TR(0, itp, 0);
                 for (int kb = 0; kb < kbt; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -205,8 +235,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                         tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA1, &full_bar[stage],
                                     (dir ? g.a1_col[1] : g.a1_col[0]) + (kb - g.kb0) * BLOCK_K, (dir ? g.a1_slot[1] : g.a1_slot[0]), m_blk * BLOCK_M);
                     // W columns: A0's k blocks first, then A1's (the host packs [W_hh | W_ih] that way)
-                    tma_load_2d(smem_w + stage * W_STAGE_BYTES, &tmW, &full_bar[stage],
-                                (g.w_kb_off + kb) * BLOCK_K, (dir ? g.w_row[1] : g.w_row[0]) + n_blk * BLOCK_N);
+                    // this CTA's slice of the W tile, multicast to every CTA of the cluster
+                    tma_load_2d_mc(smem_w + stage * W_STAGE_BYTES + crank * W_SLICE_ROWS * BLOCK_K * 2, &tmW, &full_bar[stage],
+                                   (g.w_kb_off + kb) * BLOCK_K, (dir ? g.w_row[1] : g.w_row[0]) + n_blk * BLOCK_N + crank * W_SLICE_ROWS, kMask);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 PV_TR(0, itp, 1);
@@ -217,7 +248,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
             int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 PV_TR(1, it, 0);
@@ -234,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     for (int k = 0; k < BLOCK_K / UMMA_K; k++)
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16),
                                   idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+                    umma_commit_mc(&empty_bar[stage], kMask);  // tells every CTA of the cluster this consumer is done with the stage
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);                  // accumulator complete
@@ -249,26 +280,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         epi.setup(epi_scratch, te);
         epi_barrier();
         int it = 0;
-        if ((int)blockIdx.x < n_tiles) {                       // state of the first tile
-            const int tile = blockIdx.x;
-            const int row = (tile / (g.dirs * g.n_blks)) * BLOCK_M + q * 32 + lane;
+        if (cluster_id < n_tiles) {                            // state of the first tile
+            const int tile = cluster_id;
+            const int row = ((tile / (g.dirs * g.n_blks)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
             epi.prefetch(epi_scratch, 0, tile % g.dirs, (tile / g.dirs) % g.n_blks, row, row < g.M, half, te);
         }
         cp_async_commit();
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
             const int dir = tile % g.dirs;
             const int n_blk = (tile / g.dirs) % g.n_blks;
-            const int m_blk = tile / (g.dirs * g.n_blks);
+            const int m_blk = (tile / (g.dirs * g.n_blks)) * CLUSTER + crank;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int nxt = tile + gridDim.x;
+            const int nxt = tile + n_clusters;
             if (nxt < n_tiles) {                               // next tile's state: lands while this tile is computed
-                const int nrow = (nxt / (g.dirs * g.n_blks)) * BLOCK_M + q * 32 + lane;
+                const int nrow = ((nxt / (g.dirs * g.n_blks)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
                 epi.prefetch(epi_scratch, acc ^ 1, nxt % g.dirs, (nxt / g.dirs) % g.n_blks, nrow, nrow < g.M, half, te);
             }
             cp_async_commit();
             if (te == 0) PV_TR(2, it, 0);
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one poller per warp
+            __syncwarp();
             if (te == 0) PV_TR(2, it, 1);
             tc_fence_after();
             cp_async_wait<1>();                                // everything but the group just committed has landed
@@ -285,6 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                        // no CTA leaves while a peer may still multicast into it
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
