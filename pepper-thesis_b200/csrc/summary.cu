@@ -28,22 +28,28 @@ constexpr int NC = 16;           // packed 32-bit counter words per position
 constexpr int K1_THREADS = 384;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
-constexpr int P_MAX = 1408;      // 2 CTAs per SM: 16 words x 1408 positions = 88 KB of counters each
+constexpr int P_MAX = 1280;      // 2 CTAs per SM: 16 words x 1280 positions = 80 KB of counters each
 constexpr int UNITS_PER_READ = 8;// a read's ops inside the tile are split into at most this many work units
-constexpr int LIST_CAP = 1024;    // work units per round
-constexpr int UNIT_OPS = 96;     // preferred CIGAR ops per work unit (3 warp steps)
-constexpr int SUB = 15;          // bases per lane sub-run (odd: conflict-free shared-memory banks along a run)
-constexpr int WARP_SCRATCH = 168;// ints of per-warp scratch
+constexpr int LIST_CAP = 512;    // work units per round
+constexpr int UNIT_OPS = 256;    // preferred CIGAR ops per work unit (normally the read's whole stretch inside the tile)
+constexpr int TBL = 128;         // match pieces a warp collects before it scans their bases
+constexpr int WARP_SCRATCH = 2 * TBL + 4;   // ints of per-warp scratch: piece table (first read index | tile position, length)
+constexpr int REF_PAD = 16;      // bytes in front of the tile's reference copy (a 16-base chunk may start before the tile)
 constexpr int WIN_ELEMS = PV_WINDOW * PV_FEATURES;   // 858
 
-// Counter words (forward strand in the low 16 bits, reverse strand in the high 16 bits unless noted). The common
-// case -- an aligned base that passes the quality threshold and equals the reference byte -- costs ONE atomic (C_T);
-// everything the reference derives from it (coverage, REFF/REFR, the base's own feature) is reconstructed at flush:
+// Counter words (forward strand in the low 16 bits, reverse strand in the high 16 bits unless noted; arithmetic is
+// modulo 2^32 on the packed word, so a field may go "negative" as long as its final value is in range). The common
+// case -- an aligned base that passes the quality threshold and equals the reference byte -- costs NO atomic at all:
+// aligned coverage is kept as a DIFFERENCE array (+1 where a match run enters the tile, -1 behind its last base; bases
+// below the quality threshold subtract themselves the same way) that the flush turns into counts with a prefix sum, and
+// everything the reference derives from an aligned base (coverage, REFF/REFR, the base's own feature) is
+// reconstructed from it:
 //   coverage = T_f + T_r + bump      REF = T - SKIP      BASE[class(ref)] = T - DEV      BASE[c != class(ref)] = CLS[c]
-enum { C_T = 0,        // aligned bases with q >= min_snp_baseq
+enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_baseq
        C_SKIP = 1,     // ... of which anchor an insert/delete (no REFF/REFR decrement, :381-391)
        C_DEV = 2,      // ... of which have a base class different from the (valid) reference base's class
-       C_CLS = 3,      // +0..6 = A C G T I D *: explicit class counts (deviating bases, insert/delete anchors, deleted spans)
+       C_CLS = 3,      // +0..5 = A C G T I D: explicit class counts (deviating bases, insert/delete anchors)
+       C_DELD = 9,     // difference array -> deleted spans ('*', :542-552); sits where class 6 would
        C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
@@ -229,218 +235,287 @@ __device__ __forceinline__ void record_event(const SumParams& p, int s, int type
     }
 }
 
-// Walks CIGAR ops [k_begin, k_end) of one read (whole warp): one work unit of the tile.
-//   MODE 0: accumulate counters (populate_summary_matrix, :337-566)
-//   MODE 1: record insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and
-//           :507-535, needed only where the site thresholds passed)
-template <int MODE>
-__device__ void walk_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
+// Per-read constants of one work unit, in TILE-LOCAL int32 coordinates (position 0 = first position of the tile).
+struct ReadCtx {
+    int64_t rel_t;          // read start relative to the tile
+    int64_t co, bo;         // first op / first base of the read
+    int nv, l_end;          // tile = [0, nv); last region position (an op that starts beyond it is never reached, :355)
+    int n_ops, read_len;
+    uint32_t rev, inc, dec; // strand; +1 / -1 in the strand's half of a packed counter word
+    const int32_t* oref; const int32_t* ori_a;
+    const uint8_t* quals; const uint8_t* bases;
+};
+
+__device__ __forceinline__ ReadCtx make_read_ctx(const SumParams& p, const TileCtx& c, int64_t r) {
     const PvReadBatch& b = p.b;
-    // everything below is in TILE-LOCAL int32 coordinates: position 0 = first position of the tile
-    const int64_t rel_t = b.read_pos[r] - b.region_ref_start[c.region] - c.t_lo;   // read start relative to the tile
-    const int nv = c.n_valid;                                                     // tile = [0, nv)
-    const int64_t l_end64 = c.L - 1 - c.t_lo;                                     // last region position, tile-local
-    const int l_end = l_end64 > (1 << 30) ? (1 << 30) : (int)l_end64;
-    const int64_t co = b.read_cigar_off[r];
-    const int n_ops = b.read_n_ops[r];
-    const int read_len = b.read_len[r];
-    const int64_t bo = b.read_base_off[r];
-    const uint32_t rev = b.read_flags[r] & 1u;
-    const uint32_t strand_inc = rev ? 0x10000u : 1u;
-    const int32_t* oref = p.op_ref + co;
-    const int32_t* ori_a = p.op_ri + co;
-    const uint8_t* quals = b.quals + bo;
-    const uint8_t* bases = b.bases + bo;
-    const int k_lo = k_begin, k_hi = k_end;
+    ReadCtx x;
+    x.rel_t = b.read_pos[r] - b.region_ref_start[c.region] - c.t_lo;
+    x.nv = c.n_valid;
+    const int64_t l_end64 = c.L - 1 - c.t_lo;
+    x.l_end = l_end64 > (1 << 30) ? (1 << 30) : (int)l_end64;
+    x.co = b.read_cigar_off[r];
+    x.n_ops = b.read_n_ops[r];
+    x.read_len = b.read_len[r];
+    x.bo = b.read_base_off[r];
+    x.rev = b.read_flags[r] & 1u;
+    x.inc = x.rev ? 0x10000u : 1u;
+    x.dec = 0u - x.inc;
+    x.oref = p.op_ref + x.co;
+    x.ori_a = p.op_ri + x.co;
+    x.quals = b.quals + x.bo;
+    x.bases = b.bases + x.bo;
+    return x;
+}
 
-    int32_t* s_pref = c.scratch;            // [33] first sub-run of each compacted op
-    int32_t* s_ri0 = c.scratch + 40;        // read index of the first clipped base
-    int32_t* s_p0 = c.scratch + 72;         // tile-local position of the first clipped base
-    int32_t* s_last = c.scratch + 104;      // clipped index of the anchor base that skips REF (or < 0)
-    int32_t* s_cnt = c.scratch + 136;       // clipped match length
+// sum of the insert's n = len + 1 qualities starting at the anchor base (:448-450) -> does it pass (:452)?
+__device__ __forceinline__ bool insert_quality_pass(const SumParams& p, const ReadCtx& x, int ori, int n) {
+    int64_t bq = 0;
+    const int i_end = ori - 1 + n < x.read_len ? ori - 1 + n : x.read_len;
+    if (i_end - (ori - 1) <= 8) {                            // short insert: three independent word loads
+        const int i0 = ori - 1, o4 = i0 & ~3, m = i_end - i0;
+        const uint32_t* gq = (const uint32_t*)(x.quals + o4);
+        const int pad_end = (x.read_len + 15) & ~15;           // reads are stored padded to 16 bytes
+        const uint32_t w0 = __ldg(gq), w1 = o4 + 4 < pad_end ? __ldg(gq + 1) : 0u, w2 = o4 + 8 < pad_end ? __ldg(gq + 2) : 0u;
+        const int sh = (i0 & 3) * 8;
+        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        if (m <= 4) { hi = 0; lo &= m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u); }
+        else hi &= m == 8 ? 0xffffffffu : ((1u << (8 * (m - 4))) - 1u);
+        const uint32_t s2 = (lo & 0x00ff00ffu) + ((lo >> 8) & 0x00ff00ffu) + (hi & 0x00ff00ffu) + ((hi >> 8) & 0x00ff00ffu);
+        bq = (int64_t)((s2 & 0xffffu) + (s2 >> 16));
+    } else {
+        for (int i = ori - 1; i < i_end; i++) bq += x.quals[i];
+    }
+    return (double)bq >= p.t.min_indel_baseq * (double)n;
+}
 
-    for (int kb = k_lo; kb < k_hi; kb += 32) {
-        const int k = kb + lane;
-        const bool have = k < k_hi;
-        const uint32_t w = have ? b.cigar[co + k] : 0u;
-        const int op = have ? (int)(w & 15u) : 15;
-        const int len = (int)(w >> 4);
-        int64_t a64 = have ? rel_t + (int64_t)oref[k] : 0;                        // op start, tile-local
-        if (a64 > (1 << 30)) a64 = (1 << 30);
-        if (a64 < -(1 << 30)) a64 = -(1 << 30);
-        const int a = (int)a64;
-        const int ori = have ? ori_a[k] : 0;
-        int m_cnt = 0, m_ri0 = 0, m_p0 = 0, m_last = -1;
+// high bit of each byte set where the quality byte is BELOW the threshold (q < qthr, qthr in [0, 256])
+__device__ __forceinline__ uint32_t lowq_mask(uint32_t q, int qthr, uint32_t thr4) {
+    if (qthr <= 128) {
+        const uint32_t s = ((q & 0x7f7f7f7fu) | 0x80808080u) - thr4;   // per byte: 0x80 + (q & 127) - qthr, never borrows
+        return ~(s | q) & 0x80808080u;
+    }
+    if (qthr >= 256) return 0x80808080u;
+    return __vcmpltu4(q, thr4) & 0x80808080u;
+}
+// high bit of each byte set where the byte is non-zero
+__device__ __forceinline__ uint32_t nonzero_mask(uint32_t x) {
+    return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+// bits 7, 15, 23, 31 -> bits 0..3
+__device__ __forceinline__ uint32_t movemask4(uint32_t m) { return (((m >> 7) * 0x01020408u) >> 24) & 0xfu; }
 
-        if (have && a <= l_end) {                                               // an op starting beyond ref_end is never reached (:355)
-            if (is_match_op(op)) {
-                if (MODE == 0) {
-                    const int i_lo = a < 0 ? -a : 0;
-                    int i_hi = nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
-                    if (i_hi > read_len - 1 - ori) i_hi = read_len - 1 - ori;
-                    if (i_hi >= i_lo) {
-                        m_cnt = i_hi - i_lo + 1;
-                        m_ri0 = ori + i_lo;
-                        m_p0 = a + i_lo;
-                        if (k != n_ops - 1) {                                   // anchor rule, :381-391
-                            const int nop = (int)(b.cigar[co + k + 1] & 15u);
-                            if (nop == 1 || nop == 2) m_last = len - 1 - i_lo;
-                        }
-                    }
-                }
-            } else if (op == 1) {                                               // IN, :431-490
-                const int ol = a - 1;
-                if (ol >= 0 && ol < nv && ori >= 1 && ori - 1 < read_len) {
-                    bool go = true;
-                    int s = -1;
-                    if (MODE == 1) { s = c.site_slot[ol]; go = s >= 0 && (c.pflag[ol] & PF_INS); }
-                    if (go) {
-                        const int n = len + 1;                                   // :442
-                        int elen = n;                                            // substr truncation, :439
-                        if (elen > read_len - (ori - 1)) elen = read_len - (ori - 1);
-                        int64_t bq = 0;                                          // sum of the n qualities, :448-450
-                        const int i_end = ori - 1 + n < read_len ? ori - 1 + n : read_len;
-                        if (i_end - (ori - 1) <= 8) {                            // short insert: three independent word loads
-                            const int i0 = ori - 1, o4 = i0 & ~3, m = i_end - i0;
-                            const uint32_t* gq = (const uint32_t*)(quals + o4);
-                            const int pad_end = (read_len + 15) & ~15;           // reads are stored padded to 16 bytes
-                            const uint32_t w0 = __ldg(gq), w1 = o4 + 4 < pad_end ? __ldg(gq + 1) : 0u,
-                                           w2 = o4 + 8 < pad_end ? __ldg(gq + 2) : 0u;
-                            const int sh = (i0 & 3) * 8;
-                            uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-                            if (m <= 4) { hi = 0; lo &= m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u); }
-                            else hi &= m == 8 ? 0xffffffffu : ((1u << (8 * (m - 4))) - 1u);
-                            const uint32_t s2 = (lo & 0x00ff00ffu) + ((lo >> 8) & 0x00ff00ffu) + (hi & 0x00ff00ffu) + ((hi >> 8) & 0x00ff00ffu);
-                            bq = (int64_t)((s2 & 0xffffu) + (s2 >> 16));
-                        } else {
-                            for (int i = ori - 1; i < i_end; i++) bq += quals[i];
-                        }
-                        const bool pass = (double)bq >= p.t.min_indel_baseq * (double)n;
-                        if (MODE == 0) {
-                            if (pass && (int)quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
-                            if (1 + elen <= 61 && pass) {                        // :461-464
-                                if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], strand_inc);
-                                atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
-                            }
-                        } else if (1 + elen <= 61 && pass) {
-                            record_event(p, s, 2, (int)rev, elen, bo + ori - 1);
-                        }
-                    }
-                }
-            } else if (op == 2) {                                               // DEL, :491-555
-                const int ol = a - 1;
-                if (ol >= 0 && ol < nv) {
-                    const int64_t rem = c.ref_len - c.t_lo - ol;                 // reference bytes from the anchor on
-                    int elen = len + 1;                                          // substr truncation, :500
-                    if ((int64_t)elen > rem) elen = (int)rem;
-                    if (MODE == 0) {
-                        if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 5) * c.P + ol], strand_inc);   // :497
-                        if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);            // :511-512
-                    } else {
-                        const int s = c.site_slot[ol];
-                        if (s >= 0 && (c.pflag[ol] & PF_DEL) && 1 + elen <= 61)
-                            record_event(p, s, 3, (int)rev, elen, c.ref_off + c.t_lo + ol);
-                    }
-                }
-                if (MODE == 0) {                                                 // :542-552
-                    const int i_lo = a < 0 ? -a : 0;
-                    int i_hi = nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
-                    for (int i = i_lo; i <= i_hi; i++) {
-                        const int pl = a + i;
-                        if (c.rcls[pl] != 0xff) atomicAdd(&c.cnt[(C_CLS + 6) * c.P + pl], strand_inc);
-                    }
-                }
+// A base that passes the quality threshold and differs from the reference byte (raw compare, :394-425)
+__device__ __forceinline__ void count_mismatch(const TileCtx& c, int pl, uint8_t base, uint32_t inc) {
+    atomicAdd(&c.cnt[C_COV2 * c.P + pl], 0x10000u);          // snp_count
+    const int rc = c.rcls[pl];
+    const int lu = c.lut[base];                               // class | dense-allele flag << 3
+    const int cb = lu & 7;
+    if (rc != 0xff && cb != rc) {
+        atomicAdd(&c.cnt[C_DEV * c.P + pl], inc);
+        if (cb < 6) atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl], inc);
+        else { atomicAdd(&c.cnt[C_DELD * c.P + pl], inc); if (pl + 1 < c.n_valid) atomicAdd(&c.cnt[C_DELD * c.P + pl + 1], 0u - inc); }
+    }
+    if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl], inc);
+}
+
+// Pass 2 of a work unit: the warp streams the read bases that the collected match pieces cover, one aligned 16-base
+// chunk per lane (two coalesced 16-byte loads: bases and qualities). A lane finds the pieces that overlap its chunk in
+// the warp's table, lines the tile's reference bytes up with the chunk (aligned shared-memory words + funnel shifts)
+// and tests all 16 bases at once with byte-parallel arithmetic; only EXCEPTIONS cost anything further:
+//   q <  min_snp_baseq : the base does not count (:378) -> it takes itself out of the coverage difference array
+//   base != reference  : snp_count, class deviation, SNP allele count (:394-425)
+__device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx& x, const int32_t* t_beg,
+                            const uint32_t* t_pc, int n_e, int lane) {
+    const int base0 = t_beg[0] & ~15;
+    const int range_end = t_beg[n_e - 1] + (int)(t_pc[n_e - 1] >> 16);
+    const int n_chunks = (range_end - base0 + 15) >> 4;
+    const uint32_t thr4 = (uint32_t)(p.qthr > 255 ? 255 : p.qthr) * 0x01010101u;
+    const bool vec_ok = x.bo + (((int64_t)range_end + 15) & ~(int64_t)15) <= p.b.n_bases;
+    for (int cb = 0; cb < n_chunks; cb += 32) {
+        const int ci = cb + lane;
+        if (ci >= n_chunks) break;
+        const int c0 = base0 + 16 * ci;
+        uint4 ub, uq;
+        if (vec_ok) {
+            ub = __ldg((const uint4*)(x.bases + c0));
+            uq = __ldg((const uint4*)(x.quals + c0));
+        } else {                                             // last read of a batch whose arrays are not padded
+            uint32_t tb[4] = {0u, 0u, 0u, 0u}, tq[4] = {0u, 0u, 0u, 0u};
+            for (int j = 0; j < 16 && x.bo + c0 + j < p.b.n_bases; j++) {
+                tb[j >> 2] |= (uint32_t)x.bases[c0 + j] << ((j & 3) * 8);
+                tq[j >> 2] |= (uint32_t)x.quals[c0 + j] << ((j & 3) * 8);
             }
+            ub = make_uint4(tb[0], tb[1], tb[2], tb[3]); uq = make_uint4(tq[0], tq[1], tq[2], tq[3]);
         }
-
-        if (MODE == 0) {
-            // The clipped match runs of these 32 ops are cut into sub-runs of at most SUB bases; each lane takes ONE sub-run
-            // (contiguous read bases AND contiguous reference positions, so no CIGAR logic in the inner loop): five aligned
-            // 32-bit loads + funnel shifts fetch its bases / qualities / reference bytes, then a fully unrolled loop issues
-            // one predicated shared-memory atomic per passing base. SUB is odd, so lanes walking one long run hit 32
-            // different banks. Mismatches (a few per cent) are collected in a bit mask and handled after the loop.
-            const int n_sub = (m_cnt + SUB - 1) / SUB;
-            int incl = n_sub;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total > 0) {
-                const int pref = incl - n_sub;                              // first sub-run of this lane's op
-                const unsigned nz = __ballot_sync(0xffffffffu, n_sub > 0);
-                const int rank = __popc(nz & ((1u << lane) - 1u));
-                __syncwarp();
-                if (n_sub > 0) { s_pref[rank] = pref; s_ri0[rank] = m_ri0; s_p0[rank] = m_p0; s_last[rank] = m_last; s_cnt[rank] = m_cnt; }
-                __syncwarp();
-                const int padded = (read_len + 15) & ~15;                   // reads are stored padded to 16 bytes
-                int s_first = 0;                                            // compacted op that holds sub-run jb
-                for (int jb = 0; jb < total; jb += 32) {
-                    // sub-run v belongs to compacted op  #{ops whose first sub-run <= v} - 1: one warp OR-reduction per block
-                    const int sl = pref - jb;                               // ops starting inside (jb, jb + 32]
-                    const unsigned bit = (n_sub > 0 && sl >= 1 && sl <= 32) ? (1u << (sl - 1)) : 0u;
-                    const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
-                    const int sidx = s_first + __popc(mask & ((1u << lane) - 1u));
-                    s_first += __popc(mask);
-                    const int v = jb + lane;
-                    if (v < total) {
-                        const int off = (v - s_pref[sidx]) * SUB;
-                        int cnt = s_cnt[sidx] - off; if (cnt > SUB) cnt = SUB;
-                        const int ri = s_ri0[sidx] + off;                   // first read base of the sub-run
-                        const int pos = s_p0[sidx] + off;                   // its tile-local reference position
-                        const int skip_i = s_last[sidx] - off;              // anchor base (no REF decrement) if in [0, cnt)
-                        const int off4 = ri & ~3;
-                        const uint32_t* gb = (const uint32_t*)(bases + off4);
-                        const uint32_t* gq = (const uint32_t*)(quals + off4);
-                        const uint32_t* sr = (const uint32_t*)(c.ref_s + (pos & ~3));
-                        uint32_t wb[5], wq[5], wr[5];
-#pragma unroll
-                        for (int j = 0; j < 5; j++) {
-                            const bool in = off4 + 4 * j < padded;
-                            wb[j] = in ? __ldg(gb + j) : 0u;
-                            wq[j] = in ? __ldg(gq + j) : 0u;
-                            wr[j] = sr[j];
-                        }
-                        const int sh = (ri & 3) * 8, shr = (pos & 3) * 8;
-                        uint32_t vq[4], vx[4];                              // qualities; bases XOR reference (0 = raw match)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            vq[j] = __funnelshift_r(wq[j], wq[j + 1], sh);
-                            vx[j] = __funnelshift_r(wb[j], wb[j + 1], sh) ^ __funnelshift_r(wr[j], wr[j + 1], shr);
-                        }
-                        uint32_t* tcnt = &c.cnt[C_T * c.P + pos];
-                        uint32_t mm = 0;
-#pragma unroll
-                        for (int i = 0; i < SUB; i++) {
-                            const int q = (int)((vq[i >> 2] >> ((i & 3) * 8)) & 0xffu);
-                            if (i < cnt && q >= p.qthr) {                        // :378
-                                atomicAdd(tcnt + i, strand_inc);                 // coverage, REF and the base's own class
-                                if ((vx[i >> 2] >> ((i & 3) * 8)) & 0xffu) mm |= 1u << i;   // raw compare, :394
-                            }
-                        }
-                        if (skip_i >= 0 && skip_i < cnt && (int)__ldg(quals + ri + skip_i) >= p.qthr)
-                            atomicAdd(&c.cnt[C_SKIP * c.P + pos + skip_i], strand_inc);
-                        while (mm) {                                             // mismatching bases (rare path)
-                            const int i = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const int pl = pos + i;
-                            atomicAdd(&c.cnt[C_COV2 * c.P + pl], 0x10000u);      // snp_count
-                            const int rc = c.rcls[pl];
-                            const int lu = c.lut[__ldg(bases + ri + i)];         // class | dense-allele flag << 3
-                            const int cb = lu & 7;
-                            if (rc != 0xff && cb != rc) {
-                                atomicAdd(&c.cnt[C_DEV * c.P + pl], strand_inc);
-                                atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl], strand_inc);
-                            }
-                            if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl], strand_inc);
-                        }
-                    }
+        // last piece that starts at or before the chunk (upper_bound - 1), else the first one
+        int lo = 0, hi = n_e;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (t_beg[mid] <= c0) lo = mid + 1; else hi = mid; }
+        int e = lo > 0 ? lo - 1 : 0;
+        const uint32_t lq0 = lowq_mask(uq.x, p.qthr, thr4), lq1 = lowq_mask(uq.y, p.qthr, thr4),
+                       lq2 = lowq_mask(uq.z, p.qthr, thr4), lq3 = lowq_mask(uq.w, p.qthr, thr4);
+        const uint32_t lowq16 = movemask4(lq0) | (movemask4(lq1) << 4) | (movemask4(lq2) << 8) | (movemask4(lq3) << 12);
+        for (; e < n_e; e++) {
+            const int beg = t_beg[e];
+            if (beg >= c0 + 16) break;
+            const uint32_t pc = t_pc[e];
+            int jb = beg - c0, je = jb + (int)(pc >> 16);
+            const int rp = (int)(pc & 0xffffu) - jb;           // tile position of the chunk's byte 0 (>= -15)
+            if (jb < 0) jb = 0;
+            if (je > 16) je = 16;
+            if (je <= jb) continue;
+            const uint32_t* sr = (const uint32_t*)(c.ref_s + (rp & ~3));   // ref_s has REF_PAD bytes in front
+            const uint32_t r0 = sr[0], r1 = sr[1], r2 = sr[2], r3 = sr[3], r4 = sr[4];
+            const int sh = (rp & 3) * 8;
+            const uint32_t n0 = nonzero_mask(ub.x ^ __funnelshift_r(r0, r1, sh)), n1 = nonzero_mask(ub.y ^ __funnelshift_r(r1, r2, sh)),
+                           n2 = nonzero_mask(ub.z ^ __funnelshift_r(r2, r3, sh)), n3 = nonzero_mask(ub.w ^ __funnelshift_r(r3, r4, sh));
+            const uint32_t bm = (0xffffu >> (16 - je)) & (0xffffu << jb);
+            uint32_t ex = (movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12) | lowq16) & bm;
+            while (ex) {                                         // a few per cent of the bases
+                const int j = __ffs(ex) - 1;
+                ex &= ex - 1;
+                const int pl = rp + j;
+                if ((lowq16 >> j) & 1u) {
+                    atomicAdd(&c.cnt[C_T * c.P + pl], x.dec);
+                    if (pl + 1 < x.nv) atomicAdd(&c.cnt[C_T * c.P + pl + 1], x.inc);
+                } else {
+                    count_mismatch(c, pl, __ldg(x.bases + c0 + j), x.inc);
                 }
             }
         }
     }
 }
+
+// Phase A work unit: CIGAR ops [k_begin, k_end) of one read (whole warp); populate_summary_matrix, :337-566.
+// Pass 1, lane per op: a match run only marks where it enters and leaves the tile in the coverage difference array
+// and files its clipped base range in the warp's piece table; inserts and deletes do their anchor counting here (the
+// anchor's missing REFF/REFR decrement of :381-391 is charged by the insert/delete op that follows the run).
+__device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
+    const PvReadBatch& b = p.b;
+    const ReadCtx x = make_read_ctx(p, c, r);
+    int32_t* t_beg = c.scratch;                              // [TBL] read index of the piece's first base
+    uint32_t* t_pc = (uint32_t*)(c.scratch + TBL);           // [TBL] tile position of that base | piece length << 16
+    int n_e = 0;
+    for (int kb = k_begin; kb < k_end; kb += 32) {
+        const int k = kb + lane;
+        const bool have = k < k_end;
+        const uint32_t w = have ? b.cigar[x.co + k] : 0u;
+        const int op = have ? (int)(w & 15u) : 15;
+        const int len = (int)(w >> 4);
+        int64_t a64 = have ? x.rel_t + (int64_t)x.oref[k] : 0;                   // op start, tile-local
+        if (a64 > (1 << 30)) a64 = (1 << 30);
+        if (a64 < -(1 << 30)) a64 = -(1 << 30);
+        const int a = (int)a64;
+        const int ori = have ? x.ori_a[k] : 0;
+        int m_cnt = 0, m_ri0 = 0, m_p0 = 0;
+
+        const bool reached = a <= x.l_end;                   // an op that starts beyond ref_end is never reached (:355)
+        if (have && is_match_op(op)) {
+            if (reached) {
+                const int i_lo = a < 0 ? -a : 0;
+                int i_hi = x.nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
+                if (i_hi > x.read_len - 1 - ori) i_hi = x.read_len - 1 - ori;
+                if (i_hi >= i_lo) {
+                    m_cnt = i_hi - i_lo + 1; m_ri0 = ori + i_lo; m_p0 = a + i_lo;
+                    atomicAdd(&c.cnt[C_T * c.P + m_p0], x.inc);
+                    if (m_p0 + m_cnt < x.nv) atomicAdd(&c.cnt[C_T * c.P + m_p0 + m_cnt], x.dec);
+                }
+            }
+        } else if (have && (op == 1 || op == 2)) {
+            const int ol = a - 1;                                                 // anchor position
+            if (ol >= 0 && ol < x.nv) {
+                // anchor rule (:381-391): the base in front of this op is the last base of a match run -> that base keeps
+                // its REFF/REFR decrement for itself. Depends only on the op TYPE, not on whether this op is reached.
+                if (k > 0 && ori >= 1 && ori - 1 < x.read_len) {
+                    const uint32_t pw = b.cigar[x.co + k - 1];
+                    if (is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u && (int)x.quals[ori - 1] >= p.qthr)
+                        atomicAdd(&c.cnt[C_SKIP * c.P + ol], x.inc);
+                }
+                if (reached && op == 1) {                                         // IN, :431-490
+                    if (ori >= 1 && ori - 1 < x.read_len) {
+                        const int n = len + 1;                                    // :442
+                        int elen = n;                                             // substr truncation, :439
+                        if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
+                        if (insert_quality_pass(p, x, ori, n)) {
+                            if ((int)x.quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
+                            if (1 + elen <= 61) {                                 // :461-464
+                                if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], x.inc);
+                                atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
+                            }
+                        }
+                    }
+                } else if (reached) {                                             // DEL anchor, :491-540
+                    const int64_t rem = c.ref_len - c.t_lo - ol;                  // reference bytes from the anchor on
+                    int elen = len + 1;                                           // substr truncation, :500
+                    if ((int64_t)elen > rem) elen = (int)rem;
+                    if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 5) * c.P + ol], x.inc);   // :497
+                    if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);       // :511-512
+                }
+            }
+            if (reached && op == 2) {                                             // deleted span, :542-552
+                const int i_lo = a < 0 ? -a : 0;
+                int i_hi = x.nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
+                if (i_hi >= i_lo) {
+                    atomicAdd(&c.cnt[C_DELD * c.P + a + i_lo], x.inc);
+                    if (a + i_hi + 1 < x.nv) atomicAdd(&c.cnt[C_DELD * c.P + a + i_hi + 1], x.dec);
+                }
+            }
+        }
+        // file the match pieces of these 32 ops (in op order) and scan the table when it may overflow next time
+        const unsigned nz = __ballot_sync(0xffffffffu, m_cnt > 0);
+        if (m_cnt > 0) {
+            const int at = n_e + __popc(nz & ((1u << lane) - 1u));
+            t_beg[at] = m_ri0;
+            t_pc[at] = (uint32_t)m_p0 | ((uint32_t)m_cnt << 16);
+        }
+        n_e += __popc(nz);
+        if (n_e > TBL - 32 || kb + 32 >= k_end) {
+            __syncwarp();
+            if (n_e > 0) scan_pieces(p, c, x, t_beg, t_pc, n_e, lane);
+            n_e = 0;
+            __syncwarp();
+        }
+    }
+}
+
+// Phase C work unit: re-walks CIGAR ops [k_begin, k_end) of one read (whole warp, lane per op) and records the
+// insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and :507-535, needed only
+// where the site thresholds passed).
+__device__ void record_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
+    const PvReadBatch& b = p.b;
+    const ReadCtx x = make_read_ctx(p, c, r);
+    for (int kb = k_begin; kb < k_end; kb += 32) {
+        const int k = kb + lane;
+        if (k >= k_end) break;
+        const uint32_t w = b.cigar[x.co + k];
+        const int op = (int)(w & 15u);
+        if (op != 1 && op != 2) continue;
+        const int len = (int)(w >> 4);
+        int64_t a64 = x.rel_t + (int64_t)x.oref[k];
+        if (a64 > (1 << 30)) a64 = (1 << 30);
+        if (a64 < -(1 << 30)) a64 = -(1 << 30);
+        const int a = (int)a64;
+        if (a > x.l_end) continue;
+        const int ol = a - 1;
+        if (ol < 0 || ol >= x.nv) continue;
+        const int s = c.site_slot[ol];
+        if (s < 0) continue;
+        if (op == 1) {
+            const int ori = x.ori_a[k];
+            if (!(c.pflag[ol] & PF_INS) || ori < 1 || ori - 1 >= x.read_len) continue;
+            const int n = len + 1;
+            int elen = n;
+            if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
+            if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n)) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
+        } else {
+            if (!(c.pflag[ol] & PF_DEL)) continue;
+            const int64_t rem = c.ref_len - c.t_lo - ol;
+            int elen = len + 1;
+            if ((int64_t)elen > rem) elen = (int)rem;
+            if (1 + elen <= 61) record_event(p, s, 3, (int)x.rev, elen, c.ref_off + c.t_lo + ol);
+        }
+    }
+}
+
 
 // SNP alleles whose byte is not an upper-case A/C/G/T (":398 candidate_string = '1' + alt" keeps the raw byte): rare,
 // recorded after the fact for registered sites only. One thread per read.
@@ -534,14 +609,13 @@ __device__ void for_each_unit(const SumParams& p, const TileCtx& c, WorkUnit* s_
             const int64_t span = p.read_span[r];
             // touched positions: aligned/deleted [rel, rel+span-1] and insert/delete anchors [rel-1, rel+span-1]
             if (rel - 1 > t_hi || rel + span - 1 < t_lo) continue;
-            // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] <= min(t_hi + 1, L - 1) (an op that starts beyond
-            // ref_end is never reached, :355) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
+            // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] <= t_hi + 1 (an insert/delete right behind the tile
+            // anchors on its last position) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
             const int32_t* oref = p.op_ref + b.read_cigar_off[r];
             const int n_ops = b.read_n_ops[r];
             int k_lo = lower_bound_i32(oref, n_ops, t_lo - rel) - 1;
             if (k_lo < 0) k_lo = 0;
-            const int64_t a_max = (t_hi + 1 < c.L - 1) ? t_hi + 1 : c.L - 1;
-            const int k_hi = lower_bound_i32(oref, n_ops, a_max - rel + 1);
+            const int k_hi = lower_bound_i32(oref, n_ops, t_hi + 1 - rel + 1);
             const int n_k = k_hi - k_lo;
             if (n_k <= 0) continue;
             int per = UNIT_OPS;
@@ -562,7 +636,8 @@ __device__ void for_each_unit(const SumParams& p, const TileCtx& c, WorkUnit* s_
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
             const WorkUnit w = s_list[i];
-            walk_unit<MODE>(p, c, base + w.read, w.k_begin, w.k_end, lane);
+            if (MODE == 0) accumulate_unit(p, c, base + w.read, w.k_begin, w.k_end, lane);
+            else record_unit(p, c, base + w.read, w.k_begin, w.k_end, lane);
         }
         __syncthreads();
     }
@@ -582,7 +657,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
     c.cnt = (uint32_t*)smem;
     c.site_slot = (int32_t*)smem;                                     // aliases cnt row 0 after phase B
     c.scratch = (int32_t*)(smem + (size_t)NC * P * 4) + warp * WARP_SCRATCH;
-    c.ref_s = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4;   // P + 32 bytes (word loads overrun)
+    uint8_t* ref_raw = smem + (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4;   // REF_PAD + P + 32 bytes
+    c.ref_s = ref_raw + REF_PAD;                                       // word loads under- and overrun the tile
     c.pflag = c.ref_s + P + 32;
     c.rcls = c.pflag + P;
     c.lut = c.rcls + P;
@@ -597,6 +673,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
 
     for (int i = tid; i < NC * P; i += K1_THREADS) c.cnt[i] = 0;
     if (tid < 32) c.ref_s[P + tid] = 0;
+    if (tid < REF_PAD) ref_raw[tid] = 0;
     for (int i = tid; i < P; i += K1_THREADS) {
         const uint8_t rbyte = i < c.n_valid ? b.ref[c.ref_off + c.t_lo + i] : (uint8_t)'N';
         c.ref_s[i] = rbyte;
@@ -610,6 +687,31 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
     for_each_unit<0>(p, c, s_list, &s_n, &s_next);
 
     // ---- phase B: image rows, site thresholds ---------------------------------------------------------------------
+    // difference arrays -> counts: in-place inclusive prefix sums over the tile (packed words, modulo 2^32: the true
+    // value of every field of a prefix is a count in [0, 65535]). Thread t owns words 4t .. 4t+3.
+    {
+        __shared__ uint32_t s_wsum[2][K1_WARPS];
+        const bool act = 4 * tid < P;                                   // P is a multiple of 4
+        uint4 vt = make_uint4(0u, 0u, 0u, 0u), vd = vt;
+        if (act) { vt = *(const uint4*)&c.cnt[C_T * P + 4 * tid]; vd = *(const uint4*)&c.cnt[C_DELD * P + 4 * tid]; }
+        vt.y += vt.x; vt.z += vt.y; vt.w += vt.z;
+        vd.y += vd.x; vd.z += vd.y; vd.w += vd.z;
+        uint32_t it = vt.w, id = vd.w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, it, d), e = __shfl_up_sync(0xffffffffu, id, d);
+            if (lane >= d) { it += a; id += e; }
+        }
+        if (lane == 31) { s_wsum[0][warp] = it; s_wsum[1][warp] = id; }
+        __syncthreads();
+        uint32_t ot = it - vt.w, od = id - vd.w;                        // exclusive prefix inside the warp
+        for (int w2 = 0; w2 < warp; w2++) { ot += s_wsum[0][w2]; od += s_wsum[1][w2]; }
+        if (act) {
+            *(uint4*)&c.cnt[C_T * P + 4 * tid] = make_uint4(vt.x + ot, vt.y + ot, vt.z + ot, vt.w + ot);
+            *(uint4*)&c.cnt[C_DELD * P + 4 * tid] = make_uint4(vd.x + od, vd.y + od, vd.z + od, vd.w + od);
+        }
+        __syncthreads();
+    }
     int my_site[MAX_PPT];
 #pragma unroll
     for (int u = 0; u < MAX_PPT; u++) {
@@ -863,11 +965,11 @@ int choose_tile(int64_t total_positions, int32_t n_regions) {
     // large tiles amortise the per-(tile, read) set-up; small batches need enough CTAs to cover the 148 SMs
     const int sms = 148;
     int P = P_MAX;
-    while (P > 352 && (total_positions / P + n_regions) < 4 * sms) P >>= 1;
+    while (P > 320 && (total_positions / P + n_regions) < 4 * sms) P >>= 1;
     return P;
 }
 
-size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4 + 3 * (size_t)P + 32 + 256 + 16; }
+size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4 + REF_PAD + 3 * (size_t)P + 32 + 256 + 16; }
 
 Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
     Plan pl;

@@ -14,13 +14,17 @@ db = device.DeviceBatch(b)
 cap = max(4096, b.total_positions // 50)
 ws = device.SummaryWorkspace.for_batch(db, cap)
 torch.cuda.synchronize()
+lib = capi.load()
 for it in range(5):
+    lib.pv_profile_reset(); lib.pv_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     device.summary_regions(db, thr, ws)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    lib.pv_profile_enable(0)
+    prof = {k: round(v[0], 3) for k, v in capi.profile_collect().items() if v[0] > 0}
     K = int(ws.count.item())
     ab = b.algorithmic_bytes(K)
     print("iter %d: %.3f ms  K=%d status=%d  %.1f Mbp/s  %.1f GB/s algorithmic (%.3f of 6536)" % (
-        it, ms, K, ws.status(), b.candidate_bp / ms / 1e3, ab / ms / 1e6, ab / ms / 1e6 / 6536), flush=True)
+        it, ms, K, ws.status(), b.candidate_bp / ms / 1e3, ab / ms / 1e6, ab / ms / 1e6 / 6536), prof, flush=True)
