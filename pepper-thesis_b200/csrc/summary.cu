@@ -32,8 +32,8 @@ constexpr int P_MAX = 1280;      // 2 CTAs per SM: 16 words x 1280 positions = 8
 constexpr int UNITS_PER_READ = 8;// a read's ops inside the tile are split into at most this many work units
 constexpr int LIST_CAP = 512;    // work units per round
 constexpr int UNIT_OPS = 256;    // preferred CIGAR ops per work unit (normally the read's whole stretch inside the tile)
-constexpr int TBL = 128;         // match pieces a warp collects before it scans their bases
-constexpr int WARP_SCRATCH = 2 * TBL + 4;   // ints of per-warp scratch: piece table (first read index | tile position, length)
+constexpr int TBL = 96;          // match pieces a warp collects before it scans their bases
+constexpr int WARP_SCRATCH = 3 * TBL + 4;   // ints of per-warp scratch: piece table (read index, tile position | length, sub-piece prefix)
 constexpr int REF_PAD = 16;      // bytes in front of the tile's reference copy (a 16-base chunk may start before the tile)
 constexpr int WIN_ELEMS = PV_WINDOW * PV_FEATURES;   // 858
 
@@ -318,70 +318,75 @@ __device__ __forceinline__ void count_mismatch(const TileCtx& c, int pl, uint8_t
     if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl], inc);
 }
 
-// Pass 2 of a work unit: the warp streams the read bases that the collected match pieces cover, one aligned 16-base
-// chunk per lane (two coalesced 16-byte loads: bases and qualities). A lane finds the pieces that overlap its chunk in
-// the warp's table, lines the tile's reference bytes up with the chunk (aligned shared-memory words + funnel shifts)
-// and tests all 16 bases at once with byte-parallel arithmetic; only EXCEPTIONS cost anything further:
+// Pass 2 of a work unit: the match pieces the warp collected are cut at the read's 16-byte boundaries into SUB-PIECES
+// (a piece of 33 bases has 3 of them), one per lane. A lane loads its aligned 16-base chunk of bases and qualities
+// (two 16-byte loads, neighbouring lanes mostly neighbouring chunks), lines the tile's reference bytes up with the
+// chunk (five aligned shared-memory words + funnel shifts) and tests all 16 bases at once with byte-parallel
+// arithmetic. The code is straight-line for every lane; only EXCEPTIONS cost anything further:
 //   q <  min_snp_baseq : the base does not count (:378) -> it takes itself out of the coverage difference array
 //   base != reference  : snp_count, class deviation, SNP allele count (:394-425)
+// Table per piece: t_beg = read index of its first base, t_pc = tile position of that base | length << 16,
+// t_sub = number of sub-pieces in front of it.
 __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx& x, const int32_t* t_beg,
-                            const uint32_t* t_pc, int n_e, int lane) {
-    const int base0 = t_beg[0] & ~15;
-    const int range_end = t_beg[n_e - 1] + (int)(t_pc[n_e - 1] >> 16);
-    const int n_chunks = (range_end - base0 + 15) >> 4;
+                            const uint32_t* t_pc, const int32_t* t_sub, int n_e, int n_sub, int lane) {
     const uint32_t thr4 = (uint32_t)(p.qthr > 255 ? 255 : p.qthr) * 0x01010101u;
+    const int range_end = t_beg[n_e - 1] + (int)(t_pc[n_e - 1] >> 16);
     const bool vec_ok = x.bo + (((int64_t)range_end + 15) & ~(int64_t)15) <= p.b.n_bases;
-    for (int cb = 0; cb < n_chunks; cb += 32) {
-        const int ci = cb + lane;
-        if (ci >= n_chunks) break;
-        const int c0 = base0 + 16 * ci;
-        uint4 ub, uq;
-        if (vec_ok) {
-            ub = __ldg((const uint4*)(x.bases + c0));
-            uq = __ldg((const uint4*)(x.quals + c0));
-        } else {                                             // last read of a batch whose arrays are not padded
-            uint32_t tb[4] = {0u, 0u, 0u, 0u}, tq[4] = {0u, 0u, 0u, 0u};
-            for (int j = 0; j < 16 && x.bo + c0 + j < p.b.n_bases; j++) {
-                tb[j >> 2] |= (uint32_t)x.bases[c0 + j] << ((j & 3) * 8);
-                tq[j >> 2] |= (uint32_t)x.quals[c0 + j] << ((j & 3) * 8);
-            }
-            ub = make_uint4(tb[0], tb[1], tb[2], tb[3]); uq = make_uint4(tq[0], tq[1], tq[2], tq[3]);
-        }
-        // last piece that starts at or before the chunk (upper_bound - 1), else the first one
-        int lo = 0, hi = n_e;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (t_beg[mid] <= c0) lo = mid + 1; else hi = mid; }
-        int e = lo > 0 ? lo - 1 : 0;
-        const uint32_t lq0 = lowq_mask(uq.x, p.qthr, thr4), lq1 = lowq_mask(uq.y, p.qthr, thr4),
-                       lq2 = lowq_mask(uq.z, p.qthr, thr4), lq3 = lowq_mask(uq.w, p.qthr, thr4);
-        const uint32_t lowq16 = movemask4(lq0) | (movemask4(lq1) << 4) | (movemask4(lq2) << 8) | (movemask4(lq3) << 12);
-        for (; e < n_e; e++) {
+    int e_first = 0;                                         // piece that holds sub-piece jb
+    for (int jb = 0; jb < n_sub; jb += 32) {
+        // sub-piece v belongs to piece  e_first + #{pieces whose first sub-piece is in (jb, v]}: the (at most 32) pieces
+        // that start inside this block mark their start in a bit mask, one warp OR-reduction per block
+        const int idx = e_first + 1 + lane;
+        const int sv = idx < n_e ? t_sub[idx] - jb - 1 : -1;
+        const unsigned mask = __reduce_or_sync(0xffffffffu, (sv >= 0 && sv < 32) ? (1u << sv) : 0u);
+        const int e = e_first + __popc(mask & ((1u << lane) - 1u));
+        e_first += __popc(mask);
+        const int v = jb + lane;
+        uint32_t ex = 0, lowq16 = 0;
+        int rp = 0, c0 = 0;
+        if (v < n_sub) {
             const int beg = t_beg[e];
-            if (beg >= c0 + 16) break;
             const uint32_t pc = t_pc[e];
-            int jb = beg - c0, je = jb + (int)(pc >> 16);
-            const int rp = (int)(pc & 0xffffu) - jb;           // tile position of the chunk's byte 0 (>= -15)
-            if (jb < 0) jb = 0;
-            if (je > 16) je = 16;
-            if (je <= jb) continue;
+            c0 = ((beg >> 4) + (v - t_sub[e])) << 4;           // first read index of the chunk
+            uint4 ub, uq;
+            if (vec_ok) {
+                ub = __ldg((const uint4*)(x.bases + c0));
+                uq = __ldg((const uint4*)(x.quals + c0));
+            } else {                                           // last read of a batch whose arrays are not padded
+                uint32_t tb[4] = {0u, 0u, 0u, 0u}, tq[4] = {0u, 0u, 0u, 0u};
+                for (int j = 0; j < 16 && x.bo + c0 + j < p.b.n_bases; j++) {
+                    tb[j >> 2] |= (uint32_t)x.bases[c0 + j] << ((j & 3) * 8);
+                    tq[j >> 2] |= (uint32_t)x.quals[c0 + j] << ((j & 3) * 8);
+                }
+                ub = make_uint4(tb[0], tb[1], tb[2], tb[3]); uq = make_uint4(tq[0], tq[1], tq[2], tq[3]);
+            }
+            int b0 = beg - c0, b1 = b0 + (int)(pc >> 16);      // the piece's bytes of the chunk: [b0, b1) clipped to [0, 16)
+            rp = (int)(pc & 0xffffu) - b0;                     // tile position of the chunk's byte 0 (>= -15)
+            b0 = b0 < 0 ? 0 : b0;
+            b1 = b1 > 16 ? 16 : b1;
             const uint32_t* sr = (const uint32_t*)(c.ref_s + (rp & ~3));   // ref_s has REF_PAD bytes in front
             const uint32_t r0 = sr[0], r1 = sr[1], r2 = sr[2], r3 = sr[3], r4 = sr[4];
             const int sh = (rp & 3) * 8;
             const uint32_t n0 = nonzero_mask(ub.x ^ __funnelshift_r(r0, r1, sh)), n1 = nonzero_mask(ub.y ^ __funnelshift_r(r1, r2, sh)),
                            n2 = nonzero_mask(ub.z ^ __funnelshift_r(r2, r3, sh)), n3 = nonzero_mask(ub.w ^ __funnelshift_r(r3, r4, sh));
-            const uint32_t bm = (0xffffu >> (16 - je)) & (0xffffu << jb);
-            uint32_t ex = (movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12) | lowq16) & bm;
-            while (ex) {                                         // a few per cent of the bases
-                const int j = __ffs(ex) - 1;
-                ex &= ex - 1;
-                const int pl = rp + j;
-                if ((lowq16 >> j) & 1u) {
-                    atomicAdd(&c.cnt[C_T * c.P + pl], x.dec);
-                    if (pl + 1 < x.nv) atomicAdd(&c.cnt[C_T * c.P + pl + 1], x.inc);
-                } else {
-                    count_mismatch(c, pl, __ldg(x.bases + c0 + j), x.inc);
-                }
+            const uint32_t l0 = lowq_mask(uq.x, p.qthr, thr4), l1 = lowq_mask(uq.y, p.qthr, thr4),
+                           l2 = lowq_mask(uq.z, p.qthr, thr4), l3 = lowq_mask(uq.w, p.qthr, thr4);
+            const uint32_t bm = (0xffffu >> (16 - b1)) & (0xffffu << b0);
+            lowq16 = (movemask4(l0) | (movemask4(l1) << 4) | (movemask4(l2) << 8) | (movemask4(l3) << 12)) & bm;
+            ex = ((movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12)) & bm) | lowq16;
+        }
+        while (ex) {                                             // a few per cent of the bases
+            const int j = __ffs(ex) - 1;
+            ex &= ex - 1;
+            const int pl = rp + j;
+            if ((lowq16 >> j) & 1u) {
+                atomicAdd(&c.cnt[C_T * c.P + pl], x.dec);
+                if (pl + 1 < x.nv) atomicAdd(&c.cnt[C_T * c.P + pl + 1], x.inc);
+            } else {
+                count_mismatch(c, pl, __ldg(x.bases + c0 + j), x.inc);
             }
         }
+        __syncwarp();
     }
 }
 
@@ -392,9 +397,10 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
 __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
     const PvReadBatch& b = p.b;
     const ReadCtx x = make_read_ctx(p, c, r);
-    int32_t* t_beg = c.scratch;                              // [TBL] read index of the piece's first base
-    uint32_t* t_pc = (uint32_t*)(c.scratch + TBL);           // [TBL] tile position of that base | piece length << 16
-    int n_e = 0;
+    int32_t* t_beg = c.scratch;                              // [TBL]
+    uint32_t* t_pc = (uint32_t*)(c.scratch + TBL);           // [TBL]
+    int32_t* t_sub = c.scratch + 2 * TBL;                    // [TBL]
+    int n_e = 0, n_sub = 0;
     for (int kb = k_begin; kb < k_end; kb += 32) {
         const int k = kb + lane;
         const bool have = k < k_end;
@@ -406,8 +412,9 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
         if (a64 < -(1 << 30)) a64 = -(1 << 30);
         const int a = (int)a64;
         const int ori = have ? x.ori_a[k] : 0;
+        uint32_t pw = __shfl_up_sync(0xffffffffu, w, 1);                         // the op in front of this one
+        if (lane == 0) pw = k > 0 ? b.cigar[x.co + k - 1] : 0u;
         int m_cnt = 0, m_ri0 = 0, m_p0 = 0;
-
         const bool reached = a <= x.l_end;                   // an op that starts beyond ref_end is never reached (:355)
         if (have && is_match_op(op)) {
             if (reached) {
@@ -423,20 +430,19 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
         } else if (have && (op == 1 || op == 2)) {
             const int ol = a - 1;                                                 // anchor position
             if (ol >= 0 && ol < x.nv) {
+                const bool anchor_ok = ori >= 1 && ori - 1 < x.read_len;          // the anchor base exists in the read
+                const int qa = anchor_ok ? (int)x.quals[ori - 1] : 0;
                 // anchor rule (:381-391): the base in front of this op is the last base of a match run -> that base keeps
                 // its REFF/REFR decrement for itself. Depends only on the op TYPE, not on whether this op is reached.
-                if (k > 0 && ori >= 1 && ori - 1 < x.read_len) {
-                    const uint32_t pw = b.cigar[x.co + k - 1];
-                    if (is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u && (int)x.quals[ori - 1] >= p.qthr)
-                        atomicAdd(&c.cnt[C_SKIP * c.P + ol], x.inc);
-                }
+                if (k > 0 && anchor_ok && is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u && qa >= p.qthr)
+                    atomicAdd(&c.cnt[C_SKIP * c.P + ol], x.inc);
                 if (reached && op == 1) {                                         // IN, :431-490
-                    if (ori >= 1 && ori - 1 < x.read_len) {
+                    if (anchor_ok) {
                         const int n = len + 1;                                    // :442
                         int elen = n;                                             // substr truncation, :439
                         if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
                         if (insert_quality_pass(p, x, ori, n)) {
-                            if ((int)x.quals[ori - 1] < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
+                            if (qa < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
                             if (1 + elen <= 61) {                                 // :461-464
                                 if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], x.inc);
                                 atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
@@ -460,22 +466,33 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
                 }
             }
         }
-        // file the match pieces of these 32 ops (in op order) and scan the table when it may overflow next time
+        // file the match pieces of these 32 ops (in op order) with the running count of 16-base sub-pieces in front of
+        // each; scan the table when the next 32 ops might overflow it
+        const int nsp = m_cnt > 0 ? ((m_ri0 + m_cnt - 1) >> 4) - (m_ri0 >> 4) + 1 : 0;
+        int incl = nsp;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
         const unsigned nz = __ballot_sync(0xffffffffu, m_cnt > 0);
         if (m_cnt > 0) {
             const int at = n_e + __popc(nz & ((1u << lane) - 1u));
             t_beg[at] = m_ri0;
             t_pc[at] = (uint32_t)m_p0 | ((uint32_t)m_cnt << 16);
+            t_sub[at] = n_sub + incl - nsp;
         }
         n_e += __popc(nz);
+        n_sub += __shfl_sync(0xffffffffu, incl, 31);
         if (n_e > TBL - 32 || kb + 32 >= k_end) {
             __syncwarp();
-            if (n_e > 0) scan_pieces(p, c, x, t_beg, t_pc, n_e, lane);
-            n_e = 0;
+            if (n_e > 0) scan_pieces(p, c, x, t_beg, t_pc, t_sub, n_e, n_sub, lane);
+            n_e = 0; n_sub = 0;
             __syncwarp();
         }
     }
 }
+
 
 // Phase C work unit: re-walks CIGAR ops [k_begin, k_end) of one read (whole warp, lane per op) and records the
 // insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and :507-535, needed only
