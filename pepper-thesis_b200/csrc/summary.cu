@@ -25,13 +25,11 @@
 namespace {
 
 constexpr int NC = 16;           // packed 32-bit counter words per position
-constexpr int K1_THREADS = 384;
+constexpr int K1_THREADS = 512;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
 constexpr int P_MAX = 1280;      // 2 CTAs per SM: 16 words x 1280 positions = 80 KB of counters each
-constexpr int UNITS_PER_READ = 8;// a read's ops inside the tile are split into at most this many work units
-constexpr int LIST_CAP = 512;    // work units per round
-constexpr int UNIT_OPS = 256;    // preferred CIGAR ops per work unit (normally the read's whole stretch inside the tile)
+constexpr int LIST_CAP = 1024;   // reads examined per round of the tile's work list
 constexpr int TBL = 96;          // match pieces a warp collects before it scans their bases
 constexpr int WARP_SCRATCH = 3 * TBL + 4;   // ints of per-warp scratch: piece table (read index, tile position | length, sub-piece prefix)
 constexpr int REF_PAD = 16;      // bytes in front of the tile's reference copy (a 16-base chunk may start before the tile)
@@ -50,7 +48,7 @@ enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_ba
        C_DEV = 2,      // ... of which have a base class different from the (valid) reference base's class
        C_CLS = 3,      // +0..5 = A C G T I D: explicit class counts (deviating bases, insert/delete anchors)
        C_DELD = 9,     // difference array -> deleted spans ('*', :542-552); sits where class 6 would
-       C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count
+       C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count of bases that are no dense SNP allele
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
 enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_COUNT = 8 };
@@ -268,22 +266,17 @@ __device__ __forceinline__ ReadCtx make_read_ctx(const SumParams& p, const TileC
 }
 
 // sum of the insert's n = len + 1 qualities starting at the anchor base (:448-450) -> does it pass (:452)?
-__device__ __forceinline__ bool insert_quality_pass(const SumParams& p, const ReadCtx& x, int ori, int n) {
-    int64_t bq = 0;
-    const int i_end = ori - 1 + n < x.read_len ? ori - 1 + n : x.read_len;
-    if (i_end - (ori - 1) <= 8) {                            // short insert: three independent word loads
-        const int i0 = ori - 1, o4 = i0 & ~3, m = i_end - i0;
-        const uint32_t* gq = (const uint32_t*)(x.quals + o4);
-        const int pad_end = (x.read_len + 15) & ~15;           // reads are stored padded to 16 bytes
-        const uint32_t w0 = __ldg(gq), w1 = o4 + 4 < pad_end ? __ldg(gq + 1) : 0u, w2 = o4 + 8 < pad_end ? __ldg(gq + 2) : 0u;
-        const int sh = (i0 & 3) * 8;
-        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        if (m <= 4) { hi = 0; lo &= m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u); }
-        else hi &= m == 8 ? 0xffffffffu : ((1u << (8 * (m - 4))) - 1u);
-        const uint32_t s2 = (lo & 0x00ff00ffu) + ((lo >> 8) & 0x00ff00ffu) + (hi & 0x00ff00ffu) + ((hi >> 8) & 0x00ff00ffu);
-        bq = (int64_t)((s2 & 0xffffu) + (s2 >> 16));
+// qa = quality of the anchor base (already loaded by the caller)
+__device__ __forceinline__ bool insert_quality_pass(const SumParams& p, const ReadCtx& x, int ori, int n, int qa) {
+    const int i0 = ori - 1;
+    const int m = (i0 + n < x.read_len ? i0 + n : x.read_len) - i0;   // qualities that exist (>= 1)
+    int64_t bq = qa;
+    if (m <= 4) {                                            // the common short insert: independent byte loads
+        const int q1 = m > 1 ? (int)__ldg(x.quals + i0 + 1) : 0, q2 = m > 2 ? (int)__ldg(x.quals + i0 + 2) : 0,
+                  q3 = m > 3 ? (int)__ldg(x.quals + i0 + 3) : 0;
+        bq += q1 + q2 + q3;
     } else {
-        for (int i = ori - 1; i < i_end; i++) bq += x.quals[i];
+        for (int i = 1; i < m; i++) bq += x.quals[i0 + i];
     }
     return (double)bq >= p.t.min_indel_baseq * (double)n;
 }
@@ -304,18 +297,27 @@ __device__ __forceinline__ uint32_t nonzero_mask(uint32_t x) {
 // bits 7, 15, 23, 31 -> bits 0..3
 __device__ __forceinline__ uint32_t movemask4(uint32_t m) { return (((m >> 7) * 0x01020408u) >> 24) & 0xfu; }
 
-// A base that passes the quality threshold and differs from the reference byte (raw compare, :394-425)
+// A base that passes the quality threshold and differs from the reference byte (raw compare, :394-425):
+//   snp_count++;  class(base) != class(valid ref): DEV++, CLS[class]++;  base is an upper-case A/C/G/T: SNP[base]++.
+// Nearly always all three happen together, so the dense SNP allele counter stands for all of them (ONE atomic) and the
+// flush adds it back: snp_count = X + sum SNP, DEV = DEVX + sum SNP, CLS[c] = CLSX[c] + SNP[c]; the rare other
+// combinations correct the explicit counters (which may go "negative" modulo 2^32 in between).
 __device__ __forceinline__ void count_mismatch(const TileCtx& c, int pl, uint8_t base, uint32_t inc) {
-    atomicAdd(&c.cnt[C_COV2 * c.P + pl], 0x10000u);          // snp_count
     const int rc = c.rcls[pl];
     const int lu = c.lut[base];                               // class | dense-allele flag << 3
     const int cb = lu & 7;
-    if (rc != 0xff && cb != rc) {
-        atomicAdd(&c.cnt[C_DEV * c.P + pl], inc);
-        if (cb < 6) atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl], inc);
-        else { atomicAdd(&c.cnt[C_DELD * c.P + pl], inc); if (pl + 1 < c.n_valid) atomicAdd(&c.cnt[C_DELD * c.P + pl + 1], 0u - inc); }
+    const bool dev = rc != 0xff && cb != rc;
+    if (lu & 8) {
+        atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl], inc);
+        if (!dev) { atomicAdd(&c.cnt[C_DEV * c.P + pl], 0u - inc); atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl], 0u - inc); }
+    } else {
+        atomicAdd(&c.cnt[C_COV2 * c.P + pl], 0x10000u);      // snp_count of the bases that are no dense allele
+        if (dev) {
+            atomicAdd(&c.cnt[C_DEV * c.P + pl], inc);
+            if (cb < 6) atomicAdd(&c.cnt[(C_CLS + cb) * c.P + pl], inc);
+            else { atomicAdd(&c.cnt[C_DELD * c.P + pl], inc); if (pl + 1 < c.n_valid) atomicAdd(&c.cnt[C_DELD * c.P + pl + 1], 0u - inc); }
+        }
     }
-    if (lu & 8) atomicAdd(&c.cnt[(C_SNP + cb) * c.P + pl], inc);
 }
 
 // Pass 2 of a work unit: the match pieces the warp collected are cut at the read's 16-byte boundaries into SUB-PIECES
@@ -441,7 +443,7 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
                         const int n = len + 1;                                    // :442
                         int elen = n;                                             // substr truncation, :439
                         if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
-                        if (insert_quality_pass(p, x, ori, n)) {
+                        if (insert_quality_pass(p, x, ori, n, qa)) {
                             if (qa < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
                             if (1 + elen <= 61) {                                 // :461-464
                                 if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], x.inc);
@@ -522,7 +524,7 @@ __device__ void record_unit(const SumParams& p, const TileCtx& c, int64_t r, int
             const int n = len + 1;
             int elen = n;
             if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
-            if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n)) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
+            if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n, (int)x.quals[ori - 1])) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
         } else {
             if (!(c.pflag[ol] & PF_DEL)) continue;
             const int64_t rem = c.ref_len - c.t_lo - ol;
@@ -562,99 +564,55 @@ __device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, i
     record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
 }
 
-// first k in [0, n) with a[k] >= key (n if none); one thread
-// op_ref grows almost linearly with the op index, so the probe alternates between an interpolated guess and plain
-// bisection (the latter keeps the worst case logarithmic); typically 3-5 dependent loads instead of ~14
-__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int n, int64_t key) {
-    int lo = 0, hi = n;
-    if (n == 0 || (int64_t)a[0] >= key) return 0;
-    if ((int64_t)a[n - 1] < key) return n;
-    int64_t alo = a[0], ahi = a[n - 1];                 // invariant: a[lo] < key <= a[hi - 1] with lo < hi - 1 possible
-    hi = n - 1;                                         // answer in (lo, hi]
-    bool interp = true;
-    while (hi - lo > 1) {
-        int mid;
-        if (interp && ahi > alo) {
-            mid = lo + (int)(((key - alo) * (int64_t)(hi - lo)) / (ahi - alo));
-            if (mid <= lo) mid = lo + 1;
-            if (mid >= hi) mid = hi - 1;
-        } else {
-            mid = (lo + hi) >> 1;
-        }
-        interp = !interp;
-        const int64_t am = a[mid];
-        if (am < key) { lo = mid; alo = am; } else { hi = mid; ahi = am; }
-    }
-    return hi;
-}
+// The tile's work list: every read of the region that touches the tile, cut into UNIT_PARTS units. A warp that pulls a
+// unit first finds the read's op range inside the tile with two warp-wide 32-ary searches in the CIGAR prefix (coalesced
+// probes, 2-3 rounds each), then walks its share of that range. No thread-serial set-up phase: the searches of one
+// warp overlap the walking of the others.
+constexpr int UNIT_PARTS = 2;
 
-struct WorkUnit { int32_t read; int32_t k_begin; int32_t k_end; };   // read index relative to the round's first read
-
-// Builds the tile's work list (a thread per read finds the read's op range inside the tile and cuts it into units of
-// about UNIT_OPS ops) and lets the warps pull units from it.
 template <int MODE>
-__device__ void for_each_unit(const SumParams& p, const TileCtx& c, WorkUnit* s_list, int* s_n, int* s_next) {
+__device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next) {
     const PvReadBatch& b = p.b;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
     const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;
-    // how many reads touch the tile decides the granularity: normally ONE round with several units per read
-    if (tid == 0) *s_n = 0;
-    __syncthreads();
-    int mine = 0;
-    for (int64_t r = rb + tid; r < re; r += blockDim.x) {
-        if (b.read_mapq[r] == 0) continue;
-        const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
-        if (rel - 1 > t_hi || rel + (int64_t)p.read_span[r] - 1 < t_lo) continue;
-        mine++;
-    }
-    if (mine) atomicAdd(s_n, mine);
-    __syncthreads();
-    const int n_ov = *s_n;
-    __syncthreads();
-    const bool single = n_ov <= LIST_CAP;
-    int budget = 1;
-    if (single && n_ov > 0) { budget = LIST_CAP / n_ov; if (budget > UNITS_PER_READ) budget = UNITS_PER_READ; }
-    const int64_t round_reads = single ? (re - rb > 0 ? re - rb : 1) : LIST_CAP;
-    for (int64_t base = rb; base < re; base += round_reads) {
+    for (int64_t base = rb; base < re; base += LIST_CAP) {
         if (tid == 0) { *s_n = 0; *s_next = 0; }
         __syncthreads();
-        const int64_t end = base + round_reads < re ? base + round_reads : re;
+        const int64_t end = base + LIST_CAP < re ? base + LIST_CAP : re;
         for (int64_t r = base + tid; r < end; r += blockDim.x) {
             if (b.read_mapq[r] == 0) continue;                                   // :619
             const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
-            const int64_t span = p.read_span[r];
             // touched positions: aligned/deleted [rel, rel+span-1] and insert/delete anchors [rel-1, rel+span-1]
-            if (rel - 1 > t_hi || rel + span - 1 < t_lo) continue;
-            // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] <= t_hi + 1 (an insert/delete right behind the tile
-            // anchors on its last position) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
-            const int32_t* oref = p.op_ref + b.read_cigar_off[r];
-            const int n_ops = b.read_n_ops[r];
-            int k_lo = lower_bound_i32(oref, n_ops, t_lo - rel) - 1;
-            if (k_lo < 0) k_lo = 0;
-            const int k_hi = lower_bound_i32(oref, n_ops, t_hi + 1 - rel + 1);
-            const int n_k = k_hi - k_lo;
-            if (n_k <= 0) continue;
-            int per = UNIT_OPS;
-            if ((n_k + per - 1) / per > budget) per = ((n_k + budget - 1) / budget + 31) & ~31;
-            const int n_units = (n_k + per - 1) / per;
-            const int at = atomicAdd(s_n, n_units);
-            for (int u = 0; u < n_units; u++) {
-                WorkUnit w; w.read = (int32_t)(r - base); w.k_begin = k_lo + u * per;
-                w.k_end = (k_lo + (u + 1) * per < k_hi) ? k_lo + (u + 1) * per : k_hi;
-                s_list[at + u] = w;
-            }
+            if (rel - 1 > t_hi || rel + (int64_t)p.read_span[r] - 1 < t_lo) continue;
+            s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
         }
         __syncthreads();
-        const int n = *s_n;
+        const int n = *s_n * UNIT_PARTS;
         while (true) {
             int i = 0;
             if (lane == 0) i = atomicAdd(s_next, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
-            const WorkUnit w = s_list[i];
-            if (MODE == 0) accumulate_unit(p, c, base + w.read, w.k_begin, w.k_end, lane);
-            else record_unit(p, c, base + w.read, w.k_begin, w.k_end, lane);
+            const int64_t r = base + s_list[i / UNIT_PARTS];
+            const int part = i % UNIT_PARTS;
+            // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] <= t_hi + 1 (an insert/delete right behind the tile
+            // anchors on its last position) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
+            const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
+            const int32_t* oref = p.op_ref + b.read_cigar_off[r];
+            const int n_ops = b.read_n_ops[r];
+            int k_lo = warp_lower_bound(oref, n_ops, t_lo - rel, lane) - 1;
+            if (k_lo < 0) k_lo = 0;
+            const int k_hi = warp_lower_bound(oref, n_ops, t_hi + 1 - rel + 1, lane);
+            const int n_k = k_hi - k_lo;
+            if (n_k <= 0) continue;
+            int per = (n_k + UNIT_PARTS - 1) / UNIT_PARTS;
+            per = (per + 31) & ~31;                                              // whole warp steps
+            const int k_begin = k_lo + part * per;
+            const int k_end = k_begin + per < k_hi ? k_begin + per : k_hi;
+            if (k_begin >= k_end) continue;
+            if (MODE == 0) accumulate_unit(p, c, r, k_begin, k_end, lane);
+            else record_unit(p, c, r, k_begin, k_end, lane);
         }
         __syncthreads();
     }
@@ -662,7 +620,7 @@ __device__ void for_each_unit(const SumParams& p, const TileCtx& c, WorkUnit* s_
 
 __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ WorkUnit s_list[LIST_CAP];
+    __shared__ int32_t s_list[LIST_CAP];
     __shared__ int s_n, s_next, s_any_events, s_any_other;
 
     const PvReadBatch& b = p.b;
@@ -747,6 +705,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
             row[4] = -(tf - (int)(w[C_SKIP] & 0xffffu));                         // REFF = T - SKIP
             row[15] = -(tr - (int)(w[C_SKIP] >> 16));
             const int rc = c.rcls[i];
+            // the dense SNP allele counters stand for snp_count, DEV and CLS[A..T] as well (count_mismatch)
+            const uint32_t snp_sum = w[C_SNP] + w[C_SNP + 1] + w[C_SNP + 2] + w[C_SNP + 3];
+            w[C_DEV] += snp_sum;
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[C_CLS + k] += w[C_SNP + k];
 #pragma unroll
             for (int k = 0; k < 7; k++) {
                 int f = (int)(w[C_CLS + k] & 0xffffu), r = (int)(w[C_CLS + k] >> 16);
@@ -761,7 +724,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumPar
             for (int f = 0; f < PV_FEATURES; f += 2)
                 dst[f >> 1] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
 
-            const int cov = tf + tr + (int)(w[C_COV2] & 0xffffu), snp = (int)(w[C_COV2] >> 16);
+            const int cov = tf + tr + (int)(w[C_COV2] & 0xffffu);
+            const int snp = (int)(w[C_COV2] >> 16) + (int)(snp_sum & 0xffffu) + (int)(snp_sum >> 16);
             const int ins = (int)(w[C_INSDEL] & 0xffffu), del = (int)(w[C_INSDEL] >> 16);
             const double cv = (double)cov > 1.0 ? (double)cov : 1.0;             // :635-637
             const double sf = (double)snp / cv, inf = (double)ins / cv, df = (double)del / cv;
