@@ -3,6 +3,7 @@
 Artefacts (all git-ignored, all travel to the GPU box with the gpurun snapshot):
   pepper-thesis_b200/libpepper_b200.so          C-ABI library (CUDA kernels), include/pepper_b200.h
   pepper-thesis_b200/libpv_synth.so             synthetic pileup generator (tests/bench input only)
+  pepper-thesis_b200/libpv_ingest.so            BAM/FASTA ingest without htslib (host only), include/pepper_ingest.h
   pepper-thesis_b200/build/PEPPER_VARIANT*.so   pybind11 drop-in for the reference's PEPPER_VARIANT module
   oracle/libpv_oracle_port.so, oracle/_ref/*    test oracles (see oracle/Makefile)
 """
@@ -23,6 +24,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 LIB = os.path.join(PKG, "libpepper_b200.so")
 SYNTH = os.path.join(PKG, "libpv_synth.so")
+INGEST = os.path.join(PKG, "libpv_ingest.so")
 PYMOD_DIR = os.path.join(PKG, "build")
 
 
@@ -75,6 +77,14 @@ def build_synth(force=False, verbose=False):
     return SYNTH
 
 
+def build_ingest(force=False, verbose=False):
+    """Host-only BAM/FASTA ingest (zlib), include/pepper_ingest.h."""
+    src = os.path.join(CSRC, "ingest.cpp")
+    if force or _newer(INGEST, [src, os.path.join(INC, "pepper_ingest.h"), os.path.join(INC, "pepper_b200.h")]):
+        _run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wall", "-I", INC, src, "-o", INGEST, "-lz", "-lpthread"], verbose)
+    return INGEST
+
+
 def build_pymod(force=False, verbose=False):
     import pybind11
     src = os.path.join(CSRC, "pybind_module.cpp")
@@ -110,6 +120,7 @@ def build_oracle(force=False, verbose=False):
 
 def build_all(force=False, verbose=False):
     build_synth(force, verbose)
+    build_ingest(force, verbose)
     build_lib(force, verbose)
     build_pymod(force, verbose)
     build_oracle(force, verbose)
