@@ -83,6 +83,7 @@ int pv_bam_get_reads(PvBamFile* bam, const char* contig, int64_t start, int64_t 
 int pv_ingest_view(const PvIngestBatch* b, PvReadBatch* view);
 const int32_t* pv_ingest_hp_tags(const PvIngestBatch* b);        /* type_read.hp_tag per read */
 const int64_t* pv_ingest_pos_end(const PvIngestBatch* b);        /* type_read.pos_end per read */
+const uint16_t* pv_ingest_bam_flags(const PvIngestBatch* b);     /* BAM FLAG per read (type_read.flags, bam_handler.cpp:72-87) */
 const char* pv_ingest_query_names(const PvIngestBatch* b, int64_t* total_bytes);   /* NUL-separated, read order */
 /* keep reads keep_idx[0..n_keep) (global read indices, grouped by region in region order); new batch */
 int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep_idx, int64_t n_keep, PvIngestBatch** out);

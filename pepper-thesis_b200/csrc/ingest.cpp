@@ -172,6 +172,7 @@ struct PvFastaFile {
 struct PvIngestBatch {
     std::vector<int64_t> read_pos, read_base_off, read_cigar_off, read_pos_end;
     std::vector<int32_t> read_len, read_n_ops, hp;
+    std::vector<uint16_t> bam_flag;
     std::vector<uint8_t> read_flags, read_mapq, bases, quals, ref;
     std::vector<uint32_t> cigar;
     std::vector<int64_t> region_ref_start, region_ref_end, region_cand_start, region_cand_end, region_ref_off, region_ref_len,
@@ -188,7 +189,9 @@ static const char NT16[] = "=ACMGRSVTWYHKDBN";
 struct ReadSink {
     PvIngestBatch* b;
     void add(int64_t pos_start, int64_t pos_end, const std::string& seq, const std::vector<uint8_t>& q,
-             const std::vector<uint32_t>& ops, bool reverse, int mapq, int hp, const char* qname) {
+             const std::vector<uint32_t>& ops, int flag, int mapq, int hp, const char* qname) {
+        const bool reverse = (flag & 0x10) != 0;
+        b->bam_flag.push_back((uint16_t)flag);
         b->read_pos.push_back(pos_start);
         b->read_pos_end.push_back(pos_end);
         b->read_base_off.push_back((int64_t)b->bases.size());
@@ -400,7 +403,7 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                     if (kept_len > 0) kept.push_back((uint32_t)(kept_len << 4) | (uint32_t)op);
                 }
                 if (!bad && !seq.empty())
-                    sink.add(pos_start, pos_end, seq, quals, kept, (flag & 0x10) != 0, mapq, parse_hp(aux_p, end_p), qname);
+                    sink.add(pos_start, pos_end, seq, quals, kept, flag, mapq, parse_hp(aux_p, end_p), qname);
             }
         }
     }
@@ -422,6 +425,7 @@ void append_batch(PvIngestBatch& dst, const PvIngestBatch& src) {
     dst.read_len.insert(dst.read_len.end(), src.read_len.begin(), src.read_len.end());
     dst.read_n_ops.insert(dst.read_n_ops.end(), src.read_n_ops.begin(), src.read_n_ops.end());
     dst.hp.insert(dst.hp.end(), src.hp.begin(), src.hp.end());
+    dst.bam_flag.insert(dst.bam_flag.end(), src.bam_flag.begin(), src.bam_flag.end());
     dst.read_flags.insert(dst.read_flags.end(), src.read_flags.begin(), src.read_flags.end());
     dst.read_mapq.insert(dst.read_mapq.end(), src.read_mapq.begin(), src.read_mapq.end());
     dst.bases.insert(dst.bases.end(), src.bases.begin(), src.bases.end());
@@ -676,6 +680,7 @@ extern "C" int pv_ingest_view(const PvIngestBatch* b, PvReadBatch* v) {
     return PV_OK;
 }
 extern "C" const int32_t* pv_ingest_hp_tags(const PvIngestBatch* b) { return b ? b->hp.data() : nullptr; }
+extern "C" const uint16_t* pv_ingest_bam_flags(const PvIngestBatch* b) { return b ? b->bam_flag.data() : nullptr; }
 extern "C" const int64_t* pv_ingest_pos_end(const PvIngestBatch* b) { return b ? b->read_pos_end.data() : nullptr; }
 extern "C" const char* pv_ingest_query_names(const PvIngestBatch* b, int64_t* total) {
     if (!b) return nullptr;
@@ -708,7 +713,7 @@ extern "C" int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep, int
         o->read_pos.push_back(b->read_pos[i]); o->read_pos_end.push_back(b->read_pos_end[i]);
         o->read_base_off.push_back((int64_t)o->bases.size()); o->read_len.push_back(b->read_len[i]);
         o->read_cigar_off.push_back((int64_t)o->cigar.size()); o->read_n_ops.push_back(b->read_n_ops[i]);
-        o->read_flags.push_back(b->read_flags[i]); o->read_mapq.push_back(b->read_mapq[i]); o->hp.push_back(b->hp[i]);
+        o->read_flags.push_back(b->read_flags[i]); o->read_mapq.push_back(b->read_mapq[i]); o->hp.push_back(b->hp[i]); o->bam_flag.push_back(b->bam_flag[i]);
         const int64_t padded = ((int64_t)b->read_len[i] + 15) & ~15ll;
         o->bases.insert(o->bases.end(), b->bases.begin() + b->read_base_off[i], b->bases.begin() + b->read_base_off[i] + padded);
         o->quals.insert(o->quals.end(), b->quals.begin() + b->read_base_off[i], b->quals.begin() + b->read_base_off[i] + padded);

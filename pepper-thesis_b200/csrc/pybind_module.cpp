@@ -7,8 +7,8 @@
 //     RegionalSummaryGenerator, CandidateImageSummary, CandidateImagePrediction, type_read, type_read_flags, CigarOp.
 // RegionalSummaryGenerator.generate_summary packs the reads into the SoA batch and calls the C-ABI
 // (pv_summary_regions_host in libpepper_b200.so): the work happens in the CUDA kernels, never on the CPU.
-// Classes of the reference module that are outside the hot path (htslib I/O, legacy generators, training labels) are
-// exported by name and raise on use -- see INTEGRATION.md.
+// BAM_handler / FASTA_handler are bound to libpv_ingest.so (no htslib). Classes of the reference module that are outside
+// the hot path (legacy generators, training labels) are exported by name and raise on use -- see INTEGRATION.md.
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -18,6 +18,8 @@
 #include <vector>
 
 #include "pepper_b200.h"
+#include "pepper_ingest.h"
+#include <set>
 
 namespace py = pybind11;
 using std::string;
@@ -180,6 +182,104 @@ public:
     }
 };
 
+struct type_sequence {                              // sequence.h (bam_handler.h): name + length of a BAM target
+    string sequence_name;
+    int sequence_length = 0;
+};
+
+// BAM_handler (bam_handler.cpp) over libpv_ingest.so: no htslib. Errors raise instead of exit(EXIT_FAILURE).
+class BAM_handler {
+    PvBamFile* f = nullptr;
+    static void check(int rc) { if (rc != 0) throw std::runtime_error(pv_ingest_last_error()); }
+
+public:
+    explicit BAM_handler(const string& path) { check(pv_bam_open(path.c_str(), nullptr, &f)); }
+    BAM_handler(const BAM_handler&) = delete;
+    ~BAM_handler() { pv_bam_close(f); }
+
+    vector<string> get_chromosome_sequence_names() {
+        vector<string> v;
+        for (int i = 0; i < pv_bam_n_targets(f); i++) v.push_back(pv_bam_target_name(f, i));
+        return v;
+    }
+    vector<type_sequence> get_chromosome_sequence_names_with_length() {
+        vector<type_sequence> v;
+        for (int i = 0; i < pv_bam_n_targets(f); i++) { type_sequence s; s.sequence_name = pv_bam_target_name(f, i); s.sequence_length = (int)pv_bam_target_len(f, i); v.push_back(s); }
+        return v;
+    }
+    std::set<string> get_sample_names() {
+        const int64_t n = pv_bam_sample_names(f, nullptr, 0);
+        string buf((size_t)n + 1, '\0');
+        pv_bam_sample_names(f, &buf[0], n + 1);
+        std::set<string> out;
+        size_t p = 0;
+        while (p < (size_t)n) { size_t e = buf.find('\n', p); if (e == string::npos || e > (size_t)n) e = (size_t)n; out.insert(buf.substr(p, e - p)); p = e + 1; }
+        return out;
+    }
+    // bam_handler.cpp:115-444
+    vector<type_read> get_reads(const string& chromosome, long long start, long long stop, bool include_supplementary,
+                                int min_mapq, int min_baseq) {
+        PvIngestOptions o; memset(&o, 0, sizeof(o));
+        o.include_supplementary = include_supplementary; o.min_mapq = min_mapq; o.min_baseq = min_baseq; o.threads = 1;
+        PvIngestBatch* b = nullptr;
+        check(pv_bam_get_reads(f, chromosome.c_str(), start, stop, &o, &b));
+        PvReadBatch v;
+        pv_ingest_view(b, &v);
+        const int32_t* hp = pv_ingest_hp_tags(b);
+        const int64_t* pe = pv_ingest_pos_end(b);
+        const uint16_t* fl = pv_ingest_bam_flags(b);
+        int64_t nbytes = 0;
+        const char* names = pv_ingest_query_names(b, &nbytes);
+        vector<type_read> out((size_t)v.n_reads);
+        for (int64_t i = 0; i < v.n_reads; i++) {
+            type_read& r = out[(size_t)i];
+            r.query_name = names; names += r.query_name.size() + 1;
+            r.pos = v.read_pos[i]; r.pos_end = pe[i];
+            const uint8_t* bs = v.bases + v.read_base_off[i];
+            const uint8_t* qs = v.quals + v.read_base_off[i];
+            const int n = v.read_len[i];
+            r.sequence.assign((const char*)bs, (size_t)n);
+            r.base_qualities.assign(qs, qs + n);
+            for (int j = 0; j < n; j++)                      // bad_indicies, :206-212
+                if ((int)qs[j] < min_baseq || (bs[j] != 'A' && bs[j] != 'C' && bs[j] != 'G' && bs[j] != 'T')) r.bad_indicies.push_back(j);
+            r.bad_indicies.push_back(n + 1);                 // :307
+            const uint32_t* cg = v.cigar + v.read_cigar_off[i];
+            for (int k = 0; k < v.read_n_ops[i]; k++) r.cigar_tuples.emplace_back((int)(cg[k] & 15u), (int)(cg[k] >> 4));
+            r.mapping_quality = v.read_mapq[i];
+            r.hp_tag = hp[i];
+            const int g = fl[i];                              // get_read_flags, :72-87
+            r.flags.is_paired = g & 0x1; r.flags.is_proper_pair = g & 0x2; r.flags.is_unmapped = g & 0x4;
+            r.flags.is_mate_unmapped = g & 0x8; r.flags.is_reverse = g & 0x10; r.flags.is_mate_is_reverse = g & 0x20;
+            r.flags.is_read1 = g & 0x40; r.flags.is_read2 = g & 0x80; r.flags.is_secondary = g & 0x100;
+            r.flags.is_qc_failed = g & 0x200; r.flags.is_duplicate = g & 0x400; r.flags.is_supplementary = g & 0x800;
+        }
+        pv_ingest_free(b);
+        return out;
+    }
+};
+
+class FASTA_handler {                              // fasta_handler.cpp
+    PvFastaFile* f = nullptr;
+
+public:
+    explicit FASTA_handler(const string& path) { if (pv_fasta_open(path.c_str(), &f) != 0) throw std::runtime_error(pv_ingest_last_error()); }
+    FASTA_handler(const FASTA_handler&) = delete;
+    ~FASTA_handler() { pv_fasta_close(f); }
+    string get_reference_sequence(const string& region, long long start, long long stop) {
+        string out((size_t)(stop > start ? stop - start : 0), '\0');
+        int64_t got = 0;
+        if (pv_fasta_fetch(f, region.c_str(), start, stop, out.empty() ? nullptr : &out[0], &got) != 0) throw std::runtime_error(pv_ingest_last_error());
+        out.resize((size_t)got);
+        return out;
+    }
+    int get_chromosome_sequence_length(const string& name) { return (int)pv_fasta_seq_len(f, name.c_str()); }
+    vector<string> get_chromosome_names() {
+        vector<string> v;
+        for (int i = 0; i < pv_fasta_n_seq(f); i++) v.push_back(pv_fasta_seq_name(f, i));
+        return v;
+    }
+};
+
 }  // namespace pvb
 using namespace pvb;
 
@@ -301,8 +401,23 @@ PYBIND11_MODULE(PEPPER_VARIANT, m) {
             }));
 
     // names of the reference module that are not on the hot path
-    out_of_scope(m, "BAM_handler", "htslib BAM reader: 'next' row 1 of SURVEY.md section 8f");
-    out_of_scope(m, "FASTA_handler", "htslib FASTA reader: 'next' row 1 of SURVEY.md section 8f");
+    py::class_<type_sequence>(m, "type_sequence")                       // pybind_api.h:234-237
+        .def_readwrite("sequence_length", &type_sequence::sequence_length)
+        .def_readwrite("sequence_name", &type_sequence::sequence_name);
+
+    py::class_<BAM_handler>(m, "BAM_handler")                           // pybind_api.h:223-232
+        .def(py::init<const string&>())
+        .def("get_chromosome_sequence_names", &BAM_handler::get_chromosome_sequence_names)
+        .def("get_chromosome_sequence_names_with_length", &BAM_handler::get_chromosome_sequence_names_with_length)
+        .def("get_sample_names", &BAM_handler::get_sample_names)
+        .def("get_reads", &BAM_handler::get_reads);
+
+    py::class_<FASTA_handler>(m, "FASTA_handler")                       // pybind_api.h:240-246
+        .def(py::init<const string&>())
+        .def("get_reference_sequence", &FASTA_handler::get_reference_sequence)
+        .def("get_chromosome_sequence_length", &FASTA_handler::get_chromosome_sequence_length)
+        .def("get_chromosome_names", &FASTA_handler::get_chromosome_names);
+
     out_of_scope(m, "SummaryGenerator", "legacy per-position generator, not called by call_variant");
     out_of_scope(m, "RegionalSummaryGeneratorHP", "haplotype-aware variant, -hp flag only");
     out_of_scope(m, "CandidateFinder", "legacy C++ candidate finder, unreachable from call_variant");

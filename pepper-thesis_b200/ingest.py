@@ -21,7 +21,7 @@ _LIB = None
 EXPORTS = ["pv_ingest_last_error", "pv_bam_open", "pv_bam_close", "pv_bam_n_targets", "pv_bam_target_name",
            "pv_bam_target_len", "pv_bam_sample_names", "pv_fasta_open", "pv_fasta_close", "pv_fasta_n_seq",
            "pv_fasta_seq_name", "pv_fasta_seq_len", "pv_fasta_fetch", "pv_ingest_regions", "pv_bam_get_reads",
-           "pv_ingest_view", "pv_ingest_hp_tags", "pv_ingest_pos_end", "pv_ingest_query_names", "pv_ingest_select",
+           "pv_ingest_view", "pv_ingest_hp_tags", "pv_ingest_pos_end", "pv_ingest_bam_flags", "pv_ingest_query_names", "pv_ingest_select",
            "pv_ingest_free"]
 
 
@@ -56,6 +56,7 @@ def load():
         lib.pv_ingest_view.argtypes = [C.c_void_p, C.POINTER(PvReadBatchStruct)]
         lib.pv_ingest_hp_tags.argtypes = [C.c_void_p]; lib.pv_ingest_hp_tags.restype = C.c_void_p
         lib.pv_ingest_pos_end.argtypes = [C.c_void_p]; lib.pv_ingest_pos_end.restype = C.c_void_p
+        lib.pv_ingest_bam_flags.argtypes = [C.c_void_p]; lib.pv_ingest_bam_flags.restype = C.c_void_p
         lib.pv_ingest_query_names.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]; lib.pv_ingest_query_names.restype = C.c_void_p
         lib.pv_ingest_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
         lib.pv_ingest_free.argtypes = [C.c_void_p]
@@ -96,6 +97,7 @@ class IngestedReads:
         self.batch = ReadBatch(contigs=[contig] * nr, **a)
         self.hp_tag = _copy(lib.pv_ingest_hp_tags(handle), n, np.int32)
         self.pos_end = _copy(lib.pv_ingest_pos_end(handle), n, np.int64)
+        self.bam_flag = _copy(lib.pv_ingest_bam_flags(handle), n, np.uint16)
         tot = C.c_int64(0)
         p = lib.pv_ingest_query_names(handle, C.byref(tot))
         raw = _copy(p, tot.value, np.uint8).tobytes()

@@ -96,9 +96,9 @@ def build_pymod(force=False, verbose=False):
         with open(init, "w") as f:
             f.write("# mirrors `from pepper_variant.build import PEPPER_VARIANT` (reference setup.py:74-84)\n")
     out = os.path.join(PYMOD_DIR, "PEPPER_VARIANT" + sysconfig.get_config_var("EXT_SUFFIX"))
-    if force or _newer(out, [src, LIB] + headers()):
+    if force or _newer(out, [src, LIB, INGEST, os.path.join(INC, "pepper_ingest.h")] + headers()):
         _run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I", INC, "-I", sysconfig.get_paths()["include"],
-              "-I", pybind11.get_include(), src, "-o", out, "-L", PKG, "-lpepper_b200",
+              "-I", pybind11.get_include(), src, "-o", out, "-L", PKG, "-lpepper_b200", "-lpv_ingest",
               "-Wl,-rpath,$ORIGIN/.."], verbose)
     return out
 

@@ -102,8 +102,8 @@ def test_alignment_summarizer_mirror():
 
 def test_out_of_scope_names_raise():
     pv = _pv()
-    with pytest.raises(RuntimeError):
-        pv.BAM_handler("x.bam")
+    with pytest.raises(RuntimeError, match="outside the B200 hot path"):
+        pv.SummaryGenerator("ACGT", "c", 0, 3)
     g = pv.RegionalSummaryGenerator("c", 0, 3, "ACGT")
     with pytest.raises(RuntimeError):
         g.generate_summary([], 1, 1, .1, .1, .1, 1, .1, .1, 1, False, 0, 3, 32, 26, True)

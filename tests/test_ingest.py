@@ -232,3 +232,55 @@ def test_bam_to_candidates_gpu(files):
         assert np.array_equal(d["images"][m].astype(np.int32), np.asarray(want["images"]).astype(np.int32))
         total += int(m.sum())
     assert total > 50
+
+
+def test_dropin_module_handlers(files):
+    """PEPPER_VARIANT.BAM_handler / FASTA_handler (pybind_api.h:223-246): same calls, type_read objects out."""
+    from pepper_thesis_b200.build import PEPPER_VARIANT as PV
+    bam = PV.BAM_handler(files["bam"])
+    fa = PV.FASTA_handler(files["fa"])
+    assert bam.get_chromosome_sequence_names() == ["chrS", "chrT"]
+    sq = bam.get_chromosome_sequence_names_with_length()
+    assert [(s.sequence_name, s.sequence_length) for s in sq] == [("chrS", CONTIG_LEN), ("chrT", 5000)]
+    assert bam.get_sample_names() == {"HG002", "HG003"}
+    reads = bam.get_reads("chrS", 39000, 47000, True, 0, 15)
+    want = bam_port.get_reads(files["recs"], 0, 39000, 47000, True, 0, 15)
+    assert len(reads) == len(want) > 5
+    for r, w in zip(reads, want):
+        assert (r.query_name, r.pos, r.pos_end, r.sequence, r.mapping_quality, r.hp_tag, r.flags.is_reverse) == \
+               (w["query_name"], w["pos"], w["pos_end"], w["sequence"], w["mapping_quality"], w["hp_tag"], w["is_reverse"])
+        assert r.base_qualities == list(w["base_qualities"])
+        assert [(c.cigar_op, c.cigar_len) for c in r.cigar_tuples] == w["cigar_tuples"]
+        bad = [j for j, (b, q) in enumerate(zip(w["sequence"], w["base_qualities"])) if q < 15 or b not in "ACGT"] + [len(w["sequence"]) + 1]
+        assert r.bad_indicies == bad
+    assert any(r.flags.is_supplementary for r in reads)
+    assert fa.get_reference_sequence("chrS", 100, 700) == files["ref"][100:700]
+    assert fa.get_chromosome_sequence_length("chrS") == CONTIG_LEN and fa.get_chromosome_names() == ["chrS", "chrT"]
+    with pytest.raises(RuntimeError):
+        PV.BAM_handler(files["bam"] + ".missing")
+
+
+@pytest.mark.gpu
+def test_create_summary_from_bam_gpu(files):
+    """The reference's own call sequence (AlignmentSummarizer.create_summary) on BAM + FASTA through the drop-in module."""
+    import types
+    import pyoracle as O
+    import helpers as H
+    from pepper_thesis_b200.build import PEPPER_VARIANT as PV
+    from pepper_thesis_b200.read_batch import Region, pack_regions
+    from pepper_thesis_b200.summarizer import AlignmentSummarizer
+    thr = synth.PROFILES["ont_r9"].thresholds
+    opt = types.SimpleNamespace(include_supplementary=False, min_mapq=1, min_snp_baseq=thr.min_snp_baseq, min_indel_baseq=thr.min_indel_baseq,
+                                snp_frequency=thr.snp_freq, insert_frequency=thr.insert_freq, delete_frequency=thr.delete_freq,
+                                min_coverage_threshold=thr.min_coverage, snp_candidate_frequency_threshold=thr.snp_candidate_freq,
+                                indel_candidate_frequency_threshold=thr.indel_candidate_freq, candidate_support_threshold=thr.candidate_support,
+                                skip_indels=False, downsample_rate=1.0, train_mode=False)
+    s, e = 40000, 70000
+    cands = AlignmentSummarizer(PV.BAM_handler(files["bam"]), PV.FASTA_handler(files["fa"]), "chrS", s, e).create_summary(opt)
+    rs, re_ = s - 100, e + 100
+    reads = [H.Read(w["pos"], w["sequence"], w["cigar_tuples"], rev=w["is_reverse"], q=w["base_qualities"], mapq=w["mapping_quality"])
+             for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 1, 1)]
+    ob = pack_regions([Region("chrS", rs, re_, files["ref"][rs:re_ + 1], s, e, reads)])
+    want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
+    assert [c.position for c in cands] == list(want["position"]) and len(cands) > 20
+    assert np.array_equal(np.asarray([c.image_matrix for c in cands], np.int32), np.asarray(want["images"]).astype(np.int32))
