@@ -216,7 +216,7 @@ def test_bam_to_candidates_gpu(files):
     from pepper_thesis_b200.read_batch import Region, pack_regions
     bam, fa = ingest.BAMHandler(files["bam"]), ingest.FASTAHandler(files["fa"])
     starts, ends = [0, 30000, 60000], [30000, 60000, 90000]
-    got = ingest.ingest_regions(bam, fa, "chrS", starts, ends, min_mapq=1)
+    got = ingest.ingest_regions(bam, fa, "chrS", starts, ends, min_mapq=55)   # drops the N-op read: UB in the reference
     thr = synth.PROFILES["ont_r9"].thresholds
     out = capi.summary_regions_host(got.batch, thr)
     d = out.trimmed()
@@ -224,7 +224,7 @@ def test_bam_to_candidates_gpu(files):
     for r, (s, e) in enumerate(zip(starts, ends)):
         rs, re_ = max(0, s - 100), e + 100
         reads = [H.Read(w["pos"], w["sequence"], w["cigar_tuples"], rev=w["is_reverse"], q=w["base_qualities"], mapq=w["mapping_quality"])
-                 for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 1, 0)]
+                 for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 55, 0)]
         ob = pack_regions([Region("chrS", rs, re_, files["ref"][rs:re_ + 1], s, e, reads)])
         want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
         m = d["region"] == r
@@ -270,7 +270,7 @@ def test_create_summary_from_bam_gpu(files):
     from pepper_thesis_b200.read_batch import Region, pack_regions
     from pepper_thesis_b200.summarizer import AlignmentSummarizer
     thr = synth.PROFILES["ont_r9"].thresholds
-    opt = types.SimpleNamespace(include_supplementary=False, min_mapq=1, min_snp_baseq=thr.min_snp_baseq, min_indel_baseq=thr.min_indel_baseq,
+    opt = types.SimpleNamespace(include_supplementary=False, min_mapq=55, min_snp_baseq=thr.min_snp_baseq, min_indel_baseq=thr.min_indel_baseq,
                                 snp_frequency=thr.snp_freq, insert_frequency=thr.insert_freq, delete_frequency=thr.delete_freq,
                                 min_coverage_threshold=thr.min_coverage, snp_candidate_frequency_threshold=thr.snp_candidate_freq,
                                 indel_candidate_frequency_threshold=thr.indel_candidate_freq, candidate_support_threshold=thr.candidate_support,
@@ -279,7 +279,7 @@ def test_create_summary_from_bam_gpu(files):
     cands = AlignmentSummarizer(PV.BAM_handler(files["bam"]), PV.FASTA_handler(files["fa"]), "chrS", s, e).create_summary(opt)
     rs, re_ = s - 100, e + 100
     reads = [H.Read(w["pos"], w["sequence"], w["cigar_tuples"], rev=w["is_reverse"], q=w["base_qualities"], mapq=w["mapping_quality"])
-             for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 1, 1)]
+             for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 55, 1)]
     ob = pack_regions([Region("chrS", rs, re_, files["ref"][rs:re_ + 1], s, e, reads)])
     want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
     assert [c.position for c in cands] == list(want["position"]) and len(cands) > 20
