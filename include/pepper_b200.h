@@ -118,8 +118,8 @@ int pv_device_count(void);
 /* Launch accounting and optional CUDA-event profiling of the library's own kernels (used by bench.py for
  * `gpu_launches` and the per-kernel roofline). Families, in order: 0 summary cigar prefix, 1 summary pileup tile,
  * 2 summary site alleles, 3 summary key sort, 4 summary window emit, 5 LSTM input prep, 6 LSTM encoder steps,
- * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc. */
-#define PV_PROFILE_FAMILIES 11
+ * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc, 11 candidate filter. */
+#define PV_PROFILE_FAMILIES 12
 void pv_profile_enable(int on);
 int pv_profile_collect(double* ms_by_family, int64_t* launches_by_family);
 void pv_profile_reset(void);
@@ -223,6 +223,39 @@ int pv_gru_forward(PvGruModel* model, const uint8_t* images_dev, int64_t n, int3
 int pv_gru_predict_chunks(PvGruModel* model, const uint8_t* images_dev, int64_t n, int32_t chunk_len, int32_t window,
                           int32_t stride, float* prob_sum_dev, uint8_t* labels_dev, void* workspace_dev,
                           int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stage 3 ("next" row 3 of SURVEY.md 8f): the per-candidate decision of small_chunk_stitch
+ * (pepper_variant/modules/python/CandidateFinder.py:391-529) on the device.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct PvFilterOptions {          /* options.* of find_candidates (CandidateFinder.py:480-515) */
+    double snp_p_value, snp_p_value_in_lc;
+    double insert_p_value, insert_p_value_in_lc;
+    double delete_p_value, delete_p_value_in_lc;
+    double report_snp_above_freq, report_indel_above_freq;
+} PvFilterOptions;
+/* flags per candidate */
+#define PV_FLT_PHASING    1    /* goes to selected_candidate_list_margin (:444-451) */
+#define PV_FLT_VARIANT    2    /* goes to selected_candidate_list_deepvariant (:480-519) */
+#define PV_FLT_IN_REPEAT  4    /* candidate_in_repeat: homopolymer run >= 5 within [-5, +4) of the site (:399-414) */
+#define PV_FLT_GT_SHIFT   3    /* bits 3-4: argmax of the class probabilities (0 hom-ref, 1 het, 2 hom-alt; :419-426) */
+#define PV_FLT_DEL_BY_FREQ 32  /* a delete kept by the frequency rule: alt = the allele string, ref stays one base (:513-515) */
+#define PV_FLT_BAD_REF    64   /* reference base not A/C/G/T: skipped (:416-417) */
+/* All pointers device memory; candidate arrays as in PvCandidates (+ probs float [n][3] from pv_lstm_infer); the region
+ * arrays / ref are those of the device PvReadBatch the candidates came from; region_contig_len (may be NULL) clips
+ * the reference context at the contig end like FASTA_handler does. */
+int pv_candidate_filter(int64_t n, const int64_t* position, const int32_t* region, const int32_t* depth,
+                        const int32_t* frequency, const uint8_t* allele, const uint8_t* allele_len, const float* probs,
+                        const int64_t* region_ref_start, const int64_t* region_ref_off, const int64_t* region_ref_len,
+                        const int64_t* region_contig_len, const uint8_t* ref, const PvFilterOptions* opt,
+                        uint8_t* flags, void* stream);
+/* same with host arrays (copies in, runs the kernel, copies the flags out) */
+int pv_candidate_filter_host(int64_t n, const int64_t* position, const int32_t* region, const int32_t* depth,
+                             const int32_t* frequency, const uint8_t* allele, const uint8_t* allele_len,
+                             const float* probs, int32_t n_regions, const int64_t* region_ref_start,
+                             const int64_t* region_ref_off, const int64_t* region_ref_len,
+                             const int64_t* region_contig_len, const uint8_t* ref, int64_t n_ref,
+                             const PvFilterOptions* opt, uint8_t* flags);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,8 @@ EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_profile_enable"
            "pv_profile_reset", "pv_launch_count", "pv_summary_status_offset", "pv_unpack_bases4", "pv_pack_bases4", "pv_batch_validate", "pv_summary_workspace_bytes",
            "pv_summary_regions", "pv_summary_regions_host", "pv_lstm_create", "pv_lstm_destroy",
            "pv_lstm_workspace_bytes", "pv_lstm_infer", "pv_lstm_infer_host", "pv_gru_create", "pv_gru_destroy",
-           "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks"]
+           "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks", "pv_candidate_filter",
+           "pv_candidate_filter_host"]
 
 
 class PvError(RuntimeError):
@@ -37,6 +38,12 @@ class PvThresholdsStruct(C.Structure):
                 ("insert_freq", C.c_double), ("delete_freq", C.c_double), ("min_coverage", C.c_double),
                 ("snp_candidate_freq", C.c_double), ("indel_candidate_freq", C.c_double),
                 ("candidate_support", C.c_double), ("skip_indels", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PvFilterOptionsStruct(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("snp_p_value", "snp_p_value_in_lc", "insert_p_value", "insert_p_value_in_lc",
+                                          "delete_p_value", "delete_p_value_in_lc", "report_snp_above_freq",
+                                          "report_indel_above_freq")]
 
 
 class PvCandidatesStruct(C.Structure):
@@ -108,12 +115,17 @@ def load() -> C.CDLL:
                                            C.c_void_p, C.c_int64, C.c_void_p]
             lib.pv_gru_predict_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        if hasattr(lib, "pv_candidate_filter"):
+            lib.pv_candidate_filter.argtypes = [C.c_int64] + [C.c_void_p] * 12 + [C.POINTER(PvFilterOptionsStruct), C.c_void_p, C.c_void_p]
+            lib.pv_candidate_filter_host.argtypes = [C.c_int64] + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 5 + \
+                [C.c_int64, C.POINTER(PvFilterOptionsStruct), C.c_void_p]
         _lib = lib
     return _lib
 
 
 FAMILIES = ["sum_cigar_prefix", "sum_pileup_tile", "sum_site_alleles", "sum_key_sort", "sum_emit_windows",
-            "lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head", "gru_steps", "gru_misc"]
+            "lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head", "gru_steps", "gru_misc",
+            "candidate_filter"]
 
 
 def profile_collect():
