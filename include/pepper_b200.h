@@ -118,8 +118,8 @@ int pv_device_count(void);
 /* Launch accounting and optional CUDA-event profiling of the library's own kernels (used by bench.py for
  * `gpu_launches` and the per-kernel roofline). Families, in order: 0 summary cigar prefix, 1 summary pileup tile,
  * 2 summary site alleles, 3 summary key sort, 4 summary window emit, 5 LSTM input prep, 6 LSTM encoder steps,
- * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc, 11 candidate filter. */
-#define PV_PROFILE_FAMILIES 12
+ * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc, 11 candidate filter, 12 polisher summary. */
+#define PV_PROFILE_FAMILIES 13
 void pv_profile_enable(int on);
 int pv_profile_collect(double* ms_by_family, int64_t* launches_by_family);
 void pv_profile_reset(void);
@@ -256,6 +256,29 @@ int pv_candidate_filter_host(int64_t n, const int64_t* position, const int32_t* 
                              const int64_t* region_ref_off, const int64_t* region_ref_len,
                              const int64_t* region_contig_len, const uint8_t* ref, int64_t n_ref,
                              const PvFilterOptions* opt, uint8_t* flags);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Polisher pileup summary ("next" row 4 of SURVEY.md 8f): SummaryGenerator::generate_summary of the `pepper` module
+ * (pepper/modules/src/pileup_summary/summary_generator.cpp:47-121, 274-306, 370-392) and chunk_images
+ * (pepper/modules/python/AlignmentSummarizer.py:19-56): the producer of model M-B's uint8 [chunk][1000][10] input.
+ * Regions of the batch: region_ref_start/end = the generator's ref_start/ref_end = start_pos/end_pos. All device
+ * memory except the *_host arguments.
+ * ------------------------------------------------------------------------------------------------------- */
+int64_t pv_polish_workspace_bytes(int64_t n_reads, int64_t n_ops, int32_t n_regions, int64_t total_positions);
+/* counts + row layout; writes the number of output rows (positions + inserted columns) to *n_rows_host and, when
+ * given, the first row of every region (n_regions + 1 entries). Synchronises the stream. */
+int pv_polish_count(const PvReadBatch* batch_dev, const int64_t* region_len_host, int64_t total_positions,
+                    void* workspace_dev, int64_t workspace_bytes, int64_t* n_rows_host, int64_t* region_rows_host,
+                    void* stream);
+/* image_dev uint8 [n_rows][10] (SummaryGenerator.image), gpos_dev int64 [n_rows][2] (genomic_pos: position, insert
+ * index), row_region_dev int32 [n_rows]; ins_scratch_dev uint32 [n_rows][10] scratch. Same workspace as pv_polish_count. */
+int pv_polish_emit(const PvReadBatch* batch_dev, const int64_t* region_len_host, int64_t total_positions,
+                   void* workspace_dev, int64_t workspace_bytes, int64_t n_rows, uint32_t* ins_scratch_dev,
+                   uint8_t* image_dev, int64_t* gpos_dev, int32_t* row_region_dev, void* stream);
+/* chunk c = rows [chunk_row[c], chunk_row[c] + chunk_valid[c]) padded with zeros / (-1,-1) to chunk_size rows */
+int pv_polish_chunks(const uint8_t* image_dev, const int64_t* gpos_dev, const int64_t* chunk_row_dev,
+                     const int64_t* chunk_valid_dev, int64_t n_chunks, int32_t chunk_size, uint8_t* out_images_dev,
+                     int64_t* out_positions_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_profile_enable"
            "pv_summary_regions", "pv_summary_regions_host", "pv_lstm_create", "pv_lstm_destroy",
            "pv_lstm_workspace_bytes", "pv_lstm_infer", "pv_lstm_infer_host", "pv_gru_create", "pv_gru_destroy",
            "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks", "pv_candidate_filter",
-           "pv_candidate_filter_host"]
+           "pv_candidate_filter_host", "pv_polish_workspace_bytes", "pv_polish_count", "pv_polish_emit", "pv_polish_chunks"]
 
 
 class PvError(RuntimeError):
@@ -115,6 +115,15 @@ def load() -> C.CDLL:
                                            C.c_void_p, C.c_int64, C.c_void_p]
             lib.pv_gru_predict_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        if hasattr(lib, "pv_polish_count"):
+            lib.pv_polish_workspace_bytes.restype = C.c_int64
+            lib.pv_polish_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64]
+            lib.pv_polish_count.argtypes = [C.POINTER(PvReadBatchStruct), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+            lib.pv_polish_emit.argtypes = [C.POINTER(PvReadBatchStruct), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.pv_polish_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
         if hasattr(lib, "pv_candidate_filter"):
             lib.pv_candidate_filter.argtypes = [C.c_int64] + [C.c_void_p] * 12 + [C.POINTER(PvFilterOptionsStruct), C.c_void_p, C.c_void_p]
             lib.pv_candidate_filter_host.argtypes = [C.c_int64] + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 5 + \
@@ -125,7 +134,7 @@ def load() -> C.CDLL:
 
 FAMILIES = ["sum_cigar_prefix", "sum_pileup_tile", "sum_site_alleles", "sum_key_sort", "sum_emit_windows",
             "lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head", "gru_steps", "gru_misc",
-            "candidate_filter"]
+            "candidate_filter", "polish_summary"]
 
 
 def profile_collect():

@@ -111,10 +111,15 @@ def build_oracle(force=False, verbose=False):
     if _newer(port, [os.path.join(odir, "region_summary_port.c")]):
         _run(["make", "-C", odir, "port"], verbose)
     ref_dir = os.path.join(odir, "_ref")
-    have_ref = os.path.isdir(ref_dir) and any(f.startswith("pv_ref_oracle") for f in os.listdir(ref_dir))
     if os.path.isdir("/root/reference/pepper_variant/modules/cpp"):
-        so = [os.path.join(ref_dir, f) for f in os.listdir(ref_dir)] if have_ref else []
-        if not so or _newer(so[0], [os.path.join(odir, "ref_shim.cpp")]):
+        have = os.listdir(ref_dir) if os.path.isdir(ref_dir) else []
+        shims = {"pv_ref_oracle": "ref_shim.cpp", "pv_ref_polisher": "ref_shim_polisher.cpp"}
+        stale = False
+        for mod, shim in shims.items():
+            so = [os.path.join(ref_dir, f) for f in have if f.startswith(mod)]
+            if not so or _newer(so[0], [os.path.join(odir, shim), os.path.join(odir, "Makefile")]):
+                stale = True
+        if stale:
             _run(["make", "-C", odir, "ref"], verbose)
 
 

@@ -89,10 +89,12 @@ KATS = {"toy": kat_toy, "clamp": kat_clamp, "del": kat_del, "ins": kat_ins, "ref
 
 
 # ---- fuzz ---------------------------------------------------------------------------------------------------------
-def fuzz_region(seed, L=400, n_reads=40, weird=True, ref_n=False, ref_start=1000):
+def fuzz_region(seed, L=400, n_reads=40, weird=True, ref_n=False, ref_start=1000, consistent=False):
     """Random reads exercising every CIGAR op, odd bytes, low qualities, mapq 0, reads crossing the region ends.
     The reference's undefined behaviours are avoided (read index stays inside the sequence under the
-    reference's own stepping, reads end in a match, no candidate on a non-ACGT reference base unless ref_n)."""
+    reference's own stepping, reads end in a match, no candidate on a non-ACGT reference base unless ref_n).
+    ``consistent``: N / P ops consume no read bases (SAM semantics, what the polisher's generator assumes) instead of the
+    variant generator's fall-through stepping."""
     rng = np.random.default_rng(seed)
     alpha = np.frombuffer(b"ACGT", np.uint8)
     ref = alpha[rng.integers(0, 4, L + 80)].copy()
@@ -142,7 +144,7 @@ def fuzz_region(seed, L=400, n_reads=40, weird=True, ref_n=False, ref_start=1000
             elif weird and r < 0.95:
                 op = int(rng.choice([3, 6])); ln = int(rng.integers(1, 8))
                 x += ln
-                for i in range(ln):                      # the reference also advances the read here
+                for i in range(0 if consistent else ln):  # the variant reference also advances the read here
                     seq.append(ord("C")); quals.append(30)
             elif weird and r < 0.97:
                 op = 5; ln = int(rng.integers(1, 5))
