@@ -103,3 +103,26 @@ def test_dropin_summary_generator():
     img, gp = ref_summary(b, 0)
     assert g.image == img.tolist() and g.genomic_pos == [tuple(x) for x in gp.tolist()]
     assert (59, 1) in g.genomic_pos and (59, 2) in g.genomic_pos
+
+
+def test_polisher_end_to_end():
+    """reads -> polisher summary -> 1000/50 chunks -> model M-B chunk loop (predict_distributed_gpu.py:63-96): the GPU
+    chain against the reference generator + the fp32 model restatement."""
+    import torch
+    import model_port as MP
+    from pepper_thesis_b200 import models
+    b = synth.generate("ont_r9", 100000, 20.0, seed=4)
+    s = polish.PolishSummary(b)
+    images, positions, ids, regs = s.chunks()
+    sd = models.random_polisher_state_dict(1)
+    m = models.PolisherTransducerGRU().load_state_dict(sd)
+    acc, labels = m.predict_chunks(images, 100, 50)
+    n = min(12, images.shape[0])
+    racc, rlab = MP.polisher_predict_chunks(sd, images[:n].cpu(), 100, 50)
+    assert (acc[:n].cpu() - racc).abs().max() < 2e-2
+    lab = labels[:n].cpu().numpy()
+    want = racc.numpy().argmax(-1)
+    srt = np.sort(racc.numpy(), -1)
+    clear = (srt[..., -1] - srt[..., -2]) > 2e-2
+    assert (lab[clear] == want[clear]).all() and clear.mean() > 0.5
+    assert int(positions[0, 0, 0]) == int(b.region_ref_start[0])
