@@ -47,7 +47,8 @@ enum { PV_CIGAR_MATCH = 0, PV_CIGAR_INS = 1, PV_CIGAR_DEL = 2, PV_CIGAR_REF_SKIP
  * Packed read batch: the reads of n_regions regions, grouped by region (region_read_begin[r] ..
  * region_read_begin[r+1]). All arrays live in the SAME memory space (all host for *_host entry points, all
  * device for the others). Invariants checked by pv_batch_validate():
- *   read_base_off[i] % 16 == 0; read_base_off[i] + read_len[i] <= n_bases; cigar ranges inside n_ops;
+ *   read_base_off[i] % 16 == 0; read_base_off[i] + read_len[i] <= n_bases; n_bases % 16 == 0 when a packed wire form
+ *   is used; cigar ranges inside n_ops;
  *   region_ref_end >= region_ref_start; region_ref_len[r] >= ref_end-ref_start+1; region_ref_off[r] + region_ref_len[r] <= n_ref;
  *   reads per region <= 32767 (window values must fit int16).
  */
@@ -82,6 +83,15 @@ typedef struct PvReadBatch {
      * only valid when every base is one of those 16 upper-case letters (what BAM_handler::get_reads produces,
      * bam_handler.cpp:213). Ignored (may be NULL) for device-resident batches. */
     const uint8_t*  bases4;
+    /* Optional wire formats of `quals` and `cigar` for HOST batches (same rules as bases4: uploaded instead of the plain
+     * arrays, expanded on the device, lossless):
+     *   quals_packed: dense little-endian bit stream, quality i in bits [i*qual_bits, (i+1)*qual_bits), qual_bits in
+     *                 1..7 = bits of the largest quality of the batch; ceil(n_bases/32)*qual_bits*4 bytes (pv_pack_quals).
+     *   cigar16:      the low 16 bits of every CIGAR word; only valid when every op length is < 4096 (pv_pack_cigar16). */
+    const uint8_t*  quals_packed;
+    int32_t         qual_bits;
+    int32_t         _pad0;
+    const uint16_t* cigar16;
 } PvReadBatch;
 
 /* The ten scalars of generate_summary (region_summary.h:191-201), same order, same double compares. */
@@ -131,6 +141,16 @@ int pv_summary_status_offset(void);
 
 /* Device: expand 4-bit packed bases (see PvReadBatch.bases4) into one byte per base; n_bases must be a multiple of 16. */
 int pv_unpack_bases4(const uint8_t* packed_dev, int64_t n_bases, uint8_t* bases_dev, void* stream);
+/* Device: expand a bit-packed quality stream (PvReadBatch.quals_packed) into one byte per quality; n_bases % 16 == 0;
+ * packed_dev must hold ceil(n_bases/32)*qual_bits*4 readable bytes. */
+int pv_unpack_quals(const uint8_t* packed_dev, int64_t n_bases, int32_t qual_bits, uint8_t* quals_dev, void* stream);
+/* Host: bits needed for the largest quality (1..8; 8 = not worth packing) and the packing itself
+ * (packed_host: ceil(n_bases/32)*qual_bits*4 bytes). */
+int32_t pv_qual_bits(const uint8_t* quals_host, int64_t n_bases, int32_t threads);
+int pv_pack_quals(const uint8_t* quals_host, int64_t n_bases, int32_t qual_bits, uint8_t* packed_host, int32_t threads);
+/* Device: zero-extend 16-bit CIGAR words; Host: truncate them (PV_EINVAL if an op length is >= 4096). */
+int pv_unpack_cigar16(const uint16_t* packed_dev, int64_t n_ops, uint32_t* cigar_dev, void* stream);
+int pv_pack_cigar16(const uint32_t* cigar_host, int64_t n_ops, uint16_t* packed_host, int32_t threads);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 

@@ -148,7 +148,10 @@ extern "C" int pv_batch_validate(const PvReadBatch* b) {
     if (!b) return pv::set_error(PV_EINVAL, "null batch");
     if (b->n_reads < 0 || b->n_bases < 0 || b->n_ops < 0 || b->n_regions < 0 || b->n_ref < 0)
         return pv::set_error(PV_EINVAL, "negative size");
-    if (b->bases4 && (b->n_bases & 15)) return pv::set_error(PV_EINVAL, "bases4 needs n_bases to be a multiple of 16");
+    if ((b->bases4 || b->quals_packed) && (b->n_bases & 15)) return pv::set_error(PV_EINVAL, "bases4 / quals_packed need n_bases to be a multiple of 16");
+    if (b->quals_packed && (b->qual_bits < 1 || b->qual_bits > 7)) return pv::set_error(PV_EINVAL, "quals_packed needs qual_bits in 1..7");
+    if (!b->quals_packed && !b->quals && b->n_bases) return pv::set_error(PV_EINVAL, "neither quals nor quals_packed given");
+    if (!b->cigar16 && !b->cigar && b->n_ops) return pv::set_error(PV_EINVAL, "neither cigar nor cigar16 given");
     if (!b->bases4 && !b->bases && b->n_bases) return pv::set_error(PV_EINVAL, "neither bases nor bases4 given");
     if (b->n_regions == 0) return PV_OK;
     if (!b->region_read_begin || b->region_read_begin[0] != 0 || b->region_read_begin[b->n_regions] != b->n_reads)
@@ -171,8 +174,13 @@ extern "C" int pv_batch_validate(const PvReadBatch* b) {
         if (b->read_cigar_off[i] < 0 || b->read_n_ops[i] < 0 || b->read_cigar_off[i] + b->read_n_ops[i] > b->n_ops)
             return pv::set_error(PV_EINVAL, "read %lld: cigar outside cigar[]", (long long)i);
         int64_t tot = 0;
-        const uint32_t* c = b->cigar + b->read_cigar_off[i];
-        for (int32_t k = 0; k < b->read_n_ops[i]; k++) tot += (int64_t)(c[k] >> 4);
+        if (b->cigar) {
+            const uint32_t* c = b->cigar + b->read_cigar_off[i];
+            for (int32_t k = 0; k < b->read_n_ops[i]; k++) tot += (int64_t)(c[k] >> 4);
+        } else {
+            const uint16_t* c = b->cigar16 + b->read_cigar_off[i];
+            for (int32_t k = 0; k < b->read_n_ops[i]; k++) tot += (int64_t)(c[k] >> 4);
+        }
         if (tot > 0x3fffffffll) return pv::set_error(PV_EINVAL, "read %lld: CIGAR longer than 2^30", (long long)i);
     }
     return PV_OK;
@@ -199,10 +207,44 @@ __global__ void unpack_bases4_kernel(const uint8_t* __restrict__ packed, int64_t
     }
 }
 
+// dense bit stream -> bytes: a thread expands 32 qualities (`bits` aligned words in, two 16-byte stores out)
+template <int BITS>
+__global__ void unpack_quals_kernel(const uint32_t* __restrict__ packed, int64_t n_grp, int64_t n_bases, uint8_t* __restrict__ quals) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_grp; g += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[BITS + 1];
+#pragma unroll
+        for (int j = 0; j < BITS; j++) w[j] = __ldg(packed + g * BITS + j);
+        w[BITS] = 0;
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const int bit = i * BITS, wi = bit >> 5, sh = bit & 31;
+            const uint32_t v = __funnelshift_r(w[wi], w[wi + 1], sh) & ((1u << BITS) - 1u);
+            if ((i & 3) == 0) o[i >> 2] = v; else o[i >> 2] |= v << ((i & 3) * 8);
+        }
+        uint4* dst = (uint4*)(quals + g * 32);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (g * 32 + 16 < n_bases) dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+__global__ void unpack_cigar16_kernel(const uint16_t* __restrict__ packed, int64_t n, uint32_t* __restrict__ cigar) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cigar[i] = packed[i];
+}
+
+template <class F> void parallel_ranges(int64_t n, int threads, F f) {
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    std::vector<std::thread> pool;
+    const int64_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) pool.emplace_back([=]() { const int64_t lo = t * per, hi = lo + per < n ? lo + per : n; if (lo < hi) f(t, lo, hi); });
+    for (auto& th : pool) th.join();
+}
+
 struct HostCtx {
     std::mutex mu;
     pv::DevBuf arr[18];      // batch arrays in PvReadBatch order
-    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense, packed;
+    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense, packed, packed_q, packed_c;
     cudaStream_t stream = nullptr;
 };
 HostCtx& host_ctx() { static HostCtx c; return c; }
@@ -221,6 +263,87 @@ extern "C" int pv_unpack_bases4(const uint8_t* packed_dev, int64_t n_bases, uint
     if (blocks > cap) blocks = cap;
     unpack_bases4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed_dev, n_vec, bases_dev);
     PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_unpack_quals(const uint8_t* packed_dev, int64_t n_bases, int32_t bits, uint8_t* quals_dev, void* stream) {
+    if (!packed_dev || !quals_dev || n_bases < 0 || (n_bases & 15) || bits < 1 || bits > 7 || ((uintptr_t)packed_dev & 3))
+        return pv::set_error(PV_EINVAL, "pv_unpack_quals: bad arguments (n_bases %% 16 == 0, qual_bits in 1..7, 4-byte aligned input)");
+    if (n_bases == 0) return PV_OK;
+    if (int rc = pv::require_device()) return rc;
+    const int64_t n_grp = (n_bases + 31) / 32;
+    int64_t blocks = (n_grp + 255) / 256;
+    const int64_t cap = (int64_t)pv::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t* p = (const uint32_t*)packed_dev;
+    switch (bits) {
+        case 1: unpack_quals_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+        case 2: unpack_quals_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+        case 3: unpack_quals_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+        case 4: unpack_quals_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+        case 5: unpack_quals_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+        case 6: unpack_quals_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+        default: unpack_quals_kernel<7><<<(unsigned)blocks, 256, 0, st>>>(p, n_grp, n_bases, quals_dev); break;
+    }
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int32_t pv_qual_bits(const uint8_t* quals, int64_t n, int32_t threads) {
+    if (!quals || n <= 0) return 1;
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    std::vector<uint8_t> mx((size_t)threads, 0);
+    parallel_ranges(n, threads, [&](int t, int64_t lo, int64_t hi) { uint8_t m = 0; for (int64_t i = lo; i < hi; i++) m |= quals[i]; mx[(size_t)t] = m; });
+    uint8_t m = 0;
+    for (uint8_t v : mx) m |= v;
+    int bits = 1;
+    while (bits < 8 && (m >> bits)) bits++;
+    return bits;
+}
+
+extern "C" int pv_pack_quals(const uint8_t* quals, int64_t n_bases, int32_t bits, uint8_t* packed, int32_t threads) {
+    if (!quals || !packed || n_bases < 0 || (n_bases & 15) || bits < 1 || bits > 7) return pv::set_error(PV_EINVAL, "pv_pack_quals: bad arguments");
+    const int64_t n_grp = (n_bases + 31) / 32;
+    std::vector<int> bad(64, 0);
+    parallel_ranges(n_grp, threads, [&](int t, int64_t lo, int64_t hi) {
+        for (int64_t g = lo; g < hi; g++) {
+            uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 32; i++) {
+                const int64_t idx = g * 32 + i;
+                const uint32_t v = idx < n_bases ? quals[idx] : 0u;
+                if (v >> bits) bad[(size_t)t] = 1;
+                const int bit = i * bits, wi = bit >> 5, sh = bit & 31;
+                w[wi] |= v << sh;
+                if (sh + bits > 32) w[wi + 1] |= v >> (32 - sh);
+            }
+            memcpy(packed + (size_t)g * bits * 4, w, (size_t)bits * 4);
+        }
+    });
+    for (int v : bad) if (v) return pv::set_error(PV_EINVAL, "pv_pack_quals: a quality does not fit %d bits", bits);
+    return PV_OK;
+}
+
+extern "C" int pv_unpack_cigar16(const uint16_t* packed_dev, int64_t n_ops, uint32_t* cigar_dev, void* stream) {
+    if (n_ops < 0 || (n_ops && (!packed_dev || !cigar_dev))) return pv::set_error(PV_EINVAL, "pv_unpack_cigar16: bad arguments");
+    if (n_ops == 0) return PV_OK;
+    if (int rc = pv::require_device()) return rc;
+    int64_t blocks = (n_ops + 255) / 256;
+    const int64_t cap = (int64_t)pv::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    unpack_cigar16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed_dev, n_ops, cigar_dev);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_pack_cigar16(const uint32_t* cigar, int64_t n_ops, uint16_t* packed, int32_t threads) {
+    if (n_ops < 0 || (n_ops && (!cigar || !packed))) return pv::set_error(PV_EINVAL, "pv_pack_cigar16: bad arguments");
+    std::vector<int> bad(64, 0);
+    parallel_ranges(n_ops, threads, [&](int t, int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) { if (cigar[i] >> 16) bad[(size_t)t] = 1; packed[i] = (uint16_t)cigar[i]; }
+    });
+    for (int v : bad) if (v) return pv::set_error(PV_EINVAL, "pv_pack_cigar16: an op length is >= 4096");
     return PV_OK;
 }
 
@@ -283,10 +406,23 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
             if (int rc = pv_unpack_bases4((const uint8_t*)h.packed.p, hb->n_bases, (uint8_t*)h.arr[7].p, st)) return rc;
             continue;
         }
+        if (i == 8 && hb->quals_packed && hb->n_bases) {     // qualities travel bit-packed
+            const size_t pb = (size_t)((hb->n_bases + 31) / 32) * hb->qual_bits * 4;
+            if (int rc = h.packed_q.reserve(pb + 16)) return rc;
+            PV_CUDA_CHECK(cudaMemcpyAsync(h.packed_q.p, hb->quals_packed, pb, cudaMemcpyHostToDevice, st));
+            if (int rc = pv_unpack_quals((const uint8_t*)h.packed_q.p, hb->n_bases, hb->qual_bits, (uint8_t*)h.arr[8].p, st)) return rc;
+            continue;
+        }
+        if (i == 9 && hb->cigar16 && hb->n_ops) {            // CIGAR words travel as 16 bits
+            if (int rc = h.packed_c.reserve((size_t)hb->n_ops * 2 + 16)) return rc;
+            PV_CUDA_CHECK(cudaMemcpyAsync(h.packed_c.p, hb->cigar16, (size_t)hb->n_ops * 2, cudaMemcpyHostToDevice, st));
+            if (int rc = pv_unpack_cigar16((const uint16_t*)h.packed_c.p, hb->n_ops, (uint32_t*)h.arr[9].p, st)) return rc;
+            continue;
+        }
         if (bytes[i]) PV_CUDA_CHECK(cudaMemcpyAsync(h.arr[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, st));
     }
     PvReadBatch db = *hb;
-    db.bases4 = nullptr;
+    db.bases4 = nullptr; db.quals_packed = nullptr; db.qual_bits = 0; db.cigar16 = nullptr;
     db.read_pos = (const int64_t*)h.arr[0].p; db.read_base_off = (const int64_t*)h.arr[1].p; db.read_len = (const int32_t*)h.arr[2].p;
     db.read_cigar_off = (const int64_t*)h.arr[3].p; db.read_n_ops = (const int32_t*)h.arr[4].p; db.read_flags = (const uint8_t*)h.arr[5].p;
     db.read_mapq = (const uint8_t*)h.arr[6].p; db.bases = (const uint8_t*)h.arr[7].p; db.quals = (const uint8_t*)h.arr[8].p;

@@ -13,6 +13,7 @@
 #include <pybind11/stl.h>
 
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -136,7 +137,7 @@ public:
         int64_t rs = ref_start, re = ref_end, cs = candidate_region_start, ce = candidate_region_end, ro = 0,
                 rl = (int64_t)reference_sequence.size(), rb[2] = {0, (int64_t)n};
         PvReadBatch b;
-        b.bases4 = nullptr;
+        memset(&b, 0, sizeof(b));
         b.n_reads = (int64_t)n; b.n_bases = (int64_t)bases.size(); b.n_ops = (int64_t)cigar.size(); b.n_ref = rl; b.n_regions = 1;
         b.read_pos = read_pos.data(); b.read_base_off = base_off.data(); b.read_len = read_len.data();
         b.read_cigar_off = cigar_off.data(); b.read_n_ops = n_ops.data(); b.read_flags = flags.data(); b.read_mapq = mapq.data();

@@ -30,7 +30,9 @@ class DeviceBatch:
         self.host = host
         self.device = torch.device(device)
         self.t = {}
-        self.packed = None
+        self.packed = None          # 4-bit bases
+        self.packed_q = None        # bit-packed qualities
+        self.packed_c = None        # 16-bit CIGAR words
         self._unpacked = True
         for name in ARRAY_NAMES:
             a = getattr(host, name)
@@ -39,30 +41,60 @@ class DeviceBatch:
                 self.packed = _to_torch(host.bases4).to(self.device, non_blocking=non_blocking)
                 self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
                 self._unpacked = False
-                if not defer_unpack:
-                    self.unpack()
+                continue
+            if name == "quals" and host.quals_packed is not None and a.size:
+                n_words = (a.size + 31) // 32 * host.qual_bits
+                self.packed_q = torch.empty(n_words * 4 + 16, dtype=torch.uint8, device=self.device)
+                need = min((a.size * host.qual_bits + 7) // 8, host.quals_packed.shape[0])
+                self.packed_q[:need].copy_(_to_torch(host.quals_packed[:need]), non_blocking=non_blocking)
+                self.t[name] = torch.empty(a.size + 16, dtype=torch.uint8, device=self.device)[:a.size]
+                self._unpacked = False
+                continue
+            if name == "cigar" and host.cigar16 is not None and a.size:
+                self.packed_c = torch.from_numpy(host.cigar16.view(np.int16)).to(self.device, non_blocking=non_blocking)
+                self.t[name] = torch.empty(a.size, dtype=torch.int32, device=self.device)
+                self._unpacked = False
                 continue
             src = _to_torch(a) if a.size else torch.zeros(1, dtype=_TORCH_DT[np.dtype(a.dtype)])
             self.t[name] = src.to(self.device, non_blocking=non_blocking)
         self.region_len = np.ascontiguousarray(host.region_len)
         self.total_positions = int(self.region_len.sum())
         self.struct = host.as_struct({n: self.t[n].data_ptr() for n in ARRAY_NAMES})
+        if not defer_unpack:
+            self.unpack()
 
     def unpack(self):
-        """Expand the 4-bit bases on the CURRENT stream (a copy stream should only carry copies: the caller runs this
-        on the compute stream after waiting for the upload)."""
+        """Expand the compact wire forms on the CURRENT stream (a copy stream should only carry copies: the caller runs
+        this on the compute stream after waiting for the upload)."""
         if self._unpacked:
             return
-        out = self.t["bases"]
-        capi.check(capi.load().pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()),
-                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        lib = capi.load()
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self.packed is not None:
+            out = self.t["bases"]
+            capi.check(lib.pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
+        if self.packed_q is not None:
+            out = self.t["quals"]
+            capi.check(lib.pv_unpack_quals(C.c_void_p(self.packed_q.data_ptr()), out.numel(), int(self.host.qual_bits),
+                                           C.c_void_p(out.data_ptr()), st))
+        if self.packed_c is not None:
+            out = self.t["cigar"]
+            capi.check(lib.pv_unpack_cigar16(C.c_void_p(self.packed_c.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
         self._unpacked = True
+
+    def record_stream(self, stream):
+        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_q, self.packed_c) if x is not None]:
+            t.record_stream(stream)
 
     @property
     def h2d_bytes(self) -> int:
         n = int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
         if self.packed is not None:
             n -= self.host.bases.nbytes - self.host.bases4.nbytes
+        if self.packed_q is not None:
+            n -= self.host.quals.nbytes - min((self.host.quals.size * self.host.qual_bits + 7) // 8, self.host.quals_packed.nbytes)
+        if self.packed_c is not None:
+            n -= self.host.cigar.nbytes - self.host.cigar16.nbytes
         return n
 
 

@@ -264,13 +264,10 @@ class HotPath:
             main.wait_event(ev)
             if i + 1 < len(groups):
                 nxt = upload(groups[i + 1])
-            db.unpack()                           # 4-bit bases -> bytes, on the compute stream
+            db.unpack()                           # compact wire forms -> plain arrays, on the compute stream
             # this path is bound by the H2D copies, so the simple synchronous form is used: the host waits for the group's
             # candidate count before queueing more (measured: queueing further ahead slows the copies down)
             ws, k = self.summarize(db)
             self._push(run, ws, k, region_offset + g[0])
-            for t in db.t.values():
-                t.record_stream(main)
-            if db.packed is not None:
-                db.packed.record_stream(main)
+            db.record_stream(main)
         return self._finish(run, True)

@@ -29,7 +29,8 @@ class PvReadBatchStruct(C.Structure):
                 ("region_ref_start", C.c_void_p), ("region_ref_end", C.c_void_p), ("region_cand_start", C.c_void_p),
                 ("region_cand_end", C.c_void_p), ("region_ref_off", C.c_void_p), ("region_ref_len", C.c_void_p),
                 ("region_read_begin", C.c_void_p),
-                ("ref", C.c_void_p), ("bases4", C.c_void_p)]
+                ("ref", C.c_void_p), ("bases4", C.c_void_p),
+                ("quals_packed", C.c_void_p), ("qual_bits", C.c_int32), ("_pad0", C.c_int32), ("cigar16", C.c_void_p)]
 
 
 ARRAY_NAMES = [n for n, _ in _READ_FIELDS] + ["bases", "quals", "cigar"] + [n for n, _ in _REGION_FIELDS] + \
@@ -59,6 +60,9 @@ class ReadBatch:
     ref: np.ndarray
     contigs: List[str] = field(default_factory=list)
     bases4: Optional[np.ndarray] = None      # optional BAM-native 4-bit packing of `bases` (n_bases / 2 bytes)
+    quals_packed: Optional[np.ndarray] = None   # optional dense bit stream of `quals` (qual_bits per quality)
+    qual_bits: int = 0
+    cigar16: Optional[np.ndarray] = None     # optional low 16 bits of every CIGAR word (all op lengths < 4096)
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -108,8 +112,60 @@ class ReadBatch:
                 a = getattr(self, name)
                 assert a.flags["C_CONTIGUOUS"], name
                 setattr(s, name, a.ctypes.data)
-        s.bases4 = self.bases4.ctypes.data if (arrays is None and self.bases4 is not None) else None
+        host = arrays is None
+        s.bases4 = self.bases4.ctypes.data if (host and self.bases4 is not None) else None
+        s.quals_packed = self.quals_packed.ctypes.data if (host and self.quals_packed is not None) else None
+        s.qual_bits = int(self.qual_bits) if (host and self.quals_packed is not None) else 0
+        s.cigar16 = self.cigar16.ctypes.data if (host and self.cigar16 is not None) else None
         return s
+
+    @staticmethod
+    def _host_buffer(nbytes: int, pinned: bool):
+        if pinned:
+            import torch
+            t = torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True)
+            return t, t.numpy()[:nbytes]
+        return None, np.empty(nbytes, np.uint8)
+
+    def pack_quals(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the bit-packed wire form of the qualities (lossless: as many bits as the largest quality needs).
+        A batch whose qualities need 8 bits is left alone."""
+        from . import capi
+        import os
+        lib = capi.load()
+        threads = threads or min(32, os.cpu_count() or 1)
+        if self.n_bases == 0 or self.n_bases % 16:
+            return self
+        bits = int(lib.pv_qual_bits(self.quals.ctypes.data, self.n_bases, threads))
+        if bits >= 8:
+            return self
+        nbytes = (self.n_bases + 31) // 32 * bits * 4
+        self._qualsp_owner, out = self._host_buffer(nbytes, pinned)
+        capi.check(lib.pv_pack_quals(self.quals.ctypes.data, self.n_bases, bits, out.ctypes.data, threads))
+        self.quals_packed, self.qual_bits = out, bits
+        return self
+
+    def pack_cigar16(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the 16-bit wire form of the CIGAR words when every op length is < 4096 (else leaves the batch alone)."""
+        from . import capi
+        import os
+        lib = capi.load()
+        if self.n_ops == 0 or int(self.cigar.max()) >> 16:
+            return self
+        self._cigar16_owner, out = self._host_buffer(self.n_ops * 2, pinned)
+        out = out.view(np.uint16)
+        capi.check(lib.pv_pack_cigar16(self.cigar.ctypes.data, self.n_ops, out.ctypes.data, threads or min(32, os.cpu_count() or 1)))
+        self.cigar16 = out
+        return self
+
+    def pack_wire(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """All compact wire forms: 4-bit bases (when the alphabet allows), bit-packed qualities, 16-bit CIGAR."""
+        from . import capi
+        try:
+            self.pack_bases4(threads, pinned)
+        except capi.PvError:
+            self.bases4 = None
+        return self.pack_quals(threads, pinned).pack_cigar16(threads, pinned)
 
     def pack_bases4(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
         """Adds the 4-bit wire form of the bases (raises if a base is outside the BAM nt16 alphabet)."""
@@ -151,7 +207,12 @@ class ReadBatch:
             region_ref_off=self.region_ref_off[r0:r1] - f_lo, region_ref_len=self.region_ref_len[r0:r1],
             region_read_begin=self.region_read_begin[r0:r1 + 1] - rb, ref=self.ref[f_lo:f_hi],
             contigs=self.contigs[r0:r1] if self.contigs else [],
-            bases4=self.bases4[b_lo // 2:b_hi // 2] if self.bases4 is not None else None)
+            bases4=self.bases4[b_lo // 2:b_hi // 2] if self.bases4 is not None else None,
+            # quality i sits at bit i * qual_bits: a 16-aligned base offset is a whole number of bytes
+            quals_packed=(self.quals_packed[b_lo * self.qual_bits // 8:min(self.quals_packed.shape[0], ((b_hi + 31) // 32 * 32) * self.qual_bits // 8)]
+                          if self.quals_packed is not None and b_lo % 16 == 0 and (b_hi - b_lo) % 16 == 0 else None),
+            qual_bits=self.qual_bits if self.quals_packed is not None else 0,
+            cigar16=self.cigar16[c_lo:c_hi] if self.cigar16 is not None else None)
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

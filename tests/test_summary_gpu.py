@@ -129,3 +129,48 @@ def test_pack_bases4_rejects_other_bytes():
     b = H.fuzz_region(3)          # contains lower-case / odd bytes
     with pytest.raises(capi.PvError):
         b.pack_bases4()
+
+
+@pytest.mark.parametrize("profile", ["ont_r9", "hifi"])
+def test_compact_wire_formats_equal_plain(profile):
+    """Bit-packed qualities + 16-bit CIGAR + 4-bit bases (host wire forms) give the same candidates as the plain arrays,
+    through the host C-ABI entry point and through the device-resident pipeline path (views of region ranges)."""
+    import torch
+    from pepper_thesis_b200 import device as dev
+    b = synth.generate(profile, 350000, 25.0, seed=8)
+    thr = synth.PROFILES[profile].thresholds
+    plain = capi.summary_regions_host(b, thr)
+    b.pack_wire()
+    assert b.quals_packed is not None and 1 <= b.qual_bits <= 6 and b.quals_packed.nbytes < b.quals.nbytes
+    packed = capi.summary_regions_host(b, thr)
+    for r in range(b.n_regions):
+        H.assert_same(gpu_region_dict(plain, r), gpu_region_dict(packed, r), "wire %s region %d" % (profile, r))
+    # a view that starts at a 16- but not 32-aligned base offset
+    v = b.region_range_view(1, 3)
+    db = dev.DeviceBatch(v)
+    torch.cuda.synchronize()
+    assert np.array_equal(db.t["quals"].cpu().numpy(), v.quals)
+    assert np.array_equal(db.t["cigar"].cpu().numpy().view(np.uint32), v.cigar)
+    assert np.array_equal(db.t["bases"].cpu().numpy(), np.where(v.bases == 0, ord("="), v.bases))
+    assert db.h2d_bytes < sum(getattr(v, n).nbytes for n in ("bases", "quals", "cigar")) * 0.75
+
+
+def test_pack_quals_roundtrip_all_widths():
+    import torch
+    rng = np.random.default_rng(0)
+    lib = capi.load()
+    for bits in range(1, 8):
+        for n in (16, 32, 48, 4096 + 16):
+            q = rng.integers(0, 1 << bits, n).astype(np.uint8)
+            q[0] = (1 << bits) - 1
+            assert lib.pv_qual_bits(q.ctypes.data, n, 3) == bits
+            packed = np.zeros((n + 31) // 32 * bits * 4, np.uint8)
+            capi.check(lib.pv_pack_quals(q.ctypes.data, n, bits, packed.ctypes.data, 3))
+            d = torch.from_numpy(packed).cuda()
+            out = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+            capi.check(lib.pv_unpack_quals(d.data_ptr(), n, bits, out.data_ptr(), None))
+            torch.cuda.synchronize()
+            assert np.array_equal(out[:n].cpu().numpy(), q) and int(out[n:].sum()) == 0
+    big = np.array([4096 << 4], np.uint32)
+    with pytest.raises(capi.PvError):
+        capi.check(lib.pv_pack_cigar16(big.ctypes.data, 1, np.zeros(1, np.uint16).ctypes.data, 1))
