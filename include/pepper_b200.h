@@ -92,6 +92,13 @@ typedef struct PvReadBatch {
     int32_t         qual_bits;
     int32_t         _pad0;
     const uint16_t* cigar16;
+    /*   bases2:      2 bits per base (A C G T = 0 1 2 3, base i in byte i/4 at bits 2*(i%4)); every base that is not an
+     *                upper-case A/C/G/T is listed in base_exceptions as (index << 8) | byte (ascending index). The 0
+     *                padding behind a read is not listed (it decodes to 'A'; no kernel looks at it). Takes precedence
+     *                over bases4 (pv_pack_bases2). */
+    const uint8_t*  bases2;
+    const uint64_t* base_exceptions;
+    int64_t         n_base_exceptions;
 } PvReadBatch;
 
 /* The ten scalars of generate_summary (region_summary.h:191-201), same order, same double compares. */
@@ -151,6 +158,13 @@ int pv_pack_quals(const uint8_t* quals_host, int64_t n_bases, int32_t qual_bits,
 /* Device: zero-extend 16-bit CIGAR words; Host: truncate them (PV_EINVAL if an op length is >= 4096). */
 int pv_unpack_cigar16(const uint16_t* packed_dev, int64_t n_ops, uint32_t* cigar_dev, void* stream);
 int pv_pack_cigar16(const uint32_t* cigar_host, int64_t n_ops, uint16_t* packed_host, int32_t threads);
+/* Device: expand 2-bit bases and apply the exception list; n_bases % 16 == 0. */
+int pv_unpack_bases2(const uint8_t* packed_dev, int64_t n_bases, const uint64_t* exceptions_dev, int64_t n_exceptions,
+                     uint8_t* bases_dev, void* stream);
+/* Host: 2-bit packing. packed_host: n_bases/4 bytes. exceptions_host may be NULL to only count; else it must hold
+ * *n_exceptions entries (the count of a previous call). */
+int pv_pack_bases2(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, uint64_t* exceptions_host,
+                   int64_t* n_exceptions, int32_t threads);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 

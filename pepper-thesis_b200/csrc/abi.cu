@@ -148,11 +148,12 @@ extern "C" int pv_batch_validate(const PvReadBatch* b) {
     if (!b) return pv::set_error(PV_EINVAL, "null batch");
     if (b->n_reads < 0 || b->n_bases < 0 || b->n_ops < 0 || b->n_regions < 0 || b->n_ref < 0)
         return pv::set_error(PV_EINVAL, "negative size");
-    if ((b->bases4 || b->quals_packed) && (b->n_bases & 15)) return pv::set_error(PV_EINVAL, "bases4 / quals_packed need n_bases to be a multiple of 16");
+    if (b->bases2 && (b->n_base_exceptions < 0 || (b->n_base_exceptions && !b->base_exceptions))) return pv::set_error(PV_EINVAL, "bases2 needs its exception list");
+    if ((b->bases4 || b->bases2 || b->quals_packed) && (b->n_bases & 15)) return pv::set_error(PV_EINVAL, "bases4 / quals_packed need n_bases to be a multiple of 16");
     if (b->quals_packed && (b->qual_bits < 1 || b->qual_bits > 7)) return pv::set_error(PV_EINVAL, "quals_packed needs qual_bits in 1..7");
     if (!b->quals_packed && !b->quals && b->n_bases) return pv::set_error(PV_EINVAL, "neither quals nor quals_packed given");
     if (!b->cigar16 && !b->cigar && b->n_ops) return pv::set_error(PV_EINVAL, "neither cigar nor cigar16 given");
-    if (!b->bases4 && !b->bases && b->n_bases) return pv::set_error(PV_EINVAL, "neither bases nor bases4 given");
+    if (!b->bases4 && !b->bases2 && !b->bases && b->n_bases) return pv::set_error(PV_EINVAL, "neither bases nor a packed form of them given");
     if (b->n_regions == 0) return PV_OK;
     if (!b->region_read_begin || b->region_read_begin[0] != 0 || b->region_read_begin[b->n_regions] != b->n_reads)
         return pv::set_error(PV_EINVAL, "region_read_begin must start at 0 and end at n_reads");
@@ -228,6 +229,28 @@ __global__ void unpack_quals_kernel(const uint32_t* __restrict__ packed, int64_t
     }
 }
 
+// 2-bit bases: a thread expands one packed word (16 bases)
+__global__ void unpack_bases2_kernel(const uint32_t* __restrict__ packed, int64_t n_vec, uint8_t* __restrict__ bases) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(packed + v);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) x |= ((0x54474341u >> (((w >> (8 * j + 2 * k)) & 3u) * 8)) & 0xffu) << (8 * k);   // "ACGT"
+            o[j] = x;
+        }
+        ((uint4*)bases)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void apply_base_exceptions_kernel(const uint64_t* __restrict__ exc, int64_t n, uint8_t* __restrict__ bases) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = exc[i];
+        bases[e >> 8] = (uint8_t)(e & 0xffu);
+    }
+}
+
 __global__ void unpack_cigar16_kernel(const uint16_t* __restrict__ packed, int64_t n, uint32_t* __restrict__ cigar) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cigar[i] = packed[i];
 }
@@ -244,7 +267,7 @@ template <class F> void parallel_ranges(int64_t n, int threads, F f) {
 struct HostCtx {
     std::mutex mu;
     pv::DevBuf arr[18];      // batch arrays in PvReadBatch order
-    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense, packed, packed_q, packed_c;
+    pv::DevBuf ws, win, pos, reg, dep, frq, al, aln, cnt, dense, packed, packed_q, packed_c, packed_e;
     cudaStream_t stream = nullptr;
 };
 HostCtx& host_ctx() { static HostCtx c; return c; }
@@ -263,6 +286,58 @@ extern "C" int pv_unpack_bases4(const uint8_t* packed_dev, int64_t n_bases, uint
     if (blocks > cap) blocks = cap;
     unpack_bases4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed_dev, n_vec, bases_dev);
     PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_unpack_bases2(const uint8_t* packed_dev, int64_t n_bases, const uint64_t* exc_dev, int64_t n_exc, uint8_t* bases_dev,
+                                void* stream) {
+    if (!packed_dev || !bases_dev || n_bases < 0 || (n_bases & 15) || n_exc < 0 || (n_exc && !exc_dev) || ((uintptr_t)packed_dev & 3))
+        return pv::set_error(PV_EINVAL, "pv_unpack_bases2: bad arguments (n_bases %% 16 == 0, 4-byte aligned input)");
+    if (n_bases == 0) return PV_OK;
+    if (int rc = pv::require_device()) return rc;
+    const int64_t n_vec = n_bases / 16, cap = (int64_t)pv::sm_count() * 16;
+    int64_t blocks = (n_vec + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    unpack_bases2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)packed_dev, n_vec, bases_dev);
+    if (n_exc) {
+        blocks = (n_exc + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        apply_base_exceptions_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(exc_dev, n_exc, bases_dev);
+    }
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_pack_bases2(const uint8_t* bases, int64_t n_bases, uint8_t* packed, uint64_t* exc, int64_t* n_exc, int32_t threads) {
+    if (!bases || !packed || !n_exc || n_bases < 0 || (n_bases & 3)) return pv::set_error(PV_EINVAL, "pv_pack_bases2: bad arguments");
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    const int64_t n_out = n_bases / 4;
+    std::vector<int64_t> cnt((size_t)threads + 1, 0);
+    auto code = [](uint8_t c) -> int { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; };
+    parallel_ranges(n_out, threads, [&](int t, int64_t lo, int64_t hi) {
+        int64_t c = 0;
+        for (int64_t i = lo; i < hi; i++) {
+            uint8_t o = 0;
+            for (int k = 0; k < 4; k++) {
+                const uint8_t b = bases[4 * i + k];
+                const int v = code(b);
+                if (v >= 0) o |= (uint8_t)(v << (2 * k)); else if (b != 0) c++;
+            }
+            packed[i] = o;
+        }
+        cnt[(size_t)t + 1] = c;
+    });
+    for (int t = 0; t < threads; t++) cnt[(size_t)t + 1] += cnt[(size_t)t];
+    const int64_t total = cnt[(size_t)threads];
+    if (exc) {
+        if (*n_exc != total) return pv::set_error(PV_EINVAL, "pv_pack_bases2: exception buffer holds %lld entries, %lld needed", (long long)*n_exc, (long long)total);
+        parallel_ranges(n_out, threads, [&](int t, int64_t lo, int64_t hi) {
+            int64_t at = cnt[(size_t)t];
+            for (int64_t i = 4 * lo; i < 4 * hi; i++) { const uint8_t b = bases[i]; if (b != 0 && code(b) < 0) exc[at++] = ((uint64_t)i << 8) | b; }
+        });
+    }
+    *n_exc = total;
     return PV_OK;
 }
 
@@ -400,6 +475,16 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
                               (size_t)hb->n_regions * 8, (size_t)(hb->n_regions + 1) * 8, (size_t)hb->n_ref};
     for (int i = 0; i < 18; i++) {
         if (int rc = h.arr[i].reserve(bytes[i] + 16)) return rc;
+        if (i == 7 && hb->bases2 && hb->n_bases) {          // bases travel 2-bit packed (+ exception list)
+            if (int rc = h.packed.reserve((size_t)hb->n_bases / 4 + 16)) return rc;
+            if (int rc = h.packed_e.reserve((size_t)hb->n_base_exceptions * 8 + 16)) return rc;
+            PV_CUDA_CHECK(cudaMemcpyAsync(h.packed.p, hb->bases2, (size_t)hb->n_bases / 4, cudaMemcpyHostToDevice, st));
+            if (hb->n_base_exceptions)
+                PV_CUDA_CHECK(cudaMemcpyAsync(h.packed_e.p, hb->base_exceptions, (size_t)hb->n_base_exceptions * 8, cudaMemcpyHostToDevice, st));
+            if (int rc = pv_unpack_bases2((const uint8_t*)h.packed.p, hb->n_bases, (const uint64_t*)h.packed_e.p, hb->n_base_exceptions,
+                                          (uint8_t*)h.arr[7].p, st)) return rc;
+            continue;
+        }
         if (i == 7 && hb->bases4 && hb->n_bases) {          // bases travel 4-bit packed and are expanded on the device
             if (int rc = h.packed.reserve((size_t)hb->n_bases / 2 + 16)) return rc;
             PV_CUDA_CHECK(cudaMemcpyAsync(h.packed.p, hb->bases4, (size_t)hb->n_bases / 2, cudaMemcpyHostToDevice, st));
@@ -423,6 +508,7 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
     }
     PvReadBatch db = *hb;
     db.bases4 = nullptr; db.quals_packed = nullptr; db.qual_bits = 0; db.cigar16 = nullptr;
+    db.bases2 = nullptr; db.base_exceptions = nullptr; db.n_base_exceptions = 0;
     db.read_pos = (const int64_t*)h.arr[0].p; db.read_base_off = (const int64_t*)h.arr[1].p; db.read_len = (const int32_t*)h.arr[2].p;
     db.read_cigar_off = (const int64_t*)h.arr[3].p; db.read_n_ops = (const int32_t*)h.arr[4].p; db.read_flags = (const uint8_t*)h.arr[5].p;
     db.read_mapq = (const uint8_t*)h.arr[6].p; db.bases = (const uint8_t*)h.arr[7].p; db.quals = (const uint8_t*)h.arr[8].p;

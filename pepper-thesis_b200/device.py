@@ -30,12 +30,21 @@ class DeviceBatch:
         self.host = host
         self.device = torch.device(device)
         self.t = {}
-        self.packed = None          # 4-bit bases
+        self.packed = None          # 4-bit or 2-bit bases
+        self.packed_exc = None      # exception list of the 2-bit form
         self.packed_q = None        # bit-packed qualities
         self.packed_c = None        # 16-bit CIGAR words
         self._unpacked = True
         for name in ARRAY_NAMES:
             a = getattr(host, name)
+            if name == "bases" and host.bases2 is not None and a.size:
+                self.packed = torch.empty(a.size // 4 + 16, dtype=torch.uint8, device=self.device)
+                self.packed[:a.size // 4].copy_(_to_torch(host.bases2), non_blocking=non_blocking)
+                if host.base_exceptions.size:
+                    self.packed_exc = torch.from_numpy(host.base_exceptions.view(np.int64)).to(self.device, non_blocking=non_blocking)
+                self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
+                self._unpacked = False
+                continue
             if name == "bases" and host.bases4 is not None and a.size:
                 # bases travel in the BAM-native 4-bit form and are expanded on the device (pv_unpack_bases4)
                 self.packed = _to_torch(host.bases4).to(self.device, non_blocking=non_blocking)
@@ -70,7 +79,12 @@ class DeviceBatch:
             return
         lib = capi.load()
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        if self.packed is not None:
+        if self.packed is not None and self.host.bases2 is not None:
+            out = self.t["bases"]
+            ne = 0 if self.packed_exc is None else self.packed_exc.numel()
+            capi.check(lib.pv_unpack_bases2(C.c_void_p(self.packed.data_ptr()), out.numel(),
+                                            C.c_void_p(self.packed_exc.data_ptr() if ne else None), ne, C.c_void_p(out.data_ptr()), st))
+        elif self.packed is not None:
             out = self.t["bases"]
             capi.check(lib.pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
         if self.packed_q is not None:
@@ -83,13 +97,15 @@ class DeviceBatch:
         self._unpacked = True
 
     def record_stream(self, stream):
-        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_q, self.packed_c) if x is not None]:
+        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c) if x is not None]:
             t.record_stream(stream)
 
     @property
     def h2d_bytes(self) -> int:
         n = int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
-        if self.packed is not None:
+        if self.packed is not None and self.host.bases2 is not None:
+            n -= self.host.bases.nbytes - self.host.bases2.nbytes - self.host.base_exceptions.nbytes
+        elif self.packed is not None:
             n -= self.host.bases.nbytes - self.host.bases4.nbytes
         if self.packed_q is not None:
             n -= self.host.quals.nbytes - min((self.host.quals.size * self.host.qual_bits + 7) // 8, self.host.quals_packed.nbytes)

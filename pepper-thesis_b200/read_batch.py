@@ -30,7 +30,8 @@ class PvReadBatchStruct(C.Structure):
                 ("region_cand_end", C.c_void_p), ("region_ref_off", C.c_void_p), ("region_ref_len", C.c_void_p),
                 ("region_read_begin", C.c_void_p),
                 ("ref", C.c_void_p), ("bases4", C.c_void_p),
-                ("quals_packed", C.c_void_p), ("qual_bits", C.c_int32), ("_pad0", C.c_int32), ("cigar16", C.c_void_p)]
+                ("quals_packed", C.c_void_p), ("qual_bits", C.c_int32), ("_pad0", C.c_int32), ("cigar16", C.c_void_p),
+                ("bases2", C.c_void_p), ("base_exceptions", C.c_void_p), ("n_base_exceptions", C.c_int64)]
 
 
 ARRAY_NAMES = [n for n, _ in _READ_FIELDS] + ["bases", "quals", "cigar"] + [n for n, _ in _REGION_FIELDS] + \
@@ -63,6 +64,8 @@ class ReadBatch:
     quals_packed: Optional[np.ndarray] = None   # optional dense bit stream of `quals` (qual_bits per quality)
     qual_bits: int = 0
     cigar16: Optional[np.ndarray] = None     # optional low 16 bits of every CIGAR word (all op lengths < 4096)
+    bases2: Optional[np.ndarray] = None      # optional 2-bit packing of `bases` (n_bases / 4 bytes) ...
+    base_exceptions: Optional[np.ndarray] = None   # ... + uint64 (index << 8 | byte) of every base that is not A/C/G/T
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -117,6 +120,10 @@ class ReadBatch:
         s.quals_packed = self.quals_packed.ctypes.data if (host and self.quals_packed is not None) else None
         s.qual_bits = int(self.qual_bits) if (host and self.quals_packed is not None) else 0
         s.cigar16 = self.cigar16.ctypes.data if (host and self.cigar16 is not None) else None
+        use2 = host and self.bases2 is not None
+        s.bases2 = self.bases2.ctypes.data if use2 else None
+        s.base_exceptions = self.base_exceptions.ctypes.data if (use2 and self.base_exceptions.size) else None
+        s.n_base_exceptions = int(self.base_exceptions.shape[0]) if use2 else 0
         return s
 
     @staticmethod
@@ -158,14 +165,45 @@ class ReadBatch:
         self.cigar16 = out
         return self
 
-    def pack_wire(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
-        """All compact wire forms: 4-bit bases (when the alphabet allows), bit-packed qualities, 16-bit CIGAR."""
+    def pack_bases2(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the 2-bit wire form of the bases + the list of bases that are not upper-case A/C/G/T (any byte value is
+        representable). Left alone when the exception list would cost more than 2-bit packing saves over 4 bits."""
         from . import capi
-        try:
-            self.pack_bases4(threads, pinned)
-        except capi.PvError:
-            self.bases4 = None
+        import os
+        lib = capi.load()
+        threads = threads or min(32, os.cpu_count() or 1)
+        if self.n_bases == 0 or self.n_bases % 16:
+            return self
+        self._bases2_owner, out = self._host_buffer(self.n_bases // 4, pinned)
+        n_exc = C.c_int64(0)
+        capi.check(lib.pv_pack_bases2(self.bases.ctypes.data, self.n_bases, out.ctypes.data, None, C.byref(n_exc), threads))
+        if n_exc.value * 8 > self.n_bases // 4:
+            return self
+        exc = np.zeros(n_exc.value, np.uint64)
+        if n_exc.value:
+            capi.check(lib.pv_pack_bases2(self.bases.ctypes.data, self.n_bases, out.ctypes.data, exc.ctypes.data, C.byref(n_exc), threads))
+        self.bases2, self.base_exceptions = out, exc
+        return self
+
+    def pack_wire(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """All compact (lossless) wire forms: 2-bit bases + exceptions (else 4-bit when the alphabet allows), bit-packed
+        qualities, 16-bit CIGAR."""
+        from . import capi
+        self.pack_bases2(threads, pinned)
+        if self.bases2 is None:
+            try:
+                self.pack_bases4(threads, pinned)
+            except capi.PvError:
+                self.bases4 = None
         return self.pack_quals(threads, pinned).pack_cigar16(threads, pinned)
+
+    def _exceptions_view(self, b_lo: int, b_hi: int):
+        if self.bases2 is None:
+            return None
+        idx = self.base_exceptions >> np.uint64(8)
+        lo, hi = np.searchsorted(idx, [b_lo, b_hi])
+        e = self.base_exceptions[lo:hi]
+        return ((idx[lo:hi] - np.uint64(b_lo)) << np.uint64(8)) | (e & np.uint64(0xff))
 
     def pack_bases4(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
         """Adds the 4-bit wire form of the bases (raises if a base is outside the BAM nt16 alphabet)."""
@@ -212,7 +250,9 @@ class ReadBatch:
             quals_packed=(self.quals_packed[b_lo * self.qual_bits // 8:min(self.quals_packed.shape[0], ((b_hi + 31) // 32 * 32) * self.qual_bits // 8)]
                           if self.quals_packed is not None and b_lo % 16 == 0 and (b_hi - b_lo) % 16 == 0 else None),
             qual_bits=self.qual_bits if self.quals_packed is not None else 0,
-            cigar16=self.cigar16[c_lo:c_hi] if self.cigar16 is not None else None)
+            cigar16=self.cigar16[c_lo:c_hi] if self.cigar16 is not None else None,
+            bases2=self.bases2[b_lo // 4:b_hi // 4] if self.bases2 is not None else None,
+            base_exceptions=self._exceptions_view(b_lo, b_hi))
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

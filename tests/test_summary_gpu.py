@@ -151,7 +151,11 @@ def test_compact_wire_formats_equal_plain(profile):
     torch.cuda.synchronize()
     assert np.array_equal(db.t["quals"].cpu().numpy(), v.quals)
     assert np.array_equal(db.t["cigar"].cpu().numpy().view(np.uint32), v.cigar)
-    assert np.array_equal(db.t["bases"].cpu().numpy(), np.where(v.bases == 0, ord("="), v.bases))
+    real = np.zeros(v.n_bases, bool)
+    for i in range(v.n_reads):
+        real[int(v.read_base_off[i]):int(v.read_base_off[i]) + int(v.read_len[i])] = True
+    assert np.array_equal(db.t["bases"].cpu().numpy()[real], v.bases[real])           # padding behind a read is don't-care
+    assert v.bases2 is not None
     assert db.h2d_bytes < sum(getattr(v, n).nbytes for n in ("bases", "quals", "cigar")) * 0.75
 
 
@@ -174,3 +178,28 @@ def test_pack_quals_roundtrip_all_widths():
     big = np.array([4096 << 4], np.uint32)
     with pytest.raises(capi.PvError):
         capi.check(lib.pv_pack_cigar16(big.ctypes.data, 1, np.zeros(1, np.uint16).ctypes.data, 1))
+
+
+def test_bases2_exceptions_roundtrip():
+    """2-bit bases with every kind of odd byte (N, lower case, '=', 255) in the exception list; views re-base the list."""
+    import torch
+    from pepper_thesis_b200 import device as dev
+    b = H.fuzz_region(3)                       # weird bytes in the reads
+    big = synth.generate("ont_r9", 250000, 10.0, seed=2)
+    rng = np.random.default_rng(1)
+    pos = rng.integers(0, big.n_bases, 500)
+    big.bases[pos] = rng.choice(np.frombuffer(b"NnacgtRY=\xff", np.uint8), 500)
+    for batch in (b, big):
+        plain = capi.summary_regions_host(batch, H.R9)
+        batch.pack_bases2()
+        assert batch.bases2 is not None and batch.base_exceptions.size > 0
+        packed = capi.summary_regions_host(batch, H.R9)
+        for r in range(batch.n_regions):
+            H.assert_same(gpu_region_dict(plain, r), gpu_region_dict(packed, r), "bases2 region %d" % r)
+    v = big.region_range_view(1, 2)
+    db = dev.DeviceBatch(v)
+    torch.cuda.synchronize()
+    got = db.t["bases"].cpu().numpy()
+    for i in range(v.n_reads):
+        o, n = int(v.read_base_off[i]), int(v.read_len[i])
+        assert np.array_equal(got[o:o + n], v.bases[o:o + n])
