@@ -35,13 +35,16 @@ class DeviceBatch:
         self.packed_q = None        # bit-packed qualities
         self.packed_c = None        # 16-bit CIGAR words
         self._unpacked = True
+        small = []
         for name in ARRAY_NAMES:
             a = getattr(host, name)
             if name == "bases" and host.bases2 is not None and a.size:
                 self.packed = torch.empty(a.size // 4 + 16, dtype=torch.uint8, device=self.device)
                 self.packed[:a.size // 4].copy_(_to_torch(host.bases2), non_blocking=non_blocking)
                 if host.base_exceptions.size:
-                    self.packed_exc = torch.from_numpy(host.base_exceptions.view(np.int64)).to(self.device, non_blocking=non_blocking)
+                    self._exc_stage = torch.empty(host.base_exceptions.size, dtype=torch.int64, pin_memory=bool(non_blocking))
+                    self._exc_stage.numpy()[:] = host.base_exceptions.view(np.int64)
+                    self.packed_exc = self._exc_stage.to(self.device, non_blocking=non_blocking)
                 self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
                 self._unpacked = False
                 continue
@@ -64,8 +67,27 @@ class DeviceBatch:
                 self.t[name] = torch.empty(a.size, dtype=torch.int32, device=self.device)
                 self._unpacked = False
                 continue
+            if name not in ("bases", "quals", "cigar", "ref"):
+                small.append(name)                       # per-read / per-region arrays: staged together below
+                continue
             src = _to_torch(a) if a.size else torch.zeros(1, dtype=_TORCH_DT[np.dtype(a.dtype)])
             self.t[name] = src.to(self.device, non_blocking=non_blocking)
+        # the ~14 small arrays (offsets rebuilt per view live in pageable memory, whose "async" copies block the host) go
+        # through ONE pinned staging buffer and one copy; the device tensors are views of one allocation
+        offs, total = {}, 0
+        for name in small:
+            offs[name] = total
+            total += (max(getattr(host, name).nbytes, 8) + 255) // 256 * 256
+        self._stage = torch.empty(max(total, 256), dtype=torch.uint8, pin_memory=bool(non_blocking))
+        stage_np = self._stage.numpy()
+        for name in small:
+            a = getattr(host, name)
+            stage_np[offs[name]:offs[name] + a.nbytes] = a.view(np.uint8).reshape(-1)
+        self._small_dev = self._stage.to(self.device, non_blocking=non_blocking)
+        for name in small:
+            a = getattr(host, name)
+            dt = _TORCH_DT[np.dtype(a.dtype)]
+            self.t[name] = self._small_dev[offs[name]:offs[name] + max(a.nbytes, 8)].view(dt)[:max(a.size, 1) if a.size == 0 else a.size]
         self.region_len = np.ascontiguousarray(host.region_len)
         self.total_positions = int(self.region_len.sum())
         self.struct = host.as_struct({n: self.t[n].data_ptr() for n in ARRAY_NAMES})
@@ -97,7 +119,7 @@ class DeviceBatch:
         self._unpacked = True
 
     def record_stream(self, stream):
-        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c) if x is not None]:
+        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self._small_dev) if x is not None]:
             t.record_stream(stream)
 
     @property

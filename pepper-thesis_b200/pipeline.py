@@ -246,7 +246,21 @@ class HotPath:
             return Predictions.empty()
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(self.device)
-        groups = [(r0, min(n, r0 + self.group_regions)) for r0 in range(0, n, self.group_regions)]
+        # The run ends one group's kernels (+ the inference of whatever windows are still waiting) after the last upload
+        # ends, so the last groups are made small: a short first group (nothing to overlap with yet), full groups, then a
+        # taper g/2, g/4, ... whose windows are inferred at once.
+        g = self.group_regions
+        taper = [t for t in (g // 2, g // 4, g // 8) if t >= 2]
+        while taper and sum(taper) > n // 2:
+            taper.pop(0)
+        body = n - sum(taper)
+        sizes = [body % g] if body % g else []
+        sizes += [g] * (body // g)
+        n_body = len(sizes)
+        sizes += taper
+        groups, r0 = [], 0
+        for sz in sizes:
+            groups.append((r0, r0 + sz)); r0 += sz
         main = torch.cuda.current_stream(self.device)
 
         def upload(g):
@@ -258,16 +272,22 @@ class HotPath:
 
         run = HotPath._Run()
         self._acc_buffer(self.infer_batch * 2)
-        nxt = upload(groups[0])
+        # uploads are queued `ahead` groups in front of the kernels: the copy stream never waits for the host (which
+        # blocks on every group's candidate count), so the copies run back to back at PCIe speed
+        ahead = 4
+        queue = [upload(groups[j]) for j in range(min(ahead, len(groups)))]
         for i, g in enumerate(groups):
-            db, ev = nxt
+            db, ev = queue.pop(0)
             main.wait_event(ev)
-            if i + 1 < len(groups):
-                nxt = upload(groups[i + 1])
+            if i + ahead < len(groups):
+                queue.append(upload(groups[i + ahead]))
             db.unpack()                           # compact wire forms -> plain arrays, on the compute stream
-            # this path is bound by the H2D copies, so the simple synchronous form is used: the host waits for the group's
-            # candidate count before queueing more (measured: queueing further ahead slows the copies down)
             ws, k = self.summarize(db)
             self._push(run, ws, k, region_offset + g[0])
+            # this path is bound by the uploads and the kernels have ~50 % slack: infer every full group's windows at once
+            # (smaller passes, a little less efficient) instead of letting full passes pile up behind the last upload;
+            # the small groups of the taper share one last pass (a pass costs >= 66 launch latencies however small)
+            if i < n_body or i == len(groups) - 1:
+                self._drain(run, final=True)
             db.record_stream(main)
         return self._finish(run, True)
