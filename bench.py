@@ -301,7 +301,18 @@ def run_ours(args):
             achieved = alg / (ms_d / 1e3) / 1e9
             roof = {"kernel": dominant, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "avg_launch_ms": round(per_launch_ms, 4),
-                    "launches": n_d, "peak_source": peak_src}
+                    "launches": n_d, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg / max(1, n_d))}
+            # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this command
+            # (profiles/r1_k1_v5_bench_traffic.json), scaled to this run's regions per launch
+            try:
+                with open(os.path.join(ROOT, "profiles", "r1_k1_v5_bench_traffic.json")) as f:
+                    tr = json.load(f)
+                if tr.get("kernel") == dominant:
+                    regions_per_launch = n_regions * args.steps / max(1, n_d)
+                    roof["traffic"] = int(tr["dram_bytes_per_launch"] * regions_per_launch / tr["regions_per_launch"])
+                    roof["traffic_source"] = "profiles/r1_k1_v5_bench_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+            except Exception:
+                pass
     # the summary chain's own HBM roofline is always reported next to it
     sum_ms = sum(fam_ms.get(f, 0.0) for f in ("sum_cigar_prefix", "sum_pileup_tile", "sum_site_alleles", "sum_key_sort", "sum_emit_windows"))
     alg = batch.algorithmic_bytes(k_per_step) * args.steps
