@@ -396,23 +396,28 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
 // Pass 1, lane per op: a match run only marks where it enters and leaves the tile in the coverage difference array
 // and files its clipped base range in the warp's piece table; inserts and deletes do their anchor counting here (the
 // anchor's missing REFF/REFR decrement of :381-391 is charged by the insert/delete op that follows the run).
-__device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
+__device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int lane) {
     const PvReadBatch& b = p.b;
     const ReadCtx x = make_read_ctx(p, c, r);
     int32_t* t_beg = c.scratch;                              // [TBL]
     uint32_t* t_pc = (uint32_t*)(c.scratch + TBL);           // [TBL]
     int32_t* t_sub = c.scratch + 2 * TBL;                    // [TBL]
     int n_e = 0, n_sub = 0;
-    for (int kb = k_begin; kb < k_end; kb += 32) {
+    // ops are walked from k_begin until one starts behind the position right after the tile (op starts never decrease;
+    // an insert/delete at nv still anchors on the tile's last position): no search for the end of the range
+    for (int kb = k_begin; kb < x.n_ops; kb += 32) {
         const int k = kb + lane;
-        const bool have = k < k_end;
+        bool have = k < x.n_ops;
         const uint32_t w = have ? b.cigar[x.co + k] : 0u;
-        const int op = have ? (int)(w & 15u) : 15;
-        const int len = (int)(w >> 4);
         int64_t a64 = have ? x.rel_t + (int64_t)x.oref[k] : 0;                   // op start, tile-local
         if (a64 > (1 << 30)) a64 = (1 << 30);
         if (a64 < -(1 << 30)) a64 = -(1 << 30);
         const int a = (int)a64;
+        const bool beyond = have && a > x.nv;
+        const bool last_step = __any_sync(0xffffffffu, beyond) || kb + 32 >= x.n_ops;
+        have = have && !beyond;
+        const int op = have ? (int)(w & 15u) : 15;
+        const int len = (int)(w >> 4);
         const int ori = have ? x.ori_a[k] : 0;
         uint32_t pw = __shfl_up_sync(0xffffffffu, w, 1);                         // the op in front of this one
         if (lane == 0) pw = k > 0 ? b.cigar[x.co + k - 1] : 0u;
@@ -486,12 +491,13 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
         }
         n_e += __popc(nz);
         n_sub += __shfl_sync(0xffffffffu, incl, 31);
-        if (n_e > TBL - 32 || kb + 32 >= k_end) {
+        if (n_e > TBL - 32 || last_step) {
             __syncwarp();
             if (n_e > 0) scan_pieces(p, c, x, t_beg, t_pc, t_sub, n_e, n_sub, lane);
             n_e = 0; n_sub = 0;
             __syncwarp();
         }
+        if (last_step) break;
     }
 }
 
@@ -499,20 +505,21 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
 // Phase C work unit: re-walks CIGAR ops [k_begin, k_end) of one read (whole warp, lane per op) and records the
 // insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and :507-535, needed only
 // where the site thresholds passed).
-__device__ void record_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int k_end, int lane) {
+__device__ void record_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int lane) {
     const PvReadBatch& b = p.b;
     const ReadCtx x = make_read_ctx(p, c, r);
-    for (int kb = k_begin; kb < k_end; kb += 32) {
+    for (int kb = k_begin; kb < x.n_ops; kb += 32) {
         const int k = kb + lane;
-        if (k >= k_end) break;
-        const uint32_t w = b.cigar[x.co + k];
-        const int op = (int)(w & 15u);
-        if (op != 1 && op != 2) continue;
-        const int len = (int)(w >> 4);
-        int64_t a64 = x.rel_t + (int64_t)x.oref[k];
+        const bool in = k < x.n_ops;
+        const uint32_t w = in ? b.cigar[x.co + k] : 0u;
+        int64_t a64 = in ? x.rel_t + (int64_t)x.oref[k] : (int64_t)(1 << 30);
         if (a64 > (1 << 30)) a64 = (1 << 30);
         if (a64 < -(1 << 30)) a64 = -(1 << 30);
         const int a = (int)a64;
+        if (__all_sync(0xffffffffu, a > x.nv)) break;          // everything from here on starts behind the tile
+        const int op = (int)(w & 15u);
+        if (!in || (op != 1 && op != 2)) continue;
+        const int len = (int)(w >> 4);
         if (a > x.l_end) continue;
         const int ol = a - 1;
         if (ol < 0 || ol >= x.nv) continue;
@@ -564,11 +571,10 @@ __device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, i
     record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
 }
 
-// The tile's work list: every read of the region that touches the tile, cut into UNIT_PARTS units. A warp that pulls a
-// unit first finds the read's op range inside the tile with two warp-wide 32-ary searches in the CIGAR prefix (coalesced
-// probes, 2-3 rounds each), then walks its share of that range. No thread-serial set-up phase: the searches of one
-// warp overlap the walking of the others.
-constexpr int UNIT_PARTS = 2;
+// The tile's work list: every read of the region that touches the tile. A warp that pulls a read first finds the read's
+// first op inside the tile with one warp-wide 32-ary search in the CIGAR prefix (coalesced probes, 2-3 rounds), then
+// walks the ops until they leave the tile. No thread-serial set-up phase: the search of one warp overlaps the walking
+// of the others.
 
 template <int MODE>
 __device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next) {
@@ -588,31 +594,22 @@ __device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_l
             s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
         }
         __syncthreads();
-        const int n = *s_n * UNIT_PARTS;
+        const int n = *s_n;
         while (true) {
             int i = 0;
             if (lane == 0) i = atomicAdd(s_next, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
-            const int64_t r = base + s_list[i / UNIT_PARTS];
-            const int part = i % UNIT_PARTS;
-            // ops [k_lo, k_hi): reference start a_k = rel + op_ref[k] <= t_hi + 1 (an insert/delete right behind the tile
-            // anchors on its last position) and end >= t_lo (one op before the first a_k >= t_lo may extend in)
+            const int64_t r = base + s_list[i];
+            // first op: one op before the first a_k = rel + op_ref[k] >= t_lo may extend into the tile; the walk ends at the
+            // first op that starts behind t_hi + 1 (an insert/delete right behind the tile anchors on its last position)
             const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
             const int32_t* oref = p.op_ref + b.read_cigar_off[r];
             const int n_ops = b.read_n_ops[r];
             int k_lo = warp_lower_bound(oref, n_ops, t_lo - rel, lane) - 1;
             if (k_lo < 0) k_lo = 0;
-            const int k_hi = warp_lower_bound(oref, n_ops, t_hi + 1 - rel + 1, lane);
-            const int n_k = k_hi - k_lo;
-            if (n_k <= 0) continue;
-            int per = (n_k + UNIT_PARTS - 1) / UNIT_PARTS;
-            per = (per + 31) & ~31;                                              // whole warp steps
-            const int k_begin = k_lo + part * per;
-            const int k_end = k_begin + per < k_hi ? k_begin + per : k_hi;
-            if (k_begin >= k_end) continue;
-            if (MODE == 0) accumulate_unit(p, c, r, k_begin, k_end, lane);
-            else record_unit(p, c, r, k_begin, k_end, lane);
+            if (MODE == 0) accumulate_unit(p, c, r, k_lo, lane);
+            else record_unit(p, c, r, k_lo, lane);
         }
         __syncthreads();
     }
