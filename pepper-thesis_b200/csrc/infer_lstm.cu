@@ -388,6 +388,12 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
                 g.a0_slot[0] = tf; g.a0_slot[1] = tb + 2;       // slot of h_{t-1} (forward) / h_{t+1} (reverse)
                 if (layer == 0) { g.a1_slot[0] = tf; g.a1_slot[1] = tb; g.a1_col[0] = g.a1_col[1] = 0; }
                 else { g.a1_slot[0] = tf + 1; g.a1_slot[1] = tb + 1; g.a1_col[0] = g.a1_col[1] = 0; }
+#ifdef PV_TRACE
+                {   // trace only the launch PV_TRACE_STEP (0..32 encoder, 33..65 decoder) of each pass; default: the last one
+                    static int target = -2; if (target == -2) { const char* v = getenv("PV_TRACE_STEP"); target = v ? atoi(v) : 65; }
+                    g.trace = (layer * T + s == target) ? pv_trace_buffer : nullptr;
+                }
+#endif
                 if (int rc = launch_gemm(layer == 0 ? map_enc : map_dec, layer == 0 ? map_x : map_enc,
                                          layer == 0 ? m->map_enc_w : m->map_dec_w, g, e, m->sms, st)) return rc;
             }

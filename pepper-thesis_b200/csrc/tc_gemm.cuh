@@ -197,6 +197,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const int cluster_id = (int)blockIdx.x / CLUSTER, n_clusters = (int)gridDim.x / CLUSTER;
     const int m_grps = (g.m_blks + CLUSTER - 1) / CLUSTER;
     const int n_tiles = m_grps * g.n_blks * g.dirs;             // groups
+    // dirs and n_blks are powers of two (1/2 and 2/4): tile -> (dir, n_blk, m group) with shifts, no integer division
+    const int dir_sh = g.dirs >> 1, nb_sh = 31 - __clz(g.n_blks), dir_mask = g.dirs - 1, nb_mask = g.n_blks - 1;
     const int kbt = g.kb0 + g.kb1;
     constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
 
@@ -221,9 +223,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0; int itp = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, itp++) {
-                const int dir = tile % g.dirs;
-                const int n_blk = (tile / g.dirs) % g.n_blks;
-                const int m_blk = (tile / (g.dirs * g.n_blks)) * CLUSTER + crank;
+                const int dir = tile & dir_mask;
+                const int n_blk = (tile >> dir_sh) & nb_mask;
+                const int m_blk = (tile >> (dir_sh + nb_sh)) * CLUSTER + crank;
                 PV_TR(0, itp, 0);
                 for (int kb = 0; kb < kbt; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -282,20 +284,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         int it = 0;
         if (cluster_id < n_tiles) {                            // state of the first tile
             const int tile = cluster_id;
-            const int row = ((tile / (g.dirs * g.n_blks)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
-            epi.prefetch(epi_scratch, 0, tile % g.dirs, (tile / g.dirs) % g.n_blks, row, row < g.M, half, te);
+            const int row = ((tile >> (dir_sh + nb_sh)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
+            epi.prefetch(epi_scratch, 0, tile & dir_mask, (tile >> dir_sh) & nb_mask, row, row < g.M, half, te);
         }
         cp_async_commit();
         for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
-            const int dir = tile % g.dirs;
-            const int n_blk = (tile / g.dirs) % g.n_blks;
-            const int m_blk = (tile / (g.dirs * g.n_blks)) * CLUSTER + crank;
+            const int dir = tile & dir_mask;
+            const int n_blk = (tile >> dir_sh) & nb_mask;
+            const int m_blk = (tile >> (dir_sh + nb_sh)) * CLUSTER + crank;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int nxt = tile + n_clusters;
             if (nxt < n_tiles) {                               // next tile's state: lands while this tile is computed
-                const int nrow = ((nxt / (g.dirs * g.n_blks)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
-                epi.prefetch(epi_scratch, acc ^ 1, nxt % g.dirs, (nxt / g.dirs) % g.n_blks, nrow, nrow < g.M, half, te);
+                const int nrow = ((nxt >> (dir_sh + nb_sh)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
+                epi.prefetch(epi_scratch, acc ^ 1, nxt & dir_mask, (nxt >> dir_sh) & nb_mask, nrow, nrow < g.M, half, te);
             }
             cp_async_commit();
             if (te == 0) PV_TR(2, it, 0);
