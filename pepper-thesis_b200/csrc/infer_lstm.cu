@@ -175,20 +175,28 @@ struct SeluEpilogue {
 // windows int16 [n][33][26] -> xhl bf16 [n][33][128]: cols 0..25 = x_hi, 26..51 = x_lo (x == x_hi + x_lo exactly; both
 // meet bf16(W_ih)), cols 64..89 = x_hi again (meets the bf16 remainder of W_ih), rest 0
 __global__ void prep_input_kernel(const int16_t* __restrict__ win, __nv_bfloat16* __restrict__ xhl, int64_t n, int wrap_int8) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over n*33*64
-    if (i >= n * T * XK) return;
-    const int col = (int)(i % XK);
-    const int64_t rt = i / XK;
-    float v = 0.f;
-    const int f = col < 2 * F ? (col < F ? col : col - F) : (col >= 64 && col < 64 + F ? col - 64 : -1);
-    if (f >= 0) {
-        int x = win[rt * F + f];
-        if (wrap_int8) x = (int)(int8_t)x;                                  // DataStore.py:68 int8 round trip
-        const float xf = (float)x;
-        const float hi = __bfloat162float(__float2bfloat16_rn(xf));
-        v = (col >= F && col < 2 * F) ? xf - hi : hi;
+    // a thread writes 8 consecutive output columns (one 16-byte store); 16 threads share one 52-byte input row
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over n*33*16
+    if (i >= n * T * (XK / 8)) return;
+    const int c0 = (int)(i & (XK / 8 - 1)) * 8;
+    const int64_t rt = i / (XK / 8);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int col = c0 + k;
+        const int f = col < 2 * F ? (col < F ? col : col - F) : (col >= 64 && col < 64 + F ? col - 64 : -1);
+        float v = 0.f;
+        if (f >= 0) {
+            int x = __ldg(win + rt * F + f);
+            if (wrap_int8) x = (int)(int8_t)x;                                  // DataStore.py:68 int8 round trip
+            const float xf = (float)x;
+            const float hi = __bfloat162float(__float2bfloat16_rn(xf));
+            v = (col >= F && col < 2 * F) ? xf - hi : hi;
+        }
+        const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+        if (k & 1) o[k >> 1] |= b << 16; else o[k >> 1] = b;
     }
-    xhl[i] = __float2bfloat16_rn(v);
+    *(uint4*)(xhl + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // output_layer_type (512 -> 3) + softmax + argmax; one warp per window
@@ -356,7 +364,7 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
 
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t nb = n - off < chunk ? n - off : chunk;
-        const int64_t elems = nb * T * XK;
+        const int64_t elems = nb * T * (XK / 8);
         pv::prof_begin(pv::FAM_LSTM_PREP, st);
         prep_input_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(windows + off * T * F, w.xhl, nb, wrap_int8);
         PV_CUDA_CHECK(cudaGetLastError());
