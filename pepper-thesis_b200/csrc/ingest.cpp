@@ -185,10 +185,27 @@ namespace {
 
 static const char NT16[] = "=ACMGRSVTWYHKDBN";
 
+// packed 4-bit bases [start, start + count) of a BAM record -> ASCII, two bases per table lookup
+struct Nt16Pairs {
+    uint16_t t[256];
+    Nt16Pairs() { for (int i = 0; i < 256; i++) t[i] = (uint16_t)((uint8_t)NT16[i >> 4] | ((uint16_t)(uint8_t)NT16[i & 15] << 8)); }
+};
+static const Nt16Pairs NT16_PAIRS;
+inline void decode_bases(const uint8_t* packed, int64_t start, int64_t count, std::vector<uint8_t>& out) {
+    if (count <= 0) return;
+    const size_t at = out.size();
+    out.resize(at + (size_t)count);
+    uint8_t* dst = out.data() + at;
+    int64_t i = start, end = start + count;
+    if (i & 1) { *dst++ = (uint8_t)NT16[packed[i >> 1] & 15]; i++; }
+    for (; i + 1 < end; i += 2) { const uint16_t v = NT16_PAIRS.t[packed[i >> 1]]; memcpy(dst, &v, 2); dst += 2; }
+    if (i < end) *dst = (uint8_t)NT16[packed[i >> 1] >> 4];
+}
+
 // the reads of one span, appended in the packed layout (bases / quals padded to 16 bytes per read)
 struct ReadSink {
     PvIngestBatch* b;
-    void add(int64_t pos_start, int64_t pos_end, const std::string& seq, const std::vector<uint8_t>& q,
+    void add(int64_t pos_start, int64_t pos_end, const std::vector<uint8_t>& seq, const std::vector<uint8_t>& q,
              const std::vector<uint32_t>& ops, int flag, int mapq, int hp, const char* qname) {
         const bool reverse = (flag & 0x10) != 0;
         b->bam_flag.push_back((uint16_t)flag);
@@ -295,7 +312,9 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
         auto it = std::lower_bound(ref.bins.begin(), ref.bins.end(), bin,
                                    [](const std::pair<uint32_t, std::vector<Chunk>>& a, uint32_t v) { return a.first < v; });
         if (it == ref.bins.end() || it->first != bin) continue;
-        for (const Chunk& c : it->second) if (c.end > min_off) chunks.push_back(c);
+        // no record that overlaps the window of `start` begins before min_off (that is what the linear index stores), so a
+        // chunk of a coarse bin that straddles it is entered there instead of at its own beginning
+        for (const Chunk& c : it->second) if (c.end > min_off) chunks.push_back(Chunk{std::max(c.beg, min_off), c.end});
     }
     if (chunks.empty()) return PV_OK;
     std::sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.beg < b.beg; });
@@ -308,7 +327,7 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
     BgzfReader rd;
     rd.fd = f.fd; rd.file_size = f.file_size;
     std::vector<uint8_t> rec;
-    std::string seq; std::vector<uint8_t> quals; std::vector<uint32_t> ops, cg;
+    std::vector<uint8_t> seq, quals; std::vector<uint32_t> ops, cg, kept;
     for (const Chunk& ch : merged) {
         if (int rc = rd.seek(ch.beg)) return rc;
         while (rd.tell() < ch.end) {
@@ -357,11 +376,9 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                 if (mapq < o.min_mapq) continue;
 
                 // bam_handler.cpp:163-304: cut the read to [start, stop]
-                seq.clear(); quals.clear();
-                std::vector<uint32_t> kept;
+                seq.clear(); quals.clear(); kept.clear();
                 int64_t pos_start = -1, pos_end = -1, cur_pos = pos, cur_idx = 0;
                 bool bad = false;                            // CIGAR walks past SEQ (e.g. SEQ '*'): the reference reads out of bounds there
-                auto base_at = [&](int64_t i) -> char { const uint8_t byte = seq_p[i >> 1]; return NT16[(i & 1) ? (byte & 15) : (byte >> 4)]; };
                 for (int k = 0; k < n_cig; k++) {
                     const int op = cig[k] & 15;
                     const int64_t len = cig[k] >> 4;
@@ -375,7 +392,8 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                             if (take > 0) {
                                 if (pos_start == -1) { pos_start = cur_pos; pos_end = pos_start; }
                                 if (cur_idx + take > l_seq) { bad = true; break; }
-                                for (int64_t i = 0; i < take; i++) { seq.push_back(base_at(cur_idx + i)); quals.push_back(qual_p[cur_idx + i]); }
+                                decode_bases(seq_p, cur_idx, take, seq);
+                                quals.insert(quals.end(), qual_p + cur_idx, qual_p + cur_idx + take);
                                 cur_idx += take; cur_pos += take; pos_end += take; kept_len = take;
                             }
                             // the reference leaves the remaining bases of the op unconsumed (its loop breaks at the first
@@ -384,7 +402,8 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                         case 4: case 1:
                             if (cur_pos >= start && cur_pos <= stop && pos_start != -1) {
                                 if (cur_idx + len > l_seq) { bad = true; break; }
-                                for (int64_t i = 0; i < len; i++) { seq.push_back(base_at(cur_idx + i)); quals.push_back(qual_p[cur_idx + i]); }
+                                decode_bases(seq_p, cur_idx, len, seq);
+                                quals.insert(quals.end(), qual_p + cur_idx, qual_p + cur_idx + len);
                                 kept_len = len;
                             }
                             cur_idx += len;
