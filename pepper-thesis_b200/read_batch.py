@@ -197,6 +197,30 @@ class ReadBatch:
                 self.bases4 = None
         return self.pack_quals(threads, pinned).pack_cigar16(threads, pinned)
 
+    def pin_uploaded(self) -> "ReadBatch":
+        """Moves the big arrays the host path actually uploads (the packed wire forms are allocated pinned by
+        ``pack_wire(pinned=True)``; this covers the reference and whatever has no packed form) into page-locked memory,
+        so every upload is truly asynchronous -- without pinning the plain arrays that never travel."""
+        import torch
+        names = ["ref"]
+        if self.bases2 is None and self.bases4 is None:
+            names.append("bases")
+        if self.quals_packed is None:
+            names.append("quals")
+        if self.cigar16 is None:
+            names.append("cigar")
+        self._pinned_owners = getattr(self, "_pinned_owners", {})
+        for name in names:
+            a = getattr(self, name)
+            if a.size == 0:
+                continue
+            t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+            dst = t.numpy().view(a.dtype)
+            dst[:] = a
+            self._pinned_owners[name] = t
+            setattr(self, name, dst)
+        return self
+
     def _exceptions_view(self, b_lo: int, b_hi: int):
         if self.bases2 is None:
             return None
