@@ -4,14 +4,15 @@
 // Kernel chain (all on one stream, no host synchronisation):
 //   K0 cigar_prefix_kernel   warp per read: exclusive prefix of (reference advance, read advance) per CIGAR op,
 //                            with the REF_SKIP/PAD -> SOFT_CLIP fall-through of region_summary.cpp:556-561.
-//   K1 pileup_tile_kernel    CTA per tile of P reference positions of one region. Phase A walks every read that
-//                            overlaps the tile (warp per read, 32 ops per step, aligned bases flattened across
-//                            the lanes) and accumulates the per-position counters in SHARED memory with 32-bit
-//                            atomics on words that pack the forward strand in the low half and the reverse
-//                            strand in the high half. Phase B turns the counters into the clamped int16
-//                            image rows (flushed to HBM), evaluates the site thresholds in fp64 exactly like
-//                            :634-646 and registers candidate sites. Phase C re-walks only the CIGAR ops (no
-//                            bases) and records the insert/delete alleles of the registered sites.
+//   K1 pileup_tile_kernel    CTA per tile of P reference positions of one region, counters in SHARED memory (16 packed
+//                            words per position: forward strand in the low half, reverse in the high half). Phase A:
+//                            a warp per read that touches the tile walks its CIGAR ops, lane per op (run ends into
+//                            difference arrays, insert/delete anchors), then scans the aligned bases 16 per lane with
+//                            byte-parallel compares against the tile's reference -- a matching base costs no atomic,
+//                            only mismatches and low-quality bases do. Phase B: prefix sums turn the difference arrays
+//                            into counts, then the clamped int16 image rows (flushed to HBM), the site thresholds in
+//                            fp64 exactly like :634-646, and the candidate sites. Phase C re-walks only the CIGAR
+//                            ops (no bases) and records the insert/delete alleles of the registered sites.
 //   K2 site_allele_kernel    warp per site: exact de-duplication of the recorded alleles (byte-wise compares, no
 //                            hashing), per-allele filters of :682-712, one candidate record per survivor with a
 //                            64-bit order key (position, type, allele rank).
