@@ -29,6 +29,7 @@ struct GruEpilogue {
     static constexpr int kBiasBytes = 2 * 2 * 4 * 64 * 4;                  // whole layer: [dir][n_blk][gate][64] fp32
     static constexpr int kStateBytes = tc::EPI_THREADS * 2 * 64;
     static constexpr int kSmemBytes = kBiasBytes + 2 * kStateBytes;
+    static constexpr bool kInlinePrefetch = false;
 
     const float* bias;        // [dirs][n_blks][4][64]: b_ir+b_hr, b_iz+b_hz, b_hn, b_in
     float* h_state;           // [M][2][GH] fp32, read as h_{t-1}, overwritten with h_t
@@ -51,7 +52,8 @@ struct GruEpilogue {
             for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, hp + j * 4);
         }
     }
-    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te) const {
+    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te,
+                               const tc::NextTile&) const {
         const float* sb = (const float*)scratch + (size_t)((dir * n_blks + n_blk) * 4) * 64;
         const uint8_t* hst = scratch + kBiasBytes + buf * kStateBytes;
 #pragma unroll 1

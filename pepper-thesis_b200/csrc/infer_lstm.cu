@@ -33,10 +33,13 @@ constexpr int FLAT = T * C;         // 16896
 
 // ---- epilogues ---------------------------------------------------------------------------------------------
 struct LstmEpilogue {
-    static constexpr int kStages = 3;
-    static constexpr int kBiasBytes = 2 * 4 * 4 * 64 * 4;                  // whole layer: [dir][n_blk][gate][64] fp32
+    // The step kernels are bound by operand latency (TMA from L2 ~2000 cycles, one k block of MMA ~550): FOUR 48 KB
+    // stages in flight instead of three. That leaves 32 KB for the epilogue: ONE c-state buffer (every thread owns its
+    // slots, so it re-fills them for the next tile the moment it has read them) and biases read through L1.
+    static constexpr int kStages = 4;
     static constexpr int kStateBytes = tc::EPI_THREADS * 2 * 64;           // one tile: 256 threads x 2 chunks x 16 fp32
-    static constexpr int kSmemBytes = kBiasBytes + 2 * kStateBytes;        // biases + double-buffered c tile
+    static constexpr int kSmemBytes = kStateBytes;
+    static constexpr bool kInlinePrefetch = true;
 
     const float* bias;        // [dirs][n_blks][4 gates][64]  (b_ih + b_hh, tile order)
     float* c_state;           // cell state, fp32, private TILE layout [m_blk][dir][n_blk][half][chunk][j][row 0..127][4]:
@@ -47,27 +50,26 @@ struct LstmEpilogue {
     int first;                // c_{t-1} == 0
     int debug;                // PV_DEBUG_EPI: 1 = skip the cell math (timing experiments only)
 
-    __device__ void setup(uint8_t* scratch, int te) const {
-        float4* sb = (float4*)scratch;
-        const float4* gb = (const float4*)bias;
-        for (int i = te; i < kBiasBytes / 16; i += tc::EPI_THREADS) sb[i] = __ldg(gb + i);
-    }
+    __device__ void setup(uint8_t*, int) const {}
     // thread te keeps its 2 x 64 bytes of a tile at [(cc*4 + j) * 256 + te] 16-byte slots: conflict-free both ways
     __device__ __forceinline__ float* c_ptr(int dir, int n_blk, int row, int half, int cc, int j) const {
         const size_t tile = ((size_t)(row >> 7) * 2 + dir) * n_blks + n_blk;
         return c_state + ((((tile * 2 + half) * 2 + cc) * 4 + j) * 128 + (row & 127)) * 4;
     }
-    __device__ void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te) const {
-        if (first || !ok) return;
-        uint8_t* dst = scratch + kBiasBytes + buf * kStateBytes;
+    __device__ __forceinline__ void fetch_chunk(uint8_t* scratch, int dir, int n_blk, int row, int half, int cc, int te) const {
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, c_ptr(dir, n_blk, row, half, cc, j));
+        for (int j = 0; j < 4; j++) tc::cp_async16(scratch + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, c_ptr(dir, n_blk, row, half, cc, j));
     }
-    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te) const {
-        const float* sb = (const float*)scratch + (size_t)((dir * n_blks + n_blk) * 4) * 64;
-        const uint8_t* cst = scratch + kBiasBytes + buf * kStateBytes;
+    // the kernel's first tile (later tiles are requested from inside operator())
+    __device__ void prefetch(uint8_t* scratch, int, int dir, int n_blk, int row, bool ok, int half, int te) const {
+        if (first || !ok) return;
+        fetch_chunk(scratch, dir, n_blk, row, half, 0, te);
+        fetch_chunk(scratch, dir, n_blk, row, half, 1, te);
+    }
+    __device__ void operator()(uint8_t* scratch, int, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te,
+                               const tc::NextTile& nx) const {
+        const float* sb = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+        const uint8_t* cst = scratch;
 #pragma unroll 1
         for (int cc = 0; cc < 2; cc++) {
             const int ch = half * 2 + cc;                      // 16 hidden units per chunk
@@ -91,11 +93,15 @@ struct LstmEpilogue {
                     c[4 * j] = v.x; c[4 * j + 1] = v.y; c[4 * j + 2] = v.z; c[4 * j + 3] = v.w;
                 }
             }
+            // these slots are free again: request the same chunk of the NEXT tile's cell state
+            if (nx.valid && nx.ok && !first) fetch_chunk(scratch, nx.dir, nx.n_blk, nx.row, half, cc, te);
+            tc::cp_async_commit();
             tc::tmem_ld_wait();
             if (debug == 1) continue;
             if (ok) {
-                const float* bi = sb + 0 * 64 + ch * 16; const float* bf = sb + 1 * 64 + ch * 16;
-                const float* bg = sb + 2 * 64 + ch * 16; const float* bo = sb + 3 * 64 + ch * 16;
+                float bi[16], bf[16], bg[16], bo[16];              // biases through L1 (the whole warp reads the same 64 bytes)
+                ld16(sb + 0 * 64 + ch * 16, bi); ld16(sb + 1 * 64 + ch * 16, bf);
+                ld16(sb + 2 * 64 + ch * 16, bg); ld16(sb + 3 * 64 + ch * 16, bo);
                 // stage-wise over the 16 cells (not cell by cell): every stage is 16 independent instructions, so the MUFU
                 // and FMA pipes stay full instead of waiting on one cell's dependency chain
 #pragma unroll
@@ -137,6 +143,7 @@ struct LstmEpilogue {
 struct SeluEpilogue {
     static constexpr int kStages = 4;
     static constexpr int kSmemBytes = 0;
+    static constexpr bool kInlinePrefetch = false;
     __device__ void setup(uint8_t*, int) const {}
     __device__ void prefetch(uint8_t*, int, int, int, int, bool, int, int) const {}
 
@@ -144,7 +151,8 @@ struct SeluEpilogue {
     __nv_bfloat16* out;       // [M][ldo]
     int ldo;
 
-    __device__ void operator()(uint8_t*, int, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int) const {
+    __device__ void operator()(uint8_t*, int, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int,
+                               const tc::NextTile&) const {
         (void)dir;
         const float alpha = 1.6732632423543772f, lambda = 1.0507009873554805f;
 #pragma unroll 1

@@ -165,13 +165,18 @@ struct GemmShape {
 #define PV_TR(role, it, ev) do { } while (0)
 #endif
 
+// the tile an epilogue thread will see next (for epilogues that prefetch their per-row state themselves)
+struct NextTile { bool valid; int dir, n_blk, row; bool ok; };
+
 // Epilogue functor interface (called by the 256 epilogue threads, two per accumulator row, half = 0/1, te = 0..255):
 //   static constexpr int kStages, kSmemBytes            operand ring depth, bytes of epilogue scratch in shared memory
 //   void setup(uint8_t* scratch, int te)                once per kernel (e.g. biases -> shared memory)
 //   void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te)
 //                                                       cp.async the NEXT tile's per-row state into buffer `buf`
-//   void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te)
-//                                                       reads its half of the 256 accumulator columns (tmem_ld16)
+//   void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te,
+//                   const NextTile& nx)                 reads its half of the 256 accumulator columns (tmem_ld16)
+//   static constexpr bool kInlinePrefetch               true: one state buffer; the functor itself issues the next tile's
+//                                                       cp.async from inside operator() as soon as it has consumed its slots
 
 template <class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -295,21 +300,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int nxt = tile + n_clusters;
-            if (nxt < n_tiles) {                               // next tile's state: lands while this tile is computed
-                const int nrow = ((nxt >> (dir_sh + nb_sh)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
-                epi.prefetch(epi_scratch, acc ^ 1, nxt & dir_mask, (nxt >> dir_sh) & nb_mask, nrow, nrow < g.M, half, te);
+            NextTile nx;
+            nx.valid = nxt < n_tiles;
+            nx.dir = nxt & dir_mask; nx.n_blk = (nxt >> dir_sh) & nb_mask;
+            nx.row = ((nxt >> (dir_sh + nb_sh)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
+            nx.ok = nx.row < g.M;
+            if constexpr (!Epilogue::kInlinePrefetch) {
+                if (nx.valid)                                  // next tile's state: lands while this tile is computed
+                    epi.prefetch(epi_scratch, acc ^ 1, nx.dir, nx.n_blk, nx.row, nx.ok, half, te);
+                cp_async_commit();
             }
-            cp_async_commit();
             if (te == 0) PV_TR(2, it, 0);
             if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one poller per warp
             __syncwarp();
             if (te == 0) PV_TR(2, it, 1);
             tc_fence_after();
-            cp_async_wait<1>();                                // everything but the group just committed has landed
+            if constexpr (Epilogue::kInlinePrefetch) cp_async_wait<0>();   // this tile's state was requested a tile ago
+            else cp_async_wait<1>();                           // everything but the group just committed has landed
             if (te == 0) PV_TR(2, it, 2);
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epi(epi_scratch, acc, dir, n_blk, row, row < g.M, taddr, half, te);
+            epi(epi_scratch, acc, dir, n_blk, row, row < g.M, taddr, half, te, nx);
             if (te == 0) PV_TR(2, it, 3);
             tc_fence_before();
             __syncwarp();
