@@ -32,14 +32,18 @@ constexpr int LIN = 512;
 constexpr int FLAT = T * C;         // 16896
 
 // ---- epilogues ---------------------------------------------------------------------------------------------
-struct LstmEpilogue {
-    // The step kernels are bound by operand latency (TMA from L2 ~2000 cycles, one k block of MMA ~550): FOUR 48 KB
-    // stages in flight instead of three. That leaves 32 KB for the epilogue: ONE c-state buffer (every thread owns its
-    // slots, so it re-fills them for the next tile the moment it has read them) and biases read through L1.
-    static constexpr int kStages = 4;
+// DEEP = true  (decoder, 12 k blocks per tile: bound by operand latency -- TMA from L2 ~2000 cycles, one k block of MMA
+//               ~550): FOUR 48 KB stages in flight. That leaves 32 KB for the epilogue: ONE c-state buffer (every thread
+//               owns its slots, so it re-fills them for the next tile the moment it has read them), biases through L1.
+// DEEP = false (encoder, 6 k blocks per tile: bound by the epilogue): three stages, biases in shared memory, the c tile
+//               double-buffered and requested by the kernel one tile ahead.
+template <bool DEEP>
+struct LstmEpilogueT {
+    static constexpr int kStages = DEEP ? 4 : 3;
+    static constexpr int kBiasBytes = DEEP ? 0 : 2 * 4 * 4 * 64 * 4;      // whole layer: [dir][n_blk][gate][64] fp32
     static constexpr int kStateBytes = tc::EPI_THREADS * 2 * 64;           // one tile: 256 threads x 2 chunks x 16 fp32
-    static constexpr int kSmemBytes = kStateBytes;
-    static constexpr bool kInlinePrefetch = true;
+    static constexpr int kSmemBytes = kBiasBytes + (DEEP ? 1 : 2) * kStateBytes;
+    static constexpr bool kInlinePrefetch = DEEP;
 
     const float* bias;        // [dirs][n_blks][4 gates][64]  (b_ih + b_hh, tile order)
     float* c_state;           // cell state, fp32, private TILE layout [m_blk][dir][n_blk][half][chunk][j][row 0..127][4]:
@@ -50,7 +54,13 @@ struct LstmEpilogue {
     int first;                // c_{t-1} == 0
     int debug;                // PV_DEBUG_EPI: 1 = skip the cell math (timing experiments only)
 
-    __device__ void setup(uint8_t*, int) const {}
+    __device__ void setup(uint8_t* scratch, int te) const {
+        if constexpr (!DEEP) {
+            float4* sb = (float4*)scratch;
+            const float4* gb = (const float4*)bias;
+            for (int i = te; i < kBiasBytes / 16; i += tc::EPI_THREADS) sb[i] = __ldg(gb + i);
+        }
+    }
     // thread te keeps its 2 x 64 bytes of a tile at [(cc*4 + j) * 256 + te] 16-byte slots: conflict-free both ways
     __device__ __forceinline__ float* c_ptr(int dir, int n_blk, int row, int half, int cc, int j) const {
         const size_t tile = ((size_t)(row >> 7) * 2 + dir) * n_blks + n_blk;
@@ -60,16 +70,17 @@ struct LstmEpilogue {
 #pragma unroll
         for (int j = 0; j < 4; j++) tc::cp_async16(scratch + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, c_ptr(dir, n_blk, row, half, cc, j));
     }
-    // the kernel's first tile (later tiles are requested from inside operator())
-    __device__ void prefetch(uint8_t* scratch, int, int dir, int n_blk, int row, bool ok, int half, int te) const {
+    // DEEP: the kernel's first tile only (later tiles are requested from inside operator()); else: every next tile
+    __device__ void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te) const {
         if (first || !ok) return;
-        fetch_chunk(scratch, dir, n_blk, row, half, 0, te);
-        fetch_chunk(scratch, dir, n_blk, row, half, 1, te);
+        uint8_t* dst = scratch + kBiasBytes + (DEEP ? 0 : buf) * kStateBytes;
+        fetch_chunk(dst, dir, n_blk, row, half, 0, te);
+        fetch_chunk(dst, dir, n_blk, row, half, 1, te);
     }
-    __device__ void operator()(uint8_t* scratch, int, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te,
+    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te,
                                const tc::NextTile& nx) const {
-        const float* sb = bias + (size_t)((dir * n_blks + n_blk) * 4) * 64;
-        const uint8_t* cst = scratch;
+        const float* sb = (DEEP ? bias : (const float*)scratch) + (size_t)((dir * n_blks + n_blk) * 4) * 64;
+        uint8_t* cst = scratch + kBiasBytes + (DEEP ? 0 : buf) * kStateBytes;
 #pragma unroll 1
         for (int cc = 0; cc < 2; cc++) {
             const int ch = half * 2 + cc;                      // 16 hidden units per chunk
@@ -94,14 +105,24 @@ struct LstmEpilogue {
                 }
             }
             // these slots are free again: request the same chunk of the NEXT tile's cell state
-            if (nx.valid && nx.ok && !first) fetch_chunk(scratch, nx.dir, nx.n_blk, nx.row, half, cc, te);
-            tc::cp_async_commit();
+            if constexpr (DEEP) {
+                if (nx.valid && nx.ok && !first) fetch_chunk(cst, nx.dir, nx.n_blk, nx.row, half, cc, te);
+                tc::cp_async_commit();
+            }
             tc::tmem_ld_wait();
             if (debug == 1) continue;
             if (ok) {
-                float bi[16], bf[16], bg[16], bo[16];              // biases through L1 (the whole warp reads the same 64 bytes)
-                ld16(sb + 0 * 64 + ch * 16, bi); ld16(sb + 1 * 64 + ch * 16, bf);
-                ld16(sb + 2 * 64 + ch * 16, bg); ld16(sb + 3 * 64 + ch * 16, bo);
+                float bi[16], bf[16], bg[16], bo[16];              // the whole warp reads the same 64 bytes (L1 or smem broadcast)
+                if constexpr (DEEP) {
+                    ld16(sb + 0 * 64 + ch * 16, bi); ld16(sb + 1 * 64 + ch * 16, bf);
+                    ld16(sb + 2 * 64 + ch * 16, bg); ld16(sb + 3 * 64 + ch * 16, bo);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        bi[i] = sb[0 * 64 + ch * 16 + i]; bf[i] = sb[1 * 64 + ch * 16 + i];
+                        bg[i] = sb[2 * 64 + ch * 16 + i]; bo[i] = sb[3 * 64 + ch * 16 + i];
+                    }
+                }
                 // stage-wise over the 16 cells (not cell by cell): every stage is 16 independent instructions, so the MUFU
                 // and FMA pipes stay full instead of waiting on one cell's dependency chain
 #pragma unroll
@@ -387,7 +408,7 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
         { static long long* tr = nullptr; if (!tr) { cudaMalloc((void**)&tr, 3 * 16 * 8 * 8); } g.trace = tr; pv_trace_buffer = tr; }
 #endif
         for (int layer = 0; layer < 2; layer++) {
-            LstmEpilogue e;
+            LstmEpilogueT<true> e;
             e.bias = layer == 0 ? m->enc_b : m->dec_b;
             e.c_state = w.c_state;
             e.out = layer == 0 ? w.enc_out : w.dec_out;
@@ -410,8 +431,14 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
                     g.trace = (layer * T + s == target) ? pv_trace_buffer : nullptr;
                 }
 #endif
-                if (int rc = launch_gemm(layer == 0 ? map_enc : map_dec, layer == 0 ? map_x : map_enc,
-                                         layer == 0 ? m->map_enc_w : m->map_dec_w, g, e, m->sms, st)) return rc;
+                if (layer == 0) {
+                    LstmEpilogueT<false> e0;                   // same fields, encoder configuration
+                    e0.bias = e.bias; e0.c_state = e.c_state; e0.out = e.out; e0.n_blks = e.n_blks; e0.debug = e.debug;
+                    e0.first = e.first; e0.out_slot[0] = e.out_slot[0]; e0.out_slot[1] = e.out_slot[1];
+                    if (int rc = launch_gemm(map_enc, map_x, m->map_enc_w, g, e0, m->sms, st)) return rc;
+                } else {
+                    if (int rc = launch_gemm(map_dec, map_enc, m->map_dec_w, g, e, m->sms, st)) return rc;
+                }
             }
             pv::prof_end(layer == 0 ? pv::FAM_LSTM_ENC : pv::FAM_LSTM_DEC, st, T);
         }

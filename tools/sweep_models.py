@@ -1,0 +1,153 @@
+"""BASELINE.json config 5: TransducerGRU inference-only sweep, batch 256 .. 16384 (and 32768) windows.
+
+  M-B  polisher biGRU x2, hidden 128, [B,100,10] uint8 counts   (pepper/modules/python/models/simple_model.py:5-42)
+  M-A  variant biLSTM x2 + MLP, hidden 256, [B,33,26] int16      (pepper_variant/modules/python/models/simple_model.py:6-82)
+
+For every batch size: this repo's tcgen05 path (bf16 operands, fp32 accumulate/state) timed with CUDA events on
+device-resident inputs, next to the reference's own GPU path -- the same torch modules (nn.GRU / nn.LSTM / nn.Linear,
+cuDNN) in fp32 and under bf16 autocast -- plus the numerical distance of our output from the fp32 torch result.
+One JSON line per (model, batch). Weights: torch.manual_seed(0) default init. Inputs: U{0..30} counts.
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn as nn
+
+from pepper_thesis_b200 import models
+
+PEAK_TFLOPS = 1389.6
+try:
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
+        _p = json.load(f)
+    for k in ("bf16_tflops_sustained", "dense_bf16_tflops_sustained", "bf16_sustained_tflops"):
+        if k in _p:
+            PEAK_TFLOPS = float(_p[k])
+except Exception:
+    pass
+
+
+class TorchPolisher(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.gru_encoder = nn.GRU(10, 128, num_layers=1, bidirectional=True, batch_first=True)
+        self.gru_decoder = nn.GRU(256, 128, num_layers=1, bidirectional=True, batch_first=True)
+        self.dense1 = nn.Linear(256, 5)
+
+    def forward(self, x, hidden):
+        hidden = hidden.transpose(0, 1).contiguous()
+        x_out, hidden_out = self.gru_encoder(x, hidden)
+        x_out, hidden_final = self.gru_decoder(x_out, hidden_out)
+        return self.dense1(x_out), hidden_final.transpose(0, 1).contiguous()
+
+
+class TorchVariant(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.encoder = nn.LSTM(26, 256, num_layers=1, bidirectional=True, batch_first=True)
+        self.decoder = nn.LSTM(512, 256, num_layers=1, bidirectional=True, batch_first=True)
+        self.linear_1 = nn.Linear(16896, 512)
+        self.linear_2 = nn.Linear(512, 512)
+        self.linear_3 = nn.Linear(512, 512)
+        self.linear_4 = nn.Linear(512, 512)
+        self.linear_5 = nn.Linear(512, 512)
+        self.output_layer_type = nn.Linear(512, 3)
+        self.act = nn.SELU()
+
+    def forward(self, x):
+        x, _ = self.encoder(x)
+        x, _ = self.decoder(x)
+        x = torch.flatten(x, start_dim=1)
+        for l in (self.linear_1, self.linear_2, self.linear_3, self.linear_4, self.linear_5):
+            x = self.act(l(x))
+        return torch.softmax(self.output_layer_type(x), dim=1)
+
+
+def timed(fn, iters):
+    fn(); fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    batches = [256, 512, 1024, 2048, 4096, 8192, 16384, 32768]
+    if len(sys.argv) > 1:
+        batches = [int(v) for v in sys.argv[1:]]
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.benchmark = True
+
+    # ---- M-B ----
+    sd = models.random_polisher_state_dict(0)
+    ours = models.PolisherTransducerGRU().load_state_dict(sd)
+    ref = TorchPolisher()
+    ref.load_state_dict(sd)
+    ref = ref.to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    for B in batches:
+        x8 = torch.randint(0, 31, (B, 100, 10), generator=g, dtype=torch.uint8).to(dev)
+        xf = x8.float()
+        h0 = torch.zeros(B, 2, 128, device=dev)
+        iters = 20 if B <= 4096 else 8
+        with torch.no_grad():
+            t_our = timed(lambda: ours(x8, h0), iters)
+            t_f32 = timed(lambda: ref(xf, h0), iters)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                t_b16 = timed(lambda: ref(xf, h0), iters)
+                lb, _ = ref(xf, h0)
+            lo, ho = ours(x8, h0)
+            lr, hr = ref(xf, h0)
+        flop = 80.44e6 * B
+        print(json.dumps({
+            "model": "M-B polisher biGRU-128", "batch": B, "positions": 100,
+            "ours_ms": round(t_our, 4), "ours_windows_per_s": round(B / t_our * 1e3), "ours_tflops": round(flop / t_our / 1e9, 1),
+            "ours_frac_of_bf16_peak": round(flop / t_our / 1e9 / PEAK_TFLOPS, 4),
+            "torch_cudnn_fp32_ms": round(t_f32, 4), "torch_cudnn_bf16_autocast_ms": round(t_b16, 4),
+            "speedup_vs_torch_fp32": round(t_f32 / t_our, 2), "speedup_vs_torch_bf16": round(t_b16 / t_our, 2),
+            "max_abs_logit_err_vs_fp32": float((lo - lr).abs().max()), "max_abs_hidden_err_vs_fp32": float((ho - hr).abs().max()),
+            "argmax_agree_vs_fp32": float((lo.argmax(-1) == lr.argmax(-1)).float().mean()),
+            "torch_bf16_max_abs_logit_err_vs_fp32": float((lb.float() - lr).abs().max()),
+        }), flush=True)
+        del x8, xf, h0, lo, lr, lb
+
+    # ---- M-A ----
+    sd = models.random_variant_state_dict(0)
+    ours = models.TransducerGRU().load_state_dict(sd)
+    ref = TorchVariant()
+    ref.load_state_dict(sd)
+    ref = ref.to(dev).eval()
+    for B in batches:
+        xi = (-torch.randint(0, 31, (B, 33, 26), generator=g)).to(torch.int16).to(dev)
+        xf = xi.float()
+        iters = 20 if B <= 4096 else 8
+        with torch.no_grad():
+            t_our = timed(lambda: ours.infer_windows(xi, wrap_int8=False), iters)
+            t_f32 = timed(lambda: ref(xf), iters)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                t_b16 = timed(lambda: ref(xf), iters)
+                pb = ref(xf)
+            po, ao = ours.infer_windows(xi, wrap_int8=False)
+            pr = ref(xf)
+        flop = 161.33e6 * B
+        print(json.dumps({
+            "model": "M-A variant biLSTM-256 + MLP", "batch": B, "positions": 33,
+            "ours_ms": round(t_our, 4), "ours_windows_per_s": round(B / t_our * 1e3), "ours_tflops": round(flop / t_our / 1e9, 1),
+            "ours_frac_of_bf16_peak": round(flop / t_our / 1e9 / PEAK_TFLOPS, 4),
+            "torch_cudnn_fp32_ms": round(t_f32, 4), "torch_cudnn_bf16_autocast_ms": round(t_b16, 4),
+            "speedup_vs_torch_fp32": round(t_f32 / t_our, 2), "speedup_vs_torch_bf16": round(t_b16 / t_our, 2),
+            "max_abs_prob_err_vs_fp32": float((po - pr).abs().max()),
+            "argmax_agree_vs_fp32": float((ao.long() == pr.argmax(-1)).float().mean()),
+            "torch_bf16_max_abs_prob_err_vs_fp32": float((pb.float() - pr).abs().max()),
+        }), flush=True)
+        del xi, xf, po, pr, pb
+
+
+if __name__ == "__main__":
+    main()
