@@ -142,7 +142,7 @@ def load() -> C.CDLL:
 
 FAMILIES = ["sum_cigar_prefix", "sum_pileup_tile", "sum_site_alleles", "sum_key_sort", "sum_emit_windows",
             "lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head", "gru_steps", "gru_misc",
-            "candidate_filter", "polish_summary"]
+            "candidate_filter", "polish_summary", "gru_gx_gemm", "gru_head"]
 
 
 def profile_collect():

@@ -85,7 +85,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
         PV_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    const int groups = ((g.m_blks + tc::CLUSTER - 1) / tc::CLUSTER) * g.n_blks * g.dirs;
+    const int groups = ((g.m_blks + tc::CLUSTER - 1) / tc::CLUSTER) * g.n_blks * (tc::slot_tiles<Epi>::value ? g.slots : g.dirs);
     int clusters = sms / tc::CLUSTER;
     if (clusters > groups) clusters = groups;
     cudaLaunchConfig_t cfg;

@@ -3,15 +3,23 @@
 // biGRU(256->128, h0 = encoder h_n) -> Linear(256->5), and the sliding-window loop around it
 // (/root/reference/pepper/modules/python/models/predict_distributed_gpu.py:63-96).
 //
-// Same machinery as model M-A (tc_gemm.cuh): one tcgen05/TMA launch per time step advances both directions,
-// A = [h_{t-1} | x_t]. PyTorch's GRU keeps the hidden part of the candidate gate separate
-// (n = tanh(W_in x + b_in + r * (W_hn h + b_hn))), so a 256-column tile holds FOUR accumulators for 64 hidden units:
-// r, z (h and x parts summed by the K-concatenation), n_h (x columns of W zeroed) and n_x (h columns zeroed).
-// The hidden state used by the element-wise update stays fp32 ([n][2][128], the caller's `hidden` buffer itself);
-// only the MMA operand copy of h is bf16.
+// Two kernels per layer (the recurrence of a GRU is serial in time, its input projection is not):
+//   gx GEMM       tc::gemm_kernel<GxEpilogue> (tcgen05/TMA, slot tiles): gx[t] = x_t * W_ih^T + b for ALL time steps and
+//                 both directions at once, written as fp16 in the tile order the recurrence streams it back in.
+//   recurrence    gru_recur_kernel: one CTA per (128 windows, direction) that stays resident for all T steps. W_hh
+//                 (384 x 128 bf16, 96 KB) is TMA-loaded into shared memory ONCE; h_{t-1} lives on chip -- as the bf16
+//                 A operand in shared memory (written by the epilogue in the canonical 128-byte-swizzle layout) and as
+//                 fp32 state in 128 TMEM columns (tcgen05.st/ld); per step one elected thread issues
+//                 tcgen05.mma 128x192x16 into the r/z/n_h accumulators (two column halves, so the epilogue of the
+//                 first half overlaps the MMAs of the second), 16 epilogue warps apply the gates and the only
+//                 HBM traffic is the gx stream (bulk-copied two half-steps ahead through an mbarrier ring) and the bf16
+//                 h_t output. No launch per step, no grid-wide dependency, h never round-trips through L2.
+// PyTorch keeps the hidden part of the candidate gate separate (n = tanh(W_in x + b_in + r * (W_hn h + b_hn))): b_hn
+// stays in the recurrence, every other bias is folded into gx.
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "infer_common.cuh"
+#include <cuda_fp16.h>
 #include <vector>
 
 namespace {
@@ -20,139 +28,394 @@ constexpr int GF = 10;              // input features
 constexpr int GH = 128;             // hidden size
 constexpr int GC = 2 * GH;          // channels of a layer output
 constexpr int GXK = 64;             // encoder input padded to one k block
-constexpr int GENC_K = GH + GXK;    // 192
-constexpr int GDEC_K = GH + GC;     // 384
 constexpr int GCLS = 5;
+constexpr int GN3 = 3 * GH;         // r, z, n rows of one direction
+constexpr int GRU_MAX_CHUNK = 16384;   // windows per pass (gx: 96 KB per 128 windows, step and direction)
 
-struct GruEpilogue {
-    static constexpr int kStages = 3;
-    static constexpr int kBiasBytes = 2 * 2 * 4 * 64 * 4;                  // whole layer: [dir][n_blk][gate][64] fp32
-    static constexpr int kStateBytes = tc::EPI_THREADS * 2 * 64;
-    static constexpr int kSmemBytes = kBiasBytes + 2 * kStateBytes;
+// ---- gx layout ---------------------------------------------------------------------------------------------
+// [m_blk][dir][t][half][gate r,z,n][quarter 0..3][sub 0..1][row 0..127][8 fp16]: hidden unit j = half*64 + quarter*16 +
+// sub*8 + e. One (m_blk, dir, t, half) is a contiguous 48 KB blob = one ring slot of the recurrence; inside it the 16
+// bytes of a (row, sub) sit 16 bytes apart from the neighbouring rows', so a warp's reads and writes are contiguous.
+constexpr int GX_HALF_BYTES = 3 * 4 * 2 * 128 * 16;      // 49152
+__host__ __device__ inline size_t gx_unit_index(int m_blk, int dir, int T, int t, int half, int gate, int quarter, int sub, int r) {
+    return ((((((((size_t)m_blk * 2 + dir) * T + t) * 2 + half) * 3 + gate) * 4 + quarter) * 2 + sub) * 128 + r);   // 16-byte units
+}
+
+// epilogue of the input-projection GEMM: 768 columns = [dir][gate][128]; `slot` (passed as dir) is the time step
+struct GxEpilogue {
+    static constexpr int kStages = 4;
+    static constexpr int kSmemBytes = 0;
     static constexpr bool kInlinePrefetch = false;
+    static constexpr bool kSlotTiles = true;
+    __device__ void setup(uint8_t*, int) const {}
+    __device__ void prefetch(uint8_t*, int, int, int, int, bool, int, int) const {}
 
-    const float* bias;        // [dirs][n_blks][4][64]: b_ir+b_hr, b_iz+b_hz, b_hn, b_in
-    float* h_state;           // [M][2][GH] fp32, read as h_{t-1}, overwritten with h_t
-    __nv_bfloat16* out;       // [M][S][GC]
-    int n_blks, S;
-    int out_slot[2];
+    const float* bias;        // [768]: b_ir+b_hr, b_iz+b_hz, b_in per direction
+    uint4* gx;
+    int T;
+    int rows_alloc;           // rows the gx buffer holds (a multiple of 128)
 
-    __device__ void setup(uint8_t* scratch, int te) const {
-        float4* sb = (float4*)scratch;
-        const float4* gb = (const float4*)bias;
-        for (int i = te; i < kBiasBytes / 16; i += tc::EPI_THREADS) sb[i] = __ldg(gb + i);
-    }
-    __device__ void prefetch(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, int half, int te) const {
-        if (!ok) return;
-        uint8_t* dst = scratch + kBiasBytes + buf * kStateBytes;
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const float* hp = h_state + ((size_t)row * 2 + dir) * GH + n_blk * 64 + (half * 2 + cc) * 16;
-#pragma unroll
-            for (int j = 0; j < 4; j++) tc::cp_async16(dst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16, hp + j * 4);
-        }
-    }
-    __device__ void operator()(uint8_t* scratch, int buf, int dir, int n_blk, int row, bool ok, uint32_t taddr, int half, int te,
+    __device__ void operator()(uint8_t*, int, int t, int n_blk, int row, bool, uint32_t taddr, int half, int,
                                const tc::NextTile&) const {
-        const float* sb = (const float*)scratch + (size_t)((dir * n_blks + n_blk) * 4) * 64;
-        const uint8_t* hst = scratch + kBiasBytes + buf * kStateBytes;
+        const bool in = row < rows_alloc;
+        const int m_blk = row >> 7, r = row & 127;
 #pragma unroll 1
-        for (int cc = 0; cc < 2; cc++) {
-            const int ch = half * 2 + cc;
-            float ar[16], az[16], ah[16], ax[16], h[16];
-            tc::tmem_ld16(taddr + 0 * 64 + ch * 16, ar);
-            tc::tmem_ld16(taddr + 1 * 64 + ch * 16, az);
-            tc::tmem_ld16(taddr + 2 * 64 + ch * 16, ah);
-            tc::tmem_ld16(taddr + 3 * 64 + ch * 16, ax);
-            if (ok) {
+        for (int c = 0; c < 8; c += 2) {                       // two 16-column chunks in flight
+            float a[2][16], b[2][16];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float4 v = *(const float4*)(hst + ((cc * 4 + j) * tc::EPI_THREADS + te) * 16);
-                    h[4 * j] = v.x; h[4 * j + 1] = v.y; h[4 * j + 2] = v.z; h[4 * j + 3] = v.w;
-                }
+            for (int u = 0; u < 2; u++) {
+                tc::tmem_ld16(taddr + (half * 8 + c + u) * 16, a[u]);
+                ld16(bias + (n_blk * 16 + half * 8 + c + u) * 16, b[u]);
             }
             tc::tmem_ld_wait();
-            if (ok) {
-                const float* br = sb + 0 * 64 + ch * 16; const float* bz = sb + 1 * 64 + ch * 16;
-                const float* bh = sb + 2 * 64 + ch * 16; const float* bx = sb + 3 * 64 + ch * 16;
-                uint32_t hp[8];
+            if (in) {
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) {
+                for (int u = 0; u < 2; u++) {
+                    const int col16 = n_blk * 16 + half * 8 + c + u;   // 0..47
+                    const int dir = col16 / 24, rem = col16 - dir * 24;
+                    const int gate = rem >> 3, c8 = rem & 7;
+                    uint32_t hp[8];
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const float r = sigmoid_f(ar[i + e] + br[i + e]);
-                        const float z = sigmoid_f(az[i + e] + bz[i + e]);
-                        const float n = tanh_f(ax[i + e] + bx[i + e] + r * (ah[i + e] + bh[i + e]));
-                        h[i + e] = (1.f - z) * n + z * h[i + e];
+                    for (int i = 0; i < 16; i += 2) {
+                        const __half2 h2 = __floats2half2_rn(a[u][i] + b[u][i], a[u][i + 1] + b[u][i + 1]);
+                        hp[i >> 1] = *(const uint32_t*)&h2;
                     }
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(h[i], h[i + 1]);
-                    hp[i >> 1] = *(const uint32_t*)&h2;
+                    const size_t x = gx_unit_index(m_blk, dir, T, t, c8 >> 2, gate, c8 & 3, 0, r);
+                    gx[x] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                    gx[x + 128] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                 }
-                float* hg = h_state + ((size_t)row * 2 + dir) * GH + n_blk * 64 + ch * 16;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) *(float4*)(hg + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
-                __nv_bfloat16* op = out + ((size_t)row * S + (dir ? out_slot[1] : out_slot[0])) * GC + dir * GH + n_blk * 64 + ch * 16;
-                *(uint4*)op = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                *(uint4*)(op + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
             }
         }
     }
 };
 
-// images uint8 [n][row_stride/10 ...]: x[r][t][f] = img[r*row_stride + (t0+t)*10 + f] -> bf16 [n][T][64]
+// ---- recurrence ----------------------------------------------------------------------------------------------
+constexpr int RC_EPI_WARPS = 16;
+constexpr int RC_THREADS = 128 + RC_EPI_WARPS * 32;            // 4 control warps + 16 epilogue warps
+constexpr int RC_W_BYTES = GN3 * GH * 2;                       // 98304: two k blocks of [384 rows][128 B]
+constexpr int RC_A_BYTES = 128 * GH * 2;                       // 32768: two k blocks of [128 rows][128 B]
+constexpr int RC_SMEM = RC_W_BYTES + RC_A_BYTES + 2 * GX_HALF_BYTES + GH * 4 + 128 + 1024;
+
+struct RecurParams {
+    const uint8_t* gx;        // gx layout above
+    const float* b_hn;        // [2][128]
+    float* h_state;           // [M][2][128] fp32: h_0 in, h_T out
+    __nv_bfloat16* out;       // [M][S][256]: h_t -> slot t + 1, channels dir*128 ..
+    int M, T, S;
+    long long* trace;         // optional (-DPV_TRACE): CTA 0 records [step < 16][event] SM-clock stamps
+};
+
+#ifdef PV_TRACE
+#define GRU_TR(step, ev) do { if (p.trace && blockIdx.x == 0 && (step) < 16) p.trace[(step) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define GRU_TR(step, ev) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(RC_THREADS, 1)
+gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, box 64 x 128 rows */,
+                 const __grid_constant__ CUtensorMap tmOut /* [rows][S][256] bf16, box 64 x 1 x 128 rows */, const RecurParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_w = smem;
+    uint8_t* smem_a = smem + RC_W_BYTES;
+    uint8_t* smem_gx = smem_a + RC_A_BYTES;
+    float* s_bhn = (float*)(smem_gx + 2 * GX_HALF_BYTES);
+    uint64_t* bars = (uint64_t*)(s_bhn + GH);
+    uint64_t* w_bar = bars;            // W_hh landed
+    uint64_t* h_ready = bars + 1;      // h_{t-1} operand written, accumulators drained (16 warp arrivals)
+    uint64_t* acc_full = bars + 2;     // [2] accumulators of a column half complete
+    uint64_t* gx_full = bars + 4;      // [2]
+    uint64_t* gx_empty = bars + 6;     // [2] (16 warp arrivals)
+    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = (int)blockIdx.x >> 1, dir = (int)blockIdx.x & 1;
+    const int T = p.T;
+
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmW); tc::tma_prefetch_desc(&tmOut); }
+    if (warp == 1 && lane == 0) {
+        tc::mbar_init(w_bar, 1);
+        tc::mbar_init(h_ready, RC_EPI_WARPS);
+        for (int i = 0; i < 2; i++) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&gx_full[i], 1); tc::mbar_init(&gx_empty[i], RC_EPI_WARPS); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, tc::TMEM_COLS);
+    if (warp == 3) for (int i = lane; i < GH; i += 32) s_bhn[i] = p.b_hn[dir * GH + i];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== loads: W_hh once, then the gx ring =====
+        if (lane == 0) {
+            tc::mbar_expect_tx(w_bar, RC_W_BYTES);
+            for (int kb = 0; kb < 2; kb++)
+                for (int rb = 0; rb < 3; rb++)
+                    tc::tma_load_2d(smem_w + kb * (GN3 * 128) + rb * (128 * 128), &tmW, w_bar, kb * 64, dir * GN3 + rb * 128);
+            for (int s = 0; s < T; s++) {
+                const int t = dir ? T - 1 - s : s;
+                for (int hf = 0; hf < 2; hf++) {
+                    tc::mbar_wait(&gx_empty[hf], (uint32_t)(s & 1) ^ 1u);
+                    tc::mbar_expect_tx(&gx_full[hf], GX_HALF_BYTES);
+                    const uint8_t* src = p.gx + gx_unit_index(m_blk, dir, T, t, hf, 0, 0, 0, 0) * 16;
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        tc::bulk_load(smem_gx + hf * GX_HALF_BYTES + c * (GX_HALF_BYTES / 3), src + c * (GX_HALF_BYTES / 3),
+                                      GX_HALF_BYTES / 3, &gx_full[hf]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc(128, 192);
+            uint64_t adesc[2], bdesc[2][2];
+#pragma unroll
+            for (int kb = 0; kb < 2; kb++) {
+                adesc[kb] = tc::make_smem_desc(tc::smem_u32(smem_a + kb * (128 * 128)));
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+                    bdesc[hf][kb] = tc::make_smem_desc(tc::smem_u32(smem_w + kb * (GN3 * 128) + hf * (192 * 128)));
+            }
+            tc::mbar_wait(w_bar, 0);
+            for (int s = 0; s <= T; s++) {
+                GRU_TR(s, 0);
+                tc::mbar_wait(h_ready, (uint32_t)s & 1u);
+                GRU_TR(s, 1);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    if (s < T) {
+#pragma unroll
+                        for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                tc::umma_bf16(tmem_base + (uint32_t)(hf * 192), adesc[kb] + (uint64_t)(k * 2), bdesc[hf][kb] + (uint64_t)(k * 2),
+                                              idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (hf == 0) {
+                        if (s < T) tc::umma_commit(&acc_full[0]);
+                        GRU_TR(s, 2);
+                        if (s > 0) {
+                            // the operand tile IS h of the step just finished (bf16, 128-byte swizzle): store it as the
+                            // layer output with two TMA tile stores instead of 32-byte stores from every epilogue thread
+                            const int tp = dir ? T - s : s - 1;
+                            tc::tma_store_3d(&tmOut, smem_a, dir * GH, tp + 1, m_blk * 128);
+                            tc::tma_store_3d(&tmOut, smem_a + 128 * 128, dir * GH + 64, tp + 1, m_blk * 128);
+                            tc::bulk_commit();
+                        }
+                    } else if (s < T) {
+                        // the epilogue overwrites the operand tile once it has seen acc_full[1]: the tile store must have read it
+                        tc::bulk_wait_read0();
+                        tc::umma_commit(&acc_full[1]);
+                        GRU_TR(s, 3);
+                    }
+                }
+            }
+            tc::bulk_wait0();
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = (row, 16 hidden units of each column half) =====
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int gq = (warp - 4) >> 2;                        // 16-unit group inside a half
+        const int r = q * 32 + lane;
+        const int row = m_blk * 128 + r;
+        const bool ok = row < p.M;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        // operand copy of this thread's units in the swizzled A tile: k block = half, 16-byte chunks 2*gq and 2*gq + 1
+        const uint32_t a_row = tc::smem_u32(smem_a) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t sw0 = (uint32_t)(((2 * gq) ^ (r & 7)) << 4), sw1 = (uint32_t)(((2 * gq + 1) ^ (r & 7)) << 4);
+        const uint32_t gx_thr = tc::smem_u32(smem_gx) + (uint32_t)((gq * 256 + r) * 16);   // + half, gate * 16384, sub * 2048
+        const uint32_t bhn_thr = tc::smem_u32(s_bhn) + (uint32_t)(gq * 64);                // + half * 256
+
+        // h_0: fp32 state -> TMEM columns 384.., bf16 -> A tile
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            float h[16];
+            if (ok) ld16(p.h_state + ((size_t)row * 2 + dir) * GH + hf * 64 + gq * 16, h);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) h[i] = 0.f;
+            }
+            tc::tmem_st16(tlane + 384 + hf * 64 + gq * 16, h);
+            uint32_t hp[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) { const __nv_bfloat162 h2 = __floats2bfloat162_rn(h[i], h[i + 1]); hp[i >> 1] = *(const uint32_t*)&h2; }
+            tc::sts128(a_row + hf * (128 * 128) + sw0, make_uint4(hp[0], hp[1], hp[2], hp[3]));
+            tc::sts128(a_row + hf * (128 * 128) + sw1, make_uint4(hp[4], hp[5], hp[6], hp[7]));
+        }
+        tc::tmem_st_wait();
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(h_ready);
+
+        for (int s = 0; s < T; s++) {
+            const uint32_t ph = (uint32_t)s & 1u;
+            uint32_t keep[8];                                  // first half's bf16 h_t until the second half's MMAs have read h_{t-1}
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                if (lane == 0) {
+                    tc::mbar_wait(&acc_full[hf], ph);
+                    if (warp == 4) GRU_TR(s, 4 + hf * 4);
+                    tc::mbar_wait(&gx_full[hf], ph);
+                    if (warp == 4) GRU_TR(s, 5 + hf * 4);
+                }
+                __syncwarp();
+                tc::tc_fence_after();
+                // two register-light stages: (r, n_h) -> candidate n, then (z, h_{t-1}) -> h_t
+                float ar[16], an[16];
+                tc::tmem_ld16(tlane + hf * 192 + 0 * 64 + gq * 16, ar);
+                tc::tmem_ld16(tlane + hf * 192 + 2 * 64 + gq * 16, an);
+                const uint32_t gxa = gx_thr + hf * GX_HALF_BYTES;
+                uint4 g4[4];
+                g4[0] = tc::lds128(gxa); g4[1] = tc::lds128(gxa + 2048);
+                g4[2] = tc::lds128(gxa + 2 * 16384); g4[3] = tc::lds128(gxa + 2 * 16384 + 2048);
+                float bh[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 v = tc::lds128(bhn_thr + hf * 256 + i * 16);
+                    bh[4 * i] = __uint_as_float(v.x); bh[4 * i + 1] = __uint_as_float(v.y);
+                    bh[4 * i + 2] = __uint_as_float(v.z); bh[4 * i + 3] = __uint_as_float(v.w);
+                }
+                tc::tmem_ld_wait();
+                if (warp == 4 && lane == 0) GRU_TR(s, 6 + hf * 4);
+                {
+                    const __half2* gr = (const __half2*)&g4[0]; const __half2* gn = (const __half2*)&g4[2];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float2 xr = __half22float2(gr[i >> 1]), xn = __half22float2(gn[i >> 1]);
+                        const float r0 = sigmoid_f(ar[i] + xr.x), r1 = sigmoid_f(ar[i + 1] + xr.y);
+                        an[i] = tanh_f(fmaf(r0, an[i] + bh[i], xn.x));
+                        an[i + 1] = tanh_f(fmaf(r1, an[i + 1] + bh[i + 1], xn.y));
+                    }
+                }
+                float az[16], h[16];
+                tc::tmem_ld16(tlane + hf * 192 + 1 * 64 + gq * 16, az);
+                tc::tmem_ld16(tlane + 384 + hf * 64 + gq * 16, h);
+                g4[0] = tc::lds128(gxa + 16384); g4[1] = tc::lds128(gxa + 16384 + 2048);
+                tc::tmem_ld_wait();
+                uint32_t hp[8];
+                {
+                    const __half2* gz = (const __half2*)&g4[0];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float2 xz = __half22float2(gz[i >> 1]);
+                        const float z0 = sigmoid_f(az[i] + xz.x), z1 = sigmoid_f(az[i + 1] + xz.y);
+                        h[i] = fmaf(z0, h[i] - an[i], an[i]);          // (1 - z) n + z h
+                        h[i + 1] = fmaf(z1, h[i + 1] - an[i + 1], an[i + 1]);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(h[i], h[i + 1]);
+                        hp[i >> 1] = *(const uint32_t*)&h2;
+                    }
+                }
+                __syncwarp();
+                if (warp == 4 && lane == 0) GRU_TR(s, 7 + hf * 4);
+                if (lane == 0) tc::mbar_arrive(&gx_empty[hf]);   // the slot may be refilled with the next step's half
+                tc::tmem_st16(tlane + 384 + hf * 64 + gq * 16, h);
+                if (ok && s == T - 1) {                         // h_T (fp32) back to the caller's hidden buffer
+                    float* hg = p.h_state + ((size_t)row * 2 + dir) * GH + hf * 64 + gq * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *(float4*)(hg + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+                }
+                if (hf == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) keep[i] = hp[i];
+                } else {
+                    // acc_full[1] has been observed: every MMA of this step has consumed the old operand tile (and the
+                    // tile store of h_{t-1} has read it). The layer output h_t leaves the SM from this tile (TMA store).
+                    tc::sts128(a_row + sw0, make_uint4(keep[0], keep[1], keep[2], keep[3]));
+                    tc::sts128(a_row + sw1, make_uint4(keep[4], keep[5], keep[6], keep[7]));
+                    tc::sts128(a_row + 128 * 128 + sw0, make_uint4(hp[0], hp[1], hp[2], hp[3]));
+                    tc::sts128(a_row + 128 * 128 + sw1, make_uint4(hp[4], hp[5], hp[6], hp[7]));
+                }
+            }
+            tc::tmem_st_wait();
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(h_ready);
+            if (warp == 4 && lane == 0) GRU_TR(s, 12);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, tc::TMEM_COLS); }
+}
+
+// images uint8 [n][row_stride/10 ...]: x[r][t][f] = img[r*row_stride + (t0+t)*10 + f] -> bf16 [n][T][64]; one thread per
+// (window, t): columns 0..9 meet the bf16 high part of W_ih, columns 10..19 (the same counts again) its bf16 remainder
 __global__ void gru_prep_kernel(const uint8_t* __restrict__ img, int64_t row_stride, int t0, __nv_bfloat16* __restrict__ x,
                                 int64_t n, int T) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * T * GXK) return;
-    const int col = (int)(i % GXK);
-    const int64_t rt = i / GXK;
-    const int64_t r = rt / T; const int t = (int)(rt % T);
-    // columns 0..9 meet the bf16 high part of W_ih, columns 10..19 (the same counts again) its bf16 remainder
-    x[i] = __float2bfloat16_rn(col < 2 * GF ? (float)img[r * row_stride + (int64_t)(t0 + t) * GF + (col % GF)] : 0.f);
+    if (i >= n * T) return;
+    const int64_t r = i / T; const int t = (int)(i - r * T);
+    const uint8_t* src = img + r * row_stride + (int64_t)(t0 + t) * GF;
+    uint32_t w[12];                                            // 24 bf16: [c0..c9 c0..c9 0 0 0 0]
+    uint16_t v[24];
+#pragma unroll
+    for (int f = 0; f < GF; f++) {
+        const __nv_bfloat16 b = __float2bfloat16_rn((float)src[f]);
+        v[f] = v[GF + f] = *(const uint16_t*)&b;
+    }
+#pragma unroll
+    for (int f = 2 * GF; f < 24; f++) v[f] = 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) w[k] = (uint32_t)v[2 * k] | ((uint32_t)v[2 * k + 1] << 16);
+    uint4* dst = (uint4*)(x + i * GXK);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+#pragma unroll
+    for (int k = 3; k < 8; k++) dst[k] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// bf16 operand copies of the initial hidden state: forward h0 -> slot 0, reverse h0 -> slot T+1
-__global__ void gru_init_slots_kernel(const float* __restrict__ h_state, __nv_bfloat16* __restrict__ out, int64_t n, int S) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over n*2*GH
-    if (i >= n * 2 * GH) return;
-    const int j = (int)(i % GH); const int dir = (int)((i / GH) % 2); const int64_t r = i / (2 * GH);
-    out[((size_t)r * S + (dir ? S - 1 : 0)) * GC + dir * GH + j] = __float2bfloat16_rn(h_state[i]);
-}
-
-// dense1 (256 -> 5) per position; one warp per (window, t). mode 0: write logits; mode 1: add softmax into acc
+// dense1 (256 -> 5) per position. A warp walks (window, t) rows; lane l owns channels 8l .. 8l+7 (one 16-byte load per
+// row) and keeps its 40 weights in registers. mode 0: write logits; mode 1: add softmax into acc
 __global__ void gru_head_kernel(const __nv_bfloat16* __restrict__ dec_out, int S, const float* __restrict__ w,
                                 const float* __restrict__ b, float* __restrict__ dst, int64_t dst_row_stride, int t0,
                                 int64_t n, int T, int mode) {
     const int lane = threadIdx.x & 31;
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= n * T) return;
-    const int64_t r = wid / T; const int t = (int)(wid % T);
-    const __nv_bfloat16* x = dec_out + ((size_t)r * S + t + 1) * GC;
-    float s[GCLS] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = lane; k < GC; k += 32) {
-        const float v = __bfloat162float(x[k]);
-#pragma unroll
-        for (int c = 0; c < GCLS; c++) s[c] += v * w[c * GC + k];
-    }
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float wr[GCLS][8];
 #pragma unroll
     for (int c = 0; c < GCLS; c++)
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], d);
-    if (lane == 0) {
+        for (int k = 0; k < 8; k++) wr[c][k] = w[c * GC + lane * 8 + k];
+    const float bias = lane < GCLS ? b[lane] : 0.f;
+    for (int64_t wid = warp; wid < n * T; wid += n_warps) {
+        const int64_t r = wid / T; const int t = (int)(wid - r * T);
+        const uint4 xv = __ldg((const uint4*)(dec_out + ((size_t)r * S + t + 1) * GC) + lane);
+        const __nv_bfloat162* x2 = (const __nv_bfloat162*)&xv;
+        float s[GCLS] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 v = __bfloat1622float2(x2[k]);
+#pragma unroll
+            for (int c = 0; c < GCLS; c++) s[c] = fmaf(v.y, wr[c][2 * k + 1], fmaf(v.x, wr[c][2 * k], s[c]));
+        }
+#pragma unroll
+        for (int c = 0; c < GCLS; c++)
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], d);
+        // lane c keeps class c
+        float mine = s[0];
+#pragma unroll
+        for (int c = 1; c < GCLS; c++) mine = lane == c ? s[c] : mine;
+        mine += bias;
         float* o = dst + r * dst_row_stride + (int64_t)(t0 + t) * GCLS;
-        float m = -1e30f;
-#pragma unroll
-        for (int c = 0; c < GCLS; c++) { s[c] += b[c]; m = fmaxf(m, s[c]); }
         if (mode == 0) {
-#pragma unroll
-            for (int c = 0; c < GCLS; c++) o[c] = s[c];
+            if (lane < GCLS) o[lane] = mine;
         } else {
-            float e[GCLS], sum = 0.f;
+            float m = -1e30f;
 #pragma unroll
-            for (int c = 0; c < GCLS; c++) { e[c] = expf(s[c] - m); sum += e[c]; }
-            const float inv = 1.f / sum;
+            for (int c = 0; c < GCLS; c++) m = fmaxf(m, __shfl_sync(0xffffffffu, mine, c));
+            const float e = lane < GCLS ? expf(mine - m) : 0.f;
+            float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < GCLS; c++) o[c] += e[c] * inv;          // windows are processed one after another
+            for (int c = 0; c < GCLS; c++) sum += __shfl_sync(0xffffffffu, e, c);
+            if (lane < GCLS) o[lane] += e / sum;                // windows are processed one after another
         }
     }
 }
@@ -166,9 +429,16 @@ __global__ void gru_argmax_kernel(const float* __restrict__ acc, uint8_t* __rest
     labels[i] = (uint8_t)best;
 }
 
+int64_t gru_head_blocks(int64_t rows, int sms) {
+    const int64_t want = (rows + 7) / 8;                       // 8 warps per block
+    const int64_t cap = (int64_t)sms * 8;
+    return want < cap ? want : cap;
+}
+
 struct GruWs {
     __nv_bfloat16 *xin, *enc_out, *dec_out;
     float* h_state;
+    uint8_t* gx;
     int64_t bytes;
 };
 
@@ -180,6 +450,7 @@ GruWs gru_carve(void* base, int64_t size, int64_t chunk, int T) {
     w.enc_out = a.take<__nv_bfloat16>(chunk * S * GC);
     w.dec_out = a.take<__nv_bfloat16>(chunk * S * GC);
     w.h_state = a.take<float>(chunk * 2 * GH);
+    w.gx = a.take<uint8_t>((chunk / 128) * 2 * (int64_t)T * 2 * GX_HALF_BYTES);
     w.bytes = pv::align_up(a.cur, 256);
     return w;
 }
@@ -187,40 +458,54 @@ GruWs gru_carve(void* base, int64_t size, int64_t chunk, int T) {
 int64_t gru_chunk_for(int64_t n) {
     int64_t c = (n + 127) / 128 * 128;
     if (c < 128) c = 128;
-    return c < MAX_CHUNK ? c : MAX_CHUNK;
+    return c < GRU_MAX_CHUNK ? c : GRU_MAX_CHUNK;
 }
 
-// rows in tile order (dir, n_blk, gate{r,z,nh,nx}, j) <- PyTorch rows r: j, z: GH + j, n: 2*GH + j
-// hi_lo: the input weights are stored as bf16 high part + bf16 remainder in two column groups (the raw 0..254 counts
-// are exact in bf16, so x * W_ih keeps ~16 mantissa bits instead of 8)
-void pack_gru(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2], const float* const b_hh[2],
-              int in_dim, int k_total, bool hi_lo, std::vector<uint16_t>& w, std::vector<float>& b) {
-    w.assign((size_t)2 * 4 * GH * k_total, 0);
-    b.assign((size_t)2 * 4 * GH, 0.f);
+// Input projection: rows [dir][gate r,z,n][128] = PyTorch's weight_ih rows, columns = k_total (zero padded).
+// hi_lo: the weights are stored as bf16 high part + bf16 remainder in two column groups (the raw 0..254 counts are
+// exact in bf16 and appear twice in the operand, so x * W_ih keeps ~16 mantissa bits instead of 8).
+// Bias folded into gx: b_ir + b_hr, b_iz + b_hz, b_in.
+void pack_gru_ih(const float* const w_ih[2], const float* const b_ih[2], const float* const b_hh[2], int in_dim, int k_total,
+                 bool hi_lo, std::vector<uint16_t>& w, std::vector<float>& b) {
+    w.assign((size_t)2 * GN3 * k_total, 0);
+    b.assign((size_t)2 * GN3, 0.f);
     for (int dir = 0; dir < 2; dir++)
-        for (int nb = 0; nb < 2; nb++)
-            for (int gate = 0; gate < 4; gate++)
+        for (int row = 0; row < GN3; row++) {
+            uint16_t* wr = &w[((size_t)dir * GN3 + row) * k_total];
+            for (int k = 0; k < in_dim; k++) {
+                const float v = w_ih[dir][(size_t)row * in_dim + k];
+                wr[k] = f2bf(v);
+                if (hi_lo) wr[in_dim + k] = f2bf(v - bf2f(wr[k]));
+            }
+            b[(size_t)dir * GN3 + row] = b_ih[dir][row] + (row < 2 * GH ? b_hh[dir][row] : 0.f);
+        }
+}
+
+// Recurrent weights in accumulator-column order: [dir][half][gate r,z,n][64] <- weight_hh row gate*128 + half*64 + j
+void pack_gru_hh(const float* const w_hh[2], const float* const b_hh[2], std::vector<uint16_t>& w, std::vector<float>& bhn) {
+    w.assign((size_t)2 * GN3 * GH, 0);
+    bhn.assign((size_t)2 * GH, 0.f);
+    for (int dir = 0; dir < 2; dir++) {
+        for (int half = 0; half < 2; half++)
+            for (int gate = 0; gate < 3; gate++)
                 for (int j = 0; j < 64; j++) {
-                    const int hj = nb * 64 + j;
-                    const int src = (gate < 2 ? gate : 2) * GH + hj;
-                    const size_t dst = ((size_t)(dir * 2 + nb) * 4 + gate) * 64 + j;
-                    uint16_t* wr = &w[dst * k_total];
-                    if (gate != 3) for (int k = 0; k < GH; k++) wr[k] = f2bf(w_hh[dir][(size_t)src * GH + k]);
-                    if (gate != 2) for (int k = 0; k < in_dim; k++) {
-                        const float v = w_ih[dir][(size_t)src * in_dim + k];
-                        wr[GH + k] = f2bf(v);
-                        if (hi_lo) wr[GH + in_dim + k] = f2bf(v - bf2f(wr[GH + k]));
-                    }
-                    b[dst] = gate < 2 ? b_ih[dir][src] + b_hh[dir][src] : (gate == 2 ? b_hh[dir][src] : b_ih[dir][src]);
+                    const int src = gate * GH + half * 64 + j;
+                    uint16_t* wr = &w[((size_t)dir * GN3 + (half * 3 + gate) * 64 + j) * GH];
+                    for (int k = 0; k < GH; k++) wr[k] = f2bf(w_hh[dir][(size_t)src * GH + k]);
                 }
+        for (int j = 0; j < GH; j++) bhn[(size_t)dir * GH + j] = b_hh[dir][2 * GH + j];
+    }
 }
 
 }  // namespace
 
+long long* pv_gru_trace_buffer = nullptr;
+extern "C" long long* pv_gru_trace_ptr(void) { return pv_gru_trace_buffer; }
+
 struct PvGruModel {
-    __nv_bfloat16 *enc_w, *dec_w;
-    float *enc_b, *dec_b, *dense_w, *dense_b;
-    CUtensorMap map_enc_w, map_dec_w;
+    __nv_bfloat16 *enc_wih, *dec_wih, *enc_whh, *dec_whh;
+    float *enc_b, *dec_b, *enc_bhn, *dec_bhn, *dense_w, *dense_b;
+    CUtensorMap map_enc_wih, map_dec_wih, map_enc_whh, map_dec_whh;
     int sms;
 };
 
@@ -231,23 +516,33 @@ extern "C" int pv_gru_create(const PvGruWeights* hw, PvGruModel** out) {
     memset(m, 0, sizeof(*m));
     m->sms = pv::sm_count();
     std::vector<uint16_t> w; std::vector<float> b;
-    pack_gru(hw->enc_w_ih, hw->enc_w_hh, hw->enc_b_ih, hw->enc_b_hh, GF, GENC_K, true, w, b);
-    if (int rc = upload(&m->enc_w, w.data(), w.size() * 2)) return rc;
+    pack_gru_ih(hw->enc_w_ih, hw->enc_b_ih, hw->enc_b_hh, GF, GXK, true, w, b);
+    if (int rc = upload(&m->enc_wih, w.data(), w.size() * 2)) return rc;
     if (int rc = upload(&m->enc_b, b.data(), b.size() * 4)) return rc;
-    pack_gru(hw->dec_w_ih, hw->dec_w_hh, hw->dec_b_ih, hw->dec_b_hh, GC, GDEC_K, false, w, b);
-    if (int rc = upload(&m->dec_w, w.data(), w.size() * 2)) return rc;
+    pack_gru_ih(hw->dec_w_ih, hw->dec_b_ih, hw->dec_b_hh, GC, GC, false, w, b);
+    if (int rc = upload(&m->dec_wih, w.data(), w.size() * 2)) return rc;
     if (int rc = upload(&m->dec_b, b.data(), b.size() * 4)) return rc;
+    pack_gru_hh(hw->enc_w_hh, hw->enc_b_hh, w, b);
+    if (int rc = upload(&m->enc_whh, w.data(), w.size() * 2)) return rc;
+    if (int rc = upload(&m->enc_bhn, b.data(), b.size() * 4)) return rc;
+    pack_gru_hh(hw->dec_w_hh, hw->dec_b_hh, w, b);
+    if (int rc = upload(&m->dec_whh, w.data(), w.size() * 2)) return rc;
+    if (int rc = upload(&m->dec_bhn, b.data(), b.size() * 4)) return rc;
     if (int rc = upload(&m->dense_w, hw->dense_w, GCLS * GC * 4)) return rc;
     if (int rc = upload(&m->dense_b, hw->dense_b, GCLS * 4)) return rc;
-    if (int rc = make_map2(&m->map_enc_w, m->enc_w, 2 * 4 * GH, GENC_K)) return rc;
-    if (int rc = make_map2(&m->map_dec_w, m->dec_w, 2 * 4 * GH, GDEC_K)) return rc;
+    if (int rc = make_map2(&m->map_enc_wih, m->enc_wih, 2 * GN3, GXK)) return rc;
+    if (int rc = make_map2(&m->map_dec_wih, m->dec_wih, 2 * GN3, GC)) return rc;
+    if (int rc = make_map2(&m->map_enc_whh, m->enc_whh, 2 * GN3, GH)) return rc;
+    if (int rc = make_map2(&m->map_dec_whh, m->dec_whh, 2 * GN3, GH)) return rc;
+    PV_CUDA_CHECK(cudaFuncSetAttribute(gru_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RC_SMEM));
     *out = m;
     return PV_OK;
 }
 
 extern "C" void pv_gru_destroy(PvGruModel* m) {
     if (!m) return;
-    cudaFree(m->enc_w); cudaFree(m->dec_w); cudaFree(m->enc_b); cudaFree(m->dec_b); cudaFree(m->dense_w); cudaFree(m->dense_b);
+    cudaFree(m->enc_wih); cudaFree(m->dec_wih); cudaFree(m->enc_whh); cudaFree(m->dec_whh);
+    cudaFree(m->enc_b); cudaFree(m->dec_b); cudaFree(m->enc_bhn); cudaFree(m->dec_bhn); cudaFree(m->dense_w); cudaFree(m->dense_b);
     delete m;
 }
 
@@ -259,39 +554,39 @@ namespace {
 
 // one TransducerGRU.forward over rows [0, nb) of a chunk; h_state [nb][2][GH] in/out
 int gru_forward_chunk(PvGruModel* m, const GruWs& w, const CUtensorMap& map_x, const CUtensorMap& map_enc,
-                      const CUtensorMap& map_dec, const uint8_t* images, int64_t img_row_stride, int t0, int64_t nb, int T,
+                      const CUtensorMap& map_dec, const uint8_t* images, int64_t img_row_stride, int t0, int64_t nb, int64_t chunk, int T,
                       float* h_state, cudaStream_t st) {
     const int S = T + 2;
-    const int64_t elems = nb * T * GXK;
+    const int64_t elems = nb * T;
     pv::prof_begin(pv::FAM_GRU_MISC, st);
     gru_prep_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(images, img_row_stride, t0, w.xin, nb, T);
     PV_CUDA_CHECK(cudaGetLastError());
     pv::prof_end(pv::FAM_GRU_MISC, st, 1);
-    tc::GemmShape g;
-    memset(&g, 0, sizeof(g));
-    g.M = (int)nb; g.m_blks = (int)((nb + 127) / 128); g.n_blks = 2; g.dirs = 2;
-    g.w_row[0] = 0; g.w_row[1] = 4 * GH;
-    g.a0_col[0] = 0; g.a0_col[1] = GH;
-    g.kb0 = GH / tc::BLOCK_K; g.w_kb_off = 0;
+    const int m_blks = (int)((nb + 127) / 128);
     for (int layer = 0; layer < 2; layer++) {
-        __nv_bfloat16* out = layer == 0 ? w.enc_out : w.dec_out;
-        gru_init_slots_kernel<<<(unsigned)((nb * 2 * GH + 255) / 256), 256, 0, st>>>(h_state, out, nb, S);
-        PV_CUDA_CHECK(cudaGetLastError());
-        GruEpilogue e;
-        e.bias = layer == 0 ? m->enc_b : m->dec_b; e.h_state = h_state; e.out = out; e.n_blks = 2; e.S = S;
-        g.kb1 = layer == 0 ? 1 : GC / tc::BLOCK_K;
+        // gx for every time step and both directions: [nb x T, K_in] x [K_in, 768]
+        tc::GemmShape g;
+        memset(&g, 0, sizeof(g));
+        g.M = (int)nb; g.m_blks = m_blks; g.n_blks = 2 * GN3 / tc::BLOCK_N; g.dirs = 1; g.slots = T;
+        g.kb0 = 0; g.kb1 = layer == 0 ? GXK / tc::BLOCK_K : GC / tc::BLOCK_K;
+        g.a1_slot[0] = layer == 0 ? 0 : 1;                     // x_t sits in slot t of xin, slot t + 1 of enc_out
+        GxEpilogue ge;
+        ge.bias = layer == 0 ? m->enc_b : m->dec_b; ge.gx = (uint4*)w.gx; ge.T = T; ge.rows_alloc = (int)chunk;
+        pv::prof_begin(pv::FAM_GRU_GX, st);
+        if (int rc = launch_gemm(map_x, layer == 0 ? map_x : map_enc, layer == 0 ? m->map_enc_wih : m->map_dec_wih, g, ge,
+                                 m->sms, st)) return rc;
+        pv::prof_end(pv::FAM_GRU_GX, st, 1);
+        RecurParams rp;
+        rp.gx = w.gx; rp.b_hn = layer == 0 ? m->enc_bhn : m->dec_bhn; rp.h_state = h_state;
+        rp.out = layer == 0 ? w.enc_out : w.dec_out; rp.M = (int)nb; rp.T = T; rp.S = S; rp.trace = nullptr;
+#ifdef PV_TRACE
+        { static long long* tr = nullptr; if (!tr) { cudaMalloc((void**)&tr, 16 * 16 * 8); cudaMemset(tr, 0, 16 * 16 * 8); } rp.trace = tr; pv_gru_trace_buffer = tr; }
+#endif
         pv::prof_begin(pv::FAM_GRU_STEP, st);
-        for (int s = 0; s < T; s++) {
-            const int tf = s, tb = T - 1 - s;
-            e.out_slot[0] = tf + 1; e.out_slot[1] = tb + 1;
-            g.a0_slot[0] = tf; g.a0_slot[1] = tb + 2;
-            if (layer == 0) { g.a1_slot[0] = tf; g.a1_slot[1] = tb; }
-            else { g.a1_slot[0] = tf + 1; g.a1_slot[1] = tb + 1; }
-            g.a1_col[0] = g.a1_col[1] = 0;
-            if (int rc = launch_gemm(layer == 0 ? map_enc : map_dec, layer == 0 ? map_x : map_enc,
-                                     layer == 0 ? m->map_enc_w : m->map_dec_w, g, e, m->sms, st)) return rc;
-        }
-        pv::prof_end(pv::FAM_GRU_STEP, st, T + 1);
+        gru_recur_kernel<<<(unsigned)(m_blks * 2), RC_THREADS, RC_SMEM, st>>>(layer == 0 ? m->map_enc_whh : m->map_dec_whh,
+                                                                                 layer == 0 ? map_enc : map_dec, rp);
+        PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_GRU_STEP, st, 1);
     }
     return PV_OK;
 }
@@ -314,11 +609,13 @@ extern "C" int pv_gru_forward(PvGruModel* m, const uint8_t* images, int64_t n, i
     if (int rc = make_map3(&map_dec, w.dec_out, chunk, S, GC, (int64_t)S * GC)) return rc;
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t nb = n - off < chunk ? n - off : chunk;
-        if (int rc = gru_forward_chunk(m, w, map_x, map_enc, map_dec, images + off * T * GF, (int64_t)T * GF, 0, nb, T,
+        if (int rc = gru_forward_chunk(m, w, map_x, map_enc, map_dec, images + off * T * GF, (int64_t)T * GF, 0, nb, chunk, T,
                                        hidden + off * 2 * GH, st)) return rc;
-        gru_head_kernel<<<(unsigned)((nb * T * 32 + 255) / 256), 256, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
+        pv::prof_begin(pv::FAM_GRU_HEAD, st);
+        gru_head_kernel<<<(unsigned)gru_head_blocks(nb * T, m->sms), 256, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
                                                                                 logits + off * T * GCLS, (int64_t)T * GCLS, 0, nb, T, 0);
         PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_GRU_HEAD, st, 1);
     }
     return PV_OK;
 }
@@ -343,11 +640,13 @@ extern "C" int pv_gru_predict_chunks(PvGruModel* m, const uint8_t* images, int64
         const int64_t nb = n - off < chunk ? n - off : chunk;
         PV_CUDA_CHECK(cudaMemsetAsync(w.h_state, 0, (size_t)nb * 2 * GH * 4, st));          // hidden = zeros (:63)
         for (int t0 = 0; t0 + window <= L; t0 += stride) {                                   // :70-73
-            if (int rc = gru_forward_chunk(m, w, map_x, map_enc, map_dec, images + off * L * GF, (int64_t)L * GF, t0, nb, T,
+            if (int rc = gru_forward_chunk(m, w, map_x, map_enc, map_dec, images + off * L * GF, (int64_t)L * GF, t0, nb, chunk, T,
                                            w.h_state, st)) return rc;
-            gru_head_kernel<<<(unsigned)((nb * T * 32 + 255) / 256), 256, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
+            pv::prof_begin(pv::FAM_GRU_HEAD, st);
+            gru_head_kernel<<<(unsigned)gru_head_blocks(nb * T, m->sms), 256, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
                                                                                     prob_sum + off * L * GCLS, (int64_t)L * GCLS, t0, nb, T, 1);
             PV_CUDA_CHECK(cudaGetLastError());
+            pv::prof_end(pv::FAM_GRU_HEAD, st, 1);
         }
     }
     const int64_t n_pos = n * L;

@@ -123,6 +123,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the reverse: thread i of the warp writes 16 consecutive fp32 columns of row (lane_base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// shared memory -> global tile store through a tensor map (bulk group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// explicit shared-space 16-byte accesses (a computed generic pointer makes nvcc emit generic LD/ST)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// contiguous bytes global -> shared (bulk asynchronous copy, completes on an mbarrier); size a multiple of 16
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // 16-byte asynchronous global -> shared copy (LDGSTS) and its group fences; used to prefetch per-tile epilogue state
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -156,6 +188,8 @@ struct GemmShape {
     int a1_slot[2];
     int w_row[2];     // first W row per direction
     int w_kb_off;     // first W k block (non-zero when the h block is skipped because h == 0)
+    int slots;        // slot-tile epilogues only (Epilogue::kSlotTiles): a tile is (row group, slot, column tile) with
+                      // dirs == 1; A1 is read at slot a1_slot[0] + slot, and the epilogue receives the slot as `dir`
     long long* trace; // optional (debug builds with -DPV_TRACE): CTA 0 records [role][tile][event] SM-clock stamps here
 };
 
@@ -177,6 +211,30 @@ struct NextTile { bool valid; int dir, n_blk, row; bool ok; };
 //                   const NextTile& nx)                 reads its half of the 256 accumulator columns (tmem_ld16)
 //   static constexpr bool kInlinePrefetch               true: one state buffer; the functor itself issues the next tile's
 //                                                       cp.async from inside operator() as soon as it has consumed its slots
+
+template <class E, class = void> struct slot_tiles { static constexpr bool value = false; };
+template <class E> struct slot_tiles<E, decltype((void)E::kSlotTiles)> { static constexpr bool value = E::kSlotTiles; };
+
+struct TileIdx { int dir, n_blk, m_grp, slot; };
+// step tiles: dirs and n_blks are powers of two (1/2 and 2/4): tile -> (dir, n_blk, m group) with shifts, no integer
+// division. Slot tiles (few, large tiles): n_blk fastest, then the slot, then the row group.
+template <bool SLOT>
+__device__ __forceinline__ TileIdx decode_tile(int tile, const GemmShape& g, int dir_sh, int nb_sh, int dir_mask, int nb_mask) {
+    TileIdx t;
+    if constexpr (SLOT) {
+        t.dir = 0;
+        t.n_blk = tile % g.n_blks;
+        const int r = tile / g.n_blks;
+        t.slot = r % g.slots;
+        t.m_grp = r / g.slots;
+    } else {
+        t.dir = tile & dir_mask;
+        t.n_blk = (tile >> dir_sh) & nb_mask;
+        t.m_grp = tile >> (dir_sh + nb_sh);
+        t.slot = 0;
+    }
+    return t;
+}
 
 template <class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -201,8 +259,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const int crank = (int)cluster_ctarank();
     const int cluster_id = (int)blockIdx.x / CLUSTER, n_clusters = (int)gridDim.x / CLUSTER;
     const int m_grps = (g.m_blks + CLUSTER - 1) / CLUSTER;
-    const int n_tiles = m_grps * g.n_blks * g.dirs;             // groups
-    // dirs and n_blks are powers of two (1/2 and 2/4): tile -> (dir, n_blk, m group) with shifts, no integer division
+    constexpr bool SLOT = slot_tiles<Epilogue>::value;
+    const int n_tiles = m_grps * g.n_blks * (SLOT ? g.slots : g.dirs);   // groups
     const int dir_sh = g.dirs >> 1, nb_sh = 31 - __clz(g.n_blks), dir_mask = g.dirs - 1, nb_mask = g.n_blks - 1;
     const int kbt = g.kb0 + g.kb1;
     constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
@@ -228,9 +286,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0; int itp = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, itp++) {
-                const int dir = tile & dir_mask;
-                const int n_blk = (tile >> dir_sh) & nb_mask;
-                const int m_blk = (tile >> (dir_sh + nb_sh)) * CLUSTER + crank;
+                const TileIdx ti = decode_tile<SLOT>(tile, g, dir_sh, nb_sh, dir_mask, nb_mask);
+                const int dir = ti.dir, n_blk = ti.n_blk;
+                const int m_blk = ti.m_grp * CLUSTER + crank;
                 PV_TR(0, itp, 0);
                 for (int kb = 0; kb < kbt; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -240,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                                     (dir ? g.a0_col[1] : g.a0_col[0]) + kb * BLOCK_K, (dir ? g.a0_slot[1] : g.a0_slot[0]), m_blk * BLOCK_M);
                     else
                         tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA1, &full_bar[stage],
-                                    (dir ? g.a1_col[1] : g.a1_col[0]) + (kb - g.kb0) * BLOCK_K, (dir ? g.a1_slot[1] : g.a1_slot[0]), m_blk * BLOCK_M);
+                                    (dir ? g.a1_col[1] : g.a1_col[0]) + (kb - g.kb0) * BLOCK_K, (dir ? g.a1_slot[1] : g.a1_slot[0]) + ti.slot, m_blk * BLOCK_M);
                     // W columns: A0's k blocks first, then A1's (the host packs [W_hh | W_ih] that way)
                     // this CTA's slice of the W tile, multicast to every CTA of the cluster
                     tma_load_2d_mc(smem_w + stage * W_STAGE_BYTES + crank * W_SLICE_ROWS * BLOCK_K * 2, &tmW, &full_bar[stage],
@@ -288,22 +346,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         epi_barrier();
         int it = 0;
         if (cluster_id < n_tiles) {                            // state of the first tile
-            const int tile = cluster_id;
-            const int row = ((tile >> (dir_sh + nb_sh)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
-            epi.prefetch(epi_scratch, 0, tile & dir_mask, (tile >> dir_sh) & nb_mask, row, row < g.M, half, te);
+            const TileIdx t0 = decode_tile<SLOT>(cluster_id, g, dir_sh, nb_sh, dir_mask, nb_mask);
+            const int row = (t0.m_grp * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
+            epi.prefetch(epi_scratch, 0, SLOT ? t0.slot : t0.dir, t0.n_blk, row, row < g.M, half, te);
         }
         cp_async_commit();
         for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
-            const int dir = tile & dir_mask;
-            const int n_blk = (tile >> dir_sh) & nb_mask;
-            const int m_blk = (tile >> (dir_sh + nb_sh)) * CLUSTER + crank;
+            const TileIdx ti = decode_tile<SLOT>(tile, g, dir_sh, nb_sh, dir_mask, nb_mask);
+            const int dir = SLOT ? ti.slot : ti.dir, n_blk = ti.n_blk;
+            const int m_blk = ti.m_grp * CLUSTER + crank;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int nxt = tile + n_clusters;
             NextTile nx;
             nx.valid = nxt < n_tiles;
-            nx.dir = nxt & dir_mask; nx.n_blk = (nxt >> dir_sh) & nb_mask;
-            nx.row = ((nxt >> (dir_sh + nb_sh)) * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
+            const TileIdx tn = decode_tile<SLOT>(nxt, g, dir_sh, nb_sh, dir_mask, nb_mask);
+            nx.dir = SLOT ? tn.slot : tn.dir; nx.n_blk = tn.n_blk;
+            nx.row = (tn.m_grp * CLUSTER + crank) * BLOCK_M + q * 32 + lane;
             nx.ok = nx.row < g.M;
             if constexpr (!Epilogue::kInlinePrefetch) {
                 if (nx.valid)                                  // next tile's state: lands while this tile is computed
