@@ -370,52 +370,52 @@ __global__ void gru_prep_kernel(const uint8_t* __restrict__ img, int64_t row_str
     for (int k = 3; k < 8; k++) dst[k] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// dense1 (256 -> 5) per position. A warp walks (window, t) rows; lane l owns channels 8l .. 8l+7 (one 16-byte load per
-// row) and keeps its 40 weights in registers. mode 0: write logits; mode 1: add softmax into acc
-__global__ void gru_head_kernel(const __nv_bfloat16* __restrict__ dec_out, int S, const float* __restrict__ w,
+// dense1 (256 -> 5) per position: one THREAD per (window, t) row -- no cross-lane reduction; the 5 x 256 weights sit in
+// shared memory (every lane reads the same address: broadcast), the row streams through 16-byte loads, 8 in flight.
+// mode 0: write logits; mode 1: add softmax into acc
+__global__ void __launch_bounds__(128) gru_head_kernel(const __nv_bfloat16* __restrict__ dec_out, int S, const float* __restrict__ w,
                                 const float* __restrict__ b, float* __restrict__ dst, int64_t dst_row_stride, int t0,
                                 int64_t n, int T, int mode) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float wr[GCLS][8];
-#pragma unroll
-    for (int c = 0; c < GCLS; c++)
-#pragma unroll
-        for (int k = 0; k < 8; k++) wr[c][k] = w[c * GC + lane * 8 + k];
-    const float bias = lane < GCLS ? b[lane] : 0.f;
-    for (int64_t wid = warp; wid < n * T; wid += n_warps) {
+    __shared__ float4 w4[GC];                                  // classes 0..3 of channel k
+    __shared__ float w1[GC];                                   // class 4
+    for (int k = threadIdx.x; k < GC; k += blockDim.x) {
+        w4[k] = make_float4(w[0 * GC + k], w[1 * GC + k], w[2 * GC + k], w[3 * GC + k]);
+        w1[k] = w[4 * GC + k];
+    }
+    __syncthreads();
+    const int64_t rows = n * T;
+    for (int64_t wid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wid < rows; wid += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = wid / T; const int t = (int)(wid - r * T);
-        const uint4 xv = __ldg((const uint4*)(dec_out + ((size_t)r * S + t + 1) * GC) + lane);
-        const __nv_bfloat162* x2 = (const __nv_bfloat162*)&xv;
-        float s[GCLS] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint4* x = (const uint4*)(dec_out + ((size_t)r * S + t + 1) * GC);
+        float s0 = b[0], s1 = b[1], s2 = b[2], s3 = b[3], s4 = b[4];
+#pragma unroll 1
+        for (int k0 = 0; k0 < GC / 8; k0 += 8) {               // 8 loads of 8 channels in flight
+            uint4 xv[8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float2 v = __bfloat1622float2(x2[k]);
+            for (int u = 0; u < 8; u++) xv[u] = __ldg(x + k0 + u);
 #pragma unroll
-            for (int c = 0; c < GCLS; c++) s[c] = fmaf(v.y, wr[c][2 * k + 1], fmaf(v.x, wr[c][2 * k], s[c]));
+            for (int u = 0; u < 8; u++) {
+                const __nv_bfloat162* x2 = (const __nv_bfloat162*)&xv[u];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 v = __bfloat1622float2(x2[j]);
+                    const int k = (k0 + u) * 8 + 2 * j;
+                    const float4 a = w4[k], c = w4[k + 1];
+                    s0 = fmaf(v.x, a.x, s0); s1 = fmaf(v.x, a.y, s1); s2 = fmaf(v.x, a.z, s2); s3 = fmaf(v.x, a.w, s3);
+                    s4 = fmaf(v.x, w1[k], s4);
+                    s0 = fmaf(v.y, c.x, s0); s1 = fmaf(v.y, c.y, s1); s2 = fmaf(v.y, c.z, s2); s3 = fmaf(v.y, c.w, s3);
+                    s4 = fmaf(v.y, w1[k + 1], s4);
+                }
+            }
         }
-#pragma unroll
-        for (int c = 0; c < GCLS; c++)
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], d);
-        // lane c keeps class c
-        float mine = s[0];
-#pragma unroll
-        for (int c = 1; c < GCLS; c++) mine = lane == c ? s[c] : mine;
-        mine += bias;
         float* o = dst + r * dst_row_stride + (int64_t)(t0 + t) * GCLS;
         if (mode == 0) {
-            if (lane < GCLS) o[lane] = mine;
+            o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4;
         } else {
-            float m = -1e30f;
-#pragma unroll
-            for (int c = 0; c < GCLS; c++) m = fmaxf(m, __shfl_sync(0xffffffffu, mine, c));
-            const float e = lane < GCLS ? expf(mine - m) : 0.f;
-            float sum = 0.f;
-#pragma unroll
-            for (int c = 0; c < GCLS; c++) sum += __shfl_sync(0xffffffffu, e, c);
-            if (lane < GCLS) o[lane] += e / sum;                // windows are processed one after another
+            const float m = fmaxf(fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)), s4);
+            const float e0 = expf(s0 - m), e1 = expf(s1 - m), e2 = expf(s2 - m), e3 = expf(s3 - m), e4 = expf(s4 - m);
+            const float inv = 1.f / (e0 + e1 + e2 + e3 + e4);
+            o[0] += e0 * inv; o[1] += e1 * inv; o[2] += e2 * inv; o[3] += e3 * inv; o[4] += e4 * inv;   // windows one after another
         }
     }
 }
@@ -430,8 +430,8 @@ __global__ void gru_argmax_kernel(const float* __restrict__ acc, uint8_t* __rest
 }
 
 int64_t gru_head_blocks(int64_t rows, int sms) {
-    const int64_t want = (rows + 7) / 8;                       // 8 warps per block
-    const int64_t cap = (int64_t)sms * 8;
+    const int64_t want = (rows + 127) / 128;                   // one thread per row
+    const int64_t cap = (int64_t)sms * 16;
     return want < cap ? want : cap;
 }
 
@@ -612,7 +612,7 @@ extern "C" int pv_gru_forward(PvGruModel* m, const uint8_t* images, int64_t n, i
         if (int rc = gru_forward_chunk(m, w, map_x, map_enc, map_dec, images + off * T * GF, (int64_t)T * GF, 0, nb, chunk, T,
                                        hidden + off * 2 * GH, st)) return rc;
         pv::prof_begin(pv::FAM_GRU_HEAD, st);
-        gru_head_kernel<<<(unsigned)gru_head_blocks(nb * T, m->sms), 256, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
+        gru_head_kernel<<<(unsigned)gru_head_blocks(nb * T, m->sms), 128, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
                                                                                 logits + off * T * GCLS, (int64_t)T * GCLS, 0, nb, T, 0);
         PV_CUDA_CHECK(cudaGetLastError());
         pv::prof_end(pv::FAM_GRU_HEAD, st, 1);
@@ -643,7 +643,7 @@ extern "C" int pv_gru_predict_chunks(PvGruModel* m, const uint8_t* images, int64
             if (int rc = gru_forward_chunk(m, w, map_x, map_enc, map_dec, images + off * L * GF, (int64_t)L * GF, t0, nb, chunk, T,
                                            w.h_state, st)) return rc;
             pv::prof_begin(pv::FAM_GRU_HEAD, st);
-            gru_head_kernel<<<(unsigned)gru_head_blocks(nb * T, m->sms), 256, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
+            gru_head_kernel<<<(unsigned)gru_head_blocks(nb * T, m->sms), 128, 0, st>>>(w.dec_out, S, m->dense_w, m->dense_b,
                                                                                     prob_sum + off * L * GCLS, (int64_t)L * GCLS, t0, nb, T, 1);
             PV_CUDA_CHECK(cudaGetLastError());
             pv::prof_end(pv::FAM_GRU_HEAD, st, 1);
