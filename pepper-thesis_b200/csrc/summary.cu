@@ -26,10 +26,15 @@
 namespace {
 
 constexpr int NC = 16;           // packed 32-bit counter words per position
-constexpr int K1_THREADS = 512;
+#ifndef PV_K1_THREADS
+#define PV_K1_THREADS 512
+#define PV_K1_PMAX 1280
+#define PV_K1_MINB 2
+#endif
+constexpr int K1_THREADS = PV_K1_THREADS;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
-constexpr int P_MAX = 1280;      // 2 CTAs per SM: 16 words x 1280 positions = 80 KB of counters each
+constexpr int P_MAX = PV_K1_PMAX;   // 2 CTAs per SM: 16 words x 1280 positions = 80 KB of counters each
 constexpr int LIST_CAP = 1024;   // reads examined per round of the tile's work list
 constexpr int TBL = 96;          // match pieces a warp collects before it scans their bases
 constexpr int WARP_SCRATCH = 3 * TBL + 4;   // ints of per-warp scratch: piece table (read index, tile position | length, sub-piece prefix)
@@ -616,7 +621,7 @@ __device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_l
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 2) pileup_tile_kernel(const SumParams p) {
+__global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(const SumParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int32_t s_list[LIST_CAP];
     __shared__ int s_n, s_next, s_any_events, s_any_other;

@@ -128,6 +128,33 @@ def test_polisher_vs_port(n):
     assert agree >= 0.9999, (agree, raw)
 
 
+@pytest.mark.parametrize("n,T", [(1, 100), (128, 1), (129, 7), (257, 33)])
+def test_polisher_ragged_rows_and_lengths(n, T):
+    """Row counts around the 128-window tile of the recurrence kernel, sequence lengths other than the window of 100."""
+    m, sd = _polisher(3)
+    g = torch.Generator().manual_seed(100 * n + T)
+    x = torch.randint(0, 255, (n, T, 10), generator=g)
+    h = torch.randn(n, 2, 128, generator=g) * 0.5
+    logits, hf = m(x, h)
+    rl, rh = MP.polisher_forward(sd, x.float(), h)
+    assert logits.shape == rl.shape and hf.shape == rh.shape
+    assert (logits - rl).abs().max() < TOL, (logits - rl).abs().max()
+    assert (hf - rh).abs().max() < TOL, (hf - rh).abs().max()
+
+
+def test_polisher_more_windows_than_one_pass():
+    """More windows than one pass of the model holds (16384): the second pass reuses the gx / layer-output workspaces."""
+    m, sd = _polisher(4)
+    n, T = 16384 + 130, 3
+    g = torch.Generator().manual_seed(9)
+    x = torch.randint(0, 255, (n, T, 10), generator=g)
+    h = torch.randn(n, 2, 128, generator=g) * 0.5
+    logits, hf = m(x, h)
+    rl, rh = MP.polisher_forward(sd, x.float(), h)
+    assert (logits - rl).abs().max() < TOL, (logits - rl).abs().max()
+    assert (hf - rh).abs().max() < TOL, (hf - rh).abs().max()
+
+
 def test_polisher_chunk_loop():
     """1000-position chunks, 100-wide windows every 50, hidden carried, softmax summed (predict_distributed_gpu.py:63-96)."""
     m, sd = _polisher(2)
