@@ -325,6 +325,14 @@ def run_ours(args):
                     "peak": hbm_peak, "unit": "GB/s", "frac": round(alg / max(tile_ms, 1e-9) * 1e3 / 1e9 / hbm_peak, 4),
                     "algorithmic_bytes_per_step": int(alg / args.steps), "chain_ms_per_step": round(sum_ms / args.steps, 3)}
 
+    # ... and the model's tensor-core roofline (161.33 MFLOP per window, elementwise work excluded)
+    inf_ms = sum(fam_ms.get(f, 0.0) for f in ("lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head"))
+    inf_tf = 161.33e6 * k_per_step * args.steps / max(inf_ms, 1e-9) * 1e3 / 1e12
+    roof_inference = {"kernels": "lstm_input_prep + lstm_encoder_steps + lstm_decoder_steps + lstm_mlp_head", "bound": "tensor",
+                      "achieved": round(inf_tf, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(inf_tf / tc_peak, 4),
+                      "windows_per_step": int(k_per_step), "ms_per_step": round(inf_ms / args.steps, 3),
+                      "windows_per_s": round(k_per_step * args.steps / max(inf_ms, 1e-9) * 1e3), "peak_source": peak_src + ", bf16 sustained"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,7 +367,7 @@ def run_ours(args):
                            "u16" if batch.cigar16 is not None else "u32 (BAM)")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mbp/s", "h2d_bytes_per_step": int(input_bytes),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 2)},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_summary": roof_summary,
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_summary": roof_summary, "roofline_inference": roof_inference,
             "kernel_ms_per_step": {f: round(v / args.steps, 3) for f, v in fam_ms.items() if v > 0},
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
