@@ -362,7 +362,8 @@ def run_ours(args):
                        "l2": "inputs (%.2f GB) larger than L2 (126 MB), no flush needed" % (input_bytes / 1e9),
                        "groups_of_regions": hp.group_regions, "resident_groups_of_regions": res_group, "synth_seconds": round(gen_s, 1),
                        "host_format": "packed SoA batch, bases %s, qualities %s, CIGAR %s (lossless, expanded on the device)" % (
-                           "2-bit + exception list" if batch.bases2 is not None else ("4-bit (BAM nt16)" if batch.bases4 is not None else "u8"),
+                           "reference-predicted + patch list" if batch.bases_patch is not None else (
+                               "2-bit + exception list" if batch.bases2 is not None else ("4-bit (BAM nt16)" if batch.bases4 is not None else "u8")),
                            "%d-bit packed" % batch.qual_bits if batch.quals_packed is not None else "u8",
                            "u16" if batch.cigar16 is not None else "u32 (BAM)")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mbp/s", "h2d_bytes_per_step": int(input_bytes),

@@ -165,6 +165,19 @@ int pv_unpack_bases2(const uint8_t* packed_dev, int64_t n_bases, const uint64_t*
  * *n_exceptions entries (the count of a previous call). */
 int pv_pack_bases2(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, uint64_t* exceptions_host,
                    int64_t* n_exceptions, int32_t threads);
+/* Reference-predicted bases (wire form "bases_ref" of the host path; csrc/wire_ref.cu). Every base of a read is predicted
+ * from the batch's own CIGAR and reference (an aligned M/=/X base inside the region's reference_sequence = that reference
+ * byte, anything else = 'A'); only bases that differ from their prediction travel, as 16-bit entries per read (low byte
+ * s: 0..254 = the patched base sits s bases behind the cursor, 255 = move the cursor 255 bases; high byte = the base).
+ * Lossless for any byte value. The reference has no counterpart (type_read.sequence is a std::string, read.h:60-108).
+ * Host: read_patch_off_host [n_reads + 1]. First call with patches_host == NULL fills it (entry counts as an exclusive
+ * prefix; the total is read_patch_off_host[n_reads]); second call writes the entries. Needs the plain bases, cigar, ref.
+ * Device: rebuilds bases_dev[read_base_off[r] .. + read_len[r]) of every read (+ zero padding to the 16-byte boundary) from
+ * a batch whose cigar, ref and per-read / per-region arrays are device pointers. */
+int pv_pack_bases_ref(const PvReadBatch* host_batch, int64_t* read_patch_off_host, uint16_t* patches_host,
+                      int64_t patch_capacity, int32_t threads);
+int pv_unpack_bases_ref(const PvReadBatch* batch_dev_ptrs, const int64_t* read_patch_off_dev, const uint16_t* patches_dev,
+                        uint8_t* bases_dev, void* stream);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 

@@ -1,0 +1,265 @@
+// Reference-predicted bases: the "bases_ref" wire form of a host batch (include/pepper_b200.h).
+//
+// The host path is bound by the PCIe upload, and most of what it uploads is redundant with data the device already
+// holds: an aligned read base nearly always equals the reference base it is aligned to. Every base of a read is
+// therefore PREDICTED on the device from the batch's own CIGAR and reference --
+//     M / = / X base at an aligned position inside the region's reference_sequence  ->  that reference byte
+//     anything else (inserted, soft-clipped, outside the reference, behind the last op)  ->  'A'
+// -- and only the bases that differ from their prediction travel, as 16-bit patch entries per read (low byte s:
+// 0..254 = the patched base sits s bases behind the cursor, which then moves behind it; 255 = the cursor moves 255 bases,
+// no patch; high byte = the base). Any byte value survives (lossless); at ONT error rates the bases cost ~0.5 bits each
+// on the wire instead of 2.
+//
+// The prediction rule is plain BAM semantics (M/=/X consume both, I/S the read, D/N the reference) -- it only has to
+// be the SAME in pv_pack_bases_ref (host) and pv_unpack_bases_ref (device); it is not the reference's CIGAR walk.
+#include "common.cuh"
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+
+__host__ __device__ __forceinline__ bool wr_match(int op) { return op == 0 || op == 7 || op == 8; }
+__host__ __device__ __forceinline__ int wr_read_adv(int op, int len) { return (wr_match(op) || op == 1 || op == 4) ? len : 0; }
+__host__ __device__ __forceinline__ int wr_ref_adv(int op, int len) { return (wr_match(op) || op == 2 || op == 3) ? len : 0; }
+
+// ---- host: prediction of one read, calling f(index, predicted byte) for index 0 .. read_len-1 in order ------------------
+template <class F>
+void predict_read_host(const PvReadBatch& b, int64_t r, int32_t region, F f) {
+    const int64_t ref_off = b.region_ref_off[region], ref_len = b.region_ref_len[region];
+    const int64_t rel = b.read_pos[r] - b.region_ref_start[region];
+    const int64_t co = b.read_cigar_off[r];
+    const int n_ops = b.read_n_ops[r], read_len = b.read_len[r];
+    int64_t ri = 0, rp = rel;
+    for (int k = 0; k < n_ops && ri < read_len; k++) {
+        const uint32_t w = b.cigar[co + k];
+        const int op = (int)(w & 15u), len = (int)(w >> 4);
+        const int qa = wr_read_adv(op, len);
+        if (qa) {
+            const bool m = wr_match(op);
+            for (int j = 0; j < qa && ri + j < read_len; j++) {
+                const int64_t p = rp + j;
+                f(ri + j, (m && p >= 0 && p < ref_len) ? b.ref[ref_off + p] : (uint8_t)'A');
+            }
+        }
+        ri += qa; rp += wr_ref_adv(op, len);
+    }
+    for (int64_t i = ri < 0 ? 0 : ri; i < read_len; i++) f(i, (uint8_t)'A');
+}
+
+// ---- device ------------------------------------------------------------------------------------------------------
+// Warp per read. The ops that consume read bases are filed in a per-warp shared-memory table (first read index, aligned
+// reference position or "no reference"); every time the table fills (and at the end of the read) the lanes expand it
+// OUTPUT-major: each lane produces one aligned 16-byte block of the read (finding its first op by binary search, then
+// walking the table) and stores it with one 16-byte store, so the 1 byte per base this kernel writes leaves coalesced.
+constexpr int WR_TBL = 128;
+constexpr int WR_WARPS = 8;
+constexpr long long WR_NOREF = -(1ll << 62);
+
+struct WrTable { int ri[WR_TBL + 1]; long long rp[WR_TBL]; };
+
+__device__ __forceinline__ uint8_t wr_byte_at(const WrTable& t, int& j, int idx, const uint8_t* __restrict__ ref, int64_t ref_len) {
+    while (idx >= t.ri[j + 1]) j++;                       // idx < t.ri[n]: terminates inside the table
+    const long long p = t.rp[j] + (idx - t.ri[j]);
+    return (p >= 0 && p < ref_len) ? __ldg(ref + p) : (uint8_t)'A';
+}
+__device__ __forceinline__ int wr_find(const WrTable& t, int n, int idx) {      // last j with t.ri[j] <= idx
+    int lo = 0, hi = n;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (t.ri[mid] <= idx) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// read indices [a, b) from the table of n entries (t.ri[n] >= b)
+__device__ void wr_expand(const WrTable& t, int n, int a, int b, const uint8_t* __restrict__ ref, int64_t ref_len,
+                          uint8_t* __restrict__ out, int lane) {
+    if (b <= a) return;
+    int blk0 = (a + 15) & ~15;
+    if (blk0 > b) blk0 = b;
+    if (lane < blk0 - a) { int j = wr_find(t, n, a + lane); out[a + lane] = wr_byte_at(t, j, a + lane, ref, ref_len); }     // head
+    const int blk1 = blk0 + ((b - blk0) & ~15);
+    for (int blk = blk0 + lane * 16; blk < blk1; blk += 32 * 16) {
+        int j = wr_find(t, n, blk);
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                      // straight-line code: 16 independent byte look-ups
+            uint32_t x = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) x |= (uint32_t)wr_byte_at(t, j, blk + 4 * q + e, ref, ref_len) << (8 * e);
+            w[q] = x;
+        }
+        *(uint4*)(out + blk) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (lane < b - blk1) { int j = wr_find(t, n, blk1 + lane); out[blk1 + lane] = wr_byte_at(t, j, blk1 + lane, ref, ref_len); }   // tail
+}
+
+// Read lengths are heavy-tailed (1 .. 100 kbp): warps take reads from a ticket counter instead of a fixed stride, so
+// the kernel ends one read after the average warp is done, not after the unluckiest fixed assignment.
+__global__ void __launch_bounds__(WR_WARPS * 32) predict_bases_kernel(const PvReadBatch b, uint8_t* __restrict__ bases,
+                                                                       unsigned long long* __restrict__ ticket) {
+    __shared__ WrTable s_tab[WR_WARPS];
+    WrTable& t = s_tab[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);
+        const int64_t r = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+        if (r >= b.n_reads) break;
+        // region of the read: last region whose first read is <= r
+        int lo = 0, hi = b.n_regions;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (b.region_read_begin[mid] <= r) lo = mid; else hi = mid; }
+        const uint8_t* ref = b.ref + b.region_ref_off[lo];
+        const int64_t ref_len = b.region_ref_len[lo];
+        const int64_t rel = b.read_pos[r] - b.region_ref_start[lo];
+        const int64_t co = b.read_cigar_off[r];
+        const int n_ops = b.read_n_ops[r], read_len = b.read_len[r];
+        uint8_t* out = bases + b.read_base_off[r];             // 16-byte aligned
+        int ri_run = 0; long long rp_run = rel;
+        int n_tab = 0, tab_a = 0;
+        for (int k0 = 0; k0 < n_ops && ri_run < read_len; k0 += 32) {
+            const int k = k0 + lane;
+            const uint32_t w = k < n_ops ? b.cigar[co + k] : 0u;
+            const int op = (int)(w & 15u), len = (int)(w >> 4);
+            // a (malformed) op longer than the read cannot write more than the read's bases: clamp so the sums stay in range
+            int qa = k < n_ops ? wr_read_adv(op, len) : 0;
+            if (qa > read_len + 1) qa = read_len + 1;
+            const long long ra = k < n_ops ? wr_ref_adv(op, len) : 0;
+            int iq = qa; long long ir = ra;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int tq = __shfl_up_sync(0xffffffffu, iq, d); const long long tr = __shfl_up_sync(0xffffffffu, ir, d);
+                if (lane >= d) { iq += tq; ir += tr; }
+            }
+            const unsigned has = __ballot_sync(0xffffffffu, qa > 0);
+            if (qa > 0) {
+                const int at = n_tab + __popc(has & ((1u << lane) - 1u));
+                t.ri[at] = ri_run + iq - qa;
+                t.rp[at] = wr_match(op) ? rp_run + ir - ra : WR_NOREF;
+            }
+            n_tab += __popc(has);
+            ri_run += __shfl_sync(0xffffffffu, iq, 31);
+            rp_run += __shfl_sync(0xffffffffu, ir, 31);
+            const bool last = k0 + 32 >= n_ops || ri_run >= read_len;
+            if (n_tab > WR_TBL - 32 || last) {
+                if (lane == 0) t.ri[n_tab] = ri_run;
+                __syncwarp();
+                wr_expand(t, n_tab, tab_a, ri_run < read_len ? ri_run : read_len, ref, ref_len, out, lane);
+                __syncwarp();
+                n_tab = 0; tab_a = ri_run;
+            }
+        }
+        // behind the last op: 'A' up to the read's end, 0 up to the 16-byte boundary (what pack_regions / synth pad with)
+        const int pad_end = ((read_len + 15) & ~15);
+        for (int i = (ri_run < read_len ? ri_run : read_len) + lane; i < pad_end; i += 32)
+            if (b.read_base_off[r] + i < b.n_bases) out[i] = i < read_len ? (uint8_t)'A' : (uint8_t)0;
+    }
+}
+
+__global__ void apply_patches_kernel(const PvReadBatch b, const int64_t* __restrict__ patch_off, const uint16_t* __restrict__ patches,
+                                     uint8_t* __restrict__ bases) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < b.n_reads; r += n_warps) {
+        const int64_t e0 = patch_off[r], e1 = patch_off[r + 1];
+        const int read_len = b.read_len[r];
+        uint8_t* out = bases + b.read_base_off[r];
+        int cursor = 0;
+        for (int64_t e = e0; e < e1; e += 32) {
+            const bool have = e + lane < e1;
+            const uint32_t w = have ? patches[e + lane] : 0u;
+            const int s = (int)(w & 0xffu);
+            const int adv = have ? (s == 255 ? 255 : s + 1) : 0;
+            int inc = adv;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const int at = cursor + inc - 1;
+            if (have && s != 255 && at < read_len) out[at] = (uint8_t)(w >> 8);
+            cursor += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+}
+
+template <class F> void wr_parallel(int64_t n, int threads, F f) {
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    std::vector<std::thread> pool;
+    const int64_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) pool.emplace_back([=]() { const int64_t lo = t * per, hi = lo + per < n ? lo + per : n; if (lo < hi) f(lo, hi); });
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" int pv_pack_bases_ref(const PvReadBatch* hb, int64_t* read_patch_off, uint16_t* patches, int64_t patch_capacity,
+                                 int32_t threads) {
+    if (!hb || !read_patch_off) return pv::set_error(PV_EINVAL, "pv_pack_bases_ref: null argument");
+    const PvReadBatch& b = *hb;
+    if (b.n_reads && (!b.bases || !b.cigar || !b.ref)) return pv::set_error(PV_EINVAL, "pv_pack_bases_ref needs the plain bases, cigar and ref arrays");
+    std::vector<int32_t> region_of((size_t)b.n_reads, 0);
+    for (int32_t g = 0; g < b.n_regions; g++)
+        for (int64_t r = b.region_read_begin[g]; r < b.region_read_begin[g + 1]; r++) region_of[(size_t)r] = g;
+    if (!patches) {
+        // pass 1: entries per read -> exclusive prefix in read_patch_off[0 .. n_reads]
+        wr_parallel(b.n_reads, threads, [&](int64_t lo, int64_t hi) {
+            for (int64_t r = lo; r < hi; r++) {
+                const uint8_t* seq = b.bases + b.read_base_off[r];
+                int64_t n = 0, cursor = 0;
+                predict_read_host(b, r, region_of[(size_t)r], [&](int64_t i, uint8_t pred) {
+                    if (seq[i] != pred) { int64_t gap = i - cursor; n += gap / 255 + 1; cursor = i + 1; }
+                });
+                read_patch_off[r + 1] = n;
+            }
+        });
+        read_patch_off[0] = 0;
+        for (int64_t r = 0; r < b.n_reads; r++) read_patch_off[r + 1] += read_patch_off[r];
+        return PV_OK;
+    }
+    if (read_patch_off[b.n_reads] > patch_capacity)
+        return pv::set_error(PV_EINVAL, "pv_pack_bases_ref: %lld patch entries needed, buffer holds %lld", (long long)read_patch_off[b.n_reads], (long long)patch_capacity);
+    wr_parallel(b.n_reads, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t r = lo; r < hi; r++) {
+            const uint8_t* seq = b.bases + b.read_base_off[r];
+            uint16_t* out = patches + read_patch_off[r];
+            int64_t cursor = 0;
+            predict_read_host(b, r, region_of[(size_t)r], [&](int64_t i, uint8_t pred) {
+                if (seq[i] == pred) return;
+                int64_t gap = i - cursor;
+                while (gap >= 255) { *out++ = 255; gap -= 255; }
+                *out++ = (uint16_t)(gap | ((uint16_t)seq[i] << 8));
+                cursor = i + 1;
+            });
+        }
+    });
+    return PV_OK;
+}
+
+extern "C" int pv_unpack_bases_ref(const PvReadBatch* dev_batch, const int64_t* read_patch_off_dev, const uint16_t* patches_dev,
+                                   uint8_t* bases_dev, void* stream) {
+    if (!dev_batch || !bases_dev) return pv::set_error(PV_EINVAL, "pv_unpack_bases_ref: null argument");
+    const PvReadBatch& b = *dev_batch;
+    if (b.n_reads == 0) return PV_OK;
+    if (!read_patch_off_dev || !b.cigar || !b.ref) return pv::set_error(PV_EINVAL, "pv_unpack_bases_ref needs cigar, ref and the patch offsets on the device");
+    if (int rc = pv::require_device()) return rc;
+    int64_t blocks = (b.n_reads + 7) / 8;
+    const int64_t cap = (int64_t)pv::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    // one ticket counter per launch, from a small ring (launches on different streams may overlap)
+    static unsigned long long* ring = nullptr;
+    static std::atomic<unsigned> next{0};
+    constexpr unsigned RING = 64;
+    if (!ring) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> l(mu);
+        if (!ring) { unsigned long long* p = nullptr; PV_CUDA_CHECK(cudaMalloc((void**)&p, RING * sizeof(unsigned long long))); ring = p; }
+    }
+    unsigned long long* ticket = ring + (next.fetch_add(1) % RING);
+    PV_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    predict_bases_kernel<<<(unsigned)blocks, WR_WARPS * 32, 0, (cudaStream_t)stream>>>(b, bases_dev, ticket);
+    apply_patches_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, read_patch_off_dev, patches_dev, bases_dev);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}

@@ -34,10 +34,18 @@ class DeviceBatch:
         self.packed_exc = None      # exception list of the 2-bit form
         self.packed_q = None        # bit-packed qualities
         self.packed_c = None        # 16-bit CIGAR words
+        self.patches = None         # reference-predicted bases: patch entries (offsets travel with the small arrays)
         self._unpacked = True
         small = []
         for name in ARRAY_NAMES:
             a = getattr(host, name)
+            if name == "bases" and host.bases_patch is not None and a.size:
+                # only the bases that differ from their reference-based prediction travel (pv_unpack_bases_ref)
+                src = host.bases_patch if host.bases_patch.size else np.zeros(1, np.uint16)
+                self.patches = torch.from_numpy(src.view(np.int16)).to(self.device, non_blocking=non_blocking)
+                self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
+                self._unpacked = False
+                continue
             if name == "bases" and host.bases2 is not None and a.size:
                 self.packed = torch.empty(a.size // 4 + 16, dtype=torch.uint8, device=self.device)
                 self.packed[:a.size // 4].copy_(_to_torch(host.bases2), non_blocking=non_blocking)
@@ -74,6 +82,8 @@ class DeviceBatch:
             self.t[name] = src.to(self.device, non_blocking=non_blocking)
         # the ~14 small arrays (offsets rebuilt per view live in pageable memory, whose "async" copies block the host) go
         # through ONE pinned staging buffer and one copy; the device tensors are views of one allocation
+        if self.patches is not None:
+            small.append("read_patch_off")
         offs, total = {}, 0
         for name in small:
             offs[name] = total
@@ -101,6 +111,12 @@ class DeviceBatch:
             return
         lib = capi.load()
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self.packed_c is not None:           # first: the base prediction below walks the CIGAR
+            out = self.t["cigar"]
+            capi.check(lib.pv_unpack_cigar16(C.c_void_p(self.packed_c.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
+        if self.patches is not None:
+            capi.check(lib.pv_unpack_bases_ref(C.byref(self.struct), C.c_void_p(self.t["read_patch_off"].data_ptr()),
+                                               C.c_void_p(self.patches.data_ptr()), C.c_void_p(self.t["bases"].data_ptr()), st))
         if self.packed is not None and self.host.bases2 is not None:
             out = self.t["bases"]
             ne = 0 if self.packed_exc is None else self.packed_exc.numel()
@@ -113,19 +129,18 @@ class DeviceBatch:
             out = self.t["quals"]
             capi.check(lib.pv_unpack_quals(C.c_void_p(self.packed_q.data_ptr()), out.numel(), int(self.host.qual_bits),
                                            C.c_void_p(out.data_ptr()), st))
-        if self.packed_c is not None:
-            out = self.t["cigar"]
-            capi.check(lib.pv_unpack_cigar16(C.c_void_p(self.packed_c.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
         self._unpacked = True
 
     def record_stream(self, stream):
-        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self._small_dev) if x is not None]:
+        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self.patches, self._small_dev) if x is not None]:
             t.record_stream(stream)
 
     @property
     def h2d_bytes(self) -> int:
         n = int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
-        if self.packed is not None and self.host.bases2 is not None:
+        if self.patches is not None:
+            n -= self.host.bases.nbytes - self.host.bases_patch.nbytes - self.host.read_patch_off.nbytes
+        elif self.packed is not None and self.host.bases2 is not None:
             n -= self.host.bases.nbytes - self.host.bases2.nbytes - self.host.base_exceptions.nbytes
         elif self.packed is not None:
             n -= self.host.bases.nbytes - self.host.bases4.nbytes

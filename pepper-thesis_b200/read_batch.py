@@ -66,6 +66,8 @@ class ReadBatch:
     cigar16: Optional[np.ndarray] = None     # optional low 16 bits of every CIGAR word (all op lengths < 4096)
     bases2: Optional[np.ndarray] = None      # optional 2-bit packing of `bases` (n_bases / 4 bytes) ...
     base_exceptions: Optional[np.ndarray] = None   # ... + uint64 (index << 8 | byte) of every base that is not A/C/G/T
+    bases_patch: Optional[np.ndarray] = None    # optional reference-predicted form of `bases`: uint16 patch entries ...
+    read_patch_off: Optional[np.ndarray] = None  # ... of read r at [read_patch_off[r], read_patch_off[r + 1])
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -185,12 +187,47 @@ class ReadBatch:
         self.bases2, self.base_exceptions = out, exc
         return self
 
-    def pack_wire(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
-        """All compact (lossless) wire forms: 2-bit bases + exceptions (else 4-bit when the alphabet allows), bit-packed
-        qualities, 16-bit CIGAR."""
+    def pack_bases_ref(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the reference-predicted wire form of the bases (pv_pack_bases_ref): the device rebuilds every read from
+        the batch's CIGAR and reference, only the bases that differ from that prediction travel (16-bit patch entries)."""
         from . import capi
+        import os
+        lib = capi.load()
+        threads = threads or min(32, os.cpu_count() or 1)
+        if self.n_reads == 0:
+            return self
+        st = self.as_struct()
+        off = np.zeros(self.n_reads + 1, np.int64)
+        capi.check(lib.pv_pack_bases_ref(C.byref(st), off.ctypes.data, None, 0, threads))
+        total = int(off[-1])
+        self._patch_owner, out = self._host_buffer(max(2, total * 2), pinned)
+        out = out[:total * 2].view(np.uint16)
+        if total:
+            capi.check(lib.pv_pack_bases_ref(C.byref(st), off.ctypes.data, out.ctypes.data, total, threads))
+        self.bases_patch, self.read_patch_off = out, off
+        return self
+
+    def pack_wire(self, threads: int = 0, pinned: bool = False, bases_ref: Optional[bool] = None) -> "ReadBatch":
+        """All compact (lossless) wire forms: 2-bit bases + exceptions (else 4-bit when the alphabet allows), bit-packed
+        qualities, 16-bit CIGAR. ``bases_ref=True`` (or PV_WIRE_BASES_REF=1) sends the bases in the reference-predicted
+        form instead when that is smaller: ~0.6 bits per base at ONT error rates, but its expansion kernel costs more
+        device time than the 2-bit form, so it pays where the upload is the bottleneck by a wide margin (several GPUs
+        sharing the host's H2D bandwidth), not on one GPU."""
+        from . import capi
+        import os
+        if bases_ref is None:
+            bases_ref = os.environ.get("PV_WIRE_BASES_REF", "0") == "1"
         self.pack_bases2(threads, pinned)
-        if self.bases2 is None:
+        if bases_ref:
+            self.pack_bases_ref(threads, pinned)
+        if self.bases_patch is not None:
+            ref_bytes = self.bases_patch.nbytes + self.read_patch_off.nbytes
+            two_bytes = (self.bases2.nbytes + self.base_exceptions.nbytes) if self.bases2 is not None else self.n_bases
+            if ref_bytes < two_bytes:
+                self.bases2, self.base_exceptions, self._bases2_owner = None, None, None
+            else:
+                self.bases_patch, self.read_patch_off, self._patch_owner = None, None, None
+        if self.bases2 is None and self.bases_patch is None:
             try:
                 self.pack_bases4(threads, pinned)
             except capi.PvError:
@@ -203,7 +240,7 @@ class ReadBatch:
         so every upload is truly asynchronous -- without pinning the plain arrays that never travel."""
         import torch
         names = ["ref"]
-        if self.bases2 is None and self.bases4 is None:
+        if self.bases2 is None and self.bases4 is None and self.bases_patch is None:
             names.append("bases")
         if self.quals_packed is None:
             names.append("quals")
@@ -276,7 +313,11 @@ class ReadBatch:
             qual_bits=self.qual_bits if self.quals_packed is not None else 0,
             cigar16=self.cigar16[c_lo:c_hi] if self.cigar16 is not None else None,
             bases2=self.bases2[b_lo // 4:b_hi // 4] if self.bases2 is not None else None,
-            base_exceptions=self._exceptions_view(b_lo, b_hi))
+            base_exceptions=self._exceptions_view(b_lo, b_hi),
+            bases_patch=(self.bases_patch[int(self.read_patch_off[rb]):int(self.read_patch_off[re_])]
+                         if self.bases_patch is not None else None),
+            read_patch_off=(self.read_patch_off[rb:re_ + 1] - self.read_patch_off[rb]
+                            if self.bases_patch is not None else None))
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

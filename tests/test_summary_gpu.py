@@ -155,7 +155,7 @@ def test_compact_wire_formats_equal_plain(profile):
     for i in range(v.n_reads):
         real[int(v.read_base_off[i]):int(v.read_base_off[i]) + int(v.read_len[i])] = True
     assert np.array_equal(db.t["bases"].cpu().numpy()[real], v.bases[real])           # padding behind a read is don't-care
-    assert v.bases2 is not None
+    assert v.bases2 is not None or v.bases_patch is not None
     assert db.h2d_bytes < sum(getattr(v, n).nbytes for n in ("bases", "quals", "cigar")) * 0.75
 
 
@@ -178,6 +178,55 @@ def test_pack_quals_roundtrip_all_widths():
     big = np.array([4096 << 4], np.uint32)
     with pytest.raises(capi.PvError):
         capi.check(lib.pv_pack_cigar16(big.ctypes.data, 1, np.zeros(1, np.uint16).ctypes.data, 1))
+
+
+def _assert_device_bases_equal(v):
+    import torch
+    from pepper_thesis_b200 import device as dev
+    db = dev.DeviceBatch(v)
+    torch.cuda.synchronize()
+    got = db.t["bases"].cpu().numpy()
+    for i in range(v.n_reads):
+        o, n = int(v.read_base_off[i]), int(v.read_len[i])
+        assert np.array_equal(got[o:o + n], v.bases[o:o + n]), "read %d" % i
+    return db
+
+
+def test_bases_ref_roundtrip():
+    """Reference-predicted bases (pv_pack_bases_ref / pv_unpack_bases_ref): every read comes back byte for byte, for
+    fuzzed CIGARs (soft clips, N, reads hanging over both region ends, q/len edge cases), odd bytes (N, lower case,
+    '=', 255), region views (patch offsets re-based) and an empty patch list."""
+    big = synth.generate("ont_r9", 350000, 12.0, seed=4)
+    rng = np.random.default_rng(2)
+    pos = rng.integers(0, big.n_bases, 800)
+    big.bases[pos] = rng.choice(np.frombuffer(b"NnacgtRY=\xff", np.uint8), 800)
+    batches = [H.fuzz_region(s) for s in range(8)] + [big]
+    for batch in batches:
+        batch.pack_bases_ref()
+        assert batch.bases_patch is not None and int(batch.read_patch_off[-1]) == batch.bases_patch.size
+        _assert_device_bases_equal(batch)
+    for r0, r1 in ((0, 1), (1, 3), (2, 3)):
+        _assert_device_bases_equal(big.region_range_view(r0, r1))
+    # at ONT error rates the patch list is far smaller than 2 bits per base, and pack_wire picks it
+    big.pack_wire(bases_ref=True)
+    assert big.bases_patch is not None and big.bases2 is None
+    assert big.bases_patch.nbytes + big.read_patch_off.nbytes < big.n_bases // 8
+    # reads that equal their prediction exactly: no patch entries at all
+    clean = synth.generate("hifi", 120000, 5.0, seed=6)
+    clean.pack_bases_ref()
+    _assert_device_bases_equal(clean)
+    # and the summary of a batch that travelled this way is the summary of the plain batch
+    from pepper_thesis_b200 import device as dev
+    import torch
+    plain = capi.summary_regions_host(big, H.R9)
+    db = dev.DeviceBatch(big)
+    ws = dev.SummaryWorkspace.for_batch(db, 1 << 15)
+    dev.summary_regions(db, H.R9, ws)
+    k = int(ws.count.item())
+    want = plain.trimmed()
+    assert k == plain.count and k > 0
+    assert np.array_equal(ws.position[:k].cpu().numpy(), want["position"])
+    assert np.array_equal(ws.windows[:k].cpu().numpy().astype(np.int32), np.asarray(want["images"]).astype(np.int32))
 
 
 def test_bases2_exceptions_roundtrip():
