@@ -24,8 +24,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "Mbp/s pileup-summary + GRU inference"
-PRESET = "ont_r9"
-COVERAGE = 50.0
+# BASELINE.json configs[1] by default; PV_BENCH_PRESET / PV_BENCH_COVERAGE select the other presets' shapes for extra
+# measurements (configs[2]: hifi at 35x, configs[3]: ont_r10 at 40x) -- the driver's bench line is always the default.
+PRESET = os.environ.get("PV_BENCH_PRESET", "ont_r9")
+COVERAGE = float(os.environ.get("PV_BENCH_COVERAGE", "50"))
+PRESET_NAME = {"ont_r9": "ONT R9 Guppy5 SUP", "ont_r10": "ONT R10 Q20", "hifi": "HiFi"}[PRESET]
 REGION_BP = 100000
 LSTM_FLOP_PER_WINDOW = 2 * 80664064
 LSTM_DEC_STEP_FLOP_PER_WINDOW = 2 * 2 * 1024 * 768   # one decoder step launch: 2 directions x [1024 x (256+512)] MACs
@@ -164,7 +167,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(mbps, 4), "unit": "Mbp/s", "n_gpus": args.gpus,
             "steps": len(steps), "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 * wall / len(steps), 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "chr20-scale synthetic 64 Mbp, 50x ONT R9 Guppy5 SUP preset (bounded sample of it)",
+            "config": {"workload": "chr20-scale synthetic 64 Mbp, %gx %s preset (bounded sample of it)" % (COVERAGE, PRESET_NAME),
                        "regions_per_step": n_regions},
             "cpu_baseline": {"value": round(mbps, 4), "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample,
                              "summary_mbps": round(float(np.mean([s["summary_mbps"] for s in steps])), 3),
@@ -356,7 +359,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tensor-core GEMMs, fp32 accumulate/state); summary int32/u8, fp64 thresholds",
             "data": "synthetic (seeded reads/contig, random-init weights torch.manual_seed(0))",
-            "config": {"workload": "chr20-scale synthetic %g Mbp per GPU, 50x ONT R9 Guppy5 SUP preset, summary+LSTM on B200" % args.mbp,
+            "config": {"workload": "chr20-scale synthetic %g Mbp per GPU, %gx %s preset, summary+LSTM on B200" % (args.mbp, COVERAGE, PRESET_NAME),
                        "regions_per_gpu": n_regions, "region_bp": REGION_BP, "reads": batch.n_reads,
                        "read_bases": int(batch.read_len.astype(np.int64).sum()), "candidates_per_step_rank0": int(k_per_step),
                        "l2": "inputs (%.2f GB) larger than L2 (126 MB), no flush needed" % (input_bytes / 1e9),
