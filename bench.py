@@ -310,14 +310,14 @@ def run_ours(args):
                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "avg_launch_ms": round(per_launch_ms, 4),
                     "launches": n_d, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg / max(1, n_d))}
             # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this command
-            # (profiles/r1_k1_v5_bench_traffic.json), scaled to this run's regions per launch
+            # (profiles/r1_k1_v7_bench_traffic.json), scaled to this run's regions per launch
             try:
-                with open(os.path.join(ROOT, "profiles", "r1_k1_v5_bench_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r1_k1_v7_bench_traffic.json")) as f:
                     tr = json.load(f)
                 if tr.get("kernel") == dominant:
                     regions_per_launch = n_regions * args.steps / max(1, n_d)
                     roof["traffic"] = int(tr["dram_bytes_per_launch"] * regions_per_launch / tr["regions_per_launch"])
-                    roof["traffic_source"] = "profiles/r1_k1_v5_bench_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+                    roof["traffic_source"] = "profiles/r1_k1_v7_bench_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
             except Exception:
                 pass
     # the summary chain's own HBM roofline is always reported next to it

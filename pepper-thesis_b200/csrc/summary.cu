@@ -96,7 +96,8 @@ struct SumParams {
     int32_t* op_ref;              // [n_ops] reference advance before the op (relative to read_pos)
     int32_t* op_ri;               // [n_ops] read index before the op
     int32_t* read_span;           // [n_reads] total reference advance
-    int16_t* img;                 // [total_positions][26]
+    int16_t* img;                 // [total_positions][26]; rows are only valid where a candidate window can read them
+    int32_t img_all;              // 1 = write every row (dense-image parity hook)
     SiteRec* sites; int32_t site_cap;
     Event* events; int32_t ev_cap;
     CandRec* cands; unsigned long long* cand_key; int32_t cand_cap;
@@ -214,6 +215,7 @@ struct TileCtx {
     uint8_t* rcls;        // [P] shared: class 0..3 of the reference base, 0xff when it is not A/C/G/T (any case)
     uint8_t* lut;         // [256] shared: base byte -> class 0..6 | 8 if the byte is an upper-case A/C/G/T
     uint8_t* pflag;       // [P] shared: PF_* of each tile position (phase B onwards)
+    uint8_t* near;        // [P] shared: 1 = the position's image row is needed by a window (a site within 16 positions)
     int32_t* site_slot;   // [P] shared (aliases cnt after phase B): site index or -1
     int32_t* scratch;     // this warp's [4][32] shared scratch
     int P;
@@ -640,6 +642,7 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     c.pflag = c.ref_s + P + 32;
     c.rcls = c.pflag + P;
     c.lut = c.rcls + P;
+    c.near = c.lut + 256;
     if (tid < 256) c.lut[tid] = (uint8_t)(base_class((uint8_t)tid) | (acgt_code((uint8_t)tid) >= 0 ? 8 : 0));
     c.region = p.tile_region[blockIdx.x];
     c.t_lo = p.tile_start[blockIdx.x];
@@ -657,6 +660,7 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
         c.ref_s[i] = rbyte;
         c.rcls[i] = valid_ref(rbyte) ? (uint8_t)base_class(rbyte) : (uint8_t)0xff;
         c.pflag[i] = 0;
+        c.near[i] = 0;
     }
     if (tid == 0) { s_any_events = 0; s_any_other = 0; }
     __syncthreads();
@@ -722,10 +726,11 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
             }
 #pragma unroll
             for (int f = 11; f < 25; f++) row[f] = row[f] < -125 ? -125 : row[f];   // :648-653 (all values <= 0 here)
-            uint32_t* dst = (uint32_t*)(p.img + (gbase + i) * PV_FEATURES);
+            // the clamped row goes back into this position's (already consumed) counter words 0..12; it is flushed to HBM
+            // below only where a candidate window can read it
 #pragma unroll
             for (int f = 0; f < PV_FEATURES; f += 2)
-                dst[f >> 1] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
+                c.cnt[(f >> 1) * P + i] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
 
             const int cov = tf + tr + (int)(w[C_COV2] & 0xffffu);
             const int snp = (int)(w[C_COV2] >> 16) + (int)(snp_sum & 0xffffu) + (int)(snp_sum >> 16);
@@ -763,11 +768,23 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
                     p.sites[s] = sr;
                     my_site[u] = s;
                     c.pflag[i] = (uint8_t)flags;
+                    const int j1 = i + (PV_WINDOW / 2) < c.n_valid ? i + (PV_WINDOW / 2) : c.n_valid - 1;
+                    for (int j = i - (PV_WINDOW / 2) > 0 ? i - (PV_WINDOW / 2) : 0; j <= j1; j++) c.near[j] = 1;
                 } else {
                     atomicOr(&p.ctr[CTR_STATUS], ST_SITE_OVF);
                 }
             }
         }
+    }
+    __syncthreads();
+    // Image rows -> HBM. Only the candidate windows read the image (K3: rows p-16 .. p+16 of a site p), so a row is
+    // written when a site of this tile lies within 16 positions, or when it is one of the tile's first / last 16 rows
+    // (a site of the neighbouring tile may reach it): ~10 % of the rows instead of 52 bytes for every position.
+    for (int i = tid; i < c.n_valid; i += K1_THREADS) {
+        if (!(p.img_all || c.near[i] || i < PV_WINDOW / 2 || i >= c.n_valid - PV_WINDOW / 2)) continue;
+        uint32_t* dst = (uint32_t*)(p.img + (gbase + i) * PV_FEATURES);
+#pragma unroll
+        for (int k = 0; k < PV_FEATURES / 2; k++) dst[k] = c.cnt[k * P + i];
     }
     __syncthreads();
     if (!s_any_events) return;
@@ -953,7 +970,7 @@ int choose_tile(int64_t total_positions, int32_t n_regions) {
     return P;
 }
 
-size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4 + REF_PAD + 3 * (size_t)P + 32 + 256 + 16; }
+size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4 + REF_PAD + 4 * (size_t)P + 32 + 256 + 16; }
 
 Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
     Plan pl;
@@ -1058,6 +1075,7 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     p.b = b; p.pos_off = w.pos_off; p.tile_region = w.tile_region; p.tile_start = w.tile_start; p.P = pl.P;
     p.op_ref = w.op_ref; p.op_ri = w.op_ri; p.read_span = w.read_span;
     p.img = dense_image_dev ? dense_image_dev : w.img;
+    p.img_all = dense_image_dev ? 1 : 0;
     p.sites = w.sites; p.site_cap = (int32_t)pl.site_cap; p.events = w.events; p.ev_cap = (int32_t)pl.ev_cap;
     p.cands = w.cands; p.cand_key = w.key_in; p.cand_cap = (int32_t)pl.cand_cap; p.ctr = w.ctr;
     double q = thr->min_snp_baseq; int qi = 0;
