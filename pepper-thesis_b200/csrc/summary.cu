@@ -413,11 +413,18 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
     int n_e = 0, n_sub = 0;
     // ops are walked from k_begin until one starts behind the position right after the tile (op starts never decrease;
     // an insert/delete at nv still anchors on the tile's last position): no search for the end of the range
+    // the three per-op loads of the NEXT 32 ops are issued before this step's work (they may turn out unused when the walk
+    // ends here: harmless, they stay inside the read's op range)
+    uint32_t w_n = 0u; int32_t oref_n = 0, ori_n = 0;
+    if (k_begin + lane < x.n_ops) { w_n = b.cigar[x.co + k_begin + lane]; oref_n = x.oref[k_begin + lane]; ori_n = x.ori_a[k_begin + lane]; }
     for (int kb = k_begin; kb < x.n_ops; kb += 32) {
         const int k = kb + lane;
         bool have = k < x.n_ops;
-        const uint32_t w = have ? b.cigar[x.co + k] : 0u;
-        int64_t a64 = have ? x.rel_t + (int64_t)x.oref[k] : 0;                   // op start, tile-local
+        const uint32_t w = w_n;
+        int64_t a64 = have ? x.rel_t + (int64_t)oref_n : 0;                      // op start, tile-local
+        const int ori_c = ori_n;
+        if (k + 32 < x.n_ops) { w_n = b.cigar[x.co + k + 32]; oref_n = x.oref[k + 32]; ori_n = x.ori_a[k + 32]; }
+        else w_n = 0u;
         if (a64 > (1 << 30)) a64 = (1 << 30);
         if (a64 < -(1 << 30)) a64 = -(1 << 30);
         const int a = (int)a64;
@@ -426,7 +433,7 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
         have = have && !beyond;
         const int op = have ? (int)(w & 15u) : 15;
         const int len = (int)(w >> 4);
-        const int ori = have ? x.ori_a[k] : 0;
+        const int ori = have ? ori_c : 0;
         uint32_t pw = __shfl_up_sync(0xffffffffu, w, 1);                         // the op in front of this one
         if (lane == 0) pw = k > 0 ? b.cigar[x.co + k - 1] : 0u;
         int m_cnt = 0, m_ri0 = 0, m_p0 = 0;
