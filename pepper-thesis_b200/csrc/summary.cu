@@ -592,29 +592,34 @@ __device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, i
 // of the others.
 
 template <int MODE>
-__device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next) {
+__device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next, int* s_n_short) {
     const PvReadBatch& b = p.b;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
     const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;
     for (int64_t base = rb; base < re; base += LIST_CAP) {
-        if (tid == 0) { *s_n = 0; *s_next = 0; }
+        if (tid == 0) { *s_n = 0; *s_next = 0; *s_n_short = 0; }
         __syncthreads();
         const int64_t end = base + LIST_CAP < re ? base + LIST_CAP : re;
         for (int64_t r = base + tid; r < end; r += blockDim.x) {
             if (b.read_mapq[r] == 0) continue;                                   // :619
             const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
             // touched positions: aligned/deleted [rel, rel+span-1] and insert/delete anchors [rel-1, rel+span-1]
-            if (rel - 1 > t_hi || rel + (int64_t)p.read_span[r] - 1 < t_lo) continue;
-            s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
+            const int64_t last = rel + (int64_t)p.read_span[r] - 1;
+            if (rel - 1 > t_hi || last < t_lo) continue;
+            // longest units first: reads that cover the whole tile are listed from the front, reads that start or end
+            // inside it (less work) from the back, so the round's last units are short ones
+            if (rel <= t_lo && last >= t_hi) s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
+            else s_list[LIST_CAP - 1 - atomicAdd(s_n_short, 1)] = (int32_t)(r - base);
         }
         __syncthreads();
-        const int n = *s_n;
+        const int n_long = *s_n, n = n_long + *s_n_short;
         while (true) {
             int i = 0;
             if (lane == 0) i = atomicAdd(s_next, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= n) break;
+            if (i >= n_long) i = LIST_CAP - 1 - (i - n_long);
             const int64_t r = base + s_list[i];
             // first op: one op before the first a_k = rel + op_ref[k] >= t_lo may extend into the tile; the walk ends at the
             // first op that starts behind t_hi + 1 (an insert/delete right behind the tile anchors on its last position)
@@ -633,7 +638,7 @@ __device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_l
 __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(const SumParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int32_t s_list[LIST_CAP];
-    __shared__ int s_n, s_next, s_any_events, s_any_other;
+    __shared__ int s_n, s_next, s_n_short, s_any_events, s_any_other;
 
     const PvReadBatch& b = p.b;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -673,7 +678,7 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     __syncthreads();
 
     // ---- phase A: accumulate -----------------------------------------------------------------------------------
-    for_each_unit<0>(p, c, s_list, &s_n, &s_next);
+    for_each_unit<0>(p, c, s_list, &s_n, &s_next, &s_n_short);
 
     // ---- phase B: image rows, site thresholds ---------------------------------------------------------------------
     // difference arrays -> counts: in-place inclusive prefix sums over the tile (packed words, modulo 2^32: the true
@@ -804,7 +809,7 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     }
     __threadfence();      // site records (n_ev, ev_off) are read back through global memory by record_event
     __syncthreads();
-    for_each_unit<1>(p, c, s_list, &s_n, &s_next);
+    for_each_unit<1>(p, c, s_list, &s_n, &s_next, &s_n_short);
     if (s_any_other) {
         const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
         for (int i = 0; i < c.n_valid; i++) {
