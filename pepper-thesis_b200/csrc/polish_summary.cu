@@ -77,7 +77,8 @@ __global__ void polish_walk_kernel(const PolishArgs a) {
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < b.n_reads; r += n_warps) {
         if (b.read_mapq[r] == 0) continue;                                          // :376
-        const int reg = a.read_region[r];
+        int reg = 0;                                                                // last region whose first read is <= r
+        { int hi = b.n_regions; while (hi - reg > 1) { const int mid = (reg + hi) >> 1; if (b.region_read_begin[mid] <= r) reg = mid; else hi = mid; } }
         const int64_t rs = b.region_ref_start[reg];
         const int64_t L = b.region_ref_end[reg] - rs + 1;
         const int64_t rel = b.read_pos[r] - rs;
@@ -123,9 +124,167 @@ __global__ void polish_walk_kernel(const PolishArgs a) {
     }
 }
 
+// ---- P1 as a tile kernel ---------------------------------------------------------------------------------------------
+// CTA per tile of PT_P positions of one region; the ten counters of a position live in SHARED memory (position-major,
+// so the flush is a straight coalesced copy). A warp takes a read that touches the tile, finds its first op with a
+// binary search in the CIGAR prefix, walks the ops lane-per-op (deletions, insert lengths, coverage quirk) and files the
+// clipped match runs in a per-warp table; the table is then expanded lane-per-BASE (coalesced base loads, one shared
+// atomic per base). Coverage is not counted per base: cov = sum of the ten counters - deleted bases + the reference's
+// deletion coverage charged to the op's first position (:108).
+constexpr int PT_THREADS = 512;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_P = 1536;
+constexpr int PT_TBL = 96;
+constexpr int PT_LIST = 1024;
+struct PtTable { int ri[PT_TBL]; int p0[PT_TBL]; int pre[PT_TBL + 1]; };
+constexpr size_t PT_SMEM = (size_t)PT_P * NF * 4 + 3 * (size_t)PT_P * 4 + PT_WARPS * sizeof(PtTable) + PT_LIST * 4 + 64;
+
+__global__ void __launch_bounds__(PT_THREADS, 2) polish_tile_kernel(const PolishArgs a) {
+    extern __shared__ __align__(16) uint8_t pt_smem[];
+    uint32_t* cnt = (uint32_t*)pt_smem;                       // [PT_P][NF]
+    uint32_t* dels = cnt + PT_P * NF;                         // [PT_P] deleted bases ('*' counts that are no coverage)
+    uint32_t* delcov = dels + PT_P;                           // [PT_P] coverage charged to a deletion's first position
+    uint32_t* longest = delcov + PT_P;                        // [PT_P]
+    PtTable* tables = (PtTable*)(longest + PT_P);
+    int32_t* s_list = (int32_t*)(tables + PT_WARPS);
+    int* s_n = s_list + PT_LIST; int* s_next = s_n + 1;
+
+    const PvReadBatch& b = a.b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int reg = blockIdx.y;
+    const int64_t rs = b.region_ref_start[reg];
+    const int64_t L = b.region_ref_end[reg] - rs + 1;
+    const int64_t t_lo = (int64_t)blockIdx.x * PT_P;
+    if (t_lo >= L) return;
+    const int nv = (int)(L - t_lo < PT_P ? L - t_lo : PT_P);
+    const int64_t t_hi = t_lo + nv - 1;
+    const int64_t g0 = a.pos_off[reg] + t_lo;
+    PtTable& tb = tables[warp];
+
+    for (int i = tid; i < PT_P * (NF + 3); i += PT_THREADS) cnt[i] = 0;       // cnt, dels, delcov, longest are contiguous
+    const int64_t rb = b.region_read_begin[reg], re = b.region_read_begin[reg + 1];
+    for (int64_t base = rb; base < re; base += PT_LIST) {
+        __syncthreads();
+        if (tid == 0) { *s_n = 0; *s_next = 0; }
+        __syncthreads();
+        const int64_t end = base + PT_LIST < re ? base + PT_LIST : re;
+        for (int64_t r = base + tid; r < end; r += PT_THREADS) {
+            if (b.read_mapq[r] == 0) continue;                                      // :376
+            const int n_ops = b.read_n_ops[r];
+            if (n_ops <= 0) continue;
+            const int64_t co = b.read_cigar_off[r];
+            const uint32_t wl = b.cigar[co + n_ops - 1];
+            const int opl = (int)(wl & 15u);
+            const int64_t span = (int64_t)a.op_ref[co + n_ops - 1] + ((is_m(opl) || opl == 2 || opl == 3 || opl == 6) ? (int64_t)(wl >> 4) : 0);
+            const int64_t rel = b.read_pos[r] - rs;
+            if (rel - 1 > t_hi || rel + span < t_lo) continue;                      // touches [rel - 1, rel + span - 1]
+            s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
+        }
+        __syncthreads();
+        const int n_list = *s_n;
+        while (true) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(s_next, 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= n_list) break;
+            const int64_t r = base + s_list[it];
+            const int64_t rel = b.read_pos[r] - rs;
+            const int64_t co = b.read_cigar_off[r], bo = b.read_base_off[r];
+            const int n_ops = b.read_n_ops[r], read_len = b.read_len[r];
+            const bool rev = b.read_flags[r] & 1;
+            const int star = feature_index('*', rev);
+            // first op that can touch the tile: one before the first op starting at or behind t_lo
+            int lo = 0, hi = n_ops;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel + (int64_t)a.op_ref[co + mid] >= t_lo) hi = mid; else lo = mid + 1; }
+            int k_lo = lo - 1; if (k_lo < 0) k_lo = 0;
+            int n_tab = 0, n_base = 0;
+            for (int k0 = k_lo; k0 < n_ops; k0 += 32) {
+                const int k = k0 + lane;
+                const bool have = k < n_ops;
+                const uint32_t w = have ? b.cigar[co + k] : 0u;
+                const int op = (int)(w & 15u);
+                const int64_t len = (int64_t)(w >> 4);
+                const int64_t p0 = have ? rel + a.op_ref[co + k] : (int64_t)1 << 40;  // region-local reference position
+                const int64_t ri = have ? a.op_ri[co + k] : 0;
+                const bool stop = __any_sync(0xffffffffu, have && p0 > t_hi + 1) || k0 + 32 >= n_ops;
+                int m_cnt = 0, m_ri = 0, m_p = 0;
+                if (have && p0 <= L - 1 && p0 <= t_hi + 1) {                        // `if (ref_position > region_end) break`, :55
+                    if (is_m(op)) {                                                 // :57-78
+                        int64_t i_lo = p0 < 0 ? -p0 : 0;
+                        int64_t i_hi = len; if (i_hi > L - p0) i_hi = L - p0; if (i_hi > read_len - ri) i_hi = read_len - ri;
+                        if (i_lo < t_lo - p0) i_lo = t_lo - p0;
+                        if (i_hi > t_hi + 1 - p0) i_hi = t_hi + 1 - p0;
+                        if (i_hi > i_lo) { m_cnt = (int)(i_hi - i_lo); m_ri = (int)(ri + i_lo); m_p = (int)(p0 + i_lo - t_lo); }
+                    } else if (op == 1) {                                           // :79-96
+                        const int64_t an = p0 - 1;
+                        if (an >= t_lo && an <= t_hi && an <= L - 1 && ri <= read_len) {
+                            int64_t alen = len; if (alen > read_len - ri) alen = read_len - ri;
+                            if (alen > 0) atomicMax(&longest[an - t_lo], (uint32_t)alen);
+                        }
+                    } else if (op == 2 || op == 3 || op == 6) {                     // :97-113
+                        const int64_t r_lo = p0 < 0 ? -p0 : 0;
+                        int64_t r_hi = len; if (r_hi > L - p0) r_hi = L - p0;
+                        int64_t i_lo = r_lo < t_lo - p0 ? t_lo - p0 : r_lo;
+                        int64_t i_hi = r_hi > t_hi + 1 - p0 ? t_hi + 1 - p0 : r_hi;
+                        for (int64_t i = i_lo; i < i_hi; i++) {
+                            atomicAdd(&cnt[(p0 + i - t_lo) * NF + star], 1u);
+                            atomicAdd(&dels[p0 + i - t_lo], 1u);
+                        }
+                        // the reference adds this coverage at ref_position (the op's start), once per in-range deleted base
+                        if (r_hi > r_lo && p0 >= t_lo && p0 <= t_hi) atomicAdd(&delcov[p0 - t_lo], (uint32_t)(r_hi - r_lo));
+                    }
+                }
+                // file the match runs of these 32 ops with the running number of bases in front of each
+                int incl = m_cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const unsigned nz = __ballot_sync(0xffffffffu, m_cnt > 0);
+                if (m_cnt > 0) {
+                    const int at = n_tab + __popc(nz & ((1u << lane) - 1u));
+                    tb.ri[at] = m_ri; tb.p0[at] = m_p; tb.pre[at] = n_base + incl - m_cnt;
+                }
+                n_tab += __popc(nz);
+                n_base += __shfl_sync(0xffffffffu, incl, 31);
+                if (n_tab > PT_TBL - 32 || stop) {
+                    if (lane == 0) tb.pre[n_tab] = n_base;
+                    __syncwarp();
+                    for (int t = lane; t < n_base; t += 32) {                   // lane per base
+                        int jl = 0, jh = n_tab;                                  // last piece with pre[j] <= t
+                        while (jh - jl > 1) { const int mid = (jl + jh) >> 1; if (tb.pre[mid] <= t) jl = mid; else jh = mid; }
+                        const int off = t - tb.pre[jl];
+                        atomicAdd(&cnt[(tb.p0[jl] + off) * NF + feature_index(b.bases[bo + tb.ri[jl] + off], rev)], 1u);
+                    }
+                    __syncwarp();
+                    n_tab = 0; n_base = 0;
+                }
+                if (stop) break;
+            }
+        }
+    }
+    __syncthreads();
+    // flush: the ten counters (a straight copy), coverage, longest insert
+    for (int i = tid; i < nv * NF; i += PT_THREADS) a.cnt[g0 * NF + i] = cnt[i];
+    for (int i = tid; i < nv; i += PT_THREADS) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int f = 0; f < NF; f++) s += cnt[i * NF + f];
+        a.cov[g0 + i] = s - dels[i] + delcov[i];
+        a.longest[g0 + i] = longest[i];
+    }
+}
+
 __global__ void polish_rows_kernel(const uint32_t* __restrict__ longest, int64_t n, int64_t* __restrict__ rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) rows[i] = i < n ? 1 + (int64_t)longest[i] : 0;
+}
+
+__global__ void polish_region_rows_kernel(const int64_t* __restrict__ row_of, const int64_t* __restrict__ pos_off, int n,
+                                          int64_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = row_of[pos_off[i]];
 }
 
 // uint8_t v = double: x86-64 converts through a truncating 32-bit integer conversion and keeps the low byte
@@ -139,7 +298,9 @@ __global__ void polish_emit_kernel(const PolishArgs a, int64_t n_pos, const int3
                                    uint8_t* __restrict__ image, int64_t* __restrict__ gpos, int32_t* __restrict__ row_region) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pos) return;
-    const int reg = pos_region[i];
+    (void)pos_region;
+    int reg = 0;                                                                    // last region whose first position is <= i
+    { int hi = a.b.n_regions; while (hi - reg > 1) { const int mid = (reg + hi) >> 1; if (a.pos_off[mid] <= i) reg = mid; else hi = mid; } }
     const int64_t pos = a.b.region_ref_start[reg] + (i - a.pos_off[reg]);
     const int64_t row = a.row_of[i];
     const uint32_t cov = a.cov[i];
@@ -202,26 +363,16 @@ extern "C" int pv_polish_count(const PvReadBatch* batch, const int64_t* region_l
     int64_t* pos_off = ar.take<int64_t>(b.n_regions + 1); void* scan_tmp = ar.take<uint8_t>((int64_t)tmp);
 
     std::vector<int64_t> po(b.n_regions + 1, 0);
-    std::vector<int32_t> pr((size_t)total_positions);
     for (int32_t r = 0; r < b.n_regions; r++) {
         if (region_len_host[r] <= 0) return pv::set_error(PV_EINVAL, "region %d has length %lld", r, (long long)region_len_host[r]);
         po[r + 1] = po[r] + region_len_host[r];
-        if (po[r + 1] > total_positions) return pv::set_error(PV_EINVAL, "total_positions does not match region lengths");
-        for (int64_t i = po[r]; i < po[r + 1]; i++) pr[(size_t)i] = r;
     }
     if (po[b.n_regions] != total_positions) return pv::set_error(PV_EINVAL, "total_positions does not match region lengths");
-    // read -> region (region_read_begin lives on the device: copy it back once; it is tiny)
-    std::vector<int64_t> rb(b.n_regions + 1);
-    PV_CUDA_CHECK(cudaMemcpyAsync(rb.data(), b.region_read_begin, rb.size() * 8, cudaMemcpyDeviceToHost, st));
-    PV_CUDA_CHECK(cudaStreamSynchronize(st));
-    std::vector<int32_t> rr((size_t)b.n_reads);
-    for (int32_t r = 0; r < b.n_regions; r++) for (int64_t i = rb[r]; i < rb[r + 1]; i++) rr[(size_t)i] = r;
+    // the region of a read / of a position is found on the device (binary search in region_read_begin / pos_off): no
+    // per-position table is built or uploaded
+    (void)pos_region; (void)read_region;
     PV_CUDA_CHECK(cudaMemcpyAsync(pos_off, po.data(), po.size() * 8, cudaMemcpyHostToDevice, st));
-    if (total_positions) PV_CUDA_CHECK(cudaMemcpyAsync(pos_region, pr.data(), pr.size() * 4, cudaMemcpyHostToDevice, st));
-    if (b.n_reads) PV_CUDA_CHECK(cudaMemcpyAsync(read_region, rr.data(), rr.size() * 4, cudaMemcpyHostToDevice, st));
-    PV_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)total_positions * NF * 4, st));
-    PV_CUDA_CHECK(cudaMemsetAsync(cov, 0, (size_t)total_positions * 4, st));
-    PV_CUDA_CHECK(cudaMemsetAsync(longest, 0, (size_t)total_positions * 4, st));
+    // cnt / cov / longest need no clearing: every position is written by the flush of its tile
 
     PolishArgs a;
     a.b = b; a.pos_off = pos_off; a.read_region = read_region; a.op_ref = op_ref; a.op_ri = op_ri; a.cnt = cnt; a.cov = cov;
@@ -231,19 +382,32 @@ extern "C" int pv_polish_count(const PvReadBatch* batch, const int64_t* region_l
         int64_t blocks = (b.n_reads + 7) / 8; if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
         pv::prof_begin(pv::FAM_POLISH, st);
         polish_prefix_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, op_ref, op_ri);
-        polish_walk_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(a);
         PV_CUDA_CHECK(cudaGetLastError());
-        pv::prof_end(pv::FAM_POLISH, st, 2);
+        pv::prof_end(pv::FAM_POLISH, st, 1);
+    }
+    if (total_positions > 0) {
+        int64_t max_len = 0;
+        for (int32_t r = 0; r < b.n_regions; r++) if (region_len_host[r] > max_len) max_len = region_len_host[r];
+        static bool attr_done = false;
+        if (!attr_done) { PV_CUDA_CHECK(cudaFuncSetAttribute(polish_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM)); attr_done = true; }
+        const dim3 grid((unsigned)((max_len + PT_P - 1) / PT_P), (unsigned)b.n_regions);
+        pv::prof_begin(pv::FAM_POLISH, st);
+        polish_tile_kernel<<<grid, PT_THREADS, PT_SMEM, st>>>(a);
+        PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_POLISH, st, 1);
     }
     pv::prof_begin(pv::FAM_POLISH, st);
     polish_rows_kernel<<<(unsigned)((total_positions + 256) / 256), 256, 0, st>>>(longest, total_positions, rows_in);
     PV_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp, rows_in, row_of, (int)(total_positions + 1), st));
     pv::prof_end(pv::FAM_POLISH, st, 2);
-    PV_CUDA_CHECK(cudaMemcpyAsync(n_rows_host, row_of + total_positions, 8, cudaMemcpyDeviceToHost, st));
-    if (region_rows_host)
-        for (int32_t r = 0; r <= b.n_regions; r++)
-            PV_CUDA_CHECK(cudaMemcpyAsync(region_rows_host + r, row_of + po[r], 8, cudaMemcpyDeviceToHost, st));
+    // first row of every region (and the total behind the last one): gathered on the device, one copy back
+    std::vector<int64_t> rr_host((size_t)b.n_regions + 1, 0);
+    polish_region_rows_kernel<<<(unsigned)((b.n_regions + 1 + 255) / 256), 256, 0, st>>>(row_of, pos_off, b.n_regions + 1, rows_in);
+    PV_CUDA_CHECK(cudaGetLastError());
+    PV_CUDA_CHECK(cudaMemcpyAsync(rr_host.data(), rows_in, rr_host.size() * 8, cudaMemcpyDeviceToHost, st));
     PV_CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_rows_host = rr_host[(size_t)b.n_regions];
+    if (region_rows_host) memcpy(region_rows_host, rr_host.data(), rr_host.size() * 8);
     return PV_OK;
 }
 

@@ -66,24 +66,28 @@ class PolishSummary:
     def chunks(self, chunk_size: int = SEQ_LENGTH, chunk_overlap: int = SEQ_OVERLAP):
         """-> (images uint8 [n_chunks][chunk_size][10], positions int64 [n_chunks][chunk_size][2], chunk_ids, chunk_region):
         chunk_images applied to every region, regions concatenated."""
-        rows, valid, ids, regs = [], [], [], []
-        for r in range(len(self.region_rows) - 1):
-            lo, hi = int(self.region_rows[r]), int(self.region_rows[r + 1])
-            if hi == lo:
-                continue
-            for cid, (s, n) in enumerate(chunk_plan(hi - lo, chunk_size, chunk_overlap)):
-                rows.append(lo + s); valid.append(n); ids.append(cid); regs.append(r)
+        # chunk_plan for every region at once: a region of n rows has 1 + ceil(max(0, n - size) / (size - overlap)) chunks,
+        # chunk k starts at row k * (size - overlap) and holds min(size, n - start) real rows
+        lo = self.region_rows[:-1]
+        n = np.diff(self.region_rows)
+        step = chunk_size - chunk_overlap
+        per = np.where(n > 0, 1 + (np.maximum(0, n - chunk_size) + step - 1) // step, 0)
+        regs = np.repeat(np.arange(len(n), dtype=np.int32), per)
+        ids = np.arange(int(per.sum()), dtype=np.int64) - np.repeat(np.cumsum(per) - per, per)
+        start = ids * step
+        rows = lo[regs] + start
+        valid = np.minimum(chunk_size, n[regs] - start)
         d = self.image.device
         n_chunks = len(rows)
         images = torch.empty((n_chunks, chunk_size, IMAGE_HEIGHT), dtype=torch.uint8, device=d)
         positions = torch.empty((n_chunks, chunk_size, 2), dtype=torch.int64, device=d)
         if n_chunks:
-            tr = torch.tensor(rows, dtype=torch.int64, device=d)
-            tv = torch.tensor(valid, dtype=torch.int64, device=d)
+            tr = torch.from_numpy(np.ascontiguousarray(rows, np.int64)).to(d)
+            tv = torch.from_numpy(np.ascontiguousarray(valid, np.int64)).to(d)
             capi.check(capi.load().pv_polish_chunks(self.image.data_ptr(), self.genomic_pos.data_ptr(), tr.data_ptr(), tv.data_ptr(),
                                                     n_chunks, chunk_size, images.data_ptr(), positions.data_ptr(),
                                                     C.c_void_p(torch.cuda.current_stream(d).cuda_stream)))
-        return images, positions, np.asarray(ids, np.int64), np.asarray(regs, np.int32)
+        return images, positions, ids.astype(np.int64), regs.astype(np.int32)
 
 
 class SummaryGenerator:
