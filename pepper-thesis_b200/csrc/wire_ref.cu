@@ -80,13 +80,32 @@ __device__ void wr_expand(const WrTable& t, int n, int a, int b, const uint8_t* 
     const int blk1 = blk0 + ((b - blk0) & ~15);
     for (int blk = blk0 + lane * 16; blk < blk1; blk += 32 * 16) {
         int j = wr_find(t, n, blk);
+        int cur = t.ri[j], nxt = t.ri[j + 1];                  // the op that holds the next byte, kept in registers
+        long long rp = t.rp[j];
         uint32_t w[4];
+        const long long p16 = rp + (blk - cur);
+        if (nxt - blk >= 16 && p16 >= 0 && p16 + 20 <= ref_len) {
+            // the whole block is one run of reference bytes: 16 unaligned bytes = five aligned words + funnel shifts
+            const uintptr_t addr = (uintptr_t)(ref + p16);
+            const uint32_t* src = (const uint32_t*)(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            const uint32_t r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
+            const uint32_t r4 = sh ? __ldg(src + 4) : 0u;      // not touched when the run is word aligned (may end the array)
+            w[0] = __funnelshift_r(r0, r1, sh); w[1] = __funnelshift_r(r1, r2, sh);
+            w[2] = __funnelshift_r(r2, r3, sh); w[3] = __funnelshift_r(r3, r4, sh);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {                      // straight-line code: 16 independent byte look-ups
-            uint32_t x = 0;
+            for (int q = 0; q < 4; q++) {
+                uint32_t x = 0;
 #pragma unroll
-            for (int e = 0; e < 4; e++) x |= (uint32_t)wr_byte_at(t, j, blk + 4 * q + e, ref, ref_len) << (8 * e);
-            w[q] = x;
+                for (int e = 0; e < 4; e++) {
+                    const int idx = blk + 4 * q + e;
+                    while (idx >= nxt) { j++; cur = nxt; nxt = t.ri[j + 1]; rp = t.rp[j]; }
+                    const long long p = rp + (idx - cur);
+                    x |= (uint32_t)((p >= 0 && p < ref_len) ? __ldg(ref + p) : (uint8_t)'A') << (8 * e);
+                }
+                w[q] = x;
+            }
         }
         *(uint4*)(out + blk) = make_uint4(w[0], w[1], w[2], w[3]);
     }
