@@ -214,7 +214,7 @@ def run_ours(args):
 
     model = models.TransducerGRU(26, 1, 256, 28, 3, True)
     model.load_state_dict(models.random_variant_state_dict(0))
-    hp = pipeline.HotPath(model, thr, device, group_regions=int(os.environ.get("PV_BENCH_HOST_GROUP", "64")))
+    hp = pipeline.HotPath(model, thr, device, group_regions=int(os.environ.get("PV_BENCH_HOST_GROUP", "128")))
 
     # resident copy for the kernel-only number (inputs in HBM before the timed region starts). Device-resident groups
     # are larger than the host-path groups: there is no upload to overlap, and K0/K2/sort/K3 are launch-latency bound.

@@ -53,7 +53,7 @@ void predict_read_host(const PvReadBatch& b, int64_t r, int32_t region, F f) {
 // reference position or "no reference"); every time the table fills (and at the end of the read) the lanes expand it
 // OUTPUT-major: each lane produces one aligned 16-byte block of the read (finding its first op by binary search, then
 // walking the table) and stores it with one 16-byte store, so the 1 byte per base this kernel writes leaves coalesced.
-constexpr int WR_TBL = 128;
+constexpr int WR_TBL = 256;
 constexpr int WR_WARPS = 8;
 constexpr long long WR_NOREF = -(1ll << 62);
 
@@ -70,7 +70,13 @@ __device__ __forceinline__ int wr_find(const WrTable& t, int n, int idx) {      
     return lo;
 }
 
-// read indices [a, b) from the table of n entries (t.ri[n] >= b)
+__device__ __forceinline__ unsigned long long wr_bytes_below(int x) {      // mask of bytes 0 .. x-1 of a 64-bit word, x in [0, 8]
+    return x >= 8 ? ~0ull : ((1ull << (8 * x)) - 1ull);
+}
+
+// read indices [a, b) from the table of n entries (t.ri[n] >= b). Aligned 16-byte blocks are produced run by run: a run
+// (the part of one op inside the block) is 16 unaligned reference bytes fetched as five aligned words + funnel shifts,
+// masked to the run's bytes; a lane takes two neighbouring blocks so it searches its first op once per 32 bytes.
 __device__ void wr_expand(const WrTable& t, int n, int a, int b, const uint8_t* __restrict__ ref, int64_t ref_len,
                           uint8_t* __restrict__ out, int lane) {
     if (b <= a) return;
@@ -78,36 +84,45 @@ __device__ void wr_expand(const WrTable& t, int n, int a, int b, const uint8_t* 
     if (blk0 > b) blk0 = b;
     if (lane < blk0 - a) { int j = wr_find(t, n, a + lane); out[a + lane] = wr_byte_at(t, j, a + lane, ref, ref_len); }     // head
     const int blk1 = blk0 + ((b - blk0) & ~15);
-    for (int blk = blk0 + lane * 16; blk < blk1; blk += 32 * 16) {
-        int j = wr_find(t, n, blk);
+    for (int s0 = blk0 + lane * 32; s0 < blk1; s0 += 32 * 32) {
+        int j = wr_find(t, n, s0);
         int cur = t.ri[j], nxt = t.ri[j + 1];                  // the op that holds the next byte, kept in registers
         long long rp = t.rp[j];
-        uint32_t w[4];
-        const long long p16 = rp + (blk - cur);
-        if (nxt - blk >= 16 && p16 >= 0 && p16 + 20 <= ref_len) {
-            // the whole block is one run of reference bytes: 16 unaligned bytes = five aligned words + funnel shifts
-            const uintptr_t addr = (uintptr_t)(ref + p16);
-            const uint32_t* src = (const uint32_t*)(addr & ~(uintptr_t)3);
-            const int sh = (int)(addr & 3) * 8;
-            const uint32_t r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
-            const uint32_t r4 = sh ? __ldg(src + 4) : 0u;      // not touched when the run is word aligned (may end the array)
-            w[0] = __funnelshift_r(r0, r1, sh); w[1] = __funnelshift_r(r1, r2, sh);
-            w[2] = __funnelshift_r(r2, r3, sh); w[3] = __funnelshift_r(r3, r4, sh);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t x = 0;
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int idx = blk + 4 * q + e;
-                    while (idx >= nxt) { j++; cur = nxt; nxt = t.ri[j + 1]; rp = t.rp[j]; }
-                    const long long p = rp + (idx - cur);
-                    x |= (uint32_t)((p >= 0 && p < ref_len) ? __ldg(ref + p) : (uint8_t)'A') << (8 * e);
+#pragma unroll 1
+        for (int blk = s0; blk < s0 + 32 && blk < blk1; blk += 16) {
+            unsigned long long lo = 0ull, hi = 0ull;           // bytes 0..7 and 8..15 of the block
+            int e = 0;
+            while (e < 16) {
+                const int idx = blk + e;
+                while (idx >= nxt) { j++; cur = nxt; nxt = t.ri[j + 1]; rp = t.rp[j]; }
+                int run = nxt - idx; if (run > 16 - e) run = 16 - e;
+                const long long q = rp + (idx - cur) - e;      // reference position that lines up with byte 0 of the block
+                unsigned long long v_lo, v_hi;
+                if (q >= 0 && q + 20 <= ref_len) {
+                    const uintptr_t addr = (uintptr_t)(ref + q);
+                    const uint32_t* src = (const uint32_t*)(addr & ~(uintptr_t)3);
+                    const int sh = (int)(addr & 3) * 8;
+                    const uint32_t r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3), r4 = __ldg(src + 4);
+                    v_lo = (unsigned long long)__funnelshift_r(r0, r1, sh) | ((unsigned long long)__funnelshift_r(r1, r2, sh) << 32);
+                    v_hi = (unsigned long long)__funnelshift_r(r2, r3, sh) | ((unsigned long long)__funnelshift_r(r3, r4, sh) << 32);
+                } else if (rp < -(1ll << 61)) {                // no reference behind this op (insert, soft clip): 'A'
+                    v_lo = v_hi = 0x4141414141414141ull;
+                } else {                                       // a run at the edge of the region's reference: byte by byte
+                    v_lo = v_hi = 0ull;
+                    for (int u = e; u < e + run; u++) {
+                        const long long pos = q + u;
+                        const unsigned long long c = (pos >= 0 && pos < ref_len) ? __ldg(ref + pos) : (uint8_t)'A';
+                        if (u < 8) v_lo |= c << (8 * u); else v_hi |= c << (8 * (u - 8));
+                    }
                 }
-                w[q] = x;
+                const int e1 = e + run;
+                const unsigned long long m_lo = wr_bytes_below(e1 < 8 ? e1 : 8) & ~wr_bytes_below(e < 8 ? e : 8);
+                const unsigned long long m_hi = wr_bytes_below(e1 > 8 ? e1 - 8 : 0) & ~wr_bytes_below(e > 8 ? e - 8 : 0);
+                lo |= v_lo & m_lo; hi |= v_hi & m_hi;
+                e = e1;
             }
+            *(uint4*)(out + blk) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
         }
-        *(uint4*)(out + blk) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     if (lane < b - blk1) { int j = wr_find(t, n, blk1 + lane); out[blk1 + lane] = wr_byte_at(t, j, blk1 + lane, ref, ref_len); }   // tail
 }

@@ -208,15 +208,14 @@ class ReadBatch:
         return self
 
     def pack_wire(self, threads: int = 0, pinned: bool = False, bases_ref: Optional[bool] = None) -> "ReadBatch":
-        """All compact (lossless) wire forms: 2-bit bases + exceptions (else 4-bit when the alphabet allows), bit-packed
-        qualities, 16-bit CIGAR. ``bases_ref=True`` (or PV_WIRE_BASES_REF=1) sends the bases in the reference-predicted
-        form instead when that is smaller: ~0.6 bits per base at ONT error rates, but its expansion kernel costs more
-        device time than the 2-bit form, so it pays where the upload is the bottleneck by a wide margin (several GPUs
-        sharing the host's H2D bandwidth), not on one GPU."""
+        """All compact (lossless) wire forms: reference-predicted bases when that is the smallest form (~0.6 bits per base
+        at ONT error rates), else 2-bit bases + exceptions (else 4-bit when the alphabet allows); bit-packed qualities;
+        16-bit CIGAR. ``bases_ref=False`` (or PV_WIRE_BASES_REF=0) keeps the bases in the 2-bit form, whose expansion
+        kernel is 6x cheaper (it pays when the device, not the upload, is the bottleneck)."""
         from . import capi
         import os
         if bases_ref is None:
-            bases_ref = os.environ.get("PV_WIRE_BASES_REF", "0") == "1"
+            bases_ref = os.environ.get("PV_WIRE_BASES_REF", "1") == "1"
         self.pack_bases2(threads, pinned)
         if bases_ref:
             self.pack_bases_ref(threads, pinned)
