@@ -368,7 +368,7 @@ def run_ours(args):
                            "reference-predicted + patch list" if batch.bases_patch is not None else (
                                "2-bit + exception list" if batch.bases2 is not None else ("4-bit (BAM nt16)" if batch.bases4 is not None else "u8")),
                            "%d-bit packed" % batch.qual_bits if batch.quals_packed is not None else "u8",
-                           "u16" if batch.cigar16 is not None else "u32 (BAM)")},
+                           "8-bit codes + escapes" if batch.cigar8 is not None else ("u16" if batch.cigar16 is not None else "u32 (BAM)"))},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mbp/s", "h2d_bytes_per_step": int(input_bytes),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 2)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_summary": roof_summary, "roofline_inference": roof_inference,

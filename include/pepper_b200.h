@@ -178,6 +178,15 @@ int pv_pack_bases_ref(const PvReadBatch* host_batch, int64_t* read_patch_off_hos
                       int64_t patch_capacity, int32_t threads);
 int pv_unpack_bases_ref(const PvReadBatch* batch_dev_ptrs, const int64_t* read_patch_off_dev, const uint16_t* patches_dev,
                         uint8_t* bases_dev, void* stream);
+/* 8-bit CIGAR (wire form "cigar8"): one code byte c per op, indexed like cigar[] -- bit 0 = 0: M of length (c >> 1) + 1
+ * (1..128); bit 0 = 1: bits 2:1 = 0 I / 1 D of length (c >> 3) + 1 (1..32), 3 = escaped: the op's full 32-bit word is the
+ * next entry of the escape stream (other op types, longer or empty ops). Escapes of read r sit at [read_esc_off[r], read_esc_off[r + 1]). Lossless.
+ * Host: first call with escapes_host == NULL writes the code bytes and fills read_esc_off_host [n_reads + 1]; second call
+ * writes the escape words. Device: rebuilds cigar_dev[] (needs read_cigar_off / read_n_ops on the device). */
+int pv_pack_cigar8(const PvReadBatch* host_batch, uint8_t* codes_host, int64_t* read_esc_off_host, uint32_t* escapes_host,
+                   int64_t escape_capacity, int32_t threads);
+int pv_unpack_cigar8(const PvReadBatch* batch_dev_ptrs, const uint8_t* codes_dev, const int64_t* read_esc_off_dev,
+                     const uint32_t* escapes_dev, uint32_t* cigar_dev, void* stream);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 

@@ -7,8 +7,9 @@
 //
 // Kernels (one stream, no host synchronisation except reading back the row count):
 //   P0 polish_prefix_kernel   warp per read: CIGAR prefix (here REF_SKIP / PAD advance only the reference, :98-113)
-//   P1 polish_count_kernel    warp per read, lane per op: base / deletion counts, coverage (incl. the reference's quirk
-//                             of charging a deletion's coverage to the op's first position, :108), longest insert
+//   P1 polish_tile_kernel     CTA per tile of 1536 positions, counters in shared memory: base / deletion counts, coverage
+//                             (incl. the reference's quirk of charging a deletion's coverage to the op's first position,
+//                             :108), longest insert
 //   -- cub exclusive scan of (1 + longest insert) -> first output row of every position
 //   P2 polish_insert_kernel   warp per read, lane per insert op: counts of the inserted columns
 //   P3 polish_emit_kernel     thread per position: normalise (double arithmetic, uint8 conversion as x86 does it) and
@@ -68,9 +69,9 @@ struct PolishArgs {
     uint32_t* ins_cnt;             // [rows][NF] (only insert rows are touched)
 };
 
-// MODE 0: P1 (bases, deletions, coverage, longest insert); MODE 1: P2 (inserted columns)
-template <int MODE>
-__global__ void polish_walk_kernel(const PolishArgs a) {
+// P2: counts of the inserted columns (warp per read, lane per insert op). Inserted bases are ~1.5 % of the bases at ONT
+// error rates and their rows are spread over the whole output, so this stays on global atomics.
+__global__ void polish_insert_kernel(const PolishArgs a) {
     const PvReadBatch& b = a.b;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -90,36 +91,17 @@ __global__ void polish_walk_kernel(const PolishArgs a) {
             const int k = k0 + lane;
             if (k >= n_ops) break;
             const uint32_t w = b.cigar[co + k];
-            const int op = (int)(w & 15u);
+            if ((w & 15u) != 1u) continue;                                          // :79-96
             const int64_t len = (int64_t)(w >> 4);
             const int64_t p0 = rel + a.op_ref[co + k];                              // region-local reference position
             const int64_t ri = a.op_ri[co + k];
             if (p0 > L - 1) continue;                                               // `if (ref_position > region_end) break`, :55
-            if (MODE == 0 && is_m(op)) {                                            // :57-78
-                int64_t i = p0 < 0 ? -p0 : 0;
-                int64_t i_hi = len; if (i_hi > L - p0) i_hi = L - p0; if (i_hi > read_len - ri) i_hi = read_len - ri;
-                for (; i < i_hi; i++) {
-                    atomicAdd(&a.cnt[(g0 + p0 + i) * NF + feature_index(b.bases[bo + ri + i], rev)], 1u);
-                    atomicAdd(&a.cov[g0 + p0 + i], 1u);
-                }
-            } else if (op == 1) {                                                   // :79-96
-                const int64_t an = p0 - 1;
-                if (an < 0 || an > L - 1 || ri > read_len) continue;                // substr(read_index > size) throws in the reference
-                int64_t alen = len; if (alen > read_len - ri) alen = read_len - ri; // substr truncation
-                if (MODE == 0) { if (alen > 0) atomicMax(&a.longest[g0 + an], (uint32_t)alen); }
-                else {
-                    const int64_t row = a.row_of[g0 + an] + 1;
-                    for (int64_t i = 0; i < alen; i++)
-                        atomicAdd(&a.ins_cnt[(row + i) * NF + feature_index(b.bases[bo + ri + i], rev)], 1u);
-                }
-            } else if (MODE == 0 && (op == 2 || op == 3 || op == 6)) {               // :97-113
-                const int64_t i_lo = p0 < 0 ? -p0 : 0;
-                int64_t i_hi = len; if (i_hi > L - p0) i_hi = L - p0;
-                const int star = feature_index('*', rev);
-                for (int64_t i = i_lo; i < i_hi; i++) atomicAdd(&a.cnt[(g0 + p0 + i) * NF + star], 1u);
-                // the reference adds this coverage at ref_position (the op's start), once per in-range deleted base
-                if (i_hi > i_lo && p0 >= 0) atomicAdd(&a.cov[g0 + p0], (uint32_t)(i_hi - i_lo));
-            }
+            const int64_t an = p0 - 1;
+            if (an < 0 || an > L - 1 || ri > read_len) continue;                    // substr(read_index > size) throws in the reference
+            int64_t alen = len; if (alen > read_len - ri) alen = read_len - ri;     // substr truncation
+            const int64_t row = a.row_of[g0 + an] + 1;
+            for (int64_t i = 0; i < alen; i++)
+                atomicAdd(&a.ins_cnt[(row + i) * NF + feature_index(b.bases[bo + ri + i], rev)], 1u);
         }
     }
 }
@@ -439,7 +421,7 @@ extern "C" int pv_polish_emit(const PvReadBatch* batch, const int64_t* region_le
     pv::prof_begin(pv::FAM_POLISH, st);
     if (b.n_reads > 0) {
         int64_t blocks = (b.n_reads + 7) / 8; if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-        polish_walk_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(a);
+        polish_insert_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     }
     polish_emit_kernel<<<(unsigned)((total_positions + 255) / 256), 256, 0, st>>>(a, total_positions, pos_region, image_dev, gpos_dev, row_region_dev);
     PV_CUDA_CHECK(cudaGetLastError());

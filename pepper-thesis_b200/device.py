@@ -35,6 +35,8 @@ class DeviceBatch:
         self.packed_q = None        # bit-packed qualities
         self.packed_c = None        # 16-bit CIGAR words
         self.patches = None         # reference-predicted bases: patch entries (offsets travel with the small arrays)
+        self.codes8 = None          # 8-bit CIGAR codes
+        self.esc8 = None            # ... and their escape words (offsets travel with the small arrays)
         self._unpacked = True
         small = []
         for name in ARRAY_NAMES:
@@ -70,6 +72,13 @@ class DeviceBatch:
                 self.t[name] = torch.empty(a.size + 16, dtype=torch.uint8, device=self.device)[:a.size]
                 self._unpacked = False
                 continue
+            if name == "cigar" and host.cigar8 is not None and a.size:
+                self.codes8 = torch.from_numpy(host.cigar8).to(self.device, non_blocking=non_blocking)
+                esc = host.cigar_esc if host.cigar_esc.size else np.zeros(1, np.uint32)
+                self.esc8 = torch.from_numpy(esc.view(np.int32)).to(self.device, non_blocking=non_blocking)
+                self.t[name] = torch.empty(a.size, dtype=torch.int32, device=self.device)
+                self._unpacked = False
+                continue
             if name == "cigar" and host.cigar16 is not None and a.size:
                 self.packed_c = torch.from_numpy(host.cigar16.view(np.int16)).to(self.device, non_blocking=non_blocking)
                 self.t[name] = torch.empty(a.size, dtype=torch.int32, device=self.device)
@@ -84,6 +93,8 @@ class DeviceBatch:
         # through ONE pinned staging buffer and one copy; the device tensors are views of one allocation
         if self.patches is not None:
             small.append("read_patch_off")
+        if self.codes8 is not None:
+            small.append("read_esc_off")
         offs, total = {}, 0
         for name in small:
             offs[name] = total
@@ -111,7 +122,11 @@ class DeviceBatch:
             return
         lib = capi.load()
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        if self.packed_c is not None:           # first: the base prediction below walks the CIGAR
+        if self.codes8 is not None:             # first: the base prediction below walks the CIGAR
+            capi.check(lib.pv_unpack_cigar8(C.byref(self.struct), C.c_void_p(self.codes8.data_ptr()),
+                                            C.c_void_p(self.t["read_esc_off"].data_ptr()), C.c_void_p(self.esc8.data_ptr()),
+                                            C.c_void_p(self.t["cigar"].data_ptr()), st))
+        if self.packed_c is not None:
             out = self.t["cigar"]
             capi.check(lib.pv_unpack_cigar16(C.c_void_p(self.packed_c.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
         if self.patches is not None:
@@ -132,7 +147,7 @@ class DeviceBatch:
         self._unpacked = True
 
     def record_stream(self, stream):
-        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self.patches, self._small_dev) if x is not None]:
+        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self.patches, self.codes8, self.esc8, self._small_dev) if x is not None]:
             t.record_stream(stream)
 
     @property
@@ -146,7 +161,9 @@ class DeviceBatch:
             n -= self.host.bases.nbytes - self.host.bases4.nbytes
         if self.packed_q is not None:
             n -= self.host.quals.nbytes - min((self.host.quals.size * self.host.qual_bits + 7) // 8, self.host.quals_packed.nbytes)
-        if self.packed_c is not None:
+        if self.codes8 is not None:
+            n -= self.host.cigar.nbytes - self.host.cigar8.nbytes - self.host.cigar_esc.nbytes - self.host.read_esc_off.nbytes
+        elif self.packed_c is not None:
             n -= self.host.cigar.nbytes - self.host.cigar16.nbytes
         return n
 

@@ -66,6 +66,9 @@ class ReadBatch:
     cigar16: Optional[np.ndarray] = None     # optional low 16 bits of every CIGAR word (all op lengths < 4096)
     bases2: Optional[np.ndarray] = None      # optional 2-bit packing of `bases` (n_bases / 4 bytes) ...
     base_exceptions: Optional[np.ndarray] = None   # ... + uint64 (index << 8 | byte) of every base that is not A/C/G/T
+    cigar8: Optional[np.ndarray] = None      # optional 8-bit CIGAR codes (one byte per op) ...
+    cigar_esc: Optional[np.ndarray] = None   # ... + the full uint32 words of the ops that do not fit a code byte ...
+    read_esc_off: Optional[np.ndarray] = None   # ... of read r at [read_esc_off[r], read_esc_off[r + 1])
     bases_patch: Optional[np.ndarray] = None    # optional reference-predicted form of `bases`: uint16 patch entries ...
     read_patch_off: Optional[np.ndarray] = None  # ... of read r at [read_patch_off[r], read_patch_off[r + 1])
 
@@ -167,6 +170,27 @@ class ReadBatch:
         self.cigar16 = out
         return self
 
+    def pack_cigar8(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the 8-bit wire form of the CIGAR (pv_pack_cigar8): one code byte per M/I/D op of length 1..64, the full
+        word of every other op in a separate escape stream."""
+        from . import capi
+        import os
+        lib = capi.load()
+        threads = threads or min(32, os.cpu_count() or 1)
+        if self.n_ops == 0 or self.n_reads == 0:
+            return self
+        st = self.as_struct()
+        self._cigar8_owner, codes = self._host_buffer(self.n_ops, pinned)
+        off = np.zeros(self.n_reads + 1, np.int64)
+        capi.check(lib.pv_pack_cigar8(C.byref(st), codes.ctypes.data, off.ctypes.data, None, 0, threads))
+        total = int(off[-1])
+        self._cigar_esc_owner, esc = self._host_buffer(max(4, total * 4), pinned)
+        esc = esc[:total * 4].view(np.uint32)
+        if total:
+            capi.check(lib.pv_pack_cigar8(C.byref(st), codes.ctypes.data, off.ctypes.data, esc.ctypes.data, total, threads))
+        self.cigar8, self.cigar_esc, self.read_esc_off = codes, esc, off
+        return self
+
     def pack_bases2(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
         """Adds the 2-bit wire form of the bases + the list of bases that are not upper-case A/C/G/T (any byte value is
         representable). Left alone when the exception list would cost more than 2-bit packing saves over 4 bits."""
@@ -231,7 +255,17 @@ class ReadBatch:
                 self.pack_bases4(threads, pinned)
             except capi.PvError:
                 self.bases4 = None
-        return self.pack_quals(threads, pinned).pack_cigar16(threads, pinned)
+        self.pack_quals(threads, pinned).pack_cigar16(threads, pinned)
+        if os.environ.get("PV_WIRE_CIGAR8", "1") == "1":
+            self.pack_cigar8(threads, pinned)
+            if self.cigar8 is not None:
+                c8 = self.cigar8.nbytes + self.cigar_esc.nbytes + self.read_esc_off.nbytes
+                other = self.cigar16.nbytes if self.cigar16 is not None else self.cigar.nbytes
+                if c8 < other:
+                    self.cigar16, self._cigar16_owner = None, None
+                else:
+                    self.cigar8, self.cigar_esc, self.read_esc_off = None, None, None
+        return self
 
     def pin_uploaded(self) -> "ReadBatch":
         """Moves the big arrays the host path actually uploads (the packed wire forms are allocated pinned by
@@ -243,7 +277,7 @@ class ReadBatch:
             names.append("bases")
         if self.quals_packed is None:
             names.append("quals")
-        if self.cigar16 is None:
+        if self.cigar16 is None and self.cigar8 is None:
             names.append("cigar")
         self._pinned_owners = getattr(self, "_pinned_owners", {})
         for name in names:
@@ -313,6 +347,10 @@ class ReadBatch:
             cigar16=self.cigar16[c_lo:c_hi] if self.cigar16 is not None else None,
             bases2=self.bases2[b_lo // 4:b_hi // 4] if self.bases2 is not None else None,
             base_exceptions=self._exceptions_view(b_lo, b_hi),
+            cigar8=self.cigar8[c_lo:c_hi] if self.cigar8 is not None else None,
+            cigar_esc=(self.cigar_esc[int(self.read_esc_off[rb]):int(self.read_esc_off[re_])]
+                       if self.cigar8 is not None else None),
+            read_esc_off=(self.read_esc_off[rb:re_ + 1] - self.read_esc_off[rb] if self.cigar8 is not None else None),
             bases_patch=(self.bases_patch[int(self.read_patch_off[rb]):int(self.read_patch_off[re_])]
                          if self.bases_patch is not None else None),
             read_patch_off=(self.read_patch_off[rb:re_ + 1] - self.read_patch_off[rb]

@@ -229,6 +229,28 @@ def test_bases_ref_roundtrip():
     assert np.array_equal(ws.windows[:k].cpu().numpy().astype(np.int32), np.asarray(want["images"]).astype(np.int32))
 
 
+def test_cigar8_roundtrip():
+    """8-bit CIGAR codes + escape stream (pv_pack_cigar8 / pv_unpack_cigar8): the device CIGAR equals the original for
+    fuzzed op mixes (S, N, =, X, long and empty ops), the synthetic presets and region views."""
+    import torch
+    from pepper_thesis_b200 import device as dev
+    big = synth.generate("ont_r9", 350000, 12.0, seed=4)
+    for batch in [H.fuzz_region(s) for s in range(6)] + [big, synth.generate("hifi", 150000, 6.0, seed=2)]:
+        batch.pack_cigar8()
+        assert batch.cigar8 is not None and int(batch.read_esc_off[-1]) == batch.cigar_esc.size
+        for v in ([batch] if batch is not big else [batch, big.region_range_view(1, 3), big.region_range_view(2, 3)]):
+            db = dev.DeviceBatch(v)
+            torch.cuda.synchronize()
+            got = db.t["cigar"].cpu().numpy().view(np.uint32)
+            for i in range(v.n_reads):
+                o, n = int(v.read_cigar_off[i]), int(v.read_n_ops[i])
+                assert np.array_equal(got[o:o + n], v.cigar[o:o + n]), "read %d" % i
+    big.pack_wire()
+    assert big.cigar8 is not None and big.cigar16 is None and big.bases_patch is not None
+    db = _assert_device_bases_equal(big)            # the base prediction walks the CIGAR rebuilt from the codes
+    assert db.h2d_bytes < 0.45 * sum(getattr(big, n).nbytes for n in ("bases", "quals", "cigar"))
+
+
 def test_bases2_exceptions_roundtrip():
     """2-bit bases with every kind of odd byte (N, lower case, '=', 255) in the exception list; views re-base the list."""
     import torch

@@ -73,3 +73,44 @@ def test_patch_lists_decode_synthetic_and_views():
         g = bisect.bisect_right(vs, r) - 1
         o, L = int(v.read_base_off[r]), int(v.read_len[r])
         assert np.array_equal(_decode(v, r, _predict(v, r, g)), v.bases[o:o + L])
+
+
+def _decode_cigar8(b):
+    out = np.zeros(b.n_ops, np.uint32)
+    for r in range(b.n_reads):
+        co, n, e = int(b.read_cigar_off[r]), int(b.read_n_ops[r]), int(b.read_esc_off[r])
+        for k in range(n):
+            c = int(b.cigar8[co + k])
+            if c & 7 == 7:
+                out[co + k] = b.cigar_esc[e]; e += 1
+            elif c & 1:
+                out[co + k] = (((c >> 3) + 1) << 4) | (((c >> 1) & 3) + 1)
+            else:
+                out[co + k] = ((c >> 1) + 1) << 4
+        assert e == int(b.read_esc_off[r + 1])
+    return out
+
+
+def test_cigar8_codes_decode():
+    """pv_pack_cigar8: code bytes + escape stream decode back to the CIGAR words (Python restatement of the format in
+    include/pepper_b200.h), incl. the length limits (M 128, I/D 32), other op types, empty ops and region views."""
+    b = synth.generate("ont_r9", 200000, 8.0, seed=4)
+    # force edge lengths / op types into the first read's ops
+    co = int(b.read_cigar_off[0])
+    edge = [(128 << 4) | 0, (129 << 4) | 0, (32 << 4) | 1, (33 << 4) | 1, (32 << 4) | 2, (33 << 4) | 2, (5 << 4) | 4, (7 << 4) | 3,
+            (0 << 4) | 0, (9 << 4) | 7, (9 << 4) | 8, (1 << 4) | 0, (1 << 4) | 1, (1 << 4) | 2]
+    keep = b.cigar[co:co + len(edge)].copy()
+    b.cigar[co:co + len(edge)] = np.array(edge, np.uint32)
+    b.pack_cigar8(threads=3)
+    used = np.zeros(b.n_ops, bool)
+    for r in range(b.n_reads):
+        used[int(b.read_cigar_off[r]):int(b.read_cigar_off[r]) + int(b.read_n_ops[r])] = True
+    assert np.array_equal(_decode_cigar8(b)[used], b.cigar[used])
+    assert b.cigar8.nbytes + b.cigar_esc.nbytes + b.read_esc_off.nbytes < 1.2 * b.n_ops       # ~1.05 bytes per op
+    v = b.region_range_view(1, 2)
+    vused = np.zeros(v.n_ops, bool)
+    for r in range(v.n_reads):
+        vused[int(v.read_cigar_off[r]):int(v.read_cigar_off[r]) + int(v.read_n_ops[r])] = True
+    assert int(v.read_esc_off[0]) == 0 and int(v.read_esc_off[-1]) == v.cigar_esc.size
+    assert np.array_equal(_decode_cigar8(v)[vused], v.cigar[vused])
+    b.cigar[co:co + len(edge)] = keep
