@@ -11,6 +11,8 @@ records (``gather_to_rank0``), exactly like the reference concatenates per-proce
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -274,7 +276,7 @@ class HotPath:
         self._acc_buffer(self.infer_batch * 2)
         # uploads are queued `ahead` groups in front of the kernels: the copy stream never waits for the host (which
         # blocks on every group's candidate count), so the copies run back to back at PCIe speed
-        ahead = 4
+        ahead = int(os.environ.get("PV_HOST_AHEAD", "4"))
         queue = [upload(groups[j]) for j in range(min(ahead, len(groups)))]
         for i, g in enumerate(groups):
             db, ev = queue.pop(0)
