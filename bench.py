@@ -277,6 +277,38 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = bp * world * args.steps / (float(t.item()) / 1e3) / 1e6
 
+    # ---- the same end-to-end call with the qualities travelling as PREDICATES (pv_pack_quals_pred: identical summaries
+    # and candidates for these thresholds, the qualities themselves stay on the host). Reported beside `e2e`, which
+    # stays on the lossless wire forms. ----------------------------------------------------------------------------------
+    e2e_qp = None
+    if os.environ.get("PV_BENCH_QUALS_PRED", "1") == "1":
+        import copy
+        bq = copy.copy(batch)
+        bq.pack_quals_pred(thr.min_snp_baseq, thr.min_indel_baseq, threads=gen_threads, pinned=True)
+        if bq.quals_patch is not None:
+            qp_bytes = input_bytes + bq.quals_patch.nbytes + bq.read_qpatch_off.nbytes - (
+                min((batch.quals.size * batch.qual_bits + 7) // 8, batch.quals_packed.nbytes) if batch.quals_packed is not None else batch.quals.nbytes)
+            bq.quals_packed, bq.qual_bits = None, 0
+            for _ in range(max(args.warmup, 3)):
+                pred_q = hp.run_host(bq, rank * n_regions)
+            same = (len(pred_q) == len(pred) and np.array_equal(pred_q.position, pred.position)
+                    and np.array_equal(pred_q.allele, pred.allele) and np.array_equal(pred_q.genotype, pred.genotype))
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                hp.run_host(bq, rank * n_regions)
+            e1.record()
+            barrier()
+            tq = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+            e2e_qp = {"value": round(bp * world * args.steps / (float(tq.item()) / 1e3) / 1e6, 2), "unit": "Mbp/s",
+                      "h2d_bytes_per_step": int(qp_bytes), "ms_per_step": round(float(tq.item()) / args.steps, 2),
+                      "same_candidates_and_genotypes_as_e2e": bool(same),
+                      "wire": "qualities as threshold predicates: fill byte %d + %d patch entries (min_snp_baseq %g, min_indel_baseq %g); "
+                              "summaries bit-identical, qualities not recoverable" % (bq.quals_fill, bq.quals_patch.size, thr.min_snp_baseq, thr.min_indel_baseq)}
+        del bq
+
     # ---- roofline of the dominant kernel (CUDA events recorded inside the timed region, per family) -----------------
     peaks = {}
     try:
@@ -371,6 +403,7 @@ def run_ours(args):
                            "8-bit codes + escapes" if batch.cigar8 is not None else ("u16" if batch.cigar16 is not None else "u32 (BAM)"))},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mbp/s", "h2d_bytes_per_step": int(input_bytes),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 2)},
+            "e2e_quals_pred": e2e_qp,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_summary": roof_summary, "roofline_inference": roof_inference,
             "kernel_ms_per_step": {f: round(v / args.steps, 3) for f, v in fam_ms.items() if v > 0},
             "cpu_baseline": cpu}

@@ -187,6 +187,19 @@ int pv_pack_cigar8(const PvReadBatch* host_batch, uint8_t* codes_host, int64_t* 
                    int64_t escape_capacity, int32_t threads);
 int pv_unpack_cigar8(const PvReadBatch* batch_dev_ptrs, const uint8_t* codes_dev, const int64_t* read_esc_off_dev,
                      const uint32_t* escapes_dev, uint32_t* cigar_dev, void* stream);
+/* Quality predicates (wire form "quals_pred"; csrc/wire_ref.cu). The summary reads a base quality only through
+ * `q >= min_snp_baseq` (region_summary.cpp:377,:393) and, per insert, `sum q[anchor .. anchor+len] >= min_indel_baseq *
+ * (len + 1)` with `q[anchor] < min_snp_baseq` (:448-463). With the thresholds known at pack time the device quality array
+ * is rebuilt as one fill byte + a per-read patch list (entry format of bases_ref) of SURROGATE values wherever the fill
+ * value would change one of those predicates (irregular inserts -- chained, behind a deletion/clip, over the read's end --
+ * carry their real qualities). Every predicate evaluates identically on the surrogate array, so summaries and candidates are
+ * bit-identical; the qualities themselves are NOT recoverable, and the form is tied to the two thresholds it was packed
+ * for (both <= 127, else PV_EINVAL). Two-call protocol like pv_pack_bases_ref; *fill_out receives the fill byte.
+ * Device: needs read_base_off / read_len on the device; n_bases % 16 == 0. */
+int pv_pack_quals_pred(const PvReadBatch* host_batch, double min_snp_baseq, double min_indel_baseq, uint8_t* fill_out,
+                       int64_t* read_patch_off_host, uint16_t* patches_host, int64_t patch_capacity, int32_t threads);
+int pv_unpack_quals_pred(const PvReadBatch* batch_dev_ptrs, int32_t fill, const int64_t* read_patch_off_dev,
+                         const uint16_t* patches_dev, uint8_t* quals_dev, void* stream);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 

@@ -57,7 +57,7 @@ enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_ba
        C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count of bases that are no dense SNP allele
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
-enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_COUNT = 8 };
+enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_COUNT = 8 };
 enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8 };
 enum { PF_SITE = 1, PF_SNP = 2, PF_INS = 4, PF_DEL = 8, PF_OTHER = 16 };
 
@@ -149,12 +149,16 @@ __device__ int warp_lower_bound(const int32_t* __restrict__ a, int n, int64_t ke
 // ------------------------------------------------------------------------------------------------------------
 // Each lane takes FOUR consecutive ops (one 16-byte load, two 16-byte stores), so a warp step covers 128 ops with a
 // single pair of shuffle scans. Ops are indexed from the 16-byte aligned slot at or below the read's first op.
+// Reads come from a ticket counter: their op counts are heavy-tailed (1 .. 100 kbp reads), a fixed stride leaves the kernel
+// waiting for the unluckiest warp.
 __global__ void cigar_prefix_kernel(PvReadBatch b, int32_t* __restrict__ op_ref, int32_t* __restrict__ op_ri,
-                                    int32_t* __restrict__ read_span) {
+                                    int32_t* __restrict__ read_span, int32_t* __restrict__ ticket) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < b.n_reads; r += n_warps) {
+    while (true) {
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1);
+        const int64_t r = __shfl_sync(0xffffffffu, tk, 0);
+        if (r >= b.n_reads) break;
         const int64_t co = b.read_cigar_off[r];
         const int n_ops = b.read_n_ops[r];
         const int64_t co_al = co & ~(int64_t)3;                 // aligned slot; ops before `co` belong to the previous read
@@ -1100,7 +1104,7 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
         int64_t blocks = (b.n_reads + 7) / 8;            // 8 warps per 256-thread block
         if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
         pv::prof_begin(pv::FAM_SUM_PREFIX, stream);
-        cigar_prefix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b, w.op_ref, w.op_ri, w.read_span);
+        cigar_prefix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b, w.op_ref, w.op_ri, w.read_span, w.ctr + CTR_K0_TICKET);
         PV_CUDA_CHECK(cudaGetLastError());
         pv::prof_end(pv::FAM_SUM_PREFIX, stream, 1);
     }

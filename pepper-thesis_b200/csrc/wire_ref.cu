@@ -14,6 +14,7 @@
 // be the SAME in pv_pack_bases_ref (host) and pv_unpack_bases_ref (device); it is not the reference's CIGAR walk.
 #include "common.cuh"
 #include <atomic>
+#include <cmath>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -388,6 +389,146 @@ extern "C" int pv_unpack_cigar8(const PvReadBatch* dev_batch, const uint8_t* cod
     const int64_t cap = (int64_t)pv::sm_count() * 16;
     if (blocks > cap) blocks = cap;
     unpack_cigar8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, codes_dev, read_esc_off_dev, escapes_dev, cigar_dev);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Quality predicates ("quals_pred" wire form). The summary reads a base quality in exactly two places
+// (/root/reference/pepper_variant/modules/cpp/region_summary.cpp): `q >= min_snp_baseq` for an aligned base (:367,:377,
+// :393) and, for an insert, `sum q[anchor .. anchor+len] >= min_indel_baseq * (len + 1)` together with
+// `q[anchor] < min_snp_baseq` (:448-463). When the thresholds are known at pack time the qualities themselves need not
+// travel: the device array is rebuilt as ONE fill value F = max(ceil(min_snp_baseq), ceil(min_indel_baseq)) plus a
+// per-read patch list (the entry format of bases_ref) holding SURROGATE values wherever F would change one of those
+// predicates:
+//     aligned base below the SNP threshold                          -> 0
+//     insert whose sum fails:   inserted bases -> 0, anchor -> ceil(min_snp_baseq) if it passes the SNP test, else 0
+//     insert whose sum passes but whose anchor fails the SNP test:  inserted bases -> 255 (anchor already 0)
+//     any insert that is not "M-run, insert, then a read-consuming op that is no insert" (chained inserts, insert after
+//     a deletion or clip, empty inserts, inserts running over the read's end): the REAL qualities of anchor + insert
+// Every predicate the summary evaluates has the same truth value on the surrogate array as on the real qualities (both
+// thresholds must be <= 127 so that 255 * len >= thr * (len + 1)); the qualities themselves are NOT recoverable. The read
+// index follows the reference's walk, including the N/P fall-through (:556-561).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct QpThr { double snp, indel; int fill, amin; };
+
+inline bool qp_read_consuming(int op) { return wr_match(op) || op == 4 || op == 3 || op == 6; }   // M = X S, and N P by fall-through
+
+// surrogate qualities of read r into s[0 .. read_len)
+void qp_surrogate_read(const PvReadBatch& b, int64_t r, const QpThr& t, std::vector<uint8_t>& s) {
+    const int read_len = b.read_len[r], n_ops = b.read_n_ops[r];
+    const uint8_t* q = b.quals + b.read_base_off[r];
+    const uint32_t* cg = b.cigar + b.read_cigar_off[r];
+    s.assign((size_t)read_len, (uint8_t)t.fill);
+    int64_t ri = 0;
+    for (int k = 0; k < n_ops; k++) {
+        const int op = (int)(cg[k] & 15u);
+        const int64_t len = (int64_t)(cg[k] >> 4);
+        if (wr_match(op)) {
+            for (int64_t i = ri; i < ri + len && i < read_len; i++)
+                if (!((double)q[i] >= t.snp)) s[(size_t)i] = 0;
+            ri += len;
+        } else if (op == 1) {
+            if (ri >= 1 && ri - 1 < read_len) {
+                bool simple = k > 0 && wr_match((int)(cg[k - 1] & 15u)) && (cg[k - 1] >> 4) != 0u && len >= 1 && ri + len <= read_len;
+                for (int k2 = k + 1; simple && k2 < n_ops; k2++) {          // the next op that touches the read index
+                    const int op2 = (int)(cg[k2] & 15u);
+                    if (op2 == 1) simple = false;
+                    else if (qp_read_consuming(op2)) break;
+                }
+                if (simple) {
+                    int64_t bq = 0;
+                    for (int64_t i = ri - 1; i < ri + len; i++) bq += q[i];
+                    const bool pass = (double)bq >= t.indel * (double)(len + 1);
+                    const bool bit = (double)q[ri - 1] >= t.snp;
+                    if (pass && !bit) { for (int64_t i = ri; i < ri + len; i++) s[(size_t)i] = 255; }
+                    else if (!pass) {
+                        for (int64_t i = ri; i < ri + len; i++) s[(size_t)i] = 0;
+                        s[(size_t)(ri - 1)] = (uint8_t)(bit ? t.amin : 0);
+                    }
+                } else {
+                    for (int64_t i = ri - 1; i < ri + len && i < read_len; i++) s[(size_t)i] = q[i];
+                }
+            }
+            ri += len;
+        } else if (op == 4 || op == 3 || op == 6) {
+            ri += len;
+        }
+        if (ri > read_len) ri = read_len;                                 // malformed CIGAR: nothing behind the read's end is read
+    }
+}
+
+__global__ void fill_quals_kernel(uint4* __restrict__ out, int64_t n16, uint32_t word) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) out[i] = make_uint4(word, word, word, word);
+}
+
+}  // namespace
+
+extern "C" int pv_pack_quals_pred(const PvReadBatch* hb, double min_snp_baseq, double min_indel_baseq, uint8_t* fill_out,
+                                  int64_t* read_patch_off, uint16_t* patches, int64_t patch_capacity, int32_t threads) {
+    if (!hb || !read_patch_off || !fill_out) return pv::set_error(PV_EINVAL, "pv_pack_quals_pred: null argument");
+    const PvReadBatch& b = *hb;
+    if (b.n_reads && (!b.quals || !b.cigar)) return pv::set_error(PV_EINVAL, "pv_pack_quals_pred needs the plain quals and cigar arrays");
+    if (!(min_snp_baseq <= 127.0) || !(min_indel_baseq <= 127.0))
+        return pv::set_error(PV_EINVAL, "pv_pack_quals_pred: thresholds above 127 (%g, %g) cannot be represented by surrogate bytes", min_snp_baseq, min_indel_baseq);
+    QpThr t;
+    t.snp = min_snp_baseq; t.indel = min_indel_baseq;
+    const double cs = std::ceil(min_snp_baseq), ci = std::ceil(min_indel_baseq);
+    t.amin = cs < 0.0 ? 0 : (int)cs;
+    const int fi = ci < 0.0 ? 0 : (int)ci;
+    t.fill = t.amin > fi ? t.amin : fi;
+    *fill_out = (uint8_t)t.fill;
+    const bool count_only = patches == nullptr;
+    if (!count_only && read_patch_off[b.n_reads] > patch_capacity)
+        return pv::set_error(PV_EINVAL, "pv_pack_quals_pred: %lld patch entries needed, buffer holds %lld", (long long)read_patch_off[b.n_reads], (long long)patch_capacity);
+    wr_parallel(b.n_reads, threads, [&](int64_t lo, int64_t hi) {
+        std::vector<uint8_t> s;
+        for (int64_t r = lo; r < hi; r++) {
+            qp_surrogate_read(b, r, t, s);
+            uint16_t* out = count_only ? nullptr : patches + read_patch_off[r];
+            int64_t n = 0, cursor = 0;
+            const int64_t L = (int64_t)s.size();
+            for (int64_t i = 0; i < L; i++) {
+                if (s[(size_t)i] == (uint8_t)t.fill) continue;
+                int64_t gap = i - cursor;
+                n += gap / 255 + 1;
+                if (out) {
+                    while (gap >= 255) { *out++ = 255; gap -= 255; }
+                    *out++ = (uint16_t)(gap | ((uint16_t)s[(size_t)i] << 8));
+                }
+                cursor = i + 1;
+            }
+            if (count_only) read_patch_off[r + 1] = n;
+        }
+    });
+    if (count_only) {
+        read_patch_off[0] = 0;
+        for (int64_t r = 0; r < b.n_reads; r++) read_patch_off[r + 1] += read_patch_off[r];
+    }
+    return PV_OK;
+}
+
+extern "C" int pv_unpack_quals_pred(const PvReadBatch* dev_batch, int32_t fill, const int64_t* read_patch_off_dev, const uint16_t* patches_dev,
+                                    uint8_t* quals_dev, void* stream) {
+    if (!dev_batch || !quals_dev) return pv::set_error(PV_EINVAL, "pv_unpack_quals_pred: null argument");
+    const PvReadBatch& b = *dev_batch;
+    if (b.n_reads == 0 || b.n_bases == 0) return PV_OK;
+    if (!read_patch_off_dev) return pv::set_error(PV_EINVAL, "pv_unpack_quals_pred needs the patch offsets on the device");
+    if (fill < 0 || fill > 255) return pv::set_error(PV_EINVAL, "pv_unpack_quals_pred: fill value %d is no byte", fill);
+    if (b.n_bases % 16 || ((uintptr_t)quals_dev & 15)) return pv::set_error(PV_EINVAL, "pv_unpack_quals_pred: the quality array must be 16-byte aligned and a multiple of 16 long");
+    if (int rc = pv::require_device()) return rc;
+    const int64_t n16 = b.n_bases / 16;
+    int64_t fblocks = (n16 + 255) / 256;
+    const int64_t fcap = (int64_t)pv::sm_count() * 8;
+    if (fblocks > fcap) fblocks = fcap;
+    fill_quals_kernel<<<(unsigned)fblocks, 256, 0, (cudaStream_t)stream>>>((uint4*)quals_dev, n16, (uint32_t)fill * 0x01010101u);
+    int64_t blocks = (b.n_reads + 7) / 8;
+    const int64_t cap = (int64_t)pv::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    apply_patches_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, read_patch_off_dev, patches_dev, quals_dev);
     PV_CUDA_CHECK(cudaGetLastError());
     return PV_OK;
 }

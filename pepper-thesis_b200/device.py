@@ -37,6 +37,7 @@ class DeviceBatch:
         self.patches = None         # reference-predicted bases: patch entries (offsets travel with the small arrays)
         self.codes8 = None          # 8-bit CIGAR codes
         self.esc8 = None            # ... and their escape words (offsets travel with the small arrays)
+        self.qpatches = None        # quality predicates: patch entries over host.quals_fill (offsets with the small arrays)
         self._unpacked = True
         small = []
         for name in ARRAY_NAMES:
@@ -62,6 +63,13 @@ class DeviceBatch:
                 # bases travel in the BAM-native 4-bit form and are expanded on the device (pv_unpack_bases4)
                 self.packed = _to_torch(host.bases4).to(self.device, non_blocking=non_blocking)
                 self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
+                self._unpacked = False
+                continue
+            if name == "quals" and host.quals_patch is not None and a.size:
+                # surrogate qualities that keep every threshold test of the summary (pv_unpack_quals_pred)
+                src = host.quals_patch if host.quals_patch.size else np.zeros(1, np.uint16)
+                self.qpatches = torch.from_numpy(src.view(np.int16)).to(self.device, non_blocking=non_blocking)
+                self.t[name] = torch.empty(a.size + 16, dtype=torch.uint8, device=self.device)[:a.size]
                 self._unpacked = False
                 continue
             if name == "quals" and host.quals_packed is not None and a.size:
@@ -95,6 +103,8 @@ class DeviceBatch:
             small.append("read_patch_off")
         if self.codes8 is not None:
             small.append("read_esc_off")
+        if self.qpatches is not None:
+            small.append("read_qpatch_off")
         offs, total = {}, 0
         for name in small:
             offs[name] = total
@@ -140,6 +150,10 @@ class DeviceBatch:
         elif self.packed is not None:
             out = self.t["bases"]
             capi.check(lib.pv_unpack_bases4(C.c_void_p(self.packed.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), st))
+        if self.qpatches is not None:
+            capi.check(lib.pv_unpack_quals_pred(C.byref(self.struct), int(self.host.quals_fill),
+                                                C.c_void_p(self.t["read_qpatch_off"].data_ptr()), C.c_void_p(self.qpatches.data_ptr()),
+                                                C.c_void_p(self.t["quals"].data_ptr()), st))
         if self.packed_q is not None:
             out = self.t["quals"]
             capi.check(lib.pv_unpack_quals(C.c_void_p(self.packed_q.data_ptr()), out.numel(), int(self.host.qual_bits),
@@ -147,7 +161,7 @@ class DeviceBatch:
         self._unpacked = True
 
     def record_stream(self, stream):
-        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self.patches, self.codes8, self.esc8, self._small_dev) if x is not None]:
+        for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self.patches, self.codes8, self.esc8, self.qpatches, self._small_dev) if x is not None]:
             t.record_stream(stream)
 
     @property
@@ -159,6 +173,8 @@ class DeviceBatch:
             n -= self.host.bases.nbytes - self.host.bases2.nbytes - self.host.base_exceptions.nbytes
         elif self.packed is not None:
             n -= self.host.bases.nbytes - self.host.bases4.nbytes
+        if self.qpatches is not None:
+            n -= self.host.quals.nbytes - self.host.quals_patch.nbytes - self.host.read_qpatch_off.nbytes
         if self.packed_q is not None:
             n -= self.host.quals.nbytes - min((self.host.quals.size * self.host.qual_bits + 7) // 8, self.host.quals_packed.nbytes)
         if self.codes8 is not None:
@@ -203,6 +219,9 @@ def summary_regions(db: DeviceBatch, thr, ws: SummaryWorkspace, window: int = 32
     """Launch the summary kernel chain on the current stream (asynchronous; no host sync)."""
     lib = capi.load()
     t = capi.thresholds_struct(thr)
+    if db.qpatches is not None and db.host.quals_pred_thr != (float(t.min_snp_baseq), float(t.min_indel_baseq)):
+        raise capi.PvError(-1, "the batch carries quality predicates packed for thresholds %s, the summary was asked for %s"
+                           % (db.host.quals_pred_thr, (float(t.min_snp_baseq), float(t.min_indel_baseq))))
     stream = torch.cuda.current_stream(db.device).cuda_stream
     rc = lib.pv_summary_regions(C.byref(db.struct), db.region_len.ctypes.data, db.total_positions, C.byref(t), window,
                                 features, C.byref(ws.out), ws.count.data_ptr(), ws.ws.data_ptr(), ws.ws.numel(),

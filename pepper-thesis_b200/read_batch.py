@@ -71,6 +71,10 @@ class ReadBatch:
     read_esc_off: Optional[np.ndarray] = None   # ... of read r at [read_esc_off[r], read_esc_off[r + 1])
     bases_patch: Optional[np.ndarray] = None    # optional reference-predicted form of `bases`: uint16 patch entries ...
     read_patch_off: Optional[np.ndarray] = None  # ... of read r at [read_patch_off[r], read_patch_off[r + 1])
+    quals_patch: Optional[np.ndarray] = None    # optional quality-predicate form of `quals` (pv_pack_quals_pred): uint16 patch
+    read_qpatch_off: Optional[np.ndarray] = None  # entries of read r at [read_qpatch_off[r], read_qpatch_off[r + 1]) ...
+    quals_fill: int = 0                         # ... over this fill byte; valid for the thresholds in quals_pred_thr only
+    quals_pred_thr: Optional[tuple] = None      # (min_snp_baseq, min_indel_baseq) the predicate form was packed for
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -231,11 +235,40 @@ class ReadBatch:
         self.bases_patch, self.read_patch_off = out, off
         return self
 
-    def pack_wire(self, threads: int = 0, pinned: bool = False, bases_ref: Optional[bool] = None) -> "ReadBatch":
+    def pack_quals_pred(self, min_snp_baseq: float, min_indel_baseq: float, threads: int = 0, pinned: bool = False) -> "ReadBatch":
+        """Adds the quality-PREDICATE wire form (pv_pack_quals_pred): a fill byte + per-read patch entries of surrogate
+        qualities on which every quality test of the summary (region_summary.cpp:377,393,448-463) has the same outcome as
+        on the real qualities -- for these two thresholds only. Summaries / candidates are bit-identical; the qualities
+        themselves do not travel. Left alone (lossless forms stay in charge) when a threshold is above 127."""
+        from . import capi
+        import os
+        lib = capi.load()
+        threads = threads or min(32, os.cpu_count() or 1)
+        if self.n_reads == 0 or self.n_bases % 16 or not (min_snp_baseq <= 127 and min_indel_baseq <= 127):
+            return self
+        st = self.as_struct()
+        off = np.zeros(self.n_reads + 1, np.int64)
+        fill = C.c_uint8(0)
+        capi.check(lib.pv_pack_quals_pred(C.byref(st), float(min_snp_baseq), float(min_indel_baseq), C.byref(fill),
+                                          off.ctypes.data, None, 0, threads))
+        total = int(off[-1])
+        self._qpatch_owner, out = self._host_buffer(max(2, total * 2), pinned)
+        out = out[:total * 2].view(np.uint16)
+        if total:
+            capi.check(lib.pv_pack_quals_pred(C.byref(st), float(min_snp_baseq), float(min_indel_baseq), C.byref(fill),
+                                              off.ctypes.data, out.ctypes.data, total, threads))
+        self.quals_patch, self.read_qpatch_off, self.quals_fill = out, off, int(fill.value)
+        self.quals_pred_thr = (float(min_snp_baseq), float(min_indel_baseq))
+        return self
+
+    def pack_wire(self, threads: int = 0, pinned: bool = False, bases_ref: Optional[bool] = None,
+                  quals_pred: Optional[tuple] = None) -> "ReadBatch":
         """All compact (lossless) wire forms: reference-predicted bases when that is the smallest form (~0.6 bits per base
         at ONT error rates), else 2-bit bases + exceptions (else 4-bit when the alphabet allows); bit-packed qualities;
         16-bit CIGAR. ``bases_ref=False`` (or PV_WIRE_BASES_REF=0) keeps the bases in the 2-bit form, whose expansion
-        kernel is 6x cheaper (it pays when the device, not the upload, is the bottleneck)."""
+        kernel is 6x cheaper (it pays when the device, not the upload, is the bottleneck). ``quals_pred=(min_snp_baseq,
+        min_indel_baseq)`` replaces the bit-packed qualities by the quality-predicate form (``pack_quals_pred``: the
+        summary's results are unchanged, the qualities themselves are not kept -- opt-in, tied to those thresholds)."""
         from . import capi
         import os
         if bases_ref is None:
@@ -255,7 +288,11 @@ class ReadBatch:
                 self.pack_bases4(threads, pinned)
             except capi.PvError:
                 self.bases4 = None
-        self.pack_quals(threads, pinned).pack_cigar16(threads, pinned)
+        if quals_pred is not None:
+            self.pack_quals_pred(quals_pred[0], quals_pred[1], threads, pinned)
+        if self.quals_patch is None:
+            self.pack_quals(threads, pinned)
+        self.pack_cigar16(threads, pinned)
         if os.environ.get("PV_WIRE_CIGAR8", "1") == "1":
             self.pack_cigar8(threads, pinned)
             if self.cigar8 is not None:
@@ -275,7 +312,7 @@ class ReadBatch:
         names = ["ref"]
         if self.bases2 is None and self.bases4 is None and self.bases_patch is None:
             names.append("bases")
-        if self.quals_packed is None:
+        if self.quals_packed is None and self.quals_patch is None:
             names.append("quals")
         if self.cigar16 is None and self.cigar8 is None:
             names.append("cigar")
@@ -354,7 +391,12 @@ class ReadBatch:
             bases_patch=(self.bases_patch[int(self.read_patch_off[rb]):int(self.read_patch_off[re_])]
                          if self.bases_patch is not None else None),
             read_patch_off=(self.read_patch_off[rb:re_ + 1] - self.read_patch_off[rb]
-                            if self.bases_patch is not None else None))
+                            if self.bases_patch is not None else None),
+            quals_patch=(self.quals_patch[int(self.read_qpatch_off[rb]):int(self.read_qpatch_off[re_])]
+                         if self.quals_patch is not None and (b_hi - b_lo) % 16 == 0 else None),
+            read_qpatch_off=(self.read_qpatch_off[rb:re_ + 1] - self.read_qpatch_off[rb]
+                             if self.quals_patch is not None and (b_hi - b_lo) % 16 == 0 else None),
+            quals_fill=self.quals_fill, quals_pred_thr=self.quals_pred_thr)
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

@@ -274,3 +274,61 @@ def test_bases2_exceptions_roundtrip():
     for i in range(v.n_reads):
         o, n = int(v.read_base_off[i]), int(v.read_len[i])
         assert np.array_equal(got[o:o + n], v.bases[o:o + n])
+
+
+def _device_summary(batch, thr, cap=1 << 15):
+    import torch
+    from pepper_thesis_b200 import device as dev
+    db = dev.DeviceBatch(batch)
+    ws = dev.SummaryWorkspace.for_batch(db, cap)
+    dev.summary_regions(db, thr, ws)
+    k = int(ws.count.item())
+    return db, {"k": k, "position": ws.position[:k].cpu().numpy(), "windows": ws.windows[:k].cpu().numpy().astype(np.int32),
+                "depth": ws.depth[:k].cpu().numpy(), "frequency": ws.frequency[:k].cpu().numpy()}
+
+
+def test_quals_pred_same_summary():
+    """Quality predicates (pv_pack_quals_pred / pv_unpack_quals_pred): the batch travels without its qualities and the
+    device summary is the summary of the plain batch -- fuzzed CIGARs (chained inserts, inserts behind deletions / clips,
+    59..61-base inserts) under thresholds on both sides of the qualities, the synthetic preset under thresholds that fail
+    half of the bases, region views, and the device array itself against the decoded patch list."""
+    import torch
+    from test_wire_cpu import _surrogate_quals
+    from pepper_thesis_b200.synth import Thresholds
+    for seed in range(10):
+        thr = H.fuzz_thresholds(seed)
+        if seed % 2:
+            thr = Thresholds(*([float([3, 7.5, 20.5, 31, 25][seed // 2]), float([12.25, 20, 5.5, 16, 30.5][seed // 2])] + thr.as_list9()[2:] + [thr.skip_indels]))
+        b = H.fuzz_region(seed, n_reads=60)
+        want = capi.summary_regions_host(b, thr).trimmed()
+        b.pack_quals_pred(thr.min_snp_baseq, thr.min_indel_baseq)
+        assert b.quals_patch is not None
+        db, got = _device_summary(b, thr)
+        assert db.qpatches is not None
+        sq = _surrogate_quals(b)
+        dq = db.t["quals"].cpu().numpy()
+        for i in range(b.n_reads):
+            o, n = int(b.read_base_off[i]), int(b.read_len[i])
+            assert np.array_equal(dq[o:o + n], sq[o:o + n]), "seed %d read %d" % (seed, i)
+        assert got["k"] == len(want["position"]), "seed %d" % seed
+        assert np.array_equal(got["position"], want["position"])
+        assert np.array_equal(got["windows"], np.asarray(want["images"]).astype(np.int32).reshape(got["windows"].shape)), "seed %d" % seed
+    big = synth.generate("ont_r9", 350000, 12.0, seed=4)
+    for snp, indel in ((17.0, 18.5), (1.0, 1.0), (10.0, 29.0)):
+        thr = Thresholds(*([snp, indel] + H.R9.as_list9()[2:] + [False]))
+        plain = capi.summary_regions_host(big, thr).trimmed()
+        b = synth.generate("ont_r9", 350000, 12.0, seed=4)
+        b.pack_wire(quals_pred=(snp, indel))
+        assert b.quals_patch is not None and b.quals_packed is None
+        for v, sel in ((b, None), (b.region_range_view(1, 3), (1, 3))):
+            db, got = _device_summary(v, thr)
+            if sel is None:
+                assert got["k"] == len(plain["position"]) and got["k"] > 0
+                assert np.array_equal(got["position"], plain["position"])
+                assert np.array_equal(got["windows"], np.asarray(plain["images"]).astype(np.int32).reshape(got["windows"].shape))
+            else:
+                pv = capi.summary_regions_host(big.region_range_view(*sel), thr).trimmed()
+                assert got["k"] == len(pv["position"]) and np.array_equal(got["position"], pv["position"])
+                assert np.array_equal(got["windows"], np.asarray(pv["images"]).astype(np.int32).reshape(got["windows"].shape))
+        if snp == 1.0:
+            assert b.quals_patch.size == 0 and db.h2d_bytes < 0.12 * sum(getattr(big, n).nbytes for n in ("bases", "quals", "cigar"))

@@ -114,3 +114,69 @@ def test_cigar8_codes_decode():
     assert int(v.read_esc_off[0]) == 0 and int(v.read_esc_off[-1]) == v.cigar_esc.size
     assert np.array_equal(_decode_cigar8(v)[vused], v.cigar[vused])
     b.cigar[co:co + len(edge)] = keep
+
+
+# ---- quality predicates (pv_pack_quals_pred) ----------------------------------------------------------------------------
+def _surrogate_quals(b):
+    """fill byte + patch entries -> the quality array the device rebuilds (format: include/pepper_b200.h)."""
+    q = np.full(b.n_bases, b.quals_fill, np.uint8)
+    for r in range(b.n_reads):
+        o, cur = int(b.read_base_off[r]), 0
+        for e in b.quals_patch[int(b.read_qpatch_off[r]):int(b.read_qpatch_off[r + 1])]:
+            s = int(e) & 255
+            if s == 255:
+                cur += 255
+            else:
+                assert cur + s < int(b.read_len[r])
+                q[o + cur + s] = int(e) >> 8
+                cur += s + 1
+    return q
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_quals_pred_keeps_every_summary(seed):
+    """The surrogate qualities give the same candidates and windows as the real ones -- checked with the CPU oracle (the
+    C restatement, and the compiled reference when it is built), never with the product path."""
+    import pyoracle
+    from pepper_thesis_b200.synth import Thresholds
+    b = H.fuzz_region(seed, n_reads=60)
+    thr = H.fuzz_thresholds(seed)
+    if seed % 2:        # thresholds that bite on both sides of the fuzz qualities {0,1,2,5,7,20,30,40}
+        thr = Thresholds(*([float([3, 7.5, 20.5, 31, 25][seed // 2]), float([12.25, 20, 5.5, 16, 30.5][seed // 2])] + thr.as_list9()[2:] + [thr.skip_indels]))
+    b.pack_quals_pred(thr.min_snp_baseq, thr.min_indel_baseq, threads=3)
+    assert b.quals_patch is not None and int(b.read_qpatch_off[-1]) == b.quals_patch.size
+    want = pyoracle.port_summary(b, 0, thr)
+    want_ref = pyoracle.ref_summary(b, 0, thr) if pyoracle.have_ref() else None
+    real = b.quals
+    b.quals = _surrogate_quals(b)
+    assert not np.array_equal(real, b.quals)
+    H.assert_same(pyoracle.port_summary(b, 0, thr), want, "port, seed %d" % seed)
+    if want_ref is not None:
+        H.assert_same(pyoracle.ref_summary(b, 0, thr), want_ref, "reference, seed %d" % seed)
+
+
+def test_quals_pred_synthetic_is_tiny_and_views():
+    """On the bench presets no quality is below a threshold: the form is the fill byte + empty patch lists."""
+    b = synth.generate("ont_r9", 250000, 6.0, seed=3)
+    t = synth.THRESHOLDS["ont_r9_guppy5_sup"]
+    b.pack_wire(quals_pred=(t.min_snp_baseq, t.min_indel_baseq))
+    assert b.quals_patch is not None and b.quals_packed is None and b.quals_patch.size == 0 and b.quals_fill == 1
+    b2 = synth.generate("ont_r9", 250000, 6.0, seed=3)
+    b2.pack_quals_pred(17.0, 18.5)                       # about half of the uniform 5..29 qualities fail
+    assert b2.quals_fill == 19 and b2.quals_patch.size > b2.n_bases // 4
+    v = b2.region_range_view(1, 3)
+    assert int(v.read_qpatch_off[0]) == 0 and int(v.read_qpatch_off[-1]) == v.quals_patch.size and v.quals_fill == 19
+    q = _surrogate_quals(v)
+    used = np.zeros(v.n_bases, bool)
+    for r in range(v.n_reads):
+        used[int(v.read_base_off[r]):int(v.read_base_off[r]) + int(v.read_len[r])] = True
+    # wherever the surrogate says "fails the SNP test" the real quality does too, and vice versa, on aligned bases: spot check
+    # through the identity every M base obeys (surrogate 0 <=> real < 17) on a read without inserts nearby is covered by the
+    # oracle test above; here only the bookkeeping of the view
+    assert q[used].size == int(v.read_len.astype(np.int64).sum())
+
+
+def test_quals_pred_rejects_large_thresholds():
+    b = H.fuzz_region(1)
+    b.pack_quals_pred(200.0, 1.0)
+    assert b.quals_patch is None
