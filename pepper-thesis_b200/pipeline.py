@@ -94,8 +94,10 @@ class HotPath:
     """
 
     def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
-                 wrap_int8: bool = True, infer_batch: int = 32768):
+                 wrap_int8: bool = True, infer_batch: int = 32768, taper: bool = True):
         self.model = model
+        self.taper = taper                  # run_host: shrink the last groups (upload-bound runs); False when the kernels,
+                                            # not the uploads, set the pace (compact wire forms): full groups to the end
         self.thr = thresholds
         self.device = torch.device(device)
         self.group_regions = group_regions
@@ -252,12 +254,14 @@ class HotPath:
         # ends, so the last groups are made small: a short first group (nothing to overlap with yet), full groups, then a
         # taper g/2, g/4, ... whose windows are inferred at once.
         g = self.group_regions
-        taper = [t for t in (g // 2, g // 4, g // 8) if t >= 2]
+        taper = [t for t in (g // 2, g // 4, g // 8) if t >= 2] if self.taper else []
         while taper and sum(taper) > n // 2:
             taper.pop(0)
         body = n - sum(taper)
         sizes = [body % g] if body % g else []
         sizes += [g] * (body // g)
+        if not self.taper and len(sizes) > 1 and sizes[0] == g and g >= 16:
+            sizes[0:1] = [g // 8, g - g // 8]        # nothing overlaps the first upload: keep it short
         n_body = len(sizes)
         sizes += taper
         groups, r0 = [], 0

@@ -10,9 +10,16 @@ n_regions = int(mbp * 10)
 batch = synth.generate("ont_r9", n_regions * 100000 + 1000, 50.0, seed=1, num_regions=n_regions, pinned=True)
 batch.pack_wire(pinned=True)
 thr = synth.PROFILES["ont_r9"].thresholds
+if os.environ.get("PV_TRACE_QP", "0") == "1":        # qualities as threshold predicates (pv_pack_quals_pred)
+    batch.pack_quals_pred(thr.min_snp_baseq, thr.min_indel_baseq, pinned=True)
+    batch.quals_packed, batch.qual_bits = None, 0
+    if os.environ.get("PV_TRACE_BASES2", "1") == "1":
+        batch.pack_bases2(pinned=True)
+        batch.bases_patch, batch.read_patch_off = None, None
 model = models.TransducerGRU(26, 1, 256, 28, 3, True).load_state_dict(models.random_variant_state_dict(0))
-hp = pipeline.HotPath(model, thr, "cuda:0", group_regions=g)
-hp.run_host(batch); hp.run_host(batch)
+hp = pipeline.HotPath(model, thr, "cuda:0", group_regions=g, taper=os.environ.get("PV_TRACE_TAPER", "1") == "1")
+for _ in range(4):
+    hp.run_host(batch)
 torch.cuda.synchronize()
 # instrument
 log = []
@@ -26,6 +33,16 @@ def traced_init(self, *a, **k):
     e1 = torch.cuda.Event(enable_timing=True); e1.record(s)
     log.append(("upload", self.host.n_regions, t0, t1, e0, e1))
 dev.DeviceBatch.__init__ = traced_init
+orig_unpack = dev.DeviceBatch.unpack
+def traced_unpack(self):
+    s = torch.cuda.current_stream()
+    e0 = torch.cuda.Event(enable_timing=True); e0.record(s)
+    t0 = time.perf_counter()
+    orig_unpack(self)
+    t1 = time.perf_counter()
+    e1 = torch.cuda.Event(enable_timing=True); e1.record(s)
+    log.append(("unpack", self.host.n_regions, t0, t1, e0, e1))
+dev.DeviceBatch.unpack = traced_unpack
 orig_sum = hp.summarize
 def traced_sum(db):
     s = torch.cuda.current_stream()
