@@ -13,7 +13,7 @@ import numpy as np
 from .read_batch import PvReadBatchStruct, ReadBatch
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libpepper_b200.so")
+LIB_PATH = os.environ.get("PV_LIB_PATH") or os.path.join(PKG, "libpepper_b200.so")   # PV_LIB_PATH: build-variant experiments
 
 PV_WINDOW, PV_FEATURES, PV_ALLELE_BYTES = 33, 26, 64
 PV_EOVERFLOW = -4

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -94,10 +95,15 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     cfg.blockDim = dim3(tc::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = tc::CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    // programmatic dependent launch (tc_gemm.cuh: launch_dependents / grid_dependency_wait); PV_NO_PDL=1 switches it off
+    static int pdl = -1;
+    if (pdl < 0) { const char* v = getenv("PV_NO_PDL"); pdl = (v && atoi(v)) ? 0 : 1; }
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
     PV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::gemm_kernel<Epi>, a0, a1, w, g, epi));
     return PV_OK;
 }

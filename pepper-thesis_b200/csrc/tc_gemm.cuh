@@ -89,6 +89,13 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Programmatic dependent launch: a recurrent step is ~50 us long and is launched 66 times per pass, each launch depending on
+// the one before. launch_dependents lets the NEXT launch's CTAs take over an SM the moment this launch's CTA has left it (its
+// barrier / TMEM / cluster set-up and the launch latency then hide behind this grid's tail); grid_dependency_wait blocks
+// until the PREVIOUS grid has completed and its writes are visible -- every thread that touches global memory calls it first.
+// Both are no-ops for a launch without cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -280,10 +287,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     cluster_sync_all();                                        // every CTA's barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    launch_dependents();
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            grid_dependency_wait();                            // A (and the state behind it) is the previous launch's output
             int stage = 0; uint32_t phase = 0; int itp = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, itp++) {
                 const TileIdx ti = decode_tile<SLOT>(tile, g, dir_sh, nb_sh, dir_mask, nb_mask);
@@ -342,7 +351,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;
         const int te = threadIdx.x - 128;
-        epi.setup(epi_scratch, te);
+        epi.setup(epi_scratch, te);                            // constants only (biases): may run ahead of the previous grid's end
+        grid_dependency_wait();
         epi_barrier();
         int it = 0;
         if (cluster_id < n_tiles) {                            // state of the first tile
