@@ -108,6 +108,7 @@ class HotPath:
         self._ws_key = None
         self._host_counts = None
         self._acc = None
+        self._wave = None
         self.copy_stream = None
 
     # ---- summary of one group -----------------------------------------------------------------------------------------
@@ -191,8 +192,24 @@ class HotPath:
         run.total += k
         self._drain(run, final=False)
 
-    def _drain(self, run, final):
+    def _wave_windows(self):
+        """Windows that fill whole waves of the recurrent step kernels: a launch works on (windows / 256) x 8 cluster tiles
+        (4 column tiles x 2 directions per pair of 128-row tiles) with one 2-CTA cluster per pair of SMs."""
+        if self._wave is None:
+            import math
+            clusters = max(1, torch.cuda.get_device_properties(self.device).multi_processor_count // 2)
+            self._wave = 256 * clusters // math.gcd(clusters, 8)
+        return self._wave
+
+    def _drain(self, run, final, aligned=False):
+        """``aligned``: infer the largest whole number of waves that has accumulated and keep the rest for the next pass
+        (a pass of 19.5 k windows is 8.3 waves on 148 SMs and costs 9)."""
         b = self.infer_batch
+        if aligned and not final:
+            q = self._wave_windows()
+            b = min(b // q, run.n_acc // q) * q
+            if b <= 0:
+                return
         while run.n_acc >= b or (final and run.n_acc > 0):
             m = b if run.n_acc >= b else run.n_acc
             probs, arg = self.model.infer_windows(self._acc[:m], wrap_int8=self.wrap_int8)
@@ -293,7 +310,9 @@ class HotPath:
             # this path is bound by the uploads and the kernels have ~50 % slack: infer every full group's windows at once
             # (smaller passes, a little less efficient) instead of letting full passes pile up behind the last upload;
             # the small groups of the taper share one last pass (a pass costs >= 66 launch latencies however small)
-            if i < n_body or i == len(groups) - 1:
+            if i == len(groups) - 1:
                 self._drain(run, final=True)
+            elif i < n_body:
+                self._drain(run, final=False, aligned=True)
             db.record_stream(main)
         return self._finish(run, True)
