@@ -277,8 +277,17 @@ class HotPath:
         body = n - sum(taper)
         sizes = [body % g] if body % g else []
         sizes += [g] * (body // g)
-        if not self.taper and len(sizes) > 1 and sizes[0] == g and g >= 16:
-            sizes[0:1] = [g // 8, g - g // 8]        # nothing overlaps the first upload: keep it short
+        if not self.taper and g >= 16 and n >= 3 * g:
+            # kernel-bound run: nothing overlaps the first upload, and every group's upload has to hide behind the
+            # kernels of the group before it (an upload takes ~0.65 of its group's kernel time): ramp up g/8, g/4, g/2
+            ramp = [g // 8, g // 4, g // 2]
+            rest = n - sum(ramp)
+            r = rest % g
+            if r >= g // 4:
+                ramp.append(r)
+            else:
+                ramp[-1] += r
+            sizes = ramp + [g] * (rest // g)
         n_body = len(sizes)
         sizes += taper
         groups, r0 = [], 0
@@ -298,14 +307,20 @@ class HotPath:
         # uploads are queued `ahead` groups in front of the kernels: the copy stream never waits for the host (which
         # blocks on every group's candidate count), so the copies run back to back at PCIe speed
         ahead = int(os.environ.get("PV_HOST_AHEAD", "4"))
-        queue = [upload(groups[j]) for j in range(min(ahead, len(groups)))]
+        # building a group's upload costs the host ~0.5 ms: the first group's kernels are launched as soon as two uploads
+        # are queued, the look-ahead fills up (two more per group) while the GPU already works
+        queue = [upload(groups[j]) for j in range(min(2, ahead, len(groups)))]
+        nxt = len(queue)
         for i, g in enumerate(groups):
             db, ev = queue.pop(0)
             main.wait_event(ev)
-            if i + ahead < len(groups):
-                queue.append(upload(groups[i + ahead]))
             db.unpack()                           # compact wire forms -> plain arrays, on the compute stream
-            ws, k = self.summarize(db)
+            self._ensure_workspaces(db)
+            h = self._launch_summary(db, 0)
+            for _ in range(2):                    # host work while the GPU runs the group
+                if nxt < len(groups) and nxt <= i + ahead:
+                    queue.append(upload(groups[nxt])); nxt += 1
+            ws, k = self._collect_summary(h)
             self._push(run, ws, k, region_offset + g[0])
             # this path is bound by the uploads and the kernels have ~50 % slack: infer every full group's windows at once
             # (smaller passes, a little less efficient) instead of letting full passes pile up behind the last upload;
