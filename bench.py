@@ -292,7 +292,9 @@ def run_ours(args):
             # 0.5 GB per step left on the wire: the kernels now set the pace, so the bases go back to the 2-bit form
             # (its expansion kernel is 6x cheaper than the reference prediction, the extra 0.6 GB hides behind the
             # kernels) and the groups stay large to the end
-            if os.environ.get("PV_BENCH_QP_BASES2", "1") == "1" and bq.bases_patch is not None:
+            # ... as long as the ranks do not saturate the host's aggregate H2D bandwidth (~178 GB/s on this box: beyond 4 GPUs
+            # the bytes per step decide again, and the reference-predicted bases stay)
+            if os.environ.get("PV_BENCH_QP_BASES2", "1" if world <= 4 else "0") == "1" and bq.bases_patch is not None:
                 bq.pack_bases2(gen_threads, pinned=True)
                 if bq.bases2 is not None:
                     qp_bytes += bq.bases2.nbytes + bq.base_exceptions.nbytes - bq.bases_patch.nbytes - bq.read_patch_off.nbytes
