@@ -71,3 +71,30 @@ def test_device_resident_api_and_counts():
     assert torch.allclose(s, torch.ones_like(s), atol=1e-5)
     pred = hp.run_device(db)
     assert len(pred) == out["count"] and (np.diff(pred.position[pred.region == 0]) >= 0).all()
+
+
+def test_kernel_bound_host_mode_and_quality_predicates_do_not_change_results():
+    """The host path's kernel-bound schedule (no taper, ramped first groups, whole-wave inference passes with the remainder
+    carried over) and the quality-predicate wire form give the records of the default schedule on the plain batch."""
+    b = synth.generate("hifi", 5000000, 8.0, seed=24)             # 50 regions
+    thr = synth.PROFILES["hifi"].thresholds
+    hp1, _ = _hot_path("hifi", group=50)
+    a = hp1.run_host(b)
+    sd = models.random_variant_state_dict(0)
+    model = models.TransducerGRU().load_state_dict(sd)
+    hp2 = pipeline.HotPath(model, thr, "cuda", group_regions=16, wrap_int8=False, taper=False)
+    hp2._wave = 256                                               # small quantum so passes really split and carry over
+    q = synth.generate("hifi", 5000000, 8.0, seed=24)
+    q.pack_wire(quals_pred=(thr.min_snp_baseq, thr.min_indel_baseq))
+    assert q.quals_patch is not None and q.quals_packed is None
+    c = hp2.run_host(q)
+    assert len(a) > 1000 and len(a) == len(c)
+    assert np.array_equal(a.region, c.region) and np.array_equal(a.position, c.position) and a.alleles() == c.alleles()
+    assert np.array_equal(a.depth, c.depth) and np.array_equal(a.frequency, c.frequency)
+    assert np.abs(a.probs - c.probs).max() < 1e-6 and np.array_equal(a.genotype, c.genotype)
+    # a batch packed for other thresholds is refused
+    other = synth.Thresholds(*([thr.min_snp_baseq + 1.0] + thr.as_list9()[1:] + [thr.skip_indels]))
+    hp3 = pipeline.HotPath(model, other, "cuda", group_regions=16, wrap_int8=False)
+    from pepper_thesis_b200 import capi
+    with pytest.raises(capi.PvError):
+        hp3.run_host(q)
