@@ -207,6 +207,9 @@ def run_ours(args):
                            threads=gen_threads)
     # host buffers in the compact wire forms: 2-bit bases (+ exceptions), bit-packed qualities, 16-bit CIGAR; only what
     # is uploaded lives in page-locked memory (3.2 GB per rank instead of 10 GB)
+    # the batch's smallest base quality travels as metadata (PvReadBatch.min_qual, like qual_bits): when it clears both
+    # quality thresholds the tile kernel never loads a quality (PV_NO_ALLQ=1 switches that off)
+    batch.scan_min_qual(gen_threads)
     batch.pack_wire(threads=gen_threads, pinned=True).pin_uploaded()
     gen_s = time.time() - t0
     thr = synth.PROFILES[PRESET].thresholds
@@ -407,7 +410,7 @@ def run_ours(args):
             "data": "synthetic (seeded reads/contig, random-init weights torch.manual_seed(0))",
             "config": {"workload": "chr20-scale synthetic %g Mbp per GPU, %gx %s preset, summary+LSTM on B200" % (args.mbp, COVERAGE, PRESET_NAME),
                        "regions_per_gpu": n_regions, "region_bp": REGION_BP, "reads": batch.n_reads,
-                       "read_bases": int(batch.read_len.astype(np.int64).sum()), "candidates_per_step_rank0": int(k_per_step),
+                       "read_bases": int(batch.read_len.astype(np.int64).sum()), "candidates_per_step_rank0": int(k_per_step), "min_qual": int(batch.min_qual),
                        "l2": "inputs (%.2f GB) larger than L2 (126 MB), no flush needed" % (input_bytes / 1e9),
                        "groups_of_regions": hp.group_regions, "resident_groups_of_regions": res_group, "synth_seconds": round(gen_s, 1),
                        "host_format": "packed SoA batch, bases %s, qualities %s, CIGAR %s (lossless, expanded on the device)" % (

@@ -90,7 +90,11 @@ typedef struct PvReadBatch {
      *   cigar16:      the low 16 bits of every CIGAR word; only valid when every op length is < 4096 (pv_pack_cigar16). */
     const uint8_t*  quals_packed;
     int32_t         qual_bits;
-    int32_t         _pad0;
+    /* Promise about `quals` (any batch, host or device): every quality of every read base [base_off, base_off + len) is
+     * >= min_qual; 0 = no promise. A batch whose min_qual clears both quality thresholds of a summary call passes every
+     * quality test of region_summary.cpp (:377, :393, :448-463), so the tile kernel skips the quality array altogether.
+     * pv_min_qual computes it for a host batch. A wrong promise gives wrong candidates. */
+    int32_t         min_qual;
     const uint16_t* cigar16;
     /*   bases2:      2 bits per base (A C G T = 0 1 2 3, base i in byte i/4 at bits 2*(i%4)); every base that is not an
      *                upper-case A/C/G/T is listed in base_exceptions as (index << 8) | byte (ascending index). The 0
@@ -200,6 +204,8 @@ int pv_pack_quals_pred(const PvReadBatch* host_batch, double min_snp_baseq, doub
                        int64_t* read_patch_off_host, uint16_t* patches_host, int64_t patch_capacity, int32_t threads);
 int pv_unpack_quals_pred(const PvReadBatch* batch_dev_ptrs, int32_t fill, const int64_t* read_patch_off_dev,
                          const uint16_t* patches_dev, uint8_t* quals_dev, void* stream);
+/* Host: the smallest quality over all read bases of a host batch (padding excluded); 255 for a batch without bases. */
+int32_t pv_min_qual(const PvReadBatch* host_batch, int32_t threads);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
 

@@ -21,6 +21,7 @@
 //                            the centre-row / deletion-span overrides of :848-905, plus position/depth/... .
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -93,6 +94,8 @@ struct SumParams {
     const int32_t* tile_region;   // [n_tiles]
     const int32_t* tile_start;    // [n_tiles] first region-relative position of the tile
     int32_t P;                    // tile size
+    int32_t allq;                 // 1: the batch promises (PvReadBatch.min_qual) that no base quality is below either threshold:
+                                  // every quality test passes, qualities are never loaded
     int32_t* op_ref;              // [n_ops] reference advance before the op (relative to read_pos)
     int32_t* op_ri;               // [n_ops] read index before the op
     int32_t* read_span;           // [n_reads] total reference advance
@@ -281,6 +284,7 @@ __device__ __forceinline__ ReadCtx make_read_ctx(const SumParams& p, const TileC
 // qa = quality of the anchor base (already loaded by the caller)
 __device__ __forceinline__ bool insert_quality_pass(const SumParams& p, const ReadCtx& x, int ori, int n, int qa) {
     const int i0 = ori - 1;
+    if (p.allq && i0 + n <= x.read_len) return true;         // n qualities, each >= min_indel_baseq
     const int m = (i0 + n < x.read_len ? i0 + n : x.read_len) - i0;   // qualities that exist (>= 1)
     int64_t bq = qa;
     if (m <= 4) {                                            // the common short insert: independent byte loads
@@ -362,10 +366,10 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
             const int beg = t_beg[e];
             const uint32_t pc = t_pc[e];
             c0 = ((beg >> 4) + (v - t_sub[e])) << 4;           // first read index of the chunk
-            uint4 ub, uq;
+            uint4 ub, uq = make_uint4(0u, 0u, 0u, 0u);
             if (vec_ok) {
                 ub = __ldg((const uint4*)(x.bases + c0));
-                uq = __ldg((const uint4*)(x.quals + c0));
+                if (!p.allq) uq = __ldg((const uint4*)(x.quals + c0));
             } else {                                           // last read of a batch whose arrays are not padded
                 uint32_t tb[4] = {0u, 0u, 0u, 0u}, tq[4] = {0u, 0u, 0u, 0u};
                 for (int j = 0; j < 16 && x.bo + c0 + j < p.b.n_bases; j++) {
@@ -383,10 +387,12 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
             const int sh = (rp & 3) * 8;
             const uint32_t n0 = nonzero_mask(ub.x ^ __funnelshift_r(r0, r1, sh)), n1 = nonzero_mask(ub.y ^ __funnelshift_r(r1, r2, sh)),
                            n2 = nonzero_mask(ub.z ^ __funnelshift_r(r2, r3, sh)), n3 = nonzero_mask(ub.w ^ __funnelshift_r(r3, r4, sh));
-            const uint32_t l0 = lowq_mask(uq.x, p.qthr, thr4), l1 = lowq_mask(uq.y, p.qthr, thr4),
-                           l2 = lowq_mask(uq.z, p.qthr, thr4), l3 = lowq_mask(uq.w, p.qthr, thr4);
             const uint32_t bm = (0xffffu >> (16 - b1)) & (0xffffu << b0);
-            lowq16 = (movemask4(l0) | (movemask4(l1) << 4) | (movemask4(l2) << 8) | (movemask4(l3) << 12)) & bm;
+            if (!p.allq) {
+                const uint32_t l0 = lowq_mask(uq.x, p.qthr, thr4), l1 = lowq_mask(uq.y, p.qthr, thr4),
+                               l2 = lowq_mask(uq.z, p.qthr, thr4), l3 = lowq_mask(uq.w, p.qthr, thr4);
+                lowq16 = (movemask4(l0) | (movemask4(l1) << 4) | (movemask4(l2) << 8) | (movemask4(l3) << 12)) & bm;
+            }
             ex = ((movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12)) & bm) | lowq16;
         }
         while (ex) {                                             // a few per cent of the bases
@@ -457,7 +463,7 @@ __device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r,
             const int ol = a - 1;                                                 // anchor position
             if (ol >= 0 && ol < x.nv) {
                 const bool anchor_ok = ori >= 1 && ori - 1 < x.read_len;          // the anchor base exists in the read
-                const int qa = anchor_ok ? (int)x.quals[ori - 1] : 0;
+                const int qa = !anchor_ok ? 0 : (p.allq ? 255 : (int)x.quals[ori - 1]);
                 // anchor rule (:381-391): the base in front of this op is the last base of a match run -> that base keeps
                 // its REFF/REFR decrement for itself. Depends only on the op TYPE, not on whether this op is reached.
                 if (k > 0 && anchor_ok && is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u && qa >= p.qthr)
@@ -550,7 +556,7 @@ __device__ void record_unit(const SumParams& p, const TileCtx& c, int64_t r, int
             const int n = len + 1;
             int elen = n;
             if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
-            if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n, (int)x.quals[ori - 1])) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
+            if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n, p.allq ? 255 : (int)x.quals[ori - 1])) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
         } else {
             if (!(c.pflag[ol] & PF_DEL)) continue;
             const int64_t rem = c.ref_len - c.t_lo - ol;
@@ -585,7 +591,7 @@ __device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, i
     if (idx >= b.read_len[r]) return;
     const int64_t bo = b.read_base_off[r];
     const uint8_t base = b.bases[bo + idx];
-    if ((int)b.quals[bo + idx] < p.qthr) return;
+    if (!p.allq && (int)b.quals[bo + idx] < p.qthr) return;
     if (base == c.ref_s[ol] || acgt_code(base) >= 0) return;
     record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
 }
@@ -1097,6 +1103,10 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     double q = thr->min_snp_baseq; int qi = 0;
     if (q > 256.0) qi = 256; else if (q > 0.0) { qi = (int)q; if ((double)qi < q) qi++; }
     p.qthr = qi;
+    // min_qual: "every quality of every read base is >= this" (0 = no promise). When it clears both thresholds (and the
+    // insert test's per-base average, min_indel_baseq) K1 never touches the quality array.
+    p.allq = (b.min_qual > 0 && b.min_qual >= qi && (double)b.min_qual >= thr->min_indel_baseq) ? 1 : 0;
+    { static int off = -1; if (off < 0) { const char* v = getenv("PV_NO_ALLQ"); off = (v && atoi(v)) ? 1 : 0; } if (off) p.allq = 0; }
     p.t = *thr;
 
     const int sms = pv::sm_count();

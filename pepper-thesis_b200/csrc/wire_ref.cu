@@ -532,3 +532,27 @@ extern "C" int pv_unpack_quals_pred(const PvReadBatch* dev_batch, int32_t fill, 
     PV_CUDA_CHECK(cudaGetLastError());
     return PV_OK;
 }
+
+extern "C" int32_t pv_min_qual(const PvReadBatch* hb, int32_t threads) {
+    if (!hb || (hb->n_reads && !hb->quals)) return 0;
+    const PvReadBatch& b = *hb;
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    std::vector<int> mins((size_t)threads, 255);
+    const int64_t per = (b.n_reads + threads - 1) / threads;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back([&, t]() {
+        const int64_t lo = t * per, hi = lo + per < b.n_reads ? lo + per : b.n_reads;
+        int m = 255;
+        for (int64_t r = lo; r < hi; r++) {
+            const uint8_t* q = b.quals + b.read_base_off[r];
+            const int n = b.read_len[r];
+            for (int i = 0; i < n; i++) m = q[i] < m ? q[i] : m;
+        }
+        mins[(size_t)t] = m;
+    });
+    for (auto& th : pool) th.join();
+    int m = 255;
+    for (int v : mins) m = v < m ? v : m;
+    return m;
+}

@@ -122,6 +122,11 @@ class DeviceBatch:
         self.region_len = np.ascontiguousarray(host.region_len)
         self.total_positions = int(self.region_len.sum())
         self.struct = host.as_struct({n: self.t[n].data_ptr() for n in ARRAY_NAMES})
+        if self.qpatches is not None:
+            # the device array holds SURROGATE qualities: the fill byte, unless a patch lowers it
+            pv = host.quals_patch
+            vals = (pv >> 8)[(pv & 255) != 255] if pv.size else pv
+            self.struct.min_qual = int(min(host.quals_fill, int(vals.min()))) if vals.size else int(host.quals_fill)
         if not defer_unpack:
             self.unpack()
 

@@ -30,7 +30,7 @@ class PvReadBatchStruct(C.Structure):
                 ("region_cand_end", C.c_void_p), ("region_ref_off", C.c_void_p), ("region_ref_len", C.c_void_p),
                 ("region_read_begin", C.c_void_p),
                 ("ref", C.c_void_p), ("bases4", C.c_void_p),
-                ("quals_packed", C.c_void_p), ("qual_bits", C.c_int32), ("_pad0", C.c_int32), ("cigar16", C.c_void_p),
+                ("quals_packed", C.c_void_p), ("qual_bits", C.c_int32), ("min_qual", C.c_int32), ("cigar16", C.c_void_p),
                 ("bases2", C.c_void_p), ("base_exceptions", C.c_void_p), ("n_base_exceptions", C.c_int64)]
 
 
@@ -75,6 +75,7 @@ class ReadBatch:
     read_qpatch_off: Optional[np.ndarray] = None  # entries of read r at [read_qpatch_off[r], read_qpatch_off[r + 1]) ...
     quals_fill: int = 0                         # ... over this fill byte; valid for the thresholds in quals_pred_thr only
     quals_pred_thr: Optional[tuple] = None      # (min_snp_baseq, min_indel_baseq) the predicate form was packed for
+    min_qual: int = 0                           # promise: every quality of every read base is >= this (0 = none); scan_min_qual()
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -117,6 +118,7 @@ class ReadBatch:
         s = PvReadBatchStruct()
         s.n_reads, s.n_bases, s.n_ops, s.n_ref = self.n_reads, self.n_bases, self.n_ops, int(self.ref.shape[0])
         s.n_regions = self.n_regions
+        s.min_qual = int(self.min_qual)
         for name in ARRAY_NAMES:
             if arrays is not None:
                 setattr(s, name, int(arrays[name]))
@@ -142,6 +144,17 @@ class ReadBatch:
             t = torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True)
             return t, t.numpy()[:nbytes]
         return None, np.empty(nbytes, np.uint8)
+
+    def scan_min_qual(self, threads: int = 0) -> "ReadBatch":
+        """Sets ``min_qual`` (PvReadBatch.min_qual) from the plain qualities: when it clears both quality thresholds of a
+        summary call, the tile kernel never loads a quality. Views made afterwards inherit it (a lower bound stays one)."""
+        from . import capi
+        import os
+        lib = capi.load()
+        if self.n_reads:
+            st = self.as_struct()
+            self.min_qual = int(lib.pv_min_qual(C.byref(st), threads or min(32, os.cpu_count() or 1)))
+        return self
 
     def pack_quals(self, threads: int = 0, pinned: bool = False) -> "ReadBatch":
         """Adds the bit-packed wire form of the qualities (lossless: as many bits as the largest quality needs).
@@ -396,7 +409,7 @@ class ReadBatch:
                          if self.quals_patch is not None and (b_hi - b_lo) % 16 == 0 else None),
             read_qpatch_off=(self.read_qpatch_off[rb:re_ + 1] - self.read_qpatch_off[rb]
                              if self.quals_patch is not None and (b_hi - b_lo) % 16 == 0 else None),
-            quals_fill=self.quals_fill, quals_pred_thr=self.quals_pred_thr)
+            quals_fill=self.quals_fill, quals_pred_thr=self.quals_pred_thr, min_qual=self.min_qual)
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

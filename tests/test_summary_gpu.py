@@ -332,3 +332,38 @@ def test_quals_pred_same_summary():
                 assert np.array_equal(got["windows"], np.asarray(pv["images"]).astype(np.int32).reshape(got["windows"].shape))
         if snp == 1.0:
             assert b.quals_patch.size == 0 and db.h2d_bytes < 0.12 * sum(getattr(big, n).nbytes for n in ("bases", "quals", "cigar"))
+
+
+def test_min_qual_promise_skips_qualities_without_changing_results():
+    """PvReadBatch.min_qual: a batch whose smallest base quality clears both thresholds takes the tile kernel's
+    no-quality path; candidates and windows equal the plain path (promise withheld) and the CPU oracle. A promise below
+    a threshold changes nothing."""
+    import pyoracle
+    from pepper_thesis_b200.synth import Thresholds
+    lib = capi.load()
+    for seed in range(6):
+        b = H.fuzz_region(seed, n_reads=60)
+        b.quals = np.maximum(b.quals, 3).astype(np.uint8)          # padding too: only read bases are promised
+        thr = H.fuzz_thresholds(seed)
+        thr = Thresholds(*([2.0, 2.5] + thr.as_list9()[2:] + [thr.skip_indels]))
+        want = capi.summary_regions_host(b, thr).trimmed()          # min_qual == 0: every quality is loaded and tested
+        port = pyoracle.port_summary(b, 0, thr)
+        H.assert_same(want, port, "plain vs oracle, seed %d" % seed)
+        b.scan_min_qual(threads=2)
+        assert b.min_qual == 3
+        _, got = _device_summary(b, thr)
+        assert got["k"] == len(want["position"]) and np.array_equal(got["position"], want["position"]), "seed %d" % seed
+        assert np.array_equal(got["windows"], np.asarray(want["images"]).astype(np.int32).reshape(got["windows"].shape)), "seed %d" % seed
+        hot = capi.summary_regions_host(b, thr).trimmed()           # host entry point with the promise
+        H.assert_same(hot, want, "host entry, seed %d" % seed)
+        thr2 = Thresholds(*([7.5, 2.5] + thr.as_list9()[2:] + [thr.skip_indels]))   # promise (3) below the SNP threshold
+        H.assert_same(capi.summary_regions_host(b, thr2).trimmed(), pyoracle.port_summary(b, 0, thr2), "no fast path, seed %d" % seed)
+    big = synth.generate("ont_r9", 350000, 12.0, seed=4)
+    plain = capi.summary_regions_host(big, H.R9).trimmed()
+    big.scan_min_qual()
+    assert big.min_qual == 5
+    for v in (big, big.region_range_view(1, 3)):
+        _, got = _device_summary(v, H.R9)
+        pv = plain if v is big else capi.summary_regions_host(synth.generate("ont_r9", 350000, 12.0, seed=4).region_range_view(1, 3), H.R9).trimmed()
+        assert got["k"] == len(pv["position"]) and got["k"] > 0 and np.array_equal(got["position"], pv["position"])
+        assert np.array_equal(got["windows"], np.asarray(pv["images"]).astype(np.int32).reshape(got["windows"].shape))

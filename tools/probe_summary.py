@@ -10,6 +10,7 @@ t = time.time()
 b = synth.generate("ont_r9", nreg * 100000, cov, seed=1)
 print("gen %.1fs regions=%d reads=%d bases=%.1fM ops=%.1fM" % (time.time() - t, b.n_regions, b.n_reads, b.n_bases / 1e6, b.n_ops / 1e6), flush=True)
 thr = synth.PROFILES["ont_r9"].thresholds
+b.scan_min_qual()                                  # PV_NO_ALLQ=1 keeps the quality loads for an A/B
 db = device.DeviceBatch(b)
 cap = max(4096, b.total_positions // 50)
 ws = device.SummaryWorkspace.for_batch(db, cap)
