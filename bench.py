@@ -358,15 +358,26 @@ def run_ours(args):
             roof = {"kernel": dominant, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "avg_launch_ms": round(per_launch_ms, 4),
                     "launches": n_d, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg / max(1, n_d))}
-            # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this command
-            # (profiles/r1_k1_v7_bench_traffic.json), scaled to this run's regions per launch
+            # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this command, scaled to
+            # this run's regions per launch: v8 = with the min_qual promise (no quality loads), v7 = without it
+            allq = (batch.min_qual > 0 and batch.min_qual >= thr.min_snp_baseq and batch.min_qual >= thr.min_indel_baseq
+                    and os.environ.get("PV_NO_ALLQ", "0") != "1")
+            tfile = "r1_k1_v8_bench_traffic.json" if allq else "r1_k1_v7_bench_traffic.json"
+            roof["quality_loads"] = ("skipped: the batch's min_qual (%d) clears both thresholds, so 1 B/base of the algorithmic "
+                                     "bytes is never read" % batch.min_qual) if allq else "1 B/base"
+            if allq:
+                # the same rate on the bytes this path actually has to read (SURVEY 8d's formula minus 1 B per read base)
+                real_bases = int(batch.read_len.astype(np.int64).sum())
+                alg_q = (batch.algorithmic_bytes(k_per_step) - real_bases) * args.steps
+                roof["achieved_without_quality_bytes"] = round(alg_q / (ms_d / 1e3) / 1e9, 1)
+                roof["frac_without_quality_bytes"] = round(alg_q / (ms_d / 1e3) / 1e9 / hbm_peak, 4)
             try:
-                with open(os.path.join(ROOT, "profiles", "r1_k1_v7_bench_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", tfile)) as f:
                     tr = json.load(f)
                 if tr.get("kernel") == dominant:
                     regions_per_launch = n_regions * args.steps / max(1, n_d)
                     roof["traffic"] = int(tr["dram_bytes_per_launch"] * regions_per_launch / tr["regions_per_launch"])
-                    roof["traffic_source"] = "profiles/r1_k1_v7_bench_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+                    roof["traffic_source"] = "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" % tfile
             except Exception:
                 pass
     # the summary chain's own HBM roofline is always reported next to it
