@@ -184,6 +184,16 @@ extern "C" int pv_batch_validate(const PvReadBatch* b) {
         }
         if (tot > 0x3fffffffll) return pv::set_error(PV_EINVAL, "read %lld: CIGAR longer than 2^30", (long long)i);
     }
+    if (b->min_qual < 0 || b->min_qual > 255) return pv::set_error(PV_EINVAL, "min_qual %d is no quality", b->min_qual);
+    if (b->min_qual > 0 && b->quals) {                       // the promise is checkable wherever the plain qualities are at hand
+        for (int64_t i = 0; i < b->n_reads; i++) {
+            const uint8_t* q = b->quals + b->read_base_off[i];
+            for (int32_t k = 0; k < b->read_len[i]; k++)
+                if ((int32_t)q[k] < b->min_qual)
+                    return pv::set_error(PV_EINVAL, "read %lld base %d has quality %d, below the batch's min_qual promise %d",
+                                         (long long)i, k, (int)q[k], b->min_qual);
+        }
+    }
     return PV_OK;
 }
 

@@ -180,3 +180,26 @@ def test_quals_pred_rejects_large_thresholds():
     b = H.fuzz_region(1)
     b.pack_quals_pred(200.0, 1.0)
     assert b.quals_patch is None
+
+
+def test_min_qual_scan_and_validation():
+    """pv_min_qual ignores the padding behind a read; pv_batch_validate refuses a broken promise (host batches)."""
+    from pepper_thesis_b200 import capi
+    import ctypes as C
+    lib = capi.load()
+    b = synth.generate("ont_r10", 150000, 5.0, seed=9)
+    assert int(b.quals.min()) == 0                      # padding bytes
+    b.scan_min_qual(threads=3)
+    assert b.min_qual == 10                             # the preset's qualities are uniform over 10..39
+    st = b.as_struct()
+    assert lib.pv_batch_validate(C.byref(st)) == 0
+    v = b.region_range_view(0, 1)
+    assert v.min_qual == 10
+    o = int(b.read_base_off[b.n_reads // 2]) + 3
+    b.quals[o] = 4
+    st = b.as_struct()
+    assert lib.pv_batch_validate(C.byref(st)) != 0 and b"min_qual" in lib.pv_last_error()
+    b.scan_min_qual(threads=3)
+    assert b.min_qual == 4
+    st = b.as_struct()
+    assert lib.pv_batch_validate(C.byref(st)) == 0
