@@ -178,6 +178,7 @@ struct PvIngestBatch {
     std::vector<int64_t> region_ref_start, region_ref_end, region_cand_start, region_cand_end, region_ref_off, region_ref_len,
         region_read_begin;
     std::string names;
+    int min_qual = 255;            // smallest quality of any read base seen (-> PvReadBatch.min_qual)
     int64_t n_reads() const { return (int64_t)read_pos.size(); }
 };
 
@@ -220,6 +221,9 @@ struct ReadSink {
         b->hp.push_back(hp);
         b->bases.insert(b->bases.end(), seq.begin(), seq.end());
         b->quals.insert(b->quals.end(), q.begin(), q.end());
+        int mq = b->min_qual;
+        for (uint8_t v : q) mq = v < mq ? v : mq;
+        b->min_qual = mq;
         const size_t pad = (16 - (seq.size() & 15)) & 15;
         b->bases.insert(b->bases.end(), pad, 0);
         b->quals.insert(b->quals.end(), pad, 0);
@@ -449,6 +453,7 @@ void append_batch(PvIngestBatch& dst, const PvIngestBatch& src) {
     dst.read_mapq.insert(dst.read_mapq.end(), src.read_mapq.begin(), src.read_mapq.end());
     dst.bases.insert(dst.bases.end(), src.bases.begin(), src.bases.end());
     dst.quals.insert(dst.quals.end(), src.quals.begin(), src.quals.end());
+    if (src.min_qual < dst.min_qual) dst.min_qual = src.min_qual;
     dst.cigar.insert(dst.cigar.end(), src.cigar.begin(), src.cigar.end());
     dst.names.append(src.names);
 }
@@ -696,6 +701,7 @@ extern "C" int pv_ingest_view(const PvIngestBatch* b, PvReadBatch* v) {
     v->region_cand_start = b->region_cand_start.data(); v->region_cand_end = b->region_cand_end.data();
     v->region_ref_off = b->region_ref_off.data(); v->region_ref_len = b->region_ref_len.data();
     v->region_read_begin = b->region_read_begin.data(); v->ref = b->ref.data();
+    v->min_qual = (b->n_reads() && b->min_qual > 0 && b->min_qual <= 255) ? b->min_qual : 0;   // 0 = no promise
     return PV_OK;
 }
 extern "C" const int32_t* pv_ingest_hp_tags(const PvIngestBatch* b) { return b ? b->hp.data() : nullptr; }
@@ -741,6 +747,7 @@ extern "C" int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep, int
     }
     for (int r = 0; r < nreg; r++) o->region_read_begin[r + 1] += o->region_read_begin[r];
     if (nreg == 0) o->region_read_begin = {0, o->n_reads()};
+    o->min_qual = b->min_qual;                                  // a subset keeps the lower bound
     *out = o;
     return PV_OK;
 }

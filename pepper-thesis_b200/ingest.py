@@ -94,7 +94,7 @@ class IngestedReads:
             a[name] = _copy(getattr(v, name), nr, dt)
         a["region_read_begin"] = _copy(v.region_read_begin, nr + 1, np.int64)
         a["ref"] = _copy(v.ref, v.n_ref, np.uint8)
-        self.batch = ReadBatch(contigs=[contig] * nr, **a)
+        self.batch = ReadBatch(contigs=[contig] * nr, min_qual=int(v.min_qual), **a)
         self.hp_tag = _copy(lib.pv_ingest_hp_tags(handle), n, np.int32)
         self.pos_end = _copy(lib.pv_ingest_pos_end(handle), n, np.int64)
         self.bam_flag = _copy(lib.pv_ingest_bam_flags(handle), n, np.uint16)

@@ -175,6 +175,15 @@ def test_ingest_regions_matches_per_interval_port(files):
         _assert_reads_equal(got, want, lo)
     from pepper_thesis_b200 import capi
     assert capi.load().pv_batch_validate(__import__("ctypes").byref(b.as_struct())) == 0
+    # the ingest hands the smallest base quality along (PvReadBatch.min_qual; validate above checked the promise)
+    true_min = min(int(b.quals[int(o):int(o) + int(n)].min()) for o, n in zip(b.read_base_off, b.read_len) if n)
+    assert b.min_qual == true_min and half_is_lower_bound(bam, fa, true_min)
+
+
+def half_is_lower_bound(bam, fa, true_min):
+    half = ingest.ingest_regions(bam, fa, "chrS", [10000, 50000], [19999, 59999], downsample_rate=0.5).batch
+    got = min(int(half.quals[int(o):int(o) + int(n)].min()) for o, n in zip(half.read_base_off, half.read_len) if n)
+    return 0 <= half.min_qual <= got
 
 
 def test_downsampling_matches_reference_reservoir(files):
