@@ -8,5 +8,6 @@ Sub-modules (imported lazily; nothing here touches CUDA at import time):
   summarizer   drop-in for pepper_variant AlignmentSummarizer.create_summary
   models       TransducerGRU contracts (variant LSTM model M-A, polisher GRU model M-B) on the CUDA path
   pipeline     region-sharded summary -> inference driver (1..8 GPUs)
+  candidate_filter / vcf_writer   stage 3: device candidate filter, pysam-free VCFWriter (BGZF .vcf.gz)
 """
 __version__ = "0.1.0"
