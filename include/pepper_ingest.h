@@ -88,6 +88,8 @@ const char* pv_ingest_query_names(const PvIngestBatch* b, int64_t* total_bytes);
 /* keep reads keep_idx[0..n_keep) (global read indices, grouped by region in region order); new batch */
 int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep_idx, int64_t n_keep, PvIngestBatch** out);
 void pv_ingest_free(PvIngestBatch* b);
+/* diagnostics: uncompressed BGZF bytes inflated by this library so far (all handles, all threads) */
+uint64_t pv_ingest_inflated_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,8 @@ bool read_file(const std::string& path, std::vector<uint8_t>& out) {
 
 // ---- BGZF ----------------------------------------------------------------------------------------------------
 // One reader per thread over a shared file descriptor (pread): holds the current inflated block.
+std::atomic<uint64_t> g_inflated_bytes{0};     // diagnostics: BGZF payload bytes inflated since the library was loaded
+
 struct BgzfReader {
     int fd = -1;
     int64_t file_size = 0;
@@ -99,6 +101,7 @@ struct BgzfReader {
                 return fail(PV_EINVAL, "BGZF: CRC mismatch at %lld", (long long)coff);
         }
         block_coff = coff; next_coff = coff + total; upos = 0;
+        g_inflated_bytes.fetch_add(isize, std::memory_order_relaxed);
         return 0;
     }
     int seek(uint64_t voff) {
@@ -299,10 +302,18 @@ bool long_cigar(const uint8_t* aux, const uint8_t* end, std::vector<uint32_t>& o
     return false;
 }
 
-// BAM_handler::get_reads for one span [start, stop] (clipping inclusive of stop, iterator half-open like htslib)
-int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, const PvIngestOptions& o, ReadSink& sink) {
-    if (tid < 0 || tid >= (int)f.index.size()) return PV_OK;
+// BAM_handler::get_reads for spans [start_j, stop_j] (clipping inclusive of stop, iterator half-open like htslib), the
+// spans ascending by start. ONE pass over the records of their union: every BGZF block is inflated and every record
+// parsed once, then cut to each span it overlaps (a per-span index query re-inflates the blocks around every shared
+// boundary and everything the coarse bins of long reads drag in: 1.4x the file for 100 kbp spans of 12 kbp reads).
+// Each span receives exactly the records its own htslib iterator would return, in file order.
+struct Span { int64_t start, stop; };
+int collect_reads_multi(const PvBamFile& f, int tid, const std::vector<Span>& spans, const PvIngestOptions& o, std::vector<ReadSink>& sinks) {
+    if (tid < 0 || tid >= (int)f.index.size() || spans.empty()) return PV_OK;
     const BaiRef& ref = f.index[tid];
+    int64_t start = spans[0].start, stop = spans[0].stop;      // the union (spans are ascending by start)
+    for (const Span& sp : spans) stop = std::max(stop, sp.stop);
+    size_t j_lo = 0;                                           // spans before j_lo end at or before every later record
     // candidate chunks: bins overlapping [start, stop), not before the linear-index lower bound
     std::vector<uint32_t> bins;
     reg2bins(start, stop, bins);
@@ -332,6 +343,7 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
     rd.fd = f.fd; rd.file_size = f.file_size;
     std::vector<uint8_t> rec;
     std::vector<uint8_t> seq, quals; std::vector<uint32_t> ops, cg, kept;
+    std::vector<std::pair<int64_t, int64_t>> runs;           // (first read index, length) of the kept bases
     for (const Chunk& ch : merged) {
         if (int rc = rd.seek(ch.beg)) return rc;
         while (rd.tell() < ch.end) {
@@ -374,13 +386,21 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                 for (int k = 0; k < n_cig; k++) { const int op = cig[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cig[k] >> 4; }
                 const int64_t endpos = pos + ((flag & 4) || rlen == 0 ? 1 : rlen);
                 if (endpos <= start) continue;
+                while (j_lo < spans.size() && spans[j_lo].stop <= pos) j_lo++;
                 // bam_handler.cpp:133-147
                 if ((flag & 0x200) || (flag & 0x400) || (flag & 0x100) || (flag & 0x4)) continue;
                 if (!o.include_supplementary && (flag & 0x800)) continue;
                 if (mapq < o.min_mapq) continue;
 
+                for (size_t j = j_lo; j < spans.size() && spans[j].start < endpos; j++) {
+                const int64_t start = spans[j].start, stop = spans[j].stop;      // this span (shadows the union)
+                if (pos >= stop || endpos <= start) continue;
+                ReadSink& sink = sinks[j];
                 // bam_handler.cpp:163-304: cut the read to [start, stop]
-                seq.clear(); quals.clear(); kept.clear();
+                // The kept bases form contiguous runs of read indices (one run for every well-formed record: once the first
+                // aligned base inside the span is kept, every later read-consuming op up to `stop` is kept too), so the ops
+                // only file index ranges here and bases / qualities are decoded once per run, not once per CIGAR op.
+                seq.clear(); quals.clear(); kept.clear(); runs.clear();
                 int64_t pos_start = -1, pos_end = -1, cur_pos = pos, cur_idx = 0;
                 bool bad = false;                            // CIGAR walks past SEQ (e.g. SEQ '*'): the reference reads out of bounds there
                 for (int k = 0; k < n_cig; k++) {
@@ -396,8 +416,8 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                             if (take > 0) {
                                 if (pos_start == -1) { pos_start = cur_pos; pos_end = pos_start; }
                                 if (cur_idx + take > l_seq) { bad = true; break; }
-                                decode_bases(seq_p, cur_idx, take, seq);
-                                quals.insert(quals.end(), qual_p + cur_idx, qual_p + cur_idx + take);
+                                if (!runs.empty() && runs.back().first + runs.back().second == cur_idx) runs.back().second += take;
+                                else runs.emplace_back(cur_idx, take);
                                 cur_idx += take; cur_pos += take; pos_end += take; kept_len = take;
                             }
                             // the reference leaves the remaining bases of the op unconsumed (its loop breaks at the first
@@ -406,8 +426,10 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                         case 4: case 1:
                             if (cur_pos >= start && cur_pos <= stop && pos_start != -1) {
                                 if (cur_idx + len > l_seq) { bad = true; break; }
-                                decode_bases(seq_p, cur_idx, len, seq);
-                                quals.insert(quals.end(), qual_p + cur_idx, qual_p + cur_idx + len);
+                                if (len > 0) {
+                                    if (!runs.empty() && runs.back().first + runs.back().second == cur_idx) runs.back().second += len;
+                                    else runs.emplace_back(cur_idx, len);
+                                }
                                 kept_len = len;
                             }
                             cur_idx += len;
@@ -425,13 +447,25 @@ int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, cons
                     if (bad) break;
                     if (kept_len > 0) kept.push_back((uint32_t)(kept_len << 4) | (uint32_t)op);
                 }
+                if (!bad)
+                    for (const auto& run : runs) {
+                        decode_bases(seq_p, run.first, run.second, seq);
+                        quals.insert(quals.end(), qual_p + run.first, qual_p + run.first + run.second);
+                    }
                 if (!bad && !seq.empty())
                     sink.add(pos_start, pos_end, seq, quals, kept, flag, mapq, parse_hp(aux_p, end_p), qname);
+                }
             }
         }
     }
 done:
     return PV_OK;
+}
+
+int collect_reads(const PvBamFile& f, int tid, int64_t start, int64_t stop, const PvIngestOptions& o, ReadSink& sink) {
+    std::vector<Span> spans{Span{start, stop}};
+    std::vector<ReadSink> sinks{sink};
+    return collect_reads_multi(f, tid, spans, o, sinks);
 }
 
 int tid_of(const PvBamFile& f, const char* contig) {
@@ -650,20 +684,42 @@ extern "C" int pv_ingest_regions(PvBamFile* bam, const PvFastaFile* fasta, const
     int nt = opt->threads > 0 ? opt->threads : (int)std::thread::hardware_concurrency();
     if (nt < 1) nt = 1;
     if (nt > n_regions) nt = n_regions > 0 ? n_regions : 1;
+    // Work items = runs of consecutive intervals read in ONE pass over the BAM (collect_reads_multi): intervals must come
+    // ascending and close to each other for that (a gap of more than 200 kbp starts a new item, so does an interval out of
+    // order).
+    std::vector<std::pair<int, int>> items;                    // [first, last) interval
+    {
+        // few intervals per thread: one item each (ceil(n / threads) intervals); many: about four items per thread
+        const int per = n_regions < 8 * nt ? std::max(1, (n_regions + nt - 1) / nt) : n_regions / (4 * nt);
+        int first = 0;
+        for (int i = 1; i <= n_regions; i++) {
+            const bool cut = i == n_regions || i - first >= per || region_start[i] < region_start[i - 1] ||
+                             region_start[i] - region_end[i - 1] > 200000;
+            if (cut) { items.emplace_back(first, i); first = i; }
+        }
+    }
     auto work = [&]() {
         for (;;) {
-            const int i = next.fetch_add(1);
-            if (i >= n_regions) break;
-            const int64_t rs = std::max<int64_t>(0, region_start[i] - opt->safe_bases);   // AlignmentSummarizer.py:181-182
-            const int64_t re = region_end[i] + opt->safe_bases;
-            ReadSink sink{&parts[i]};
-            rcs[i] = collect_reads(*bam, tid, rs, re, *opt, sink);
-            if (rcs[i]) { errs[i] = g_err; continue; }
-            std::string& ref = refs[i];
-            ref.assign((size_t)(re + 1 - rs), 'N');       // region_end + 1 exclusive (:214-216); 'N' past the contig end
-            int64_t got = 0;
-            rcs[i] = pv_fasta_fetch(fasta, contig, rs, re + 1, &ref[0], &got);
-            if (rcs[i]) errs[i] = g_err;
+            const int it = next.fetch_add(1);
+            if (it >= (int)items.size()) break;
+            const int i0 = items[it].first, i1 = items[it].second;
+            std::vector<Span> spans;
+            std::vector<ReadSink> sinks;
+            for (int i = i0; i < i1; i++) {
+                spans.push_back(Span{std::max<int64_t>(0, region_start[i] - opt->safe_bases),   // AlignmentSummarizer.py:181-182
+                                     region_end[i] + opt->safe_bases});
+                sinks.push_back(ReadSink{&parts[i]});
+            }
+            const int rc = collect_reads_multi(*bam, tid, spans, *opt, sinks);
+            if (rc) { rcs[i0] = rc; errs[i0] = g_err; continue; }
+            for (int i = i0; i < i1; i++) {
+                const int64_t rs = spans[i - i0].start, re = spans[i - i0].stop;
+                std::string& ref = refs[i];
+                ref.assign((size_t)(re + 1 - rs), 'N');       // region_end + 1 exclusive (:214-216); 'N' past the contig end
+                int64_t got = 0;
+                rcs[i] = pv_fasta_fetch(fasta, contig, rs, re + 1, &ref[0], &got);
+                if (rcs[i]) errs[i] = g_err;
+            }
         }
     };
     std::vector<std::thread> pool;
@@ -753,3 +809,5 @@ extern "C" int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep, int
 }
 
 extern "C" void pv_ingest_free(PvIngestBatch* b) { delete b; }
+
+extern "C" uint64_t pv_ingest_inflated_bytes(void) { return g_inflated_bytes.load(); }
