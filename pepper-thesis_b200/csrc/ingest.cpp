@@ -730,6 +730,16 @@ extern "C" int pv_ingest_regions(PvBamFile* bam, const PvFastaFile* fasta, const
 
     PvIngestBatch* b = new PvIngestBatch();
     b->region_read_begin.push_back(0);
+    {   // one allocation per big array instead of a doubling chain (each step of which copies what is already there)
+        size_t nb = 0, nc = 0, nr = 0, nf = 0, nn = 0;
+        for (int i = 0; i < n_regions; i++) {
+            nb += parts[i].bases.size(); nc += parts[i].cigar.size(); nr += parts[i].read_pos.size(); nf += refs[i].size(); nn += parts[i].names.size();
+        }
+        b->bases.reserve(nb); b->quals.reserve(nb); b->cigar.reserve(nc); b->ref.reserve(nf); b->names.reserve(nn);
+        b->read_pos.reserve(nr); b->read_pos_end.reserve(nr); b->read_base_off.reserve(nr); b->read_cigar_off.reserve(nr);
+        b->read_len.reserve(nr); b->read_n_ops.reserve(nr); b->hp.reserve(nr); b->bam_flag.reserve(nr);
+        b->read_flags.reserve(nr); b->read_mapq.reserve(nr);
+    }
     for (int i = 0; i < n_regions; i++) {
         const int64_t rs = std::max<int64_t>(0, region_start[i] - opt->safe_bases), re = region_end[i] + opt->safe_bases;
         append_batch(*b, parts[i]);
