@@ -90,6 +90,11 @@ int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep_idx, int64_t n_
 void pv_ingest_free(PvIngestBatch* b);
 /* diagnostics: uncompressed BGZF bytes inflated by this library so far (all handles, all threads) */
 uint64_t pv_ingest_inflated_bytes(void);
+/* ... and how many BGZF blocks were decoded by the library's own DEFLATE decoder (csrc/fast_inflate.h; every block is
+ * confirmed by its CRC-32, zlib takes over otherwise; PV_INGEST_ZLIB_ONLY=1 switches the decoder off) */
+uint64_t pv_ingest_fast_blocks(void);
+/* The decoder itself, for tests: raw DEFLATE (RFC 1951) of exactly n_out bytes; PV_OK or PV_EINVAL. */
+int pv_inflate_raw(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t n_out);
 
 #ifdef __cplusplus
 }

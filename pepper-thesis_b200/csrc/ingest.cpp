@@ -7,6 +7,7 @@
 // BAM / BGZF / BAI layouts are those of the SAM specification (SAMv1 sections 4.1, 4.2, 5.2); the region iterator
 // reproduces htslib's sam_itr_queryi contract: records of the contig with pos < end and end-position > beg.
 #include "pepper_ingest.h"
+#include "fast_inflate.h"
 
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -48,6 +49,8 @@ bool read_file(const std::string& path, std::vector<uint8_t>& out) {
 
 // ---- BGZF ----------------------------------------------------------------------------------------------------
 // One reader per thread over a shared file descriptor (pread): holds the current inflated block.
+std::atomic<uint64_t> g_fast_blocks{0};        // diagnostics: blocks decoded by fast_inflate.h (the rest went through zlib)
+const bool g_fast_inflate = []() { const char* v = getenv("PV_INGEST_ZLIB_ONLY"); return !(v && atoi(v)); }();
 std::atomic<uint64_t> g_inflated_bytes{0};     // diagnostics: BGZF payload bytes inflated since the library was loaded
 
 struct BgzfReader {
@@ -60,6 +63,7 @@ struct BgzfReader {
     size_t upos = 0;
     z_stream zs;
     bool zs_init = false;
+    std::vector<fastinf::Tables> tables;   // one element, on the heap (46 KB)
 
     ~BgzfReader() { if (zs_init) inflateEnd(&zs); }
 
@@ -86,18 +90,32 @@ struct BgzfReader {
         const int total = bsize + 1;
         const int cdata_off = 12 + xlen, cdata_len = total - cdata_off - 8;
         if (cdata_len < 0) return fail(PV_EINVAL, "BGZF: bad block size");
-        raw.resize(total);
+        raw.resize((size_t)total + 16);                       // fast_inflate.h reads up to 16 bytes behind the stream
         if (pread(fd, raw.data(), total, coff) != total) return fail(PV_EINVAL, "BGZF: truncated block at %lld", (long long)coff);
         const uint32_t isize = le32(&raw[total - 4]);
+        const uint32_t want_crc = le32(&raw[total - 8]);
         data.resize(isize);
-        if (isize) {
+        bool done = false;
+        if (isize && g_fast_inflate) {
+            // own decoder first (written for literal-heavy BAM payloads); zlib below takes over whenever it gives up or the
+            // block's CRC-32 does not confirm its output
+            if (tables.empty()) tables.resize(1);
+            uint8_t tail[16];
+            memcpy(tail, raw.data() + total - 8, 8);         // the trailer sits right behind the stream: keep it, zero the padding
+            memset(raw.data() + total - 8, 0, 24);
+            done = fastinf::inflate_raw(raw.data() + cdata_off, (size_t)cdata_len, data.data(), isize, tables[0]) &&
+                   (uint32_t)crc32(crc32(0L, Z_NULL, 0), data.data(), isize) == want_crc;
+            memcpy(raw.data() + total - 8, tail, 8);
+            if (done) g_fast_blocks.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (isize && !done) {
             if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) return fail(PV_ENOMEM, "inflateInit2"); zs_init = true; }
             else inflateReset(&zs);
             zs.next_in = raw.data() + cdata_off; zs.avail_in = (uInt)cdata_len;
             zs.next_out = data.data(); zs.avail_out = isize;
             const int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0) return fail(PV_EINVAL, "BGZF: inflate failed (%d) at %lld", rc, (long long)coff);
-            if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), data.data(), isize) != le32(&raw[total - 8]))
+            if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), data.data(), isize) != want_crc)
                 return fail(PV_EINVAL, "BGZF: CRC mismatch at %lld", (long long)coff);
         }
         block_coff = coff; next_coff = coff + total; upos = 0;
@@ -821,3 +839,12 @@ extern "C" int pv_ingest_select(const PvIngestBatch* b, const int64_t* keep, int
 extern "C" void pv_ingest_free(PvIngestBatch* b) { delete b; }
 
 extern "C" uint64_t pv_ingest_inflated_bytes(void) { return g_inflated_bytes.load(); }
+extern "C" uint64_t pv_ingest_fast_blocks(void) { return g_fast_blocks.load(); }
+
+extern "C" int pv_inflate_raw(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t n_out) {
+    if (!in || !out || n_in < 0 || n_out < 0) return fail(PV_EINVAL, "null argument");
+    std::vector<uint8_t> padded((size_t)n_in + 16, 0);
+    memcpy(padded.data(), in, (size_t)n_in);
+    std::vector<fastinf::Tables> t(1);
+    return fastinf::inflate_raw(padded.data(), (size_t)n_in, out, (size_t)n_out, t[0]) ? PV_OK : fail(PV_EINVAL, "pv_inflate_raw: not a DEFLATE stream of %lld bytes", (long long)n_out);
+}

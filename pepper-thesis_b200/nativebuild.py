@@ -50,7 +50,8 @@ def cuda_sources():
 
 
 def headers():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    # fast_inflate.h belongs to the host-only ingest library (build_ingest lists it)
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh")) and f != "fast_inflate.h"]
     return hs + [os.path.join(INC, "pepper_b200.h")]
 
 
@@ -80,7 +81,7 @@ def build_synth(force=False, verbose=False):
 def build_ingest(force=False, verbose=False):
     """Host-only BAM/FASTA ingest (zlib), include/pepper_ingest.h."""
     src = os.path.join(CSRC, "ingest.cpp")
-    if force or _newer(INGEST, [src, os.path.join(INC, "pepper_ingest.h"), os.path.join(INC, "pepper_b200.h")]):
+    if force or _newer(INGEST, [src, os.path.join(CSRC, "fast_inflate.h"), os.path.join(INC, "pepper_ingest.h"), os.path.join(INC, "pepper_b200.h")]):
         _run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wall", "-I", INC, src, "-o", INGEST, "-lz", "-lpthread"], verbose)
     return INGEST
 
