@@ -13,9 +13,11 @@
 namespace fastinf {
 
 constexpr int LIT_PB = 11, DIST_PB = 8;
-constexpr uint32_t F_LIT = 1u << 15, F_EOB = 1u << 14, F_SUB = 1u << 13, F_BAD = 1u << 12;
+constexpr uint32_t F_LIT = 1u << 15, F_EOB = 1u << 14, F_SUB = 1u << 13, F_BAD = 1u << 12, F_LIT2 = 1u << 9;
 // entry: bits 0..3 = code length to consume (sub-table pointer: primary bits), 4..8 = extra bits (length/distance symbols),
-// flags, bits 16..31 = literal byte / base value / sub-table offset
+// flags, bits 16..31 = literal byte / base value / sub-table offset. F_LIT2: TWO literals whose codes fit the primary index
+// together (bits 16..23 the first, 24..31 the second, length = both codes): quality-like data has ~5-bit codes, so most
+// lookups emit two bytes and the load -> shift -> load dependency chain is paid once per pair.
 
 struct Tables {
     uint32_t lit[(1 << LIT_PB) + 320 * 16];        // primary + sub-tables (sum of sub-table sizes is bounded by the codes above PB)
@@ -102,6 +104,21 @@ inline bool build(const uint8_t* lens, int n, uint32_t* tab, int pb, int cap) {
     return true;
 }
 
+// second pass over the primary literal table: entry i whose first symbol is a literal of l1 bits and whose remaining
+// LIT_PB - l1 index bits already hold a complete second literal code becomes a pair entry
+inline void pair_literals(uint32_t* tab) {
+    uint32_t single[1 << LIT_PB];
+    memcpy(single, tab, sizeof(single));
+    for (uint32_t i = 0; i < (1u << LIT_PB); i++) {
+        const uint32_t e = single[i];
+        if (!(e & F_LIT)) continue;
+        const uint32_t l1 = e & 15u;
+        const uint32_t e2 = single[i >> l1];                  // the unknown high bits read as zero: valid iff the code is short enough
+        if ((e2 & F_LIT) && (e2 & 15u) + l1 <= (uint32_t)LIT_PB)
+            tab[i] = (e & 0x00ff0000u) | ((e2 & 0x00ff0000u) << 8) | F_LIT | F_LIT2 | (l1 + (e2 & 15u));
+    }
+}
+
 inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
 // in: n_in bytes of raw DEFLATE, with at least 16 more readable bytes behind them. out: exactly n_out bytes expected.
@@ -141,6 +158,7 @@ inline bool inflate_raw(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_o
                 for (; i < 280; i++) lens[i] = 7;
                 for (; i < 288; i++) lens[i] = 8;
                 if (!build<true>(lens, 288, T.lit, LIT_PB, (int)(sizeof(T.lit) / 4))) return false;
+                pair_literals(T.lit);
                 for (i = 0; i < 32; i++) lens[i] = 5;
                 if (!build<false>(lens, 32, T.dist, DIST_PB, (int)(sizeof(T.dist) / 4))) return false;
             } else {                                                        // dynamic code
@@ -188,6 +206,7 @@ inline bool inflate_raw(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_o
                 uint8_t dl[32];
                 memcpy(dl, lens + hlit, (size_t)hdist);
                 if (!build<true>(lens, hlit, T.lit, LIT_PB, (int)(sizeof(T.lit) / 4))) return false;
+                pair_literals(T.lit);
                 if (!build<false>(dl, hdist, T.dist, DIST_PB, (int)(sizeof(T.dist) / 4))) return false;
             }
             // ---- the symbols of the block ----
@@ -195,17 +214,18 @@ inline bool inflate_raw(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_o
                 if (ip - (bc >> 3) > in_end) return false;
                 FI_REFILL();                                                // >= 56 bits: a literal/length code (<= 15) + its
                 uint32_t e = T.lit[FI_BITS(LIT_PB)];                        // extra bits (<= 5) + a distance code (<= 15) + 13
-                if (e & F_LIT) {                                            // fast path: up to three literals per refill
-                    if (op >= out_end) return false;
-                    FI_DROP(e & 15u); *op++ = (uint8_t)(e >> 16);
+#define FI_EMIT(e) do { \
+                    if (e & F_LIT2) { if (out_end - op < 2) return false; op[0] = (uint8_t)(e >> 16); op[1] = (uint8_t)(e >> 24); op += 2; } \
+                    else { if (op >= out_end) return false; *op++ = (uint8_t)(e >> 16); } \
+                    FI_DROP(e & 15u); } while (0)
+                if (e & F_LIT) {                                            // fast path: up to three lookups (six literals) per refill
+                    FI_EMIT(e);
                     e = T.lit[FI_BITS(LIT_PB)];
                     if (e & F_LIT) {
-                        if (op >= out_end) return false;
-                        FI_DROP(e & 15u); *op++ = (uint8_t)(e >> 16);
+                        FI_EMIT(e);
                         e = T.lit[FI_BITS(LIT_PB)];
                         if (e & F_LIT) {
-                            if (op >= out_end) return false;
-                            FI_DROP(e & 15u); *op++ = (uint8_t)(e >> 16);
+                            FI_EMIT(e);
                             continue;
                         }
                     }
@@ -251,6 +271,7 @@ inline bool inflate_raw(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_o
         }
         if (final) break;
     }
+#undef FI_EMIT
 #undef FI_REFILL
 #undef FI_BITS
 #undef FI_DROP
