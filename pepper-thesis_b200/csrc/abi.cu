@@ -483,7 +483,14 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
                               (size_t)hb->n_bases, (size_t)hb->n_ops * 4, (size_t)hb->n_regions * 8, (size_t)hb->n_regions * 8,
                               (size_t)hb->n_regions * 8, (size_t)hb->n_regions * 8, (size_t)hb->n_regions * 8,
                               (size_t)hb->n_regions * 8, (size_t)(hb->n_regions + 1) * 8, (size_t)hb->n_ref};
+    // A batch whose min_qual promise clears both quality thresholds passes every quality test by construction (same rule as
+    // pv_summary_regions): its quality array -- half of the plain bytes -- is not uploaded. The one case the promise cannot
+    // decide (a read whose CIGAR runs over its own end) comes back as status bit 4 and the call is repeated with qualities.
+    double qd = thr->min_snp_baseq; int qi = 0;
+    if (qd > 256.0) qi = 256; else if (qd > 0.0) { qi = (int)qd; if ((double)qi < qd) qi++; }
+    bool skip_q = hb->min_qual > 0 && hb->min_qual >= qi && (double)hb->min_qual >= thr->min_indel_baseq;
     for (int i = 0; i < 18; i++) {
+        if (i == 8 && skip_q) continue;
         if (int rc = h.arr[i].reserve(bytes[i] + 16)) return rc;
         if (i == 7 && hb->bases2 && hb->n_bases) {          // bases travel 2-bit packed (+ exception list)
             if (int rc = h.packed.reserve((size_t)hb->n_bases / 4 + 16)) return rc;
@@ -521,7 +528,7 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
     db.bases2 = nullptr; db.base_exceptions = nullptr; db.n_base_exceptions = 0;
     db.read_pos = (const int64_t*)h.arr[0].p; db.read_base_off = (const int64_t*)h.arr[1].p; db.read_len = (const int32_t*)h.arr[2].p;
     db.read_cigar_off = (const int64_t*)h.arr[3].p; db.read_n_ops = (const int32_t*)h.arr[4].p; db.read_flags = (const uint8_t*)h.arr[5].p;
-    db.read_mapq = (const uint8_t*)h.arr[6].p; db.bases = (const uint8_t*)h.arr[7].p; db.quals = (const uint8_t*)h.arr[8].p;
+    db.read_mapq = (const uint8_t*)h.arr[6].p; db.bases = (const uint8_t*)h.arr[7].p; db.quals = skip_q ? nullptr : (const uint8_t*)h.arr[8].p;
     db.cigar = (const uint32_t*)h.arr[9].p; db.region_ref_start = (const int64_t*)h.arr[10].p; db.region_ref_end = (const int64_t*)h.arr[11].p;
     db.region_cand_start = (const int64_t*)h.arr[12].p; db.region_cand_end = (const int64_t*)h.arr[13].p;
     db.region_ref_off = (const int64_t*)h.arr[14].p; db.region_ref_len = (const int64_t*)h.arr[15].p;
@@ -547,12 +554,25 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
     dout.capacity = cap; dout.windows = (int16_t*)h.win.p; dout.position = (int64_t*)h.pos.p; dout.region = (int32_t*)h.reg.p;
     dout.depth = (int32_t*)h.dep.p; dout.frequency = (int32_t*)h.frq.p; dout.allele = (uint8_t*)h.al.p; dout.allele_len = (uint8_t*)h.aln.p;
 
-    if (int rc = pv_summary_regions(&db, rlen.data(), total, thr, window, features, &dout, (int64_t*)h.cnt.p, h.ws.p,
-                                    (int64_t)h.ws.cap, dense_dev, st)) return rc;
     int64_t found = 0; int32_t status = 0;
-    PV_CUDA_CHECK(cudaMemcpyAsync(&found, h.cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    PV_CUDA_CHECK(cudaMemcpyAsync(&status, (const uint8_t*)h.ws.p + pv_summary_status_offset(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    PV_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (int rc = pv_summary_regions(&db, rlen.data(), total, thr, window, features, &dout, (int64_t*)h.cnt.p, h.ws.p,
+                                        (int64_t)h.ws.cap, dense_dev, st)) return rc;
+        PV_CUDA_CHECK(cudaMemcpyAsync(&found, h.cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaMemcpyAsync(&status, (const uint8_t*)h.ws.p + pv_summary_status_offset(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PV_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!(status & 16) || !skip_q) break;
+        skip_q = false;                                      // rare: the qualities are needed after all
+        if (int rc = h.arr[8].reserve(bytes[8] + 16)) return rc;
+        if (hb->quals) PV_CUDA_CHECK(cudaMemcpyAsync(h.arr[8].p, hb->quals, bytes[8], cudaMemcpyHostToDevice, st));
+        else {
+            const size_t pb = (size_t)((hb->n_bases + 31) / 32) * hb->qual_bits * 4;
+            if (int rc = h.packed_q.reserve(pb + 16)) return rc;
+            PV_CUDA_CHECK(cudaMemcpyAsync(h.packed_q.p, hb->quals_packed, pb, cudaMemcpyHostToDevice, st));
+            if (int rc = pv_unpack_quals((const uint8_t*)h.packed_q.p, hb->n_bases, hb->qual_bits, (uint8_t*)h.arr[8].p, st)) return rc;
+        }
+        db.quals = (const uint8_t*)h.arr[8].p;
+    }
     *n_candidates = found;
     if (status & 8) return pv::set_error(PV_ECUDA, "internal inconsistency in the allele event pass (status %d)", status);
     if (status & 3) return pv::set_error(PV_EOVERFLOW, "site/event scratch overflow (status %d): raise the candidate capacity", status);

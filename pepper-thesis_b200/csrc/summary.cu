@@ -59,7 +59,8 @@ enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_ba
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
 enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_COUNT = 8 };
-enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8 };
+enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8,
+       ST_NEED_QUALS = 16 };   // a quality was needed (insert over the read's end) but the batch came without its quality array
 enum { PF_SITE = 1, PF_SNP = 2, PF_INS = 4, PF_DEL = 8, PF_OTHER = 16 };
 
 struct SiteRec {
@@ -285,6 +286,10 @@ __device__ __forceinline__ ReadCtx make_read_ctx(const SumParams& p, const TileC
 __device__ __forceinline__ bool insert_quality_pass(const SumParams& p, const ReadCtx& x, int ori, int n, int qa) {
     const int i0 = ori - 1;
     if (p.allq && i0 + n <= x.read_len) return true;         // n qualities, each >= min_indel_baseq
+    if (p.b.quals == nullptr) {                              // the promise alone cannot decide: the caller re-runs with qualities
+        atomicOr(&p.ctr[CTR_STATUS], ST_NEED_QUALS);
+        return true;
+    }
     const int m = (i0 + n < x.read_len ? i0 + n : x.read_len) - i0;   // qualities that exist (>= 1)
     int64_t bq = qa;
     if (m <= 4) {                                            // the common short insert: independent byte loads
@@ -1001,7 +1006,8 @@ Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_
     pl.cand_cap = capacity < 1 ? 1 : capacity;
     pl.site_cap = 4 * pl.cand_cap + 4096;
     if (pl.site_cap > total_positions) pl.site_cap = total_positions > 0 ? total_positions : 1;
-    pl.ev_cap = n_ops + (1 << 20);
+    pl.ev_cap = n_ops + (1 << 20);                          // grows with the candidate capacity, so the caller's overflow retry
+    if (pl.ev_cap < 8 * pl.cand_cap) pl.ev_cap = 8 * pl.cand_cap;   // (larger capacity) also cures an event overflow
     if (pl.ev_cap > 0x7fffff00ll) pl.ev_cap = 0x7fffff00ll;
     if (pl.cand_cap > 0x7fffff00ll) pl.cand_cap = 0x7fffff00ll;
     if (pl.site_cap > 0x7fffff00ll) pl.site_cap = 0x7fffff00ll;
@@ -1106,7 +1112,9 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     // min_qual: "every quality of every read base is >= this" (0 = no promise). When it clears both thresholds (and the
     // insert test's per-base average, min_indel_baseq) K1 never touches the quality array.
     p.allq = (b.min_qual > 0 && b.min_qual >= qi && (double)b.min_qual >= thr->min_indel_baseq) ? 1 : 0;
-    { static int off = -1; if (off < 0) { const char* v = getenv("PV_NO_ALLQ"); off = (v && atoi(v)) ? 1 : 0; } if (off) p.allq = 0; }
+    { static int off = -1; if (off < 0) { const char* v = getenv("PV_NO_ALLQ"); off = (v && atoi(v)) ? 1 : 0; } if (off && b.quals) p.allq = 0; }
+    if (!p.allq && b.quals == nullptr && b.n_bases > 0)
+        return pv::set_error(PV_EINVAL, "the batch has no quality array and its min_qual promise (%d) does not clear the thresholds", b.min_qual);
     p.t = *thr;
 
     const int sms = pv::sm_count();

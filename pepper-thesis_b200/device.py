@@ -26,9 +26,15 @@ class DeviceBatch:
     """A ReadBatch whose arrays live in HBM (``PvReadBatch`` with device pointers)."""
 
     def __init__(self, host: ReadBatch, device: torch.device | str = "cuda", non_blocking: bool = True,
-                 defer_unpack: bool = False):
+                 defer_unpack: bool = False, skip_quals: bool = False):
+        """``skip_quals``: the caller has checked that the batch's ``min_qual`` promise clears both quality thresholds of
+        the summary it is going to run (``quals_not_needed``): no kernel then reads a quality, so the quality array --
+        half of the plain bytes -- is neither uploaded nor allocated (``PvReadBatch.quals == NULL``). Results are
+        identical; the one case the promise cannot decide (a read whose CIGAR runs over its own end) is flagged by the
+        kernels (status bit 4) and the caller re-runs after ``ensure_quals()``."""
         self.host = host
         self.device = torch.device(device)
+        self.quals_skipped = bool(skip_quals and host.min_qual > 0 and host.quals.size)
         self.t = {}
         self.packed = None          # 4-bit or 2-bit bases
         self.packed_exc = None      # exception list of the 2-bit form
@@ -64,6 +70,8 @@ class DeviceBatch:
                 self.packed = _to_torch(host.bases4).to(self.device, non_blocking=non_blocking)
                 self.t[name] = torch.empty(a.size, dtype=torch.uint8, device=self.device)
                 self._unpacked = False
+                continue
+            if name == "quals" and self.quals_skipped:
                 continue
             if name == "quals" and host.quals_patch is not None and a.size:
                 # surrogate qualities that keep every threshold test of the summary (pv_unpack_quals_pred)
@@ -121,7 +129,7 @@ class DeviceBatch:
             self.t[name] = self._small_dev[offs[name]:offs[name] + max(a.nbytes, 8)].view(dt)[:max(a.size, 1) if a.size == 0 else a.size]
         self.region_len = np.ascontiguousarray(host.region_len)
         self.total_positions = int(self.region_len.sum())
-        self.struct = host.as_struct({n: self.t[n].data_ptr() for n in ARRAY_NAMES})
+        self.struct = host.as_struct({n: (self.t[n].data_ptr() if n in self.t else 0) for n in ARRAY_NAMES})
         if self.qpatches is not None:
             # the device array holds SURROGATE qualities: the fill byte, unless a patch lowers it
             pv = host.quals_patch
@@ -165,6 +173,23 @@ class DeviceBatch:
                                            C.c_void_p(out.data_ptr()), st))
         self._unpacked = True
 
+    def with_min_qual(self, min_qual: int) -> "DeviceBatch":
+        """The same device arrays under a different ``min_qual`` promise (0 = none: every quality is loaded and tested)."""
+        import copy
+        other = copy.copy(self)
+        other.struct = type(self.struct).from_buffer_copy(self.struct)
+        other.struct.min_qual = int(min_qual)
+        return other
+
+    def ensure_quals(self):
+        """Uploads the plain qualities of a batch that was created with ``skip_quals`` (blocking; the rare re-run path)."""
+        if not self.quals_skipped:
+            return
+        q = self.host.quals
+        self.t["quals"] = torch.from_numpy(np.ascontiguousarray(q)).to(self.device)
+        self.struct.quals = self.t["quals"].data_ptr()
+        self.quals_skipped = False
+
     def record_stream(self, stream):
         for t in list(self.t.values()) + [x for x in (self.packed, self.packed_exc, self.packed_q, self.packed_c, self.patches, self.codes8, self.esc8, self.qpatches, self._small_dev) if x is not None]:
             t.record_stream(stream)
@@ -172,15 +197,17 @@ class DeviceBatch:
     @property
     def h2d_bytes(self) -> int:
         n = int(sum(getattr(self.host, n).nbytes for n in ARRAY_NAMES))
+        if self.quals_skipped:
+            n -= self.host.quals.nbytes
         if self.patches is not None:
             n -= self.host.bases.nbytes - self.host.bases_patch.nbytes - self.host.read_patch_off.nbytes
         elif self.packed is not None and self.host.bases2 is not None:
             n -= self.host.bases.nbytes - self.host.bases2.nbytes - self.host.base_exceptions.nbytes
         elif self.packed is not None:
             n -= self.host.bases.nbytes - self.host.bases4.nbytes
-        if self.qpatches is not None:
+        if self.qpatches is not None and not self.quals_skipped:
             n -= self.host.quals.nbytes - self.host.quals_patch.nbytes - self.host.read_qpatch_off.nbytes
-        if self.packed_q is not None:
+        if self.packed_q is not None and not self.quals_skipped:
             n -= self.host.quals.nbytes - min((self.host.quals.size * self.host.qual_bits + 7) // 8, self.host.quals_packed.nbytes)
         if self.codes8 is not None:
             n -= self.host.cigar.nbytes - self.host.cigar8.nbytes - self.host.cigar_esc.nbytes - self.host.read_esc_off.nbytes
@@ -218,6 +245,14 @@ class SummaryWorkspace:
 
     def status(self) -> int:
         return int(self.ws[12:16].view(torch.int32).item())
+
+
+def quals_not_needed(min_qual: int, thr) -> bool:
+    """True when a batch promising ``min_qual`` passes every quality test of the summary for these thresholds
+    (same rule as pv_summary_regions: min_qual >= ceil(min_snp_baseq) and >= min_indel_baseq)."""
+    import math
+    t = capi.thresholds_struct(thr)
+    return bool(min_qual > 0 and min_qual >= math.ceil(max(0.0, float(t.min_snp_baseq))) and min_qual >= float(t.min_indel_baseq))
 
 
 def summary_regions(db: DeviceBatch, thr, ws: SummaryWorkspace, window: int = 32, features: int = 26):

@@ -94,8 +94,10 @@ class HotPath:
     """
 
     def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
-                 wrap_int8: bool = True, infer_batch: int = 32768, taper: bool = True):
+                 wrap_int8: bool = True, infer_batch: int = 32768, taper: bool = True, skip_quals: bool = True):
         self.model = model
+        self.skip_quals = skip_quals        # run_host: a batch whose min_qual promise clears both quality thresholds is
+                                            # uploaded without its quality array (no kernel would read it)
         self.taper = taper                  # run_host: shrink the last groups (upload-bound runs); False when the kernels,
                                             # not the uploads, set the pace (compact wire forms): full groups to the end
         self.thr = thresholds
@@ -110,6 +112,7 @@ class HotPath:
         self._acc = None
         self._wave = None
         self.copy_stream = None
+        self.last_h2d_bytes = 0
 
     # ---- summary of one group -----------------------------------------------------------------------------------------
     # Two workspaces alternate: the kernels of group i+1 are already queued when the host waits (on an event, not on the
@@ -146,17 +149,25 @@ class HotPath:
         h["ev"].synchronize()
         k, st = int(h["hc"][0]), int(h["hc"][1])
         ws = h["ws"]
-        while True:
+        for _ in range(12):
             if st & 8:
                 raise RuntimeError("internal inconsistency in the allele event pass")
-            if k <= ws.capacity and not (st & 7):
+            if k <= ws.capacity and not (st & 23):
                 return ws, k
-            self.cand_per_kbp *= 2.0 * max(1.0, k / max(1, ws.capacity))
-            self._ws = None
-            self._ensure_workspaces(h["db"])
-            ws = self._ws[h["slot"]]
+            if st & 16:
+                # the batch travelled without its qualities (min_qual promise) and a read whose CIGAR runs over its own
+                # end needed one: upload them and run the group again
+                h["db"].ensure_quals()
+            if k > ws.capacity or (st & 7):
+                # site / event / candidate scratch all grow with the candidate capacity (summary.cu make_plan)
+                self.cand_per_kbp *= 2.0 * max(1.0, k / max(1, ws.capacity))
+                self._ws = None
+                self._ensure_workspaces(h["db"])
+                ws = self._ws[h["slot"]]
             dev.summary_regions(h["db"], self.thr, ws)
             k, st = int(ws.count.item()), ws.status()
+        raise RuntimeError("summary scratch still overflows after 12 capacity doublings (status %d, %d candidates, capacity %d)"
+                           % (st, k, ws.capacity))
 
     def summarize(self, db: dev.DeviceBatch):
         """Summary kernel chain on one group (synchronous form); returns (workspace, K)."""
@@ -295,9 +306,14 @@ class HotPath:
             groups.append((r0, r0 + sz)); r0 += sz
         main = torch.cuda.current_stream(self.device)
 
+        skip_q = bool(self.skip_quals and dev.quals_not_needed(batch.min_qual, self.thr))
+        self.last_h2d_bytes = 0              # bytes this call copies host -> device (counted from the uploaded arrays)
+
         def upload(g):
             with torch.cuda.stream(self.copy_stream):
-                db = dev.DeviceBatch(batch.region_range_view(*g), self.device, non_blocking=True, defer_unpack=True)
+                db = dev.DeviceBatch(batch.region_range_view(*g), self.device, non_blocking=True, defer_unpack=True,
+                                     skip_quals=skip_q)
+                self.last_h2d_bytes += db.h2d_bytes
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
             return db, ev

@@ -341,6 +341,22 @@ class ReadBatch:
             setattr(self, name, dst)
         return self
 
+    def pin_plain(self, with_quals: bool = True) -> "ReadBatch":
+        """Moves the PLAIN big arrays (bases, cigar, ref and -- unless ``with_quals`` is False -- quals) into page-locked
+        memory in place, so a host batch in its plain form uploads asynchronously at PCIe speed."""
+        import torch
+        self._pinned_owners = getattr(self, "_pinned_owners", {})
+        for name in ["bases", "cigar", "ref"] + (["quals"] if with_quals else []):
+            a = getattr(self, name)
+            if a.size == 0 or name in self._pinned_owners:
+                continue
+            t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+            dst = t.numpy().view(a.dtype)
+            dst[:] = a
+            self._pinned_owners[name] = t
+            setattr(self, name, dst)
+        return self
+
     def _exceptions_view(self, b_lo: int, b_hi: int):
         if self.bases2 is None:
             return None

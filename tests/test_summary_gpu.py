@@ -367,3 +367,53 @@ def test_min_qual_promise_skips_qualities_without_changing_results():
         pv = plain if v is big else capi.summary_regions_host(synth.generate("ont_r9", 350000, 12.0, seed=4).region_range_view(1, 3), H.R9).trimmed()
         assert got["k"] == len(pv["position"]) and got["k"] > 0 and np.array_equal(got["position"], pv["position"])
         assert np.array_equal(got["windows"], np.asarray(pv["images"]).astype(np.int32).reshape(got["windows"].shape))
+
+
+def test_quality_array_not_uploaded_when_the_promise_clears_the_thresholds():
+    """DeviceBatch(skip_quals=True) / the host entry point: a batch whose min_qual promise clears both thresholds travels
+    WITHOUT its quality array (PvReadBatch.quals == NULL on the device) and gives the candidates of the plain batch. A
+    read whose CIGAR runs over its own end -- the one case the promise cannot decide -- raises status bit 4 and the host
+    entry point repeats the call with the qualities; a promise that does not clear the thresholds keeps the upload."""
+    import torch
+    from pepper_thesis_b200 import device as dev
+    from pepper_thesis_b200.synth import Thresholds
+    for seed in range(4):
+        b = H.fuzz_region(100 + seed, n_reads=60)
+        b.quals = np.maximum(b.quals, 3).astype(np.uint8)
+        thr = H.fuzz_thresholds(seed)
+        thr = Thresholds(*([2.0, 2.5] + thr.as_list9()[2:] + [thr.skip_indels]))
+        want = capi.summary_regions_host(b, thr).trimmed()          # no promise: qualities uploaded and tested
+        b.scan_min_qual(threads=2)
+        assert dev.quals_not_needed(b.min_qual, thr)
+        db = dev.DeviceBatch(b, skip_quals=True)
+        assert db.quals_skipped and db.struct.quals in (0, None) and db.h2d_bytes == dev.DeviceBatch(b).h2d_bytes - b.quals.nbytes
+        ws = dev.SummaryWorkspace.for_batch(db, 1 << 15)
+        dev.summary_regions(db, thr, ws)
+        k = int(ws.count.item())
+        assert ws.status() == 0
+        assert k == len(want["position"]) and np.array_equal(ws.position[:k].cpu().numpy(), want["position"]), "seed %d" % seed
+        assert np.array_equal(ws.windows[:k].cpu().numpy().astype(np.int32),
+                              np.asarray(want["images"]).astype(np.int32).reshape(k, 33, 26)), "seed %d" % seed
+        H.assert_same(capi.summary_regions_host(b, thr).trimmed(), want, "host entry without qualities, seed %d" % seed)
+        assert not dev.quals_not_needed(b.min_qual, Thresholds(*([7.5, 2.5] + thr.as_list9()[2:] + [thr.skip_indels])))
+    # an insert that runs over the end of its read: 10M 5I with 12 bases. Qualities: the two inserted bases that exist are
+    # low, so the plain path fails the insert's quality test where a blind "promise" pass would count it.
+    ref = (b"ACGT" * 30)
+    reads = [H.Read(5, ref[5:15].decode() + "TT", [(0, 10), (1, 5)], rev=bool(i & 1), q=[30] * 10 + [3, 3]) for i in range(6)]
+    reads += [H.Read(0, ref[0:60].decode(), [(0, 60)], rev=bool(i & 1), q=[30] * 60) for i in range(4)]
+    b = H.one_region(ref, reads)
+    thr = Thresholds(2.0, 20.0, 0.1, 0.15, 0.15, 1.0, 0.1, 0.1, 1.0, False)
+    want = capi.summary_regions_host(b, thr).trimmed()
+    H.assert_same(want, O.port_summary(b, 0, thr), "plain vs port")
+    b.min_qual = 3
+    thr_ok = Thresholds(2.0, 2.5, 0.1, 0.15, 0.15, 1.0, 0.1, 0.1, 1.0, False)
+    want_ok = O.port_summary(b, 0, thr_ok)
+    db = dev.DeviceBatch(b, skip_quals=True)
+    ws = dev.SummaryWorkspace.for_batch(db, 4096)
+    dev.summary_regions(db, thr_ok, ws)
+    torch.cuda.synchronize()
+    assert ws.status() & 16, "the kernels must flag the missing quality"
+    db.ensure_quals()
+    dev.summary_regions(db, thr_ok, ws)
+    assert ws.status() == 0 and int(ws.count.item()) == len(want_ok["position"])
+    H.assert_same(capi.summary_regions_host(b, thr_ok).trimmed(), want_ok, "host entry retries with qualities")
