@@ -137,7 +137,7 @@ const char* pv_last_error(void);
 int pv_device_count(void);
 
 /* Launch accounting and optional CUDA-event profiling of the library's own kernels (used by bench.py for
- * `gpu_launches` and the per-kernel roofline). Families, in order: 0 summary cigar prefix, 1 summary pileup tile,
+ * `gpu_launches` and the per-kernel roofline). Families, in order: 0 summary per-tile work lists (CIGAR spans), 1 summary pileup tile,
  * 2 summary site alleles, 3 summary key sort, 4 summary window emit, 5 LSTM input prep, 6 LSTM encoder steps,
  * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc, 11 candidate filter, 12 polisher summary. */
 #define PV_PROFILE_FAMILIES 13
@@ -216,7 +216,9 @@ int pv_batch_validate(const PvReadBatch* host_batch);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Summary: device-resident interface. `stream` is a cudaStream_t passed as void*.
- * pv_summary_workspace_bytes: bytes of scratch pv_summary_regions needs for this batch shape.
+ * pv_summary_workspace_bytes: bytes of scratch pv_summary_regions needs for this batch shape (max_region_len = the longest
+ *   region_ref_end - region_ref_start + 1 of the batch; it bounds the per-tile work lists: a read touches at most every
+ *   tile of its own region. <= 0 means "unknown": total_positions is assumed).
  * pv_summary_regions: everything asynchronous on `stream`; *n_candidates_dev (device int64) receives the
  *   number of candidates found. If it exceeds out->capacity an unspecified subset of `capacity` candidates is
  *   stored (still sorted); the host wrapper reports PV_EOVERFLOW and the caller retries with a larger capacity.
@@ -224,7 +226,7 @@ int pv_batch_validate(const PvReadBatch* host_batch);
  *   back to back (debug / parity hook for region_summary.cpp:598-654).
  * ------------------------------------------------------------------------------------------------------- */
 int64_t pv_summary_workspace_bytes(int64_t n_reads, int64_t n_ops, int32_t n_regions, int64_t total_positions,
-                                   int64_t capacity);
+                                   int64_t max_region_len, int64_t capacity);
 int pv_summary_regions(const PvReadBatch* batch_dev_ptrs, const int64_t* region_len_host, int64_t total_positions,
                        const PvThresholds* thr, int32_t window, int32_t features,
                        const PvCandidates* out_dev_ptrs, int64_t* n_candidates_dev,

@@ -104,7 +104,7 @@ def load() -> C.CDLL:
         lib.pv_unpack_cigar16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         lib.pv_pack_cigar16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
         lib.pv_summary_workspace_bytes.restype = C.c_int64
-        lib.pv_summary_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64]
+        lib.pv_summary_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64]
         lib.pv_summary_regions.argtypes = [C.POINTER(PvReadBatchStruct), C.c_void_p, C.c_int64,
                                            C.POINTER(PvThresholdsStruct), C.c_int32, C.c_int32,
                                            C.POINTER(PvCandidatesStruct), C.c_void_p, C.c_void_p, C.c_int64,

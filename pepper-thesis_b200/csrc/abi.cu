@@ -535,7 +535,9 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
     db.region_read_begin = (const int64_t*)h.arr[16].p; db.ref = (const uint8_t*)h.arr[17].p;
 
     const int64_t cap = out->capacity > 0 ? out->capacity : 1;
-    const int64_t ws_bytes = pv_summary_workspace_bytes(hb->n_reads, hb->n_ops, hb->n_regions, total, cap);
+    int64_t max_len = 0;
+    for (int32_t r = 0; r < hb->n_regions; r++) if (rlen[r] > max_len) max_len = rlen[r];
+    const int64_t ws_bytes = pv_summary_workspace_bytes(hb->n_reads, hb->n_ops, hb->n_regions, total, max_len, cap);
     if (int rc = h.ws.reserve((size_t)ws_bytes)) return rc;
     if (int rc = h.win.reserve((size_t)cap * PV_WINDOW * PV_FEATURES * 2)) return rc;
     if (int rc = h.pos.reserve((size_t)cap * 8)) return rc;

@@ -2,17 +2,24 @@
 // (/root/reference/pepper_variant/modules/cpp/region_summary.cpp:337-916, inference mode).
 //
 // Kernel chain (all on one stream, no host synchronisation):
-//   K0 cigar_prefix_kernel   warp per read: exclusive prefix of (reference advance, read advance) per CIGAR op,
-//                            with the REF_SKIP/PAD -> SOFT_CLIP fall-through of region_summary.cpp:556-561.
+//   K0 read_span_kernel / tile_scan_kernel / tile_entry_kernel
+//                            warp per read: reference span of the CIGAR (with the REF_SKIP/PAD -> SOFT_CLIP fall-through of
+//                            region_summary.cpp:556-561), the tiles the read touches counted, scanned, and then filled with
+//                            one ENTRY per (tile, read): the op the walk of that tile starts at, with the tile-local
+//                            position and the read index in front of it. K1 never searches a CIGAR and no per-op prefix
+//                            array ever goes to HBM.
 //   K1 pileup_tile_kernel    CTA per tile of P reference positions of one region, counters in SHARED memory (16 packed
 //                            words per position: forward strand in the low half, reverse in the high half). Phase A:
-//                            a warp per read that touches the tile walks its CIGAR ops, lane per op (run ends into
-//                            difference arrays, insert/delete anchors), then scans the aligned bases 16 per lane with
-//                            byte-parallel compares against the tile's reference -- a matching base costs no atomic,
-//                            only mismatches and low-quality bases do. Phase B: prefix sums turn the difference arrays
-//                            into counts, then the clamped int16 image rows (flushed to HBM), the site thresholds in
-//                            fp64 exactly like :634-646, and the candidate sites. Phase C re-walks only the CIGAR
-//                            ops (no bases) and records the insert/delete alleles of the registered sites.
+//                            a warp per entry stages up to 128 CIGAR ops at a time in its shared-memory table (coalesced
+//                            loads, four ops per lane, one warp scan for positions and read indices); pass 1, lane per
+//                            op: run ends into difference arrays, insert/delete anchors; pass 2, lane per 16-byte-aligned
+//                            SLICE of the read's bases: each lane finds its first op by bisection in the table and walks
+//                            the match runs that cross its slice, 16 bases per load, byte-parallel compares against the
+//                            tile's reference -- a matching base costs no atomic, only mismatches and low-quality bases
+//                            do. Phase B: prefix sums turn the difference arrays into counts, then the clamped int16
+//                            image rows (flushed to HBM), the site thresholds in fp64 exactly like :634-646, and the
+//                            candidate sites. Phase C re-walks only the CIGAR ops (no bases) and records the
+//                            insert/delete alleles of the registered sites.
 //   K2 site_allele_kernel    warp per site: exact de-duplication of the recorded alleles (byte-wise compares, no
 //                            hashing), per-allele filters of :682-712, one candidate record per survivor with a
 //                            64-bit order key (position, type, allele rank).
@@ -29,16 +36,18 @@ namespace {
 constexpr int NC = 16;           // packed 32-bit counter words per position
 #ifndef PV_K1_THREADS
 #define PV_K1_THREADS 512
-#define PV_K1_PMAX 1280
+#define PV_K1_PMAX 1088
 #define PV_K1_MINB 2
 #endif
 constexpr int K1_THREADS = PV_K1_THREADS;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
-constexpr int P_MAX = PV_K1_PMAX;   // 2 CTAs per SM: 16 words x 1280 positions = 80 KB of counters each
-constexpr int LIST_CAP = 1024;   // reads examined per round of the tile's work list
-constexpr int TBL = 96;          // match pieces a warp collects before it scans their bases
-constexpr int WARP_SCRATCH = 3 * TBL + 4;   // ints of per-warp scratch: piece table (read index, tile position | length, sub-piece prefix)
+constexpr int P_MAX = PV_K1_PMAX;   // 2 CTAs per SM: 16 words x 1088 positions = 68 KB of counters each
+constexpr int K0_CHUNK = 4;      // reads a K0 warp takes per ticket
+constexpr int ROUND_OPS = 128;   // CIGAR ops a warp stages per round (four per lane)
+constexpr int QCAP = 63;         // exceptions (mismatches, low-quality bases) a warp queues per round before it counts them
+constexpr int WARP_SCRATCH = 4 * ROUND_OPS + 1 + QCAP;   // ints of per-warp scratch: the round's op words, its table of match
+                                 // pieces / inserts / deletes (three ints per entry), the exception queue
 constexpr int REF_PAD = 16;      // bytes in front of the tile's reference copy (a 16-base chunk may start before the tile)
 constexpr int WIN_ELEMS = PV_WINDOW * PV_FEATURES;   // 858
 
@@ -58,9 +67,10 @@ enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_ba
        C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count of bases that are no dense SNP allele
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
-enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_COUNT = 8 };
+enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_K0_TICKET2 = 5, CTR_ENTRIES = 6, CTR_COUNT = 8 };
 enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8,
-       ST_NEED_QUALS = 16 };   // a quality was needed (insert over the read's end) but the batch came without its quality array
+       ST_NEED_QUALS = 16,     // a quality was needed (insert over the read's end) but the batch came without its quality array
+       ST_ENTRY_OVF = 32 };    // more (tile, read) entries than the workspace was sized for (cannot happen with pv_summary_workspace_bytes' bound)
 enum { PF_SITE = 1, PF_SNP = 2, PF_INS = 4, PF_DEL = 8, PF_OTHER = 16 };
 
 struct SiteRec {
@@ -89,17 +99,30 @@ struct CandRec {
     int32_t nf, nr;
 };
 
+// One (tile, read) pair of the work lists K0 builds: where the walk of that tile starts in the read's CIGAR.
+struct TileEntry {
+    int32_t read;          // read index in the batch
+    int32_t k;             // first op of the walk: the op in front of the first op that starts inside the tile (0 if none)
+    int32_t a;             // tile-local reference position at which op k starts (negative: the op starts in front of the tile)
+    int32_t ri;            // read index in front of op k
+};
+
 struct SumParams {
     PvReadBatch b;
     const int64_t* pos_off;       // [n_regions + 1] dense position offset of each region
     const int32_t* tile_region;   // [n_tiles]
     const int32_t* tile_start;    // [n_tiles] first region-relative position of the tile
+    const int32_t* tile_base;     // [n_regions + 1] first tile of each region
     int32_t P;                    // tile size
+    int32_t n_tiles;
+    int32_t* read_region;         // [n_reads] region of each read (K0)
+    int32_t* tile_count;          // [n_tiles] entries per tile (K0 count pass)
+    int32_t* tile_fill;           // [n_tiles][2] fill cursors from the front / from the back (K0 fill pass)
+    int32_t* tile_off;            // [n_tiles + 1] exclusive prefix of tile_count
+    TileEntry* entries; int32_t entry_cap;
     int32_t allq;                 // 1: the batch promises (PvReadBatch.min_qual) that no base quality is below either threshold:
                                   // every quality test passes, qualities are never loaded
-    int32_t* op_ref;              // [n_ops] reference advance before the op (relative to read_pos)
-    int32_t* op_ri;               // [n_ops] read index before the op
-    int32_t* read_span;           // [n_reads] total reference advance
+    int32_t* read_span;           // [n_reads] total reference advance of the read's CIGAR
     int16_t* img;                 // [total_positions][26]; rows are only valid where a candidate window can read them
     int32_t img_all;              // 1 = write every row (dense-image parity hook)
     SiteRec* sites; int32_t site_cap;
@@ -127,90 +150,184 @@ __device__ __forceinline__ int acgt_code(uint8_t b) {           // upper-case on
 __device__ __forceinline__ bool is_match_op(int op) { return op == 0 || op == 7 || op == 8; }
 __device__ __forceinline__ int min125(int v) { return v < 125 ? v : 125; }
 
-// first k in [0, n) with a[k] >= key (n if none); a non-decreasing; all 32 lanes cooperate (32-ary search)
-__device__ int warp_lower_bound(const int32_t* __restrict__ a, int n, int64_t key, int lane) {
-    int lo = 0, hi = n;
-    while (hi > lo) {
-        const int len = hi - lo;
-        const int step = (len + 31) >> 5;
-        int idx = lo + (lane + 1) * step - 1;
-        if (idx > hi - 1) idx = hi - 1;
-        const bool pred = (int64_t)a[idx] >= key;
-        const unsigned m = __ballot_sync(0xffffffffu, pred);
-        if (m == 0) return hi;
-        const int l = __ffs(m) - 1;
-        const int nlo = lo + l * step;
-        int nhi = lo + (l + 1) * step - 1;
-        if (nhi > hi - 1) nhi = hi - 1;
-        if (step == 1) return nlo;
-        lo = nlo; hi = nhi;
-    }
-    return lo;
+// ------------------------------------------------------------------------------------------------------------
+// K0: per-tile work lists
+// ------------------------------------------------------------------------------------------------------------
+// :357-563 -- what an op adds to ref_position / read_index (REF_SKIP and PAD also advance the read: the missing `break`)
+__device__ __forceinline__ void op_advance(uint32_t w, int& ra, int& qa) {
+    const int op = (int)(w & 15u), len = (int)(w >> 4);
+    ra = (is_match_op(op) || op == 2 || op == 3 || op == 6) ? len : 0;
+    qa = (is_match_op(op) || op == 1 || op == 4 || op == 3 || op == 6) ? len : 0;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K0
-// ------------------------------------------------------------------------------------------------------------
-// Each lane takes FOUR consecutive ops (one 16-byte load, two 16-byte stores), so a warp step covers 128 ops with a
-// single pair of shuffle scans. Ops are indexed from the 16-byte aligned slot at or below the read's first op.
-// Reads come from a ticket counter: their op counts are heavy-tailed (1 .. 100 kbp reads), a fixed stride leaves the kernel
-// waiting for the unluckiest warp.
-__global__ void cigar_prefix_kernel(PvReadBatch b, int32_t* __restrict__ op_ref, int32_t* __restrict__ op_ri,
-                                    int32_t* __restrict__ read_span, int32_t* __restrict__ ticket) {
+// four consecutive CIGAR words starting at the 16-byte aligned slot `co_al + k` of a read whose ops occupy slots
+// [skip, n_slots): words outside the read come back as 0 (an empty match)
+__device__ __forceinline__ void load_ops4(const PvReadBatch& b, int64_t co_al, int k, int skip, int n_slots, uint32_t ws[4]) {
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (k + 3 < n_slots && co_al + k + 3 < b.n_ops) w = __ldg((const uint4*)(b.cigar + co_al + k));
+    else {
+        if (k + 0 < n_slots) w.x = b.cigar[co_al + k + 0];
+        if (k + 1 < n_slots) w.y = b.cigar[co_al + k + 1];
+        if (k + 2 < n_slots) w.z = b.cigar[co_al + k + 2];
+    }
+    ws[0] = w.x; ws[1] = w.y; ws[2] = w.z; ws[3] = w.w;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (k + j < skip || k + j >= n_slots) ws[j] = 0u;
+}
+
+// The tiles of its region a read touches: aligned / deleted positions [rel, rel + span - 1] and insert / delete anchors
+// [rel - 1, rel + span - 1], clipped to the region. Returns false when there are none.
+__device__ __forceinline__ bool touched_tiles(const SumParams& p, int64_t r, int reg, int span, int64_t& rel, int& t0, int& t1) {
+    const PvReadBatch& b = p.b;
+    rel = b.read_pos[r] - b.region_ref_start[reg];
+    const int64_t L = b.region_ref_end[reg] - b.region_ref_start[reg] + 1;
+    int64_t lo = rel - 1, hi = rel + (int64_t)span - 1;
+    if (b.read_mapq[r] == 0 || b.read_n_ops[r] <= 0 || hi < 0 || lo > L - 1) return false;      // :619
+    if (lo < 0) lo = 0;
+    if (hi > L - 1) hi = L - 1;
+    t0 = (int)(lo / p.P); t1 = (int)(hi / p.P);
+    return true;
+}
+
+// Pass 1, warp per read (ticket counter: op counts are heavy-tailed): region of the read, reference span of its CIGAR,
+// one count for every tile it touches. Each lane takes FOUR consecutive ops per step (one 16-byte load).
+__global__ void read_span_kernel(const SumParams p) {
+    const PvReadBatch& b = p.b;
     const int lane = threadIdx.x & 31;
-    while (true) {
-        int tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1);
-        const int64_t r = __shfl_sync(0xffffffffu, tk, 0);
-        if (r >= b.n_reads) break;
+    for (int64_t r = 0, r_end = 0;; r++) {
+        if (r >= r_end) {                                     // K0_CHUNK reads per ticket: one global atomic serves several reads
+            int tk = 0;
+            if (lane == 0) tk = atomicAdd(&p.ctr[CTR_K0_TICKET], K0_CHUNK);
+            r = __shfl_sync(0xffffffffu, tk, 0);
+            if (r >= b.n_reads) break;
+            r_end = r + K0_CHUNK < b.n_reads ? r + K0_CHUNK : b.n_reads;
+        }
+        int lo = 0, hi = b.n_regions - 1;                     // region: first one whose read range ends behind r
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (b.region_read_begin[mid + 1] <= r) lo = mid + 1; else hi = mid; }
+        const int reg = lo;
         const int64_t co = b.read_cigar_off[r];
         const int n_ops = b.read_n_ops[r];
-        const int64_t co_al = co & ~(int64_t)3;                 // aligned slot; ops before `co` belong to the previous read
-        const int skip = (int)(co - co_al);
-        const int n_slots = skip + n_ops;
-        int ref_run = 0, ri_run = 0;
-        for (int k0 = 0; k0 < n_slots; k0 += 128) {
-            const int k = k0 + lane * 4;                        // first slot of this lane
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (k + 3 < n_slots && co_al + k + 3 < b.n_ops) w = __ldg((const uint4*)(b.cigar + co_al + k));
-            else {
-                if (k + 0 < n_slots) w.x = b.cigar[co_al + k + 0];
-                if (k + 1 < n_slots) w.y = b.cigar[co_al + k + 1];
-                if (k + 2 < n_slots) w.z = b.cigar[co_al + k + 2];
-            }
-            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        const int64_t co_al = co & ~(int64_t)3;
+        const int skip = (int)(co - co_al), n_slots = skip + n_ops;
+        int64_t part = 0;
+        for (int k = lane * 4; k < n_slots; k += 128) {
+            uint32_t ws[4];
+            load_ops4(b, co_al, k, skip, n_slots, ws);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { int ra, qa; op_advance(ws[j], ra, qa); part += ra; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        const int span = part > (1ll << 30) ? (1 << 30) : (int)part;
+        if (lane == 0) { p.read_span[r] = span; p.read_region[r] = reg; }
+        int64_t rel; int t0, t1;
+        if (!touched_tiles(p, r, reg, span, rel, t0, t1)) continue;
+        const int tb = p.tile_base[reg];
+        for (int t = t0 + lane; t <= t1; t += 32) atomicAdd(&p.tile_count[tb + t], 1);
+    }
+}
+
+// exclusive prefix of the tile counts (one block); the total is checked against the entry capacity
+__global__ void tile_scan_kernel(const SumParams p) {
+    __shared__ int64_t s_part[1024];
+    const int tid = threadIdx.x, n = p.n_tiles;
+    const int per = (n + 1023) / 1024;
+    const int lo = tid * per, hi = lo + per < n ? lo + per : n;
+    int64_t sum = 0;
+    for (int i = lo; i < hi; i++) sum += p.tile_count[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const int64_t v = tid >= d ? s_part[tid - d] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int64_t run = s_part[tid] - sum;
+    const bool ovf = s_part[1023] > (int64_t)p.entry_cap;
+    for (int i = lo; i < hi; i++) { p.tile_off[i] = ovf ? 0 : (int32_t)run; run += p.tile_count[i]; }
+    if (tid == 0) {
+        p.tile_off[n] = ovf ? 0 : (int32_t)s_part[1023];
+        p.ctr[CTR_ENTRIES] = ovf ? 0 : (int32_t)s_part[1023];
+        if (ovf) atomicOr(&p.ctr[CTR_STATUS], ST_ENTRY_OVF);
+    }
+}
+
+// Entries of reads that cross the whole tile are filed from the front of the tile's list, reads that start or end inside
+// it (less work) from the back: the warps of a CTA pull the long units first and finish closer together.
+__device__ __forceinline__ void emit_entry(const SumParams& p, int tile, int64_t r, int k, int64_t a, int64_t ri, bool whole) {
+    const int slot = whole ? p.tile_off[tile] + atomicAdd(&p.tile_fill[2 * tile], 1)
+                           : p.tile_off[tile + 1] - 1 - atomicAdd(&p.tile_fill[2 * tile + 1], 1);
+    if (slot >= p.tile_off[tile] && slot < p.tile_off[tile + 1]) {
+        TileEntry e; e.read = (int32_t)r; e.k = k; e.a = (int32_t)a; e.ri = ri > (1ll << 30) ? (1 << 30) : (int32_t)ri;
+        p.entries[slot] = e;
+    } else {
+        atomicOr(&p.ctr[CTR_STATUS], ST_INTERNAL);
+    }
+}
+
+// Pass 2, warp per read: one entry per touched tile. The walk of tile t starts at the op in front of the first op that
+// starts at or behind the tile's first position t_lo, i.e. the one op k with  a_k < t_lo <= a_k + (its reference advance)
+// (a_k = op start, region-relative); tiles that begin at or in front of the read's own start begin at op 0.
+__global__ void tile_entry_kernel(const SumParams p) {
+    const PvReadBatch& b = p.b;
+    const int lane = threadIdx.x & 31;
+    if (p.ctr[CTR_STATUS] & ST_ENTRY_OVF) return;
+    for (int64_t r = 0, r_end = 0;; r++) {
+        if (r >= r_end) {
+            int tk = 0;
+            if (lane == 0) tk = atomicAdd(&p.ctr[CTR_K0_TICKET2], K0_CHUNK);
+            r = __shfl_sync(0xffffffffu, tk, 0);
+            if (r >= b.n_reads) break;
+            r_end = r + K0_CHUNK < b.n_reads ? r + K0_CHUNK : b.n_reads;
+        }
+        const int reg = p.read_region[r];
+        int64_t rel; int t0, t1;
+        const int64_t span_r = p.read_span[r];
+        if (!touched_tiles(p, r, reg, (int)span_r, rel, t0, t1)) continue;
+        const int tb = p.tile_base[reg];
+        const int64_t P = p.P;
+        if (rel >= 0) {
+            const int64_t tf64 = rel / P;
+            const int tf = tf64 < (int64_t)t1 ? (int)tf64 : t1;
+            for (int t = t0 + lane; t <= tf; t += 32) emit_entry(p, tb + t, r, 0, rel - (int64_t)t * P, 0, false);
+        }
+        const int64_t co = b.read_cigar_off[r];
+        const int n_ops = b.read_n_ops[r];
+        const int64_t co_al = co & ~(int64_t)3;
+        const int skip = (int)(co - co_al), n_slots = skip + n_ops;
+        int64_t ref_run = 0, ri_run = 0;
+        // the next tile boundary behind the read's start (one division per read; from there on boundaries are counted)
+        int tcur = rel >= 0 ? (int)(rel / P) + 1 : 0;
+        if (tcur < t0) tcur = t0;
+        int64_t bpos = (int64_t)tcur * P;
+        for (int k0 = 0; k0 < n_slots && tcur <= t1; k0 += 128) {
+            const int k = k0 + lane * 4;
+            uint32_t ws[4];
+            load_ops4(b, co_al, k, skip, n_slots, ws);
             int ra[4], qa[4], sr = 0, sq = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool mine = k + j >= skip && k + j < n_slots;
-                const int op = (int)(ws[j] & 15u), len = (int)(ws[j] >> 4);
-                // :357-563 -- what each op adds to ref_position / read_index (REF_SKIP and PAD also advance the read)
-                ra[j] = (mine && (is_match_op(op) || op == 2 || op == 3 || op == 6)) ? len : 0;
-                qa[j] = (mine && (is_match_op(op) || op == 1 || op == 4 || op == 3 || op == 6)) ? len : 0;
-                sr += ra[j]; sq += qa[j];
-            }
+            for (int j = 0; j < 4; j++) { op_advance(ws[j], ra[j], qa[j]); sr += ra[j]; sq += qa[j]; }
             int ir = sr, iq = sq;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int tr = __shfl_up_sync(0xffffffffu, ir, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
                 if (lane >= d) { ir += tr; iq += tq; }
             }
-            int pr = ref_run + ir - sr, pq = ri_run + iq - sq;  // prefix before this lane's first slot
-            int o_r[4], o_q[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { o_r[j] = pr; o_q[j] = pq; pr += ra[j]; pq += qa[j]; }
-            if (k >= skip && k + 3 < n_slots) {
-                *(int4*)(op_ref + co_al + k) = make_int4(o_r[0], o_r[1], o_r[2], o_r[3]);
-                *(int4*)(op_ri + co_al + k) = make_int4(o_q[0], o_q[1], o_q[2], o_q[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (k + j >= skip && k + j < n_slots) { op_ref[co_al + k + j] = o_r[j]; op_ri[co_al + k + j] = o_q[j]; }
-            }
+            const int64_t a_first = rel + ref_run + (int64_t)(ir - sr), q_first = ri_run + (int64_t)(iq - sq);
             ref_run += __shfl_sync(0xffffffffu, ir, 31);
             ri_run += __shfl_sync(0xffffffffu, iq, 31);
+            while (tcur <= t1 && bpos <= rel + ref_run) {    // boundaries inside the ops of this step: a_k < bpos <= a_k + advance
+                int64_t a_k = a_first, q_k = q_first;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (ra[j] > 0 && a_k < bpos && bpos <= a_k + ra[j])
+                        emit_entry(p, tb + tcur, r, k + j - skip, a_k - bpos, q_k, rel + span_r >= bpos + P);
+                    a_k += ra[j]; q_k += qa[j];
+                }
+                tcur++; bpos += P;
+            }
         }
-        if (lane == 0) read_span[r] = ref_run;
     }
 }
 
@@ -225,7 +342,7 @@ struct TileCtx {
     uint8_t* pflag;       // [P] shared: PF_* of each tile position (phase B onwards)
     uint8_t* near;        // [P] shared: 1 = the position's image row is needed by a window (a site within 16 positions)
     int32_t* site_slot;   // [P] shared (aliases cnt after phase B): site index or -1
-    int32_t* scratch;     // this warp's [4][32] shared scratch
+    int32_t* scratch;     // this warp's shared op table: [3][TBL_STRIDE] (op word, start position, read index)
     int P;
     int n_valid;          // positions of the tile that exist in the region
     int region;
@@ -256,7 +373,6 @@ struct ReadCtx {
     int nv, l_end;          // tile = [0, nv); last region position (an op that starts beyond it is never reached, :355)
     int n_ops, read_len;
     uint32_t rev, inc, dec; // strand; +1 / -1 in the strand's half of a packed counter word
-    const int32_t* oref; const int32_t* ori_a;
     const uint8_t* quals; const uint8_t* bases;
 };
 
@@ -274,8 +390,6 @@ __device__ __forceinline__ ReadCtx make_read_ctx(const SumParams& p, const TileC
     x.rev = b.read_flags[r] & 1u;
     x.inc = x.rev ? 0x10000u : 1u;
     x.dec = 0u - x.inc;
-    x.oref = p.op_ref + x.co;
-    x.ori_a = p.op_ri + x.co;
     x.quals = b.quals + x.bo;
     x.bases = b.bases + x.bo;
     return x;
@@ -341,17 +455,163 @@ __device__ __forceinline__ void count_mismatch(const TileCtx& c, int pl, uint8_t
     }
 }
 
-// Pass 2 of a work unit: the match pieces the warp collected are cut at the read's 16-byte boundaries into SUB-PIECES
-// (a piece of 33 bases has 3 of them), one per lane. A lane loads its aligned 16-base chunk of bases and qualities
-// (two 16-byte loads, neighbouring lanes mostly neighbouring chunks), lines the tile's reference bytes up with the
-// chunk (five aligned shared-memory words + funnel shifts) and tests all 16 bases at once with byte-parallel
-// arithmetic. The code is straight-line for every lane; only EXCEPTIONS cost anything further:
+// ---- the warp's round table ------------------------------------------------------------------------------------------
+// A round stages the (up to) 128 ops [kb, kb + 128) of the read: the words arrive coalesced (lane + 32 u), are transposed
+// through shared memory so that every lane holds four CONSECUTIVE ops, and one pair of shuffle scans gives every op its
+// tile-local start position and the read index in front of it. The same converged code sorts the ops into ONE table of
+// 128 three-word entries -- an op is a match run, an insert, a delete or none of them:
+//   match pieces   [0, n_m)               read index of the first base | tile position of it + length << 16 | 16-byte
+//                                         sub-pieces in front of the piece
+//   inserts        [n_m, n_m + n_ins)     tile-local start | read index in front | length << 1 + "follows a match run"
+//   deletes        from the back          the same
+// so that pass 1 walks inserts and deletes lane per op without diverging on the op type, and pass 2 walks the sub-pieces
+// lane per 16-byte chunk. REF_SKIP / PAD and match bases behind the read's end (both rare) take themselves out of the
+// coverage on the spot.
+struct OpTable {
+    uint32_t* w;          // [ROUND_OPS] op words of the round (0 behind the read's last op)
+    int32_t* e0;          // [ROUND_OPS] entry word 0
+    int32_t* e1;          // [ROUND_OPS] entry word 1
+    int32_t* e2;          // [ROUND_OPS] entry word 2
+    int32_t* qn;          // exception queue: fill count ...
+    uint32_t* q;          // ... and [QCAP] entries: tile position | base << 16 | low-quality flag << 31
+};
+__device__ __forceinline__ OpTable op_table(const TileCtx& c) {
+    OpTable t; t.w = (uint32_t*)c.scratch; t.e0 = c.scratch + ROUND_OPS; t.e1 = c.scratch + 2 * ROUND_OPS;
+    t.e2 = c.scratch + 3 * ROUND_OPS; t.qn = c.scratch + 4 * ROUND_OPS; t.q = (uint32_t*)(t.qn + 1);
+    return t;
+}
+__device__ __forceinline__ void fetch_round(const PvReadBatch& b, const ReadCtx& x, int kb, int lane, uint32_t wv[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = kb + lane + 32 * u;
+        wv[u] = j < x.n_ops ? __ldg(b.cigar + x.co + j) : 0u;
+    }
+}
+struct Round {
+    int cnt;              // staged ops that start at a tile position <= nv (they form a prefix: op starts never decrease; an
+                          // insert / delete that starts right behind the tile still anchors on its last position)
+    int n_m, n_ins, n_del;   // match pieces / inserts / deletes among them
+    int n_sub;            // 16-byte sub-pieces of the match pieces
+    int a_next, ri_next;  // state behind op 127
+    uint32_t w_last;      // op 127
+};
+// the part [s, e) of a reference span that lies in the tile leaves the coverage difference array
+__device__ __forceinline__ void uncover(const TileCtx& c, const ReadCtx& x, int s, int e) {
+    if (s < 0) s = 0;
+    if (e > x.nv) e = x.nv;
+    if (e <= s) return;
+    atomicAdd(&c.cnt[C_T * c.P + s], x.dec);
+    if (e < x.nv) atomicAdd(&c.cnt[C_T * c.P + e], x.inc);
+}
+// ACC: phase A (match pieces filed, coverage corrections applied); else phase C (inserts and deletes only)
+template <bool ACC>
+__device__ __forceinline__ Round stage_round(const TileCtx& c, const ReadCtx& x, const OpTable& t, const uint32_t wv[4], int kb,
+                                             int a_run, int ri_run, uint32_t w_prev, int lane) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) t.w[lane + 32 * u] = wv[u];
+    __syncwarp();
+    const uint4 m = *(const uint4*)(t.w + 4 * lane);
+    const uint32_t ws[4] = {m.x, m.y, m.z, m.w};
+    int ra[4], qa[4], sr = 0, sq = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { op_advance(ws[j], ra[j], qa[j]); sr += ra[j]; sq += qa[j]; }
+    int ir = sr, iq = sq;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int tr = __shfl_up_sync(0xffffffffu, ir, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
+        if (lane >= d) { ir += tr; iq += tq; }
+    }
+    uint32_t pw = __shfl_up_sync(0xffffffffu, ws[3], 1);   // the op in front of this lane's first one
+    if (lane == 0) pw = w_prev;
+    int pr = a_run + ir - sr, pq = ri_run + iq - sq;       // state in front of this lane's first op
+    int f0[4], f1[4], f2[4];                               // entry words of this lane's ops
+    uint32_t kind = 0;                                     // per op: 1 match piece, 2 insert, 3 delete
+    int v = 0, n_m = 0, n_i = 0, n_d = 0, nsp = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int op = (int)(ws[j] & 15u), len = (int)(ws[j] >> 4);
+        f0[j] = pr; f1[j] = pq; f2[j] = (len << 1) | ((is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u) ? 1 : 0);
+        if (kb + 4 * lane + j < x.n_ops && pr <= x.nv) {
+            v++;
+            if (op == 1) { n_i++; kind |= 2u << (2 * j); }
+            else if (op == 2) { n_d++; kind |= 3u << (2 * j); }
+            else if (ACC && pr <= x.l_end) {                 // an op that starts beyond ref_end is never reached (:355)
+                if (is_match_op(op)) {
+                    const int i_lo = pr < 0 ? -pr : 0;
+                    int i_hi = x.nv - pr; if (i_hi > len) i_hi = len;
+                    if (x.read_len - pq < i_hi) {            // rare: the run continues behind the read's last base; those bases are absent
+                        const int have = x.read_len - pq > 0 ? x.read_len - pq : 0;
+                        uncover(c, x, pr + have, pr + len);
+                        i_hi = have < i_hi ? have : i_hi;
+                    }
+                    if (i_hi > i_lo) {
+                        const int ri0 = pq + i_lo, nb = i_hi - i_lo;
+                        f0[j] = ri0; f1[j] = (pr + i_lo) | (nb << 16); f2[j] = nsp;     // f2: sub-pieces of this lane in front (completed below)
+                        nsp += ((ri0 + nb - 1) >> 4) - (ri0 >> 4) + 1;
+                        n_m++; kind |= 1u << (2 * j);
+                    }
+                } else if ((op == 3 || op == 6) && len > 0) { // REF_SKIP / PAD advance the reference without aligning a base
+                    uncover(c, x, pr, pr + len);
+                }
+            }
+        }
+        pw = ws[j];
+        pr += ra[j]; pq += qa[j];
+    }
+    // where this lane's entries go: behind those of the lanes in front of it
+    const uint32_t pk = (uint32_t)v | ((uint32_t)n_m << 8) | ((uint32_t)n_i << 16) | ((uint32_t)n_d << 24);
+    uint32_t incl = pk; int isub = nsp;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tv = __shfl_up_sync(0xffffffffu, incl, d); const int ts = __shfl_up_sync(0xffffffffu, isub, d);
+        if (lane >= d) { incl += tv; isub += ts; }
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    Round r;
+    r.cnt = tot & 0xff; r.n_m = (tot >> 8) & 0xff; r.n_ins = (tot >> 16) & 0xff; r.n_del = (tot >> 24) & 0xff;
+    r.n_sub = __shfl_sync(0xffffffffu, isub, 31);
+    int at_m = ((incl - pk) >> 8) & 0xff, at_i = r.n_m + (((incl - pk) >> 16) & 0xff), at_d = ROUND_OPS - 1 - (((incl - pk) >> 24) & 0xff);
+    const int sub0 = isub - nsp;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t kd = (kind >> (2 * j)) & 3u;
+        if (kd) {
+            const int at = kd == 1u ? at_m++ : kd == 2u ? at_i++ : at_d--;
+            t.e0[at] = f0[j]; t.e1[at] = f1[j]; t.e2[at] = kd == 1u ? f2[j] + sub0 : f2[j];
+        }
+    }
+    r.a_next = __shfl_sync(0xffffffffu, pr, 31);
+    r.ri_next = __shfl_sync(0xffffffffu, pq, 31);
+    r.w_last = __shfl_sync(0xffffffffu, ws[3], 31);
+    __syncwarp();
+    return r;
+}
+
+// an aligned base that needs counting: queued, so that the warp counts a round's exceptions lane-parallel
+__device__ __forceinline__ void count_exception(const TileCtx& c, const ReadCtx& x, uint32_t entry) {
+    const int pl = (int)(entry & 0xffffu);
+    if (entry >> 31) {                                       // below the quality threshold: the base leaves the coverage
+        atomicAdd(&c.cnt[C_T * c.P + pl], x.dec);
+        if (pl + 1 < x.nv) atomicAdd(&c.cnt[C_T * c.P + pl + 1], x.inc);
+    } else {
+        count_mismatch(c, pl, (uint8_t)(entry >> 16), x.inc);
+    }
+}
+__device__ __forceinline__ void push_exception(const TileCtx& c, const ReadCtx& x, const OpTable& t, uint32_t entry) {
+    const int slot = atomicAdd(t.qn, 1);
+    if (slot < QCAP) t.q[slot] = entry;
+    else count_exception(c, x, entry);                       // queue full: count it here
+}
+
+// Pass 2 of a round: the match pieces are cut at the read's 16-byte boundaries into SUB-PIECES (a piece of 33 bases has
+// 3 of them), one per lane. A lane loads its aligned 16-base chunk of bases and qualities (two 16-byte loads,
+// neighbouring lanes mostly neighbouring chunks), lines the tile's reference bytes up with the chunk (five aligned
+// shared-memory words + funnel shifts) and tests all 16 bases at once with byte-parallel arithmetic. The code is
+// straight-line for every lane; only EXCEPTIONS cost anything further, and they are queued and counted lane-parallel:
 //   q <  min_snp_baseq : the base does not count (:378) -> it takes itself out of the coverage difference array
 //   base != reference  : snp_count, class deviation, SNP allele count (:394-425)
-// Table per piece: t_beg = read index of its first base, t_pc = tile position of that base | length << 16,
-// t_sub = number of sub-pieces in front of it.
-__device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx& x, const int32_t* t_beg,
-                            const uint32_t* t_pc, const int32_t* t_sub, int n_e, int n_sub, int lane) {
+__device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx& x, const OpTable& t, int n_e, int n_sub, int lane) {
+    const int32_t* t_beg = t.e0; const uint32_t* t_pc = (const uint32_t*)t.e1; const int32_t* t_sub = t.e2;
     const uint32_t thr4 = (uint32_t)(p.qthr > 255 ? 255 : p.qthr) * 0x01010101u;
     const int range_end = t_beg[n_e - 1] + (int)(t_pc[n_e - 1] >> 16);
     const bool vec_ok = x.bo + (((int64_t)range_end + 15) & ~(int64_t)15) <= p.b.n_bases;
@@ -365,12 +625,10 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
         const int e = e_first + __popc(mask & ((1u << lane) - 1u));
         e_first += __popc(mask);
         const int v = jb + lane;
-        uint32_t ex = 0, lowq16 = 0;
-        int rp = 0, c0 = 0;
         if (v < n_sub) {
             const int beg = t_beg[e];
             const uint32_t pc = t_pc[e];
-            c0 = ((beg >> 4) + (v - t_sub[e])) << 4;           // first read index of the chunk
+            const int c0 = ((beg >> 4) + (v - t_sub[e])) << 4;  // first read index of the chunk
             uint4 ub, uq = make_uint4(0u, 0u, 0u, 0u);
             if (vec_ok) {
                 ub = __ldg((const uint4*)(x.bases + c0));
@@ -379,12 +637,12 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
                 uint32_t tb[4] = {0u, 0u, 0u, 0u}, tq[4] = {0u, 0u, 0u, 0u};
                 for (int j = 0; j < 16 && x.bo + c0 + j < p.b.n_bases; j++) {
                     tb[j >> 2] |= (uint32_t)x.bases[c0 + j] << ((j & 3) * 8);
-                    tq[j >> 2] |= (uint32_t)x.quals[c0 + j] << ((j & 3) * 8);
+                    if (!p.allq) tq[j >> 2] |= (uint32_t)x.quals[c0 + j] << ((j & 3) * 8);
                 }
                 ub = make_uint4(tb[0], tb[1], tb[2], tb[3]); uq = make_uint4(tq[0], tq[1], tq[2], tq[3]);
             }
             int b0 = beg - c0, b1 = b0 + (int)(pc >> 16);      // the piece's bytes of the chunk: [b0, b1) clipped to [0, 16)
-            rp = (int)(pc & 0xffffu) - b0;                     // tile position of the chunk's byte 0 (>= -15)
+            const int rp = (int)(pc & 0xffffu) - b0;           // tile position of the chunk's byte 0 (>= -15)
             b0 = b0 < 0 ? 0 : b0;
             b1 = b1 > 16 ? 16 : b1;
             const uint32_t* sr = (const uint32_t*)(c.ref_s + (rp & ~3));   // ref_s has REF_PAD bytes in front
@@ -393,267 +651,206 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
             const uint32_t n0 = nonzero_mask(ub.x ^ __funnelshift_r(r0, r1, sh)), n1 = nonzero_mask(ub.y ^ __funnelshift_r(r1, r2, sh)),
                            n2 = nonzero_mask(ub.z ^ __funnelshift_r(r2, r3, sh)), n3 = nonzero_mask(ub.w ^ __funnelshift_r(r3, r4, sh));
             const uint32_t bm = (0xffffu >> (16 - b1)) & (0xffffu << b0);
+            uint32_t lowq16 = 0;
             if (!p.allq) {
                 const uint32_t l0 = lowq_mask(uq.x, p.qthr, thr4), l1 = lowq_mask(uq.y, p.qthr, thr4),
                                l2 = lowq_mask(uq.z, p.qthr, thr4), l3 = lowq_mask(uq.w, p.qthr, thr4);
                 lowq16 = (movemask4(l0) | (movemask4(l1) << 4) | (movemask4(l2) << 8) | (movemask4(l3) << 12)) & bm;
             }
-            ex = ((movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12)) & bm) | lowq16;
-        }
-        while (ex) {                                             // a few per cent of the bases
-            const int j = __ffs(ex) - 1;
-            ex &= ex - 1;
-            const int pl = rp + j;
-            if ((lowq16 >> j) & 1u) {
-                atomicAdd(&c.cnt[C_T * c.P + pl], x.dec);
-                if (pl + 1 < x.nv) atomicAdd(&c.cnt[C_T * c.P + pl + 1], x.inc);
-            } else {
-                count_mismatch(c, pl, __ldg(x.bases + c0 + j), x.inc);
+            uint32_t ex = ((movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12)) & bm) | lowq16;
+            while (ex) {                                        // a few per cent of the bases
+                const int j = __ffs(ex) - 1;
+                ex &= ex - 1;
+                const uint32_t wsel = j < 4 ? ub.x : j < 8 ? ub.y : j < 12 ? ub.z : ub.w;
+                push_exception(c, x, t, (uint32_t)(rp + j) | (((wsel >> ((j & 3) * 8)) & 0xffu) << 16) | (((lowq16 >> j) & 1u) << 31));
             }
         }
         __syncwarp();
     }
+    const int nq = *t.qn < QCAP ? *t.qn : QCAP;                 // count the queued exceptions, a lane each
+    for (int i = lane; i < nq; i += 32) count_exception(c, x, t.q[i]);
+    __syncwarp();
+    if (lane == 0) *t.qn = 0;
 }
 
-// Phase A work unit: CIGAR ops [k_begin, k_end) of one read (whole warp); populate_summary_matrix, :337-566.
-// Pass 1, lane per op: a match run only marks where it enters and leaves the tile in the coverage difference array
-// and files its clipped base range in the warp's piece table; inserts and deletes do their anchor counting here (the
-// anchor's missing REFF/REFR decrement of :381-391 is charged by the insert/delete op that follows the run).
-__device__ void accumulate_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int lane) {
+// Phase A work unit: one entry = one read's walk of this tile (whole warp); populate_summary_matrix, :337-566.
+// Aligned coverage is a difference array: the read covers [its start, its start + span) of the tile, and everything that
+// is not an aligned base with a passing quality takes itself out again -- deleted / skipped spans and bases behind the
+// read's end per op, low-quality bases per base. Pass 1, lane per insert and lane per delete: anchor counting (the
+// anchor's missing REFF/REFR decrement of :381-391 is charged by the insert/delete op that follows the run) and the
+// deleted spans. Pass 2 (scan_pieces) compares the aligned bases.
+__device__ void accumulate_entry(const SumParams& p, const TileCtx& c, const TileEntry e, int lane) {
     const PvReadBatch& b = p.b;
-    const ReadCtx x = make_read_ctx(p, c, r);
-    int32_t* t_beg = c.scratch;                              // [TBL]
-    uint32_t* t_pc = (uint32_t*)(c.scratch + TBL);           // [TBL]
-    int32_t* t_sub = c.scratch + 2 * TBL;                    // [TBL]
-    int n_e = 0, n_sub = 0;
-    // ops are walked from k_begin until one starts behind the position right after the tile (op starts never decrease;
-    // an insert/delete at nv still anchors on the tile's last position): no search for the end of the range
-    // the three per-op loads of the NEXT 32 ops are issued before this step's work (they may turn out unused when the walk
-    // ends here: harmless, they stay inside the read's op range)
-    uint32_t w_n = 0u; int32_t oref_n = 0, ori_n = 0;
-    if (k_begin + lane < x.n_ops) { w_n = b.cigar[x.co + k_begin + lane]; oref_n = x.oref[k_begin + lane]; ori_n = x.ori_a[k_begin + lane]; }
-    for (int kb = k_begin; kb < x.n_ops; kb += 32) {
-        const int k = kb + lane;
-        bool have = k < x.n_ops;
-        const uint32_t w = w_n;
-        int64_t a64 = have ? x.rel_t + (int64_t)oref_n : 0;                      // op start, tile-local
-        const int ori_c = ori_n;
-        if (k + 32 < x.n_ops) { w_n = b.cigar[x.co + k + 32]; oref_n = x.oref[k + 32]; ori_n = x.ori_a[k + 32]; }
-        else w_n = 0u;
-        if (a64 > (1 << 30)) a64 = (1 << 30);
-        if (a64 < -(1 << 30)) a64 = -(1 << 30);
-        const int a = (int)a64;
-        const bool beyond = have && a > x.nv;
-        const bool last_step = __any_sync(0xffffffffu, beyond) || kb + 32 >= x.n_ops;
-        have = have && !beyond;
-        const int op = have ? (int)(w & 15u) : 15;
-        const int len = (int)(w >> 4);
-        const int ori = have ? ori_c : 0;
-        uint32_t pw = __shfl_up_sync(0xffffffffu, w, 1);                         // the op in front of this one
-        if (lane == 0) pw = k > 0 ? b.cigar[x.co + k - 1] : 0u;
-        int m_cnt = 0, m_ri0 = 0, m_p0 = 0;
-        const bool reached = a <= x.l_end;                   // an op that starts beyond ref_end is never reached (:355)
-        if (have && is_match_op(op)) {
-            if (reached) {
-                const int i_lo = a < 0 ? -a : 0;
-                int i_hi = x.nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
-                if (i_hi > x.read_len - 1 - ori) i_hi = x.read_len - 1 - ori;
-                if (i_hi >= i_lo) {
-                    m_cnt = i_hi - i_lo + 1; m_ri0 = ori + i_lo; m_p0 = a + i_lo;
-                    atomicAdd(&c.cnt[C_T * c.P + m_p0], x.inc);
-                    if (m_p0 + m_cnt < x.nv) atomicAdd(&c.cnt[C_T * c.P + m_p0 + m_cnt], x.dec);
+    const ReadCtx x = make_read_ctx(p, c, e.read);
+    const OpTable t = op_table(c);
+    int kb = e.k, a_run = e.a, ri_run = e.ri;
+    uint32_t w_prev = kb > 0 ? __ldg(b.cigar + x.co + kb - 1) : 0u;   // the op in front of the round's first one
+    uint32_t wv[4];
+    fetch_round(b, x, kb, lane, wv);
+    if (lane == 0) {                                          // the read's reference span inside the tile
+        int64_t s = x.rel_t, en = x.rel_t + (int64_t)p.read_span[e.read];
+        if (s < 0) s = 0;
+        if (en > x.nv) en = x.nv;
+        if (en > s) {
+            atomicAdd(&c.cnt[C_T * c.P + (int)s], x.inc);
+            if (en < x.nv) atomicAdd(&c.cnt[C_T * c.P + (int)en], x.dec);
+        }
+    }
+    while (true) {
+        const Round rd = stage_round<true>(c, x, t, wv, kb, a_run, ri_run, w_prev, lane);
+        const bool more = rd.cnt == ROUND_OPS && kb + ROUND_OPS < x.n_ops;
+        if (more) fetch_round(b, x, kb + ROUND_OPS, lane, wv);           // in flight while this round is worked on
+        for (int i = lane; i < rd.n_ins; i += 32) {                      // ---- inserts, :431-490
+            const int a = t.e0[rd.n_m + i], ori = t.e1[rd.n_m + i], f = t.e2[rd.n_m + i], len = f >> 1;
+            const int ol = a - 1;                                        // anchor position
+            if (ol < 0 || ol >= x.nv) continue;
+            const bool anchor_ok = ori >= 1 && ori - 1 < x.read_len;     // the anchor base exists in the read
+            const int qa = !anchor_ok ? 0 : (p.allq ? 255 : (int)x.quals[ori - 1]);
+            // anchor rule (:381-391): the base in front of this op is the last base of a match run -> that base keeps
+            // its REFF/REFR decrement for itself. Depends only on the op TYPE, not on whether this op is reached.
+            if ((f & 1) && anchor_ok && qa >= p.qthr) atomicAdd(&c.cnt[C_SKIP * c.P + ol], x.inc);
+            if (a <= x.l_end && anchor_ok) {                             // reached (:355)
+                const int n = len + 1;                                   // :442
+                int elen = n;                                            // substr truncation, :439
+                if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
+                if (insert_quality_pass(p, x, ori, n, qa)) {
+                    if (qa < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
+                    if (1 + elen <= 61) {                                // :461-464
+                        if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], x.inc);
+                        atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
+                    }
                 }
             }
-        } else if (have && (op == 1 || op == 2)) {
-            const int ol = a - 1;                                                 // anchor position
+        }
+        for (int i = lane; i < rd.n_del; i += 32) {                      // ---- deletes, :491-555
+            const int a = t.e0[ROUND_OPS - 1 - i], ori = t.e1[ROUND_OPS - 1 - i], f = t.e2[ROUND_OPS - 1 - i], len = f >> 1;
+            const bool reached = a <= x.l_end;
+            const int ol = a - 1;
             if (ol >= 0 && ol < x.nv) {
-                const bool anchor_ok = ori >= 1 && ori - 1 < x.read_len;          // the anchor base exists in the read
+                const bool anchor_ok = ori >= 1 && ori - 1 < x.read_len;
                 const int qa = !anchor_ok ? 0 : (p.allq ? 255 : (int)x.quals[ori - 1]);
-                // anchor rule (:381-391): the base in front of this op is the last base of a match run -> that base keeps
-                // its REFF/REFR decrement for itself. Depends only on the op TYPE, not on whether this op is reached.
-                if (k > 0 && anchor_ok && is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u && qa >= p.qthr)
-                    atomicAdd(&c.cnt[C_SKIP * c.P + ol], x.inc);
-                if (reached && op == 1) {                                         // IN, :431-490
-                    if (anchor_ok) {
-                        const int n = len + 1;                                    // :442
-                        int elen = n;                                             // substr truncation, :439
-                        if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
-                        if (insert_quality_pass(p, x, ori, n, qa)) {
-                            if (qa < p.qthr) atomicAdd(&c.cnt[C_COV2 * c.P + ol], 1u);   // :453-454
-                            if (1 + elen <= 61) {                                 // :461-464
-                                if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 4) * c.P + ol], x.inc);
-                                atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 1u);
-                            }
-                        }
-                    }
-                } else if (reached) {                                             // DEL anchor, :491-540
-                    const int64_t rem = c.ref_len - c.t_lo - ol;                  // reference bytes from the anchor on
-                    int elen = len + 1;                                           // substr truncation, :500
+                if ((f & 1) && anchor_ok && qa >= p.qthr) atomicAdd(&c.cnt[C_SKIP * c.P + ol], x.inc);
+                if (reached) {
+                    const int64_t rem = c.ref_len - c.t_lo - ol;         // reference bytes from the anchor on
+                    int elen = len + 1;                                  // substr truncation, :500
                     if ((int64_t)elen > rem) elen = (int)rem;
                     if (c.rcls[ol] != 0xff) atomicAdd(&c.cnt[(C_CLS + 5) * c.P + ol], x.inc);   // :497
                     if (1 + elen <= 61) atomicAdd(&c.cnt[C_INSDEL * c.P + ol], 0x10000u);       // :511-512
                 }
             }
-            if (reached && op == 2) {                                             // deleted span, :542-552
-                const int i_lo = a < 0 ? -a : 0;
-                int i_hi = x.nv - 1 - a; if (i_hi > len - 1) i_hi = len - 1;
-                if (i_hi >= i_lo) {
-                    atomicAdd(&c.cnt[C_DELD * c.P + a + i_lo], x.inc);
-                    if (a + i_hi + 1 < x.nv) atomicAdd(&c.cnt[C_DELD * c.P + a + i_hi + 1], x.dec);
+            if (reached) {                                               // deleted span, :542-552: '*' instead of an aligned base
+                const int s0 = a < 0 ? 0 : a;
+                const int e0 = a + len < x.nv ? a + len : x.nv;
+                if (e0 > s0) {
+                    atomicAdd(&c.cnt[C_DELD * c.P + s0], x.inc);
+                    atomicAdd(&c.cnt[C_T * c.P + s0], x.dec);
+                    if (e0 < x.nv) { atomicAdd(&c.cnt[C_DELD * c.P + e0], x.dec); atomicAdd(&c.cnt[C_T * c.P + e0], x.inc); }
                 }
             }
         }
-        // file the match pieces of these 32 ops (in op order) with the running count of 16-base sub-pieces in front of
-        // each; scan the table when the next 32 ops might overflow it
-        const int nsp = m_cnt > 0 ? ((m_ri0 + m_cnt - 1) >> 4) - (m_ri0 >> 4) + 1 : 0;
-        int incl = nsp;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const unsigned nz = __ballot_sync(0xffffffffu, m_cnt > 0);
-        if (m_cnt > 0) {
-            const int at = n_e + __popc(nz & ((1u << lane) - 1u));
-            t_beg[at] = m_ri0;
-            t_pc[at] = (uint32_t)m_p0 | ((uint32_t)m_cnt << 16);
-            t_sub[at] = n_sub + incl - nsp;
-        }
-        n_e += __popc(nz);
-        n_sub += __shfl_sync(0xffffffffu, incl, 31);
-        if (n_e > TBL - 32 || last_step) {
-            __syncwarp();
-            if (n_e > 0) scan_pieces(p, c, x, t_beg, t_pc, t_sub, n_e, n_sub, lane);
-            n_e = 0; n_sub = 0;
-            __syncwarp();
-        }
-        if (last_step) break;
+        if (rd.n_m > 0) scan_pieces(p, c, x, t, rd.n_m, rd.n_sub, lane);
+        __syncwarp();
+        if (!more) break;
+        w_prev = rd.w_last;
+        kb += ROUND_OPS; a_run = rd.a_next; ri_run = rd.ri_next;
     }
 }
 
-
-// Phase C work unit: re-walks CIGAR ops [k_begin, k_end) of one read (whole warp, lane per op) and records the
-// insert/delete alleles of registered sites (the AlleleFrequencyMap updates of :458-487 and :507-535, needed only
-// where the site thresholds passed).
-__device__ void record_unit(const SumParams& p, const TileCtx& c, int64_t r, int k_begin, int lane) {
+// Phase C work unit: re-walks the ops of one entry (whole warp, lane per op) and records the insert/delete alleles of
+// registered sites (the AlleleFrequencyMap updates of :458-487 and :507-535, needed only where the site thresholds passed).
+__device__ void record_entry(const SumParams& p, const TileCtx& c, const TileEntry e, int lane) {
     const PvReadBatch& b = p.b;
-    const ReadCtx x = make_read_ctx(p, c, r);
-    for (int kb = k_begin; kb < x.n_ops; kb += 32) {
-        const int k = kb + lane;
-        const bool in = k < x.n_ops;
-        const uint32_t w = in ? b.cigar[x.co + k] : 0u;
-        int64_t a64 = in ? x.rel_t + (int64_t)x.oref[k] : (int64_t)(1 << 30);
-        if (a64 > (1 << 30)) a64 = (1 << 30);
-        if (a64 < -(1 << 30)) a64 = -(1 << 30);
-        const int a = (int)a64;
-        if (__all_sync(0xffffffffu, a > x.nv)) break;          // everything from here on starts behind the tile
-        const int op = (int)(w & 15u);
-        if (!in || (op != 1 && op != 2)) continue;
-        const int len = (int)(w >> 4);
-        if (a > x.l_end) continue;
-        const int ol = a - 1;
-        if (ol < 0 || ol >= x.nv) continue;
-        const int s = c.site_slot[ol];
-        if (s < 0) continue;
-        if (op == 1) {
-            const int ori = x.ori_a[k];
-            if (!(c.pflag[ol] & PF_INS) || ori < 1 || ori - 1 >= x.read_len) continue;
-            const int n = len + 1;
-            int elen = n;
-            if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
-            if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n, p.allq ? 255 : (int)x.quals[ori - 1])) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
-        } else {
-            if (!(c.pflag[ol] & PF_DEL)) continue;
-            const int64_t rem = c.ref_len - c.t_lo - ol;
-            int elen = len + 1;
-            if ((int64_t)elen > rem) elen = (int)rem;
-            if (1 + elen <= 61) record_event(p, s, 3, (int)x.rev, elen, c.ref_off + c.t_lo + ol);
+    const ReadCtx x = make_read_ctx(p, c, e.read);
+    const OpTable t = op_table(c);
+    int kb = e.k, a_run = e.a, ri_run = e.ri;
+    uint32_t wv[4];
+    fetch_round(b, x, kb, lane, wv);
+    while (true) {
+        const Round rd = stage_round<false>(c, x, t, wv, kb, a_run, ri_run, 0u, lane);
+        const bool more = rd.cnt == ROUND_OPS && kb + ROUND_OPS < x.n_ops;
+        if (more) fetch_round(b, x, kb + ROUND_OPS, lane, wv);
+        for (int i = lane; i < rd.n_ins + rd.n_del; i += 32) {
+            const bool ins = i < rd.n_ins;
+            const int at = ins ? rd.n_m + i : ROUND_OPS - 1 - (i - rd.n_ins);
+            const int a = t.e0[at], len = t.e2[at] >> 1;
+            if (a > x.l_end) continue;
+            const int ol = a - 1;
+            if (ol < 0 || ol >= x.nv) continue;
+            const int s = c.site_slot[ol];
+            if (s < 0) continue;
+            if (ins) {
+                const int ori = t.e1[at];
+                if (!(c.pflag[ol] & PF_INS) || ori < 1 || ori - 1 >= x.read_len) continue;
+                const int n = len + 1;
+                int elen = n;
+                if (elen > x.read_len - (ori - 1)) elen = x.read_len - (ori - 1);
+                if (1 + elen <= 61 && insert_quality_pass(p, x, ori, n, p.allq ? 255 : (int)x.quals[ori - 1])) record_event(p, s, 2, (int)x.rev, elen, x.bo + ori - 1);
+            } else {
+                if (!(c.pflag[ol] & PF_DEL)) continue;
+                const int64_t rem = c.ref_len - c.t_lo - ol;
+                int elen = len + 1;
+                if ((int64_t)elen > rem) elen = (int)rem;
+                if (1 + elen <= 61) record_event(p, s, 3, (int)x.rev, elen, c.ref_off + c.t_lo + ol);
+            }
         }
+        __syncwarp();
+        if (!more) break;
+        kb += ROUND_OPS; a_run = rd.a_next; ri_run = rd.ri_next;
     }
 }
-
 
 // SNP alleles whose byte is not an upper-case A/C/G/T (":398 candidate_string = '1' + alt" keeps the raw byte): rare,
-// recorded after the fact for registered sites only. One thread per read.
-__device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, int64_t r) {
+// recorded after the fact for registered sites only. One thread per entry of the tile: walks the read's ops from the
+// entry's start until it finds the op that covers tile position ol.
+__device__ void record_other_snp(const SumParams& p, const TileCtx& c, int ol, const TileEntry e) {
     const PvReadBatch& b = p.b;
-    if (b.read_mapq[r] == 0) return;
-    const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
-    const int64_t x = c.t_lo + ol - rel;                 // reference offset inside the read
-    if (x < 0 || x >= (int64_t)p.read_span[r]) return;
+    const int64_t r = e.read;
     const int64_t co = b.read_cigar_off[r];
     const int n_ops = b.read_n_ops[r];
-    const int32_t* oref = p.op_ref + co;
-    int lo = 0, hi = n_ops;                              // upper_bound: first k with op_ref[k] > x
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)oref[mid] <= x) lo = mid + 1; else hi = mid; }
-    const int k = lo - 1;
-    if (k < 0) return;
-    const uint32_t w = b.cigar[co + k];
-    if (!is_match_op((int)(w & 15u))) return;
-    const int64_t i = x - oref[k];
-    if (i >= (int64_t)(w >> 4)) return;
-    const int64_t idx = (int64_t)p.op_ri[co + k] + i;
-    if (idx >= b.read_len[r]) return;
-    const int64_t bo = b.read_base_off[r];
-    const uint8_t base = b.bases[bo + idx];
-    if (!p.allq && (int)b.quals[bo + idx] < p.qthr) return;
-    if (base == c.ref_s[ol] || acgt_code(base) >= 0) return;
-    record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
+    const int64_t l_end = c.L - 1 - c.t_lo;
+    int a = e.a, ri = e.ri;
+    for (int k = e.k; k < n_ops; k++) {
+        if (a > ol || (int64_t)a > l_end) return;
+        const uint32_t w = b.cigar[co + k];
+        int ra, qa;
+        op_advance(w, ra, qa);
+        if (ra > 0 && ol < a + ra) {
+            if (!is_match_op((int)(w & 15u))) return;
+            const int64_t idx = (int64_t)ri + (ol - a);
+            if (idx >= b.read_len[r]) return;
+            const int64_t bo = b.read_base_off[r];
+            const uint8_t base = b.bases[bo + idx];
+            if (!p.allq && (int)b.quals[bo + idx] < p.qthr) return;
+            if (base == c.ref_s[ol] || acgt_code(base) >= 0) return;
+            record_event(p, c.site_slot[ol], 1, (int)(b.read_flags[r] & 1u), 1, bo + idx);
+            return;
+        }
+        a += ra; ri += qa;
+    }
 }
 
-// The tile's work list: every read of the region that touches the tile. A warp that pulls a read first finds the read's
-// first op inside the tile with one warp-wide 32-ary search in the CIGAR prefix (coalesced probes, 2-3 rounds), then
-// walks the ops until they leave the tile. No thread-serial set-up phase: the search of one warp overlaps the walking
-// of the others.
-
+// The tile's work list (K0): warps pull entries from a shared ticket counter.
 template <int MODE>
-__device__ void for_each_unit(const SumParams& p, const TileCtx& c, int32_t* s_list, int* s_n, int* s_next, int* s_n_short) {
-    const PvReadBatch& b = p.b;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
-    const int64_t t_lo = c.t_lo, t_hi = c.t_lo + c.n_valid - 1;
-    for (int64_t base = rb; base < re; base += LIST_CAP) {
-        if (tid == 0) { *s_n = 0; *s_next = 0; *s_n_short = 0; }
-        __syncthreads();
-        const int64_t end = base + LIST_CAP < re ? base + LIST_CAP : re;
-        for (int64_t r = base + tid; r < end; r += blockDim.x) {
-            if (b.read_mapq[r] == 0) continue;                                   // :619
-            const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
-            // touched positions: aligned/deleted [rel, rel+span-1] and insert/delete anchors [rel-1, rel+span-1]
-            const int64_t last = rel + (int64_t)p.read_span[r] - 1;
-            if (rel - 1 > t_hi || last < t_lo) continue;
-            // longest units first: reads that cover the whole tile are listed from the front, reads that start or end
-            // inside it (less work) from the back, so the round's last units are short ones
-            if (rel <= t_lo && last >= t_hi) s_list[atomicAdd(s_n, 1)] = (int32_t)(r - base);
-            else s_list[LIST_CAP - 1 - atomicAdd(s_n_short, 1)] = (int32_t)(r - base);
-        }
-        __syncthreads();
-        const int n_long = *s_n, n = n_long + *s_n_short;
-        while (true) {
-            int i = 0;
-            if (lane == 0) i = atomicAdd(s_next, 1);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            if (i >= n) break;
-            if (i >= n_long) i = LIST_CAP - 1 - (i - n_long);
-            const int64_t r = base + s_list[i];
-            // first op: one op before the first a_k = rel + op_ref[k] >= t_lo may extend into the tile; the walk ends at the
-            // first op that starts behind t_hi + 1 (an insert/delete right behind the tile anchors on its last position)
-            const int64_t rel = b.read_pos[r] - b.region_ref_start[c.region];
-            const int32_t* oref = p.op_ref + b.read_cigar_off[r];
-            const int n_ops = b.read_n_ops[r];
-            int k_lo = warp_lower_bound(oref, n_ops, t_lo - rel, lane) - 1;
-            if (k_lo < 0) k_lo = 0;
-            if (MODE == 0) accumulate_unit(p, c, r, k_lo, lane);
-            else record_unit(p, c, r, k_lo, lane);
-        }
-        __syncthreads();
+__device__ void for_each_entry(const SumParams& p, const TileCtx& c, const TileEntry* ent, int n_ent, int* s_next) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) *s_next = 0;
+    __syncthreads();
+    while (true) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(s_next, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_ent) break;
+        const int4 raw = __ldg((const int4*)(ent + i));
+        TileEntry e; e.read = raw.x; e.k = raw.y; e.a = raw.z; e.ri = raw.w;
+        if (MODE == 0) accumulate_entry(p, c, e, lane);
+        else record_entry(p, c, e, lane);
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(const SumParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int32_t s_list[LIST_CAP];
-    __shared__ int s_n, s_next, s_n_short, s_any_events, s_any_other;
+    __shared__ int s_next, s_any_events, s_any_other;
 
     const PvReadBatch& b = p.b;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -671,6 +868,7 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     c.lut = c.rcls + P;
     c.near = c.lut + 256;
     if (tid < 256) c.lut[tid] = (uint8_t)(base_class((uint8_t)tid) | (acgt_code((uint8_t)tid) >= 0 ? 8 : 0));
+    if (lane == 0) *op_table(c).qn = 0;
     c.region = p.tile_region[blockIdx.x];
     c.t_lo = p.tile_start[blockIdx.x];
     c.L = b.region_ref_end[c.region] - b.region_ref_start[c.region] + 1;
@@ -693,7 +891,10 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     __syncthreads();
 
     // ---- phase A: accumulate -----------------------------------------------------------------------------------
-    for_each_unit<0>(p, c, s_list, &s_n, &s_next, &s_n_short);
+    if (p.ctr[CTR_STATUS] & ST_ENTRY_OVF) return;
+    const TileEntry* ent = p.entries + p.tile_off[blockIdx.x];
+    const int n_ent = p.tile_off[blockIdx.x + 1] - p.tile_off[blockIdx.x];
+    for_each_entry<0>(p, c, ent, n_ent, &s_next);
 
     // ---- phase B: image rows, site thresholds ---------------------------------------------------------------------
     // difference arrays -> counts: in-place inclusive prefix sums over the tile (packed words, modulo 2^32: the true
@@ -824,12 +1025,11 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     }
     __threadfence();      // site records (n_ev, ev_off) are read back through global memory by record_event
     __syncthreads();
-    for_each_unit<1>(p, c, s_list, &s_n, &s_next, &s_n_short);
+    for_each_entry<1>(p, c, ent, n_ent, &s_next);
     if (s_any_other) {
-        const int64_t rb = b.region_read_begin[c.region], re = b.region_read_begin[c.region + 1];
         for (int i = 0; i < c.n_valid; i++) {
             if (!(c.pflag[i] & PF_OTHER)) continue;
-            for (int64_t r = rb + tid; r < re; r += K1_THREADS) record_other_snp(p, c, i, r);
+            for (int j = tid; j < n_ent; j += K1_THREADS) record_other_snp(p, c, i, ent[j]);
         }
     }
 }
@@ -985,7 +1185,7 @@ __global__ void emit_window_kernel(const SumParams p, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------------------
 struct Plan {
     int P; int64_t n_tiles;
-    int64_t site_cap, ev_cap, cand_cap;
+    int64_t site_cap, ev_cap, cand_cap, entry_cap;
     size_t sort_tmp;
 };
 
@@ -999,10 +1199,15 @@ int choose_tile(int64_t total_positions, int32_t n_regions) {
 
 size_t k1_smem_bytes(int P) { return (size_t)NC * P * 4 + (size_t)K1_WARPS * WARP_SCRATCH * 4 + REF_PAD + 4 * (size_t)P + 32 + 256 + 16; }
 
-Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t capacity) {
+Plan make_plan(int64_t n_reads, int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_t max_region_len, int64_t capacity) {
     Plan pl;
     pl.P = choose_tile(total_positions, n_regions);
     pl.n_tiles = total_positions / pl.P + n_regions + 1;     // upper bound
+    // (tile, read) entries: a read touches at most every tile of its own region
+    if (max_region_len <= 0 || max_region_len > total_positions) max_region_len = total_positions;
+    const int64_t tiles_per_region = max_region_len / pl.P + 1;
+    pl.entry_cap = n_reads > 0 ? ((double)n_reads * (double)tiles_per_region > 2.0e9 ? 0x7fffff00ll : n_reads * tiles_per_region) : 1;
+    if (pl.entry_cap > 0x7fffff00ll) pl.entry_cap = 0x7fffff00ll;
     pl.cand_cap = capacity < 1 ? 1 : capacity;
     pl.site_cap = 4 * pl.cand_cap + 4096;
     if (pl.site_cap > total_positions) pl.site_cap = total_positions > 0 ? total_positions : 1;
@@ -1019,7 +1224,8 @@ Plan make_plan(int64_t n_ops, int32_t n_regions, int64_t total_positions, int64_
 
 struct WsLayout {
     int64_t* pos_off; int32_t* tile_region; int32_t* tile_start;
-    int32_t* op_ref; int32_t* op_ri; int32_t* read_span;
+    int32_t* tile_base; int32_t* tile_count; int32_t* tile_fill; int32_t* tile_off; int32_t* read_region; TileEntry* entries;
+    int32_t* read_span;
     int16_t* img; SiteRec* sites; Event* events; CandRec* cands;
     unsigned long long* key_in; unsigned long long* key_out; uint32_t* val_in; uint32_t* val_out;
     void* sort_tmp; int32_t* ctr;
@@ -1034,8 +1240,12 @@ WsLayout carve(void* base, int64_t size, const Plan& pl, int64_t n_reads, int64_
     w.pos_off = a.take<int64_t>(n_regions + 1);
     w.tile_region = a.take<int32_t>(pl.n_tiles);
     w.tile_start = a.take<int32_t>(pl.n_tiles);
-    w.op_ref = a.take<int32_t>(n_ops);
-    w.op_ri = a.take<int32_t>(n_ops);
+    w.tile_base = a.take<int32_t>(n_regions + 1);
+    w.tile_count = a.take<int32_t>(3 * pl.n_tiles);              // counts, then the two fill cursors per tile: zeroed together
+    w.tile_fill = w.tile_count ? w.tile_count + pl.n_tiles : nullptr;
+    w.tile_off = a.take<int32_t>(pl.n_tiles + 1);
+    w.read_region = a.take<int32_t>(n_reads);
+    w.entries = a.take<TileEntry>(pl.entry_cap);
     w.read_span = a.take<int32_t>(n_reads);
     w.img = need_img ? a.take<int16_t>(total_positions * PV_FEATURES) : nullptr;
     w.sites = a.take<SiteRec>(pl.site_cap);
@@ -1053,8 +1263,8 @@ WsLayout carve(void* base, int64_t size, const Plan& pl, int64_t n_reads, int64_
 }  // namespace
 
 extern "C" int64_t pv_summary_workspace_bytes(int64_t n_reads, int64_t n_ops, int32_t n_regions,
-                                              int64_t total_positions, int64_t capacity) {
-    const Plan pl = make_plan(n_ops, n_regions, total_positions, capacity);
+                                              int64_t total_positions, int64_t max_region_len, int64_t capacity) {
+    const Plan pl = make_plan(n_reads, n_ops, n_regions, total_positions, max_region_len, capacity);
     return carve(nullptr, 0, pl, n_reads, n_ops, n_regions, total_positions, true).bytes;
 }
 
@@ -1074,7 +1284,9 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
         PV_CUDA_CHECK(cudaMemsetAsync(n_candidates_dev, 0, sizeof(int64_t), stream));
         return PV_OK;
     }
-    const Plan pl = make_plan(b.n_ops, b.n_regions, total_positions, out->capacity);
+    int64_t max_region_len = 0;
+    for (int32_t r = 0; r < b.n_regions; r++) if (region_len_host[r] > max_region_len) max_region_len = region_len_host[r];
+    const Plan pl = make_plan(b.n_reads, b.n_ops, b.n_regions, total_positions, max_region_len, out->capacity);
     const WsLayout w = carve(workspace_dev, workspace_bytes, pl, b.n_reads, b.n_ops, b.n_regions, total_positions,
                              dense_image_dev == nullptr);
     if (w.bytes > workspace_bytes)
@@ -1082,12 +1294,13 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
 
     // host-side planning: dense position offsets and the tile table
     std::vector<int64_t> pos_off(b.n_regions + 1, 0);
-    std::vector<int32_t> t_region, t_start;
+    std::vector<int32_t> t_region, t_start, t_base(b.n_regions + 1, 0);
     for (int32_t r = 0; r < b.n_regions; r++) {
         const int64_t L = region_len_host[r];
         if (L <= 0 || L > 0x7fffffffll) return pv::set_error(PV_EINVAL, "region %d has length %lld", r, (long long)L);
         pos_off[r + 1] = pos_off[r] + L;
         for (int64_t s = 0; s < L; s += pl.P) { t_region.push_back(r); t_start.push_back((int32_t)s); }
+        t_base[r + 1] = (int32_t)t_region.size();
     }
     if (pos_off[b.n_regions] != total_positions) return pv::set_error(PV_EINVAL, "total_positions does not match region lengths");
     if (total_positions >= (1ll << 40)) return pv::set_error(PV_EINVAL, "too many positions in one batch");
@@ -1096,12 +1309,16 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     PV_CUDA_CHECK(cudaMemcpyAsync(w.pos_off, pos_off.data(), pos_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
     PV_CUDA_CHECK(cudaMemcpyAsync(w.tile_region, t_region.data(), n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     PV_CUDA_CHECK(cudaMemcpyAsync(w.tile_start, t_start.data(), n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    PV_CUDA_CHECK(cudaMemcpyAsync(w.tile_base, t_base.data(), t_base.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    PV_CUDA_CHECK(cudaMemsetAsync(w.tile_count, 0, 3 * pl.n_tiles * sizeof(int32_t), stream));
     PV_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_COUNT * sizeof(int32_t), stream));
     PV_CUDA_CHECK(cudaMemsetAsync(w.key_in, 0xff, pl.cand_cap * sizeof(unsigned long long), stream));
 
     SumParams p;
     p.b = b; p.pos_off = w.pos_off; p.tile_region = w.tile_region; p.tile_start = w.tile_start; p.P = pl.P;
-    p.op_ref = w.op_ref; p.op_ri = w.op_ri; p.read_span = w.read_span;
+    p.tile_base = w.tile_base; p.n_tiles = (int32_t)n_tiles; p.read_region = w.read_region; p.tile_count = w.tile_count;
+    p.tile_fill = w.tile_fill; p.tile_off = w.tile_off; p.entries = w.entries; p.entry_cap = (int32_t)pl.entry_cap;
+    p.read_span = w.read_span;
     p.img = dense_image_dev ? dense_image_dev : w.img;
     p.img_all = dense_image_dev ? 1 : 0;
     p.sites = w.sites; p.site_cap = (int32_t)pl.site_cap; p.events = w.events; p.ev_cap = (int32_t)pl.ev_cap;
@@ -1118,13 +1335,18 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     p.t = *thr;
 
     const int sms = pv::sm_count();
-    if (b.n_reads > 0) {
+    {
         int64_t blocks = (b.n_reads + 7) / 8;            // 8 warps per 256-thread block
         if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+        if (blocks < 1) blocks = 1;
         pv::prof_begin(pv::FAM_SUM_PREFIX, stream);
-        cigar_prefix_kernel<<<(unsigned)blocks, 256, 0, stream>>>(b, w.op_ref, w.op_ri, w.read_span, w.ctr + CTR_K0_TICKET);
+        read_span_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
-        pv::prof_end(pv::FAM_SUM_PREFIX, stream, 1);
+        tile_scan_kernel<<<1, 1024, 0, stream>>>(p);
+        PV_CUDA_CHECK(cudaGetLastError());
+        tile_entry_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+        PV_CUDA_CHECK(cudaGetLastError());
+        pv::prof_end(pv::FAM_SUM_PREFIX, stream, 3);
     }
     const size_t smem = k1_smem_bytes(pl.P);
     PV_CUDA_CHECK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -219,11 +219,16 @@ class DeviceBatch:
 class SummaryWorkspace:
     """Caller-allocated outputs + scratch of ``pv_summary_regions`` (reused across calls of the same shape)."""
 
-    def __init__(self, n_reads, n_ops, n_regions, total_positions, capacity, device="cuda", want_dense=False):
-        lib = capi.load()
+    @staticmethod
+    def scratch_bytes(n_reads, n_ops, n_regions, total_positions, capacity, max_region_len=0) -> int:
+        return int(capi.load().pv_summary_workspace_bytes(int(n_reads), int(n_ops), int(n_regions), int(total_positions),
+                                                          int(max_region_len), int(capacity)))
+
+    def __init__(self, n_reads, n_ops, n_regions, total_positions, capacity, device="cuda", want_dense=False,
+                 max_region_len=0, min_scratch_bytes=0):
         self.capacity = int(capacity)
         dev = torch.device(device)
-        ws_bytes = int(lib.pv_summary_workspace_bytes(n_reads, n_ops, n_regions, total_positions, capacity))
+        ws_bytes = max(self.scratch_bytes(n_reads, n_ops, n_regions, total_positions, capacity, max_region_len), int(min_scratch_bytes))
         self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         self.windows = torch.empty((capacity, capi.PV_WINDOW, capi.PV_FEATURES), dtype=torch.int16, device=dev)
         self.position = torch.empty(capacity, dtype=torch.int64, device=dev)
@@ -241,7 +246,8 @@ class SummaryWorkspace:
     @classmethod
     def for_batch(cls, db: DeviceBatch, capacity: int, want_dense=False) -> "SummaryWorkspace":
         h = db.host
-        return cls(h.n_reads, h.n_ops, h.n_regions, db.total_positions, capacity, db.device, want_dense)
+        return cls(h.n_reads, h.n_ops, h.n_regions, db.total_positions, capacity, db.device, want_dense,
+                   max_region_len=int(db.region_len.max()) if db.region_len.size else 0)
 
     def status(self) -> int:
         return int(self.ws[12:16].view(torch.int32).item())

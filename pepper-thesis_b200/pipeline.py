@@ -120,14 +120,18 @@ class HotPath:
     def _key(self, db: dev.DeviceBatch):
         h = db.host
         cap = max(4096, int(db.total_positions / 1000.0 * self.cand_per_kbp))
-        return (h.n_reads, h.n_ops, h.n_regions, db.total_positions, cap)
+        return (h.n_reads, h.n_ops, h.n_regions, db.total_positions, cap, int(db.region_len.max()) if db.region_len.size else 0)
 
     def _ensure_workspaces(self, db: dev.DeviceBatch):
         key = self._key(db)
-        if self._ws is None or any(a < b for a, b in zip(self._ws_key, key)):
+        # the scratch a shape needs is not monotone in the shape (a smaller batch gets smaller tiles, hence more of them):
+        # the pool is checked against the bytes this very shape asks for, not against the shape it was built for
+        need = dev.SummaryWorkspace.scratch_bytes(key[0], key[1], key[2], key[3], key[4], key[5])
+        if self._ws is None or key[4] > self._ws[0].capacity or need > self._ws[0].ws.numel():
             torch.cuda.current_stream(self.device).synchronize()
             grow = tuple(int(max(a, b) * 1.05) + 16 for a, b in zip(self._ws_key or key, key))
-            self._ws = [dev.SummaryWorkspace(grow[0], grow[1], grow[2], grow[3], grow[4], self.device) for _ in range(2)]
+            self._ws = [dev.SummaryWorkspace(grow[0], grow[1], grow[2], grow[3], grow[4], self.device, max_region_len=grow[5],
+                                             min_scratch_bytes=int(need * 1.05)) for _ in range(2)]
             self._ws_key = grow
             self._host_counts = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
             return True
