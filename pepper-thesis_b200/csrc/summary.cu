@@ -43,6 +43,7 @@ constexpr int K1_THREADS = PV_K1_THREADS;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
 constexpr int P_MAX = PV_K1_PMAX;   // 2 CTAs per SM: 16 words x 1088 positions = 68 KB of counters each
+constexpr int FREQ_TABLE = 4096; // coverages with a precomputed site-threshold entry (deeper positions divide)
 constexpr int K0_CHUNK = 4;      // reads a K0 warp takes per ticket
 constexpr int ROUND_OPS = 128;   // CIGAR ops a warp stages per round (four per lane)
 constexpr int QCAP = 63;         // exceptions (mismatches, low-quality bases) a warp queues per round before it counts them
@@ -129,6 +130,7 @@ struct SumParams {
     Event* events; int32_t ev_cap;
     CandRec* cands; unsigned long long* cand_key; int32_t cand_cap;
     int32_t* ctr;                 // CTR_*
+    ushort4* freq_min;            // [FREQ_TABLE] smallest snp / insert / delete count that passes its frequency threshold at coverage c
     int32_t qthr;                 // ceil(min_snp_baseq): q >= min_snp_baseq  <=>  q >= qthr for integer q
     PvThresholds t;
 };
@@ -147,7 +149,7 @@ __device__ __forceinline__ int ref_value(uint8_t b) {           // get_reference
 __device__ __forceinline__ int acgt_code(uint8_t b) {           // upper-case only: dense SNP allele slot
     return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1;
 }
-__device__ __forceinline__ bool is_match_op(int op) { return op == 0 || op == 7 || op == 8; }
+__device__ __forceinline__ bool is_match_op(int op) { return (0x181u >> op) & 1u; }     // M, =, X
 __device__ __forceinline__ int min125(int v) { return v < 125 ? v : 125; }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -156,8 +158,8 @@ __device__ __forceinline__ int min125(int v) { return v < 125 ? v : 125; }
 // :357-563 -- what an op adds to ref_position / read_index (REF_SKIP and PAD also advance the read: the missing `break`)
 __device__ __forceinline__ void op_advance(uint32_t w, int& ra, int& qa) {
     const int op = (int)(w & 15u), len = (int)(w >> 4);
-    ra = (is_match_op(op) || op == 2 || op == 3 || op == 6) ? len : 0;
-    qa = (is_match_op(op) || op == 1 || op == 4 || op == 3 || op == 6) ? len : 0;
+    ra = ((0x1cdu >> op) & 1u) ? len : 0;                     // M D N P = X
+    qa = ((0x1dbu >> op) & 1u) ? len : 0;                     // M I N S P = X
 }
 
 // four consecutive CIGAR words starting at the 16-byte aligned slot `co_al + k` of a read whose ops occupy slots
@@ -329,6 +331,24 @@ __global__ void tile_entry_kernel(const SumParams p) {
             }
         }
     }
+}
+
+// The site test (:634-646) compares count / max(1, coverage) with a frequency threshold in fp64. For a fixed coverage
+// that is a threshold on the integer count: the smallest count whose quotient -- the same fp64 division -- reaches the
+// threshold. One table entry per coverage spares the tile kernel three divisions per position.
+__global__ void freq_table_kernel(const SumParams p) {
+    const int cov = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cov >= FREQ_TABLE) return;
+    const double cv = (double)cov > 1.0 ? (double)cov : 1.0;
+    const double thr[3] = {p.t.snp_freq, p.t.insert_freq, p.t.delete_freq};
+    unsigned short m[3];
+    for (int k = 0; k < 3; k++) {
+        int lo = 0, hi = 65535;                              // counts are 16-bit fields; 65535 = no count passes
+        if (!((double)hi / cv >= thr[k])) lo = hi;           // also NaN thresholds: nothing passes, as in the reference's >=
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)mid / cv >= thr[k]) hi = mid; else lo = mid + 1; }
+        m[k] = (unsigned short)lo;
+    }
+    p.freq_min[cov] = make_ushort4(m[0], m[1], m[2], 0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -661,8 +681,8 @@ __device__ void scan_pieces(const SumParams& p, const TileCtx& c, const ReadCtx&
             while (ex) {                                        // a few per cent of the bases
                 const int j = __ffs(ex) - 1;
                 ex &= ex - 1;
-                const uint32_t wsel = j < 4 ? ub.x : j < 8 ? ub.y : j < 12 ? ub.z : ub.w;
-                push_exception(c, x, t, (uint32_t)(rp + j) | (((wsel >> ((j & 3) * 8)) & 0xffu) << 16) | (((lowq16 >> j) & 1u) << 31));
+                const uint32_t base = __byte_perm(j & 8 ? ub.z : ub.x, j & 8 ? ub.w : ub.y, (uint32_t)(j & 7)) & 0xffu;
+                push_exception(c, x, t, (uint32_t)(rp + j) | (base << 16) | (((lowq16 >> j) & 1u) << 31));
             }
         }
         __syncwarp();
@@ -877,7 +897,7 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
     c.n_valid = (int)((c.L - c.t_lo) < P ? (c.L - c.t_lo) : P);
     const int64_t gbase = p.pos_off[c.region] + c.t_lo;
 
-    for (int i = tid; i < NC * P; i += K1_THREADS) c.cnt[i] = 0;
+    for (int i = tid; i < NC * P / 4; i += K1_THREADS) ((uint4*)c.cnt)[i] = make_uint4(0u, 0u, 0u, 0u);   // P is a multiple of 4
     if (tid < 32) c.ref_s[P + tid] = 0;
     if (tid < REF_PAD) ref_raw[tid] = 0;
     for (int i = tid; i < P; i += K1_THREADS) {
@@ -922,97 +942,102 @@ __global__ void __launch_bounds__(K1_THREADS, PV_K1_MINB) pileup_tile_kernel(con
         }
         __syncthreads();
     }
+    // B1, every position: coverage and the three counts the site thresholds look at (:625-646) -- nothing else of the row
     int my_site[MAX_PPT];
 #pragma unroll
     for (int u = 0; u < MAX_PPT; u++) {
         my_site[u] = -1;
         const int i = tid + u * K1_THREADS;
         if (i < c.n_valid) {
-            uint32_t w[NC];
+            const uint32_t wt = c.cnt[C_T * P + i], wc2 = c.cnt[C_COV2 * P + i], wid = c.cnt[C_INSDEL * P + i];
+            uint32_t ws[4];
 #pragma unroll
-            for (int k = 0; k < NC; k++) w[k] = c.cnt[k * P + i];
-            const uint8_t rb = c.ref_s[i];
-            int row[PV_FEATURES];
-#pragma unroll
-            for (int f = 0; f < PV_FEATURES; f++) row[f] = 0;
-            row[0] = ref_value(rb);                                             // :174-191
-            const int tf = (int)(w[C_T] & 0xffffu), tr = (int)(w[C_T] >> 16);
-            row[4] = -(tf - (int)(w[C_SKIP] & 0xffffu));                         // REFF = T - SKIP
-            row[15] = -(tr - (int)(w[C_SKIP] >> 16));
-            const int rc = c.rcls[i];
-            // the dense SNP allele counters stand for snp_count, DEV and CLS[A..T] as well (count_mismatch)
-            const uint32_t snp_sum = w[C_SNP] + w[C_SNP + 1] + w[C_SNP + 2] + w[C_SNP + 3];
-            w[C_DEV] += snp_sum;
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[C_CLS + k] += w[C_SNP + k];
-#pragma unroll
-            for (int k = 0; k < 7; k++) {
-                int f = (int)(w[C_CLS + k] & 0xffffu), r = (int)(w[C_CLS + k] >> 16);
-                if (k == rc) { f += tf - (int)(w[C_DEV] & 0xffffu); r += tr - (int)(w[C_DEV] >> 16); }   // BASE[class(ref)] = T - DEV
-                row[8 + k] = rc == 0xff ? 0 : -f;
-                row[19 + k] = rc == 0xff ? 0 : -r;
+            for (int k = 0; k < 4; k++) ws[k] = c.cnt[(C_SNP + k) * P + i];
+            // the dense SNP allele counters stand for snp_count as well (count_mismatch)
+            const uint32_t snp_sum = ws[0] + ws[1] + ws[2] + ws[3];
+            const int cov = (int)(wt & 0xffffu) + (int)(wt >> 16) + (int)(wc2 & 0xffffu);
+            const int dense = (int)(snp_sum & 0xffffu) + (int)(snp_sum >> 16);
+            const int snp = (int)(wc2 >> 16) + dense;
+            const int ins = (int)(wid & 0xffffu), del = (int)(wid >> 16);
+            bool ps, pi, pd;
+            if (cov < FREQ_TABLE) {                          // smallest passing count per coverage, computed with the same fp64 division
+                const ushort4 m = p.freq_min[cov];
+                ps = snp >= (int)m.x; pi = ins >= (int)m.y; pd = del >= (int)m.z;
+            } else {
+                const double cv = (double)cov > 1.0 ? (double)cov : 1.0;         // :635-637
+                ps = (double)snp / cv >= p.t.snp_freq; pi = (double)ins / cv >= p.t.insert_freq; pd = (double)del / cv >= p.t.delete_freq;
             }
+            if (ps || pi || pd) {
+                const int64_t pos = b.region_ref_start[c.region] + c.t_lo + i;
+                if (pos >= b.region_cand_start[c.region] && pos <= b.region_cand_end[c.region] && (double)cov >= p.t.min_coverage) {   // :639-645
+                    int flags = PF_SITE | (ps ? PF_SNP : 0) | (pi ? PF_INS : 0) | (pd ? PF_DEL : 0);
+                    const int n_other = ps ? snp - dense : 0;
+                    if (n_other > 0) flags |= PF_OTHER;
+                    const int n_ev = (pi ? ins : 0) + (pd ? del : 0) + n_other;
+                    const int s = atomicAdd(&p.ctr[CTR_SITES], 1);
+                    if (s < p.site_cap) {
+                        int ev_off = 0;
+                        if (n_ev > 0) {
+                            ev_off = atomicAdd(&p.ctr[CTR_EVENTS], n_ev);
+                            if ((int64_t)ev_off + n_ev > p.ev_cap) atomicOr(&p.ctr[CTR_STATUS], ST_EVENT_OVF);
+                            s_any_events = 1;
+                            if (n_other > 0) s_any_other = 1;
+                        }
+                        SiteRec sr;
+                        sr.gpos = gbase + i; sr.region = c.region; sr.local = (int32_t)(c.t_lo + i); sr.cov = cov;
+                        sr.flags = flags; sr.ev_off = ev_off; sr.n_ev = n_ev; sr.fill = 0; sr.pad = 0;
 #pragma unroll
-            for (int f = 11; f < 25; f++) row[f] = row[f] < -125 ? -125 : row[f];   // :648-653 (all values <= 0 here)
-            // the clamped row goes back into this position's (already consumed) counter words 0..12; it is flushed to HBM
-            // below only where a candidate window can read it
-#pragma unroll
-            for (int f = 0; f < PV_FEATURES; f += 2)
-                c.cnt[(f >> 1) * P + i] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
-
-            const int cov = tf + tr + (int)(w[C_COV2] & 0xffffu);
-            const int snp = (int)(w[C_COV2] >> 16) + (int)(snp_sum & 0xffffu) + (int)(snp_sum >> 16);
-            const int ins = (int)(w[C_INSDEL] & 0xffffu), del = (int)(w[C_INSDEL] >> 16);
-            const double cv = (double)cov > 1.0 ? (double)cov : 1.0;             // :635-637
-            const double sf = (double)snp / cv, inf = (double)ins / cv, df = (double)del / cv;
-            const bool ps = sf >= p.t.snp_freq, pi = inf >= p.t.insert_freq, pd = df >= p.t.delete_freq;
-            const int64_t pos = b.region_ref_start[c.region] + c.t_lo + i;
-            if ((ps || pi || pd) && pos >= b.region_cand_start[c.region] && pos <= b.region_cand_end[c.region] &&
-                (double)cov >= p.t.min_coverage) {                              // :639-645
-                int flags = PF_SITE | (ps ? PF_SNP : 0) | (pi ? PF_INS : 0) | (pd ? PF_DEL : 0);
-                int dense = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) dense += (int)(w[C_SNP + k] & 0xffffu) + (int)(w[C_SNP + k] >> 16);
-                const int n_other = ps ? snp - dense : 0;
-                if (n_other > 0) flags |= PF_OTHER;
-                const int n_ev = (pi ? ins : 0) + (pd ? del : 0) + n_other;
-                const int s = atomicAdd(&p.ctr[CTR_SITES], 1);
-                if (s < p.site_cap) {
-                    int ev_off = 0;
-                    if (n_ev > 0) {
-                        ev_off = atomicAdd(&p.ctr[CTR_EVENTS], n_ev);
-                        if ((int64_t)ev_off + n_ev > p.ev_cap) atomicOr(&p.ctr[CTR_STATUS], ST_EVENT_OVF);
-                        s_any_events = 1;
-                        if (n_other > 0) s_any_other = 1;
+                        for (int k = 0; k < 4; k++) {
+                            sr.snp[2 * k] = (uint16_t)(ws[k] & 0xffffu);
+                            sr.snp[2 * k + 1] = (uint16_t)(ws[k] >> 16);
+                        }
+                        p.sites[s] = sr;
+                        my_site[u] = s;
+                        c.pflag[i] = (uint8_t)flags;
+                        const int j1 = i + (PV_WINDOW / 2) < c.n_valid ? i + (PV_WINDOW / 2) : c.n_valid - 1;
+                        for (int j = i - (PV_WINDOW / 2) > 0 ? i - (PV_WINDOW / 2) : 0; j <= j1; j++) c.near[j] = 1;
+                    } else {
+                        atomicOr(&p.ctr[CTR_STATUS], ST_SITE_OVF);
                     }
-                    SiteRec sr;
-                    sr.gpos = gbase + i; sr.region = c.region; sr.local = (int32_t)(c.t_lo + i); sr.cov = cov;
-                    sr.flags = flags; sr.ev_off = ev_off; sr.n_ev = n_ev; sr.fill = 0; sr.pad = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        sr.snp[2 * k] = (uint16_t)(w[C_SNP + k] & 0xffffu);
-                        sr.snp[2 * k + 1] = (uint16_t)(w[C_SNP + k] >> 16);
-                    }
-                    p.sites[s] = sr;
-                    my_site[u] = s;
-                    c.pflag[i] = (uint8_t)flags;
-                    const int j1 = i + (PV_WINDOW / 2) < c.n_valid ? i + (PV_WINDOW / 2) : c.n_valid - 1;
-                    for (int j = i - (PV_WINDOW / 2) > 0 ? i - (PV_WINDOW / 2) : 0; j <= j1; j++) c.near[j] = 1;
-                } else {
-                    atomicOr(&p.ctr[CTR_STATUS], ST_SITE_OVF);
                 }
             }
         }
     }
     __syncthreads();
-    // Image rows -> HBM. Only the candidate windows read the image (K3: rows p-16 .. p+16 of a site p), so a row is
-    // written when a site of this tile lies within 16 positions, or when it is one of the tile's first / last 16 rows
-    // (a site of the neighbouring tile may reach it): ~10 % of the rows instead of 52 bytes for every position.
+    // B2, image rows -> HBM. Only the candidate windows read the image (K3: rows p-16 .. p+16 of a site p), so a row is
+    // BUILT and written only when a site of this tile lies within 16 positions, or when it is one of the tile's first /
+    // last 16 rows (a site of the neighbouring tile may reach it): ~10 % of the rows.
     for (int i = tid; i < c.n_valid; i += K1_THREADS) {
         if (!(p.img_all || c.near[i] || i < PV_WINDOW / 2 || i >= c.n_valid - PV_WINDOW / 2)) continue;
+        uint32_t w[NC];
+#pragma unroll
+        for (int k = 0; k < NC; k++) w[k] = c.cnt[k * P + i];
+        const uint8_t rb = c.ref_s[i];
+        int row[PV_FEATURES];
+#pragma unroll
+        for (int f = 0; f < PV_FEATURES; f++) row[f] = 0;
+        row[0] = ref_value(rb);                                             // :174-191
+        const int tf = (int)(w[C_T] & 0xffffu), tr = (int)(w[C_T] >> 16);
+        row[4] = -(tf - (int)(w[C_SKIP] & 0xffffu));                         // REFF = T - SKIP
+        row[15] = -(tr - (int)(w[C_SKIP] >> 16));
+        const int rc = c.rcls[i];
+        // the dense SNP allele counters stand for DEV and CLS[A..T] as well (count_mismatch)
+        w[C_DEV] += w[C_SNP] + w[C_SNP + 1] + w[C_SNP + 2] + w[C_SNP + 3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[C_CLS + k] += w[C_SNP + k];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            int f = (int)(w[C_CLS + k] & 0xffffu), r = (int)(w[C_CLS + k] >> 16);
+            if (k == rc) { f += tf - (int)(w[C_DEV] & 0xffffu); r += tr - (int)(w[C_DEV] >> 16); }   // BASE[class(ref)] = T - DEV
+            row[8 + k] = rc == 0xff ? 0 : -f;
+            row[19 + k] = rc == 0xff ? 0 : -r;
+        }
+#pragma unroll
+        for (int f = 11; f < 25; f++) row[f] = row[f] < -125 ? -125 : row[f];   // :648-653 (all values <= 0 here)
         uint32_t* dst = (uint32_t*)(p.img + (gbase + i) * PV_FEATURES);
 #pragma unroll
-        for (int k = 0; k < PV_FEATURES / 2; k++) dst[k] = c.cnt[k * P + i];
+        for (int f = 0; f < PV_FEATURES; f += 2)
+            dst[f >> 1] = ((uint32_t)(uint16_t)(int16_t)row[f]) | ((uint32_t)(uint16_t)(int16_t)row[f + 1] << 16);
     }
     __syncthreads();
     if (!s_any_events) return;
@@ -1228,7 +1253,7 @@ struct WsLayout {
     int32_t* read_span;
     int16_t* img; SiteRec* sites; Event* events; CandRec* cands;
     unsigned long long* key_in; unsigned long long* key_out; uint32_t* val_in; uint32_t* val_out;
-    void* sort_tmp; int32_t* ctr;
+    void* sort_tmp; int32_t* ctr; ushort4* freq_min;
     int64_t bytes;
 };
 
@@ -1237,6 +1262,7 @@ WsLayout carve(void* base, int64_t size, const Plan& pl, int64_t n_reads, int64_
     pv::Arena a(base, size);
     WsLayout w;
     w.ctr = a.take<int32_t>(CTR_COUNT);
+    w.freq_min = a.take<ushort4>(FREQ_TABLE);
     w.pos_off = a.take<int64_t>(n_regions + 1);
     w.tile_region = a.take<int32_t>(pl.n_tiles);
     w.tile_start = a.take<int32_t>(pl.n_tiles);
@@ -1318,7 +1344,7 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     p.b = b; p.pos_off = w.pos_off; p.tile_region = w.tile_region; p.tile_start = w.tile_start; p.P = pl.P;
     p.tile_base = w.tile_base; p.n_tiles = (int32_t)n_tiles; p.read_region = w.read_region; p.tile_count = w.tile_count;
     p.tile_fill = w.tile_fill; p.tile_off = w.tile_off; p.entries = w.entries; p.entry_cap = (int32_t)pl.entry_cap;
-    p.read_span = w.read_span;
+    p.read_span = w.read_span; p.freq_min = w.freq_min;
     p.img = dense_image_dev ? dense_image_dev : w.img;
     p.img_all = dense_image_dev ? 1 : 0;
     p.sites = w.sites; p.site_cap = (int32_t)pl.site_cap; p.events = w.events; p.ev_cap = (int32_t)pl.ev_cap;
@@ -1340,13 +1366,15 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
         if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
         if (blocks < 1) blocks = 1;
         pv::prof_begin(pv::FAM_SUM_PREFIX, stream);
+        freq_table_kernel<<<FREQ_TABLE / 256, 256, 0, stream>>>(p);
+        PV_CUDA_CHECK(cudaGetLastError());
         read_span_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
         tile_scan_kernel<<<1, 1024, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
         tile_entry_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
-        pv::prof_end(pv::FAM_SUM_PREFIX, stream, 3);
+        pv::prof_end(pv::FAM_SUM_PREFIX, stream, 4);
     }
     const size_t smem = k1_smem_bytes(pl.P);
     PV_CUDA_CHECK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
