@@ -149,7 +149,8 @@ int64_t pv_launch_count(void);
 /* byte offset, inside the summary workspace, of the int32 status word of the last pv_summary_regions call
  * (bit0 site scratch overflow, bit1 allele-event scratch overflow, bit2 candidate capacity overflow -- all three cured by a
  * larger out->capacity --, bit3 internal, bit4 the batch came without its quality array (quals == NULL, allowed when min_qual
- * clears both thresholds) but a read whose CIGAR runs over its own end needed one: re-run with the qualities). */
+ * clears both thresholds) but a read whose CIGAR runs over its own end needed one: re-run with the qualities, bit5 internal:
+ * work-list scratch exhausted). */
 int pv_summary_status_offset(void);
 
 /* Device: expand 4-bit packed bases (see PvReadBatch.bases4) into one byte per base; n_bases must be a multiple of 16. */

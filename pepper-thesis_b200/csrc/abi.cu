@@ -576,7 +576,7 @@ extern "C" int pv_summary_regions_host(const PvReadBatch* hb, const PvThresholds
         db.quals = (const uint8_t*)h.arr[8].p;
     }
     *n_candidates = found;
-    if (status & 8) return pv::set_error(PV_ECUDA, "internal inconsistency in the allele event pass (status %d)", status);
+    if (status & 40) return pv::set_error(PV_ECUDA, "internal inconsistency in the summary kernels (status %d)", status);
     if (status & 3) return pv::set_error(PV_EOVERFLOW, "site/event scratch overflow (status %d): raise the candidate capacity", status);
     const int64_t n = found < out->capacity ? found : out->capacity;
     if (n > 0) {

@@ -2,12 +2,12 @@
 // (/root/reference/pepper_variant/modules/cpp/region_summary.cpp:337-916, inference mode).
 //
 // Kernel chain (all on one stream, no host synchronisation):
-//   K0 read_span_kernel / tile_scan_kernel / tile_entry_kernel
-//                            warp per read: reference span of the CIGAR (with the REF_SKIP/PAD -> SOFT_CLIP fall-through of
-//                            region_summary.cpp:556-561), the tiles the read touches counted, scanned, and then filled with
-//                            one ENTRY per (tile, read): the op the walk of that tile starts at, with the tile-local
-//                            position and the read index in front of it. K1 never searches a CIGAR and no per-op prefix
-//                            array ever goes to HBM.
+//   K0 read_entries_kernel / tile_scan_kernel / entry_scatter_kernel
+//                            warp per read, ONE pass over the CIGAR: reference span (with the REF_SKIP/PAD -> SOFT_CLIP
+//                            fall-through of region_summary.cpp:556-561) and one ENTRY per (tile, read) -- the op the walk
+//                            of that tile starts at, with the tile-local position and the read index in front of it --
+//                            pooled, counted per tile, scanned, scattered into per-tile lists. K1 never searches a
+//                            CIGAR and no per-op prefix array ever goes to HBM.
 //   K1 pileup_tile_kernel    CTA per tile of P reference positions of one region, counters in SHARED memory (16 packed
 //                            words per position: forward strand in the low half, reverse in the high half). Phase A:
 //                            a warp per entry stages up to 128 CIGAR ops at a time in its shared-memory table (coalesced
@@ -68,7 +68,7 @@ enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_ba
        C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count of bases that are no dense SNP allele
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
-enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_K0_TICKET2 = 5, CTR_ENTRIES = 6, CTR_COUNT = 8 };
+enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_ENTRIES = 6, CTR_COUNT = 8 };
 enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8,
        ST_NEED_QUALS = 16,     // a quality was needed (insert over the read's end) but the batch came without its quality array
        ST_ENTRY_OVF = 32 };    // more (tile, read) entries than the workspace was sized for (cannot happen with pv_summary_workspace_bytes' bound)
@@ -121,6 +121,7 @@ struct SumParams {
     int32_t* tile_fill;           // [n_tiles][2] fill cursors from the front / from the back (K0 fill pass)
     int32_t* tile_off;            // [n_tiles + 1] exclusive prefix of tile_count
     TileEntry* entries; int32_t entry_cap;
+    void* pool; int32_t* pool_tile;   // [entry_cap] entries in the order K0a found them + the tile each belongs to
     int32_t allq;                 // 1: the batch promises (PvReadBatch.min_qual) that no base quality is below either threshold:
                                   // every quality test passes, qualities are never loaded
     int32_t* read_span;           // [n_reads] total reference advance of the read's CIGAR
@@ -177,59 +178,116 @@ __device__ __forceinline__ void load_ops4(const PvReadBatch& b, int64_t co_al, i
     for (int j = 0; j < 4; j++) if (k + j < skip || k + j >= n_slots) ws[j] = 0u;
 }
 
-// The tiles of its region a read touches: aligned / deleted positions [rel, rel + span - 1] and insert / delete anchors
-// [rel - 1, rel + span - 1], clipped to the region. Returns false when there are none.
-__device__ __forceinline__ bool touched_tiles(const SumParams& p, int64_t r, int reg, int span, int64_t& rel, int& t0, int& t1) {
-    const PvReadBatch& b = p.b;
-    rel = b.read_pos[r] - b.region_ref_start[reg];
-    const int64_t L = b.region_ref_end[reg] - b.region_ref_start[reg] + 1;
-    int64_t lo = rel - 1, hi = rel + (int64_t)span - 1;
-    if (b.read_mapq[r] == 0 || b.read_n_ops[r] <= 0 || hi < 0 || lo > L - 1) return false;      // :619
-    if (lo < 0) lo = 0;
-    if (hi > L - 1) hi = L - 1;
-    t0 = (int)(lo / p.P); t1 = (int)(hi / p.P);
-    return true;
+// K0a, warp per read (K0_CHUNK reads per ticket: op counts are heavy-tailed, a static split leaves the kernel waiting for the
+// unluckiest warp): ONE pass over the read's CIGAR -- each lane takes four consecutive ops per step (one 16-byte load),
+// two shuffle scans give every op its start -- yields the read's reference span and one entry per tile the read touches:
+// the walk of tile t starts at the op in front of the first op that starts at or behind the tile's first position, i.e.
+// the one op k with  a_k < t * P <= a_k + (its reference advance)  (a_k = op start, region-relative); tiles that begin
+// at or in front of the read's own start begin at op 0. Touched = aligned / deleted positions [rel, rel + span - 1] and
+// insert / delete anchors [rel - 1, rel + span - 1], clipped to the region. (A boundary exactly at the read's end gives
+// an entry whose walk finds nothing: harmless, the span is not known yet when it is filed.) Entries are collected in a
+// per-warp buffer and appended to a global pool 32 at a time (one atomic per 32 entries), tiles counted as they go.
+struct PoolEntry { int32_t read, k, a, ri; };
+__device__ __forceinline__ void pool_flush(const SumParams& p, const PoolEntry* buf, const int32_t* buf_tile, int n, int lane) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&p.ctr[CTR_ENTRIES], n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < n) {
+        if (base + lane < p.entry_cap) {
+            ((int4*)p.pool)[base + lane] = *(const int4*)&buf[lane];
+            p.pool_tile[base + lane] = buf_tile[lane];
+            atomicAdd(&p.tile_count[buf_tile[lane]], 1);
+        } else {
+            atomicOr(&p.ctr[CTR_STATUS], ST_ENTRY_OVF);
+        }
+    }
+    __syncwarp();
 }
 
-// Pass 1, warp per read (ticket counter: op counts are heavy-tailed): region of the read, reference span of its CIGAR,
-// one count for every tile it touches. Each lane takes FOUR consecutive ops per step (one 16-byte load).
-__global__ void read_span_kernel(const SumParams p) {
+__global__ void read_entries_kernel(const SumParams p) {
+    __shared__ __align__(16) PoolEntry s_buf[8][32];
+    __shared__ int32_t s_tile[8][32];
     const PvReadBatch& b = p.b;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PoolEntry* buf = s_buf[warp];
+    int32_t* buf_tile = s_tile[warp];
+    int n_buf = 0;                                            // warp-uniform
+    const int64_t P = p.P;
+    int reg = 0;
     for (int64_t r = 0, r_end = 0;; r++) {
-        if (r >= r_end) {                                     // K0_CHUNK reads per ticket: one global atomic serves several reads
+        if (r >= r_end) {
             int tk = 0;
             if (lane == 0) tk = atomicAdd(&p.ctr[CTR_K0_TICKET], K0_CHUNK);
             r = __shfl_sync(0xffffffffu, tk, 0);
             if (r >= b.n_reads) break;
             r_end = r + K0_CHUNK < b.n_reads ? r + K0_CHUNK : b.n_reads;
+            int lo = 0, hi = b.n_regions - 1;                 // region: first one whose read range ends behind r
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (b.region_read_begin[mid + 1] <= r) lo = mid + 1; else hi = mid; }
+            reg = lo;
         }
-        int lo = 0, hi = b.n_regions - 1;                     // region: first one whose read range ends behind r
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (b.region_read_begin[mid + 1] <= r) lo = mid + 1; else hi = mid; }
-        const int reg = lo;
-        const int64_t co = b.read_cigar_off[r];
+        while (b.region_read_begin[reg + 1] <= r) reg++;
         const int n_ops = b.read_n_ops[r];
+        const int64_t rel = b.read_pos[r] - b.region_ref_start[reg];
+        const int64_t L = b.region_ref_end[reg] - b.region_ref_start[reg] + 1;
+        const bool live = b.read_mapq[r] != 0 && n_ops > 0 && rel - 1 <= L - 1;      // :619
+        const int t_last = (int)((L - 1) / P);                // last tile of the region
+        const int tb = p.tile_base[reg];
+        int tcur = 0;                                         // next tile boundary behind the read's start
+        if (live && rel >= 0) {
+            const int t0 = (int)((rel > 0 ? rel - 1 : 0) / P);
+            int tf = (int)(rel / P);
+            tcur = tf + 1;
+            if (tf > t_last) tf = t_last;
+            const int n_first = tf - t0 + 1;                  // 1 or 2 tiles begin at or in front of the read's start
+            if (lane < n_first) {
+                PoolEntry e; e.read = (int32_t)r; e.k = 0; e.a = (int32_t)(rel - (int64_t)(t0 + lane) * P); e.ri = 0;
+                buf[n_buf + lane] = e; buf_tile[n_buf + lane] = tb + t0 + lane;
+            }
+            n_buf += n_first;
+        }
+        const int64_t co = b.read_cigar_off[r];
         const int64_t co_al = co & ~(int64_t)3;
         const int skip = (int)(co - co_al), n_slots = skip + n_ops;
-        int64_t part = 0;
-        for (int k = lane * 4; k < n_slots; k += 128) {
+        int64_t ref_run = 0, ri_run = 0, bpos = (int64_t)tcur * P;
+        for (int k0 = 0; k0 < n_slots; k0 += 128) {
+            const int k = k0 + lane * 4;
             uint32_t ws[4];
             load_ops4(b, co_al, k, skip, n_slots, ws);
+            int ra[4], qa[4], sr = 0, sq = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) { int ra, qa; op_advance(ws[j], ra, qa); part += ra; }
+            for (int j = 0; j < 4; j++) { op_advance(ws[j], ra[j], qa[j]); sr += ra[j]; sq += qa[j]; }
+            int ir = sr, iq = sq;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int tr = __shfl_up_sync(0xffffffffu, ir, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
+                if (lane >= d) { ir += tr; iq += tq; }
+            }
+            const int64_t a_first = rel + ref_run + (int64_t)(ir - sr), q_first = ri_run + (int64_t)(iq - sq);
+            ref_run += __shfl_sync(0xffffffffu, ir, 31);
+            ri_run += __shfl_sync(0xffffffffu, iq, 31);
+            while (live && tcur <= t_last && bpos <= rel + ref_run) {   // boundaries inside the ops of this step
+                if (n_buf > 29) { __syncwarp(); pool_flush(p, buf, buf_tile, n_buf, lane); n_buf = 0; }
+                int64_t a_k = a_first, q_k = q_first;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (ra[j] > 0 && a_k < bpos && bpos <= a_k + ra[j]) {
+                        PoolEntry e; e.read = (int32_t)r; e.k = k + j - skip; e.a = (int32_t)(a_k - bpos);
+                        e.ri = q_k > (1ll << 30) ? (1 << 30) : (int32_t)q_k;
+                        buf[n_buf] = e; buf_tile[n_buf] = tb + tcur;
+                    }
+                    a_k += ra[j]; q_k += qa[j];
+                }
+                n_buf++; tcur++; bpos += P;
+            }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-        const int span = part > (1ll << 30) ? (1 << 30) : (int)part;
-        if (lane == 0) { p.read_span[r] = span; p.read_region[r] = reg; }
-        int64_t rel; int t0, t1;
-        if (!touched_tiles(p, r, reg, span, rel, t0, t1)) continue;
-        const int tb = p.tile_base[reg];
-        for (int t = t0 + lane; t <= t1; t += 32) atomicAdd(&p.tile_count[tb + t], 1);
+        if (lane == 0) { p.read_span[r] = ref_run > (1ll << 30) ? (1 << 30) : (int32_t)ref_run; p.read_region[r] = reg; }
+        if (n_buf > 29) { __syncwarp(); pool_flush(p, buf, buf_tile, n_buf, lane); n_buf = 0; }
     }
+    __syncwarp();
+    if (n_buf > 0) pool_flush(p, buf, buf_tile, n_buf, lane);
 }
 
-// exclusive prefix of the tile counts (one block); the total is checked against the entry capacity
+// exclusive prefix of the tile counts (one block)
 __global__ void tile_scan_kernel(const SumParams p) {
     __shared__ int64_t s_part[1024];
     const int tid = threadIdx.x, n = p.n_tiles;
@@ -246,90 +304,29 @@ __global__ void tile_scan_kernel(const SumParams p) {
         __syncthreads();
     }
     int64_t run = s_part[tid] - sum;
-    const bool ovf = s_part[1023] > (int64_t)p.entry_cap;
-    for (int i = lo; i < hi; i++) { p.tile_off[i] = ovf ? 0 : (int32_t)run; run += p.tile_count[i]; }
-    if (tid == 0) {
-        p.tile_off[n] = ovf ? 0 : (int32_t)s_part[1023];
-        p.ctr[CTR_ENTRIES] = ovf ? 0 : (int32_t)s_part[1023];
-        if (ovf) atomicOr(&p.ctr[CTR_STATUS], ST_ENTRY_OVF);
-    }
+    for (int i = lo; i < hi; i++) { p.tile_off[i] = (int32_t)run; run += p.tile_count[i]; }
+    if (tid == 0) p.tile_off[n] = (int32_t)s_part[1023];
 }
 
-// Entries of reads that cross the whole tile are filed from the front of the tile's list, reads that start or end inside
-// it (less work) from the back: the warps of a CTA pull the long units first and finish closer together.
-__device__ __forceinline__ void emit_entry(const SumParams& p, int tile, int64_t r, int k, int64_t a, int64_t ri, bool whole) {
-    const int slot = whole ? p.tile_off[tile] + atomicAdd(&p.tile_fill[2 * tile], 1)
-                           : p.tile_off[tile + 1] - 1 - atomicAdd(&p.tile_fill[2 * tile + 1], 1);
-    if (slot >= p.tile_off[tile] && slot < p.tile_off[tile + 1]) {
-        TileEntry e; e.read = (int32_t)r; e.k = k; e.a = (int32_t)a; e.ri = ri > (1ll << 30) ? (1 << 30) : (int32_t)ri;
-        p.entries[slot] = e;
-    } else {
-        atomicOr(&p.ctr[CTR_STATUS], ST_INTERNAL);
-    }
-}
-
-// Pass 2, warp per read: one entry per touched tile. The walk of tile t starts at the op in front of the first op that
-// starts at or behind the tile's first position t_lo, i.e. the one op k with  a_k < t_lo <= a_k + (its reference advance)
-// (a_k = op start, region-relative); tiles that begin at or in front of the read's own start begin at op 0.
-__global__ void tile_entry_kernel(const SumParams p) {
-    const PvReadBatch& b = p.b;
-    const int lane = threadIdx.x & 31;
+// K0b, thread per pool entry: the entry goes into its tile's list. Entries of reads that cross the whole tile are filed
+// from the front, reads that start or end inside it (less work) from the back: the warps of a CTA pull the long units
+// first and finish closer together.
+__global__ void entry_scatter_kernel(const SumParams p) {
     if (p.ctr[CTR_STATUS] & ST_ENTRY_OVF) return;
-    for (int64_t r = 0, r_end = 0;; r++) {
-        if (r >= r_end) {
-            int tk = 0;
-            if (lane == 0) tk = atomicAdd(&p.ctr[CTR_K0_TICKET2], K0_CHUNK);
-            r = __shfl_sync(0xffffffffu, tk, 0);
-            if (r >= b.n_reads) break;
-            r_end = r + K0_CHUNK < b.n_reads ? r + K0_CHUNK : b.n_reads;
-        }
-        const int reg = p.read_region[r];
-        int64_t rel; int t0, t1;
-        const int64_t span_r = p.read_span[r];
-        if (!touched_tiles(p, r, reg, (int)span_r, rel, t0, t1)) continue;
-        const int tb = p.tile_base[reg];
-        const int64_t P = p.P;
-        if (rel >= 0) {
-            const int64_t tf64 = rel / P;
-            const int tf = tf64 < (int64_t)t1 ? (int)tf64 : t1;
-            for (int t = t0 + lane; t <= tf; t += 32) emit_entry(p, tb + t, r, 0, rel - (int64_t)t * P, 0, false);
-        }
-        const int64_t co = b.read_cigar_off[r];
-        const int n_ops = b.read_n_ops[r];
-        const int64_t co_al = co & ~(int64_t)3;
-        const int skip = (int)(co - co_al), n_slots = skip + n_ops;
-        int64_t ref_run = 0, ri_run = 0;
-        // the next tile boundary behind the read's start (one division per read; from there on boundaries are counted)
-        int tcur = rel >= 0 ? (int)(rel / P) + 1 : 0;
-        if (tcur < t0) tcur = t0;
-        int64_t bpos = (int64_t)tcur * P;
-        for (int k0 = 0; k0 < n_slots && tcur <= t1; k0 += 128) {
-            const int k = k0 + lane * 4;
-            uint32_t ws[4];
-            load_ops4(b, co_al, k, skip, n_slots, ws);
-            int ra[4], qa[4], sr = 0, sq = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) { op_advance(ws[j], ra[j], qa[j]); sr += ra[j]; sq += qa[j]; }
-            int ir = sr, iq = sq;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int tr = __shfl_up_sync(0xffffffffu, ir, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
-                if (lane >= d) { ir += tr; iq += tq; }
-            }
-            const int64_t a_first = rel + ref_run + (int64_t)(ir - sr), q_first = ri_run + (int64_t)(iq - sq);
-            ref_run += __shfl_sync(0xffffffffu, ir, 31);
-            ri_run += __shfl_sync(0xffffffffu, iq, 31);
-            while (tcur <= t1 && bpos <= rel + ref_run) {    // boundaries inside the ops of this step: a_k < bpos <= a_k + advance
-                int64_t a_k = a_first, q_k = q_first;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (ra[j] > 0 && a_k < bpos && bpos <= a_k + ra[j])
-                        emit_entry(p, tb + tcur, r, k + j - skip, a_k - bpos, q_k, rel + span_r >= bpos + P);
-                    a_k += ra[j]; q_k += qa[j];
-                }
-                tcur++; bpos += P;
-            }
-        }
+    const PvReadBatch& b = p.b;
+    int n = p.ctr[CTR_ENTRIES];
+    if (n > p.entry_cap) n = p.entry_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 e = ((const int4*)p.pool)[i];
+        const int tile = p.pool_tile[i];
+        const int reg = p.read_region[e.x];
+        const int64_t rel = b.read_pos[e.x] - b.region_ref_start[reg];
+        const int64_t t_lo = (int64_t)(tile - p.tile_base[reg]) * p.P;
+        const bool whole = rel <= t_lo && rel + (int64_t)p.read_span[e.x] >= t_lo + p.P;
+        const int slot = whole ? p.tile_off[tile] + atomicAdd(&p.tile_fill[2 * tile], 1)
+                               : p.tile_off[tile + 1] - 1 - atomicAdd(&p.tile_fill[2 * tile + 1], 1);
+        if (slot >= p.tile_off[tile] && slot < p.tile_off[tile + 1]) ((int4*)p.entries)[slot] = e;
+        else atomicOr(&p.ctr[CTR_STATUS], ST_INTERNAL);
     }
 }
 
@@ -1231,7 +1228,7 @@ Plan make_plan(int64_t n_reads, int64_t n_ops, int32_t n_regions, int64_t total_
     // (tile, read) entries: a read touches at most every tile of its own region
     if (max_region_len <= 0 || max_region_len > total_positions) max_region_len = total_positions;
     const int64_t tiles_per_region = max_region_len / pl.P + 1;
-    pl.entry_cap = n_reads > 0 ? ((double)n_reads * (double)tiles_per_region > 2.0e9 ? 0x7fffff00ll : n_reads * tiles_per_region) : 1;
+    pl.entry_cap = n_reads > 0 ? ((double)n_reads * (double)(tiles_per_region + 1) > 2.0e9 ? 0x7fffff00ll : n_reads * (tiles_per_region + 1)) : 1;
     if (pl.entry_cap > 0x7fffff00ll) pl.entry_cap = 0x7fffff00ll;
     pl.cand_cap = capacity < 1 ? 1 : capacity;
     pl.site_cap = 4 * pl.cand_cap + 4096;
@@ -1250,6 +1247,7 @@ Plan make_plan(int64_t n_reads, int64_t n_ops, int32_t n_regions, int64_t total_
 struct WsLayout {
     int64_t* pos_off; int32_t* tile_region; int32_t* tile_start;
     int32_t* tile_base; int32_t* tile_count; int32_t* tile_fill; int32_t* tile_off; int32_t* read_region; TileEntry* entries;
+    TileEntry* pool; int32_t* pool_tile;
     int32_t* read_span;
     int16_t* img; SiteRec* sites; Event* events; CandRec* cands;
     unsigned long long* key_in; unsigned long long* key_out; uint32_t* val_in; uint32_t* val_out;
@@ -1272,6 +1270,8 @@ WsLayout carve(void* base, int64_t size, const Plan& pl, int64_t n_reads, int64_
     w.tile_off = a.take<int32_t>(pl.n_tiles + 1);
     w.read_region = a.take<int32_t>(n_reads);
     w.entries = a.take<TileEntry>(pl.entry_cap);
+    w.pool = a.take<TileEntry>(pl.entry_cap);
+    w.pool_tile = a.take<int32_t>(pl.entry_cap);
     w.read_span = a.take<int32_t>(n_reads);
     w.img = need_img ? a.take<int16_t>(total_positions * PV_FEATURES) : nullptr;
     w.sites = a.take<SiteRec>(pl.site_cap);
@@ -1344,6 +1344,7 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     p.b = b; p.pos_off = w.pos_off; p.tile_region = w.tile_region; p.tile_start = w.tile_start; p.P = pl.P;
     p.tile_base = w.tile_base; p.n_tiles = (int32_t)n_tiles; p.read_region = w.read_region; p.tile_count = w.tile_count;
     p.tile_fill = w.tile_fill; p.tile_off = w.tile_off; p.entries = w.entries; p.entry_cap = (int32_t)pl.entry_cap;
+    p.pool = w.pool; p.pool_tile = w.pool_tile;
     p.read_span = w.read_span; p.freq_min = w.freq_min;
     p.img = dense_image_dev ? dense_image_dev : w.img;
     p.img_all = dense_image_dev ? 1 : 0;
@@ -1368,11 +1369,11 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
         pv::prof_begin(pv::FAM_SUM_PREFIX, stream);
         freq_table_kernel<<<FREQ_TABLE / 256, 256, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
-        read_span_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+        read_entries_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
         tile_scan_kernel<<<1, 1024, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
-        tile_entry_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+        entry_scatter_kernel<<<(unsigned)(sms * 4), 256, 0, stream>>>(p);
         PV_CUDA_CHECK(cudaGetLastError());
         pv::prof_end(pv::FAM_SUM_PREFIX, stream, 4);
     }

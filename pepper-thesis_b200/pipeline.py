@@ -154,8 +154,8 @@ class HotPath:
         k, st = int(h["hc"][0]), int(h["hc"][1])
         ws = h["ws"]
         for _ in range(12):
-            if st & 8:
-                raise RuntimeError("internal inconsistency in the allele event pass")
+            if st & 40:
+                raise RuntimeError("internal inconsistency in the summary kernels (status %d)" % st)
             if k <= ws.capacity and not (st & 23):
                 return ws, k
             if st & 16:
