@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE ONLY: CPU restatement of the per-candidate block of small_chunk_stitch and of find_candidates'
 de-duplication (/root/reference/pepper_variant/modules/python/CandidateFinder.py:279-297, 391-529, 536-600). The
-reference module itself cannot be imported here (h5py, the compiled PEPPER_VARIANT), so this follows its source text
-line by line over plain Python values: PARITY UNPINNED against an executed reference for this row."""
+reference module itself needs h5py and the compiled PEPPER_VARIANT, so this follows its source text line by line over
+plain Python values. PARITY PINNED: oracle/ref_stage3.py runs the UNMODIFIED reference module (stand-ins for those two
+imports only) and tests/golden/stage3_filter_seed*.json hold its output; tests/test_candidate_filter.py checks this port
+against them everywhere and against the live reference where /root/reference exists."""
 from collections import defaultdict
 
 import numpy as np

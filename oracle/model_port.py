@@ -70,7 +70,7 @@ def _bilstm(x, sd, name):
     return torch.cat([f, r], dim=2)
 
 
-def variant_forward(sd, x, return_logits=False):
+def variant_forward(sd, x, return_logits=False, return_features=False):
     """simple_model.py:48-82 in eval mode (dropout = identity). x float32 [B,33,26] -> softmax [B,3]."""
     with torch.no_grad():
         x = x.float()
@@ -79,6 +79,8 @@ def variant_forward(sd, x, return_logits=False):
         x = torch.flatten(x, 1, 2)
         for i in range(1, 6):
             x = torch.selu(x @ sd["linear_%d.weight" % i].T + sd["linear_%d.bias" % i])
+        if return_features:                                   # input of output_layer_type (tests fit a separated head on it)
+            return x
         logits = x @ sd["output_layer_type.weight"].T + sd["output_layer_type.bias"]
         return logits if return_logits else torch.softmax(logits, dim=1)
 
@@ -107,12 +109,14 @@ def _bigru(x, h0, sd, name):
     return torch.cat([f, r], dim=2), torch.stack([hf, hr], dim=0)
 
 
-def polisher_forward(sd, x, hidden):
+def polisher_forward(sd, x, hidden, return_features=False):
     """pepper simple_model.py:27-42. x [B,T,10] float, hidden [B,2,128] -> logits [B,T,5], hidden_final [B,2,128]."""
     with torch.no_grad():
         h0 = hidden.float().transpose(0, 1).contiguous()
         x_out, h_enc = _bigru(x.float(), h0, sd, "gru_encoder")
         x_out, h_dec = _bigru(x_out, h_enc, sd, "gru_decoder")            # decoder h0 = encoder h_n
+        if return_features:                                   # input of dense1
+            return x_out
         logits = x_out @ sd["dense1.weight"].T + sd["dense1.bias"]
         return logits, h_dec.transpose(0, 1).contiguous()
 

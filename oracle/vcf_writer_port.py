@@ -3,9 +3,10 @@
 Follows /root/reference/pepper_variant/modules/python/VcfWriter.py:
   candidate_list_to_variant  :48-139   (multi-allelic merge of the selected candidates of one position)
   write_vcf_records          :141-221  (QUAL, the q cut-offs, which of the five files a record goes to)
-pysam is not installed here, so the reference module cannot be imported and run: **parity unpinned** against the
-reference's own output files; this port is a line-by-line restatement kept deliberately close to the source so the
-product (`pepper_thesis_b200/vcf_writer.py`, written differently) can be checked against it on random inputs.
+pysam is not installed here; oracle/ref_stage3.py runs the UNMODIFIED reference module with a recording stand-in for
+pysam's VariantFile and tests/golden/stage3_vcf_seed*.json hold the records it produced (which file, which fields):
+PARITY PINNED at the record level (tests/test_vcf_writer.py checks this port and the product writer against them). What
+stays open is only the text pysam/htslib render for a float field.
 Only tests may import this file.
 """
 import math

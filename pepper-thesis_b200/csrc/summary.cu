@@ -704,6 +704,13 @@ __device__ void accumulate_entry(const SumParams& p, const TileCtx& c, const Til
     uint32_t w_prev = kb > 0 ? __ldg(b.cigar + x.co + kb - 1) : 0u;   // the op in front of the round's first one
     uint32_t wv[4];
     fetch_round(b, x, kb, lane, wv);
+    {   // the bases this walk will compare (about one per tile position from read index e.ri on) start their way from DRAM now
+        const int64_t off = (int64_t)e.ri + 128 * lane;
+        if (off < x.read_len && 128 * lane < x.nv + 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(x.bases + off));
+            if (!p.allq) asm volatile("prefetch.global.L2 [%0];" ::"l"(x.quals + off));
+        }
+    }
     if (lane == 0) {                                          // the read's reference span inside the tile
         int64_t s = x.rel_t, en = x.rel_t + (int64_t)p.read_span[e.read];
         if (s < 0) s = 0;

@@ -1,72 +1,87 @@
-"""Stage 3 (candidate filter): the device kernel + host tuple builder against the restatement of
-CandidateFinder.py:391-600 in oracle/candidate_finder_port.py."""
+"""Stage 3 (candidate filter): the device kernel + host tuple builder against
+  * golden vectors written by the UNMODIFIED reference module (CandidateFinder.find_candidates / small_chunk_stitch run
+    through oracle/ref_stage3.py's h5py / PEPPER_VARIANT stand-ins; tests/golden/make_stage3_golden.py) -- parity pinned,
+  * the restatement of CandidateFinder.py:391-600 in oracle/candidate_finder_port.py (itself checked against the same
+    golden vectors and, where /root/reference exists, against the live reference)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 import candidate_finder_port as CP
+import stage3_worlds as W
 from pepper_thesis_b200 import candidate_filter as CF
-from pepper_thesis_b200.pipeline import Predictions
-from pepper_thesis_b200.read_batch import ReadBatch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _world(seed, lower=False, **kw):
+    batch, pred, cands, contig, contig_len = W.world(seed, lower=lower, **kw)
+    return batch, pred, cands, W.fetcher(contig), contig_len
+
+
+def _golden(seed):
+    with open(os.path.join(GOLDEN, "stage3_filter_seed%d.json" % seed)) as f:
+        return json.load(f)
+
+
+def _as_golden(result):
+    contigs, phasing, variant = result
+    return {"contigs": list(contigs), "phasing": [[list(k), W.plain(v)] for k, v in sorted(phasing.items())],
+            "variant": [[list(k), W.plain(v)] for k, v in sorted(variant.items())]}
+
+
+def _assert_equals_golden(result, g, what):
+    got = _as_golden(result)
+    assert got["contigs"] == g["contigs"], what
+    for part in ("phasing", "variant"):
+        assert [k for k, _ in got[part]] == [k for k, _ in g[part]], (what, part)
+        for (k, a), (_, b) in zip(got[part], g[part]):
+            assert a == b, (what, part, k, a, b)
+
+
+@pytest.mark.parametrize("seed,opt", W.FILTER_CASES)
+def test_port_matches_reference_golden(seed, opt):
+    """The restatement against the golden vectors of the unmodified reference (CPU, everywhere)."""
+    _, _, cands, fetch, _ = _world(seed, lower=(seed == 1))
+    margin, deepv = CP.stitch(cands, fetch, CF.FilterOptions(*opt))
+    _assert_equals_golden(CP.find_candidates(margin, deepv), _golden(seed), "port seed %d" % seed)
+
+
+def test_live_reference_reproduces_golden():
+    """Where the reference tree exists: the unmodified CandidateFinder.py, run now, gives the committed vectors."""
+    import ref_stage3 as R
+    if not R.available():
+        pytest.skip("no /root/reference here")
+    for seed, opt in W.FILTER_CASES:
+        _, _, cands, contig, _ = W.world(seed, lower=(seed == 1))
+        _assert_equals_golden(R.ref_find_candidates(cands, [("ctg", contig)], opt), _golden(seed), "live seed %d" % seed)
+    # the per-batch function on its own, against the restatement's lists
+    _, _, cands, contig, _ = W.world(2)
+    m_ref, d_ref = R.ref_stitch(cands, [("ctg", contig)], W.FILTER_CASES[2][1])
+    m, d = CP.stitch(cands, W.fetcher(contig), CF.FilterOptions(*W.FILTER_CASES[2][1]))
+    assert W.plain(m_ref) == W.plain(m) and W.plain(d_ref) == W.plain(d) and len(d) > 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,opt", W.FILTER_CASES)
+def test_filter_matches_reference_golden(seed, opt):
+    """candidate_filter.cu + find_candidates against the unmodified reference's output on the same candidates."""
+    batch, pred, _, _, contig_len = _world(seed, lower=(seed == 1))
+    got = CF.find_candidates(pred, batch, CF.FilterOptions(*opt), contig_len=[contig_len] * batch.n_regions)
+    g = _golden(seed)
+    _assert_equals_golden(got, g, "device seed %d" % seed)
+    if seed in (0, 1, 2):
+        assert len(g["variant"]) > 20
+
+
 
 
 def test_port_repeat_annotation():
     assert CP.repeat_annotation("AAAAACGT", 1) == [5, 5, 5, 5, 5, 1, 1, 1]
     assert CP.repeat_annotation("ACAAAT", 1) == [1, 1, 3, 3, 3, 1]
     assert CP.repeat_annotation("", 1) == []
-
-
-def _world(seed, n_regions=3, L=700, K=600, lower=False):
-    """Random reference (homopolymer-rich, some N / lower-case), regions with margins, random candidates and probs."""
-    rng = np.random.RandomState(seed)
-    contig_len = n_regions * L
-    seq = []
-    while len(seq) < contig_len:
-        b = "ACGT"[rng.randint(4)] if rng.rand() > 0.01 else "N"
-        seq.extend(b * int(rng.choice([1, 1, 1, 2, 3, 5, 6, 9])))
-    contig = "".join(seq[:contig_len])
-    if lower:
-        contig = "".join(c.lower() if rng.rand() < 0.3 else c for c in contig)
-    starts = [r * L for r in range(n_regions)]
-    ends = [min(contig_len - 1, (r + 1) * L) for r in range(n_regions)]
-    rs = [max(0, s - 100) for s in starts]
-    re_ = [e + 100 for e in ends]
-    refs, off = [], [0]
-    for a, b in zip(rs, re_):
-        piece = contig[a:b + 1]
-        piece += "N" * (b + 1 - a - len(piece))                  # what the ingest pads past the contig end
-        refs.append(piece); off.append(off[-1] + len(piece))
-    z = np.zeros(0, np.int64)
-    batch = ReadBatch(read_pos=z, read_base_off=z, read_len=np.zeros(0, np.int32), read_cigar_off=z, read_n_ops=np.zeros(0, np.int32),
-                      read_flags=np.zeros(0, np.uint8), read_mapq=np.zeros(0, np.uint8), bases=np.zeros(0, np.uint8),
-                      quals=np.zeros(0, np.uint8), cigar=np.zeros(0, np.uint32),
-                      region_ref_start=np.array(rs, np.int64), region_ref_end=np.array(re_, np.int64),
-                      region_cand_start=np.array(starts, np.int64), region_cand_end=np.array(ends, np.int64),
-                      region_ref_off=np.array(off[:-1], np.int64), region_ref_len=np.array([len(x) for x in refs], np.int64),
-                      region_read_begin=np.zeros(n_regions + 1, np.int64), ref=np.frombuffer("".join(refs).encode(), np.uint8).copy(),
-                      contigs=["ctg"] * n_regions)
-    region = np.sort(rng.randint(0, n_regions, K)).astype(np.int32)
-    position = np.array([rng.randint(starts[r], ends[r] + 1) for r in region], np.int64)
-    position[:4] = [0, 3, 9, 12][:min(4, K)]; region[:4] = 0                 # contig start: short downstream context
-    position[-3:] = [contig_len - 1, contig_len - 4, contig_len - 11]; region[-3:] = n_regions - 1
-    order = np.lexsort((position, region)); region, position = region[order], position[order]
-    depth = rng.randint(3, 126, K).astype(np.int32)
-    freq = np.minimum(depth, rng.randint(1, 126, K)).astype(np.int32)
-    allele = np.zeros((K, 64), np.uint8); alen = np.zeros(K, np.uint8)
-    strs = []
-    for i in range(K):
-        t = rng.choice([1, 1, 2, 3])
-        n = 1 if t == 1 else rng.randint(2, 12)
-        bases = "".join(rng.choice(list("ACGT") if rng.rand() > 0.05 else list("ACGTN")) for _ in range(n))
-        s = str(t) + bases
-        strs.append(s); allele[i, :len(s)] = np.frombuffer(s.encode(), np.uint8); alen[i] = len(s)
-    raw = rng.rand(K, 3).astype(np.float32) ** 3
-    raw[rng.rand(K) < 0.1] = [0.25, 0.25, 0.25]                              # ties: np.argmax takes the first
-    probs = (raw / raw.sum(1, keepdims=True)).astype(np.float32)
-    probs[rng.rand(K) < 0.05, 1] = np.float32(0.1)                          # exactly at a threshold (float32 0.1 > double 0.1)
-    pred = Predictions(region, position, depth, freq, allele, alen, probs, probs.argmax(1).astype(np.uint8))
-    fetch = lambda c, a, b: contig[max(0, a):max(0, b)].upper()             # FASTA_handler semantics (clips, upper-cases)
-    cands = [("ctg", int(position[i]), int(depth[i]), [strs[i]], [int(freq[i])], probs[i]) for i in range(K)]
-    return batch, pred, cands, fetch, contig_len
 
 
 def _same_tuple(a, b):

@@ -1,46 +1,87 @@
-"""Stage-3 VCF writer (pepper_thesis_b200/vcf_writer.py) against the restatement of the reference's site logic
-(oracle/vcf_writer_port.py, VcfWriter.py:48-221) on random candidate sets, and the files it writes (BGZF, header, five
-outputs). CPU only; pysam is absent, so byte-level parity with the reference's files is unpinned (stated in both files)."""
+"""Stage-3 VCF writer (pepper_thesis_b200/vcf_writer.py) against
+  * golden vectors from the UNMODIFIED reference VcfWriter.py (run through oracle/ref_stage3.py with a recording stand-in
+    for pysam; tests/golden/make_stage3_golden.py): which record goes to which of the five files with which fields,
+  * the restatement of the site logic (oracle/vcf_writer_port.py, VcfWriter.py:48-221), itself checked against the same
+    vectors, on more random candidate sets,
+and the files it writes (BGZF framing, header, tabix index). CPU only. What stays unpinned: the text pysam/htslib would
+render for a float field (pysam is absent); fields are compared numerically."""
 import gzip
+import json
+import os
 import struct
 
 import numpy as np
 import pytest
 
+import stage3_worlds as W
 import vcf_writer_port as port
 from pepper_thesis_b200 import vcf_writer as vw
 
 
-def _random_sites(seed, n_sites=300):
-    rng = np.random.default_rng(seed)
-    alpha = "ACGT"
-    sites = {}
-    pos = 1000
-    for _ in range(n_sites):
-        pos += int(rng.integers(0, 40))                         # 0: two keys can share a start only across contigs
-        contig = "chr%d" % (1 + int(rng.random() < 0.2))
-        cands = []
-        for _ in range(int(rng.integers(1, 7))):
-            kind = rng.random()
-            ref_base = alpha[int(rng.integers(0, 4))]
-            if kind < 0.5:
-                ref, alts = ref_base, [alpha[int(rng.integers(0, 4))]]
-            elif kind < 0.75:
-                ref, alts = ref_base, [ref_base + "".join(alpha[int(x)] for x in rng.integers(0, 4, int(rng.integers(1, 6))))]
-            else:
-                ref, alts = ref_base + "".join(alpha[int(x)] for x in rng.integers(0, 4, int(rng.integers(1, 6)))), [ref_base]
-            probs = rng.dirichlet([0.6, 0.6, 0.6]).astype(np.float32)
-            if rng.random() < 0.1:
-                probs = np.array([0.25, 0.375, 0.375], np.float32)      # tie: first maximum wins
-            if rng.random() < 0.05:
-                probs = np.array([0.0, 0.0, 1.0], np.float32)           # 1 - p == 0: QUAL saturates at 90
-            g = int(np.argmax(probs))
-            gt = [[0, 0], [0, 1], [1, 1]][g]
-            depth = int(rng.integers(1, 120))
-            cands.append((contig, pos, pos + len(ref), ref, alts, gt, depth, [int(rng.integers(0, depth + 1))], probs[g], probs,
-                          [max(probs[1], probs[2])], bool(rng.random() < 0.3)))
-        sites[(contig, pos)] = cands
-    return sites
+_random_sites = W.random_sites
+
+
+def _golden(seed):
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stage3_vcf_seed%d.json" % seed)) as f:
+        return json.load(f)
+
+
+def _norm(r):
+    """A record dict (port or golden) -> comparable plain values; the file list as a sorted list."""
+    d = W.plain({k: v for k, v in r.items() if k != "id"})
+    d["files"] = sorted(d["files"]); d["alleles"] = list(d["alleles"])
+    return d
+
+
+@pytest.mark.parametrize("seed,opt", W.VCF_CASES)
+def test_port_records_match_reference_golden(seed, opt):
+    """The restatement against the records the UNMODIFIED VcfWriter.py handed to (a recording stand-in of) pysam."""
+    g = _golden(seed)
+    want = [_norm(r) for r in g["records"]]
+    got = [_norm(r) for r in port.records(W.random_sites(seed, 800), vw.VcfOptions(*opt))]
+    assert len(got) == len(want) == g["counts"][0]
+    for a, b in zip(got, want):
+        assert a == b, (a, b)
+
+
+def test_live_reference_reproduces_vcf_golden():
+    import ref_stage3 as R
+    if not R.available():
+        pytest.skip("no /root/reference here")
+    for seed, opt in W.VCF_CASES:
+        g = _golden(seed)
+        counts, recs, header = R.ref_vcf(W.random_sites(seed, 800), opt, [("chr1", "A" * 50), ("chr2", "C" * 40), ("chrUn", "G" * 7)])
+        assert list(counts) == g["counts"] and [_norm(r) for r in recs] == [_norm(r) for r in g["records"]]
+        assert W.plain(header) == g["header"]
+
+
+@pytest.mark.parametrize("seed,opt", W.VCF_CASES)
+def test_files_match_reference_golden(tmp_path, seed, opt):
+    """The product writer's five .vcf.gz files against the unmodified reference's records: same records in the same
+    files, same header lines (FILTER / FORMAT ids, contigs, sample)."""
+    g = _golden(seed)
+    w = vw.VCFWriter(["chr1", "chr2"], [("chr1", 50), ("chr2", 40), ("chrUn", 7)], "HG002", str(tmp_path) + "/", "FULL", "PEPPER", "VC")
+    counts = w.write_vcf_records(W.random_sites(seed, 800), vw.VcfOptions(*opt))
+    w.close()
+    assert list(counts) == g["counts"]
+    for k in vw.VCFWriter.FILES:
+        head, rows = _read_vcf(w.paths[k])
+        want = [r for r in g["records"] if k in r["files"]]
+        assert len(rows) == len(want)
+        for key, items in g["header"]["meta"]:
+            d = dict(items)
+            assert any(h.startswith("##%s=<ID=%s," % (key, d["ID"])) for h in head), (key, d["ID"])
+        for name, length in g["header"]["contigs"]:
+            assert "##contig=<ID=%s,length=%d>" % (name, length) in head
+        assert head[-1].split("\t")[-1] == g["header"]["samples"][0]
+        for row, r in zip(rows, want):
+            assert row[0] == r["contig"] and int(row[1]) == r["start"] + 1 and row[2] == "." and row[3] == r["alleles"][0]
+            assert row[4].split(",") == list(r["alleles"][1:]) and int(row[5]) == r["qual"] and row[6] == r["filter"]
+            gt, ap, gq, dp, ad, vaf, rep = row[9].split(":")
+            assert [int(x) for x in gt.split("/")] == r["GT"] and float(gq) == r["GQ"] and int(dp) == r["DP"] and rep == r["REP"]
+            assert [int(x) for x in ad.split(",")] == r["AD"]
+            assert np.allclose([float(x) for x in vaf.split(",")], r["VAF"], rtol=1e-5, atol=0)
+            assert np.allclose([float(x) for x in ap.split(",")], r["AP"], rtol=1e-5, atol=0)
 
 
 @pytest.mark.parametrize("seed", range(5))
