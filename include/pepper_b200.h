@@ -360,6 +360,21 @@ int pv_polish_chunks(const uint8_t* image_dev, const int64_t* gpos_dev, const in
                      const int64_t* chunk_valid_dev, int64_t n_chunks, int32_t chunk_size, uint8_t* out_images_dev,
                      int64_t* out_positions_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Synthetic inputs generated on the device (bench / tests only; csrc/synth_device.cu): the device twin of the seeded host
+ * generator csrc/synth_reads.c, bit-identical to it, so that whole-genome-scale workloads are
+ * streamed group by group without existing on the host. cfg = the host generator's PvSynthConfig. Count pass: bases and
+ * CIGAR ops of every read (read lengths come from the host: pv_synth_read_lengths of libpv_synth.so); fill pass: the arrays
+ * of a device PvReadBatch at the offsets the caller derived from the counts (bases padded to 16 per read).
+ * ------------------------------------------------------------------------------------------------------- */
+int pv_synth_device_count(const void* cfg, int64_t first_region, int32_t n_regions, const int64_t* read_begin_dev,
+                          const int32_t* read_len_dev, int64_t n_reads, int32_t* n_bases_dev, int32_t* n_ops_dev, void* stream);
+int pv_synth_device_fill(const void* cfg, int64_t first_region, int32_t n_regions, const int64_t* read_begin_dev,
+                         const int32_t* read_len_in_dev, int64_t n_reads, const int64_t* base_off_dev, const int64_t* op_off_dev,
+                         int64_t* read_pos_dev, int32_t* read_len_dev, int32_t* read_n_ops_dev, uint8_t* read_flags_dev,
+                         uint8_t* read_mapq_dev, uint8_t* bases_dev, uint8_t* quals_dev, uint32_t* cigar_dev,
+                         const int64_t* ref_off_dev, uint8_t* ref_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

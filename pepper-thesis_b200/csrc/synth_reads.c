@@ -217,3 +217,48 @@ void pv_synth_fill(const PvSynthConfig* c, int64_t first, int64_t n, int threads
     j.base.read_mapq = read_mapq; j.base.bases = bases; j.base.quals = quals; j.base.cigar = cigar; j.base.ref = ref;
     run_jobs(&j, first, n, threads);
 }
+
+/* ---- host half of the DEVICE generator (csrc/synth_device.cu) -------------------------------------------------------
+ * reads per region and the clamped read lengths: the only part of a read that goes through libm (exp / log / cos of the
+ * length sample), which the GPU's math library does not reproduce bit for bit. 4 bytes per read. */
+static int64_t region_reads(const PvSynthConfig* c, int64_t region) {
+    int64_t cs, ce, rs, re; region_bounds(c, region, &cs, &ce, &rs, &re);
+    const int64_t L = re - rs + 1;
+    double mean_len = c->len_sigma > 0 ? c->len_median * exp(0.5 * c->len_sigma * c->len_sigma) : c->len_median;
+    if (mean_len > (double)c->len_max) mean_len = (double)c->len_max;
+    return (int64_t)(c->coverage * ((double)L + mean_len) / mean_len + 0.5);
+}
+
+/* counts[i] = reads of region first + i (before any are dropped: none is, a read always overlaps its region) */
+void pv_synth_region_reads(const PvSynthConfig* c, int64_t first, int64_t n, int64_t* counts) {
+    for (int64_t i = 0; i < n; i++) counts[i] = region_reads(c, first + i);
+}
+
+typedef struct { const PvSynthConfig* c; int64_t first, r0, r1, stride; const int64_t* read_begin; int32_t* len_out; } LenJob;
+static void* len_worker(void* p) {
+    LenJob* j = (LenJob*)p;
+    for (int64_t reg = j->r0; reg < j->r1; reg += j->stride) {
+        const PvSynthConfig* c = j->c;
+        const int64_t region = j->first + reg, n = j->read_begin[reg + 1] - j->read_begin[reg];
+        for (int64_t r = 0; r < n; r++) {
+            Rng g; g.s = mix64(c->seed ^ ((uint64_t)region << 24) ^ (uint64_t)r * 0xD1B54A32D192ED03ull);
+            double u1 = rng_unif(&g), u2 = rng_unif(&g); if (u1 < 1e-12) u1 = 1e-12;
+            double len_d;
+            if (c->len_sigma > 0) len_d = c->len_median * exp(c->len_sigma * sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2));
+            else len_d = c->len_median + c->len_sd * sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+            int64_t len = (int64_t)len_d; if (len < c->len_min) len = c->len_min; if (len > c->len_max) len = c->len_max;
+            j->len_out[j->read_begin[reg] + r] = (int32_t)len;
+        }
+    }
+    return NULL;
+}
+void pv_synth_read_lengths(const PvSynthConfig* c, int64_t first, int64_t n, int threads, const int64_t* read_begin, int32_t* len_out) {
+    if (threads < 1) threads = 1; if (threads > 256) threads = 256;
+    pthread_t th[256]; LenJob jobs[256];
+    for (int t = 0; t < threads; t++) {
+        jobs[t].c = c; jobs[t].first = first; jobs[t].r0 = t; jobs[t].r1 = n; jobs[t].stride = threads;
+        jobs[t].read_begin = read_begin; jobs[t].len_out = len_out;
+        pthread_create(&th[t], NULL, len_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+}
