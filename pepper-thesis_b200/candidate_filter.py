@@ -41,13 +41,17 @@ class FilterOptions:
 def filter_flags(pred, batch: ReadBatch, options: FilterOptions, contig_len: Optional[Sequence[int]] = None,
                  region_offset: int = 0) -> np.ndarray:
     """uint8 flag per candidate (PV_FLT_* of include/pepper_b200.h). ``pred.region`` indexes ``batch`` regions after
-    subtracting ``region_offset``. ``contig_len`` (per batch region) clips the context at the contig end."""
+    subtracting ``region_offset``. ``contig_len`` (per batch region; default: ``batch.region_contig_len``, which the ingest
+    fills) clips the context at the contig end. A candidate that reaches the allele-frequency division with depth 0 raises
+    ZeroDivisionError like the reference's ``float(allele_frequency) / float(candidate.depth)`` (CandidateFinder.py:477)."""
     n = len(pred)
     flags = np.zeros(n, np.uint8)
     if n == 0:
         return flags
     lib = capi.load()
     region = np.ascontiguousarray(pred.region - region_offset, np.int32)
+    if contig_len is None:
+        contig_len = batch.region_contig_len
     cl = None if contig_len is None else np.ascontiguousarray(contig_len, np.int64)
     arrs = [np.ascontiguousarray(pred.position, np.int64), region, np.ascontiguousarray(pred.depth, np.int32),
             np.ascontiguousarray(pred.frequency, np.int32), np.ascontiguousarray(pred.allele, np.uint8),
@@ -57,6 +61,11 @@ def filter_flags(pred, batch: ReadBatch, options: FilterOptions, contig_len: Opt
         n, *[a.ctypes.data for a in arrs], batch.n_regions, batch.region_ref_start.ctypes.data,
         batch.region_ref_off.ctypes.data, batch.region_ref_len.ctypes.data, cl.ctypes.data if cl is not None else None,
         batch.ref.ctypes.data, int(batch.ref.shape[0]), C.byref(opt), flags.ctypes.data))
+    zero = np.nonzero((np.asarray(pred.depth) <= 0) & ((flags & BAD_REF) == 0))[0]
+    if zero.size:
+        al = pred.alleles()
+        if any(all(ch in b"ACGT" for ch in al[i][1:]) for i in zero):
+            raise ZeroDivisionError("float division by zero (candidate with depth 0 at position %d)" % int(pred.position[zero[0]]))
     return flags
 
 

@@ -62,7 +62,8 @@ __global__ void candidate_filter_kernel(const FilterArgs a) {
     if (valid && alen > 0) {
         const int type = al[0] - '0';
         if (type == 1 && g != 0) f |= 1;                             // phasing list: SNPs with a non-reference genotype (:444-448)
-        const double vaf = (double)a.frequency[i] / (double)a.depth[i];                  // :477
+        // :477 (depth 0 raises ZeroDivisionError in the reference; the host wrapper does the same, here it just must not trap)
+        const double vaf = a.depth[i] > 0 ? (double)a.frequency[i] / (double)a.depth[i] : 0.0;
         const double non_alt = (double)(p1 > p2 ? p1 : p2);                              // :478
         const double pv = type == 1 ? (in_repeat ? a.o.snp_p_value_in_lc : a.o.snp_p_value)
                         : type == 2 ? (in_repeat ? a.o.insert_p_value_in_lc : a.o.insert_p_value)

@@ -94,6 +94,9 @@ struct BgzfReader {
         if (pread(fd, raw.data(), total, coff) != total) return fail(PV_EINVAL, "BGZF: truncated block at %lld", (long long)coff);
         const uint32_t isize = le32(&raw[total - 4]);
         const uint32_t want_crc = le32(&raw[total - 8]);
+        // SAMv1 4.1: a BGZF block holds at most 64 KiB of data; a larger ISIZE is a corrupt (or hostile) trailer, not a
+        // reason to allocate up to 4 GiB per reader thread
+        if (isize > 65536u) return fail(PV_EINVAL, "BGZF: block at %lld claims %u bytes of data (limit 65536)", (long long)coff, isize);
         data.resize(isize);
         bool done = false;
         if (isize && g_fast_inflate) {
@@ -299,18 +302,22 @@ bool long_cigar(const uint8_t* aux, const uint8_t* end, std::vector<uint32_t>& o
         const bool is_cg = s[0] == 'C' && s[1] == 'G';
         const uint8_t t = s[2];
         s += 3;
-        switch (t) {
-            case 'A': case 'c': case 'C': s += 1; break;
-            case 's': case 'S': s += 2; break;
-            case 'i': case 'I': case 'f': s += 4; break;
-            case 'Z': case 'H': while (s < end && *s) ++s; ++s; break;
+        switch (t) {                                          // every advance is checked against the end of the aux block first
+            case 'A': case 'c': case 'C': if (end - s < 1) return false; s += 1; break;
+            case 's': case 'S': if (end - s < 2) return false; s += 2; break;
+            case 'i': case 'I': case 'f': if (end - s < 4) return false; s += 4; break;
+            case 'Z': case 'H':
+                while (s < end && *s) ++s;
+                if (s >= end) return false;                   // unterminated string
+                ++s;
+                break;
             case 'B': {
                 if (end - s < 5) return false;
                 const uint8_t st = s[0];
                 const int es = aux_size(st);
                 if (es < 0) return false;
                 const uint32_t n = le32(s + 1);
-                if (s + 5 + (size_t)n * es > end) return false;
+                if ((uint64_t)n * (uint64_t)es > (uint64_t)(end - s - 5)) return false;
                 if (is_cg && st == 'I') { out.resize(n); for (uint32_t i = 0; i < n; i++) out[i] = le32(s + 5 + 4 * (size_t)i); return true; }
                 s += 5 + (size_t)n * es;
             } break;

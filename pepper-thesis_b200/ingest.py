@@ -235,6 +235,10 @@ def ingest_regions(bam: BAMHandler, fasta: FASTAHandler, contig: str, starts: Se
             _check(lib.pv_ingest_select(out, k.ctypes.data, int(k.shape[0]), C.byref(sel)))
             lib.pv_ingest_free(out)
             out = sel
-        return IngestedReads(out, contig)
+        got = IngestedReads(out, contig)
+        # the regions' reference is padded with 'N' past the contig end; the stage-3 filter needs the true length to clip its
+        # +-10 bp context there like FASTA_handler does (candidate_filter.filter_flags picks this up by default)
+        got.batch.region_contig_len = np.full(got.batch.n_regions, int(fasta.get_chromosome_sequence_length(contig)), np.int64)
+        return got
     finally:
         lib.pv_ingest_free(out)

@@ -76,6 +76,8 @@ class ReadBatch:
     quals_fill: int = 0                         # ... over this fill byte; valid for the thresholds in quals_pred_thr only
     quals_pred_thr: Optional[tuple] = None      # (min_snp_baseq, min_indel_baseq) the predicate form was packed for
     min_qual: int = 0                           # promise: every quality of every read base is >= this (0 = none); scan_min_qual()
+    region_contig_len: Optional[np.ndarray] = None   # int64 [n_regions] length of each region's contig (ingest fills it): the
+                                                # stage-3 filter clips its reference context there like FASTA_handler does
 
     # ---- shape helpers -------------------------------------------------------------------------------------
     @property
@@ -425,7 +427,8 @@ class ReadBatch:
                          if self.quals_patch is not None and (b_hi - b_lo) % 16 == 0 else None),
             read_qpatch_off=(self.read_qpatch_off[rb:re_ + 1] - self.read_qpatch_off[rb]
                              if self.quals_patch is not None and (b_hi - b_lo) % 16 == 0 else None),
-            quals_fill=self.quals_fill, quals_pred_thr=self.quals_pred_thr, min_qual=self.min_qual)
+            quals_fill=self.quals_fill, quals_pred_thr=self.quals_pred_thr, min_qual=self.min_qual,
+            region_contig_len=self.region_contig_len[r0:r1] if self.region_contig_len is not None else None)
 
     def region_slice(self, r: int) -> "ReadBatch":
         """A single-region batch sharing no offsets with the parent (used for per-region oracle calls)."""

@@ -41,9 +41,13 @@ class BgzfTextWriter:
         self._f = open(path, "wb")
         self._buf = bytearray()
         self._level = level
+        self.upos = 0                                            # uncompressed bytes accepted so far
+        self.block_coff = []                                     # compressed file offset of every data block written
 
     def write(self, text: str):
-        self._buf += text.encode()
+        data = text.encode()
+        self._buf += data
+        self.upos += len(data)
         while len(self._buf) >= self.BLOCK:
             self._block(bytes(self._buf[:self.BLOCK]))
             del self._buf[:self.BLOCK]
@@ -52,9 +56,19 @@ class BgzfTextWriter:
         c = zlib.compressobj(self._level, zlib.DEFLATED, -15)
         body = c.compress(data) + c.flush()
         bsize = len(body) + 25                                   # total block size - 1
+        if data:
+            self.block_coff.append(self._f.tell())
         self._f.write(struct.pack("<4BI2BH2BHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, bsize))
         self._f.write(body)
         self._f.write(struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+    def virtual_offset(self, upos: int) -> int:
+        """BGZF virtual file offset (compressed block start << 16 | offset inside the block) of uncompressed byte ``upos``;
+        valid once the file is closed. Data blocks are cut every BLOCK bytes of text."""
+        if not self.block_coff:
+            return 0
+        blk = min(upos // self.BLOCK, len(self.block_coff) - 1)  # the position right behind the file's last byte stays in its block
+        return (self.block_coff[blk] << 16) | (upos - blk * self.BLOCK)
 
     def close(self):
         if self._f is None:
@@ -65,6 +79,74 @@ class BgzfTextWriter:
         self._block(b"")                                         # EOF marker: an empty block
         self._f.close()
         self._f = None
+
+
+def _reg2bin(beg: int, end: int) -> int:
+    """UCSC binning scheme of tabix / BAI (SAMv1 5.3): 0-based half-open [beg, end), 16 kbp smallest bins, 5 levels."""
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+def write_tabix_index(path: str, names: Sequence[str], records: Sequence[tuple]):
+    """``<vcf.gz>.tbi`` as ``pysam.tabix_index(..., preset="vcf")`` leaves it beside every output (VcfWriter.py:41-45): the
+    tabix format of the htslib specification -- BGZF-compressed; header (format 2 = VCF, columns 1/2/0, meta '#'), the
+    sequence names, per sequence the bins with their chunks of virtual offsets and the 16 kbp linear index.
+    ``records``: (sequence index, 0-based begin, end, virtual offset of the line, virtual offset behind it), in file order."""
+    n_ref = len(names)
+    bins = [dict() for _ in range(n_ref)]
+    lin = [[] for _ in range(n_ref)]
+    span = [[None, None, 0] for _ in range(n_ref)]             # first / last virtual offset, record count (the meta pseudo-bin)
+    for tid, beg, end, v0, v1 in records:
+        end = max(end, beg + 1)
+        chunks = bins[tid].setdefault(_reg2bin(beg, end), [])
+        if chunks and chunks[-1][1] == v0:
+            chunks[-1][1] = v1                                   # adjacent records of one bin share a chunk
+        else:
+            chunks.append([v0, v1])
+        w0, w1 = beg >> 14, (end - 1) >> 14
+        if len(lin[tid]) <= w1:
+            lin[tid].extend([0] * (w1 + 1 - len(lin[tid])))
+        for w in range(w0, w1 + 1):
+            if lin[tid][w] == 0:
+                lin[tid][w] = v0
+        span[tid][0] = v0 if span[tid][0] is None else span[tid][0]
+        span[tid][1] = v1
+        span[tid][2] += 1
+    out = bytearray()
+    nm = b"".join(n.encode() + b"\0" for n in names)
+    out += struct.pack("<4s8i", b"TBI\1", n_ref, 2, 1, 2, 0, ord("#"), 0, len(nm)) + nm
+    for tid in range(n_ref):
+        b = bins[tid]
+        out += struct.pack("<i", len(b) + (1 if span[tid][2] else 0))
+        for k in sorted(b):
+            out += struct.pack("<Ii", k, len(b[k]))
+            for v0, v1 in b[k]:
+                out += struct.pack("<QQ", v0, v1)
+        if span[tid][2]:                                         # htslib's pseudo-bin 37450: file span and record counts
+            out += struct.pack("<Ii4Q", 37450, 2, span[tid][0], span[tid][1], span[tid][2], 0)
+        last = 0
+        filled = []
+        for v in lin[tid]:                                       # windows without a record carry the offset of the window before
+            last = v if v else last
+            filled.append(v if v else last)
+        out += struct.pack("<i", len(filled)) + b"".join(struct.pack("<Q", v) for v in filled)
+    w = BgzfTextWriter(path + ".tbi")
+    w._buf += bytes(out)
+    w.upos += len(out)
+    while len(w._buf) >= w.BLOCK:
+        w._block(bytes(w._buf[:w.BLOCK]))
+        del w._buf[:w.BLOCK]
+    w.close()
 
 
 def _phred(p_correct: float) -> int:
@@ -152,6 +234,7 @@ class VCFWriter:
         self.paths = {k: output_dir + v + ".vcf.gz" for k, v in names.items()}         # string concatenation, :21-25
         header = self.header_text(sample_name, contigs)
         self._out = {k: BgzfTextWriter(p) for k, p in self.paths.items()}
+        self._index = {k: [] for k in self.paths}                  # per file: (contig, begin, end, text offset, text offset behind)
         for w in self._out.values():
             w.write(header)
 
@@ -207,13 +290,27 @@ class VCFWriter:
             targets = ["full"] + ((["variant_calling_snp" if snp else "variant_calling_indel", "variant_calling"])
                                   if regenotype else ["pepper"])
             for t in targets:
+                u0 = self._out[t].upos
                 self._out[t].write(line)
+                self._index[t].append((str(contig), int(start), int(start) + len(ref), u0, self._out[t].upos))
                 n[t] += 1
         return n["full"], n["pepper"], n["variant_calling"], n["variant_calling_snp"], n["variant_calling_indel"]
 
     def close(self):
-        for w in self._out.values():
+        """Closes the five files and writes a tabix index beside each (the reference: pysam.tabix_index, VcfWriter.py:41-45)."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        for k, w in self._out.items():
             w.close()
+            tid = {n: i for i, n in enumerate(self.contigs)}
+            names = list(self.contigs)
+            recs = []
+            for contig, beg, end, u0, u1 in self._index[k]:
+                if contig not in tid:                              # a contig the FASTA does not list: indexed behind the others
+                    tid[contig] = len(names); names.append(contig)
+                recs.append((tid[contig], beg, end, w.virtual_offset(u0), w.virtual_offset(u1)))
+            write_tabix_index(self.paths[k], names, recs)
 
     def __del__(self):
         try:

@@ -151,3 +151,67 @@ def test_fasta_path_constructor(tmp_path):
     assert "##contig=<ID=chrS,length=400>" in head and "##contig=<ID=chrT,length=33>" in head
     assert rows == [["chrS", "11", ".", "G", "T", "13", "PASS", ".", "GT:AP:GQ:DP:AD:VAF:REP", "1/1:0.95:13:30:28:0.933:0"]]
     assert _read_vcf(w.paths["variant_calling_snp"])[1] == rows and _read_vcf(w.paths["pepper"])[1] == []
+
+
+def _bgzf_read(path):
+    """-> (decompressed bytes, {compressed block offset: offset of its data in the decompressed stream})"""
+    import zlib
+    raw = open(path, "rb").read()
+    out, starts, off = bytearray(), {}, 0
+    while off < len(raw):
+        size = struct.unpack_from("<H", raw, off + 16)[0] + 1
+        starts[off] = len(out)
+        out += zlib.decompress(raw[off + 18:off + size - 8], -15)
+        off += size
+    return bytes(out), starts
+
+
+def test_tabix_index_finds_every_record(tmp_path):
+    """close() leaves a .tbi beside every file (the reference calls pysam.tabix_index): format per the tabix specification
+    (magic, VCF preset columns, names, bins with chunks, linear index); a region query through it -- bins of the region,
+    chunk offsets resolved to text -- returns exactly the records that overlap the region."""
+    sites = W.random_sites(21, 3000)
+    w = vw.VCFWriter(["chr1", "chr2"], [("chr1", 5_000_000), ("chr2", 100_000)], "S", str(tmp_path) + "/", "F", "P", "V")
+    w.write_vcf_records(sites, vw.VcfOptions())
+    w.close()
+    for k in vw.VCFWriter.FILES:
+        text, starts = _bgzf_read(w.paths[k])
+        idx, _ = _bgzf_read(w.paths[k] + ".tbi")
+        magic, n_ref, fmt, c_seq, c_beg, c_end, meta, skip, l_nm = struct.unpack_from("<4s8i", idx, 0)
+        assert (magic, n_ref, fmt, c_seq, c_beg, c_end, meta, skip) == (b"TBI\1", 2, 2, 1, 2, 0, ord("#"), 0)
+        names = idx[36:36 + l_nm].split(b"\0")[:-1]
+        assert names == [b"chr1", b"chr2"]
+        p = 36 + l_nm
+        rows = [l.split("\t") for l in text.decode().splitlines() if not l.startswith("#")]
+        for tid in range(n_ref):
+            n_bin = struct.unpack_from("<i", idx, p)[0]; p += 4
+            bins = {}
+            for _ in range(n_bin):
+                b, n_chunk = struct.unpack_from("<Ii", idx, p); p += 8
+                bins[b] = [struct.unpack_from("<QQ", idx, p + 16 * i) for i in range(n_chunk)]; p += 16 * n_chunk
+            n_intv = struct.unpack_from("<i", idx, p)[0]; p += 4
+            lin = struct.unpack_from("<%dQ" % n_intv, idx, p); p += 8 * n_intv
+            mine = [r for r in rows if r[0] == names[tid].decode()]
+            if not mine:
+                assert n_bin == 0
+                continue
+            assert 37450 in bins and bins[37450][1][0] == len(mine)
+            lo = int(mine[len(mine) // 3][1]) - 1
+            hi = lo + 20000
+            want = [r for r in mine if int(r[1]) - 1 < hi and int(r[1]) - 1 + len(r[3]) > lo]
+            got = []
+            for b, chunks in bins.items():
+                if b == 37450:
+                    continue
+                for v0, v1 in chunks:
+                    t0 = starts[v0 >> 16] + (v0 & 0xffff)
+                    t1 = starts[v1 >> 16] + (v1 & 0xffff) if (v1 >> 16) in starts else len(text)
+                    for line in text[t0:t1].decode().splitlines():
+                        r = line.split("\t")
+                        assert vw._reg2bin(int(r[1]) - 1, int(r[1]) - 1 + len(r[3])) == b      # every record sits in its bin's chunks
+                        if int(r[1]) - 1 < hi and int(r[1]) - 1 + len(r[3]) > lo:
+                            got.append(r)
+            assert sorted(got) == sorted(want) and len(want) > 0
+            # linear index: the first record at or behind each window starts no earlier than the window's offset
+            first = int(mine[0][1]) - 1
+            assert lin[first >> 14] == bins[vw._reg2bin(first, first + len(mine[0][3]))][0][0]
