@@ -36,16 +36,20 @@ namespace {
 constexpr int NC = 16;           // packed 32-bit counter words per position
 #ifndef PV_K1_THREADS
 #define PV_K1_THREADS 512
-#define PV_K1_PMAX 1088
+#define PV_K1_PMAX 1216
 #define PV_K1_MINB 2
 #endif
 constexpr int K1_THREADS = PV_K1_THREADS;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int MAX_PPT = 4;       // flush: positions per thread  => P <= MAX_PPT * K1_THREADS
-constexpr int P_MAX = PV_K1_PMAX;   // 2 CTAs per SM: 16 words x 1088 positions = 68 KB of counters each
+constexpr int P_MAX = PV_K1_PMAX;   // 2 CTAs per SM: 16 words x 1216 positions = 76 KB of counters each
 constexpr int FREQ_TABLE = 4096; // coverages with a precomputed site-threshold entry (deeper positions divide)
 constexpr int K0_CHUNK = 4;      // reads a K0 warp takes per ticket
-constexpr int ROUND_OPS = 128;   // CIGAR ops a warp stages per round (four per lane)
+#ifndef PV_K1_OPL
+#define PV_K1_OPL 3
+#endif
+constexpr int OPL = PV_K1_OPL;   // consecutive CIGAR ops a lane holds in a round
+constexpr int ROUND_OPS = 32 * OPL;   // CIGAR ops a warp stages per round
 constexpr int QCAP = 63;         // exceptions (mismatches, low-quality bases) a warp queues per round before it counts them
 constexpr int WARP_SCRATCH = 4 * ROUND_OPS + 1 + QCAP;   // ints of per-warp scratch: the round's op words, its table of match
                                  // pieces / inserts / deletes (three ints per entry), the exception queue
@@ -497,9 +501,9 @@ __device__ __forceinline__ OpTable op_table(const TileCtx& c) {
     t.e2 = c.scratch + 3 * ROUND_OPS; t.qn = c.scratch + 4 * ROUND_OPS; t.q = (uint32_t*)(t.qn + 1);
     return t;
 }
-__device__ __forceinline__ void fetch_round(const PvReadBatch& b, const ReadCtx& x, int kb, int lane, uint32_t wv[4]) {
+__device__ __forceinline__ void fetch_round(const PvReadBatch& b, const ReadCtx& x, int kb, int lane, uint32_t wv[OPL]) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < OPL; u++) {
         const int j = kb + lane + 32 * u;
         wv[u] = j < x.n_ops ? __ldg(b.cigar + x.co + j) : 0u;
     }
@@ -522,33 +526,34 @@ __device__ __forceinline__ void uncover(const TileCtx& c, const ReadCtx& x, int 
 }
 // ACC: phase A (match pieces filed, coverage corrections applied); else phase C (inserts and deletes only)
 template <bool ACC>
-__device__ __forceinline__ Round stage_round(const TileCtx& c, const ReadCtx& x, const OpTable& t, const uint32_t wv[4], int kb,
+__device__ __forceinline__ Round stage_round(const TileCtx& c, const ReadCtx& x, const OpTable& t, const uint32_t wv[OPL], int kb,
                                              int a_run, int ri_run, uint32_t w_prev, int lane) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) t.w[lane + 32 * u] = wv[u];
+    for (int u = 0; u < OPL; u++) t.w[lane + 32 * u] = wv[u];
     __syncwarp();
-    const uint4 m = *(const uint4*)(t.w + 4 * lane);
-    const uint32_t ws[4] = {m.x, m.y, m.z, m.w};
-    int ra[4], qa[4], sr = 0, sq = 0;
+    uint32_t ws[OPL];
 #pragma unroll
-    for (int j = 0; j < 4; j++) { op_advance(ws[j], ra[j], qa[j]); sr += ra[j]; sq += qa[j]; }
+    for (int j = 0; j < OPL; j++) ws[j] = t.w[OPL * lane + j];
+    int ra[OPL], qa[OPL], sr = 0, sq = 0;
+#pragma unroll
+    for (int j = 0; j < OPL; j++) { op_advance(ws[j], ra[j], qa[j]); sr += ra[j]; sq += qa[j]; }
     int ir = sr, iq = sq;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int tr = __shfl_up_sync(0xffffffffu, ir, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
         if (lane >= d) { ir += tr; iq += tq; }
     }
-    uint32_t pw = __shfl_up_sync(0xffffffffu, ws[3], 1);   // the op in front of this lane's first one
+    uint32_t pw = __shfl_up_sync(0xffffffffu, ws[OPL - 1], 1);   // the op in front of this lane's first one
     if (lane == 0) pw = w_prev;
     int pr = a_run + ir - sr, pq = ri_run + iq - sq;       // state in front of this lane's first op
-    int f0[4], f1[4], f2[4];                               // entry words of this lane's ops
+    int f0[OPL], f1[OPL], f2[OPL];                               // entry words of this lane's ops
     uint32_t kind = 0;                                     // per op: 1 match piece, 2 insert, 3 delete
     int v = 0, n_m = 0, n_i = 0, n_d = 0, nsp = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < OPL; j++) {
         const int op = (int)(ws[j] & 15u), len = (int)(ws[j] >> 4);
         f0[j] = pr; f1[j] = pq; f2[j] = (len << 1) | ((is_match_op((int)(pw & 15u)) && (pw >> 4) != 0u) ? 1 : 0);
-        if (kb + 4 * lane + j < x.n_ops && pr <= x.nv) {
+        if (kb + OPL * lane + j < x.n_ops && pr <= x.nv) {
             v++;
             if (op == 1) { n_i++; kind |= 2u << (2 * j); }
             else if (op == 2) { n_d++; kind |= 3u << (2 * j); }
@@ -590,7 +595,7 @@ __device__ __forceinline__ Round stage_round(const TileCtx& c, const ReadCtx& x,
     int at_m = ((incl - pk) >> 8) & 0xff, at_i = r.n_m + (((incl - pk) >> 16) & 0xff), at_d = ROUND_OPS - 1 - (((incl - pk) >> 24) & 0xff);
     const int sub0 = isub - nsp;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < OPL; j++) {
         const uint32_t kd = (kind >> (2 * j)) & 3u;
         if (kd) {
             const int at = kd == 1u ? at_m++ : kd == 2u ? at_i++ : at_d--;
@@ -599,7 +604,7 @@ __device__ __forceinline__ Round stage_round(const TileCtx& c, const ReadCtx& x,
     }
     r.a_next = __shfl_sync(0xffffffffu, pr, 31);
     r.ri_next = __shfl_sync(0xffffffffu, pq, 31);
-    r.w_last = __shfl_sync(0xffffffffu, ws[3], 31);
+    r.w_last = __shfl_sync(0xffffffffu, ws[OPL - 1], 31);
     __syncwarp();
     return r;
 }
@@ -702,7 +707,7 @@ __device__ void accumulate_entry(const SumParams& p, const TileCtx& c, const Til
     const OpTable t = op_table(c);
     int kb = e.k, a_run = e.a, ri_run = e.ri;
     uint32_t w_prev = kb > 0 ? __ldg(b.cigar + x.co + kb - 1) : 0u;   // the op in front of the round's first one
-    uint32_t wv[4];
+    uint32_t wv[OPL];
     fetch_round(b, x, kb, lane, wv);
     {   // the bases this walk will compare (about one per tile position from read index e.ri on) start their way from DRAM now
         const int64_t off = (int64_t)e.ri + 128 * lane;
@@ -787,7 +792,7 @@ __device__ void record_entry(const SumParams& p, const TileCtx& c, const TileEnt
     const ReadCtx x = make_read_ctx(p, c, e.read);
     const OpTable t = op_table(c);
     int kb = e.k, a_run = e.a, ri_run = e.ri;
-    uint32_t wv[4];
+    uint32_t wv[OPL];
     fetch_round(b, x, kb, lane, wv);
     while (true) {
         const Round rd = stage_round<false>(c, x, t, wv, kb, a_run, ri_run, 0u, lane);
