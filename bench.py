@@ -327,7 +327,7 @@ def measure_workload(ctx, preset, coverage, mbp, scaling, steps, warmup, main):
     bp = batch.candidate_bp
     bp_all = _sum_over_ranks(ctx, bp)
     hp = pipeline.HotPath(ctx.model, thr, ctx.device, group_regions=int(os.environ.get("PV_BENCH_HOST_GROUP", "128")),
-                          skip_quals=skip_q)
+                          skip_quals=skip_q, infer_batch=int(os.environ.get("PV_BENCH_INFER_BATCH", "32768")))
     out = {"preset": preset, "coverage": coverage, "mbp": mbp, "scaling": scaling, "regions_rank0": n_regions,
            "reads_rank0": batch.n_reads, "read_bases_rank0": int(batch.read_len.astype(np.int64).sum()),
            "min_qual": int(batch.min_qual), "synth_seconds": round(gen_s, 1), "bp_all_ranks": int(bp_all)}

@@ -92,7 +92,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(clusters * tc::CLUSTER));
-    cfg.blockDim = dim3(tc::THREADS);
+    cfg.blockDim = dim3(tc::threads_of<Epi>());
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];

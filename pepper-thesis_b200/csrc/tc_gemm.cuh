@@ -129,6 +129,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// the same for 8 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // the reverse: thread i of the warp writes 16 consecutive fp32 columns of row (lane_base + i)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
@@ -169,7 +178,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+template <int THREADS_> __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS_) : "memory"); }   // the epilogue warps only
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
@@ -219,6 +228,12 @@ struct NextTile { bool valid; int dir, n_blk, row; bool ok; };
 //   static constexpr bool kInlinePrefetch               true: one state buffer; the functor itself issues the next tile's
 //                                                       cp.async from inside operator() as soon as it has consumed its slots
 
+// epilogue warps of gemm_kernel<E>: 8 (two per TMEM lane quarter, each taking half of the tile's columns) unless the functor
+// asks for 16 (E::kEpiWarps: four per lane quarter, a quarter of the columns each -- for epilogue-bound tiles)
+template <class E, class = void> struct epi_warps { static constexpr int value = 8; };
+template <class E> struct epi_warps<E, decltype((void)E::kEpiWarps)> { static constexpr int value = E::kEpiWarps; };
+template <class E> constexpr int threads_of() { return 128 + 32 * epi_warps<E>::value; }
+
 template <class E, class = void> struct slot_tiles { static constexpr bool value = false; };
 template <class E> struct slot_tiles<E, decltype((void)E::kSlotTiles)> { static constexpr bool value = E::kSlotTiles; };
 
@@ -244,7 +259,7 @@ __device__ __forceinline__ TileIdx decode_tile(int tile, const GemmShape& g, int
 }
 
 template <class Epilogue>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(threads_of<Epilogue>(), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
             const __grid_constant__ CUtensorMap tmW /* box = 64 k x W_SLICE_ROWS rows */, const GemmShape g, const Epilogue epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -278,7 +293,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     if (warp == 1 && lane == 0) {
         // a stage may be refilled only when ALL CTAs of the cluster have consumed it (peers multicast into it)
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], epi_warps<Epilogue>::value); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -349,11 +364,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;
+        const int half = (warp - 4) >> 2;                       // which part of the columns: 0..1 (8 warps) or 0..3 (16 warps)
         const int te = threadIdx.x - 128;
         epi.setup(epi_scratch, te);                            // constants only (biases): may run ahead of the previous grid's end
         grid_dependency_wait();
-        epi_barrier();
+        epi_barrier<32 * epi_warps<Epilogue>::value>();
         int it = 0;
         if (cluster_id < n_tiles) {                            // state of the first tile
             const TileIdx t0 = decode_tile<SLOT>(cluster_id, g, dir_sh, nb_sh, dir_mask, nb_mask);
