@@ -72,7 +72,7 @@ enum { C_T = 0,        // difference array -> aligned bases with q >= min_snp_ba
        C_COV2 = 10,    // low: insert-anchored coverage bumps (:453-454); high: snp_count of bases that are no dense SNP allele
        C_INSDEL = 11,  // low: insert_count; high: delete_count
        C_SNP = 12 };   // +0..3 = "1A" "1C" "1G" "1T" allele counts
-enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_ENTRIES = 6, CTR_COUNT = 8 };
+enum { CTR_SITES = 0, CTR_EVENTS = 1, CTR_CANDS = 2, CTR_STATUS = 3, CTR_K0_TICKET = 4, CTR_K2_TICKET = 5, CTR_ENTRIES = 6, CTR_COUNT = 8 };
 enum { ST_SITE_OVF = 1, ST_EVENT_OVF = 2, ST_CAND_OVF = 4, ST_INTERNAL = 8,
        ST_NEED_QUALS = 16,     // a quality was needed (insert over the read's end) but the batch came without its quality array
        ST_ENTRY_OVF = 32 };    // more (tile, read) entries than the workspace was sized for (cannot happen with pv_summary_workspace_bytes' bound)
@@ -1090,58 +1090,162 @@ __device__ int cmp_event(const SumParams& p, const Event& x, const Event& y) {
     return lx == ly ? 0 : (lx < ly ? -1 : 1);
 }
 
-__device__ void try_emit(const SumParams& p, const SiteRec& sr, int s, int type, bool dense, int elen, int64_t ptr,
-                         int nf, int nr, uint32_t sub) {
+// the per-allele filters of :682-712; fills the candidate record and its order key when the allele survives
+__device__ __forceinline__ bool make_candidate(const SumParams& p, const SiteRec& sr, int s, int type, bool dense, int elen, int64_t ptr,
+                                               int nf, int nr, uint32_t sub, CandRec& cr, unsigned long long& key) {
     const int depth = min125(sr.cov);                                           // :682
     const int ad = nf + nr;
-    if ((double)ad < p.t.candidate_support) return;                             // :693
+    if ((double)ad < p.t.candidate_support) return false;                       // :693
     const double cf = (double)ad / ((double)depth > 1.0 ? (double)depth : 1.0); // :689
-    if (type != 1 && cf < p.t.indel_candidate_freq) return;                     // :697
-    if (type == 1 && cf < p.t.snp_candidate_freq) return;                       // :700
-    if (type != 1 && p.t.skip_indels) return;                                   // :704
-    if (!(sr.flags & (1 << type))) return;                                      // :708-712
-    const int slot = atomicAdd(&p.ctr[CTR_CANDS], 1);
-    if (slot >= p.cand_cap) { atomicOr(&p.ctr[CTR_STATUS], ST_CAND_OVF); return; }
-    CandRec cr; cr.ptr = ptr; cr.site = s; cr.info = (uint32_t)type | (dense ? 4u : 0u) | ((uint32_t)elen << 8);
+    if (type != 1 && cf < p.t.indel_candidate_freq) return false;               // :697
+    if (type == 1 && cf < p.t.snp_candidate_freq) return false;                 // :700
+    if (type != 1 && p.t.skip_indels) return false;                             // :704
+    if (!(sr.flags & (1 << type))) return false;                                // :708-712
+    cr.ptr = ptr; cr.site = s; cr.info = (uint32_t)type | (dense ? 4u : 0u) | ((uint32_t)elen << 8);
     cr.nf = nf; cr.nr = nr;
-    p.cands[slot] = cr;
-    p.cand_key[slot] = ((unsigned long long)sr.gpos << 24) | ((unsigned long long)type << 22) | (unsigned long long)sub;
+    key = ((unsigned long long)sr.gpos << 24) | ((unsigned long long)type << 22) | (unsigned long long)sub;
+    return true;
 }
 
+// Candidates are collected 32 at a time in the warp's shared-memory buffer and appended to the global list with ONE atomic
+// per 32 (one per candidate serialised the whole kernel on a single L2 address). Called by all 32 lanes.
+struct CandStage {
+    CandRec* rec; unsigned long long* key; int used;
+    __device__ __forceinline__ void flush(const SumParams& p, int lane) {
+        if (used == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&p.ctr[CTR_CANDS], used);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < used) {
+            if (base + lane < p.cand_cap) { p.cands[base + lane] = rec[lane]; p.cand_key[base + lane] = key[lane]; }
+            else atomicOr(&p.ctr[CTR_STATUS], ST_CAND_OVF);
+        }
+        __syncwarp();
+        used = 0;
+    }
+    __device__ __forceinline__ void add(const SumParams& p, bool pass, const CandRec& cr, unsigned long long k, int lane) {
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        const int need = __popc(m);
+        if (need == 0) return;
+        if (used + need > 32) flush(p, lane);
+        if (pass) { const int at = used + __popc(m & ((1u << lane) - 1u)); rec[at] = cr; key[at] = k; }
+        used += need;
+        __syncwarp();
+    }
+};
+
+// type and the first seven allele bytes of an event as ONE big-endian 64-bit word: comparing two words compares
+// "<type><bytes>" up to byte 7; shorter strings are zero-padded, and equal words are told apart by the lengths (both <= 7:
+// the shorter string is a prefix of the longer and sorts first) or, rarely, by the remaining bytes
+// Delete alleles of one site are all reference substrings that START at the site: one is a prefix of the other, so their
+// order and equality are those of their lengths -- the key is exact and needs no byte at all (they are also the long ones:
+// the same 10-base deletion seen in 25 reads used to cost 25 x 25 byte-wise compares in global memory).
+__device__ __forceinline__ unsigned long long event_key(const SumParams& p, const Event& e) {
+    const int len = (int)(e.info >> 8);
+    if ((e.info & 3u) == 3u) return (3ull << 56) | (unsigned long long)len;
+    const uint8_t* s = event_bytes(p, e);
+    unsigned long long k = (unsigned long long)(e.info & 3u) << 56;
+    const int m = len < 7 ? len : 7;
+    for (int i = 0; i < m; i++) k |= (unsigned long long)s[i] << (48 - 8 * i);
+    return k;
+}
+// bytes 7 .. 14 of the allele (zero-padded): with it, alleles of up to 15 bytes compare without touching memory again
+__device__ __forceinline__ unsigned long long event_key2(const SumParams& p, const Event& e) {
+    const int len = (int)(e.info >> 8);
+    if ((e.info & 3u) == 3u || len <= 7) return 0ull;
+    const uint8_t* s = event_bytes(p, e);
+    unsigned long long k = 0;
+    const int m = len < 15 ? len : 15;
+    for (int i = 7; i < m; i++) k |= (unsigned long long)s[i] << (56 - 8 * (i - 7));
+    return k;
+}
+
+// Warp per site. The alleles a site recorded are de-duplicated EXACTLY (no hashing): every lane holds one event's key in
+// registers, the keys of 32 events at a time go round the warp by shuffle, and only equal keys of alleles longer than seven
+// bytes fall back to byte-wise compares in global memory. Per distinct allele: forward / reverse counts, its rank in
+// std::set<std::string> order, the filters of :682-712, one candidate record.
 __global__ void site_allele_kernel(const SumParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     int n_sites = p.ctr[CTR_SITES];
     if (n_sites > p.site_cap) n_sites = p.site_cap;
-    for (int s = warp; s < n_sites; s += n_warps) {
-        const SiteRec sr = p.sites[s];
-        if ((sr.flags & PF_SNP) && lane < 4) {                                  // dense "1A" "1C" "1G" "1T"
-            const int nf = sr.snp[2 * lane], nr = sr.snp[2 * lane + 1];
-            if (nf + nr > 0) {
-                const uint8_t byte = (uint8_t)("ACGT"[lane]);
-                try_emit(p, sr, s, 1, true, 1, (int64_t)byte, nf, nr, (uint32_t)byte);
+    __shared__ CandRec s_rec[8][32];
+    __shared__ unsigned long long s_key[8][32];
+    CandStage st; st.rec = s_rec[threadIdx.x >> 5]; st.key = s_key[threadIdx.x >> 5]; st.used = 0;
+    (void)warp; (void)n_warps;
+    // 32 sites per ticket. First LANE per site: the dense SNP alleles need nothing but the site record (most sites have no
+    // recorded event at all). Then WARP per site for the sites of the block that did record events.
+    for (;;) {
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(&p.ctr[CTR_K2_TICKET], 32);
+        const int base = __shfl_sync(0xffffffffu, tk, 0);
+        if (base >= n_sites) break;
+        const bool have = base + lane < n_sites;
+        SiteRec mine;
+        mine.flags = 0; mine.n_ev = 0; mine.ev_off = 0;
+        if (have) mine = p.sites[base + lane];
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {                                           // dense "1A" "1C" "1G" "1T"
+            CandRec cr; unsigned long long key = 0; bool pass = false;
+            if (have && (mine.flags & PF_SNP)) {
+                const int nf = mine.snp[2 * a], nr = mine.snp[2 * a + 1];
+                const uint8_t byte = (uint8_t)("ACGT"[a]);
+                pass = nf + nr > 0 && make_candidate(p, mine, base + lane, 1, true, 1, (int64_t)byte, nf, nr, (uint32_t)byte, cr, key);
             }
+            st.add(p, pass, cr, key, lane);
         }
+        unsigned heavy = __ballot_sync(0xffffffffu, have && mine.n_ev > 0 && (int64_t)mine.ev_off + mine.n_ev <= p.ev_cap);
+        while (heavy) {
+        const int s = base + __ffs(heavy) - 1;
+        heavy &= heavy - 1;
+        const SiteRec sr = p.sites[s];
         const int n = sr.n_ev;
-        if (n <= 0 || (int64_t)sr.ev_off + n > p.ev_cap) continue;
         if (sr.fill != n && lane == 0) atomicOr(&p.ctr[CTR_STATUS], ST_INTERNAL);
         const Event* ev = p.events + sr.ev_off;
-        for (int i = lane; i < n; i += 32) {
-            const Event ei = ev[i];
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            Event ei; ei.ptr = 0; ei.info = 0; ei.pad = 0;
+            unsigned long long ki = 0, ki2 = 0;
+            if (i < n) { ei = ev[i]; ki = event_key(p, ei); ki2 = event_key2(p, ei); }
+            const int li = (int)(ei.info >> 8);
             int less = 0, nf = 0, nr = 0; bool dup = false;
-            for (int j = 0; j < n; j++) {
-                const Event ej = ev[j];
-                const int cc = (j == i) ? 0 : cmp_event(p, ej, ei);
-                if (cc < 0) less++;
-                else if (cc == 0) { if (j < i) dup = true; if ((ej.info >> 2) & 1u) nr++; else nf++; }
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                Event ej = ei; unsigned long long kj = ki, kj2 = ki2;        // the block on the diagonal is already in registers
+                if (j0 != i0) {
+                    ej.ptr = 0; ej.info = 0; kj = 0; kj2 = 0;
+                    if (j0 + lane < n) { ej = ev[j0 + lane]; kj = event_key(p, ej); kj2 = event_key2(p, ej); }
+                }
+                const int cnt = n - j0 < 32 ? n - j0 : 32;
+                for (int jj = 0; jj < cnt; jj++) {
+                    const unsigned long long k = __shfl_sync(0xffffffffu, kj, jj);
+                    const unsigned long long k2 = __shfl_sync(0xffffffffu, kj2, jj);
+                    const uint32_t info = __shfl_sync(0xffffffffu, ej.info, jj);
+                    if (i >= n) continue;
+                    int cc;
+                    if (k != ki) cc = k < ki ? -1 : 1;
+                    else if (k2 != ki2) cc = k2 < ki2 ? -1 : 1;
+                    else {
+                        const int lj = (int)(info >> 8);
+                        if ((info & 3u) == 3u) cc = 0;                          // deletes: equal keys are equal lengths are equal alleles
+                        else if (li <= 15 || lj <= 15) cc = lj == li ? 0 : (lj < li ? -1 : 1);
+                        else { const Event e2 = ev[j0 + jj]; cc = cmp_event(p, e2, ei); }     // rare: both longer than the keys
+                    }
+                    if (cc < 0) less++;
+                    else if (cc == 0) { if (j0 + jj < i) dup = true; if ((info >> 2) & 1u) nr++; else nf++; }
+                }
             }
-            if (dup) continue;
-            const int type = (int)(ei.info & 3u);
-            const uint32_t sub = type == 1 ? (uint32_t)(*event_bytes(p, ei)) : (uint32_t)less;
-            try_emit(p, sr, s, type, false, (int)(ei.info >> 8), ei.ptr, nf, nr, sub);
+            CandRec cr; unsigned long long key = 0; bool pass = false;
+            if (i < n && !dup) {
+                const int type = (int)(ei.info & 3u);
+                const uint32_t sub = type == 1 ? (uint32_t)(*event_bytes(p, ei)) : (uint32_t)less;
+                pass = make_candidate(p, sr, s, type, false, li, ei.ptr, nf, nr, sub, cr, key);
+            }
+            st.add(p, pass, cr, key, lane);
+        }
         }
     }
+    st.flush(p, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1397,7 +1501,7 @@ extern "C" int pv_summary_regions(const PvReadBatch* batch, const int64_t* regio
     pv::prof_end(pv::FAM_SUM_TILE, stream, 1);
 
     pv::prof_begin(pv::FAM_SUM_ALLELE, stream);
-    site_allele_kernel<<<sms * 8, 256, 0, stream>>>(p);
+    site_allele_kernel<<<sms * 4, 256, 0, stream>>>(p);
     PV_CUDA_CHECK(cudaGetLastError());
     pv::prof_end(pv::FAM_SUM_ALLELE, stream, 1);
 

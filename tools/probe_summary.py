@@ -27,5 +27,6 @@ for it in range(5):
     prof = {k: round(v[0], 3) for k, v in capi.profile_collect().items() if v[0] > 0}
     K = int(ws.count.item())
     ab = b.algorithmic_bytes(K)
+    print("ctr", ws.ws[:32].view(torch.int32).tolist())
     print("iter %d: %.3f ms  K=%d status=%d  %.1f Mbp/s  %.1f GB/s algorithmic (%.3f of 6536)" % (
         it, ms, K, ws.status(), b.candidate_bp / ms / 1e3, ab / ms / 1e6, ab / ms / 1e6 / 6536), prof, flush=True)
