@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY (see oracle/pyoracle.py): CPU restatement of BAM_handler::get_reads
 (/root/reference/pepper_variant/modules/cpp/bam_handler.cpp:115-444) over already-decoded BAM records, written as the
-same per-base loops as the reference. The reference file needs htslib (absent here), so this restatement is pinned
-only by the reference's source text and by hand-built records in tests/test_ingest.py: PARITY UNPINNED against a
-compiled reference for the ingest row.
+same per-base loops as the reference. PINNED (round 2): tests/test_ingest.py::test_get_reads_matches_compiled_reference
+checks it against the UNMODIFIED bam_handler.cpp compiled over oracle/hts_mini (oracle/_ref/pv_ref_bam) and against the
+digests that reference wrote (tests/golden/bam_get_reads.json, tests/golden/make_bam_golden.py).
 
 Iterator contract of htslib sam_itr_queryi(idx, tid, beg, end) as used at :128: records of `tid` with
 pos < end and bam_endpos > beg, in file order."""

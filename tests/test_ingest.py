@@ -1,10 +1,16 @@
 """BAM/FASTA ingest (libpv_ingest.so) against files written by the pure-Python writer in tests/bamio.py, an independent
-Python BAM decoder, and the restatement of BAM_handler::get_reads in oracle/bam_port.py."""
+Python BAM decoder, the restatement of BAM_handler::get_reads in oracle/bam_port.py and -- round 2 --
+the UNMODIFIED reference bam_handler.cpp / fasta_handler.cpp compiled over a minimal htslib stand-in
+(oracle/_ref/pv_ref_bam, oracle/ref_shim_bam.cpp, oracle/hts_mini/) plus digests of its output (tests/golden/bam_get_reads.json)."""
 import os
 import struct
 
 import numpy as np
 import pytest
+
+import hashlib
+import json
+import sys
 
 import bam_port
 import bamio
@@ -83,6 +89,46 @@ def files(tmp_path_factory):
     return dict(bam=bam, fa=fa, ref=ref, recs=decoded)
 
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(_HERE, "golden", "bam_get_reads.json")
+SPANS = [(0, 5000), (19900, 20100), (39000, 47000), (61234, 71234), (CONTIG_LEN - 3000, CONTIG_LEN + 100), (50000, 50001), (7, 8),
+         (29000, 31000), (0, CONTIG_LEN)]
+FILTERS = [(False, 0, 1), (True, 10, 1), (True, 0, 15)]
+
+
+def ref_bam_module():
+    """oracle/_ref/pv_ref_bam (the compiled reference) or None where it was never built."""
+    d = os.path.join(os.path.dirname(_HERE), "oracle", "_ref")
+    if not (os.path.isdir(d) and any(f.startswith("pv_ref_bam") for f in os.listdir(d))):
+        return None
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import pv_ref_bam
+    return pv_ref_bam
+
+
+def _ref_reads(handler, contig, a, b, supp, mapq, baseq):
+    """Reads of the compiled reference as the dicts bam_port returns. The record with SEQ '*' is left out: the reference
+    indexes seq / qual of that record unchecked (bam_handler.cpp:210-213: reads past the record, undefined)."""
+    out = []
+    for r in handler.get_reads(contig, a, b, supp, mapq, baseq):
+        if r["query_name"] == "noseq":
+            continue
+        r = dict(r)
+        r["sequence"] = r["sequence"].decode()
+        r["cigar_tuples"] = [tuple(c) for c in r["cigar_tuples"]]
+        out.append(r)
+    return out
+
+
+def _digest(reads):
+    h = hashlib.sha256()
+    for w in reads:
+        h.update(repr((w["query_name"], w["pos"], w["pos_end"], w["sequence"], list(w["base_qualities"]), [tuple(c) for c in w["cigar_tuples"]],
+                       bool(w["is_reverse"]), w["mapping_quality"], w["hp_tag"])).encode())
+    return "%d:%s" % (len(reads), h.hexdigest()[:24])
+
+
 def _assert_reads_equal(got: ingest.IngestedReads, want, lo=0):
     b = got.batch
     assert b.n_reads - lo >= 0
@@ -120,6 +166,81 @@ def test_get_reads_matches_port(files, span, supp, min_mapq):
     if span == (39000, 47000):
         names = [w["query_name"] for w in want]
         assert "refskip" in names and "noseq" not in names
+
+
+def _packed_as_dicts(got):
+    b = got.batch
+    out = []
+    for i in range(b.n_reads):
+        n = int(b.read_len[i]); bo = int(b.read_base_off[i]); co = int(b.read_cigar_off[i]); k = int(b.read_n_ops[i])
+        out.append(dict(query_name=got.query_names[i], pos=int(b.read_pos[i]), pos_end=int(got.pos_end[i]),
+                        sequence=bytes(b.bases[bo:bo + n]).decode(), base_qualities=[int(q) for q in b.quals[bo:bo + n]],
+                        cigar_tuples=[(int(c) & 15, int(c) >> 4) for c in b.cigar[co:co + k]], is_reverse=bool(b.read_flags[i] & 1),
+                        mapping_quality=int(b.read_mapq[i]), hp_tag=int(got.hp_tag[i])))
+    return out
+
+
+def test_get_reads_matches_compiled_reference(files):
+    """PINNED: the product's get_reads against the reference's own bam_handler.cpp (compiled over oracle/hts_mini, which
+    finds the records by a linear scan, so the product's BAI query is checked too), the restatement against the same, and
+    all three against the committed digests."""
+    golden = json.load(open(GOLDEN))
+    mod = ref_bam_module()
+    ref = mod.BAM_handler(files["bam"]) if mod else None
+    bam = ingest.BAMHandler(files["bam"])
+    n_checked = 0
+    for span in SPANS:
+        for supp, mapq, baseq in FILTERS:
+            key = "%d-%d supp=%d mapq=%d baseq=%d" % (span[0], span[1], supp, mapq, baseq)
+            port = bam_port.get_reads(files["recs"], 0, span[0], span[1], supp, mapq, baseq)
+            got = bam.get_reads_packed("chrS", span[0], span[1], supp, mapq, baseq)
+            assert _digest(port) == golden["get_reads"][key], key
+            assert _digest(_packed_as_dicts(got)) == golden["get_reads"][key], key
+            if ref is not None:
+                want = _ref_reads(ref, "chrS", span[0], span[1], supp, mapq, baseq)
+                assert _digest(want) == golden["get_reads"][key], key
+                _assert_reads_equal(got, want)
+                n_checked += len(want)
+    assert ref is None or n_checked > 500
+    if ref is not None:
+        assert ref.get_chromosome_sequence_names() == bam.get_chromosome_sequence_names()
+        assert set(mod.BAM_handler(files["bam"]).get_sample_names()) == bam.get_sample_names()
+        assert [tuple(x) for x in mod.BAM_handler(files["bam"]).get_chromosome_sequence_names_with_length()] == \
+            bam.get_chromosome_sequence_names_with_length()
+        other = _ref_reads(ref, "chrT", 0, 5000, False, 0, 0)
+        assert [r["query_name"] for r in other] == ["other_contig"]
+
+
+def test_bad_indicies_match_compiled_reference(files):
+    """type_read.bad_indicies of the drop-in module (bam_handler.cpp:216-222, :307) against the compiled reference."""
+    mod = ref_bam_module()
+    if mod is None:
+        pytest.skip("oracle/_ref/pv_ref_bam not built")
+    from pepper_thesis_b200.build import PEPPER_VARIANT as PV
+    ours = PV.BAM_handler(files["bam"]).get_reads("chrS", 39000, 47000, True, 0, 15)
+    want = _ref_reads(mod.BAM_handler(files["bam"]), "chrS", 39000, 47000, True, 0, 15)
+    assert len(ours) == len(want) > 5
+    for r, w in zip(ours, want):
+        assert r.query_name == w["query_name"] and r.bad_indicies == list(w["bad_indicies"])
+        assert r.flags.is_supplementary == w["is_supplementary"]
+
+
+def test_fasta_matches_compiled_reference(files):
+    mod = ref_bam_module()
+    golden = json.load(open(GOLDEN))
+    fa = ingest.FASTAHandler(files["fa"])
+    ref = mod.FASTA_handler(files["fa"]) if mod else None
+    for c, a, b in [("chrS", 0, 1), ("chrS", 0, 70), ("chrS", 69, 71), ("chrS", 1, 1000), ("chrS", 433, 567), ("chrS", CONTIG_LEN - 10, CONTIG_LEN),
+                    ("chrS", CONTIG_LEN - 10, CONTIG_LEN + 50), ("chrT", 3, 12), ("chrT", 4990, 5600), ("chrS", 0, CONTIG_LEN)]:
+        got = fa.get_reference_sequence(c, a, b)
+        key = "%s:%d-%d" % (c, a, b)
+        assert hashlib.sha256(got.encode()).hexdigest()[:24] == golden["fasta"][key], key
+        if ref is not None:
+            assert got == ref.get_reference_sequence(c, a, b).decode(), key
+    if ref is not None:
+        assert ref.get_chromosome_names() == fa.get_chromosome_names()
+        assert ref.get_chromosome_sequence_length("chrS") == fa.get_chromosome_sequence_length("chrS")
+        assert ref.get_chromosome_sequence_length("zz") == fa.get_chromosome_sequence_length("zz")
 
 
 def test_get_reads_other_contig_and_missing(files):
@@ -216,6 +337,14 @@ def test_exports():
         assert hasattr(lib, s), s
 
 
+def _oracle_reads(files, a, b, supp, mapq, baseq):
+    """get_reads of the compiled reference where it was built (else the restatement, which the CPU tests pin to it)."""
+    mod = ref_bam_module()
+    if mod is None:
+        return bam_port.get_reads(files["recs"], 0, a, b, supp, mapq, baseq)
+    return _ref_reads(mod.BAM_handler(files["bam"]), "chrS", a, b, supp, mapq, baseq)
+
+
 @pytest.mark.gpu
 def test_bam_to_candidates_gpu(files):
     """Config-1 shape: BAM + FASTA -> ingest -> CUDA summary, against the reference oracle fed by the get_reads port."""
@@ -233,7 +362,7 @@ def test_bam_to_candidates_gpu(files):
     for r, (s, e) in enumerate(zip(starts, ends)):
         rs, re_ = max(0, s - 100), e + 100
         reads = [H.Read(w["pos"], w["sequence"], w["cigar_tuples"], rev=w["is_reverse"], q=w["base_qualities"], mapq=w["mapping_quality"])
-                 for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 55, 0)]
+                 for w in _oracle_reads(files, rs, re_, False, 55, 0)]
         ob = pack_regions([Region("chrS", rs, re_, files["ref"][rs:re_ + 1], s, e, reads)])
         want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
         m = d["region"] == r
@@ -288,7 +417,7 @@ def test_create_summary_from_bam_gpu(files):
     cands = AlignmentSummarizer(PV.BAM_handler(files["bam"]), PV.FASTA_handler(files["fa"]), "chrS", s, e).create_summary(opt)
     rs, re_ = s - 100, e + 100
     reads = [H.Read(w["pos"], w["sequence"], w["cigar_tuples"], rev=w["is_reverse"], q=w["base_qualities"], mapq=w["mapping_quality"])
-             for w in bam_port.get_reads(files["recs"], 0, rs, re_, False, 55, 1)]
+             for w in _oracle_reads(files, rs, re_, False, 55, 1)]
     ob = pack_regions([Region("chrS", rs, re_, files["ref"][rs:re_ + 1], s, e, reads)])
     want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
     assert [c.position for c in cands] == list(want["position"]) and len(cands) > 20
