@@ -139,8 +139,9 @@ int pv_device_count(void);
 /* Launch accounting and optional CUDA-event profiling of the library's own kernels (used by bench.py for
  * `gpu_launches` and the per-kernel roofline). Families, in order: 0 summary per-tile work lists (CIGAR spans), 1 summary pileup tile,
  * 2 summary site alleles, 3 summary key sort, 4 summary window emit, 5 LSTM input prep, 6 LSTM encoder steps,
- * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc, 11 candidate filter, 12 polisher summary. */
-#define PV_PROFILE_FAMILIES 13
+ * 7 LSTM decoder steps, 8 LSTM MLP + head, 9 GRU steps, 10 GRU misc, 11 candidate filter, 12 polisher summary,
+ * 13 GRU input-projection GEMMs, 14 GRU head, 15 BAM decode (pv_bam_*). */
+#define PV_PROFILE_FAMILIES 16
 void pv_profile_enable(int on);
 int pv_profile_collect(double* ms_by_family, int64_t* launches_by_family);
 void pv_profile_reset(void);
@@ -374,6 +375,66 @@ int pv_synth_device_fill(const void* cfg, int64_t first_region, int32_t n_region
                          int64_t* read_pos_dev, int32_t* read_len_dev, int32_t* read_n_ops_dev, uint8_t* read_flags_dev,
                          uint8_t* read_mapq_dev, uint8_t* bases_dev, uint8_t* quals_dev, uint32_t* cigar_dev,
                          const int64_t* ref_off_dev, uint8_t* ref_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BAM decoding on the device ("next" row 1 of SURVEY.md 8f; csrc/ingest_gpu.cu, csrc/bam_core.cuh): what
+ * BAM_handler::get_reads (pepper_variant/modules/cpp/bam_handler.cpp:115-451) does per byte -- BGZF inflate, record
+ * parsing, the cut of every read to its region -- as kernels, so that the packed read batch is written straight into
+ * HBM. The host's share (which bytes to read, where the BGZF blocks and the record-chain entry points are) is
+ * pv_bam_plan* of pepper_ingest.h. All pointers are device memory; results are bit-identical to pv_ingest_regions.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct PvBgzfBlock {
+    int64_t  c_off;      /* offset of the block's DEFLATE payload in the compressed buffer */
+    int32_t  c_len;      /* payload bytes */
+    int32_t  isize;      /* bytes it inflates to (<= 65536) */
+    int64_t  u_off;      /* where they go in the inflated stream (blocks are concatenated) */
+    uint32_t crc;        /* CRC-32 of those bytes (BGZF trailer) */
+    uint32_t _pad;
+} PvBgzfBlock;
+typedef struct PvBamPair {   /* one read of the batch: a record cut to one span */
+    int64_t rec_off;     /* offset of the record's block_size field in the inflated stream */
+    int32_t span;
+    int32_t n_ops;       /* kept CIGAR ops */
+    int64_t n_bases;     /* kept bases */
+} PvBamPair;
+/* One thread per BGZF block; *n_bad_dev = blocks that did not decode to isize bytes (or, with verify_crc, whose CRC-32
+ * differs from the trailer). */
+int pv_bam_inflate_blocks(const uint8_t* comp_dev, int64_t comp_bytes, const PvBgzfBlock* blocks_dev, int32_t n_blocks,
+                          uint8_t* inflated_dev, int64_t inflated_bytes, int32_t verify_crc, int32_t* n_bad_dev, void* stream);
+/* Record boundaries. Segment s = [seg_begin[s], seg_end[s]) of the inflated stream starts at a record and ends where the
+ * next one starts. rec_off_dev == NULL: count pass -- seg_first_dev[0..n_segments] receives the exclusive scan of the
+ * record counts (total in [n_segments]); else fill pass with the same seg_first_dev. *status_dev: bit0 a chain left its
+ * segment / ran into a malformed record, bit1 rec_capacity too small. */
+int pv_bam_index_records(const uint8_t* inflated_dev, int64_t inflated_bytes, const int64_t* seg_begin_dev,
+                         const int64_t* seg_end_dev, int32_t n_segments, int64_t* seg_first_dev, int64_t* rec_off_dev,
+                         int64_t rec_capacity, int32_t* status_dev, void* stream);
+/* Reads per record: span j = [span_start[j], span_stop[j]] (ascending in both), the get_reads interval of region j.
+ * rec_pair_first_dev[0..n_records] receives the exclusive scan of the number of (record, span) pairs that yield a read
+ * (flag / mapq filters :137-150, iterator overlap, non-empty cut). status bits: 2 malformed record, 3 internal. */
+int pv_bam_clip_count(const uint8_t* inflated_dev, int64_t inflated_bytes, const int64_t* rec_off_dev, int64_t n_records,
+                      int32_t tid, const int64_t* span_start_dev, const int64_t* span_stop_dev, int32_t n_spans,
+                      int32_t include_supplementary, int32_t min_mapq, int64_t* rec_pair_first_dev, int32_t* status_dev, void* stream);
+int64_t pv_bam_clip_workspace_bytes(int64_t n_pairs);
+/* The batch's read order (span ascending, file order inside a span) and layout: pairs_sorted_dev[n_pairs],
+ * read_base_off_dev / read_cigar_off_dev [n_pairs] (bases padded to 16 per read), region_read_begin_dev[n_spans + 1],
+ * totals_dev[2] = {bytes of the base / quality arrays, CIGAR ops}. */
+int pv_bam_clip_layout(const uint8_t* inflated_dev, int64_t inflated_bytes, const int64_t* rec_off_dev, int64_t n_records,
+                       int32_t tid, const int64_t* span_start_dev, const int64_t* span_stop_dev, int32_t n_spans,
+                       int32_t include_supplementary, int32_t min_mapq, const int64_t* rec_pair_first_dev, int64_t n_pairs,
+                       void* workspace_dev, int64_t workspace_bytes, PvBamPair* pairs_sorted_dev, int64_t* read_base_off_dev,
+                       int64_t* read_cigar_off_dev, int64_t* region_read_begin_dev, int64_t* totals_dev, int32_t* status_dev,
+                       void* stream);
+/* One warp per read: the PvReadBatch arrays + type_read.pos_end / hp_tag / BAM FLAG, where each query name sits in the
+ * inflated stream, and the smallest kept quality (-> PvReadBatch.min_qual). status bit 4: internal. */
+int pv_bam_clip_write(const uint8_t* inflated_dev, int64_t inflated_bytes, const PvBamPair* pairs_sorted_dev, int64_t n_pairs,
+                      const int64_t* span_start_dev, const int64_t* span_stop_dev, const int64_t* read_base_off_dev,
+                      const int64_t* read_cigar_off_dev, int64_t* read_pos_dev, int64_t* read_pos_end_dev, int32_t* read_len_dev,
+                      int32_t* read_n_ops_dev, uint8_t* read_flags_dev, uint8_t* read_mapq_dev, int32_t* hp_dev,
+                      uint16_t* bam_flag_dev, int64_t* name_off_dev, int32_t* name_len_dev, uint8_t* bases_dev,
+                      uint8_t* quals_dev, uint32_t* cigar_dev, int32_t* min_qual_dev, int32_t* status_dev, void* stream);
+/* NUL-terminated query names, read i at out_off_dev[i] (the caller's exclusive scan of name_len + 1) */
+int pv_bam_gather_names(const uint8_t* inflated_dev, const int64_t* name_off_dev, const int32_t* name_len_dev,
+                        const int64_t* out_off_dev, int64_t n, uint8_t* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

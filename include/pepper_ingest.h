@@ -96,6 +96,23 @@ uint64_t pv_ingest_fast_blocks(void);
 /* The decoder itself, for tests: raw DEFLATE (RFC 1951) of exactly n_out bytes; PV_OK or PV_EINVAL. */
 int pv_inflate_raw(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t n_out);
 
+/* ---- host plan of the device-side decode (pv_bam_inflate_blocks ... pv_bam_clip_write of pepper_b200.h) ----
+ * pv_bam_plan: the BAI query of get_reads(contig, start, stop) (bam_handler.cpp:127-130) -> the byte ranges of the file that
+ * can hold a record overlapping [start, stop). pv_bam_plan_load reads them (threaded pread) into the caller's buffer of
+ * pv_bam_plan_comp_bytes bytes -- page-locked, so the upload runs at PCIe speed -- and walks the BGZF headers there:
+ * block table (payload offset in that buffer, sizes, CRC, position in the concatenated inflated stream) and the chain
+ * segments (record-aligned entry points: chunk starts + the linear index's offsets). */
+typedef struct PvBamPlan PvBamPlan;
+int pv_bam_plan(const PvBamFile* bam, const char* contig, int64_t start, int64_t stop, PvBamPlan** out);
+int64_t pv_bam_plan_comp_bytes(const PvBamPlan* p);
+int32_t pv_bam_plan_tid(const PvBamPlan* p);
+int pv_bam_plan_load(PvBamPlan* p, uint8_t* comp_out, int32_t threads);
+int32_t pv_bam_plan_n_blocks(const PvBamPlan* p);
+int32_t pv_bam_plan_n_segments(const PvBamPlan* p);
+int64_t pv_bam_plan_inflated_bytes(const PvBamPlan* p);
+int pv_bam_plan_tables(const PvBamPlan* p, PvBgzfBlock* blocks_out, int64_t* seg_begin_out, int64_t* seg_end_out);
+void pv_bam_plan_free(PvBamPlan* p);
+
 #ifdef __cplusplus
 }
 #endif

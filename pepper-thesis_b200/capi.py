@@ -24,7 +24,9 @@ EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_profile_enable"
            "pv_summary_regions", "pv_summary_regions_host", "pv_lstm_create", "pv_lstm_destroy",
            "pv_lstm_workspace_bytes", "pv_lstm_infer", "pv_lstm_infer_host", "pv_gru_create", "pv_gru_destroy",
            "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks", "pv_candidate_filter",
-           "pv_candidate_filter_host", "pv_polish_workspace_bytes", "pv_polish_count", "pv_polish_emit", "pv_polish_chunks"]
+           "pv_candidate_filter_host", "pv_polish_workspace_bytes", "pv_polish_count", "pv_polish_emit", "pv_polish_chunks",
+           "pv_bam_inflate_blocks", "pv_bam_index_records", "pv_bam_clip_count", "pv_bam_clip_workspace_bytes", "pv_bam_clip_layout",
+           "pv_bam_clip_write", "pv_bam_gather_names"]
 
 
 class PvError(RuntimeError):
@@ -144,13 +146,21 @@ def load() -> C.CDLL:
             lib.pv_candidate_filter.argtypes = [C.c_int64] + [C.c_void_p] * 12 + [C.POINTER(PvFilterOptionsStruct), C.c_void_p, C.c_void_p]
             lib.pv_candidate_filter_host.argtypes = [C.c_int64] + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 5 + \
                 [C.c_int64, C.POINTER(PvFilterOptionsStruct), C.c_void_p]
+        P, I64, I32 = C.c_void_p, C.c_int64, C.c_int32
+        lib.pv_bam_inflate_blocks.argtypes = [P, I64, P, I32, P, I64, I32, P, P]
+        lib.pv_bam_index_records.argtypes = [P, I64, P, P, I32, P, P, I64, P, P]
+        lib.pv_bam_clip_count.argtypes = [P, I64, P, I64, I32, P, P, I32, I32, I32, P, P, P]
+        lib.pv_bam_clip_workspace_bytes.argtypes = [I64]; lib.pv_bam_clip_workspace_bytes.restype = I64
+        lib.pv_bam_clip_layout.argtypes = [P, I64, P, I64, I32, P, P, I32, I32, I32, P, I64, P, I64, P, P, P, P, P, P, P]
+        lib.pv_bam_clip_write.argtypes = [P, I64, P, I64, P, P, P, P] + [P] * 13 + [P, P, P]
+        lib.pv_bam_gather_names.argtypes = [P, P, P, P, I64, P, P]
         _lib = lib
     return _lib
 
 
 FAMILIES = ["sum_cigar_prefix", "sum_pileup_tile", "sum_site_alleles", "sum_key_sort", "sum_emit_windows",
             "lstm_input_prep", "lstm_encoder_steps", "lstm_decoder_steps", "lstm_mlp_head", "gru_steps", "gru_misc",
-            "candidate_filter", "polish_summary", "gru_gx_gemm", "gru_head"]
+            "candidate_filter", "polish_summary", "gru_gx_gemm", "gru_head", "bam_decode"]
 
 
 def profile_collect():

@@ -28,7 +28,7 @@ int sm_count();
 
 // kernel families for launch counting and optional CUDA-event profiling (pv_profile_*)
 enum Family { FAM_SUM_PREFIX = 0, FAM_SUM_TILE, FAM_SUM_ALLELE, FAM_SUM_SORT, FAM_SUM_EMIT, FAM_LSTM_PREP, FAM_LSTM_ENC,
-              FAM_LSTM_DEC, FAM_LSTM_MLP, FAM_GRU_STEP, FAM_GRU_MISC, FAM_FILTER, FAM_POLISH, FAM_GRU_GX, FAM_GRU_HEAD, FAM_COUNT };
+              FAM_LSTM_DEC, FAM_LSTM_MLP, FAM_GRU_STEP, FAM_GRU_MISC, FAM_FILTER, FAM_POLISH, FAM_GRU_GX, FAM_GRU_HEAD, FAM_INGEST, FAM_COUNT };
 // brackets `launches` kernel launches of one family on `stream`; records events only while profiling is enabled
 void prof_begin(int fam, cudaStream_t stream);
 void prof_end(int fam, cudaStream_t stream, int launches);

@@ -327,19 +327,9 @@ bool long_cigar(const uint8_t* aux, const uint8_t* end, std::vector<uint32_t>& o
     return false;
 }
 
-// BAM_handler::get_reads for spans [start_j, stop_j] (clipping inclusive of stop, iterator half-open like htslib), the
-// spans ascending by start. ONE pass over the records of their union: every BGZF block is inflated and every record
-// parsed once, then cut to each span it overlaps (a per-span index query re-inflates the blocks around every shared
-// boundary and everything the coarse bins of long reads drag in: 1.4x the file for 100 kbp spans of 12 kbp reads).
-// Each span receives exactly the records its own htslib iterator would return, in file order.
-struct Span { int64_t start, stop; };
-int collect_reads_multi(const PvBamFile& f, int tid, const std::vector<Span>& spans, const PvIngestOptions& o, std::vector<ReadSink>& sinks) {
-    if (tid < 0 || tid >= (int)f.index.size() || spans.empty()) return PV_OK;
-    const BaiRef& ref = f.index[tid];
-    int64_t start = spans[0].start, stop = spans[0].stop;      // the union (spans are ascending by start)
-    for (const Span& sp : spans) stop = std::max(stop, sp.stop);
-    size_t j_lo = 0;                                           // spans before j_lo end at or before every later record
-    // candidate chunks: bins overlapping [start, stop), not before the linear-index lower bound
+// merged BAI chunks that can hold a record overlapping [start, stop): bins overlapping the span, not before the
+// linear-index lower bound (what htslib's iterator reads)
+std::vector<Chunk> query_chunks(const BaiRef& ref, int64_t start, int64_t stop) {
     std::vector<uint32_t> bins;
     reg2bins(start, stop, bins);
     uint64_t min_off = 0;
@@ -356,13 +346,29 @@ int collect_reads_multi(const PvBamFile& f, int tid, const std::vector<Span>& sp
         // chunk of a coarse bin that straddles it is entered there instead of at its own beginning
         for (const Chunk& c : it->second) if (c.end > min_off) chunks.push_back(Chunk{std::max(c.beg, min_off), c.end});
     }
-    if (chunks.empty()) return PV_OK;
     std::sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.beg < b.beg; });
     std::vector<Chunk> merged;
     for (const Chunk& c : chunks) {
         if (!merged.empty() && c.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, c.end);
         else merged.push_back(c);
     }
+    return merged;
+}
+
+// BAM_handler::get_reads for spans [start_j, stop_j] (clipping inclusive of stop, iterator half-open like htslib), the
+// spans ascending by start. ONE pass over the records of their union: every BGZF block is inflated and every record
+// parsed once, then cut to each span it overlaps (a per-span index query re-inflates the blocks around every shared
+// boundary and everything the coarse bins of long reads drag in: 1.4x the file for 100 kbp spans of 12 kbp reads).
+// Each span receives exactly the records its own htslib iterator would return, in file order.
+struct Span { int64_t start, stop; };
+int collect_reads_multi(const PvBamFile& f, int tid, const std::vector<Span>& spans, const PvIngestOptions& o, std::vector<ReadSink>& sinks) {
+    if (tid < 0 || tid >= (int)f.index.size() || spans.empty()) return PV_OK;
+    const BaiRef& ref = f.index[tid];
+    int64_t start = spans[0].start, stop = spans[0].stop;      // the union (spans are ascending by start)
+    for (const Span& sp : spans) stop = std::max(stop, sp.stop);
+    size_t j_lo = 0;                                           // spans before j_lo end at or before every later record
+    const std::vector<Chunk> merged = query_chunks(ref, start, stop);
+    if (merged.empty()) return PV_OK;
 
     BgzfReader rd;
     rd.fd = f.fd; rd.file_size = f.file_size;
@@ -779,6 +785,151 @@ extern "C" int pv_ingest_regions(PvBamFile* bam, const PvFastaFile* fasta, const
     *out = b;
     return PV_OK;
 }
+
+// ---- plan for the device-side decode (pv_bam_inflate_blocks / pv_bam_index_records / pv_bam_clip_* of pepper_b200.h) --------
+// The host's share of the GPU ingest: which compressed bytes to read (BAI query, as collect_reads_multi), where every BGZF
+// block's DEFLATE payload sits in them, where its bytes land in the concatenated inflated stream, and where record chains
+// can be entered (chunk starts + the linear index's per-16-kbp record offsets), so that the device can find all record
+// boundaries with many short pointer chases instead of one long one.
+struct PvBamPlan {
+    const PvBamFile* bam = nullptr;
+    int tid = -1;
+    struct Range { int64_t file_off, bytes, buf_off; uint64_t vbeg, vend; };
+    std::vector<Range> ranges;                    // one per merged chunk
+    int64_t comp_bytes = 0;
+    std::vector<PvBgzfBlock> blocks;
+    std::vector<int64_t> block_file_off;          // file offset of every block (ascending)
+    std::vector<int64_t> seg_begin, seg_end;
+    int64_t inflated_bytes = 0;
+};
+
+extern "C" int pv_bam_plan(const PvBamFile* bam, const char* contig, int64_t start, int64_t stop, PvBamPlan** out) {
+    if (!bam || !contig || !out) return fail(PV_EINVAL, "null argument");
+    PvBamPlan* p = new PvBamPlan();
+    p->bam = bam;
+    p->tid = tid_of(*bam, contig);
+    *out = p;
+    if (p->tid < 0 || p->tid >= (int)bam->index.size() || stop <= start) return PV_OK;      // empty plan
+    for (const Chunk& c : query_chunks(bam->index[p->tid], start, stop)) {
+        PvBamPlan::Range r;
+        r.vbeg = c.beg; r.vend = c.end;
+        r.file_off = (int64_t)(c.beg >> 16);
+        int64_t last = (int64_t)(c.end >> 16) + ((c.end & 0xffff) ? 65536 + 26 : 0);   // the end block is needed unless the chunk ends at its first byte
+        if (last > bam->file_size) last = bam->file_size;
+        r.bytes = last > r.file_off ? last - r.file_off : 0;
+        r.buf_off = p->comp_bytes;
+        p->comp_bytes += (r.bytes + 255) & ~(int64_t)255;
+        p->ranges.push_back(r);
+    }
+    p->comp_bytes += 256;                         // the decoder may look a few bytes past a payload
+    return PV_OK;
+}
+extern "C" int64_t pv_bam_plan_comp_bytes(const PvBamPlan* p) { return p ? p->comp_bytes : 0; }
+extern "C" int32_t pv_bam_plan_tid(const PvBamPlan* p) { return p ? p->tid : -1; }
+
+// reads the planned byte ranges into comp_out (pv_bam_plan_comp_bytes bytes; page-locked memory lets the upload run at
+// PCIe speed) with `threads` readers, then walks the BGZF headers there
+extern "C" int pv_bam_plan_load(PvBamPlan* p, uint8_t* comp_out, int32_t threads) {
+    if (!p || (!comp_out && p->comp_bytes > 256)) return fail(PV_EINVAL, "null argument");
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    struct Piece { int64_t file_off, bytes, buf_off; };
+    std::vector<Piece> pieces;
+    for (const auto& r : p->ranges)
+        for (int64_t o = 0; o < r.bytes; o += (8 << 20)) pieces.push_back(Piece{r.file_off + o, std::min<int64_t>(8 << 20, r.bytes - o), r.buf_off + o});
+    std::atomic<size_t> next(0);
+    std::atomic<int> bad(0);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= pieces.size()) break;
+            int64_t got = 0;
+            while (got < pieces[i].bytes) {
+                const ssize_t n = pread(p->bam->fd, comp_out + pieces[i].buf_off + got, (size_t)(pieces[i].bytes - got), pieces[i].file_off + got);
+                if (n <= 0) { bad = 1; return; }
+                got += n;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads && t < (int)pieces.size(); t++) pool.emplace_back(work);
+    work();
+    for (std::thread& t : pool) t.join();
+    if (bad) return fail(PV_EINVAL, "BAM: short read of the planned byte ranges");
+
+    p->blocks.clear(); p->block_file_off.clear(); p->seg_begin.clear(); p->seg_end.clear();
+    int64_t u = 0;
+    const std::vector<uint64_t>& linear = p->bam->index[p->tid].linear;
+    for (const auto& r : p->ranges) {
+        const size_t first_block = p->blocks.size();
+        const int64_t end_coff = (int64_t)(r.vend >> 16);
+        const bool end_block_needed = (r.vend & 0xffff) != 0;
+        int64_t o = 0;
+        while (o < r.bytes) {
+            const int64_t coff = r.file_off + o;
+            if (coff > end_coff || (coff == end_coff && !end_block_needed)) break;
+            const uint8_t* h = comp_out + r.buf_off + o;
+            if (r.bytes - o < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(PV_EINVAL, "BGZF: bad block magic at %lld", (long long)coff);
+            const int xlen = le16(h + 10);
+            int bsize = -1;
+            if (r.bytes - o < 12 + xlen) return fail(PV_EINVAL, "BGZF: truncated extra field at %lld", (long long)coff);
+            for (int x = 0; x + 4 <= xlen;) {
+                const int sl = le16(h + 12 + x + 2);
+                if (h[12 + x] == 'B' && h[12 + x + 1] == 'C' && sl == 2 && x + 6 <= xlen) { bsize = le16(h + 12 + x + 4); break; }
+                x += 4 + sl;
+            }
+            if (bsize < 0) return fail(PV_EINVAL, "BGZF: block without BC subfield at %lld", (long long)coff);
+            const int total = bsize + 1, cdata_off = 12 + xlen, cdata_len = total - cdata_off - 8;
+            if (cdata_len < 0 || r.bytes - o < total) return fail(PV_EINVAL, "BGZF: truncated block at %lld", (long long)coff);
+            const uint32_t isize = le32(h + total - 4);
+            if (isize > 65536u) return fail(PV_EINVAL, "BGZF: block at %lld claims %u bytes of data (limit 65536)", (long long)coff, isize);
+            PvBgzfBlock b;
+            b.c_off = r.buf_off + o + cdata_off; b.c_len = cdata_len; b.isize = (int32_t)isize; b.u_off = u; b.crc = le32(h + total - 8); b._pad = 0;
+            p->blocks.push_back(b);
+            p->block_file_off.push_back(coff);
+            u += isize;
+            o += total;
+        }
+        // virtual offset -> offset in the inflated stream (only offsets inside this range's blocks)
+        auto to_u = [&](uint64_t v, int64_t& out_u) -> bool {
+            const int64_t coff = (int64_t)(v >> 16);
+            auto it = std::lower_bound(p->block_file_off.begin() + first_block, p->block_file_off.end(), coff);
+            if (it == p->block_file_off.end() || *it != coff) {
+                if (it == p->block_file_off.end() && (v & 0xffff) == 0 && !p->blocks.empty()) { out_u = u; return true; }   // right behind the last block
+                return false;
+            }
+            const PvBgzfBlock& b = p->blocks[(size_t)(it - p->block_file_off.begin())];
+            if ((int64_t)(v & 0xffff) > b.isize) return false;
+            out_u = b.u_off + (int64_t)(v & 0xffff);
+            return true;
+        };
+        int64_t ub, ue;
+        if (!to_u(r.vbeg, ub) || !to_u(r.vend, ue)) return fail(PV_EINVAL, "BAI: a chunk boundary does not fall on a BGZF block of the file");
+        std::vector<int64_t> starts{ub};
+        for (uint64_t v : linear) {
+            int64_t x;
+            if (v > r.vbeg && v < r.vend && to_u(v, x) && x > starts.back() && x < ue) starts.push_back(x);
+        }
+        for (size_t i = 0; i < starts.size(); i++) {
+            p->seg_begin.push_back(starts[i]);
+            p->seg_end.push_back(i + 1 < starts.size() ? starts[i + 1] : ue);
+        }
+    }
+    p->inflated_bytes = u;
+    g_inflated_bytes.fetch_add((uint64_t)u, std::memory_order_relaxed);
+    return PV_OK;
+}
+extern "C" int32_t pv_bam_plan_n_blocks(const PvBamPlan* p) { return p ? (int32_t)p->blocks.size() : 0; }
+extern "C" int32_t pv_bam_plan_n_segments(const PvBamPlan* p) { return p ? (int32_t)p->seg_begin.size() : 0; }
+extern "C" int64_t pv_bam_plan_inflated_bytes(const PvBamPlan* p) { return p ? p->inflated_bytes : 0; }
+extern "C" int pv_bam_plan_tables(const PvBamPlan* p, PvBgzfBlock* blocks_out, int64_t* seg_begin_out, int64_t* seg_end_out) {
+    if (!p) return fail(PV_EINVAL, "null argument");
+    if (blocks_out && !p->blocks.empty()) memcpy(blocks_out, p->blocks.data(), p->blocks.size() * sizeof(PvBgzfBlock));
+    if (seg_begin_out && !p->seg_begin.empty()) memcpy(seg_begin_out, p->seg_begin.data(), p->seg_begin.size() * 8);
+    if (seg_end_out && !p->seg_end.empty()) memcpy(seg_end_out, p->seg_end.data(), p->seg_end.size() * 8);
+    return PV_OK;
+}
+extern "C" void pv_bam_plan_free(PvBamPlan* p) { delete p; }
 
 extern "C" int pv_ingest_view(const PvIngestBatch* b, PvReadBatch* v) {
     if (!b || !v) return fail(PV_EINVAL, "null argument");

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .read_batch import ARRAY_NAMES, ReadBatch
+from .read_batch import ARRAY_NAMES, PvReadBatchStruct as PvReadBatchStructT, ReadBatch
 
 _TORCH_DT = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
              np.dtype(np.uint32): torch.int32}
@@ -214,6 +214,75 @@ class DeviceBatch:
         elif self.packed_c is not None:
             n -= self.host.cigar.nbytes - self.host.cigar16.nbytes
         return n
+
+
+class _Shape:
+    """What the pipeline asks a batch's ``host`` for when there is no host copy (sizes and the quality promise)."""
+
+    def __init__(self, n_reads, n_bases, n_ops, n_regions, min_qual, contigs, region_contig_len):
+        self.n_reads, self.n_bases, self.n_ops, self.n_regions = int(n_reads), int(n_bases), int(n_ops), int(n_regions)
+        self.min_qual = int(min_qual)
+        self.contigs = contigs
+        self.region_contig_len = region_contig_len
+        self.quals_pred_thr = None
+
+
+class DeviceReadBatch:
+    """A ``PvReadBatch`` that was BORN on the device (``ingest_gpu``: BAM decoded by kernels): same interface as
+    :class:`DeviceBatch` for the summary / pipeline code, no host arrays behind it. ``tensors`` maps every name of
+    ``ARRAY_NAMES`` to a device tensor; the region fields are also kept as numpy (``regions``)."""
+
+    def __init__(self, tensors, regions, min_qual, device, contigs=None, region_contig_len=None, h2d_bytes=0):
+        self.t = dict(tensors)
+        self.device = torch.device(device)
+        self.regions = regions                                # dict of numpy arrays: the region_* fields
+        self.region_len = np.ascontiguousarray(regions["region_ref_end"] - regions["region_ref_start"] + 1).astype(np.int64)
+        self.total_positions = int(self.region_len.sum())
+        n_reads = int(self.t["read_pos"].numel()) if "read_pos" in self.t else 0
+        self.host = _Shape(n_reads, self.t["bases"].numel(), self.t["cigar"].numel(), len(self.region_len), min_qual,
+                           contigs or [], region_contig_len)
+        self.quals_skipped = False
+        self.qpatches = None
+        self._h2d = int(h2d_bytes)
+        s = PvReadBatchStructT()
+        s.n_reads, s.n_bases, s.n_ops, s.n_ref = n_reads, self.host.n_bases, self.host.n_ops, int(self.t["ref"].numel())
+        s.n_regions = self.host.n_regions
+        s.min_qual = int(min_qual)
+        for name in ARRAY_NAMES:
+            setattr(s, name, self.t[name].data_ptr() if self.t[name].numel() else None)
+        self.struct = s
+
+    def unpack(self):
+        pass
+
+    def ensure_quals(self):
+        pass
+
+    def with_min_qual(self, min_qual: int) -> "DeviceReadBatch":
+        import copy
+        other = copy.copy(self)
+        other.struct = type(self.struct).from_buffer_copy(self.struct)
+        other.struct.min_qual = int(min_qual)
+        return other
+
+    def record_stream(self, stream):
+        for t in self.t.values():
+            t.record_stream(stream)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self._h2d
+
+    def to_host(self) -> ReadBatch:
+        """Download (tests, interop)."""
+        a = {}
+        for name in ARRAY_NAMES:
+            v = self.t[name].cpu().numpy()
+            a[name] = v.view(np.uint32) if name == "cigar" else v
+        n = self.host.n_reads
+        for name in ("read_pos", "read_base_off", "read_len", "read_cigar_off", "read_n_ops", "read_flags", "read_mapq"):
+            a[name] = a[name][:n]
+        return ReadBatch(contigs=list(self.host.contigs), min_qual=self.host.min_qual, region_contig_len=self.host.region_contig_len, **a)
 
 
 class SummaryWorkspace:

@@ -22,7 +22,9 @@ EXPORTS = ["pv_ingest_last_error", "pv_bam_open", "pv_bam_close", "pv_bam_n_targ
            "pv_bam_target_len", "pv_bam_sample_names", "pv_fasta_open", "pv_fasta_close", "pv_fasta_n_seq",
            "pv_fasta_seq_name", "pv_fasta_seq_len", "pv_fasta_fetch", "pv_ingest_regions", "pv_bam_get_reads",
            "pv_ingest_view", "pv_ingest_hp_tags", "pv_ingest_pos_end", "pv_ingest_bam_flags", "pv_ingest_query_names", "pv_ingest_select",
-           "pv_ingest_free", "pv_ingest_inflated_bytes", "pv_ingest_fast_blocks", "pv_inflate_raw"]
+           "pv_ingest_free", "pv_ingest_inflated_bytes", "pv_ingest_fast_blocks", "pv_inflate_raw",
+           "pv_bam_plan", "pv_bam_plan_comp_bytes", "pv_bam_plan_tid", "pv_bam_plan_load", "pv_bam_plan_n_blocks",
+           "pv_bam_plan_n_segments", "pv_bam_plan_inflated_bytes", "pv_bam_plan_tables", "pv_bam_plan_free"]
 
 
 class _Opt(C.Structure):
@@ -63,6 +65,15 @@ def load():
         lib.pv_ingest_inflated_bytes.restype = C.c_uint64
         lib.pv_ingest_fast_blocks.restype = C.c_uint64
         lib.pv_inflate_raw.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        lib.pv_bam_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+        lib.pv_bam_plan_comp_bytes.argtypes = [C.c_void_p]; lib.pv_bam_plan_comp_bytes.restype = C.c_int64
+        lib.pv_bam_plan_tid.argtypes = [C.c_void_p]
+        lib.pv_bam_plan_load.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        lib.pv_bam_plan_n_blocks.argtypes = [C.c_void_p]
+        lib.pv_bam_plan_n_segments.argtypes = [C.c_void_p]
+        lib.pv_bam_plan_inflated_bytes.argtypes = [C.c_void_p]; lib.pv_bam_plan_inflated_bytes.restype = C.c_int64
+        lib.pv_bam_plan_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pv_bam_plan_free.argtypes = [C.c_void_p]
         _LIB = lib
     return _LIB
 

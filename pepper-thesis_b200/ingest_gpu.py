@@ -1,0 +1,231 @@
+"""BAM -> packed read batch ON THE DEVICE ("overlapping inflate with GPU work").
+
+The host reads the compressed bytes a BAI query names into page-locked memory and walks the BGZF block headers
+(``pv_bam_plan*`` of libpv_ingest.so); the bytes go up once, and kernels of libpepper_b200.so (csrc/ingest_gpu.cu) inflate
+every BGZF block (one thread per block), find the record boundaries, apply ``BAM_handler::get_reads``
+(/root/reference/pepper_variant/modules/cpp/bam_handler.cpp:115-451: flag / mapq filters, the cut of every read to its
+region +- 100 bases, HP tag) and write the ``PvReadBatch`` arrays in HBM -- the summary kernels start from there, no read
+byte ever exists on the host in decoded form. Bit-identical to :func:`ingest.ingest_regions` (tests/test_ingest_gpu.py).
+There is no CPU fallback: without a device the C-ABI returns PV_ENODEVICE.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import capi, ingest
+from .device import DeviceReadBatch
+from .read_batch import ARRAY_NAMES
+from .summarizer import REGION_SAFE_BASES
+
+_BLOCK_DT = np.dtype([("c_off", np.int64), ("c_len", np.int32), ("isize", np.int32), ("u_off", np.int64), ("crc", np.uint32), ("_pad", np.uint32)])
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else None)
+
+
+class DeviceIngestedReads:
+    """Result of :func:`ingest_regions_gpu`: ``batch`` (a :class:`DeviceReadBatch`) + per-read ``pos_end``, ``hp_tag``,
+    ``bam_flag`` device tensors; ``query_names`` are gathered and downloaded on first use."""
+
+    def __init__(self, batch, pos_end, hp_tag, bam_flag, inflated, name_off, name_len, stats):
+        self.batch, self.pos_end, self.hp_tag, self.bam_flag = batch, pos_end, hp_tag, bam_flag
+        self._inflated, self._name_off, self._name_len = inflated, name_off, name_len
+        self.stats = stats
+        self._names = None
+
+    @property
+    def query_names(self) -> List[str]:
+        if self._names is None:
+            n = int(self._name_len.numel())
+            if n == 0:
+                self._names = []
+            else:
+                sizes = self._name_len.to(torch.int64) + 1
+                off = torch.cumsum(sizes, 0) - sizes
+                total = int(sizes.sum().item())
+                out = torch.empty(total, dtype=torch.uint8, device=self._inflated.device)
+                st = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+                capi.check(capi.load().pv_bam_gather_names(_ptr(self._inflated), _ptr(self._name_off), _ptr(self._name_len), _ptr(off), n, _ptr(out), st))
+                self._names = [s.decode() for s in out.cpu().numpy().tobytes().split(b"\0")[:-1]]
+        return self._names
+
+    def release_stream(self):
+        """Drop the inflated BAM bytes (kept only for the query names)."""
+        self.query_names
+        self._inflated = None
+
+
+def _status(t, what):
+    v = int(t.item())
+    if v:
+        raise capi.PvError(-1, "%s: device status %d (1 record chain broken, 2 capacity, 4 malformed record, 8/16 internal)" % (what, v))
+
+
+def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, contig: str, starts: Sequence[int], ends: Sequence[int],
+                       include_supplementary=False, min_mapq=0, min_baseq=0, downsample_rate=1.0, threads=0,
+                       safe_bases=REGION_SAFE_BASES, device="cuda", verify_crc=True) -> DeviceIngestedReads:
+    """Device twin of :func:`ingest.ingest_regions`: packed batch for intervals ``[starts[i], ends[i]]`` (ascending) of one
+    contig, decoded and cut on the GPU. ``min_baseq`` is accepted for signature parity (it only feeds ``bad_indicies`` in
+    the reference, which the packed batch does not carry)."""
+    import os
+    import time
+    lib, ilib = capi.load(), ingest.load()
+    dev = torch.device(device)
+    if dev.index is not None:
+        torch.cuda.set_device(dev)
+    t0 = time.perf_counter()
+    s = np.ascontiguousarray(starts, np.int64)
+    e = np.ascontiguousarray(ends, np.int64)
+    assert s.shape == e.shape and s.ndim == 1
+    n_spans = int(s.shape[0])
+    span_start = np.maximum(0, s - safe_bases)
+    span_stop = e + safe_bases
+    if n_spans > 1 and (np.any(np.diff(span_start) < 0) or np.any(np.diff(span_stop) < 0)):
+        raise ValueError("ingest_regions_gpu: intervals must ascend")
+    if threads <= 0:
+        threads = min(16, os.cpu_count() or 1)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    # ---- host: which bytes, which blocks, which chain entry points
+    plan = C.c_void_p()
+    ingest._check(ilib.pv_bam_plan(bam._h, contig.encode(), int(span_start.min()) if n_spans else 0, int(span_stop.max()) if n_spans else 0, C.byref(plan)))
+    try:
+        tid = int(ilib.pv_bam_plan_tid(plan))
+        if n_spans and tid < 0:
+            raise RuntimeError("contig %s is not in the BAM header" % contig)
+        comp_bytes = int(ilib.pv_bam_plan_comp_bytes(plan))
+        comp_host = torch.empty(max(comp_bytes, 256), dtype=torch.uint8, pin_memory=True)
+        ingest._check(ilib.pv_bam_plan_load(plan, C.c_void_p(comp_host.data_ptr()), int(threads)))
+        n_blocks, n_seg = int(ilib.pv_bam_plan_n_blocks(plan)), int(ilib.pv_bam_plan_n_segments(plan))
+        u_bytes = int(ilib.pv_bam_plan_inflated_bytes(plan))
+        blocks = np.zeros(max(n_blocks, 1), _BLOCK_DT)
+        seg = np.zeros((2, max(n_seg, 1)), np.int64)
+        ingest._check(ilib.pv_bam_plan_tables(plan, blocks.ctypes.data, seg[0].ctypes.data, seg[1].ctypes.data))
+    finally:
+        ilib.pv_bam_plan_free(plan)
+    t_plan = time.perf_counter()
+    trace = {} if os.environ.get("PV_INGEST_TRACE") else None
+
+    def mark(name, _last=[t_plan]):
+        if trace is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            trace[name] = round((now - _last[0]) * 1e3, 3)
+            _last[0] = now
+
+    # ---- device: inflate, records, clip
+    comp = comp_host.to(dev, non_blocking=True)
+    blocks_d = torch.from_numpy(blocks.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
+    seg_d = torch.from_numpy(seg).to(dev, non_blocking=True)
+    spans_d = torch.from_numpy(np.stack([span_start, span_stop]) if n_spans else np.zeros((2, 1), np.int64)).to(dev, non_blocking=True)
+    U = torch.empty(u_bytes + 64, dtype=torch.uint8, device=dev)
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)       # [0] bad blocks, [1] chain status, [2] clip status, [3] min_qual
+    mark("upload")
+    capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, _ptr(blocks_d), n_blocks, _ptr(U), u_bytes, int(bool(verify_crc)), _ptr(flags[0:1]), st))
+    mark("inflate")
+    seg_first = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    capi.check(lib.pv_bam_index_records(_ptr(U), u_bytes, _ptr(seg_d[0]), _ptr(seg_d[1]), n_seg, _ptr(seg_first), None, 0, _ptr(flags[1:2]), st))
+    n_rec = int(seg_first[n_seg].item())
+    bad = int(flags[0].item())
+    if bad:
+        raise capi.PvError(-1, "BGZF: %d block(s) failed to inflate or their CRC-32 does not match" % bad)
+    _status(flags[1], "record index (count)")
+    rec_off = torch.empty(max(n_rec, 1), dtype=torch.int64, device=dev)
+    capi.check(lib.pv_bam_index_records(_ptr(U), u_bytes, _ptr(seg_d[0]), _ptr(seg_d[1]), n_seg, _ptr(seg_first), _ptr(rec_off), n_rec, _ptr(flags[1:2]), st))
+    mark("record_index")
+    pair_first = torch.zeros(n_rec + 1, dtype=torch.int64, device=dev)
+    clip_args = (_ptr(U), u_bytes, _ptr(rec_off), n_rec, tid, _ptr(spans_d[0]), _ptr(spans_d[1]), n_spans, int(bool(include_supplementary)), int(min_mapq))
+    capi.check(lib.pv_bam_clip_count(*clip_args, _ptr(pair_first), _ptr(flags[2:3]), st))
+    n_pairs = int(pair_first[n_rec].item())
+    _status(flags[1], "record index (fill)")
+    mark("clip_count")
+    ws = torch.empty(int(lib.pv_bam_clip_workspace_bytes(n_pairs)), dtype=torch.uint8, device=dev)
+    pairs = torch.empty((max(n_pairs, 1), 3), dtype=torch.int64, device=dev)
+    base_off = torch.empty(max(n_pairs, 1), dtype=torch.int64, device=dev)
+    cigar_off = torch.empty(max(n_pairs, 1), dtype=torch.int64, device=dev)
+    read_begin = torch.zeros(n_spans + 1, dtype=torch.int64, device=dev)
+    totals = torch.zeros(2, dtype=torch.int64, device=dev)
+    capi.check(lib.pv_bam_clip_layout(*clip_args, _ptr(pair_first), n_pairs, _ptr(ws), ws.numel(), _ptr(pairs), _ptr(base_off), _ptr(cigar_off),
+                                      _ptr(read_begin), _ptr(totals), _ptr(flags[2:3]), st))
+    rb_host = read_begin.cpu().numpy()
+    tot = totals.cpu().numpy()
+    mark("clip_layout")
+    _status(flags[2], "clip")
+    n_reads, n_bases, n_ops = n_pairs, int(tot[0]), int(tot[1])
+    # reservoir down-sampling (AlignmentSummarizer.py:191-208) on read indices, before any read is materialised
+    keep, changed = [], False
+    for r in range(n_spans):
+        idx = ingest.reservoir_indices(int(rb_host[r + 1] - rb_host[r]), downsample_rate)
+        if idx is None:
+            keep.append(np.arange(rb_host[r], rb_host[r + 1], dtype=np.int64))
+        else:
+            keep.append(idx + rb_host[r]); changed = True
+    if changed:
+        k = torch.from_numpy(np.concatenate(keep)).to(dev)
+        pairs = pairs[:n_pairs].index_select(0, k).contiguous()
+        n_reads = int(k.numel())
+        padded = (pairs[:, 2] + 15) & ~15
+        nops = pairs[:, 1] >> 32                                  # PvBamPair: span (low 32 bits) | n_ops (high 32 bits)
+        base_off = (torch.cumsum(padded, 0) - padded).contiguous()
+        cigar_off = (torch.cumsum(nops, 0) - nops).contiguous()
+        n_bases, n_ops = int(padded.sum().item()), int(nops.sum().item())
+        rb_host = np.concatenate([[0], np.cumsum([len(x) for x in keep])]).astype(np.int64)
+        read_begin = torch.from_numpy(rb_host).to(dev)
+        if n_reads == 0:
+            pairs = torch.empty((1, 3), dtype=torch.int64, device=dev)
+
+    def new(n, dt):
+        return torch.empty(max(int(n), 1), dtype=dt, device=dev)
+    t = {"read_pos": new(n_reads, torch.int64), "read_base_off": base_off, "read_len": new(n_reads, torch.int32),
+         "read_cigar_off": cigar_off, "read_n_ops": new(n_reads, torch.int32), "read_flags": new(n_reads, torch.uint8),
+         "read_mapq": new(n_reads, torch.uint8), "bases": torch.empty(n_bases, dtype=torch.uint8, device=dev),
+         "quals": torch.empty(n_bases, dtype=torch.uint8, device=dev), "cigar": torch.empty(n_ops, dtype=torch.int32, device=dev),
+         "region_read_begin": read_begin}
+    pos_end, hp = new(n_reads, torch.int64), new(n_reads, torch.int32)
+    bam_flag = new(n_reads, torch.int16)
+    name_off, name_len = new(n_reads, torch.int64), new(n_reads, torch.int32)
+    capi.check(lib.pv_bam_clip_write(_ptr(U), u_bytes, _ptr(pairs), n_reads, _ptr(spans_d[0]), _ptr(spans_d[1]), _ptr(base_off), _ptr(cigar_off),
+                                     _ptr(t["read_pos"]), _ptr(pos_end), _ptr(t["read_len"]), _ptr(t["read_n_ops"]), _ptr(t["read_flags"]),
+                                     _ptr(t["read_mapq"]), _ptr(hp), _ptr(bam_flag), _ptr(name_off), _ptr(name_len), _ptr(t["bases"]),
+                                     _ptr(t["quals"]), _ptr(t["cigar"]), _ptr(flags[3:4]), _ptr(flags[2:3]), st))
+    mark("clip_write")
+    # ---- reference + region fields (host: FASTA_handler; one fetch for the whole covering span)
+    clen = int(fasta.get_chromosome_sequence_length(contig)) if n_spans else 0
+    if n_spans and clen < 0:
+        raise RuntimeError("CHROMOSOME NAME NOT PRESENT IN REFERENCE FASTA FILE: %s" % contig)
+    regions = {"region_ref_start": span_start.astype(np.int64), "region_ref_end": span_stop.astype(np.int64),
+               "region_cand_start": s.copy(), "region_cand_end": e.copy()}
+    rlen = (span_stop + 1 - span_start).astype(np.int64) if n_spans else np.zeros(0, np.int64)     # region_end + 1 exclusive (:214-216)
+    regions["region_ref_len"] = rlen
+    regions["region_ref_off"] = (np.cumsum(rlen) - rlen).astype(np.int64)
+    ref = np.full(int(rlen.sum()), ord("N"), np.uint8)                                      # 'N' past the contig end
+    if n_spans:
+        lo, hi = int(span_start.min()), int(span_stop.max()) + 1
+        whole = np.frombuffer(fasta.get_reference_sequence(contig, lo, hi).encode(), np.uint8)
+        for r in range(n_spans):
+            a = int(span_start[r]) - lo
+            seg_r = whole[a:a + int(rlen[r])]
+            o = int(regions["region_ref_off"][r])
+            ref[o:o + seg_r.size] = seg_r
+    for name in ("region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end", "region_ref_off", "region_ref_len"):
+        t[name] = torch.from_numpy(np.ascontiguousarray(regions[name])).to(dev) if n_spans else torch.zeros(1, dtype=torch.int64, device=dev)[:0]
+    t["ref"] = torch.from_numpy(ref).to(dev)
+    mq = int(flags[3].item())
+    _status(flags[2], "clip (write)")
+    for name in ("read_pos", "read_base_off", "read_len", "read_cigar_off", "read_n_ops", "read_flags", "read_mapq"):
+        t[name] = t[name][:n_reads]
+    batch = DeviceReadBatch(t, regions, mq if (n_reads and 0 < mq <= 255) else 0, dev, contigs=[contig] * n_spans,
+                            region_contig_len=np.full(n_spans, clen, np.int64), h2d_bytes=comp_bytes + ref.nbytes)
+    assert set(ARRAY_NAMES) <= set(t)
+    mark("reference")
+    t_done = time.perf_counter()
+    stats = {"compressed_bytes": comp_bytes, "inflated_bytes": u_bytes, "bgzf_blocks": n_blocks, "chain_segments": n_seg,
+             "records": n_rec, "reads": n_reads, "host_plan_s": t_plan - t0, "device_s": t_done - t_plan}
+    if trace is not None:
+        stats["trace_ms"] = trace
+    return DeviceIngestedReads(batch, pos_end[:n_reads], hp[:n_reads], bam_flag[:n_reads], U, name_off[:n_reads], name_len[:n_reads], stats)

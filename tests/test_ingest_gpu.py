@@ -1,0 +1,102 @@
+"""BAM decoded on the device (pepper_thesis_b200.ingest_gpu, csrc/ingest_gpu.cu) against the host ingest (which
+tests/test_ingest.py pins to the compiled reference bam_handler.cpp): every array of the packed batch bit-identical, then
+BAM -> candidates through the summary kernels from the device-born batch."""
+import numpy as np
+import pytest
+
+import test_ingest as TI
+from test_ingest import files  # noqa: F401  (fixture)
+from pepper_thesis_b200 import ingest, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ([0, 20000, 40000, 60000, 100000], [20000, 40000, 60000, 80000, TI.CONTIG_LEN - 1], dict(min_mapq=5)),
+    ([0], [TI.CONTIG_LEN - 1], dict()),
+    ([39000], [47000], dict(include_supplementary=True, min_mapq=10)),
+    ([0, 30000, 60000], [30000, 60000, 90000], dict(min_mapq=55)),
+    ([19950, 20050, 20060], [20050, 20060, 29000], dict()),                   # tiny spans: one record feeds three regions
+    ([50000], [50001], dict()),
+    ([10000, 50000], [19999, 59999], dict(downsample_rate=0.5)),
+]
+
+
+def _compare(got, want):
+    gb, wb = got.batch.to_host(), want.batch
+    assert gb.n_reads == wb.n_reads and gb.n_regions == wb.n_regions
+    for name in ("read_pos", "read_base_off", "read_len", "read_cigar_off", "read_n_ops", "read_flags", "read_mapq", "bases", "quals",
+                 "cigar", "region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end", "region_ref_off", "region_ref_len",
+                 "region_read_begin", "ref"):
+        a, b = getattr(gb, name), getattr(wb, name)
+        assert a.shape == b.shape and np.array_equal(a, b), name
+    assert np.array_equal(got.pos_end.cpu().numpy(), want.pos_end)
+    assert np.array_equal(got.hp_tag.cpu().numpy(), want.hp_tag)
+    assert np.array_equal(got.bam_flag.cpu().numpy().view(np.uint16), want.bam_flag)
+    assert got.query_names == want.query_names
+    assert gb.min_qual == wb.min_qual
+    assert np.array_equal(gb.region_contig_len, wb.region_contig_len)
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_gpu_ingest_matches_host_ingest(files, case):
+    from pepper_thesis_b200 import ingest_gpu
+    starts, ends, kw = CASES[case]
+    bam, fa = ingest.BAMHandler(files["bam"]), ingest.FASTAHandler(files["fa"])
+    want = ingest.ingest_regions(bam, fa, "chrS", starts, ends, **kw)
+    got = ingest_gpu.ingest_regions_gpu(bam, fa, "chrS", starts, ends, **kw)
+    _compare(got, want)
+    assert got.stats["records"] >= want.batch.n_reads * (0 if kw.get("downsample_rate") else 1) // 3
+
+
+def test_gpu_ingest_other_contig_and_empty(files):
+    from pepper_thesis_b200 import ingest_gpu
+    bam, fa = ingest.BAMHandler(files["bam"]), ingest.FASTAHandler(files["fa"])
+    got = ingest_gpu.ingest_regions_gpu(bam, fa, "chrT", [0], [4000])
+    want = ingest.ingest_regions(bam, fa, "chrT", [0], [4000])
+    _compare(got, want)
+    assert got.query_names == ["other_contig"]
+
+
+def test_gpu_ingest_refuses_corrupt_blocks(files, tmp_path):
+    """A flipped payload byte must be caught on the device (decoder error or CRC-32 mismatch), not decoded into reads."""
+    from pepper_thesis_b200 import capi, ingest_gpu
+    raw = bytearray(open(files["bam"], "rb").read())
+    raw[len(raw) // 2] ^= 0x40
+    p = str(tmp_path / "bad.bam")
+    open(p, "wb").write(bytes(raw))
+    open(p + ".bai", "wb").write(open(files["bam"] + ".bai", "rb").read())
+    bam, fa = ingest.BAMHandler(p), ingest.FASTAHandler(files["fa"])
+    with pytest.raises((capi.PvError, RuntimeError)):
+        ingest_gpu.ingest_regions_gpu(bam, fa, "chrS", [0], [TI.CONTIG_LEN - 1])
+
+
+def test_bam_to_candidates_from_device_born_batch(files):
+    """BAM + FASTA -> device decode -> summary kernels, equal to the host-ingested batch through the same kernels and to the
+    reference oracle fed by the compiled reference's get_reads."""
+    import torch
+    import helpers as H
+    import pyoracle as O
+    from pepper_thesis_b200 import capi, device as dev, ingest_gpu
+    from pepper_thesis_b200.read_batch import Region, pack_regions
+    bam, fa = ingest.BAMHandler(files["bam"]), ingest.FASTAHandler(files["fa"])
+    starts, ends = [0, 30000, 60000], [30000, 60000, 90000]
+    thr = synth.PROFILES["ont_r9"].thresholds
+    got = ingest_gpu.ingest_regions_gpu(bam, fa, "chrS", starts, ends, min_mapq=55)
+    db = got.batch
+    ws = dev.SummaryWorkspace.for_batch(db, 8192)
+    dev.summary_regions(db, thr, ws)
+    torch.cuda.synchronize()
+    k = int(ws.count.item())
+    assert ws.status() == 0 and k > 50
+    pos, reg, img = ws.position[:k].cpu().numpy(), ws.region[:k].cpu().numpy(), ws.windows[:k].cpu().numpy()
+    host = ingest.ingest_regions(bam, fa, "chrS", starts, ends, min_mapq=55)
+    d = capi.summary_regions_host(host.batch, thr).trimmed()
+    assert np.array_equal(pos, d["position"]) and np.array_equal(reg, d["region"]) and np.array_equal(img, d["images"])
+    for r, (s, e) in enumerate(zip(starts, ends)):
+        rs, re_ = max(0, s - 100), e + 100
+        reads = [H.Read(w["pos"], w["sequence"], w["cigar_tuples"], rev=w["is_reverse"], q=w["base_qualities"], mapq=w["mapping_quality"])
+                 for w in TI._oracle_reads(files, rs, re_, False, 55, 0)]
+        ob = pack_regions([Region("chrS", rs, re_, files["ref"][rs:re_ + 1], s, e, reads)])
+        want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
+        m = reg == r
+        assert np.array_equal(pos[m], want["position"]) and np.array_equal(img[m].astype(np.int32), np.asarray(want["images"]).astype(np.int32))
