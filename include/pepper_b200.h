@@ -397,8 +397,8 @@ typedef struct PvBamPair {   /* one read of the batch: a record cut to one span 
     int32_t n_ops;       /* kept CIGAR ops */
     int64_t n_bases;     /* kept bases */
 } PvBamPair;
-/* One thread per BGZF block; *n_bad_dev = blocks that did not decode to isize bytes (or, with verify_crc, whose CRC-32
- * differs from the trailer). */
+/* One warp per BGZF block (csrc/inflate_warp.cuh); *n_bad_dev = blocks that did not decode to isize bytes (or, with
+ * verify_crc, whose CRC-32 differs from the trailer). comp_dev must be 4-byte aligned. */
 int pv_bam_inflate_blocks(const uint8_t* comp_dev, int64_t comp_bytes, const PvBgzfBlock* blocks_dev, int32_t n_blocks,
                           uint8_t* inflated_dev, int64_t inflated_bytes, int32_t verify_crc, int32_t* n_bad_dev, void* stream);
 /* Record boundaries. Segment s = [seg_begin[s], seg_end[s]) of the inflated stream starts at a record and ends where the
@@ -435,6 +435,12 @@ int pv_bam_clip_write(const uint8_t* inflated_dev, int64_t inflated_bytes, const
 /* NUL-terminated query names, read i at out_off_dev[i] (the caller's exclusive scan of name_len + 1) */
 int pv_bam_gather_names(const uint8_t* inflated_dev, const int64_t* name_off_dev, const int32_t* name_len_dev,
                         const int64_t* out_off_dev, int64_t n, uint8_t* out_dev, void* stream);
+/* PvReadBatch.ref from ONE fetch of the contig: region r receives bytes [span_start[r], span_start[r] + region_ref_len[r])
+ * of the contig at ref_dev + region_ref_off[r], taken from fetched_dev = contig[fetch_start, fetch_start + fetch_len)
+ * ('N' outside it: FASTA_handler clamps at the contig end, the region's reference span can reach one base past it). */
+int pv_bam_gather_reference(const uint8_t* fetched_dev, int64_t fetch_len, int64_t fetch_start, const int64_t* span_start_dev,
+                            const int64_t* region_ref_off_dev, const int64_t* region_ref_len_dev, int32_t n_spans,
+                            int64_t max_ref_len, uint8_t* ref_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_profile_enable"
            "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks", "pv_candidate_filter",
            "pv_candidate_filter_host", "pv_polish_workspace_bytes", "pv_polish_count", "pv_polish_emit", "pv_polish_chunks",
            "pv_bam_inflate_blocks", "pv_bam_index_records", "pv_bam_clip_count", "pv_bam_clip_workspace_bytes", "pv_bam_clip_layout",
-           "pv_bam_clip_write", "pv_bam_gather_names"]
+           "pv_bam_clip_write", "pv_bam_gather_names", "pv_bam_gather_reference"]
 
 
 class PvError(RuntimeError):
@@ -154,6 +154,7 @@ def load() -> C.CDLL:
         lib.pv_bam_clip_layout.argtypes = [P, I64, P, I64, I32, P, P, I32, I32, I32, P, I64, P, I64, P, P, P, P, P, P, P]
         lib.pv_bam_clip_write.argtypes = [P, I64, P, I64, P, P, P, P] + [P] * 13 + [P, P, P]
         lib.pv_bam_gather_names.argtypes = [P, P, P, P, I64, P, P]
+        lib.pv_bam_gather_reference.argtypes = [P, I64, I64, P, P, P, I32, I64, P, P]
         _lib = lib
     return _lib
 

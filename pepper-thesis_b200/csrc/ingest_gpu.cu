@@ -2,8 +2,8 @@
 // bytes the BAI query names and walks the BGZF block headers (libpv_ingest.so: pv_bam_plan*); everything per byte happens
 // here, and the packed read batch is born in HBM, where the summary kernels take it from:
 //
-//   inflate_kernel        one thread per BGZF block (independent <= 64 KiB DEFLATE streams): bam_core.cuh's decoder, then
-//   crc_kernel            the block's CRC-32 against its trailer
+//   inflate_kernel        one WARP per BGZF block (independent <= 64 KiB DEFLATE streams, inflate_warp.cuh): tables in shared
+//                         memory built by the warp, matches copied by all lanes, the block's CRC-32 against its trailer
 //   chain_kernel          record boundaries: one thread per chain segment (chunk starts + the linear index's record
 //                         offsets every 16 kbp), a pointer chase over block_size fields; count pass, scan, fill pass
 //   clip_count / _pairs   one thread per record: flag / mapq filters (bam_handler.cpp:137-150), bam_endpos, the spans
@@ -16,39 +16,39 @@
 // Results are bit-identical to the host ingest (pv_ingest_regions), which tests pin to the compiled reference.
 #include "common.cuh"
 #include "bam_core.cuh"
+#include "inflate_warp.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
 using namespace bamcore;
 
-constexpr int INFLATE_THREADS = 64;
+constexpr int INFLATE_WARPS = 4;
 
-__global__ void __launch_bounds__(INFLATE_THREADS) inflate_kernel(const uint8_t* __restrict__ comp, int64_t comp_bytes,
-                                                                  const PvBgzfBlock* __restrict__ blocks, int n_blocks,
-                                                                  uint8_t* __restrict__ out, int64_t out_bytes, int32_t* n_bad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    const PvBgzfBlock b = blocks[i];
-    bool ok = b.c_off >= 0 && b.c_len >= 0 && b.c_off + b.c_len <= comp_bytes && b.isize >= 0 && b.u_off >= 0 && b.u_off + b.isize <= out_bytes;
-    if (ok && b.isize > 0) {
-        InflateState S;
-        ok = inflate_block(comp + b.c_off, b.c_len, out + b.u_off, b.isize, S);
-    }
-    if (!ok) atomicAdd(n_bad, 1);
-}
-
-__global__ void crc_kernel(const PvBgzfBlock* __restrict__ blocks, int n_blocks, const uint8_t* __restrict__ data, int32_t* n_bad) {
-    __shared__ uint32_t table[256];
-    if (threadIdx.x < 256) {
-        uint32_t c = threadIdx.x;
-        for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
-        table[threadIdx.x] = c;
+// one warp per BGZF block (inflate_warp.cuh); with `verify` the block's CRC-32 is checked against its trailer
+__global__ void __launch_bounds__(INFLATE_WARPS * 32) inflate_kernel(const uint8_t* __restrict__ comp, int64_t comp_bytes,
+                                                                     const PvBgzfBlock* __restrict__ blocks, int n_blocks,
+                                                                     uint8_t* __restrict__ out, int64_t out_bytes, int verify, int32_t* n_bad) {
+    __shared__ winf::WarpTables T[INFLATE_WARPS];
+    __shared__ uint32_t crc_tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? winf::CRC_POLY ^ (c >> 1) : c >> 1;
+        crc_tab[i] = c;
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * INFLATE_WARPS + warp;
     if (i >= n_blocks) return;
     const PvBgzfBlock b = blocks[i];
-    if (crc32_bytes(table, data + b.u_off, b.isize) != b.crc) atomicAdd(n_bad, 1);
+    bool ok = b.c_off >= 0 && b.c_len >= 0 && b.c_off + b.c_len <= comp_bytes && b.isize >= 0 && b.isize <= 65536 && b.u_off >= 0 &&
+              b.u_off + b.isize <= out_bytes;
+    if (ok && b.isize > 0) {
+        ok = winf::inflate_warp(comp, comp_bytes, b.c_off, b.c_len, out + b.u_off, b.isize, T[warp], lane);
+        if (ok && verify) ok = winf::crc32_warp(out + b.u_off, b.isize, crc_tab, lane) == b.crc;
+    } else if (ok && verify) {
+        ok = b.crc == 0;
+    }
+    if (!ok && lane == 0) atomicAdd(n_bad, 1);
 }
 
 // record chain of one segment; FILL: offsets go to rec_off[first[s] ...]
@@ -219,6 +219,19 @@ __global__ void names_kernel(const uint8_t* __restrict__ U, const int64_t* __res
     out[o + l] = 0;
 }
 
+// region r's reference bytes [span_start[r], span_start[r] + ref_len[r]) out of ONE fetch [fetch_start, fetch_start + fetch_len) of the contig;
+// 'N' behind the fetch (past the contig end, AlignmentSummarizer's region_end + 1 can reach there)
+__global__ void gather_reference_kernel(const uint8_t* __restrict__ fetched, int64_t fetch_len, int64_t fetch_start,
+                                        const int64_t* __restrict__ span_start, const int64_t* __restrict__ ref_off,
+                                        const int64_t* __restrict__ ref_len, uint8_t* __restrict__ ref) {
+    const int r = blockIdx.y;
+    const int64_t len = ref_len[r], src = span_start[r] - fetch_start, o = ref_off[r];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = src + i;
+        ref[o + i] = (k >= 0 && k < fetch_len) ? fetched[k] : (uint8_t)'N';
+    }
+}
+
 inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 struct ClipWs { unsigned long long* keys_in; unsigned long long* keys_out; uint32_t* vals_in; uint32_t* vals_out; PvBamPair* pairs_in;
@@ -242,14 +255,14 @@ extern "C" int pv_bam_inflate_blocks(const uint8_t* comp_dev, int64_t comp_bytes
                                      uint8_t* inflated_dev, int64_t inflated_bytes, int32_t verify_crc, int32_t* n_bad_dev, void* stream) {
     if (n_blocks < 0 || !n_bad_dev || (n_blocks > 0 && (!comp_dev || !blocks_dev || !inflated_dev)))
         return pv::set_error(PV_EINVAL, "pv_bam_inflate_blocks: bad arguments");
+    if ((uintptr_t)comp_dev & 3) return pv::set_error(PV_EINVAL, "pv_bam_inflate_blocks: the compressed buffer must be 4-byte aligned");
     if (int rc = pv::require_device()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     PV_CUDA_CHECK(cudaMemsetAsync(n_bad_dev, 0, 4, st));
     if (n_blocks == 0) return PV_OK;
     pv::prof_begin(pv::FAM_INGEST, st);
-    inflate_kernel<<<grid_for(n_blocks, INFLATE_THREADS), INFLATE_THREADS, 0, st>>>(comp_dev, comp_bytes, blocks_dev, n_blocks, inflated_dev, inflated_bytes, n_bad_dev);
-    if (verify_crc) crc_kernel<<<grid_for(n_blocks, 256), 256, 0, st>>>(blocks_dev, n_blocks, inflated_dev, n_bad_dev);
-    pv::prof_end(pv::FAM_INGEST, st, verify_crc ? 2 : 1);
+    inflate_kernel<<<grid_for(n_blocks, INFLATE_WARPS), INFLATE_WARPS * 32, 0, st>>>(comp_dev, comp_bytes, blocks_dev, n_blocks, inflated_dev, inflated_bytes, verify_crc, n_bad_dev);
+    pv::prof_end(pv::FAM_INGEST, st, 1);
     PV_CUDA_CHECK(cudaGetLastError());
     return PV_OK;
 }
@@ -379,6 +392,26 @@ extern "C" int pv_bam_gather_names(const uint8_t* inflated_dev, const int64_t* n
     cudaStream_t st = (cudaStream_t)stream;
     pv::prof_begin(pv::FAM_INGEST, st);
     names_kernel<<<grid_for(n, 128), 128, 0, st>>>(inflated_dev, name_off_dev, name_len_dev, out_off_dev, n, out_dev);
+    pv::prof_end(pv::FAM_INGEST, st, 1);
+    PV_CUDA_CHECK(cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_bam_gather_reference(const uint8_t* fetched_dev, int64_t fetch_len, int64_t fetch_start, const int64_t* span_start_dev,
+                                       const int64_t* region_ref_off_dev, const int64_t* region_ref_len_dev, int32_t n_spans,
+                                       int64_t max_ref_len, uint8_t* ref_dev, void* stream) {
+    if (n_spans < 0 || fetch_len < 0 || max_ref_len < 0 ||
+        (n_spans > 0 && max_ref_len > 0 && (!span_start_dev || !region_ref_off_dev || !region_ref_len_dev || !ref_dev || (fetch_len > 0 && !fetched_dev))))
+        return pv::set_error(PV_EINVAL, "pv_bam_gather_reference: bad arguments");
+    if (n_spans > 65535) return pv::set_error(PV_EINVAL, "pv_bam_gather_reference: at most 65535 regions per call");
+    if (int rc = pv::require_device()) return rc;
+    if (n_spans == 0 || max_ref_len == 0) return PV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    pv::prof_begin(pv::FAM_INGEST, st);
+    unsigned gx = grid_for(max_ref_len, 256 * 8);
+    if (gx > 1024) gx = 1024;
+    gather_reference_kernel<<<dim3(gx, (unsigned)n_spans), 256, 0, st>>>(fetched_dev, fetch_len, fetch_start, span_start_dev, region_ref_off_dev,
+                                                                         region_ref_len_dev, ref_dev);
     pv::prof_end(pv::FAM_INGEST, st, 1);
     PV_CUDA_CHECK(cudaGetLastError());
     return PV_OK;

@@ -127,7 +127,30 @@ def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, conti
     flags = torch.zeros(4, dtype=torch.int32, device=dev)       # [0] bad blocks, [1] chain status, [2] clip status, [3] min_qual
     mark("upload")
     capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, _ptr(blocks_d), n_blocks, _ptr(U), u_bytes, int(bool(verify_crc)), _ptr(flags[0:1]), st))
-    mark("inflate")
+    # ---- reference + region fields while the blocks inflate: ONE fetch of the covering span by FASTA_handler's C side into
+    # page-locked memory, cut into the per-region pieces on the device
+    clen = int(fasta.get_chromosome_sequence_length(contig)) if n_spans else 0
+    if n_spans and clen < 0:
+        raise RuntimeError("CHROMOSOME NAME NOT PRESENT IN REFERENCE FASTA FILE: %s" % contig)
+    regions = {"region_ref_start": span_start.astype(np.int64), "region_ref_end": span_stop.astype(np.int64),
+               "region_cand_start": s.copy(), "region_cand_end": e.copy()}
+    rlen = (span_stop + 1 - span_start).astype(np.int64) if n_spans else np.zeros(0, np.int64)     # region_end + 1 exclusive (:214-216)
+    regions["region_ref_len"] = rlen
+    regions["region_ref_off"] = (np.cumsum(rlen) - rlen).astype(np.int64)
+    ref_bytes = int(rlen.sum())
+    ref_t = {}
+    for name in ("region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end", "region_ref_off", "region_ref_len"):
+        ref_t[name] = torch.from_numpy(np.ascontiguousarray(regions[name])).to(dev, non_blocking=True) if n_spans else torch.zeros(1, dtype=torch.int64, device=dev)[:0]
+    ref_t["ref"] = torch.empty(ref_bytes, dtype=torch.uint8, device=dev)
+    if n_spans:
+        lo, hi = int(span_start.min()), int(span_stop.max()) + 1
+        fetched_host = torch.empty(max(hi - lo, 1), dtype=torch.uint8, pin_memory=True)
+        got_len = C.c_int64(0)
+        ingest._check(ilib.pv_fasta_fetch(fasta._h, contig.encode(), lo, hi, C.c_void_p(fetched_host.data_ptr()), C.byref(got_len)))
+        fetched = fetched_host.to(dev, non_blocking=True)
+        capi.check(lib.pv_bam_gather_reference(_ptr(fetched), int(got_len.value), lo, _ptr(spans_d[0]), _ptr(ref_t["region_ref_off"]),
+                                               _ptr(ref_t["region_ref_len"]), n_spans, int(rlen.max()), _ptr(ref_t["ref"]), st))
+    mark("inflate+reference")
     seg_first = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
     capi.check(lib.pv_bam_index_records(_ptr(U), u_bytes, _ptr(seg_d[0]), _ptr(seg_d[1]), n_seg, _ptr(seg_first), None, 0, _ptr(flags[1:2]), st))
     n_rec = int(seg_first[n_seg].item())
@@ -194,35 +217,16 @@ def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, conti
                                      _ptr(t["read_mapq"]), _ptr(hp), _ptr(bam_flag), _ptr(name_off), _ptr(name_len), _ptr(t["bases"]),
                                      _ptr(t["quals"]), _ptr(t["cigar"]), _ptr(flags[3:4]), _ptr(flags[2:3]), st))
     mark("clip_write")
-    # ---- reference + region fields (host: FASTA_handler; one fetch for the whole covering span)
-    clen = int(fasta.get_chromosome_sequence_length(contig)) if n_spans else 0
-    if n_spans and clen < 0:
-        raise RuntimeError("CHROMOSOME NAME NOT PRESENT IN REFERENCE FASTA FILE: %s" % contig)
-    regions = {"region_ref_start": span_start.astype(np.int64), "region_ref_end": span_stop.astype(np.int64),
-               "region_cand_start": s.copy(), "region_cand_end": e.copy()}
-    rlen = (span_stop + 1 - span_start).astype(np.int64) if n_spans else np.zeros(0, np.int64)     # region_end + 1 exclusive (:214-216)
-    regions["region_ref_len"] = rlen
-    regions["region_ref_off"] = (np.cumsum(rlen) - rlen).astype(np.int64)
-    ref = np.full(int(rlen.sum()), ord("N"), np.uint8)                                      # 'N' past the contig end
-    if n_spans:
-        lo, hi = int(span_start.min()), int(span_stop.max()) + 1
-        whole = np.frombuffer(fasta.get_reference_sequence(contig, lo, hi).encode(), np.uint8)
-        for r in range(n_spans):
-            a = int(span_start[r]) - lo
-            seg_r = whole[a:a + int(rlen[r])]
-            o = int(regions["region_ref_off"][r])
-            ref[o:o + seg_r.size] = seg_r
     for name in ("region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end", "region_ref_off", "region_ref_len"):
-        t[name] = torch.from_numpy(np.ascontiguousarray(regions[name])).to(dev) if n_spans else torch.zeros(1, dtype=torch.int64, device=dev)[:0]
-    t["ref"] = torch.from_numpy(ref).to(dev)
+        t[name] = ref_t[name]
+    t["ref"] = ref_t["ref"]
     mq = int(flags[3].item())
     _status(flags[2], "clip (write)")
     for name in ("read_pos", "read_base_off", "read_len", "read_cigar_off", "read_n_ops", "read_flags", "read_mapq"):
         t[name] = t[name][:n_reads]
     batch = DeviceReadBatch(t, regions, mq if (n_reads and 0 < mq <= 255) else 0, dev, contigs=[contig] * n_spans,
-                            region_contig_len=np.full(n_spans, clen, np.int64), h2d_bytes=comp_bytes + ref.nbytes)
+                            region_contig_len=np.full(n_spans, clen, np.int64), h2d_bytes=comp_bytes + (hi - lo if n_spans else 0))
     assert set(ARRAY_NAMES) <= set(t)
-    mark("reference")
     t_done = time.perf_counter()
     stats = {"compressed_bytes": comp_bytes, "inflated_bytes": u_bytes, "bgzf_blocks": n_blocks, "chain_segments": n_seg,
              "records": n_rec, "reads": n_reads, "host_plan_s": t_plan - t0, "device_s": t_done - t_plan}
