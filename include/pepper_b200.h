@@ -397,8 +397,10 @@ typedef struct PvBamPair {   /* one read of the batch: a record cut to one span 
     int32_t n_ops;       /* kept CIGAR ops */
     int64_t n_bases;     /* kept bases */
 } PvBamPair;
-/* One warp per BGZF block (csrc/inflate_warp.cuh); *n_bad_dev = blocks that did not decode to isize bytes (or, with
- * verify_crc, whose CRC-32 differs from the trailer). comp_dev must be 4-byte aligned. */
+/* One warp per BGZF block (csrc/inflate_warp.cuh), blocks pulled from a ticket by a grid that fills the device once.
+ * n_bad_dev[2]: [0] = blocks that did not decode to isize bytes (or, with verify_crc, whose CRC-32 differs from the
+ * trailer), [1] = scratch (the ticket). comp_dev must be 4-byte aligned; it is read in whole 32-bit words, so the
+ * allocation must cover comp_bytes rounded up to a multiple of 4. */
 int pv_bam_inflate_blocks(const uint8_t* comp_dev, int64_t comp_bytes, const PvBgzfBlock* blocks_dev, int32_t n_blocks,
                           uint8_t* inflated_dev, int64_t inflated_bytes, int32_t verify_crc, int32_t* n_bad_dev, void* stream);
 /* Record boundaries. Segment s = [seg_begin[s], seg_end[s]) of the inflated stream starts at a record and ends where the

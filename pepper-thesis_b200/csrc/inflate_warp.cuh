@@ -17,7 +17,10 @@
 
 namespace winf {
 
-constexpr int LIT_ROOT = 10, DIST_ROOT = 8, CL_ROOT = 7;
+#ifndef PV_LIT_ROOT
+#define PV_LIT_ROOT 10
+#endif
+constexpr int LIT_ROOT = PV_LIT_ROOT, DIST_ROOT = 8, CL_ROOT = 7;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t CRC_POLY = 0xedb88320u;
 

@@ -23,6 +23,7 @@
 #include <set>
 #include <string>
 #include <thread>
+#include <memory>
 #include <vector>
 
 namespace {
@@ -676,14 +677,67 @@ extern "C" int pv_fasta_fetch(const PvFastaFile* f, const char* name, int64_t st
     if (!out) return fail(PV_EINVAL, "null output");
     const int64_t first = s->offset + (start / s->linebases) * s->linewidth + start % s->linebases;
     const int64_t last = s->offset + ((stop - 1) / s->linebases) * s->linewidth + (stop - 1) % s->linebases;
-    std::vector<uint8_t> raw((size_t)(last - first + 1));
-    if (pread(f->fd, raw.data(), raw.size(), first) != (ssize_t)raw.size())
-        return fail(PV_EINVAL, "ENCOUNTERED ERROR IN FETCHING REFERENCE FASTA FILE: %s %lld %lld", name, (long long)start, (long long)stop);
+    const size_t raw_n = (size_t)(last - first + 1);
+    const int64_t want = stop - start;
     int64_t n = 0;
-    for (uint8_t ch : raw) {
-        if (ch == '\n' || ch == '\r') continue;
-        out[n++] = (char)((ch >= 'a' && ch <= 'z') ? ch - 32 : ch);   // fasta_handler.cpp:49
-        if (n == stop - start) break;
+    auto read_all = [&](uint8_t* dst, size_t bytes, int64_t at) -> bool {
+        for (size_t got = 0; got < bytes;) {
+            const ssize_t k = pread(f->fd, dst + got, bytes - got, at + (int64_t)got);
+            if (k <= 0) return false;
+            got += (size_t)k;
+        }
+        return true;
+    };
+    // line by line (the .fai promises linebases bases + a terminator of linewidth - linebases bytes per line), through a
+    // buffer of whole lines that stays in cache: memcpy per line, then ONE long loop over the result for the upper-casing.
+    // A terminator that is not made of line breaks, or a line break inside a line, sends the fetch down the generic loop.
+    bool regular = s->linebases > 0 && s->linewidth > s->linebases;
+    if (regular) {
+        const int64_t term = s->linewidth - s->linebases;
+        const int64_t lines = std::max<int64_t>(1, (1 << 20) / s->linewidth);
+        std::unique_ptr<uint8_t[]> buf(new uint8_t[(size_t)(lines * s->linewidth)]);
+        int64_t col = start % s->linebases, fpos = first;
+        while (regular && n < want) {
+            const int64_t bytes = std::min<int64_t>((s->linebases - col) + term + (lines - 1) * s->linewidth, last + 1 - fpos);
+            if (!read_all(buf.get(), (size_t)bytes, fpos))
+                return fail(PV_EINVAL, "ENCOUNTERED ERROR IN FETCHING REFERENCE FASTA FILE: %s %lld %lld", name, (long long)start, (long long)stop);
+            int64_t j = 0;
+            while (n < want && j < bytes) {
+                const int64_t take = std::min<int64_t>(s->linebases - col, want - n);
+                if (j + take > bytes) { regular = false; break; }
+                memcpy(out + n, buf.get() + j, (size_t)take);
+                n += take; j += take; col = 0;
+                if (n < want) {
+                    if (j + term > bytes) { regular = false; break; }
+                    for (int64_t t = 0; t < term; t++, j++)
+                        if (buf[(size_t)j] != '\n' && buf[(size_t)j] != '\r') regular = false;
+                    if (!regular) break;
+                }
+            }
+            fpos += bytes;
+        }
+        if (regular) {
+            int any = 0;
+            uint8_t* o = (uint8_t*)out;
+            for (int64_t i = 0; i < n; i++) {                     // upper-casing (fasta_handler.cpp:49) and the line-break check
+                const uint8_t ch = o[i];
+                any |= (ch == '\n') | (ch == '\r');
+                o[i] = (uint8_t)(ch - (((ch >= 'a') & (ch <= 'z')) << 5));
+            }
+            regular = !any;
+        }
+    }
+    if (!regular) {
+        std::unique_ptr<uint8_t[]> raw(new uint8_t[raw_n]);
+        if (!read_all(raw.get(), raw_n, first))
+            return fail(PV_EINVAL, "ENCOUNTERED ERROR IN FETCHING REFERENCE FASTA FILE: %s %lld %lld", name, (long long)start, (long long)stop);
+        n = 0;
+        for (size_t j = 0; j < raw_n; j++) {
+            const uint8_t ch = raw[j];
+            if (ch == '\n' || ch == '\r') continue;
+            out[n++] = (char)((ch >= 'a' && ch <= 'z') ? ch - 32 : ch);   // fasta_handler.cpp:49
+            if (n == want) break;
+        }
     }
     *out_len = n;
     return PV_OK;

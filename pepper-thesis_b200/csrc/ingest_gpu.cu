@@ -22,12 +22,12 @@
 namespace {
 using namespace bamcore;
 
-constexpr int INFLATE_WARPS = 4;
+constexpr int INFLATE_WARPS = winf::LIT_ROOT >= 12 ? 2 : 4;     // static shared memory: <= 48 KB per CTA
 
 // one warp per BGZF block (inflate_warp.cuh); with `verify` the block's CRC-32 is checked against its trailer
 __global__ void __launch_bounds__(INFLATE_WARPS * 32) inflate_kernel(const uint8_t* __restrict__ comp, int64_t comp_bytes,
                                                                      const PvBgzfBlock* __restrict__ blocks, int n_blocks,
-                                                                     uint8_t* __restrict__ out, int64_t out_bytes, int verify, int32_t* n_bad) {
+                                                                     uint8_t* __restrict__ out, int64_t out_bytes, int verify, int32_t* n_bad, int32_t* ticket) {
     __shared__ winf::WarpTables T[INFLATE_WARPS];
     __shared__ uint32_t crc_tab[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -36,19 +36,25 @@ __global__ void __launch_bounds__(INFLATE_WARPS * 32) inflate_kernel(const uint8
         crc_tab[i] = c;
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * INFLATE_WARPS + warp;
-    if (i >= n_blocks) return;
-    const PvBgzfBlock b = blocks[i];
-    bool ok = b.c_off >= 0 && b.c_len >= 0 && b.c_off + b.c_len <= comp_bytes && b.isize >= 0 && b.isize <= 65536 && b.u_off >= 0 &&
-              b.u_off + b.isize <= out_bytes;
-    if (ok && b.isize > 0) {
-        ok = winf::inflate_warp(comp, comp_bytes, b.c_off, b.c_len, out + b.u_off, b.isize, T[warp], lane);
-        if (ok && verify) ok = winf::crc32_warp(out + b.u_off, b.isize, crc_tab, lane) == b.crc;
-    } else if (ok && verify) {
-        ok = b.crc == 0;
+    const int lane = threadIdx.x & 31;
+    winf::WarpTables& Tw = T[threadIdx.x >> 5];
+    for (;;) {                                                    // blocks are pulled from a ticket: no wave of warps waits for its slowest
+        int i = 0;
+        if (lane == 0) i = atomicAdd(ticket, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_blocks) break;
+        const PvBgzfBlock b = blocks[i];
+        bool ok = b.c_off >= 0 && b.c_len >= 0 && b.c_off + b.c_len <= comp_bytes && b.isize >= 0 && b.isize <= 65536 && b.u_off >= 0 &&
+                  b.u_off + b.isize <= out_bytes;
+        if (ok && b.isize > 0) {
+            ok = winf::inflate_warp(comp, comp_bytes, b.c_off, b.c_len, out + b.u_off, b.isize, Tw, lane);
+            if (ok && verify) ok = winf::crc32_warp(out + b.u_off, b.isize, crc_tab, lane) == b.crc;
+        } else if (ok && verify) {
+            ok = b.crc == 0;
+        }
+        if (!ok && lane == 0) atomicAdd(n_bad, 1);
+        __syncwarp();
     }
-    if (!ok && lane == 0) atomicAdd(n_bad, 1);
 }
 
 // record chain of one segment; FILL: offsets go to rec_off[first[s] ...]
@@ -258,10 +264,20 @@ extern "C" int pv_bam_inflate_blocks(const uint8_t* comp_dev, int64_t comp_bytes
     if ((uintptr_t)comp_dev & 3) return pv::set_error(PV_EINVAL, "pv_bam_inflate_blocks: the compressed buffer must be 4-byte aligned");
     if (int rc = pv::require_device()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    PV_CUDA_CHECK(cudaMemsetAsync(n_bad_dev, 0, 4, st));
+    PV_CUDA_CHECK(cudaMemsetAsync(n_bad_dev, 0, 8, st));
     if (n_blocks == 0) return PV_OK;
+    static int resident = 0;                                      // CTAs the device holds at a time
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        PV_CUDA_CHECK(cudaGetDevice(&dev));
+        PV_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_kernel, INFLATE_WARPS * 32, 0));
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    unsigned grid = grid_for(n_blocks, INFLATE_WARPS);
+    if (grid > (unsigned)resident) grid = (unsigned)resident;
     pv::prof_begin(pv::FAM_INGEST, st);
-    inflate_kernel<<<grid_for(n_blocks, INFLATE_WARPS), INFLATE_WARPS * 32, 0, st>>>(comp_dev, comp_bytes, blocks_dev, n_blocks, inflated_dev, inflated_bytes, verify_crc, n_bad_dev);
+    inflate_kernel<<<grid, INFLATE_WARPS * 32, 0, st>>>(comp_dev, comp_bytes, blocks_dev, n_blocks, inflated_dev, inflated_bytes, verify_crc, n_bad_dev, n_bad_dev + 1);
     pv::prof_end(pv::FAM_INGEST, st, 1);
     PV_CUDA_CHECK(cudaGetLastError());
     return PV_OK;

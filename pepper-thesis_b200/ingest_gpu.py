@@ -66,49 +66,134 @@ def _status(t, what):
         raise capi.PvError(-1, "%s: device status %d (1 record chain broken, 2 capacity, 4 malformed record, 8/16 internal)" % (what, v))
 
 
-def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, contig: str, starts: Sequence[int], ends: Sequence[int],
-                       include_supplementary=False, min_mapq=0, min_baseq=0, downsample_rate=1.0, threads=0,
-                       safe_bases=REGION_SAFE_BASES, device="cuda", verify_crc=True) -> DeviceIngestedReads:
-    """Device twin of :func:`ingest.ingest_regions`: packed batch for intervals ``[starts[i], ends[i]]`` (ascending) of one
-    contig, decoded and cut on the GPU. ``min_baseq`` is accepted for signature parity (it only feeds ``bad_indicies`` in
-    the reference, which the packed batch does not carry)."""
+class _PinnedPool:
+    """Page-locked staging buffers, reused across calls (cudaHostAlloc of a GB costs more than decoding it). A buffer goes
+    back with the event behind its last upload and is handed out again only after that event."""
+
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._free = []
+
+    def take(self, nbytes):
+        nbytes = max(int(nbytes), 256)
+        with self._lock:
+            best = None
+            for i, (buf, ev) in enumerate(self._free):
+                if buf.numel() >= nbytes and (best is None or buf.numel() < self._free[best][0].numel()):
+                    best = i
+            got = self._free.pop(best) if best is not None else None
+        if got is None:
+            return torch.empty(nbytes + nbytes // 8, dtype=torch.uint8, pin_memory=True)
+        if got[1] is not None:
+            got[1].synchronize()
+        return got[0]
+
+    def give(self, buf, event):
+        with self._lock:
+            self._free.append((buf, event))
+            if len(self._free) > 6:                               # keep the largest few
+                self._free.sort(key=lambda x: -x[0].numel())
+                del self._free[6:]
+
+
+_PINNED = _PinnedPool()
+
+
+class _HostStage:
+    """What the host prepares for one group of intervals: compressed bytes + block / segment tables + the reference fetch,
+    all in page-locked memory. Built by :func:`_host_stage` (no CUDA call besides the pinned allocations), consumed by
+    :func:`_device_stage`."""
+    __slots__ = ("contig", "s", "e", "span_start", "span_stop", "n_spans", "tid", "comp_bytes", "comp_host", "blocks", "seg", "n_blocks",
+                 "n_seg", "u_bytes", "clen", "regions", "rlen", "fetched_host", "fetched_len", "lo", "hi", "seconds", "opts")
+
+
+def _host_stage(bam, fasta, contig, starts, ends, include_supplementary, min_mapq, downsample_rate, threads, safe_bases) -> _HostStage:
     import os
     import time
-    lib, ilib = capi.load(), ingest.load()
-    dev = torch.device(device)
-    if dev.index is not None:
-        torch.cuda.set_device(dev)
+    ilib = ingest.load()
     t0 = time.perf_counter()
-    s = np.ascontiguousarray(starts, np.int64)
-    e = np.ascontiguousarray(ends, np.int64)
-    assert s.shape == e.shape and s.ndim == 1
-    n_spans = int(s.shape[0])
-    span_start = np.maximum(0, s - safe_bases)
-    span_stop = e + safe_bases
-    if n_spans > 1 and (np.any(np.diff(span_start) < 0) or np.any(np.diff(span_stop) < 0)):
+    h = _HostStage()
+    h.contig = contig
+    h.s = np.ascontiguousarray(starts, np.int64)
+    h.e = np.ascontiguousarray(ends, np.int64)
+    assert h.s.shape == h.e.shape and h.s.ndim == 1
+    h.n_spans = n_spans = int(h.s.shape[0])
+    h.span_start = np.maximum(0, h.s - safe_bases)
+    h.span_stop = h.e + safe_bases
+    if n_spans > 1 and (np.any(np.diff(h.span_start) < 0) or np.any(np.diff(h.span_stop) < 0)):
         raise ValueError("ingest_regions_gpu: intervals must ascend")
     if threads <= 0:
         threads = min(16, os.cpu_count() or 1)
-    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    h.opts = (int(bool(include_supplementary)), int(min_mapq), float(downsample_rate))
+    # ---- reference + region fields: ONE fetch of the covering span by FASTA_handler's C side (cut per region on the device),
+    # on a thread of its own beside the BAM reads (both release the GIL)
+    h.clen = int(fasta.get_chromosome_sequence_length(contig)) if n_spans else 0
+    if n_spans and h.clen < 0:
+        raise RuntimeError("CHROMOSOME NAME NOT PRESENT IN REFERENCE FASTA FILE: %s" % contig)
+    h.regions = {"region_ref_start": h.span_start.astype(np.int64), "region_ref_end": h.span_stop.astype(np.int64),
+                 "region_cand_start": h.s.copy(), "region_cand_end": h.e.copy()}
+    h.rlen = (h.span_stop + 1 - h.span_start).astype(np.int64) if n_spans else np.zeros(0, np.int64)     # region_end + 1 exclusive (:214-216)
+    h.regions["region_ref_len"] = h.rlen
+    h.regions["region_ref_off"] = (np.cumsum(h.rlen) - h.rlen).astype(np.int64)
+    h.lo = h.hi = 0
+    h.fetched_host, h.fetched_len = None, 0
+    fetch_thread, fetch_err = None, []
+    if n_spans:
+        import threading
+        h.lo, h.hi = int(h.span_start.min()), int(h.span_stop.max()) + 1
+        h.fetched_host = _PINNED.take(h.hi - h.lo)
 
-    # ---- host: which bytes, which blocks, which chain entry points
+        def fetch():
+            try:
+                got_len = C.c_int64(0)
+                ingest._check(ilib.pv_fasta_fetch(fasta._h, contig.encode(), h.lo, h.hi, C.c_void_p(h.fetched_host.data_ptr()), C.byref(got_len)))
+                h.fetched_len = int(got_len.value)
+            except Exception as ex:                               # re-raised on the caller's thread
+                fetch_err.append(ex)
+        fetch_thread = threading.Thread(target=fetch)
+        fetch_thread.start()
+    # ---- which bytes, which blocks, which chain entry points
     plan = C.c_void_p()
-    ingest._check(ilib.pv_bam_plan(bam._h, contig.encode(), int(span_start.min()) if n_spans else 0, int(span_stop.max()) if n_spans else 0, C.byref(plan)))
     try:
-        tid = int(ilib.pv_bam_plan_tid(plan))
-        if n_spans and tid < 0:
+        ingest._check(ilib.pv_bam_plan(bam._h, contig.encode(), int(h.span_start.min()) if n_spans else 0, int(h.span_stop.max()) if n_spans else 0, C.byref(plan)))
+        h.tid = int(ilib.pv_bam_plan_tid(plan))
+        if n_spans and h.tid < 0:
             raise RuntimeError("contig %s is not in the BAM header" % contig)
-        comp_bytes = int(ilib.pv_bam_plan_comp_bytes(plan))
-        comp_host = torch.empty(max(comp_bytes, 256), dtype=torch.uint8, pin_memory=True)
-        ingest._check(ilib.pv_bam_plan_load(plan, C.c_void_p(comp_host.data_ptr()), int(threads)))
-        n_blocks, n_seg = int(ilib.pv_bam_plan_n_blocks(plan)), int(ilib.pv_bam_plan_n_segments(plan))
-        u_bytes = int(ilib.pv_bam_plan_inflated_bytes(plan))
-        blocks = np.zeros(max(n_blocks, 1), _BLOCK_DT)
-        seg = np.zeros((2, max(n_seg, 1)), np.int64)
-        ingest._check(ilib.pv_bam_plan_tables(plan, blocks.ctypes.data, seg[0].ctypes.data, seg[1].ctypes.data))
+        h.comp_bytes = int(ilib.pv_bam_plan_comp_bytes(plan))
+        h.comp_host = _PINNED.take(h.comp_bytes)
+        ingest._check(ilib.pv_bam_plan_load(plan, C.c_void_p(h.comp_host.data_ptr()), int(threads)))
+        h.n_blocks, h.n_seg = int(ilib.pv_bam_plan_n_blocks(plan)), int(ilib.pv_bam_plan_n_segments(plan))
+        h.u_bytes = int(ilib.pv_bam_plan_inflated_bytes(plan))
+        h.blocks = np.zeros(max(h.n_blocks, 1), _BLOCK_DT)
+        h.seg = np.zeros((2, max(h.n_seg, 1)), np.int64)
+        ingest._check(ilib.pv_bam_plan_tables(plan, h.blocks.ctypes.data, h.seg[0].ctypes.data, h.seg[1].ctypes.data))
     finally:
-        ilib.pv_bam_plan_free(plan)
+        if plan:
+            ilib.pv_bam_plan_free(plan)
+        if fetch_thread is not None:
+            fetch_thread.join()
+    if fetch_err:
+        raise fetch_err[0]
+    h.seconds = time.perf_counter() - t0
+    return h
+
+
+_COPY_STREAMS = {}
+
+
+def _device_stage(h: _HostStage, dev, verify_crc=True) -> DeviceIngestedReads:
+    import os
+    import time
+    lib = capi.load()
+    if dev.index is not None:
+        torch.cuda.set_device(dev)
     t_plan = time.perf_counter()
+    n_spans, n_blocks, n_seg, u_bytes, comp_bytes, tid = h.n_spans, h.n_blocks, h.n_seg, h.u_bytes, h.comp_bytes, h.tid
+    include_supplementary, min_mapq, downsample_rate = h.opts
+    span_start, span_stop, s, e = h.span_start, h.span_stop, h.s, h.e
+    main = torch.cuda.current_stream(dev)
+    st = C.c_void_p(main.cuda_stream)
     trace = {} if os.environ.get("PV_INGEST_TRACE") else None
 
     def mark(name, _last=[t_plan]):
@@ -118,43 +203,55 @@ def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, conti
             trace[name] = round((now - _last[0]) * 1e3, 3)
             _last[0] = now
 
-    # ---- device: inflate, records, clip
-    comp = comp_host.to(dev, non_blocking=True)
-    blocks_d = torch.from_numpy(blocks.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
-    seg_d = torch.from_numpy(seg).to(dev, non_blocking=True)
+    # ---- upload in pieces on a copy stream; the blocks of a piece inflate as soon as its bytes have landed
+    key = (dev.type, torch.cuda.current_device())
+    copy = _COPY_STREAMS.get(key)
+    if copy is None:
+        copy = _COPY_STREAMS[key] = torch.cuda.Stream(dev)
+    comp_n = (comp_bytes + 255) & ~255
+    comp = torch.empty(comp_n, dtype=torch.uint8, device=dev)
+    blocks_d = torch.from_numpy(h.blocks.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
+    seg_d = torch.from_numpy(h.seg).to(dev, non_blocking=True)
     spans_d = torch.from_numpy(np.stack([span_start, span_stop]) if n_spans else np.zeros((2, 1), np.int64)).to(dev, non_blocking=True)
     U = torch.empty(u_bytes + 64, dtype=torch.uint8, device=dev)
-    flags = torch.zeros(4, dtype=torch.int32, device=dev)       # [0] bad blocks, [1] chain status, [2] clip status, [3] min_qual
-    mark("upload")
-    capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, _ptr(blocks_d), n_blocks, _ptr(U), u_bytes, int(bool(verify_crc)), _ptr(flags[0:1]), st))
-    # ---- reference + region fields while the blocks inflate: ONE fetch of the covering span by FASTA_handler's C side into
-    # page-locked memory, cut into the per-region pieces on the device
-    clen = int(fasta.get_chromosome_sequence_length(contig)) if n_spans else 0
-    if n_spans and clen < 0:
-        raise RuntimeError("CHROMOSOME NAME NOT PRESENT IN REFERENCE FASTA FILE: %s" % contig)
-    regions = {"region_ref_start": span_start.astype(np.int64), "region_ref_end": span_stop.astype(np.int64),
-               "region_cand_start": s.copy(), "region_cand_end": e.copy()}
-    rlen = (span_stop + 1 - span_start).astype(np.int64) if n_spans else np.zeros(0, np.int64)     # region_end + 1 exclusive (:214-216)
-    regions["region_ref_len"] = rlen
-    regions["region_ref_off"] = (np.cumsum(rlen) - rlen).astype(np.int64)
-    ref_bytes = int(rlen.sum())
+    # pieces of whole waves of the inflate kernel (32 warps = blocks per SM at a time): one wave, two waves, the rest --
+    # only the first piece's upload is exposed, the others land while the piece before them inflates
+    wave = 32 * torch.cuda.get_device_properties(dev).multi_processor_count
+    first = [0] + [b for b in (wave, 3 * wave) if b < n_blocks - wave // 2] + [n_blocks]
+    pieces = len(first) - 1
+    bad_d = torch.zeros((pieces, 2), dtype=torch.int32, device=dev)   # per piece: bad blocks, the kernel's ticket
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)       # [1] chain status, [2] clip status, [3] min_qual
+    cut = [0] + [int(h.blocks["c_off"][first[k]]) & ~255 for k in range(1, pieces)] + [min(comp_n, h.comp_host.numel())]
+    copy.wait_stream(main)
+    bs = _BLOCK_DT.itemsize
+    for k in range(pieces):
+        with torch.cuda.stream(copy):
+            comp[cut[k]:cut[k + 1]].copy_(h.comp_host[cut[k]:cut[k + 1]], non_blocking=True)
+        main.wait_stream(copy)
+        if first[k + 1] > first[k]:
+            capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, C.c_void_p(blocks_d.data_ptr() + first[k] * bs), first[k + 1] - first[k],
+                                                 _ptr(U), u_bytes, int(bool(verify_crc)), C.c_void_p(bad_d.data_ptr() + 8 * k), st))
+    # ---- the regions' reference bytes
+    ref_bytes = int(h.rlen.sum())
     ref_t = {}
     for name in ("region_ref_start", "region_ref_end", "region_cand_start", "region_cand_end", "region_ref_off", "region_ref_len"):
-        ref_t[name] = torch.from_numpy(np.ascontiguousarray(regions[name])).to(dev, non_blocking=True) if n_spans else torch.zeros(1, dtype=torch.int64, device=dev)[:0]
+        ref_t[name] = torch.from_numpy(np.ascontiguousarray(h.regions[name])).to(dev, non_blocking=True) if n_spans else torch.zeros(1, dtype=torch.int64, device=dev)[:0]
     ref_t["ref"] = torch.empty(ref_bytes, dtype=torch.uint8, device=dev)
     if n_spans:
-        lo, hi = int(span_start.min()), int(span_stop.max()) + 1
-        fetched_host = torch.empty(max(hi - lo, 1), dtype=torch.uint8, pin_memory=True)
-        got_len = C.c_int64(0)
-        ingest._check(ilib.pv_fasta_fetch(fasta._h, contig.encode(), lo, hi, C.c_void_p(fetched_host.data_ptr()), C.byref(got_len)))
-        fetched = fetched_host.to(dev, non_blocking=True)
-        capi.check(lib.pv_bam_gather_reference(_ptr(fetched), int(got_len.value), lo, _ptr(spans_d[0]), _ptr(ref_t["region_ref_off"]),
-                                               _ptr(ref_t["region_ref_len"]), n_spans, int(rlen.max()), _ptr(ref_t["ref"]), st))
-    mark("inflate+reference")
+        fetched = h.fetched_host[:max(h.fetched_len, 1)].to(dev, non_blocking=True)
+        capi.check(lib.pv_bam_gather_reference(_ptr(fetched), h.fetched_len, h.lo, _ptr(spans_d[0]), _ptr(ref_t["region_ref_off"]),
+                                               _ptr(ref_t["region_ref_len"]), n_spans, int(h.rlen.max()), _ptr(ref_t["ref"]), st))
+    ev_copy, ev_main = torch.cuda.Event(), torch.cuda.Event()
+    ev_copy.record(copy); ev_main.record(main)
+    _PINNED.give(h.comp_host, ev_copy)
+    if h.fetched_host is not None:
+        _PINNED.give(h.fetched_host, ev_main)
+    h.comp_host = h.fetched_host = None
+    mark("upload+inflate+reference")
     seg_first = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
     capi.check(lib.pv_bam_index_records(_ptr(U), u_bytes, _ptr(seg_d[0]), _ptr(seg_d[1]), n_seg, _ptr(seg_first), None, 0, _ptr(flags[1:2]), st))
     n_rec = int(seg_first[n_seg].item())
-    bad = int(flags[0].item())
+    bad = int(bad_d[:, 0].sum().item())
     if bad:
         raise capi.PvError(-1, "BGZF: %d block(s) failed to inflate or their CRC-32 does not match" % bad)
     _status(flags[1], "record index (count)")
@@ -224,12 +321,43 @@ def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, conti
     _status(flags[2], "clip (write)")
     for name in ("read_pos", "read_base_off", "read_len", "read_cigar_off", "read_n_ops", "read_flags", "read_mapq"):
         t[name] = t[name][:n_reads]
-    batch = DeviceReadBatch(t, regions, mq if (n_reads and 0 < mq <= 255) else 0, dev, contigs=[contig] * n_spans,
-                            region_contig_len=np.full(n_spans, clen, np.int64), h2d_bytes=comp_bytes + (hi - lo if n_spans else 0))
+    batch = DeviceReadBatch(t, h.regions, mq if (n_reads and 0 < mq <= 255) else 0, dev, contigs=[h.contig] * n_spans,
+                            region_contig_len=np.full(n_spans, h.clen, np.int64), h2d_bytes=comp_bytes + (h.hi - h.lo))
     assert set(ARRAY_NAMES) <= set(t)
     t_done = time.perf_counter()
     stats = {"compressed_bytes": comp_bytes, "inflated_bytes": u_bytes, "bgzf_blocks": n_blocks, "chain_segments": n_seg,
-             "records": n_rec, "reads": n_reads, "host_plan_s": t_plan - t0, "device_s": t_done - t_plan}
+             "records": n_rec, "reads": n_reads, "host_plan_s": h.seconds, "device_s": t_done - t_plan}
     if trace is not None:
         stats["trace_ms"] = trace
     return DeviceIngestedReads(batch, pos_end[:n_reads], hp[:n_reads], bam_flag[:n_reads], U, name_off[:n_reads], name_len[:n_reads], stats)
+
+
+def ingest_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, contig: str, starts: Sequence[int], ends: Sequence[int],
+                       include_supplementary=False, min_mapq=0, min_baseq=0, downsample_rate=1.0, threads=0,
+                       safe_bases=REGION_SAFE_BASES, device="cuda", verify_crc=True) -> DeviceIngestedReads:
+    """Device twin of :func:`ingest.ingest_regions`: packed batch for intervals ``[starts[i], ends[i]]`` (ascending) of one
+    contig, decoded and cut on the GPU. ``min_baseq`` is accepted for signature parity (it only feeds ``bad_indicies`` in
+    the reference, which the packed batch does not carry)."""
+    h = _host_stage(bam, fasta, contig, starts, ends, include_supplementary, min_mapq, downsample_rate, threads, safe_bases)
+    return _device_stage(h, torch.device(device), verify_crc)
+
+
+def stream_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, contig: str, groups, include_supplementary=False, min_mapq=0,
+                       downsample_rate=1.0, threads=0, safe_bases=REGION_SAFE_BASES, device="cuda", verify_crc=True):
+    """Generator over ``groups`` = [(starts, ends), ...] of one contig: yields one :class:`DeviceIngestedReads` per group, with
+    the HOST share of group i+1 (BAI query, threaded read of the compressed bytes into page-locked memory, BGZF header walk,
+    FASTA fetch) running on a worker thread while the caller's kernels -- the decode of group i and whatever consumes its
+    batch -- occupy the device ("overlapping inflate with GPU work"). The C side releases the GIL."""
+    from concurrent.futures import ThreadPoolExecutor
+    dev = torch.device(device)
+    groups = list(groups)
+    if not groups:
+        return
+    args = (include_supplementary, min_mapq, downsample_rate, threads, safe_bases)
+    with ThreadPoolExecutor(1) as ex:
+        fut = ex.submit(_host_stage, bam, fasta, contig, groups[0][0], groups[0][1], *args)
+        for i in range(len(groups)):
+            h = fut.result()
+            if i + 1 < len(groups):
+                fut = ex.submit(_host_stage, bam, fasta, contig, groups[i + 1][0], groups[i + 1][1], *args)
+            yield _device_stage(h, dev, verify_crc)

@@ -82,7 +82,7 @@ def build_ingest(force=False, verbose=False):
     """Host-only BAM/FASTA ingest (zlib), include/pepper_ingest.h."""
     src = os.path.join(CSRC, "ingest.cpp")
     if force or _newer(INGEST, [src, os.path.join(CSRC, "fast_inflate.h"), os.path.join(INC, "pepper_ingest.h"), os.path.join(INC, "pepper_b200.h")]):
-        _run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wall", "-I", INC, src, "-o", INGEST, "-lz", "-lpthread"], verbose)
+        _run(["g++", "-O3", "-fPIC", "-shared", "-std=c++17", "-Wall", "-I", INC, src, "-o", INGEST, "-lz", "-lpthread"], verbose)
     return INGEST
 
 

@@ -62,12 +62,12 @@ def run_blocks(comp, table, total, verify=True):
     c = torch.from_numpy(np.frombuffer(bytes(comp) + b"\0" * 0, np.uint8).copy() if len(comp) else np.zeros(4, np.uint8)).cuda()
     t = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()).cuda()
     U = torch.full((total + 64,), 0xEE, dtype=torch.uint8, device="cuda")
-    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    bad = torch.zeros(2, dtype=torch.int32, device="cuda")        # bad blocks, the kernel's ticket
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     capi.check(lib.pv_bam_inflate_blocks(C.c_void_p(c.data_ptr()), len(comp), C.c_void_p(t.data_ptr()), len(table), C.c_void_p(U.data_ptr()), total,
                                          int(verify), C.c_void_p(bad.data_ptr()), st))
     torch.cuda.synchronize()
-    return U.cpu().numpy(), int(bad.item())
+    return U.cpu().numpy(), int(bad[0].item())
 
 
 def pack(items, gap_rng=None):

@@ -54,4 +54,19 @@ def once():
 once(); torch.cuda.synchronize()
 t0 = time.perf_counter(); k = once(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
 out["bam_to_candidates"] = dict(value=round(L / dt / 1e6, 2), unit="Mbp/s", seconds=round(dt, 4), candidates=k, status=ws.status())
+# streamed: the contig in groups of regions, host share of group i+1 under the device work of group i (decode + summary kernels)
+group_mbp = float(os.environ.get("PV_INGEST_GROUP_MBP", "8"))
+per = max(1, int(group_mbp * 1e6 / 100000))
+groups = [(starts[i:i + per], ends[i:i + per]) for i in range(0, len(starts), per)]
+def streamed():
+    total = 0
+    for g in ingest_gpu.stream_regions_gpu(bh, fh, "chrS", groups, min_mapq=1, verify_crc=crc):
+        w = dev.SummaryWorkspace.for_batch(g.batch, max(8192, int(group_mbp * 1000 * 8)))
+        dev.summary_regions(g.batch, thr, w)
+        total += int(w.count.item())
+    return total
+streamed(); torch.cuda.synchronize()
+t0 = time.perf_counter(); k2 = streamed(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+out["bam_to_candidates_streamed"] = dict(value=round(L / dt / 1e6, 2), unit="Mbp/s", seconds=round(dt, 4), groups=len(groups), group_mbp=group_mbp, candidates=k2,
+                                         same_candidate_count=bool(k2 == k))
 print(json.dumps(out))
