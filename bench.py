@@ -12,6 +12,8 @@ carries, under "extras", the other BASELINE configs the box can run in a bounded
     config4   ONT R10 Q20 preset at 40x, whole-genome scale, reads generated per region ON the device and streamed
               (3.1 Gbp over 8 GPUs = 387.5 Mbp per GPU; with fewer GPUs the same per-GPU share is run and said so)
     config5   TransducerGRU inference-only sweep (windows x 100 positions, hidden 128) next to the LSTM model
+    bam_ingest  SURVEY 8f row 1: a synthetic 30x ONT BAM + FASTA written here, decoded ON the device (BGZF inflate, record
+              parsing, get_reads clipping -> PvReadBatch in HBM) and taken through the summary kernels: BAM -> candidates
 Flags select any of them as the main workload instead: --preset/--coverage/--mbp/--scaling.
 
 Three numbers per workload:
@@ -615,6 +617,13 @@ def run_ours(args):
                 extras["config5"] = extras_config5(ctx)
             except Exception as e:
                 extras["config5"] = {"error": repr(e)[:300]}
+            # BAM + FASTA -> candidates with the BAM decoded on the device (a synthetic 30x ONT BAM written here)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_ingest_gpu
+                extras["bam_ingest"] = bench_ingest_gpu.run(float(os.environ.get("PV_BENCH_INGEST_MBP", "8")), 30.0)
+            except Exception as e:
+                extras["bam_ingest"] = {"error": repr(e)[:300]}
 
     if ctx.rank != 0:
         if ctx.world > 1:

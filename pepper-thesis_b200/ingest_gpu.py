@@ -80,7 +80,7 @@ class _PinnedPool:
         with self._lock:
             best = None
             for i, (buf, ev) in enumerate(self._free):
-                if buf.numel() >= nbytes and (best is None or buf.numel() < self._free[best][0].numel()):
+                if nbytes <= buf.numel() <= max(4 * nbytes, nbytes + (64 << 20)) and (best is None or buf.numel() < self._free[best][0].numel()):
                     best = i
             got = self._free.pop(best) if best is not None else None
         if got is None:
