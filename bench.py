@@ -621,7 +621,7 @@ def run_ours(args):
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_ingest_gpu
-                extras["bam_ingest"] = bench_ingest_gpu.run(float(os.environ.get("PV_BENCH_INGEST_MBP", "8")), 30.0)
+                extras["bam_ingest"] = bench_ingest_gpu.run(float(os.environ.get("PV_BENCH_INGEST_MBP", "16")), 30.0)
             except Exception as e:
                 extras["bam_ingest"] = {"error": repr(e)[:300]}
 

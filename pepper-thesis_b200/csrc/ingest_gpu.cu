@@ -206,10 +206,40 @@ __global__ void __launch_bounds__(256) write_kernel(const WriteArgs a, int32_t* 
     idx0 = __shfl_sync(0xffffffffu, idx0, 0);
     const int64_t n = p.n_bases, padded = (n + 15) & ~(int64_t)15, bo = a.base_off[i];
     int mq = 255;
-    for (int64_t k = lane; k < padded; k += 32) {
-        uint8_t b = 0, q = 0;
-        if (k < n) { b = record_base(a.U, h, idx0 + k); q = a.U[h.qual_off + idx0 + k]; mq = q < mq ? q : mq; }
-        a.bases[bo + k] = b; a.quals[bo + k] = q;
+    // four bases per lane and step: nt16 codes -> upper-case ASCII through a 16-byte table held in two registers, qualities
+    // copied, both leave as one aligned 32-bit store (the read's slot starts on a 16-byte boundary)
+    const unsigned long long NT_LO = 0x565352474d43413dULL, NT_HI = 0x4e42444b48595754ULL;   // "=ACMGRSV", "TWYHKDBN"
+    const uint8_t* seq = a.U + h.seq_off;
+    const uint8_t* qual = a.U + h.qual_off + idx0;
+    uint32_t* ob = (uint32_t*)(a.bases + bo);
+    uint32_t* oq = (uint32_t*)(a.quals + bo);
+#pragma unroll 2
+    for (int64_t k = 4 * (int64_t)lane; k < padded; k += 128) {
+        uint32_t bw = 0, qw = 0;
+        if (k + 4 <= n) {
+            const int64_t s0 = idx0 + k;
+            const uint8_t* sp = seq + (s0 >> 1);
+            const uint32_t b0 = sp[0], b1 = sp[1], b2 = (s0 & 1) ? sp[2] : 0u;
+            const uint32_t nibs = (s0 & 1) ? (((b0 & 15u) << 12) | (b1 << 4) | (b2 >> 4)) : ((b0 << 8) | b1);   // four codes, first in the top nibble
+            const uint32_t q0 = qual[k], q1 = qual[k + 1], q2 = qual[k + 2], q3 = qual[k + 3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t c = (nibs >> (12 - 4 * j)) & 15u;
+                bw |= (uint32_t)(((c & 8u) ? NT_HI : NT_LO) >> (8 * (c & 7u)) & 0xffu) << (8 * j);
+            }
+            qw = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            const int m01 = q0 < q1 ? q0 : q1, m23 = q2 < q3 ? q2 : q3, m = m01 < m23 ? m01 : m23;
+            mq = m < mq ? m : mq;
+        } else {
+            for (int j = 0; j < 4; j++) {
+                if (k + j < n) {
+                    const uint32_t b = record_base(a.U, h, idx0 + k + j), q = qual[k + j];
+                    bw |= b << (8 * j); qw |= q << (8 * j);
+                    mq = (int)q < mq ? (int)q : mq;
+                }
+            }
+        }
+        ob[k >> 2] = bw; oq[k >> 2] = qw;
     }
     for (int d = 16; d; d >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, mq, d); mq = o < mq ? o : mq; }
     if (lane == 0) atomicMin(a.min_qual, mq);
