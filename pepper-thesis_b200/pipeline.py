@@ -250,7 +250,7 @@ class HotPath:
     # ---- public entry points --------------------------------------------------------------------------------------------
     def run_device(self, dbs, region_offsets=None, to_host: bool = True):
         """Groups of regions already resident in HBM (one DeviceBatch or a list of them)."""
-        if isinstance(dbs, dev.DeviceBatch):
+        if isinstance(dbs, (dev.DeviceBatch, dev.DeviceReadBatch)):
             dbs = [dbs]
         if region_offsets is None:
             region_offsets, o = [], 0

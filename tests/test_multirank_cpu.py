@@ -73,3 +73,52 @@ def test_shard_regions_partition():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
             sizes = [b[1] - b[0] for b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _cv_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pepper_thesis_b200 import call_variant as CV
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # interval i belongs to rank i % world (ImageGenerationUI.py:211); sites 10000 and 30000 sit on interval boundaries and
+    # are reported by both neighbours
+    def cand(contig, pos, ref, alt, tag):
+        return (contig, pos, pos + 1, ref, [alt], [0, 1], 30, [12], 0.9, [0.05, 0.9, 0.05], [0.9], False, tag)[:12]
+    sites = {0: [("chr1", 500, "A", "C"), ("chr1", 10000, "G", "T")], 1: [("chr1", 10000, "G", "T"), ("chr1", 10000, "G", "GA"), ("chr1", 15000, "C", "A")],
+             2: [("chr1", 20500, "T", "G"), ("chr1", 30000, "A", "AT")], 3: [("chr1", 30000, "A", "AT"), ("chr0", 7, "C", "G")]}
+    variant, phasing, contigs = {}, {}, []
+    for i in range(4):
+        if i % world != rank:
+            continue
+        for c, pos, ref, alt in sites[i]:
+            variant.setdefault((c, pos), []).append(cand(c, pos, ref, alt, i))
+            phasing.setdefault((c, pos), []).append(cand(c, pos, ref, alt, i)[:10])
+            if c not in contigs:
+                contigs.append(c)
+    res = CV.gather_candidates((contigs, phasing, variant, dict(intervals=2, candidates=len(variant))), rank, world)
+    if rank == 0:
+        contigs, p, v, st = res
+        ok = (contigs == ["chr0", "chr1"] and list(v) == [("chr0", 7), ("chr1", 500), ("chr1", 10000), ("chr1", 15000), ("chr1", 20500), ("chr1", 30000)]
+              and [(c[3], c[4][0]) for c in v[("chr1", 10000)]] == [("G", "T"), ("G", "GA")] and len(v[("chr1", 30000)]) == 1
+              and list(p) == list(v) and st["intervals"] == 4)
+        q.put(bool(ok))
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_candidate_gather():
+    """call_variant's gather of the selected candidates: sites sorted, one entry per (ref, alt) across the ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_cv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+    assert ok and all(p.exitcode == 0 for p in procs)
