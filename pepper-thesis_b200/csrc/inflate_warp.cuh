@@ -7,10 +7,7 @@
 //   * Huffman tables are built by the warp (counts by shared atomics, canonical order by match_any / popc, replicas
 //     filled lane per symbol) into shared memory: a 10-bit table for literals / lengths whose entries carry TWO literals
 //     when both codes fit the index, an 8-bit table for distances; longer codes take a canonical bit walk;
-//   * runs of literals are decoded 32 bit offsets at a time: every lane looks up the symbol that would start at its
-//     offset, pointer doubling over the lanes finds the offsets that really start symbols, and the literals on that
-//     chain are stored together (only the symbol that ends a run -- a length, the end of block, a long code -- is decoded
-//     by the serial path, where literals collect in a register per lane and leave as one 32-byte store);
+//   * literals collect in a register per lane and leave as one 32-byte store per 32 bytes of output;
 //   * matches are copied by all lanes (32 bytes per step, periodic patterns of short distances expanded directly);
 //   * the block's CRC-32 is 32 partial CRCs over 1/32 of the bytes each, combined with x^(8 n) mod P (zlib's
 //     crc32_combine identity), and compared with the BGZF trailer.
@@ -214,42 +211,6 @@ template <bool CAREFUL>
 __device__ __forceinline__ int decode_symbols(Dec& D, WarpTables& T, uint8_t* __restrict__ out, const int n_out, const int lane) {
     Bits& B = D.B;
     for (;;) {
-        if (!CAREFUL) {
-            // A ROUND: lane k decodes the symbol that would start k bits from here (32 candidate starts, one table lookup
-            // each); the true starts are the chain 0 -> 0 + len(0) -> ..., found by pointer doubling over the lanes; the
-            // literals on the chain go to memory together and the reader moves past all of them. The chain ends where it
-            // leaves the 32 starts or at the first symbol that is not a literal, which the serial code below takes.
-            flush_pending(D, out, lane);
-            const uint32_t r3 = B.ldw(B.wp), r4 = B.ldw(B.wp + 1);
-            const uint32_t w0 = __funnelshift_r(B.lo, B.hi, B.bp), w1 = __funnelshift_r(B.hi, B.nxt, B.bp);
-            const uint32_t v = __funnelshift_r(w0, w1, lane);
-            const uint32_t e = T.lit[v & ((1u << LIT_ROOT) - 1u)];
-            const uint32_t t = e & 0x70u;
-            const bool lit = t == 0x10u || t == 0x20u;          // a paired entry still carries its first literal and length
-            const int n1 = e & 15;
-            int jump = lit ? lane + n1 : 64;
-            const int adv0 = lit ? lane + n1 : (lane | 0x100);   // bits to consume when the chain ends here; bit 8: it ends AT a non-literal
-            unsigned M = 1u;
-            for (;;) {
-                const unsigned add = __reduce_or_sync(FULL, (((M >> lane) & 1u) && jump < 32) ? (1u << jump) : 0u);
-                if ((add & ~M) == 0u) break;
-                M |= add;
-                const int j2 = __shfl_sync(FULL, jump, jump & 31);
-                if (jump < 32) jump = j2;
-            }
-            const unsigned C = M & __ballot_sync(FULL, lit);
-            if ((C >> lane) & 1u) out[D.op + __popc(C & ((1u << lane) - 1u))] = (uint8_t)(e >> 8);
-            D.op += __popc(C); D.pend = D.op;
-            const int adv = __shfl_sync(FULL, adv0, 31 - __clz(M));
-            B.bp += adv & 0xff;
-            if (B.bp >= 32) {
-                B.lo = B.hi; B.hi = B.nxt; B.nxt = r3; B.wp++; B.bp -= 32;
-                if (B.bp >= 32) { B.lo = B.hi; B.hi = B.nxt; B.nxt = r4; B.wp++; B.bp -= 32; }
-                if ((B.wp & 15) < 2 && B.wp + 64 < B.n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(B.w + B.wp + 64));
-            }
-            if (D.op + FAST_MARGIN > n_out) return 1;
-            if (!(adv & 0x100)) continue;
-        }
         uint32_t w = B.window();
         uint32_t e = T.lit[w & ((1u << LIT_ROOT) - 1u)];
         uint32_t t = e & 0x70u;
