@@ -33,7 +33,7 @@ class CallOptions:
     include_supplementary: bool = False
     min_mapq: int = 5
     downsample_rate: float = 1.0
-    group_mbp: float = 16.0                     # contig span decoded per device call
+    group_mbp: float = 32.0                     # contig span decoded per device call (a BGZF block takes ~10 ms: large calls amortise that)
     threads: int = 0
     filter: candidate_filter.FilterOptions = field(default_factory=candidate_filter.FilterOptions)
 

@@ -24,7 +24,20 @@
 namespace bamcore {
 
 PV_HD uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
-PV_HD uint32_t ld32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+// 32-bit little-endian load at any alignment. On the device: the aligned word(s) that hold the four bytes and a funnel
+// shift (one or two transactions instead of four); the second word is only touched when the value really reaches into it,
+// so nothing behind p + 3 is read.
+PV_HD uint32_t ld32(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    const uint32_t lo = q[0], hi = sh ? q[1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
 
 // ---- DEFLATE ---------------------------------------------------------------------------------------------------
 constexpr int FAST_BITS = 9;

@@ -182,7 +182,35 @@ def _host_stage(bam, fasta, contig, starts, ends, include_supplementary, min_map
 _COPY_STREAMS = {}
 
 
-def _device_stage(h: _HostStage, dev, verify_crc=True) -> DeviceIngestedReads:
+def _copy_stream(dev):
+    key = (dev.type, torch.cuda.current_device())
+    copy = _COPY_STREAMS.get(key)
+    if copy is None:
+        copy = _COPY_STREAMS[key] = torch.cuda.Stream(dev)
+    return copy
+
+
+def _start_upload(h: _HostStage, dev):
+    """Queues the whole compressed buffer of a host stage on the copy stream NOW (the streamed generator calls this for group
+    i+1 before it queues the kernels of group i, so the transfer runs under them); :func:`_device_stage` then waits for the
+    event and inflates with one launch."""
+    if dev.index is not None:
+        torch.cuda.set_device(dev)
+    copy, main = _copy_stream(dev), torch.cuda.current_stream(dev)
+    comp_n = (h.comp_bytes + 255) & ~255
+    comp = torch.empty(comp_n, dtype=torch.uint8, device=dev)
+    copy.wait_stream(main)
+    n = min(comp_n, h.comp_host.numel())
+    with torch.cuda.stream(copy):
+        comp[:n].copy_(h.comp_host[:n], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(copy)
+    _PINNED.give(h.comp_host, ev)
+    h.comp_host = None
+    return comp, ev
+
+
+def _device_stage(h: _HostStage, dev, verify_crc=True, uploaded=None) -> DeviceIngestedReads:
     import os
     import time
     lib = capi.load()
@@ -204,33 +232,42 @@ def _device_stage(h: _HostStage, dev, verify_crc=True) -> DeviceIngestedReads:
             _last[0] = now
 
     # ---- upload in pieces on a copy stream; the blocks of a piece inflate as soon as its bytes have landed
-    key = (dev.type, torch.cuda.current_device())
-    copy = _COPY_STREAMS.get(key)
-    if copy is None:
-        copy = _COPY_STREAMS[key] = torch.cuda.Stream(dev)
-    comp_n = (comp_bytes + 255) & ~255
-    comp = torch.empty(comp_n, dtype=torch.uint8, device=dev)
+    copy = _copy_stream(dev)
     blocks_d = torch.from_numpy(h.blocks.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
     seg_d = torch.from_numpy(h.seg).to(dev, non_blocking=True)
     spans_d = torch.from_numpy(np.stack([span_start, span_stop]) if n_spans else np.zeros((2, 1), np.int64)).to(dev, non_blocking=True)
     U = torch.empty(u_bytes + 64, dtype=torch.uint8, device=dev)
-    # pieces of whole waves of the inflate kernel (32 warps = blocks per SM at a time): one wave, two waves, the rest --
-    # only the first piece's upload is exposed, the others land while the piece before them inflates
-    wave = 32 * torch.cuda.get_device_properties(dev).multi_processor_count
-    first = [0] + [b for b in (wave, 3 * wave) if b < n_blocks - wave // 2] + [n_blocks]
-    pieces = len(first) - 1
-    bad_d = torch.zeros((pieces, 2), dtype=torch.int32, device=dev)   # per piece: bad blocks, the kernel's ticket
     flags = torch.zeros(4, dtype=torch.int32, device=dev)       # [1] chain status, [2] clip status, [3] min_qual
-    cut = [0] + [int(h.blocks["c_off"][first[k]]) & ~255 for k in range(1, pieces)] + [min(comp_n, h.comp_host.numel())]
-    copy.wait_stream(main)
     bs = _BLOCK_DT.itemsize
-    for k in range(pieces):
-        with torch.cuda.stream(copy):
-            comp[cut[k]:cut[k + 1]].copy_(h.comp_host[cut[k]:cut[k + 1]], non_blocking=True)
-        main.wait_stream(copy)
-        if first[k + 1] > first[k]:
-            capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, C.c_void_p(blocks_d.data_ptr() + first[k] * bs), first[k + 1] - first[k],
-                                                 _ptr(U), u_bytes, int(bool(verify_crc)), C.c_void_p(bad_d.data_ptr() + 8 * k), st))
+    if uploaded is not None:
+        # the bytes were queued on the copy stream earlier (under the previous group's kernels): one launch for all blocks
+        comp, ev_up = uploaded
+        bad_d = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        main.wait_event(ev_up)
+        capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, _ptr(blocks_d), n_blocks, _ptr(U), u_bytes, int(bool(verify_crc)),
+                                             _ptr(bad_d), st))
+    else:
+        comp_n = (comp_bytes + 255) & ~255
+        comp = torch.empty(comp_n, dtype=torch.uint8, device=dev)
+        # pieces of whole waves of the inflate kernel (32 warps = blocks per SM at a time): one wave, two waves, the rest --
+        # only the first piece's upload is exposed, the others land while the piece before them inflates
+        wave = 32 * torch.cuda.get_device_properties(dev).multi_processor_count
+        first = [0] + [b for b in (wave, 3 * wave) if b < n_blocks - wave // 2] + [n_blocks]
+        pieces = len(first) - 1
+        bad_d = torch.zeros((pieces, 2), dtype=torch.int32, device=dev)   # per piece: bad blocks, the kernel's ticket
+        cut = [0] + [int(h.blocks["c_off"][first[k]]) & ~255 for k in range(1, pieces)] + [min(comp_n, h.comp_host.numel())]
+        copy.wait_stream(main)
+        for k in range(pieces):
+            with torch.cuda.stream(copy):
+                comp[cut[k]:cut[k + 1]].copy_(h.comp_host[cut[k]:cut[k + 1]], non_blocking=True)
+            main.wait_stream(copy)
+            if first[k + 1] > first[k]:
+                capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, C.c_void_p(blocks_d.data_ptr() + first[k] * bs), first[k + 1] - first[k],
+                                                     _ptr(U), u_bytes, int(bool(verify_crc)), C.c_void_p(bad_d.data_ptr() + 8 * k), st))
+        ev_copy = torch.cuda.Event()
+        ev_copy.record(copy)
+        _PINNED.give(h.comp_host, ev_copy)
+        h.comp_host = None
     # ---- the regions' reference bytes
     ref_bytes = int(h.rlen.sum())
     ref_t = {}
@@ -241,12 +278,11 @@ def _device_stage(h: _HostStage, dev, verify_crc=True) -> DeviceIngestedReads:
         fetched = h.fetched_host[:max(h.fetched_len, 1)].to(dev, non_blocking=True)
         capi.check(lib.pv_bam_gather_reference(_ptr(fetched), h.fetched_len, h.lo, _ptr(spans_d[0]), _ptr(ref_t["region_ref_off"]),
                                                _ptr(ref_t["region_ref_len"]), n_spans, int(h.rlen.max()), _ptr(ref_t["ref"]), st))
-    ev_copy, ev_main = torch.cuda.Event(), torch.cuda.Event()
-    ev_copy.record(copy); ev_main.record(main)
-    _PINNED.give(h.comp_host, ev_copy)
     if h.fetched_host is not None:
+        ev_main = torch.cuda.Event()
+        ev_main.record(main)
         _PINNED.give(h.fetched_host, ev_main)
-    h.comp_host = h.fetched_host = None
+        h.fetched_host = None
     mark("upload+inflate+reference")
     seg_first = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
     capi.check(lib.pv_bam_index_records(_ptr(U), u_bytes, _ptr(seg_d[0]), _ptr(seg_d[1]), n_seg, _ptr(seg_first), None, 0, _ptr(flags[1:2]), st))
@@ -353,11 +389,22 @@ def stream_regions_gpu(bam: ingest.BAMHandler, fasta: ingest.FASTAHandler, conti
     groups = list(groups)
     if not groups:
         return
+    if threads <= 0:
+        import os
+        threads = max(2, min(8, (os.cpu_count() or 2) // 2))      # the caller's thread needs a core to keep the device fed
     args = (include_supplementary, min_mapq, downsample_rate, threads, safe_bases)
     with ThreadPoolExecutor(1) as ex:
-        fut = ex.submit(_host_stage, bam, fasta, contig, groups[0][0], groups[0][1], *args)
+        # three stages in flight: host stage of group i+2 (worker thread) | upload of group i+1 (copy stream) | kernels of group i
+        futs = [ex.submit(_host_stage, bam, fasta, contig, g[0], g[1], *args) for g in groups[:2]]
+        h = futs.pop(0).result()
+        up = _start_upload(h, dev)
         for i in range(len(groups)):
-            h = fut.result()
-            if i + 1 < len(groups):
-                fut = ex.submit(_host_stage, bam, fasta, contig, groups[i + 1][0], groups[i + 1][1], *args)
-            yield _device_stage(h, dev, verify_crc)
+            nxt = None
+            if futs:
+                h_next = futs.pop(0).result()
+                if i + 2 < len(groups):
+                    futs.append(ex.submit(_host_stage, bam, fasta, contig, groups[i + 2][0], groups[i + 2][1], *args))
+                nxt = (h_next, _start_upload(h_next, dev))         # queued before this group's kernels: runs under them
+            yield _device_stage(h, dev, verify_crc, uploaded=up)
+            if nxt is not None:
+                h, up = nxt

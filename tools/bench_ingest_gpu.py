@@ -55,20 +55,28 @@ def run(mbp=8.0, cov=30.0, group_mbp=None, crc=True, host_arm=True):
     out["bam_to_candidates"] = dict(value=round(L / dt / 1e6, 2), unit="Mbp/s", seconds=round(dt, 4), candidates=k, status=ws.status())
     # streamed: the contig in groups of regions, host share of group i+1 under the device work of group i (decode + summary kernels)
     if group_mbp is None:
-        group_mbp = float(os.environ.get("PV_INGEST_GROUP_MBP", "16"))
+        group_mbp = float(os.environ.get("PV_INGEST_GROUP_MBP", "32"))
     per = max(1, int(group_mbp * 1e6 / 100000))
     groups = [(starts[i:i + per], ends[i:i + per]) for i in range(0, len(starts), per)]
+    from pepper_thesis_b200 import models, pipeline
+    hot = pipeline.HotPath(None, thr, "cuda", group_regions=per)  # its summary half only: workspaces pooled across groups
+    trace = []
     def streamed():
         total = 0
+        del trace[:]
+        t_last = time.perf_counter()
         for g in ingest_gpu.stream_regions_gpu(bh, fh, "chrS", groups, min_mapq=1, verify_crc=crc):
-            w = dev.SummaryWorkspace.for_batch(g.batch, max(8192, int(group_mbp * 1000 * 8)))
-            dev.summary_regions(g.batch, thr, w)
-            total += int(w.count.item())
+            t_in = time.perf_counter()
+            w, kk = hot.summarize(g.batch)
+            total += kk
+            t_sum = time.perf_counter()
+            trace.append((round((t_in - t_last) * 1e3, 1), round((t_sum - t_in) * 1e3, 1), round(g.stats["host_plan_s"] * 1e3, 1), round(g.stats["device_s"] * 1e3, 1)))
+            t_last = t_sum
         return total
     streamed(); streamed(); torch.cuda.synchronize()                # twice: the pool of page-locked buffers fills on the way
     t0 = time.perf_counter(); k2 = streamed(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
     out["bam_to_candidates_streamed"] = dict(value=round(L / dt / 1e6, 2), unit="Mbp/s", seconds=round(dt, 4), groups=len(groups), group_mbp=group_mbp, candidates=k2,
-                                             same_candidate_count=bool(k2 == k))
+                                             same_candidate_count=bool(k2 == k), per_group_ms_ingest_summary_hoststage_devicestage=list(trace))
     import shutil
     shutil.rmtree(d, ignore_errors=True)
     return out
