@@ -36,8 +36,10 @@ class PolishSummary:
     """Summary of every region of a batch: ``image`` uint8 [rows][10], ``genomic_pos`` int64 [rows][2],
     ``region_rows`` int64 [n_regions + 1] (row range of each region) -- all torch tensors in HBM except region_rows."""
 
-    def __init__(self, batch: ReadBatch | dev.DeviceBatch, device="cuda"):
-        db = batch if isinstance(batch, dev.DeviceBatch) else dev.DeviceBatch(batch, device)
+    def __init__(self, batch: ReadBatch | dev.DeviceBatch | dev.DeviceReadBatch, device="cuda"):
+        # a DeviceReadBatch is a batch born on the device (ingest_gpu: BAM decoded by kernels, safe_bases=0 for the polisher's
+        # get_reads(chr, start, end) of pepper/modules/python/AlignmentSummarizer.py:300-305)
+        db = batch if isinstance(batch, (dev.DeviceBatch, dev.DeviceReadBatch)) else dev.DeviceBatch(batch, device)
         self.db = db
         lib = capi.load()
         h = db.host

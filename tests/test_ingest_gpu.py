@@ -100,3 +100,20 @@ def test_bam_to_candidates_from_device_born_batch(files):
         want = O.ref_summary(ob, 0, thr) if O.have_ref() else O.port_summary(ob, 0, thr)
         m = reg == r
         assert np.array_equal(pos[m], want["position"]) and np.array_equal(img[m].astype(np.int32), np.asarray(want["images"]).astype(np.int32))
+
+
+def test_polisher_summary_from_device_born_batch(files):
+    """The polisher's path from a BAM (pepper/modules/python/AlignmentSummarizer.py:296-350: get_reads(chr, start, end) with
+    no safe bases and mapq 0, reference [start, end + 1), SummaryGenerator, 1000 / 50 chunks) with the BAM decoded on the
+    device: image, positions and chunks equal the same kernels fed by the host ingest (pinned to the compiled reference)."""
+    import torch
+    from pepper_thesis_b200 import ingest_gpu, polish
+    bam, fa = ingest.BAMHandler(files["bam"]), ingest.FASTAHandler(files["fa"])
+    starts, ends = [1000, 40000, 90000], [21000, 47500, TI.CONTIG_LEN - 1]
+    got = ingest_gpu.ingest_regions_gpu(bam, fa, "chrS", starts, ends, safe_bases=0, min_mapq=0)
+    want = ingest.ingest_regions(bam, fa, "chrS", starts, ends, safe_bases=0, min_mapq=0)
+    a, b = polish.PolishSummary(got.batch), polish.PolishSummary(want.batch)
+    assert a.n_rows == b.n_rows > 20000 and np.array_equal(a.region_rows, b.region_rows)
+    assert torch.equal(a.image, b.image) and torch.equal(a.genomic_pos, b.genomic_pos)
+    ca, cb = a.chunks(), b.chunks()
+    assert torch.equal(ca[0], cb[0]) and torch.equal(ca[1], cb[1]) and np.array_equal(ca[2], cb[2]) and np.array_equal(ca[3], cb[3])
