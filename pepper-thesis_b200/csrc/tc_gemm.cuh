@@ -37,6 +37,18 @@ constexpr int EPI_THREADS = 256;
 // k block (the kernel is bound by exactly that traffic).
 constexpr int CLUSTER = 2;
 constexpr int W_SLICE_ROWS = BLOCK_N / CLUSTER;
+// PV_TWO_CTA = 1: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 of M = 256 per k step (the pair's two row tiles
+// stacked): every CTA keeps only ITS half of the W tile (128 of the 256 rows: the tensor core reads the other half from the
+// peer's shared memory), so a k block brings 16 + 16 KB into an SM instead of 16 + 32 KB. The leader (cluster rank 0) issues
+// the MMAs for both; both CTAs run their own TMA producer and their own epilogue on their own 128 accumulator rows.
+// Measured (round 2, 32768 windows, `tools/probe_lstm.py`, both builds in one box): decoder steps 3.08 vs 3.10 ms, MLP 0.64 vs
+// 0.66 ms, encoder steps 2.16 vs 1.97 ms -- halving the W bytes that enter an SM buys nothing, so the multicast form stays the
+// default; build with -DPV_TWO_CTA=1 (PV_NVCC_FLAGS) for the pair form (all model parity tests pass with it).
+#ifndef PV_TWO_CTA
+#define PV_TWO_CTA 0
+#endif
+constexpr bool TWO_CTA = PV_TWO_CTA != 0;
+constexpr int W_BYTES_PER_CTA = TWO_CTA ? W_STAGE_BYTES / CLUSTER : W_STAGE_BYTES;   // W bytes that land in one CTA per k block
 // dynamic shared memory of gemm_kernel<Epilogue>: operand ring + alignment slack + barriers + epilogue scratch
 template <class Epilogue> constexpr int smem_bytes() {
     return Epilogue::kStages * STAGE_BYTES + 1024 + 256 + Epilogue::kSmemBytes;
@@ -84,6 +96,22 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
                  ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+// 2-CTA forms: the data lands in the issuing CTA's shared memory, the bytes complete on the LEADER's mbarrier (same offset,
+// peer bit of the shared::cluster address cleared: cute::Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on the barrier at this offset in the cluster's CTA `rank`
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -106,6 +134,24 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// the pair's forms: the same warp of BOTH CTAs executes them
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// M = 256 over the pair: issued by the leader only; A rows / W rows of the second half come from the peer's shared memory
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_2sm(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -292,11 +338,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
     if (warp == 1 && lane == 0) {
         // a stage may be refilled only when ALL CTAs of the cluster have consumed it (peers multicast into it)
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], epi_warps<Epilogue>::value); }
+        // TWO_CTA: one commit (the leader's, multicast) frees a stage in each CTA; the leader's accumulator-free barrier
+        // collects the epilogue warps of BOTH CTAs
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO_CTA ? 1 : CLUSTER); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], (TWO_CTA ? CLUSTER : 1) * epi_warps<Epilogue>::value); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    if constexpr (TWO_CTA) {
+        __syncthreads();
+        cluster_sync_all();                                    // both CTAs are resident before the pair allocates
+        if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    } else {
+        if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                        // every CTA's barriers are initialised before any remote arrive
@@ -316,17 +370,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 PV_TR(0, itp, 0);
                 for (int kb = 0; kb < kbt; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    if (kb < g.kb0)
-                        tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA0, &full_bar[stage],
-                                    (dir ? g.a0_col[1] : g.a0_col[0]) + kb * BLOCK_K, (dir ? g.a0_slot[1] : g.a0_slot[0]), m_blk * BLOCK_M);
-                    else
-                        tma_load_3d(smem_a + stage * A_STAGE_BYTES, &tmA1, &full_bar[stage],
-                                    (dir ? g.a1_col[1] : g.a1_col[0]) + (kb - g.kb0) * BLOCK_K, (dir ? g.a1_slot[1] : g.a1_slot[0]) + ti.slot, m_blk * BLOCK_M);
+                    const bool from_a0 = kb < g.kb0;
+                    const CUtensorMap* tmA = from_a0 ? &tmA0 : &tmA1;
+                    const int a_col = from_a0 ? (dir ? g.a0_col[1] : g.a0_col[0]) + kb * BLOCK_K : (dir ? g.a1_col[1] : g.a1_col[0]) + (kb - g.kb0) * BLOCK_K;
+                    const int a_slot = from_a0 ? (dir ? g.a0_slot[1] : g.a0_slot[0]) : (dir ? g.a1_slot[1] : g.a1_slot[0]) + ti.slot;
                     // W columns: A0's k blocks first, then A1's (the host packs [W_hh | W_ih] that way)
-                    // this CTA's slice of the W tile, multicast to every CTA of the cluster
-                    tma_load_2d_mc(smem_w + stage * W_STAGE_BYTES + crank * W_SLICE_ROWS * BLOCK_K * 2, &tmW, &full_bar[stage],
-                                   (g.w_kb_off + kb) * BLOCK_K, (dir ? g.w_row[1] : g.w_row[0]) + n_blk * BLOCK_N + crank * W_SLICE_ROWS, kMask);
+                    const int w_col = (g.w_kb_off + kb) * BLOCK_K, w_row = (dir ? g.w_row[1] : g.w_row[0]) + n_blk * BLOCK_N + crank * W_SLICE_ROWS;
+                    if constexpr (TWO_CTA) {
+                        // both CTAs' bytes complete on the leader's barrier; this CTA's half of the W tile stays here
+                        if (crank == 0) mbar_expect_tx(&full_bar[stage], CLUSTER * (A_STAGE_BYTES + W_BYTES_PER_CTA));
+                        tma_load_3d_2sm(smem_a + stage * A_STAGE_BYTES, tmA, &full_bar[stage], a_col, a_slot, m_blk * BLOCK_M);
+                        tma_load_2d_2sm(smem_w + stage * W_STAGE_BYTES, &tmW, &full_bar[stage], w_col, w_row);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_3d(smem_a + stage * A_STAGE_BYTES, tmA, &full_bar[stage], a_col, a_slot, m_blk * BLOCK_M);
+                        // this CTA's slice of the W tile, multicast to every CTA of the cluster
+                        tma_load_2d_mc(smem_w + stage * W_STAGE_BYTES + crank * W_SLICE_ROWS * BLOCK_K * 2, &tmW, &full_bar[stage], w_col, w_row, kMask);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 PV_TR(0, itp, 1);
@@ -334,8 +394,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+        if (lane == 0 && (!TWO_CTA || crank == 0)) {
+            constexpr uint32_t idesc = make_idesc(TWO_CTA ? CLUSTER * BLOCK_M : BLOCK_M, BLOCK_N);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
                 const int acc = it & 1;
@@ -351,13 +411,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_w + stage * W_STAGE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; k++)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16),
-                                  idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_mc(&empty_bar[stage], kMask);  // tells every CTA of the cluster this consumer is done with the stage
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                        if constexpr (TWO_CTA)
+                            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16),
+                                          idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    // tells every CTA of the cluster this consumer is done with the stage
+                    if constexpr (TWO_CTA) umma_commit_mc_2sm(&empty_bar[stage], kMask); else umma_commit_mc(&empty_bar[stage], kMask);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                  // accumulator complete
+                // accumulator complete (TWO_CTA: in both CTAs' tensor memory, announced to both epilogues)
+                if constexpr (TWO_CTA) umma_commit_mc_2sm(&tfull_bar[acc], kMask); else umma_commit(&tfull_bar[acc]);
                 PV_TR(1, it, 2);
             }
         }
@@ -408,14 +475,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             if (te == 0) PV_TR(2, it, 3);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (TWO_CTA) { if (crank == 0) mbar_arrive(&tempty_bar[acc]); else mbar_arrive_cluster(&tempty_bar[acc], 0); }
+                else mbar_arrive(&tempty_bar[acc]);
+            }
         }
         cp_async_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                        // no CTA leaves while a peer may still multicast into it
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (warp == 2) {
+        tc_fence_after();
+        if constexpr (TWO_CTA) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 }  // namespace tc
