@@ -65,6 +65,16 @@ void prof_begin(int fam, cudaStream_t stream) {
     g_prof_open.push_back(r);
 }
 
+bool prof_enabled() {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    return g_prof_on;
+}
+
+void count_launches(int fam, int launches) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    g_launches[fam] += launches;
+}
+
 void prof_end(int fam, cudaStream_t stream, int launches) {
     std::lock_guard<std::mutex> l(g_prof_mu);
     g_launches[fam] += launches;

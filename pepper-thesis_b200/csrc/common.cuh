@@ -32,6 +32,8 @@ enum Family { FAM_SUM_PREFIX = 0, FAM_SUM_TILE, FAM_SUM_ALLELE, FAM_SUM_SORT, FA
 // brackets `launches` kernel launches of one family on `stream`; records events only while profiling is enabled
 void prof_begin(int fam, cudaStream_t stream);
 void prof_end(int fam, cudaStream_t stream, int launches);
+bool prof_enabled();                                  // per-family timing is on (pv_profile_enable)
+void count_launches(int fam, int launches);           // launches that did not pass through prof_end (graph replays)
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

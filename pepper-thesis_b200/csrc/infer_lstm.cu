@@ -270,6 +270,11 @@ struct PvLstmModel {
     void* ws; int64_t ws_bytes;
     int16_t* win_dev; float* probs_dev; uint8_t* arg_dev; int64_t io_cap;
     cudaStream_t stream;
+    // small batches (the reference calls the model on 512 windows at a time): the 72 launches of a pass replayed as one CUDA graph
+    struct GraphEntry { void* ws; int64_t ws_bytes; int64_t n; int32_t wrap; int32_t uses; cudaGraphExec_t exec; };
+    GraphEntry graphs[8];
+    int n_graphs;
+    cudaStream_t capture_stream;
 };
 
 namespace {
@@ -277,8 +282,10 @@ namespace {
 struct Ws {
     __nv_bfloat16 *xhl, *enc_out, *dec_out, *act0, *act1;
     float* c_state;
+    int16_t* win_stage; float* probs_stage; uint8_t* arg_stage;   // fixed addresses for the graph of a small pass
     int64_t bytes;
 };
+constexpr int64_t GRAPH_MAX_WINDOWS = 4096;
 
 Ws carve_ws(void* base, int64_t size, int64_t chunk) {
     pv::Arena a(base, size);
@@ -289,6 +296,10 @@ Ws carve_ws(void* base, int64_t size, int64_t chunk) {
     w.act0 = a.take<__nv_bfloat16>(chunk * LIN);
     w.act1 = a.take<__nv_bfloat16>(chunk * LIN);
     w.c_state = a.take<float>(((chunk + 127) / 128 * 128) * 2 * H);
+    const int64_t stage = chunk < GRAPH_MAX_WINDOWS ? chunk : GRAPH_MAX_WINDOWS;
+    w.win_stage = a.take<int16_t>(stage * T * F);
+    w.probs_stage = a.take<float>(stage * 3);
+    w.arg_stage = a.take<uint8_t>(stage);
     w.bytes = pv::align_up(a.cur, 256);
     return w;
 }
@@ -364,6 +375,8 @@ extern "C" void pv_lstm_destroy(PvLstmModel* m) {
     if (m->probs_dev) cudaFree(m->probs_dev);
     if (m->arg_dev) cudaFree(m->arg_dev);
     if (m->stream) cudaStreamDestroy(m->stream);
+    for (int i = 0; i < m->n_graphs; i++) if (m->graphs[i].exec) cudaGraphExecDestroy(m->graphs[i].exec);
+    if (m->capture_stream) cudaStreamDestroy(m->capture_stream);
     delete m;
 }
 
@@ -371,11 +384,71 @@ extern "C" int64_t pv_lstm_workspace_bytes(int64_t max_windows) {
     return carve_ws(nullptr, 0, chunk_for(max_windows)).bytes;
 }
 
+namespace {
+int lstm_run(PvLstmModel* m, const int16_t* windows, int64_t n, int32_t wrap_int8, float* probs, uint8_t* argmax, void* workspace,
+             int64_t workspace_bytes, cudaStream_t st);
+}
+
 extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, int32_t wrap_int8, float* probs,
                              uint8_t* argmax, void* workspace, int64_t workspace_bytes, void* stream_) {
     if (!m || !windows || !probs || !workspace) return pv::set_error(PV_EINVAL, "null argument");
     if (n <= 0) return PV_OK;
     cudaStream_t st = (cudaStream_t)stream_;
+    static int use_graph = -1;
+    if (use_graph < 0) { const char* v = getenv("PV_LSTM_GRAPH"); use_graph = (v && !atoi(v)) ? 0 : 1; }
+    if (!use_graph || n > GRAPH_MAX_WINDOWS || pv::prof_enabled())
+        return lstm_run(m, windows, n, wrap_int8, probs, argmax, workspace, workspace_bytes, st);
+    // A small pass is 72 dependent launches of a few microseconds each. The second time a (workspace, n) pair is seen the
+    // launches are captured -- reading and writing fixed staging slots of the workspace -- and from then on one graph launch
+    // between two small device copies replaces them.
+    const int64_t chunk = chunk_for(n);
+    const Ws w = carve_ws(workspace, workspace_bytes, chunk);
+    if (w.bytes > workspace_bytes) return lstm_run(m, windows, n, wrap_int8, probs, argmax, workspace, workspace_bytes, st);
+    PvLstmModel::GraphEntry* e = nullptr;
+    for (int i = 0; i < m->n_graphs; i++)
+        if (m->graphs[i].ws == workspace && m->graphs[i].ws_bytes == workspace_bytes && m->graphs[i].n == n && m->graphs[i].wrap == wrap_int8) e = &m->graphs[i];
+    if (!e) {
+        if (m->n_graphs == 8) {                                  // full: forget the oldest
+            if (m->graphs[0].exec) cudaGraphExecDestroy(m->graphs[0].exec);
+            for (int i = 1; i < 8; i++) m->graphs[i - 1] = m->graphs[i];
+            m->n_graphs = 7;
+        }
+        e = &m->graphs[m->n_graphs++];
+        e->ws = workspace; e->ws_bytes = workspace_bytes; e->n = n; e->wrap = wrap_int8; e->uses = 0; e->exec = nullptr;
+    }
+    if (!e->exec && e->uses++ == 0)                              // first sight: plain launches (also sets the kernels' attributes)
+        return lstm_run(m, windows, n, wrap_int8, probs, argmax, workspace, workspace_bytes, st);
+    if (!e->exec) {
+        if (!m->capture_stream) PV_CUDA_CHECK(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        PV_CUDA_CHECK(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = lstm_run(m, w.win_stage, n, wrap_int8, w.probs_stage, w.arg_stage, workspace, workspace_bytes, m->capture_stream);
+        const cudaError_t ce = cudaStreamEndCapture(m->capture_stream, &graph);
+        if (rc != PV_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            e->uses = -1000000;                                  // do not try again for this pair
+            return lstm_run(m, windows, n, wrap_int8, probs, argmax, workspace, workspace_bytes, st);
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            e->exec = nullptr; e->uses = -1000000; cudaGetLastError();
+            return lstm_run(m, windows, n, wrap_int8, probs, argmax, workspace, workspace_bytes, st);
+        }
+    }
+    PV_CUDA_CHECK(cudaMemcpyAsync(w.win_stage, windows, (size_t)n * T * F * 2, cudaMemcpyDeviceToDevice, st));
+    PV_CUDA_CHECK(cudaGraphLaunch(e->exec, st));
+    PV_CUDA_CHECK(cudaMemcpyAsync(probs, w.probs_stage, (size_t)n * 12, cudaMemcpyDeviceToDevice, st));
+    if (argmax) PV_CUDA_CHECK(cudaMemcpyAsync(argmax, w.arg_stage, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    pv::count_launches(pv::FAM_LSTM_PREP, 1); pv::count_launches(pv::FAM_LSTM_ENC, T); pv::count_launches(pv::FAM_LSTM_DEC, T);
+    pv::count_launches(pv::FAM_LSTM_MLP, 6);
+    return PV_OK;
+}
+
+namespace {
+int lstm_run(PvLstmModel* m, const int16_t* windows, int64_t n, int32_t wrap_int8, float* probs, uint8_t* argmax, void* workspace,
+             int64_t workspace_bytes, cudaStream_t st) {
     // the largest chunk the workspace can hold
     int64_t chunk = chunk_for(n);
     while (chunk > 128 && carve_ws(nullptr, 0, chunk).bytes > workspace_bytes) chunk -= 128;
@@ -461,6 +534,7 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
     }
     return PV_OK;
 }
+}  // namespace
 
 extern "C" int pv_lstm_infer_host(PvLstmModel* m, const int16_t* windows_host, int64_t n, int32_t wrap_int8,
                                   float* probs_host, uint8_t* argmax_host) {

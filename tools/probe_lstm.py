@@ -8,7 +8,7 @@ m = models.TransducerGRU().load_state_dict(models.random_variant_state_dict(0))
 x = (-torch.randint(0, 50, (n, 33, 26))).to(torch.int16).cuda()
 m.infer_windows(x); torch.cuda.synchronize()
 lib = capi.load()
-for it in range(3):
+for it in range(int(os.environ.get("PV_PROBE_ITERS", "3"))):
     lib.pv_profile_reset(); lib.pv_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); m.infer_windows(x); e1.record(); torch.cuda.synchronize()
