@@ -98,3 +98,49 @@ def test_kernel_bound_host_mode_and_quality_predicates_do_not_change_results():
     from pepper_thesis_b200 import capi
     with pytest.raises(capi.PvError):
         hp3.run_host(q)
+
+
+def test_full_size_properties_64mbp_50x():
+    """BASELINE.json configs[1] at its full size (64 Mbp, 50x ONT R9: 640 regions, ~3 G read bases) through properties that do not
+    need the oracle on every base: (1) seven regions drawn across the contig are bit-exact against the compiled reference /
+    port, window for window; (2) groups of 160 regions and groups of 37 regions give the same records (a checksum of every
+    output array); (3) a second run gives the same bytes (the kernels' atomics are order-free); (4) records are ordered by
+    (region, position) and every genotype carries the largest probability."""
+    import hashlib
+    b = synth.generate("ont_r9", 64000000, 50.0, seed=7, threads=16)
+    assert b.n_regions == 640
+    thr = synth.PROFILES["ont_r9"].thresholds
+    hp160, _ = _hot_path("ont_r9", wrap=True, group=160)
+    hp37, _ = _hot_path("ont_r9", wrap=True, group=37)
+
+    def digest(p):
+        h = hashlib.sha256()
+        for a in (p.region, p.position, p.depth, p.frequency, p.allele, p.allele_len, p.genotype):
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.hexdigest()
+    a = hp160.run_host(b)
+    c = hp37.run_host(b)
+    a2 = hp160.run_host(b)
+    assert len(a) > 60000
+    assert digest(a) == digest(c) == digest(a2)
+    assert np.array_equal(a.probs, a2.probs) and np.abs(a.probs - c.probs).max() < 1e-6
+    key = a.region.astype(np.int64) * (1 << 32) + a.position
+    assert (np.diff(key) >= 0).all()
+    # the genotype is taken on the logits: its probability is the largest one (two logits closer than float32's softmax can
+    # tell apart give equal probabilities, where numpy's argmax would name the first)
+    assert np.array_equal(a.probs[np.arange(len(a)), a.genotype], a.probs.max(-1))
+    assert (a.genotype != a.probs.argmax(-1)).mean() < 1e-3
+    # windows and records of sampled regions against the oracle
+    rng = np.random.default_rng(3)
+    for r in sorted(set([0, 639] + [int(x) for x in rng.integers(1, 639, 5)])):
+        o = O.ref_summary(b, r, thr) if O.have_ref() else O.port_summary(b, r, thr)
+        m = a.region == r
+        assert np.array_equal(a.position[m], np.asarray(o["position"])), r
+        assert [x for x, k in zip(a.alleles(), m) if k] == list(o["alleles"]), r
+        assert np.array_equal(a.depth[m], np.asarray(o["depth"])) and np.array_equal(a.frequency[m], np.asarray(o["frequency"])), r
+        db = dev.DeviceBatch(b.region_range_view(r, r + 1))
+        ws = dev.SummaryWorkspace.for_batch(db, 8192)
+        dev.summary_regions(db, thr, ws)
+        k = int(ws.count.item())
+        assert k == int(m.sum())
+        assert np.array_equal(ws.windows[:k].cpu().numpy().astype(np.int32), np.asarray(o["images"]).astype(np.int32)), r
