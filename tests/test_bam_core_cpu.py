@@ -152,3 +152,35 @@ def test_host_plan_blocks_and_chain_segments(core, files, span):
     n = core.pvt_get_reads(Ub, len(Ub), 0, recs.ctypes.data, len(recs), 0, span[0], span[1], 0, 0, *[x.ctypes.data for x in a])
     want = bam.get_reads_packed("chrS", span[0], span[1], False, 0, 1)
     assert n == want.batch.n_reads and np.array_equal(a[0][:n], want.batch.read_pos)
+
+
+def test_record_helpers_under_sanitizers(tmp_path):
+    """A valid record stream corrupted a few bytes at a time (length fields above all) through the chain / parse / clip / base
+    reads the device kernels perform, in a heap buffer of exactly the stream's size, built with AddressSanitizer +
+    UndefinedBehaviorSanitizer: no read leaves the stream, whatever the fields claim."""
+    rng = np.random.default_rng(8)
+    recs = []
+    for i in range(40):
+        n = int(rng.integers(50, 3000))
+        seq = "".join("ACGTN"[int(x)] for x in rng.choice(5, n, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+        cig, left = [], n
+        if rng.random() < 0.3:
+            s = int(rng.integers(1, 20)); cig.append((4, s)); left -= s
+        while left > 0:
+            op = int(rng.choice([0, 1, 2, 3, 7, 8], p=[0.5, 0.15, 0.15, 0.05, 0.1, 0.05]))
+            l = int(rng.integers(1, 60))
+            if op in (0, 1, 7, 8):
+                l = min(l, left); left -= l
+            cig.append((op, l))
+        tags = b"HPi" + struct.pack("<i", int(rng.integers(0, 3))) if i % 3 == 0 else (b"XZZ" + b"abc\0" + b"HPC\x01" if i % 3 == 1 else b"")
+        recs.append(dict(tid=0, pos=100 + 150 * i, mapq=int(rng.integers(0, 61)), flag=int(rng.choice([0, 16, 2048])), name="read%d" % i,
+                         cigar=cig, seq=seq, qual=list(rng.integers(0, 60, n)), tags=tags))
+    stream = b"".join(bamio.encode_record(r) for r in recs)
+    p = tmp_path / "stream.bin"
+    p.write_bytes(stream)
+    exe = str(tmp_path / "bam_core_fuzz")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I",
+                    os.path.join(ROOT, "pepper-thesis_b200", "csrc"), os.path.join(HERE, "native", "bam_core_fuzz.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe, str(p), "0", "30000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    assert "reads cut" in r.stdout

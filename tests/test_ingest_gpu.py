@@ -117,3 +117,61 @@ def test_polisher_summary_from_device_born_batch(files):
     assert torch.equal(a.image, b.image) and torch.equal(a.genomic_pos, b.genomic_pos)
     ca, cb = a.chunks(), b.chunks()
     assert torch.equal(ca[0], cb[0]) and torch.equal(ca[1], cb[1]) and np.array_equal(ca[2], cb[2]) and np.array_equal(ca[3], cb[3])
+
+
+def _bam_with_patched_record(tmp_path, tag, patch):
+    """A small BAM whose SECOND record is `patch`ed after encoding (a writer that lies about a length field)."""
+    import struct
+    import bamio
+    rng = np.random.default_rng(4)
+    recs = []
+    for i in range(6):
+        n = 400
+        seq = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, n))
+        recs.append(dict(tid=0, pos=100 + 300 * i, mapq=60, flag=0, name="q%d" % i, cigar=[(0, 200), (1, 5), (0, 195)], seq=seq, qual=[30] * n))
+    real = bamio.encode_record
+
+    def enc(rec):
+        b = bytearray(real(rec))
+        if rec["name"] == "q1":
+            patch(b, struct)
+        return bytes(b)
+    bamio.encode_record = enc
+    try:
+        path = str(tmp_path / ("bad_%s.bam" % tag))
+        bamio.write_bam(path, [("chrS", 5000)], recs)
+    finally:
+        bamio.encode_record = real
+    fa = str(tmp_path / ("bad_%s.fa" % tag))
+    bamio.write_fasta(fa, [("chrS", "ACGT" * 1250)])
+    return path, fa
+
+
+@pytest.mark.parametrize("tag", ["n_cigar", "l_seq", "block_small", "block_large", "l_name"])
+def test_lying_length_fields_are_refused_on_the_device(tmp_path, tag):
+    """Records whose length fields point outside the record (valid BGZF, valid CRC: only the record parser can notice): the
+    device decode reports them through its status words and the call raises (the same record / clip helpers run under ASan on
+    the CPU in tests/test_bam_core_cpu.py)."""
+    from pepper_thesis_b200 import capi, ingest_gpu
+
+    def patch(b, struct):
+        if tag == "n_cigar":
+            struct.pack_into("<H", b, 4 + 12, 60000)             # 60000 CIGAR ops in a 600-byte record
+        elif tag == "l_seq":
+            struct.pack_into("<i", b, 4 + 16, 1 << 20)           # a megabase of sequence
+        elif tag == "block_small":
+            struct.pack_into("<i", b, 0, 10)                     # shorter than the fixed part
+        elif tag == "block_large":
+            struct.pack_into("<i", b, 0, 1 << 28)                # runs past the stream
+        elif tag == "l_name":
+            b[4 + 8] = 255                                       # the name swallows the CIGAR
+    path, fa = _bam_with_patched_record(tmp_path, tag, patch)
+    bam, fah = ingest.BAMHandler(path), ingest.FASTAHandler(fa)
+    try:
+        got = ingest_gpu.ingest_regions_gpu(bam, fah, "chrS", [0], [4000])
+    except (capi.PvError, RuntimeError):
+        return
+    # a patched field can still describe a record that parses (l_name = 255 inside a long record): then the device must agree
+    # with the host ingest on what it means
+    want = ingest.ingest_regions(bam, fah, "chrS", [0], [4000])
+    _compare(got, want)
