@@ -175,3 +175,34 @@ def test_lying_length_fields_are_refused_on_the_device(tmp_path, tag):
     # with the host ingest on what it means
     want = ingest.ingest_regions(bam, fah, "chrS", [0], [4000])
     _compare(got, want)
+
+
+@pytest.mark.parametrize("preset,cov", [("hifi", 12.0), ("ont_r10", 20.0)])
+def test_other_presets_through_a_written_bam(tmp_path, preset, cov):
+    """HiFi-like (15 kbp reads, few CIGAR ops) and R10-like reads of the synthetic generator written as a BAM (level-1
+    DEFLATE, 64 KiB blocks: the layout of a real file) and decoded both ways: every array of the batch identical, and
+    BAM -> candidates equal to the summary of the generator's own batch (the BAM round trip loses nothing)."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bamio
+    import fast_bam
+    from pepper_thesis_b200 import capi, device as dev, ingest_gpu
+    L = 600000
+    b = synth.generate(preset, L, cov, seed=9, region_size=L, margin=0)
+    bam, fa = str(tmp_path / "p.bam"), str(tmp_path / "p.fa")
+    fast_bam.write_bam_from_batch(bam, b, "chrS", L)
+    bamio.write_fasta(fa, [("chrS", bytes(b.ref[:L]).decode())])
+    bh, fh = ingest.BAMHandler(bam), ingest.FASTAHandler(fa)
+    starts = list(range(0, L, 100000)); ends = [min(L - 1, s + 100000) for s in starts]
+    want = ingest.ingest_regions(bh, fh, "chrS", starts, ends, min_mapq=1)
+    got = ingest_gpu.ingest_regions_gpu(bh, fh, "chrS", starts, ends, min_mapq=1)
+    _compare(got, want)
+    thr = synth.PROFILES[preset].thresholds
+    ws = dev.SummaryWorkspace.for_batch(got.batch, 16384)
+    dev.summary_regions(got.batch, thr, ws)
+    k = int(ws.count.item())
+    d = capi.summary_regions_host(want.batch, thr).trimmed()
+    assert ws.status() == 0 and k == len(d["position"]) > 100
+    assert np.array_equal(ws.position[:k].cpu().numpy(), d["position"]) and np.array_equal(ws.windows[:k].cpu().numpy(), d["images"])
