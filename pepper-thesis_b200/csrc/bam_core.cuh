@@ -5,7 +5,9 @@
 // on a GPU; the product path only calls it from the kernels of ingest_gpu.cu.
 //
 //   inflate_block   RFC 1951 (stored / fixed / dynamic) for ONE BGZF payload of <= 64 KiB, canonical Huffman decoding
-//                   with a 9-bit first-level table per code and a bit-serial walk for longer codes; ~2 KB of state
+//                   with a 9-bit first-level table per code and a bit-serial walk for longer codes; ~2 KB of state.
+//                   The single-thread form: the first device decoder, now the CPU-testable reference of the
+//                   warp-cooperative inflate_warp.cuh the kernels use
 //   crc32_update    the block's CRC-32 (BGZF trailer), table-driven
 //   parse_record    fixed part + field offsets of a BAM record, long-CIGAR (CG:B,I) convention of SAMv1 4.2.2
 //   clip_walk       the cut of one record to [start, stop] of bam_handler.cpp:178-306 in closed form per op

@@ -2,7 +2,7 @@
 
 The host reads the compressed bytes a BAI query names into page-locked memory and walks the BGZF block headers
 (``pv_bam_plan*`` of libpv_ingest.so); the bytes go up once, and kernels of libpepper_b200.so (csrc/ingest_gpu.cu) inflate
-every BGZF block (one thread per block), find the record boundaries, apply ``BAM_handler::get_reads``
+every BGZF block (one warp per block, csrc/inflate_warp.cuh), find the record boundaries, apply ``BAM_handler::get_reads``
 (/root/reference/pepper_variant/modules/cpp/bam_handler.cpp:115-451: flag / mapq filters, the cut of every read to its
 region +- 100 bases, HP tag) and write the ``PvReadBatch`` arrays in HBM -- the summary kernels start from there, no read
 byte ever exists on the host in decoded form. Bit-identical to :func:`ingest.ingest_regions` (tests/test_ingest_gpu.py).

@@ -1,7 +1,9 @@
 """The __host__ __device__ core of the GPU ingest (pepper-thesis_b200/csrc/bam_core.cuh) run on the CPU through a small
 harness (tests/native/bam_core_host.cpp, built here with g++): its DEFLATE decoder against zlib, its CRC-32 against
 zlib's, and its record parsing + get_reads clipping against the CPU ingest (which tests/test_ingest.py pins to the compiled
-reference bam_handler.cpp). The GPU kernels (ingest_gpu.cu) call exactly these functions, one thread per block / record."""
+reference bam_handler.cpp). The GPU kernels (ingest_gpu.cu) call exactly these record / clip functions, one thread or warp per
+record; the device's DEFLATE decoder is the warp-cooperative one of inflate_warp.cuh (tests/test_inflate_gpu.py), of which
+inflate_block here is the single-thread reference form."""
 import ctypes as C
 import gzip
 import os
