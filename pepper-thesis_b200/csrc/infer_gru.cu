@@ -95,9 +95,20 @@ constexpr int RC_THREADS = 128 + RC_EPI_WARPS * 32;            // 4 control warp
 constexpr int RC_W_BYTES = GN3 * GH * 2;                       // 98304: two k blocks of [384 rows][128 B]
 constexpr int RC_A_BYTES = 128 * GH * 2;                       // 32768: two k blocks of [128 rows][128 B]
 constexpr int RC_SMEM = RC_W_BYTES + RC_A_BYTES + 2 * GX_HALF_BYTES + GH * 4 + 128 + 1024;
+// FOLD variant (layer 1, 10 input features): no gx stream. The x-part of the r and z gates rides on the MMA (a third k atom:
+// A = [h | x x 0], B = [W_hh | W_ir,iz hi lo]), the x-part of the candidate gate (which PyTorch keeps outside r * (...)) is 160
+// FMAs per thread and half step on fp32 W_in; x_t arrives as 16 bytes per window through a four-slot ring.
+constexpr int RCF_XSLOTS = 4;
+constexpr int RCF_X_BYTES = 128 * 16;                          // one step: 128 windows x (10 counts + 6 zero bytes)
+constexpr int RCF_W_BYTES = RC_W_BYTES + GN3 * 128;            // + the x atom of the B operand
+constexpr int RCF_A_BYTES = RC_A_BYTES + 128 * 128;            // + the x atom of the A operand
+constexpr int RCF_SMEM = RCF_W_BYTES + RCF_A_BYTES + RCF_XSLOTS * RCF_X_BYTES + GH * 4 + 3 * GH * 4 + GF * GH * 4 + 128 + 1024;
 
 struct RecurParams {
-    const uint8_t* gx;        // gx layout above
+    const uint8_t* gx;        // gx layout above (not FOLD)
+    const uint8_t* xt;        // FOLD: [m_blk][T][128 rows][16] counts of x_t
+    const float* bias;        // FOLD: [2][3][128] b_ir + b_hr, b_iz + b_hz, b_in
+    const float* w_in;        // FOLD: [2][10][128] fp32 W_in (candidate gate, input part)
     const float* b_hn;        // [2][128]
     float* h_state;           // [M][2][128] fp32: h_0 in, h_T out
     __nv_bfloat16* out;       // [M][S][256]: h_t -> slot t + 1, channels dir*128 ..
@@ -111,22 +122,26 @@ struct RecurParams {
 #define GRU_TR(step, ev) do { } while (0)
 #endif
 
+template <bool FOLD>
 __global__ void __launch_bounds__(RC_THREADS, 1)
 gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, box 64 x 128 rows */,
+                 const __grid_constant__ CUtensorMap tmWx /* FOLD: [2*384][64] bf16 input weights of r, z (hi | lo), box 64 x 128 rows */,
                  const __grid_constant__ CUtensorMap tmOut /* [rows][S][256] bf16, box 64 x 1 x 128 rows */, const RecurParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_w = smem;
-    uint8_t* smem_a = smem + RC_W_BYTES;
-    uint8_t* smem_gx = smem_a + RC_A_BYTES;
-    float* s_bhn = (float*)(smem_gx + 2 * GX_HALF_BYTES);
-    uint64_t* bars = (uint64_t*)(s_bhn + GH);
+    uint8_t* smem_a = smem + (FOLD ? RCF_W_BYTES : RC_W_BYTES);
+    uint8_t* smem_gx = smem_a + (FOLD ? RCF_A_BYTES : RC_A_BYTES);     // FOLD: the x ring
+    float* s_bhn = (float*)(smem_gx + (FOLD ? RCF_XSLOTS * RCF_X_BYTES : 2 * GX_HALF_BYTES));
+    float* s_bias = s_bhn + GH;                                        // FOLD only: [3][128]
+    float* s_win = s_bias + (FOLD ? 3 * GH : 0);                       // FOLD only: [10][128]
+    uint64_t* bars = (uint64_t*)(s_win + (FOLD ? GF * GH : 0));
     uint64_t* w_bar = bars;            // W_hh landed
     uint64_t* h_ready = bars + 1;      // h_{t-1} operand written, accumulators drained (16 warp arrivals)
     uint64_t* acc_full = bars + 2;     // [2] accumulators of a column half complete
-    uint64_t* gx_full = bars + 4;      // [2]
-    uint64_t* gx_empty = bars + 6;     // [2] (16 warp arrivals)
-    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+    uint64_t* gx_full = bars + 4;      // [2]; FOLD: x_full[4]
+    uint64_t* gx_empty = bars + 8;     // [2] (16 warp arrivals); FOLD: x_empty[4]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = (int)blockIdx.x >> 1, dir = (int)blockIdx.x & 1;
@@ -136,11 +151,18 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
     if (warp == 1 && lane == 0) {
         tc::mbar_init(w_bar, 1);
         tc::mbar_init(h_ready, RC_EPI_WARPS);
-        for (int i = 0; i < 2; i++) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&gx_full[i], 1); tc::mbar_init(&gx_empty[i], RC_EPI_WARPS); }
+        for (int i = 0; i < 2; i++) tc::mbar_init(&acc_full[i], 1);
+        for (int i = 0; i < (FOLD ? RCF_XSLOTS : 2); i++) { tc::mbar_init(&gx_full[i], 1); tc::mbar_init(&gx_empty[i], RC_EPI_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(tmem_slot, tc::TMEM_COLS);
-    if (warp == 3) for (int i = lane; i < GH; i += 32) s_bhn[i] = p.b_hn[dir * GH + i];
+    if (warp == 3) {
+        for (int i = lane; i < GH; i += 32) s_bhn[i] = p.b_hn[dir * GH + i];
+        if constexpr (FOLD) {
+            for (int i = lane; i < 3 * GH; i += 32) s_bias[i] = p.bias[dir * 3 * GH + i];
+            for (int i = lane; i < GF * GH; i += 32) s_win[i] = p.w_in[dir * GF * GH + i];
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -149,12 +171,21 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
     if (warp == 0) {
         // ===== loads: W_hh once, then the gx ring =====
         if (lane == 0) {
-            tc::mbar_expect_tx(w_bar, RC_W_BYTES);
+            tc::mbar_expect_tx(w_bar, FOLD ? RCF_W_BYTES : RC_W_BYTES);
             for (int kb = 0; kb < 2; kb++)
                 for (int rb = 0; rb < 3; rb++)
                     tc::tma_load_2d(smem_w + kb * (GN3 * 128) + rb * (128 * 128), &tmW, w_bar, kb * 64, dir * GN3 + rb * 128);
+            if constexpr (FOLD)
+                for (int rb = 0; rb < 3; rb++)
+                    tc::tma_load_2d(smem_w + 2 * (GN3 * 128) + rb * (128 * 128), &tmWx, w_bar, 0, dir * GN3 + rb * 128);
             for (int s = 0; s < T; s++) {
                 const int t = dir ? T - 1 - s : s;
+                if constexpr (FOLD) {
+                    const int slot = s & (RCF_XSLOTS - 1);
+                    tc::mbar_wait(&gx_empty[slot], (uint32_t)((s / RCF_XSLOTS) & 1) ^ 1u);
+                    tc::mbar_expect_tx(&gx_full[slot], RCF_X_BYTES);
+                    tc::bulk_load(smem_gx + slot * RCF_X_BYTES, p.xt + ((size_t)m_blk * T + t) * RCF_X_BYTES, RCF_X_BYTES, &gx_full[slot]);
+                } else
                 for (int hf = 0; hf < 2; hf++) {
                     tc::mbar_wait(&gx_empty[hf], (uint32_t)(s & 1) ^ 1u);
                     tc::mbar_expect_tx(&gx_full[hf], GX_HALF_BYTES);
@@ -170,9 +201,9 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc(128, 192);
-            uint64_t adesc[2], bdesc[2][2];
+            uint64_t adesc[3], bdesc[2][3];
 #pragma unroll
-            for (int kb = 0; kb < 2; kb++) {
+            for (int kb = 0; kb < 3; kb++) {
                 adesc[kb] = tc::make_smem_desc(tc::smem_u32(smem_a + kb * (128 * 128)));
 #pragma unroll
                 for (int hf = 0; hf < 2; hf++)
@@ -193,6 +224,11 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                             for (int k = 0; k < 4; k++)
                                 tc::umma_bf16(tmem_base + (uint32_t)(hf * 192), adesc[kb] + (uint64_t)(k * 2), bdesc[hf][kb] + (uint64_t)(k * 2),
                                               idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (FOLD) {                  // x atom: columns 0..31 = [x | x | 0] against [W hi | W lo | 0]
+#pragma unroll
+                            for (int k = 0; k < 2; k++)
+                                tc::umma_bf16(tmem_base + (uint32_t)(hf * 192), adesc[2] + (uint64_t)(k * 2), bdesc[hf][2] + (uint64_t)(k * 2), idesc, 1u);
+                        }
                     }
                     if (hf == 0) {
                         if (s < T) tc::umma_commit(&acc_full[0]);
@@ -228,6 +264,33 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
         const uint32_t sw0 = (uint32_t)(((2 * gq) ^ (r & 7)) << 4), sw1 = (uint32_t)(((2 * gq + 1) ^ (r & 7)) << 4);
         const uint32_t gx_thr = tc::smem_u32(smem_gx) + (uint32_t)((gq * 256 + r) * 16);   // + half, gate * 16384, sub * 2048
         const uint32_t bhn_thr = tc::smem_u32(s_bhn) + (uint32_t)(gq * 64);                // + half * 256
+        // FOLD: this row's 16 count bytes in an x ring slot; its 16-byte chunk gq of the x atom of the A operand
+        // (columns 8 gq .. 8 gq + 7 of [x0..x9 | x0..x9 | 0 ...]); biases / W_in of this thread's 16 units (+ half * 256)
+        const uint32_t x_thr = tc::smem_u32(smem_gx) + (uint32_t)(r * 16);
+        const uint32_t xa_thr = a_row + 2 * (128 * 128) + (uint32_t)((gq ^ (r & 7)) << 4);
+        const uint32_t bias_thr = tc::smem_u32(s_bias) + (uint32_t)(gq * 64);
+        const uint32_t win_thr = tc::smem_u32(s_win) + (uint32_t)(gq * 64);
+        auto write_x_atom = [&](int step) {                      // x of `step` -> bf16 chunk of the A operand
+            const int slot = step & (RCF_XSLOTS - 1);
+            if (lane == 0) tc::mbar_wait(&gx_full[slot], (uint32_t)((step / RCF_XSLOTS) & 1));
+            __syncwarp();
+            const uint4 xv = tc::lds128(x_thr + slot * RCF_X_BYTES);
+            uint32_t hp[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                float v[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = 8 * gq + e + u;                // column of the atom
+                    const int idx = j < GF ? j : j - GF;         // which count
+                    const uint32_t wsel = idx < 4 ? xv.x : idx < 8 ? xv.y : xv.z;
+                    v[u] = j < 2 * GF ? (float)((wsel >> (8 * (idx & 3))) & 0xffu) : 0.f;
+                }
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+                hp[e >> 1] = *(const uint32_t*)&h2;
+            }
+            tc::sts128(xa_thr, make_uint4(hp[0], hp[1], hp[2], hp[3]));
+        };
 
         // h_0: fp32 state -> TMEM columns 384.., bf16 -> A tile
 #pragma unroll
@@ -245,6 +308,7 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
             tc::sts128(a_row + hf * (128 * 128) + sw0, make_uint4(hp[0], hp[1], hp[2], hp[3]));
             tc::sts128(a_row + hf * (128 * 128) + sw1, make_uint4(hp[4], hp[5], hp[6], hp[7]));
         }
+        if constexpr (FOLD) write_x_atom(0);
         tc::tmem_st_wait();
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -259,7 +323,7 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                 if (lane == 0) {
                     tc::mbar_wait(&acc_full[hf], ph);
                     if (warp == 4) GRU_TR(s, 4 + hf * 4);
-                    tc::mbar_wait(&gx_full[hf], ph);
+                    if constexpr (!FOLD) tc::mbar_wait(&gx_full[hf], ph);   // FOLD: x_t's slot was awaited when its atom was written
                     if (warp == 4) GRU_TR(s, 5 + hf * 4);
                 }
                 __syncwarp();
@@ -270,8 +334,6 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                 tc::tmem_ld16(tlane + hf * 192 + 2 * 64 + gq * 16, an);
                 const uint32_t gxa = gx_thr + hf * GX_HALF_BYTES;
                 uint4 g4[4];
-                g4[0] = tc::lds128(gxa); g4[1] = tc::lds128(gxa + 2048);
-                g4[2] = tc::lds128(gxa + 2 * 16384); g4[3] = tc::lds128(gxa + 2 * 16384 + 2048);
                 float bh[16];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -279,6 +341,64 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                     bh[4 * i] = __uint_as_float(v.x); bh[4 * i + 1] = __uint_as_float(v.y);
                     bh[4 * i + 2] = __uint_as_float(v.z); bh[4 * i + 3] = __uint_as_float(v.w);
                 }
+                float az[16], h[16];
+                uint32_t hp[8];
+                if constexpr (FOLD) {
+                    // the accumulators already hold W_h h + W_i x for r and z; the candidate's input part is computed here
+                    const uint4 xv = tc::lds128(x_thr + (s & (RCF_XSLOTS - 1)) * RCF_X_BYTES);
+                    float xf[GF];
+#pragma unroll
+                    for (int f = 0; f < GF; f++) xf[f] = (float)(((f < 4 ? xv.x : f < 8 ? xv.y : xv.z) >> (8 * (f & 3))) & 0xffu);
+                    float nx[16];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint4 v = tc::lds128(bias_thr + 2 * GH * 4 + hf * 256 + i * 16);       // b_in
+                        nx[4 * i] = __uint_as_float(v.x); nx[4 * i + 1] = __uint_as_float(v.y);
+                        nx[4 * i + 2] = __uint_as_float(v.z); nx[4 * i + 3] = __uint_as_float(v.w);
+                    }
+#pragma unroll
+                    for (int f = 0; f < GF; f++) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint4 v = tc::lds128(win_thr + f * GH * 4 + hf * 256 + i * 16);
+                            nx[4 * i] = fmaf(__uint_as_float(v.x), xf[f], nx[4 * i]); nx[4 * i + 1] = fmaf(__uint_as_float(v.y), xf[f], nx[4 * i + 1]);
+                            nx[4 * i + 2] = fmaf(__uint_as_float(v.z), xf[f], nx[4 * i + 2]); nx[4 * i + 3] = fmaf(__uint_as_float(v.w), xf[f], nx[4 * i + 3]);
+                        }
+                    }
+                    float br[16];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint4 v = tc::lds128(bias_thr + hf * 256 + i * 16);                    // b_ir + b_hr
+                        br[4 * i] = __uint_as_float(v.x); br[4 * i + 1] = __uint_as_float(v.y);
+                        br[4 * i + 2] = __uint_as_float(v.z); br[4 * i + 3] = __uint_as_float(v.w);
+                    }
+                    tc::tmem_ld_wait();
+                    if (warp == 4 && lane == 0) GRU_TR(s, 6 + hf * 4);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float r0 = sigmoid_f(ar[i] + br[i]);
+                        an[i] = tanh_f(fmaf(r0, an[i] + bh[i], nx[i]));
+                    }
+                    tc::tmem_ld16(tlane + hf * 192 + 1 * 64 + gq * 16, az);
+                    tc::tmem_ld16(tlane + 384 + hf * 64 + gq * 16, h);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint4 v = tc::lds128(bias_thr + GH * 4 + hf * 256 + i * 16);           // b_iz + b_hz
+                        br[4 * i] = __uint_as_float(v.x); br[4 * i + 1] = __uint_as_float(v.y);
+                        br[4 * i + 2] = __uint_as_float(v.z); br[4 * i + 3] = __uint_as_float(v.w);
+                    }
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float z0 = sigmoid_f(az[i] + br[i]), z1 = sigmoid_f(az[i + 1] + br[i + 1]);
+                        h[i] = fmaf(z0, h[i] - an[i], an[i]);          // (1 - z) n + z h
+                        h[i + 1] = fmaf(z1, h[i + 1] - an[i + 1], an[i + 1]);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(h[i], h[i + 1]);
+                        hp[i >> 1] = *(const uint32_t*)&h2;
+                    }
+                } else {
+                g4[0] = tc::lds128(gxa); g4[1] = tc::lds128(gxa + 2048);
+                g4[2] = tc::lds128(gxa + 2 * 16384); g4[3] = tc::lds128(gxa + 2 * 16384 + 2048);
                 tc::tmem_ld_wait();
                 if (warp == 4 && lane == 0) GRU_TR(s, 6 + hf * 4);
                 {
@@ -291,12 +411,10 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                         an[i + 1] = tanh_f(fmaf(r1, an[i + 1] + bh[i + 1], xn.y));
                     }
                 }
-                float az[16], h[16];
                 tc::tmem_ld16(tlane + hf * 192 + 1 * 64 + gq * 16, az);
                 tc::tmem_ld16(tlane + 384 + hf * 64 + gq * 16, h);
                 g4[0] = tc::lds128(gxa + 16384); g4[1] = tc::lds128(gxa + 16384 + 2048);
                 tc::tmem_ld_wait();
-                uint32_t hp[8];
                 {
                     const __half2* gz = (const __half2*)&g4[0];
 #pragma unroll
@@ -309,9 +427,10 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                         hp[i >> 1] = *(const uint32_t*)&h2;
                     }
                 }
+                }
                 __syncwarp();
                 if (warp == 4 && lane == 0) GRU_TR(s, 7 + hf * 4);
-                if (lane == 0) tc::mbar_arrive(&gx_empty[hf]);   // the slot may be refilled with the next step's half
+                if constexpr (!FOLD) { if (lane == 0) tc::mbar_arrive(&gx_empty[hf]); }   // the slot may be refilled with the next step's half
                 tc::tmem_st16(tlane + 384 + hf * 64 + gq * 16, h);
                 if (ok && s == T - 1) {                         // h_T (fp32) back to the caller's hidden buffer
                     float* hg = p.h_state + ((size_t)row * 2 + dir) * GH + hf * 64 + gq * 16;
@@ -328,6 +447,11 @@ gru_recur_kernel(const __grid_constant__ CUtensorMap tmW /* [2*384][128] bf16, b
                     tc::sts128(a_row + sw1, make_uint4(keep[4], keep[5], keep[6], keep[7]));
                     tc::sts128(a_row + 128 * 128 + sw0, make_uint4(hp[0], hp[1], hp[2], hp[3]));
                     tc::sts128(a_row + 128 * 128 + sw1, make_uint4(hp[4], hp[5], hp[6], hp[7]));
+                    if constexpr (FOLD) {
+                        if (s + 1 < T) write_x_atom(s + 1);     // the MMAs of this step have read the x atom too
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&gx_empty[s & (RCF_XSLOTS - 1)]);   // x_t is not needed any more
+                    }
                 }
             }
             tc::tmem_st_wait();
@@ -368,6 +492,22 @@ __global__ void gru_prep_kernel(const uint8_t* __restrict__ img, int64_t row_str
     dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
 #pragma unroll
     for (int k = 3; k < 8; k++) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// FOLD path: x_t as the recurrence streams it: [m_blk][T][128 rows][16 bytes] = the 10 counts of (window, t) + 6 zero bytes;
+// rows behind n are zero. One thread per (row of the padded chunk, t).
+__global__ void gru_pack_x_kernel(const uint8_t* __restrict__ img, int64_t row_stride, int t0, uint8_t* __restrict__ xt, int64_t n,
+                                  int64_t rows_alloc, int T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_alloc * T) return;
+    const int64_t r = i / T; const int t = (int)(i - r * T);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (r < n) {
+        const uint8_t* src = img + r * row_stride + (int64_t)(t0 + t) * GF;
+#pragma unroll
+        for (int f = 0; f < GF; f++) w[f >> 2] |= (uint32_t)src[f] << (8 * (f & 3));
+    }
+    *(uint4*)(xt + (((r >> 7) * T + t) * 128 + (r & 127)) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // dense1 (256 -> 5) per position: one THREAD per (window, t) row -- no cross-lane reduction; the 5 x 256 weights sit in
@@ -439,6 +579,7 @@ struct GruWs {
     __nv_bfloat16 *xin, *enc_out, *dec_out;
     float* h_state;
     uint8_t* gx;
+    uint8_t* xt;              // FOLD path of layer 1
     int64_t bytes;
 };
 
@@ -451,6 +592,7 @@ GruWs gru_carve(void* base, int64_t size, int64_t chunk, int T) {
     w.dec_out = a.take<__nv_bfloat16>(chunk * S * GC);
     w.h_state = a.take<float>(chunk * 2 * GH);
     w.gx = a.take<uint8_t>((chunk / 128) * 2 * (int64_t)T * 2 * GX_HALF_BYTES);
+    w.xt = a.take<uint8_t>((chunk / 128) * (int64_t)T * RCF_X_BYTES);
     w.bytes = pv::align_up(a.cur, 256);
     return w;
 }
@@ -506,6 +648,9 @@ struct PvGruModel {
     __nv_bfloat16 *enc_wih, *dec_wih, *enc_whh, *dec_whh;
     float *enc_b, *dec_b, *enc_bhn, *dec_bhn, *dense_w, *dense_b;
     CUtensorMap map_enc_wih, map_dec_wih, map_enc_whh, map_dec_whh;
+    // FOLD path of layer 1: input weights of r, z in accumulator-column order (hi | lo | 0), fp32 W_in [dir][10][128]
+    __nv_bfloat16* enc_wx; float* enc_win; CUtensorMap map_enc_wx;
+    int fold;
     int sms;
 };
 
@@ -534,7 +679,34 @@ extern "C" int pv_gru_create(const PvGruWeights* hw, PvGruModel** out) {
     if (int rc = make_map2(&m->map_dec_wih, m->dec_wih, 2 * GN3, GC)) return rc;
     if (int rc = make_map2(&m->map_enc_whh, m->enc_whh, 2 * GN3, GH)) return rc;
     if (int rc = make_map2(&m->map_dec_whh, m->dec_whh, 2 * GN3, GH)) return rc;
-    PV_CUDA_CHECK(cudaFuncSetAttribute(gru_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RC_SMEM));
+    {   // layer-1 weights for the FOLD recurrence
+        std::vector<uint16_t> wx((size_t)2 * GN3 * GXK, 0);
+        std::vector<float> win((size_t)2 * GF * GH, 0.f);
+        for (int dir = 0; dir < 2; dir++) {
+            for (int half = 0; half < 2; half++)
+                for (int gate = 0; gate < 2; gate++)           // r, z only: the candidate's rows stay zero
+                    for (int j = 0; j < 64; j++) {
+                        const int src = gate * GH + half * 64 + j;
+                        uint16_t* wr = &wx[((size_t)dir * GN3 + (half * 3 + gate) * 64 + j) * GXK];
+                        for (int k = 0; k < GF; k++) {
+                            const float v = hw->enc_w_ih[dir][(size_t)src * GF + k];
+                            wr[k] = f2bf(v);
+                            wr[GF + k] = f2bf(v - bf2f(wr[k]));
+                        }
+                    }
+            for (int f = 0; f < GF; f++)
+                for (int j = 0; j < GH; j++) win[((size_t)dir * GF + f) * GH + j] = hw->enc_w_ih[dir][(size_t)(2 * GH + j) * GF + f];
+        }
+        if (int rc = upload(&m->enc_wx, wx.data(), wx.size() * 2)) return rc;
+        if (int rc = upload(&m->enc_win, win.data(), win.size() * 4)) return rc;
+        if (int rc = make_map2(&m->map_enc_wx, m->enc_wx, 2 * GN3, GXK)) return rc;
+        // measured (round 2, tools/probe_gru.py): 11.54 vs 11.80 ms at 65536 windows, 2.96 vs 3.01 at 16384, but 1.01 vs 0.78 ms at
+        // 256 (the candidate gate's input part on the CUDA cores lengthens a step from 3.2 to 5.7 us): opt-in, PV_GRU_FOLD=1
+        const char* e = getenv("PV_GRU_FOLD");
+        m->fold = (e && atoi(e)) ? 1 : 0;
+    }
+    PV_CUDA_CHECK(cudaFuncSetAttribute(gru_recur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RC_SMEM));
+    PV_CUDA_CHECK(cudaFuncSetAttribute(gru_recur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RCF_SMEM));
     *out = m;
     return PV_OK;
 }
@@ -543,6 +715,7 @@ extern "C" void pv_gru_destroy(PvGruModel* m) {
     if (!m) return;
     cudaFree(m->enc_wih); cudaFree(m->dec_wih); cudaFree(m->enc_whh); cudaFree(m->dec_whh);
     cudaFree(m->enc_b); cudaFree(m->dec_b); cudaFree(m->enc_bhn); cudaFree(m->dec_bhn); cudaFree(m->dense_w); cudaFree(m->dense_b);
+    cudaFree(m->enc_wx); cudaFree(m->enc_win);
     delete m;
 }
 
@@ -558,12 +731,30 @@ int gru_forward_chunk(PvGruModel* m, const GruWs& w, const CUtensorMap& map_x, c
                       float* h_state, cudaStream_t st) {
     const int S = T + 2;
     const int64_t elems = nb * T;
+    const int m_blks = (int)((nb + 127) / 128);
     pv::prof_begin(pv::FAM_GRU_MISC, st);
-    gru_prep_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(images, img_row_stride, t0, w.xin, nb, T);
+    if (m->fold) {
+        const int64_t rows = (int64_t)m_blks * 128;
+        gru_pack_x_kernel<<<(unsigned)((rows * T + 255) / 256), 256, 0, st>>>(images, img_row_stride, t0, w.xt, nb, rows, T);
+    } else {
+        gru_prep_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(images, img_row_stride, t0, w.xin, nb, T);
+    }
     PV_CUDA_CHECK(cudaGetLastError());
     pv::prof_end(pv::FAM_GRU_MISC, st, 1);
-    const int m_blks = (int)((nb + 127) / 128);
     for (int layer = 0; layer < 2; layer++) {
+        const bool fold = layer == 0 && m->fold;
+        RecurParams rp;
+        memset(&rp, 0, sizeof(rp));
+        if (fold) {
+            // layer 1 without a gx round trip: the recurrence projects its 10-feature input itself
+            rp.xt = w.xt; rp.bias = m->enc_b; rp.w_in = m->enc_win;
+            rp.b_hn = m->enc_bhn; rp.h_state = h_state; rp.out = w.enc_out; rp.M = (int)nb; rp.T = T; rp.S = S; rp.trace = nullptr;
+            pv::prof_begin(pv::FAM_GRU_STEP, st);
+            gru_recur_kernel<true><<<(unsigned)(m_blks * 2), RC_THREADS, RCF_SMEM, st>>>(m->map_enc_whh, m->map_enc_wx, map_enc, rp);
+            PV_CUDA_CHECK(cudaGetLastError());
+            pv::prof_end(pv::FAM_GRU_STEP, st, 1);
+            continue;
+        }
         // gx for every time step and both directions: [nb x T, K_in] x [K_in, 768]
         tc::GemmShape g;
         memset(&g, 0, sizeof(g));
@@ -576,15 +767,15 @@ int gru_forward_chunk(PvGruModel* m, const GruWs& w, const CUtensorMap& map_x, c
         if (int rc = launch_gemm(map_x, layer == 0 ? map_x : map_enc, layer == 0 ? m->map_enc_wih : m->map_dec_wih, g, ge,
                                  m->sms, st)) return rc;
         pv::prof_end(pv::FAM_GRU_GX, st, 1);
-        RecurParams rp;
         rp.gx = w.gx; rp.b_hn = layer == 0 ? m->enc_bhn : m->dec_bhn; rp.h_state = h_state;
         rp.out = layer == 0 ? w.enc_out : w.dec_out; rp.M = (int)nb; rp.T = T; rp.S = S; rp.trace = nullptr;
 #ifdef PV_TRACE
         { static long long* tr = nullptr; if (!tr) { cudaMalloc((void**)&tr, 16 * 16 * 8); cudaMemset(tr, 0, 16 * 16 * 8); } rp.trace = tr; pv_gru_trace_buffer = tr; }
 #endif
         pv::prof_begin(pv::FAM_GRU_STEP, st);
-        gru_recur_kernel<<<(unsigned)(m_blks * 2), RC_THREADS, RC_SMEM, st>>>(layer == 0 ? m->map_enc_whh : m->map_dec_whh,
-                                                                                 layer == 0 ? map_enc : map_dec, rp);
+        gru_recur_kernel<false><<<(unsigned)(m_blks * 2), RC_THREADS, RC_SMEM, st>>>(layer == 0 ? m->map_enc_whh : m->map_dec_whh,
+                                                                                        layer == 0 ? m->map_enc_whh : m->map_dec_whh,
+                                                                                        layer == 0 ? map_enc : map_dec, rp);
         PV_CUDA_CHECK(cudaGetLastError());
         pv::prof_end(pv::FAM_GRU_STEP, st, 1);
     }

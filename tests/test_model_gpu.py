@@ -230,3 +230,22 @@ def test_polisher_chunk_loop():
     agree, raw = _argmax_agreement(acc.cpu().numpy(), racc.numpy(), 2 * TOL)
     assert agree >= 0.9999, (agree, raw)
     assert (labels.cpu().numpy() == acc.cpu().numpy().argmax(-1)).all()
+
+
+def test_polisher_folded_input_projection_variant(monkeypatch):
+    """PV_GRU_FOLD=1: layer 1 without the gx round trip (r / z input parts on the MMA through a third k atom, the candidate's on
+    fp32 FMAs in the epilogue, x_t streamed 16 bytes per window and step): same outputs as the default path within the
+    tolerance both have against the fp32 port."""
+    monkeypatch.setenv("PV_GRU_FOLD", "1")
+    m, sd = _polisher(1)                                        # the variable is read when the model is created
+    monkeypatch.delenv("PV_GRU_FOLD")
+    m0, _ = _polisher(1)
+    for n, T in ((300, 100), (129, 37), (5, 100)):
+        g = torch.Generator().manual_seed(7 * n + T)
+        x = torch.randint(0, 255, (n, T, 10), generator=g)
+        h = torch.randn(n, 2, 128, generator=g) * 0.5
+        la, ha = m(x, h.clone())
+        lb, hb = m0(x, h.clone())
+        rl, rh = MP.polisher_forward(sd, x.float(), h)
+        assert (la - rl).abs().max() < TOL and (ha - rh).abs().max() < TOL
+        assert (la - lb).abs().max() < TOL and (ha - hb).abs().max() < TOL
