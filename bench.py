@@ -565,7 +565,10 @@ def run_ours(args):
     ctx.rank = int(os.environ.get("RANK", "0"))
     ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
     if ctx.world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner appears at NCCL_DEBUG=VERSION / WARN / INFO, so an
+        # inherited setting is dropped for this process (NCCL_DEBUG_FILE keeps it available to whoever wants the log)
+        if not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local))
     torch.cuda.set_device(ctx.local)
     ctx.device = torch.device("cuda", ctx.local)
