@@ -16,6 +16,7 @@
 #include "infer_common.cuh"
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -404,6 +405,8 @@ extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, 
     const int64_t chunk = chunk_for(n);
     const Ws w = carve_ws(workspace, workspace_bytes, chunk);
     if (w.bytes > workspace_bytes) return lstm_run(m, windows, n, wrap_int8, probs, argmax, workspace, workspace_bytes, st);
+    static std::mutex graph_mu;                                  // the cache belongs to the model: one caller at a time edits it
+    std::lock_guard<std::mutex> lock(graph_mu);
     PvLstmModel::GraphEntry* e = nullptr;
     for (int i = 0; i < m->n_graphs; i++)
         if (m->graphs[i].ws == workspace && m->graphs[i].ws_bytes == workspace_bytes && m->graphs[i].n == n && m->graphs[i].wrap == wrap_int8) e = &m->graphs[i];
