@@ -396,6 +396,13 @@ typedef struct PvBamPair {   /* one read of the batch: a record cut to one span 
     int32_t span;
     int32_t n_ops;       /* kept CIGAR ops */
     int64_t n_bases;     /* kept bases */
+    int32_t k_first;     /* first / last kept op of the record's CIGAR: every op between them is kept whole, these two  */
+    int32_t k_last;      /* with the lengths below (clipping can only shorten the ends)                                 */
+    int32_t first_kept;
+    int32_t last_kept;
+    int64_t idx0;        /* read index of the first kept base */
+    int64_t pos_start;   /* type_read.pos */
+    int64_t pos_end;     /* type_read.pos_end */
 } PvBamPair;
 /* One warp per BGZF block (csrc/inflate_warp.cuh), blocks pulled from a ticket by a grid that fills the device once.
  * n_bad_dev[2]: [0] = blocks that did not decode to isize bytes (or, with verify_crc, whose CRC-32 differs from the

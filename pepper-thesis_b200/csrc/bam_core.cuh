@@ -339,6 +339,8 @@ struct Clip {
     int64_t pos_start, pos_end;    // type_read.pos / pos_end
     int64_t idx0;                  // first kept read index (the kept bases are ONE run of read indices)
     int64_t n_bases; int32_t n_ops;
+    int32_t k_first, k_last;       // first / last kept op of the record's CIGAR (every kept op lies between them, whole)
+    int32_t first_kept, last_kept; // kept lengths of those two ops (the only ones a cut can shorten)
     bool bad;                      // the CIGAR walks past SEQ (the reference reads out of bounds there): read dropped
     bool split;                    // the kept bases were not one contiguous run (cannot happen for a well-formed record)
 };
@@ -349,6 +351,7 @@ template <bool WRITE>
 PV_HDN Clip clip_walk(const uint8_t* U, const RecHdr& h, int64_t start, int64_t stop, uint32_t* ops_out) {
     Clip c;
     c.pos_start = -1; c.pos_end = -1; c.idx0 = -1; c.n_bases = 0; c.n_ops = 0; c.bad = false; c.split = false;
+    c.k_first = c.k_last = -1; c.first_kept = c.last_kept = 0;
     int64_t cur_pos = h.pos, cur_idx = 0;
     for (int k = 0; k < h.n_ops; k++) {
         const uint32_t w = ld32(U + h.ops_off + 4 * (int64_t)k);
@@ -394,6 +397,8 @@ PV_HDN Clip clip_walk(const uint8_t* U, const RecHdr& h, int64_t start, int64_t 
                 c.n_bases += kept;
             }
             if (WRITE) ops_out[c.n_ops] = (uint32_t)(kept << 4) | (uint32_t)op;
+            if (c.n_ops == 0) { c.k_first = k; c.first_kept = (int32_t)kept; }
+            c.k_last = k; c.last_kept = (int32_t)kept;
             c.n_ops++;
         }
     }

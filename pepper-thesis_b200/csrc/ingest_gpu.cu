@@ -142,6 +142,8 @@ __global__ void clip_kernel(const ClipArgs a, int64_t* first, PvBamPair* pairs, 
             if (c.bad || c.n_bases == 0) continue;
             if (PAIRS) {
                 PvBamPair p; p.rec_off = a.rec_off[r]; p.span = j; p.n_ops = c.n_ops; p.n_bases = c.n_bases;
+                p.k_first = c.k_first; p.k_last = c.k_last; p.first_kept = c.first_kept; p.last_kept = c.last_kept;
+                p.idx0 = c.idx0; p.pos_start = c.pos_start; p.pos_end = c.pos_end;
                 pairs[at + n] = p;
                 keys[at + n] = ((unsigned long long)j << 32) | (unsigned long long)(at + n);
                 vals[at + n] = (uint32_t)(at + n);
@@ -187,23 +189,41 @@ __global__ void __launch_bounds__(256) write_kernel(const WriteArgs a, int32_t* 
     if (i >= a.n) return;
     const PvBamPair p = a.pairs[i];
     const RecHdr h = parse_record(a.U, p.rec_off, a.u_size);     // every lane (cheap), so that all have the field offsets
-    int64_t idx0 = 0;
-    if (lane == 0) {
-        const Clip c = clip_walk<true>(a.U, h, a.span_start[p.span], a.span_stop[p.span], a.cigar + a.cigar_off[i]);
-        if (c.n_bases != p.n_bases || c.n_ops != p.n_ops || c.bad) atomicOr(status, 16);
-        idx0 = c.idx0;
-        a.read_pos[i] = c.pos_start; a.read_pos_end[i] = c.pos_end;
-        a.read_len[i] = (int32_t)c.n_bases; a.read_n_ops[i] = c.n_ops;
-        a.read_flags[i] = (h.flag & 0x10) ? 1 : 0;
-        a.read_mapq[i] = (uint8_t)h.mapq;
-        a.hp[i] = parse_hp(a.U, h.aux_off, h.rec_end);
-        a.bam_flag[i] = (uint16_t)h.flag;
-        a.name_off[i] = h.name_off;
-        int nl = 0;
-        while (nl < h.l_name && a.U[h.name_off + nl]) nl++;
-        a.name_len[i] = nl;
+    // the kept ops are ops k_first .. k_last of the record, whole except for the two ends (the pairs pass recorded their kept
+    // lengths); ops of other kinds in between (hard clip, pad) drop out: 32 ops per step, compacted by ballot
+    {
+        uint32_t* out_ops = a.cigar + a.cigar_off[i];
+        int written = 0;
+        for (int k0 = p.k_first; k0 <= p.k_last && p.k_first >= 0; k0 += 32) {
+            const int k = k0 + lane;
+            bool keep = false;
+            uint32_t word = 0;
+            if (k <= p.k_last) {
+                const uint32_t w = ld32(a.U + h.ops_off + 4 * (int64_t)k);
+                const int op = (int)(w & 15u);
+                const uint32_t kept = k == p.k_first ? (uint32_t)p.first_kept : k == p.k_last ? (uint32_t)p.last_kept : (w >> 4);
+                keep = kept > 0 && (op == 0 || op == 1 || op == 2 || op == 3 || op == 4 || op == 7 || op == 8);
+                word = (kept << 4) | (uint32_t)op;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) out_ops[written + __popc(m & ((1u << lane) - 1u))] = word;
+            written += __popc(m);
+        }
+        if (lane == 0) {
+            if (written != p.n_ops || p.k_last >= h.n_ops) atomicOr(status, 16);
+            a.read_pos[i] = p.pos_start; a.read_pos_end[i] = p.pos_end;
+            a.read_len[i] = (int32_t)p.n_bases; a.read_n_ops[i] = p.n_ops;
+            a.read_flags[i] = (h.flag & 0x10) ? 1 : 0;
+            a.read_mapq[i] = (uint8_t)h.mapq;
+            a.hp[i] = parse_hp(a.U, h.aux_off, h.rec_end);
+            a.bam_flag[i] = (uint16_t)h.flag;
+            a.name_off[i] = h.name_off;
+            int nl = 0;
+            while (nl < h.l_name && a.U[h.name_off + nl]) nl++;
+            a.name_len[i] = nl;
+        }
     }
-    idx0 = __shfl_sync(0xffffffffu, idx0, 0);
+    const int64_t idx0 = p.idx0;
     const int64_t n = p.n_bases, padded = (n + 15) & ~(int64_t)15, bo = a.base_off[i];
     int mq = 255;
     // four bases per lane and step: nt16 codes -> upper-case ASCII through a 16-byte table held in two registers, qualities

@@ -180,6 +180,7 @@ def _host_stage(bam, fasta, contig, starts, ends, include_supplementary, min_map
 
 
 _COPY_STREAMS = {}
+_PIECE_STREAMS = {}
 
 
 def _copy_stream(dev):
@@ -233,6 +234,7 @@ def _device_stage(h: _HostStage, dev, verify_crc=True, uploaded=None) -> DeviceI
 
     # ---- upload in pieces on a copy stream; the blocks of a piece inflate as soon as its bytes have landed
     copy = _copy_stream(dev)
+    key_dev = (dev.type, torch.cuda.current_device())
     blocks_d = torch.from_numpy(h.blocks.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
     seg_d = torch.from_numpy(h.seg).to(dev, non_blocking=True)
     spans_d = torch.from_numpy(np.stack([span_start, span_stop]) if n_spans else np.zeros((2, 1), np.int64)).to(dev, non_blocking=True)
@@ -257,13 +259,23 @@ def _device_stage(h: _HostStage, dev, verify_crc=True, uploaded=None) -> DeviceI
         bad_d = torch.zeros((pieces, 2), dtype=torch.int32, device=dev)   # per piece: bad blocks, the kernel's ticket
         cut = [0] + [int(h.blocks["c_off"][first[k]]) & ~255 for k in range(1, pieces)] + [min(comp_n, h.comp_host.numel())]
         copy.wait_stream(main)
+        # every piece inflates on a stream of its own: the next piece's warps move into the SMs that the tail of the piece
+        # before leaves idle (a BGZF block takes ~10 ms, so a launch ends in a tail of about that length)
+        side = _PIECE_STREAMS.get(key_dev)
+        if side is None:
+            side = _PIECE_STREAMS[key_dev] = [torch.cuda.Stream(dev) for _ in range(3)]
         for k in range(pieces):
             with torch.cuda.stream(copy):
                 comp[cut[k]:cut[k + 1]].copy_(h.comp_host[cut[k]:cut[k + 1]], non_blocking=True)
-            main.wait_stream(copy)
+            sk = side[k % len(side)]
+            sk.wait_stream(main)                                 # the block table, U
+            sk.wait_stream(copy)                                 # this piece's bytes
             if first[k + 1] > first[k]:
                 capi.check(lib.pv_bam_inflate_blocks(_ptr(comp), comp_bytes, C.c_void_p(blocks_d.data_ptr() + first[k] * bs), first[k + 1] - first[k],
-                                                     _ptr(U), u_bytes, int(bool(verify_crc)), C.c_void_p(bad_d.data_ptr() + 8 * k), st))
+                                                     _ptr(U), u_bytes, int(bool(verify_crc)), C.c_void_p(bad_d.data_ptr() + 8 * k),
+                                                     C.c_void_p(sk.cuda_stream)))
+        for k in range(min(pieces, len(side))):
+            main.wait_stream(side[k])
         ev_copy = torch.cuda.Event()
         ev_copy.record(copy)
         _PINNED.give(h.comp_host, ev_copy)
@@ -301,7 +313,7 @@ def _device_stage(h: _HostStage, dev, verify_crc=True, uploaded=None) -> DeviceI
     _status(flags[1], "record index (fill)")
     mark("clip_count")
     ws = torch.empty(int(lib.pv_bam_clip_workspace_bytes(n_pairs)), dtype=torch.uint8, device=dev)
-    pairs = torch.empty((max(n_pairs, 1), 3), dtype=torch.int64, device=dev)
+    pairs = torch.empty((max(n_pairs, 1), 8), dtype=torch.int64, device=dev)     # PvBamPair: 64 bytes
     base_off = torch.empty(max(n_pairs, 1), dtype=torch.int64, device=dev)
     cigar_off = torch.empty(max(n_pairs, 1), dtype=torch.int64, device=dev)
     read_begin = torch.zeros(n_spans + 1, dtype=torch.int64, device=dev)
@@ -333,7 +345,7 @@ def _device_stage(h: _HostStage, dev, verify_crc=True, uploaded=None) -> DeviceI
         rb_host = np.concatenate([[0], np.cumsum([len(x) for x in keep])]).astype(np.int64)
         read_begin = torch.from_numpy(rb_host).to(dev)
         if n_reads == 0:
-            pairs = torch.empty((1, 3), dtype=torch.int64, device=dev)
+            pairs = torch.empty((1, 8), dtype=torch.int64, device=dev)
 
     def new(n, dt):
         return torch.empty(max(int(n), 1), dtype=dt, device=dev)
