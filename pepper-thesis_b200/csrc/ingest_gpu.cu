@@ -123,24 +123,105 @@ __device__ __forceinline__ int first_span(const ClipArgs& a, int64_t pos) {
     return lo;
 }
 
-// PAIRS: writes the record's pairs at first[r] ...; else counts them into first[r]
+__device__ __forceinline__ int64_t warp_incl_scan(int64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int64_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+__device__ __forceinline__ int64_t warp_sum(int64_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// bam_endpos by the warp: pos + the reference length of the CIGAR (pos + 1 for unmapped / zero-length alignments)
+__device__ int64_t endpos_warp(const uint8_t* U, const RecHdr& h, int lane) {
+    int64_t rlen = 0;
+    for (int k = lane; k < h.n_ops; k += 32) {
+        const uint32_t w = ld32(U + h.ops_off + 4 * (int64_t)k);
+        const int op = (int)(w & 15u);
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += w >> 4;
+    }
+    rlen = warp_sum(rlen);
+    return h.pos + (((h.flag & 4) || rlen == 0) ? 1 : rlen);
+}
+
+// clip_walk<false> (bam_core.cuh) by the warp, 32 ops per step. Until the walk ends every op advances the reference / read
+// position by its whole length, so both are prefix sums; the first match op that keeps a base (k_first) opens the read,
+// from there on every op that is reached (its start <= stop) is kept, clipped at stop at most. The result is uniform.
+__device__ Clip clip_warp(const uint8_t* U, const RecHdr& h, int64_t start, int64_t stop, int lane) {
+    Clip c;
+    c.pos_start = -1; c.pos_end = -1; c.idx0 = -1; c.n_bases = 0; c.n_ops = 0; c.bad = false; c.split = false;
+    c.k_first = c.k_last = -1; c.first_kept = c.last_kept = 0;
+    int64_t cp = h.pos, ci = 0;                                  // positions in front of the step's first op
+    for (int k0 = 0; k0 < h.n_ops; k0 += 32) {
+        if (cp > stop) break;
+        const int k = k0 + lane;
+        uint32_t w = 0;
+        if (k < h.n_ops) w = ld32(U + h.ops_off + 4 * (int64_t)k);
+        const int op = k < h.n_ops ? (int)(w & 15u) : 15;
+        const int64_t len = w >> 4;
+        const bool is_m = op == 0 || op == 7 || op == 8, is_i = op == 1 || op == 4, is_d = op == 2 || op == 3;
+        const int64_t radv = (is_m || is_d) ? len : 0, qadv = (is_m || is_i) ? len : 0;
+        const int64_t rincl = warp_incl_scan(radv, lane), qincl = warp_incl_scan(qadv, lane);
+        const int64_t p0 = cp + rincl - radv, q0 = ci + qincl - qadv;   // where this op starts
+        const bool reached = k < h.n_ops && p0 <= stop;
+        // a match op: bases in front of start are skipped, bases behind stop are cut
+        const int64_t i0 = (is_m && p0 < start) ? (start - p0 < len ? start - p0 : len) : 0;
+        int64_t take = len - i0 < stop - (p0 + i0) + 1 ? len - i0 : stop - (p0 + i0) + 1;
+        if (take < 0) take = 0;
+        if (c.k_first < 0) {
+            const unsigned m = __ballot_sync(0xffffffffu, reached && is_m && take > 0);
+            if (m) {
+                const int src = __ffs(m) - 1;
+                c.k_first = k0 + src;
+                c.pos_start = __shfl_sync(0xffffffffu, p0 + i0, src);
+                c.idx0 = __shfl_sync(0xffffffffu, q0 + i0, src);
+                c.first_kept = (int32_t)__shfl_sync(0xffffffffu, take, src);
+            }
+        }
+        int64_t kept = 0;
+        if (c.k_first >= 0 && reached && k >= c.k_first) {
+            if (is_m) kept = take;
+            else if (is_i) kept = len;
+            else if (is_d) kept = len < stop - p0 + 1 ? len : stop - p0 + 1;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, kept > 0);
+        if (km) {
+            const int last = 31 - __clz(km);
+            c.k_last = k0 + last;
+            c.last_kept = (int32_t)__shfl_sync(0xffffffffu, kept, last);
+            c.n_ops += __popc(km);
+        }
+        c.n_bases += warp_sum((is_m || is_i) ? kept : 0);
+        // where the walk stands behind the step's reached ops
+        const int64_t rsum = warp_sum(reached ? radv : 0);
+        cp += __shfl_sync(0xffffffffu, rincl, 31); ci += __shfl_sync(0xffffffffu, qincl, 31);
+        if (c.k_first >= 0) { const int64_t e = (cp - __shfl_sync(0xffffffffu, rincl, 31)) + rsum; c.pos_end = e < stop + 1 ? e : stop + 1; }
+        if (__ballot_sync(0xffffffffu, k < h.n_ops && !reached)) break;
+    }
+    if (c.k_first >= 0 && c.idx0 + c.n_bases > h.l_seq) c.bad = true;
+    return c;
+}
+
+// PAIRS: writes the record's pairs at first[r] ...; else counts them into first[r]. One warp per record.
 template <bool PAIRS>
-__global__ void clip_kernel(const ClipArgs a, int64_t* first, PvBamPair* pairs, unsigned long long* keys, uint32_t* vals, int32_t* status) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) clip_kernel(const ClipArgs a, int64_t* first, PvBamPair* pairs, unsigned long long* keys, uint32_t* vals, int32_t* status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= a.n_rec) return;
     int64_t n = 0;
     const int64_t at = PAIRS ? first[r] : 0;
-    const RecHdr h = parse_record(a.U, a.rec_off[r], a.u_size);
-    if (!h.ok) atomicOr(status, 4);
+    const RecHdr h = parse_record(a.U, a.rec_off[r], a.u_size);   // every lane: the field offsets
+    if (!h.ok) { if (lane == 0) atomicOr(status, 4); }
     else if (h.tid == a.tid && record_passes(h, a.supp, a.min_mapq)) {
-        const int64_t endpos = record_endpos(a.U, h);
+        const int64_t endpos = endpos_warp(a.U, h, lane);
         for (int j = first_span(a, h.pos); j < a.n_spans && a.span_start[j] < endpos; j++) {
             const int64_t start = a.span_start[j], stop = a.span_stop[j];
             if (h.pos >= stop || endpos <= start) continue;
-            const Clip c = clip_walk<false>(a.U, h, start, stop, nullptr);
-            if (c.split) atomicOr(status, 8);
+            const Clip c = clip_warp(a.U, h, start, stop, lane);
             if (c.bad || c.n_bases == 0) continue;
-            if (PAIRS) {
+            if (PAIRS && lane == 0) {
                 PvBamPair p; p.rec_off = a.rec_off[r]; p.span = j; p.n_ops = c.n_ops; p.n_bases = c.n_bases;
                 p.k_first = c.k_first; p.k_last = c.k_last; p.first_kept = c.first_kept; p.last_kept = c.last_kept;
                 p.idx0 = c.idx0; p.pos_start = c.pos_start; p.pos_end = c.pos_end;
@@ -151,7 +232,7 @@ __global__ void clip_kernel(const ClipArgs a, int64_t* first, PvBamPair* pairs, 
             n++;
         }
     }
-    if (!PAIRS) first[r] = n;
+    if (!PAIRS && lane == 0) first[r] = n;
 }
 
 __global__ void gather_pairs_kernel(const PvBamPair* __restrict__ in, const uint32_t* __restrict__ order, int64_t n, PvBamPair* out,
@@ -376,7 +457,7 @@ extern "C" int pv_bam_clip_count(const uint8_t* inflated_dev, int64_t inflated_b
     const ClipArgs a{inflated_dev, inflated_bytes, rec_off_dev, n_records, tid, span_start_dev, span_stop_dev, n_spans, include_supplementary, min_mapq};
     pv::prof_begin(pv::FAM_INGEST, st);
     int launches = 1;
-    if (n_records > 0) { clip_kernel<false><<<grid_for(n_records, 128), 128, 0, st>>>(a, rec_pair_first_dev, nullptr, nullptr, nullptr, status_dev); launches++; }
+    if (n_records > 0) { clip_kernel<false><<<grid_for(n_records * 32, 256), 256, 0, st>>>(a, rec_pair_first_dev, nullptr, nullptr, nullptr, status_dev); launches++; }
     scan_kernel<<<1, 1024, 0, st>>>(rec_pair_first_dev, n_records);
     pv::prof_end(pv::FAM_INGEST, st, launches);
     PV_CUDA_CHECK(cudaGetLastError());
@@ -405,7 +486,7 @@ extern "C" int pv_bam_clip_layout(const uint8_t* inflated_dev, int64_t inflated_
     if (!ar.ok()) return pv::set_error(PV_EINVAL, "pv_bam_clip_layout: workspace of %lld bytes, %lld needed", (long long)workspace_bytes, (long long)ar.cur);
     const ClipArgs a{inflated_dev, inflated_bytes, rec_off_dev, n_records, tid, span_start_dev, span_stop_dev, n_spans, include_supplementary, min_mapq};
     pv::prof_begin(pv::FAM_INGEST, st);
-    clip_kernel<true><<<grid_for(n_records, 128), 128, 0, st>>>(a, (int64_t*)rec_pair_first_dev, w.pairs_in, w.keys_in, w.vals_in, status_dev);
+    clip_kernel<true><<<grid_for(n_records * 32, 256), 256, 0, st>>>(a, (int64_t*)rec_pair_first_dev, w.pairs_in, w.keys_in, w.vals_in, status_dev);
     int span_bits = 1;
     while ((1ll << span_bits) < (int64_t)n_spans + 1) span_bits++;
     PV_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.sort_tmp, w.sort_bytes, (const unsigned long long*)w.keys_in, w.keys_out,
