@@ -389,26 +389,50 @@ def measure_workload(ctx, preset, coverage, mbp, scaling, steps, warmup, main):
     torch.cuda.empty_cache()
 
     # ---- end to end through the public API, PLAIN host arrays in page-locked memory ("e2e") ----------------------------
-    for _ in range(max(warmup, 3)):          # the caching allocators (device + pinned staging) settle after two passes
-        hp.run_host(batch, first)
+    # Two ways of moving the same plain arrays, both entirely inside the timed region: uploaded as they are (PCIe-bound), or
+    # squeezed group by group into 2-bit bases / 16-bit CIGAR by host threads while the group before is on the wire
+    # (HotPath(pack_inline=True), csrc/host_pack.cpp) and expanded again on the device. The faster one is the line's `e2e`
+    # (which one wins depends on the host cores per GPU); both are reported.
     pred_box = {}
 
     def step_host(b=batch):
         pred_box["p"] = hp.run_host(b, first)
         return pred_box["p"]
 
-    ms_e, pred = _timed(ctx, step_host, steps)
-    ms_e = _max_over_ranks(ctx, ms_e)
+    def measure_host(pack_inline):
+        hp.pack_inline = pack_inline
+        for _ in range(max(warmup, 3)):      # the caching allocators (device + pinned staging) settle after two passes
+            hp.run_host(batch, first)
+        ms_h, pred_h = _timed(ctx, step_host, steps)
+        return _max_over_ranks(ctx, ms_h), pred_h, int(hp.last_h2d_bytes)
+
+    quals_txt = ("NOT uploaded: min_qual %d clears both thresholds (%g, %g), so no kernel reads one (PV_BENCH_UPLOAD_QUALS=1 "
+                 "uploads them)" % (batch.min_qual, thr.min_snp_baseq, thr.min_indel_baseq) if skip_q else "u8")
+    ms_e, pred, h2d_e = measure_host(False)
+    modes = {"plain_upload": {"value": round(bp_all * steps / (ms_e / 1e3) / 1e6, 2), "ms_per_step": round(ms_e / steps, 2),
+                              "h2d_bytes_per_step": h2d_e}}
+    fmt = "plain PvReadBatch arrays in page-locked memory: bases u8, CIGAR u32 (BAM words), per-read / per-region headers, " \
+          "reference; qualities %s" % quals_txt
+    if os.environ.get("PV_BENCH_PACK_INLINE", "1") == "1":
+        ms_p, pred_p, h2d_p = measure_host(True)
+        same_p = (len(pred_p) == len(pred) and np.array_equal(pred_p.position, pred.position)
+                  and np.array_equal(pred_p.allele, pred.allele) and np.array_equal(pred_p.genotype, pred.genotype)
+                  and np.array_equal(pred_p.probs, pred.probs))
+        modes["packed_inline"] = {"value": round(bp_all * steps / (ms_p / 1e3) / 1e6, 2), "ms_per_step": round(ms_p / steps, 2),
+                                  "h2d_bytes_per_step": h2d_p, "pack_threads": hp.pack_threads,
+                                  "identical_results_to_plain_upload": bool(same_p)}
+        if ms_p < ms_e and same_p:
+            ms_e, pred, h2d_e = ms_p, pred_p, h2d_p
+            fmt = ("the same plain PvReadBatch arrays in page-locked memory (bases u8, CIGAR u32, headers, reference); INSIDE the "
+                   "timed region %d host threads squeeze each group of regions into 2-bit bases + exception list and 16-bit CIGAR "
+                   "(pv_pack_group) into pinned staging while the group before is on the wire, the device expands them "
+                   "(pv_unpack_bases2 / pv_unpack_cigar16); qualities %s" % (hp.pack_threads, quals_txt))
+    hp.pack_inline = False
     d2h = sum(getattr(pred, f).nbytes for f in ("region", "position", "depth", "frequency", "allele", "allele_len", "probs", "genotype"))
     out["e2e"] = {"value": round(bp_all * steps / (ms_e / 1e3) / 1e6, 2), "unit": "Mbp/s",
-                  "h2d_bytes_per_step": int(hp.last_h2d_bytes), "d2h_bytes_per_step": int(d2h),
-                  "ms_per_step": round(ms_e / steps, 2),
-                  "host_format": "plain PvReadBatch arrays in page-locked memory: bases u8, CIGAR u32 (BAM words), per-read / "
-                                 "per-region headers, reference; qualities %s" % (
-                                     "NOT uploaded: min_qual %d clears both thresholds (%g, %g), so no kernel reads one "
-                                     "(PV_BENCH_UPLOAD_QUALS=1 uploads them)" % (batch.min_qual, thr.min_snp_baseq, thr.min_indel_baseq)
-                                     if skip_q else "u8"),
-                  "groups_of_regions": hp.group_regions}
+                  "h2d_bytes_per_step": int(h2d_e), "d2h_bytes_per_step": int(d2h),
+                  "ms_per_step": round(ms_e / steps, 2), "host_format": fmt, "groups_of_regions": hp.group_regions,
+                  "modes": modes}
 
     # ---- the same call on the compact wire forms; packing is host work outside the timed region and is reported -----------
     if main and os.environ.get("PV_BENCH_WIRE", "1") == "1" and n_regions > 0:

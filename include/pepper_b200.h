@@ -212,6 +212,17 @@ int pv_unpack_quals_pred(const PvReadBatch* batch_dev_ptrs, int32_t fill, const 
 int32_t pv_min_qual(const PvReadBatch* host_batch, int32_t threads);
 /* Host: pack ASCII bases into the 4-bit form; returns PV_EINVAL if a byte is outside the nt16 alphabet (0 pads map to '='). */
 int pv_pack_bases4(const uint8_t* bases_host, int64_t n_bases, uint8_t* packed_host, int32_t threads);
+/* Host: the bases2 + cigar16 forms of one GROUP of regions in one streaming pass per array (csrc/host_pack.cpp: AVX2 when the
+ * CPU has it, non-temporal stores, `threads` slices) -- fast enough to run inside the end-to-end path while the group before
+ * is on the wire (pipeline.HotPath.run_host(pack_inline=True)). The plain arrays are what the reference hands over
+ * (type_read.sequence / cigar_tuples, read.h:60-108); the compact forms are a transport detail, expanded on the device by
+ * pv_unpack_bases2 / pv_unpack_cigar16. n_bases % 4 == 0. exceptions_host holds up to exception_capacity entries;
+ * *n_exceptions receives the number found (larger than the capacity = nothing was written: call again with room).
+ * *cigar_fits = 0 when an op length is >= 4096 (cigar16_host is then not usable: upload the plain words). Output identical to
+ * pv_pack_bases2 / pv_pack_cigar16. */
+int pv_pack_group(const uint8_t* bases_host, int64_t n_bases, uint8_t* bases2_host, uint64_t* exceptions_host,
+                  int64_t exception_capacity, int64_t* n_exceptions, const uint32_t* cigar_host, int64_t n_ops,
+                  uint16_t* cigar16_host, int32_t* cigar_fits, int32_t threads);
 
 /* Host-side consistency check of a HOST-resident batch. */
 int pv_batch_validate(const PvReadBatch* host_batch);

@@ -20,7 +20,7 @@ PV_EOVERFLOW = -4
 
 # every symbol include/pepper_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = ["pv_version", "pv_last_error", "pv_device_count", "pv_profile_enable", "pv_profile_collect",
-           "pv_profile_reset", "pv_launch_count", "pv_summary_status_offset", "pv_unpack_bases4", "pv_pack_bases4", "pv_unpack_bases2", "pv_pack_bases2", "pv_pack_bases_ref", "pv_unpack_bases_ref", "pv_pack_cigar8", "pv_unpack_cigar8", "pv_pack_quals_pred", "pv_unpack_quals_pred", "pv_min_qual", "pv_unpack_quals", "pv_qual_bits", "pv_pack_quals", "pv_unpack_cigar16", "pv_pack_cigar16", "pv_batch_validate", "pv_synth_device_count", "pv_synth_device_fill", "pv_summary_workspace_bytes",
+           "pv_profile_reset", "pv_launch_count", "pv_summary_status_offset", "pv_unpack_bases4", "pv_pack_bases4", "pv_unpack_bases2", "pv_pack_bases2", "pv_pack_group", "pv_pack_bases_ref", "pv_unpack_bases_ref", "pv_pack_cigar8", "pv_unpack_cigar8", "pv_pack_quals_pred", "pv_unpack_quals_pred", "pv_min_qual", "pv_unpack_quals", "pv_qual_bits", "pv_pack_quals", "pv_unpack_cigar16", "pv_pack_cigar16", "pv_batch_validate", "pv_synth_device_count", "pv_synth_device_fill", "pv_summary_workspace_bytes",
            "pv_summary_regions", "pv_summary_regions_host", "pv_lstm_create", "pv_lstm_destroy",
            "pv_lstm_workspace_bytes", "pv_lstm_infer", "pv_lstm_infer_host", "pv_gru_create", "pv_gru_destroy",
            "pv_gru_workspace_bytes", "pv_gru_forward", "pv_gru_predict_chunks", "pv_candidate_filter",
@@ -91,6 +91,8 @@ def load() -> C.CDLL:
         lib.pv_pack_bases4.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
         lib.pv_unpack_bases2.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         lib.pv_pack_bases2.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        lib.pv_pack_group.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.POINTER(C.c_int32), C.c_int32]
         lib.pv_pack_bases_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
         lib.pv_unpack_bases_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pv_pack_quals_pred.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]

@@ -1,0 +1,161 @@
+// Host-side packing of a group's big arrays into the compact wire forms that travel over PCIe (include/pepper_b200.h:
+// bases2 + base_exceptions, cigar16), fast enough to run INSIDE the timed end-to-end path: the plain batch is what the
+// caller owns (the analogue of the reference's pre-built type_read lists, read.h:60-108), one base per byte; a B200 behind a
+// 50 GB/s PCIe link summarises faster than those bytes arrive, so the host squeezes each group into 2 bits per base and
+// 16 bits per CIGAR op while the group before it is on the wire. One streaming pass per array: AVX2 (runtime-dispatched;
+// a portable 64-bit path otherwise), non-temporal stores into the page-locked staging buffer, one thread per slice.
+//
+// Compiled by g++ (not nvcc: target attributes + immintrin) and linked into libpepper_b200.so.
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <algorithm>
+
+#include "pepper_b200.h"
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define PV_X86 1
+#else
+#define PV_X86 0
+#endif
+
+namespace pv { int set_error(int code, const char* fmt, ...); }
+
+namespace {
+
+// 2-bit code of an upper-case A/C/G/T byte: A 0x41 -> 0, C 0x43 -> 1, G 0x47 -> 2, T 0x54 -> 3
+inline uint32_t code2(uint8_t b) { return ((uint32_t)(b >> 1) ^ (uint32_t)(b >> 2)) & 3u; }
+inline bool plain_base(uint8_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+
+// bases [lo, hi) (lo, hi multiples of 4) -> packed[lo/4, hi/4); exceptions appended as (index << 8 | byte)
+void pack2_scalar(const uint8_t* bases, int64_t lo, int64_t hi, uint8_t* packed, std::vector<uint64_t>& exc) {
+    for (int64_t i = lo; i < hi; i += 4) {
+        uint32_t o = 0;
+        for (int k = 0; k < 4; k++) {
+            const uint8_t b = bases[i + k];
+            if (plain_base(b)) o |= code2(b) << (2 * k);
+            else if (b != 0) exc.push_back(((uint64_t)(i + k) << 8) | b);
+        }
+        packed[i >> 2] = (uint8_t)o;
+    }
+}
+
+#if PV_X86
+// 32 bases -> one packed byte in every 32-bit lane; *valid is ANDed with 0xff where the byte is A/C/G/T or 0. Both the byte a
+// low nibble has to belong to and its 2-bit code come from 16-entry tables (pshufb): nibble 1 'A', 3 'C', 7 'G', 4 'T', 0 the
+// padding byte; every other nibble expects a byte with a different nibble, i.e. never matches.
+__attribute__((target("avx2"))) inline __m256i pack2_32(const __m256i v, __m256i* valid) {
+    const __m256i expect = _mm256_setr_epi8(0, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1, 0, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1);
+    const __m256i codes = _mm256_setr_epi8(0, 0, 0, 1, 3, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 3, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i nib = _mm256_and_si256(v, _mm256_set1_epi8(0x0f));
+    const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(expect, nib), v);
+    *valid = _mm256_and_si256(*valid, ok);
+    const __m256i code = _mm256_and_si256(_mm256_shuffle_epi8(codes, nib), ok);
+    // c0 + 4 c1 per 16-bit lane, then + 16 (c2 + 4 c3) per 32-bit lane
+    return _mm256_madd_epi16(_mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401)), _mm256_set1_epi32(0x00100001));
+}
+
+__attribute__((target("avx2"))) void pack2_avx2(const uint8_t* bases, int64_t lo, int64_t hi, uint8_t* packed, std::vector<uint64_t>& exc) {
+    int64_t i = lo;
+    // head up to a 32-byte boundary of the OUTPUT (the streaming stores need packed + i/4 aligned)
+    while (i < hi && (((uintptr_t)(packed + (i >> 2))) & 31)) { pack2_scalar(bases, i, i + 4, packed, exc); i += 4; }
+    const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    for (; i + 128 <= hi; i += 128) {
+        __m256i valid = _mm256_set1_epi8(-1);
+        const __m256i a = pack2_32(_mm256_loadu_si256((const __m256i*)(bases + i)), &valid);
+        const __m256i b = pack2_32(_mm256_loadu_si256((const __m256i*)(bases + i + 32)), &valid);
+        const __m256i c = pack2_32(_mm256_loadu_si256((const __m256i*)(bases + i + 64)), &valid);
+        const __m256i d = pack2_32(_mm256_loadu_si256((const __m256i*)(bases + i + 96)), &valid);
+        // dwords -> bytes: per 128-bit lane a0-3 b0-3 c0-3 d0-3 | a4-7 b4-7 c4-7 d4-7, then the lanes interleaved dword-wise
+        const __m256i pk = _mm256_packus_epi16(_mm256_packus_epi32(a, b), _mm256_packus_epi32(c, d));
+        _mm256_stream_si256((__m256i*)(packed + (i >> 2)), _mm256_permutevar8x32_epi32(pk, order));
+        if (_mm256_movemask_epi8(valid) != -1)
+            for (int64_t j = i; j < i + 128; j++) { const uint8_t x = bases[j]; if (x != 0 && !plain_base(x)) exc.push_back(((uint64_t)j << 8) | x); }
+    }
+    _mm_sfence();
+    if (i < hi) pack2_scalar(bases, i, hi, packed, exc);
+}
+
+// 16 CIGAR words -> 16 half words; returns the OR of the words (bits 16.. set = an op length >= 4096)
+__attribute__((target("avx2"))) uint32_t cigar16_avx2(const uint32_t* cigar, int64_t lo, int64_t hi, uint16_t* packed) {
+    uint32_t acc = 0;
+    int64_t i = lo;
+    while (i < hi && (((uintptr_t)(packed + i)) & 31)) { acc |= cigar[i]; packed[i] = (uint16_t)cigar[i]; i++; }
+    __m256i vacc = _mm256_setzero_si256();
+    for (; i + 16 <= hi; i += 16) {
+        const __m256i x = _mm256_loadu_si256((const __m256i*)(cigar + i)), y = _mm256_loadu_si256((const __m256i*)(cigar + i + 8));
+        vacc = _mm256_or_si256(vacc, _mm256_or_si256(x, y));
+        const __m256i m = _mm256_set1_epi32(0xffff);
+        const __m256i pk = _mm256_packus_epi32(_mm256_and_si256(x, m), _mm256_and_si256(y, m));   // lanes interleaved: x0-3 y0-3 | x4-7 y4-7
+        _mm256_stream_si256((__m256i*)(packed + i), _mm256_permute4x64_epi64(pk, 0xd8));
+    }
+    _mm_sfence();
+    alignas(32) uint32_t t[8];
+    _mm256_store_si256((__m256i*)t, vacc);
+    for (int k = 0; k < 8; k++) acc |= t[k];
+    for (; i < hi; i++) { acc |= cigar[i]; packed[i] = (uint16_t)cigar[i]; }
+    return acc;
+}
+bool have_avx2() { static const bool v = __builtin_cpu_supports("avx2"); return v; }
+#else
+bool have_avx2() { return false; }
+#endif
+
+void pack2_range(const uint8_t* bases, int64_t lo, int64_t hi, uint8_t* packed, std::vector<uint64_t>& exc) {
+#if PV_X86
+    if (have_avx2()) { pack2_avx2(bases, lo, hi, packed, exc); return; }
+#endif
+    pack2_scalar(bases, lo, hi, packed, exc);
+}
+uint32_t cigar16_range(const uint32_t* cigar, int64_t lo, int64_t hi, uint16_t* packed) {
+#if PV_X86
+    if (have_avx2()) return cigar16_avx2(cigar, lo, hi, packed);
+#endif
+    uint32_t acc = 0;
+    for (int64_t i = lo; i < hi; i++) { acc |= cigar[i]; packed[i] = (uint16_t)cigar[i]; }
+    return acc;
+}
+
+}  // namespace
+
+// see include/pepper_b200.h
+extern "C" int pv_pack_group(const uint8_t* bases, int64_t n_bases, uint8_t* bases2, uint64_t* exceptions, int64_t exception_cap,
+                             int64_t* n_exceptions, const uint32_t* cigar, int64_t n_ops, uint16_t* cigar16, int32_t* cigar_fits,
+                             int32_t threads) {
+    if (n_bases < 0 || (n_bases & 3) || n_ops < 0 || exception_cap < 0 || !n_exceptions || !cigar_fits ||
+        (n_bases && (!bases || !bases2)) || (n_ops && (!cigar || !cigar16)) || (exception_cap && !exceptions))
+        return pv::set_error(PV_EINVAL, "pv_pack_group: bad arguments (n_bases %% 4 == 0, outputs non-null)");
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    // slices of whole 128-base / 16-op blocks, bases and ops dealt to every thread in proportion
+    std::vector<std::vector<uint64_t>> exc((size_t)threads);
+    std::vector<uint32_t> hib((size_t)threads, 0u);
+    const int64_t nb_blk = (n_bases + 127) / 128, no_blk = (n_ops + 15) / 16;
+    auto work = [&](int t) {
+        const int64_t b_lo = std::min(n_bases, nb_blk * t / threads * 128), b_hi = std::min(n_bases, nb_blk * (t + 1) / threads * 128);
+        if (b_hi > b_lo) pack2_range(bases, b_lo, b_hi, bases2, exc[(size_t)t]);
+        const int64_t c_lo = std::min(n_ops, no_blk * t / threads * 16), c_hi = std::min(n_ops, no_blk * (t + 1) / threads * 16);
+        if (c_hi > c_lo) hib[(size_t)t] = cigar16_range(cigar, c_lo, c_hi, cigar16);
+    };
+    if (threads == 1 || n_bases + 4 * n_ops < (1 << 16)) {
+        for (int t = 0; t < threads; t++) work(t);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    int64_t total = 0;
+    for (auto& v : exc) total += (int64_t)v.size();
+    *n_exceptions = total;
+    if (total <= exception_cap) {
+        int64_t at = 0;
+        for (auto& v : exc) { if (!v.empty()) memcpy(exceptions + at, v.data(), v.size() * 8); at += (int64_t)v.size(); }
+    }
+    uint32_t acc = 0;
+    for (uint32_t v : hib) acc |= v;
+    *cigar_fits = (acc >> 16) ? 0 : 1;
+    return PV_OK;
+}

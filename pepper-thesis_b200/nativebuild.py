@@ -55,11 +55,20 @@ def headers():
     return hs + [os.path.join(INC, "pepper_b200.h")]
 
 
+HOST_SOURCES = ["host_pack.cpp"]      # g++ pieces of libpepper_b200.so (target attributes / immintrin: not for nvcc)
+
+
 def build_lib(force=False, verbose=False):
     srcs = cuda_sources()
-    if not force and not _newer(LIB, srcs + headers()):
+    host_srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES]
+    if not force and not _newer(LIB, srcs + host_srcs + headers()):
         return LIB
     objs = []
+    for s in host_srcs:
+        o = s[:-4] + ".o"
+        if force or _newer(o, [s] + headers()):
+            _run(["g++", "-O3", "-fPIC", "-std=c++17", "-Wall", "-I", INC, "-I", CSRC, "-c", s, "-o", o], verbose)
+        objs.append(o)
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
         if force or _newer(o, [s] + headers()):

@@ -85,6 +85,74 @@ def gather_to_rank0(local: Predictions, group=None) -> Optional[Predictions]:
     return merge_results(gathered) if rank == 0 else None
 
 
+class _GroupPacker:
+    """Packs the groups of a PLAIN host batch into the compact transport forms (2-bit bases + exception list, 16-bit CIGAR;
+    ``pv_pack_group``, csrc/host_pack.cpp) on a worker thread, a few groups in front of their upload, into a ring of
+    page-locked staging slots. A slot is reused only after the upload that read it has completed (its event)."""
+
+    def __init__(self, threads: int, slots: int):
+        from concurrent.futures import ThreadPoolExecutor
+        self.threads = threads
+        self.pool = ThreadPoolExecutor(max_workers=1)      # the C call is threaded itself and releases the GIL
+        self.slots = [dict(b2=None, c16=None, exc=None, ev=None) for _ in range(slots)]
+        self.lib = None
+
+    @staticmethod
+    def _pinned(nbytes):
+        # (page-locked whenever there is a device to upload to; the packing itself is host work and is unit-tested without one)
+        return torch.empty(max(64, int(nbytes * 1.1) + 4096), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+
+    def _pack(self, batch: ReadBatch, g, slot_i: int):
+        import ctypes as C
+        from . import capi
+        if self.lib is None:
+            self.lib = capi.load()
+        view = batch.region_range_view(*g)
+        nb, no = view.n_bases, view.n_ops
+        if nb == 0 or nb % 16 or no == 0:
+            return view, slot_i
+        sl = self.slots[slot_i]
+        if sl["ev"] is not None:
+            sl["ev"].synchronize()
+            sl["ev"] = None
+        if sl["b2"] is None or sl["b2"].numel() < nb // 4:
+            sl["b2"] = self._pinned(nb // 4)
+        if sl["c16"] is None or sl["c16"].numel() < no * 2:
+            sl["c16"] = self._pinned(no * 2)
+        if sl["exc"] is None:
+            sl["exc"] = self._pinned(1 << 20)
+        n_exc, fits = C.c_int64(0), C.c_int32(0)
+        for _ in range(2):
+            cap = sl["exc"].numel() // 8
+            capi.check(self.lib.pv_pack_group(C.c_void_p(view.bases.ctypes.data), C.c_int64(nb), C.c_void_p(sl["b2"].data_ptr()),
+                                              C.c_void_p(sl["exc"].data_ptr()), C.c_int64(cap), C.byref(n_exc),
+                                              C.c_void_p(view.cigar.ctypes.data), C.c_int64(no), C.c_void_p(sl["c16"].data_ptr()),
+                                              C.byref(fits), C.c_int32(self.threads)))
+            if n_exc.value <= cap or n_exc.value * 8 > nb // 4:
+                break
+            sl["exc"] = self._pinned(n_exc.value * 8)
+        if n_exc.value * 8 <= nb // 4:            # else the exception list would cost more than the packing saves: plain bases
+            view.bases2 = sl["b2"].numpy()[:nb // 4]
+            view.base_exceptions = sl["exc"].numpy()[:n_exc.value * 8].view(np.uint64)
+        if fits.value:
+            view.cigar16 = sl["c16"].numpy()[:no * 2].view(np.uint16)
+        return view, slot_i
+
+    def submit(self, batch, g, j):
+        return self.pool.submit(self._pack, batch, g, j % len(self.slots))
+
+    def uploaded(self, slot_i, ev):
+        self.slots[slot_i]["ev"] = ev
+
+
+def default_pack_threads() -> int:
+    """Host threads one rank may spend on packing: its share of the cores, less one for the Python thread that drives the
+    GPU."""
+    cores = os.cpu_count() or 1
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return int(os.environ.get("PV_PACK_THREADS", max(1, min(32, cores // max(1, local) - 1))))
+
+
 class HotPath:
     """summary + inference for batches of regions on one GPU.
 
@@ -94,8 +162,14 @@ class HotPath:
     """
 
     def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
-                 wrap_int8: bool = True, infer_batch: int = 32768, taper: bool = True, skip_quals: bool = True):
+                 wrap_int8: bool = True, infer_batch: int = 32768, taper: bool = True, skip_quals: bool = True,
+                 pack_inline: bool = False, pack_threads: int = 0):
         self.model = model
+        self.pack_inline = pack_inline      # run_host on a PLAIN batch: every group is squeezed into the 2-bit / 16-bit transport
+                                            # forms by host threads while the group before it is on the wire (_GroupPacker);
+                                            # pays when the host has cores to spare per GPU (the plain upload is PCIe-bound)
+        self.pack_threads = pack_threads or default_pack_threads()
+        self._packer = None
         self.skip_quals = skip_quals        # run_host: a batch whose min_qual promise clears both quality thresholds is
                                             # uploaded without its quality array (no kernel would read it)
         self.taper = taper                  # run_host: shrink the last groups (upload-bound runs); False when the kernels,
@@ -312,34 +386,61 @@ class HotPath:
 
         skip_q = bool(self.skip_quals and dev.quals_not_needed(batch.min_qual, self.thr))
         self.last_h2d_bytes = 0              # bytes this call copies host -> device (counted from the uploaded arrays)
+        ahead = int(os.environ.get("PV_HOST_AHEAD", "4"))
+        # inline packing only of a batch that carries no transport form of its own
+        packing = bool(self.pack_inline and batch.bases2 is None and batch.bases4 is None and batch.bases_patch is None
+                       and batch.cigar16 is None and batch.cigar8 is None)
+        futs = {}
+        if packing:
+            pack_ahead = 2
+            if self._packer is None or len(self._packer.slots) < ahead + pack_ahead + 2:
+                self._packer = _GroupPacker(self.pack_threads, ahead + pack_ahead + 2)
+            packer = self._packer
 
-        def upload(g):
+            def request_packs(upto):
+                for j in range(len(futs), min(len(groups), upto)):
+                    futs[j] = packer.submit(batch, groups[j], j)
+            request_packs(2 + pack_ahead)
+
+        def ready(j):
+            """the group's upload can be built without waiting for a packing job"""
+            return not packing or futs[j].done()
+
+        def upload(j):
+            slot = None
+            if packing:
+                request_packs(j + 1 + pack_ahead)
+                view, slot = futs[j].result()
+            else:
+                view = batch.region_range_view(*groups[j])
             with torch.cuda.stream(self.copy_stream):
-                db = dev.DeviceBatch(batch.region_range_view(*g), self.device, non_blocking=True, defer_unpack=True,
-                                     skip_quals=skip_q)
+                db = dev.DeviceBatch(view, self.device, non_blocking=True, defer_unpack=True, skip_quals=skip_q)
                 self.last_h2d_bytes += db.h2d_bytes
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
+            if slot is not None:
+                packer.uploaded(slot, ev)
             return db, ev
 
         run = HotPath._Run()
         self._acc_buffer(self.infer_batch * 2)
         # uploads are queued `ahead` groups in front of the kernels: the copy stream never waits for the host (which
         # blocks on every group's candidate count), so the copies run back to back at PCIe speed
-        ahead = int(os.environ.get("PV_HOST_AHEAD", "4"))
         # building a group's upload costs the host ~0.5 ms: the first group's kernels are launched as soon as two uploads
         # are queued, the look-ahead fills up (two more per group) while the GPU already works
-        queue = [upload(groups[j]) for j in range(min(2, ahead, len(groups)))]
+        queue = [upload(j) for j in range(min(1 if packing else 2, ahead, len(groups)))]
         nxt = len(queue)
         for i, g in enumerate(groups):
+            if not queue:                         # (inline packing) the group's packing job is the pace setter: wait for it
+                queue.append(upload(nxt)); nxt += 1
             db, ev = queue.pop(0)
             main.wait_event(ev)
             db.unpack()                           # compact wire forms -> plain arrays, on the compute stream
             self._ensure_workspaces(db)
             h = self._launch_summary(db, 0)
             for _ in range(2):                    # host work while the GPU runs the group
-                if nxt < len(groups) and nxt <= i + ahead:
-                    queue.append(upload(groups[nxt])); nxt += 1
+                if nxt < len(groups) and nxt <= i + ahead and ready(nxt):
+                    queue.append(upload(nxt)); nxt += 1
             ws, k = self._collect_summary(h)
             self._push(run, ws, k, region_offset + g[0])
             # this path is bound by the uploads and the kernels have ~50 % slack: infer every full group's windows at once

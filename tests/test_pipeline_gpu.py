@@ -144,3 +144,32 @@ def test_full_size_properties_64mbp_50x():
         k = int(ws.count.item())
         assert k == int(m.sum())
         assert np.array_equal(ws.windows[:k].cpu().numpy().astype(np.int32), np.asarray(o["images"]).astype(np.int32)), r
+
+
+def test_inline_packing_of_plain_batches_does_not_change_results():
+    """HotPath(pack_inline=True): the plain arrays are squeezed into 2-bit bases / 16-bit CIGAR group by group on host
+    threads (pv_pack_group) and expanded on the device -- same records, bit-identical probabilities, fewer bytes on the
+    wire; a batch with non-ACGT bases and one with an op too long for 16 bits take the same path."""
+    b = synth.generate("ont_r9", 2100000, 14.0, seed=27)          # 21 regions
+    b.scan_min_qual()
+    hp, _ = _hot_path("ont_r9", group=4)
+    a = hp.run_host(b)
+    plain_bytes = hp.last_h2d_bytes
+    hp.pack_inline = True
+    for _ in range(2):                                            # second pass reuses the staging ring
+        c = hp.run_host(b)
+    assert hp.last_h2d_bytes < 0.45 * plain_bytes
+    assert len(a) > 500 and len(a) == len(c)
+    assert np.array_equal(a.region, c.region) and np.array_equal(a.position, c.position) and a.alleles() == c.alleles()
+    assert np.array_equal(a.depth, c.depth) and np.array_equal(a.frequency, c.frequency)
+    assert np.array_equal(a.probs, c.probs) and np.array_equal(a.genotype, c.genotype)
+    # exceptions (lower case, N) and a CIGAR word that does not fit 16 bits: the group travels with plain CIGAR words
+    q = synth.generate("ont_r9", 600000, 10.0, seed=28)
+    q.bases = q.bases.copy(); q.cigar = q.cigar.copy()
+    real = np.nonzero(q.bases)[0]
+    q.bases[real[::97]] = ord("N"); q.bases[real[5::389]] = ord("c")
+    hp2, _ = _hot_path("ont_r9", group=2)
+    w = hp2.run_host(q)
+    hp2.pack_inline = True
+    v = hp2.run_host(q)
+    assert len(w) > 50 and np.array_equal(w.position, v.position) and w.alleles() == v.alleles() and np.array_equal(w.probs, v.probs)
