@@ -395,20 +395,26 @@ def measure_workload(ctx, preset, coverage, mbp, scaling, steps, warmup, main):
     # (which one wins depends on the host cores per GPU); both are reported.
     pred_box = {}
 
-    def step_host(b=batch):
-        pred_box["p"] = hp.run_host(b, first)
-        return pred_box["p"]
+    # measured on a 16-core box (tools/probe_pack_inline.py): groups of 32-48 regions, two uploads in flight, CIGAR words
+    # left plain (packing them costs more host memory bandwidth than the wire time it saves) -> 45-46 ms per 64 Mbp
+    hp_pack = pipeline.HotPath(ctx.model, thr, ctx.device, group_regions=int(os.environ.get("PV_BENCH_PACK_GROUP", "48")),
+                               skip_quals=skip_q, infer_batch=hp.infer_batch, pack_inline=True, host_ahead=2)
 
     def measure_host(pack_inline):
-        hp.pack_inline = pack_inline
+        h = hp_pack if pack_inline else hp
+
+        def step_host():
+            pred_box["p"] = h.run_host(batch, first)
+            return pred_box["p"]
         for _ in range(max(warmup, 3)):      # the caching allocators (device + pinned staging) settle after two passes
-            hp.run_host(batch, first)
+            h.run_host(batch, first)
         ms_h, pred_h = _timed(ctx, step_host, steps)
-        return _max_over_ranks(ctx, ms_h), pred_h, int(hp.last_h2d_bytes)
+        return _max_over_ranks(ctx, ms_h), pred_h, int(h.last_h2d_bytes)
 
     quals_txt = ("NOT uploaded: min_qual %d clears both thresholds (%g, %g), so no kernel reads one (PV_BENCH_UPLOAD_QUALS=1 "
                  "uploads them)" % (batch.min_qual, thr.min_snp_baseq, thr.min_indel_baseq) if skip_q else "u8")
     ms_e, pred, h2d_e = measure_host(False)
+    e2e_groups = hp.group_regions
     modes = {"plain_upload": {"value": round(bp_all * steps / (ms_e / 1e3) / 1e6, 2), "ms_per_step": round(ms_e / steps, 2),
                               "h2d_bytes_per_step": h2d_e}}
     fmt = "plain PvReadBatch arrays in page-locked memory: bases u8, CIGAR u32 (BAM words), per-read / per-region headers, " \
@@ -419,19 +425,21 @@ def measure_workload(ctx, preset, coverage, mbp, scaling, steps, warmup, main):
                   and np.array_equal(pred_p.allele, pred.allele) and np.array_equal(pred_p.genotype, pred.genotype)
                   and np.array_equal(pred_p.probs, pred.probs))
         modes["packed_inline"] = {"value": round(bp_all * steps / (ms_p / 1e3) / 1e6, 2), "ms_per_step": round(ms_p / steps, 2),
-                                  "h2d_bytes_per_step": h2d_p, "pack_threads": hp.pack_threads,
+                                  "h2d_bytes_per_step": h2d_p, "pack_threads": hp_pack.pack_threads,
+                                  "groups_of_regions": hp_pack.group_regions,
                                   "identical_results_to_plain_upload": bool(same_p)}
         if ms_p < ms_e and same_p:
             ms_e, pred, h2d_e = ms_p, pred_p, h2d_p
+            e2e_groups = hp_pack.group_regions
             fmt = ("the same plain PvReadBatch arrays in page-locked memory (bases u8, CIGAR u32, headers, reference); INSIDE the "
-                   "timed region %d host threads squeeze each group of regions into 2-bit bases + exception list and 16-bit CIGAR "
-                   "(pv_pack_group) into pinned staging while the group before is on the wire, the device expands them "
-                   "(pv_unpack_bases2 / pv_unpack_cigar16); qualities %s" % (hp.pack_threads, quals_txt))
-    hp.pack_inline = False
+                   "timed region %d host threads squeeze each group's bases into 2 bits + an exception list (pv_pack_group) in "
+                   "pinned staging while the group before is on the wire, the device expands them (pv_unpack_bases2); "
+                   "qualities %s" % (hp_pack.pack_threads, quals_txt))
+    del hp_pack
     d2h = sum(getattr(pred, f).nbytes for f in ("region", "position", "depth", "frequency", "allele", "allele_len", "probs", "genotype"))
     out["e2e"] = {"value": round(bp_all * steps / (ms_e / 1e3) / 1e6, 2), "unit": "Mbp/s",
                   "h2d_bytes_per_step": int(h2d_e), "d2h_bytes_per_step": int(d2h),
-                  "ms_per_step": round(ms_e / steps, 2), "host_format": fmt, "groups_of_regions": hp.group_regions,
+                  "ms_per_step": round(ms_e / steps, 2), "host_format": fmt, "groups_of_regions": e2e_groups,
                   "modes": modes}
 
     # ---- the same call on the compact wire forms; packing is host work outside the timed region and is reported -----------

@@ -11,6 +11,10 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <unistd.h>
 
 #include "pepper_b200.h"
 
@@ -118,6 +122,63 @@ uint32_t cigar16_range(const uint32_t* cigar, int64_t lo, int64_t hi, uint16_t* 
     return acc;
 }
 
+// Persistent workers: a group is packed in 2-4 ms, so spawning a dozen threads per call would cost a tenth of it. Worker i
+// runs slice i + 1 of a job, the caller slice 0. One job at a time (callers queue on `gate`). The pool is leaked on purpose:
+// its detached workers sleep on the condition variable until the process ends.
+class Pool {
+  public:
+    void run(int n, const std::function<void(int)>& f) {
+        std::lock_guard<std::mutex> one(gate);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            while ((int)workers < n - 1) { std::thread(&Pool::loop, this, (int)workers).detach(); workers++; }
+            job = &f; n_jobs = n; pending = n - 1; gen++;
+        }
+        cv_work.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        job = nullptr;
+    }
+
+  private:
+    void loop(int idx) {
+        uint64_t seen = 0;
+        {   // a worker born during a job's set-up starts with that job
+            std::unique_lock<std::mutex> lk(mu);
+            seen = gen - 1;
+        }
+        while (true) {
+            const std::function<void(int)>* f = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return gen != seen; });
+                seen = gen;
+                if (idx + 1 < n_jobs) f = job;
+            }
+            if (f) {
+                (*f)(idx + 1);
+                std::unique_lock<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    std::mutex gate, mu;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(int)>* job = nullptr;
+    int n_jobs = 0, pending = 0;
+    size_t workers = 0;
+    uint64_t gen = 1;
+};
+Pool& pool() {          // a forked child owns no workers: it gets a pool of its own
+    static std::mutex m;
+    static Pool* p = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(m);
+    if (!p || owner != getpid()) { p = new Pool(); owner = getpid(); }
+    return *p;
+}
+
 }  // namespace
 
 // see include/pepper_b200.h
@@ -142,10 +203,7 @@ extern "C" int pv_pack_group(const uint8_t* bases, int64_t n_bases, uint8_t* bas
     if (threads == 1 || n_bases + 4 * n_ops < (1 << 16)) {
         for (int t = 0; t < threads; t++) work(t);
     } else {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; t++) pool.emplace_back(work, t);
-        work(0);
-        for (auto& th : pool) th.join();
+        pool().run(threads, work);
     }
     int64_t total = 0;
     for (auto& v : exc) total += (int64_t)v.size();

@@ -90,9 +90,10 @@ class _GroupPacker:
     ``pv_pack_group``, csrc/host_pack.cpp) on a worker thread, a few groups in front of their upload, into a ring of
     page-locked staging slots. A slot is reused only after the upload that read it has completed (its event)."""
 
-    def __init__(self, threads: int, slots: int):
+    def __init__(self, threads: int, slots: int, pack_cigar: bool = True):
         from concurrent.futures import ThreadPoolExecutor
         self.threads = threads
+        self.pack_cigar = pack_cigar
         self.pool = ThreadPoolExecutor(max_workers=1)      # the C call is threaded itself and releases the GIL
         self.slots = [dict(b2=None, c16=None, exc=None, ev=None) for _ in range(slots)]
         self.lib = None
@@ -110,7 +111,7 @@ class _GroupPacker:
         view = batch.region_range_view(*g)
         nb, no = view.n_bases, view.n_ops
         if nb == 0 or nb % 16 or no == 0:
-            return view, slot_i
+            return view, None
         sl = self.slots[slot_i]
         if sl["ev"] is not None:
             sl["ev"].synchronize()
@@ -126,15 +127,15 @@ class _GroupPacker:
             cap = sl["exc"].numel() // 8
             capi.check(self.lib.pv_pack_group(C.c_void_p(view.bases.ctypes.data), C.c_int64(nb), C.c_void_p(sl["b2"].data_ptr()),
                                               C.c_void_p(sl["exc"].data_ptr()), C.c_int64(cap), C.byref(n_exc),
-                                              C.c_void_p(view.cigar.ctypes.data), C.c_int64(no), C.c_void_p(sl["c16"].data_ptr()),
-                                              C.byref(fits), C.c_int32(self.threads)))
+                                              C.c_void_p(view.cigar.ctypes.data), C.c_int64(no if self.pack_cigar else 0),
+                                              C.c_void_p(sl["c16"].data_ptr()), C.byref(fits), C.c_int32(self.threads)))
             if n_exc.value <= cap or n_exc.value * 8 > nb // 4:
                 break
             sl["exc"] = self._pinned(n_exc.value * 8)
         if n_exc.value * 8 <= nb // 4:            # else the exception list would cost more than the packing saves: plain bases
             view.bases2 = sl["b2"].numpy()[:nb // 4]
             view.base_exceptions = sl["exc"].numpy()[:n_exc.value * 8].view(np.uint64)
-        if fits.value:
+        if fits.value and self.pack_cigar:
             view.cigar16 = sl["c16"].numpy()[:no * 2].view(np.uint16)
         return view, slot_i
 
@@ -163,12 +164,15 @@ class HotPath:
 
     def __init__(self, model, thresholds, device="cuda", group_regions: int = 40, candidates_per_kbp: float = 8.0,
                  wrap_int8: bool = True, infer_batch: int = 32768, taper: bool = True, skip_quals: bool = True,
-                 pack_inline: bool = False, pack_threads: int = 0):
+                 pack_inline: bool = False, pack_threads: int = 0, pack_cigar: bool = False, host_ahead: int = 0):
         self.model = model
         self.pack_inline = pack_inline      # run_host on a PLAIN batch: every group is squeezed into the 2-bit / 16-bit transport
                                             # forms by host threads while the group before it is on the wire (_GroupPacker);
                                             # pays when the host has cores to spare per GPU (the plain upload is PCIe-bound)
         self.pack_threads = pack_threads or default_pack_threads()
+        self.pack_cigar = pack_cigar        # also the CIGAR words (32 -> 16 bits): pays only while the wire, not the host's
+                                            # memory bandwidth, sets the pace (measured on 16 cores: 49 ms without, 54-61 with)
+        self.host_ahead = host_ahead or int(os.environ.get("PV_HOST_AHEAD", "4"))   # groups uploaded in front of the kernels
         self._packer = None
         self.skip_quals = skip_quals        # run_host: a batch whose min_qual promise clears both quality thresholds is
                                             # uploaded without its quality array (no kernel would read it)
@@ -386,7 +390,7 @@ class HotPath:
 
         skip_q = bool(self.skip_quals and dev.quals_not_needed(batch.min_qual, self.thr))
         self.last_h2d_bytes = 0              # bytes this call copies host -> device (counted from the uploaded arrays)
-        ahead = int(os.environ.get("PV_HOST_AHEAD", "4"))
+        ahead = self.host_ahead
         # inline packing only of a batch that carries no transport form of its own
         packing = bool(self.pack_inline and batch.bases2 is None and batch.bases4 is None and batch.bases_patch is None
                        and batch.cigar16 is None and batch.cigar8 is None)
@@ -394,7 +398,8 @@ class HotPath:
         if packing:
             pack_ahead = 2
             if self._packer is None or len(self._packer.slots) < ahead + pack_ahead + 2:
-                self._packer = _GroupPacker(self.pack_threads, ahead + pack_ahead + 2)
+                self._packer = _GroupPacker(self.pack_threads, ahead + pack_ahead + 2,
+                                            pack_cigar=self.pack_cigar)
             packer = self._packer
 
             def request_packs(upto):
