@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -190,21 +191,27 @@ extern "C" int pv_pack_group(const uint8_t* bases, int64_t n_bases, uint8_t* bas
         return pv::set_error(PV_EINVAL, "pv_pack_group: bad arguments (n_bases %% 4 == 0, outputs non-null)");
     if (threads < 1) threads = 1;
     if (threads > 64) threads = 64;
-    // slices of whole 128-base / 16-op blocks, bases and ops dealt to every thread in proportion
-    std::vector<std::vector<uint64_t>> exc((size_t)threads);
+    // Chunks of 1 MiB of bases / 256 Ki ops, claimed from a shared counter: a worker that loses its core for a while (the
+    // caller's other threads drive the GPU on the same cores) holds up one chunk, not a fixed share of the group.
+    constexpr int64_t BASE_CHUNK = 1 << 20, OP_CHUNK = 1 << 18;
+    const int64_t nb_chunks = (n_bases + BASE_CHUNK - 1) / BASE_CHUNK, no_chunks = (n_ops + OP_CHUNK - 1) / OP_CHUNK;
+    std::vector<std::vector<uint64_t>> exc((size_t)nb_chunks);
     std::vector<uint32_t> hib((size_t)threads, 0u);
-    const int64_t nb_blk = (n_bases + 127) / 128, no_blk = (n_ops + 15) / 16;
+    std::atomic<int64_t> next{0};
     auto work = [&](int t) {
-        const int64_t b_lo = std::min(n_bases, nb_blk * t / threads * 128), b_hi = std::min(n_bases, nb_blk * (t + 1) / threads * 128);
-        if (b_hi > b_lo) pack2_range(bases, b_lo, b_hi, bases2, exc[(size_t)t]);
-        const int64_t c_lo = std::min(n_ops, no_blk * t / threads * 16), c_hi = std::min(n_ops, no_blk * (t + 1) / threads * 16);
-        if (c_hi > c_lo) hib[(size_t)t] = cigar16_range(cigar, c_lo, c_hi, cigar16);
+        while (true) {
+            const int64_t c = next.fetch_add(1, std::memory_order_relaxed);
+            if (c >= nb_chunks + no_chunks) break;
+            if (c < nb_chunks) {
+                pack2_range(bases, c * BASE_CHUNK, std::min(n_bases, (c + 1) * BASE_CHUNK), bases2, exc[(size_t)c]);
+            } else {
+                const int64_t k = c - nb_chunks;
+                hib[(size_t)t] |= cigar16_range(cigar, k * OP_CHUNK, std::min(n_ops, (k + 1) * OP_CHUNK), cigar16);
+            }
+        }
     };
-    if (threads == 1 || n_bases + 4 * n_ops < (1 << 16)) {
-        for (int t = 0; t < threads; t++) work(t);
-    } else {
-        pool().run(threads, work);
-    }
+    if (threads == 1 || nb_chunks + no_chunks <= 1) work(0);
+    else pool().run((int)std::min<int64_t>(threads, nb_chunks + no_chunks), work);
     int64_t total = 0;
     for (auto& v : exc) total += (int64_t)v.size();
     *n_exceptions = total;

@@ -94,7 +94,9 @@ class _GroupPacker:
         from concurrent.futures import ThreadPoolExecutor
         self.threads = threads
         self.pack_cigar = pack_cigar
-        self.pool = ThreadPoolExecutor(max_workers=1)      # the C call is threaded itself and releases the GIL
+        # two workers take turns: while one queues its group's upload (Python, ~0.5 ms) the other one is already packing
+        # (the C call is threaded itself, admits one job at a time and releases the GIL)
+        self.pool = ThreadPoolExecutor(max_workers=2)
         self.slots = [dict(b2=None, c16=None, exc=None, ev=None) for _ in range(slots)]
         self.lib = None
 
@@ -221,6 +223,8 @@ class HotPath:
         hc = self._host_counts[slot]
         hc[0:1].copy_(ws.count, non_blocking=True)
         hc[1:2].copy_(ws.ws[12:16].view(torch.int32), non_blocking=True)       # status word
+        # (a blocking event -- the host sleeps instead of spinning while the packing threads use the cores -- was measured with
+        # inline packing and lost: 50.8 against 46.8 ms per 64 Mbp, the wake-up comes late)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         return dict(db=db, slot=slot, ev=ev, ws=ws, hc=hc)      # keeps its workspace alive even if the pool is regrown
@@ -394,57 +398,34 @@ class HotPath:
         # inline packing only of a batch that carries no transport form of its own
         packing = bool(self.pack_inline and batch.bases2 is None and batch.bases4 is None and batch.bases_patch is None
                        and batch.cigar16 is None and batch.cigar8 is None)
-        futs = {}
+        run = HotPath._Run()
+        self._acc_buffer(self.infer_batch * 2)
         if packing:
-            pack_ahead = 2
-            if self._packer is None or len(self._packer.slots) < ahead + pack_ahead + 2:
-                self._packer = _GroupPacker(self.pack_threads, ahead + pack_ahead + 2,
-                                            pack_cigar=self.pack_cigar)
-            packer = self._packer
-
-            def request_packs(upto):
-                for j in range(len(futs), min(len(groups), upto)):
-                    futs[j] = packer.submit(batch, groups[j], j)
-            request_packs(2 + pack_ahead)
-
-        def ready(j):
-            """the group's upload can be built without waiting for a packing job"""
-            return not packing or futs[j].done()
+            return self._run_host_packing(batch, groups, n_body, region_offset, run, main, skip_q)
 
         def upload(j):
-            slot = None
-            if packing:
-                request_packs(j + 1 + pack_ahead)
-                view, slot = futs[j].result()
-            else:
-                view = batch.region_range_view(*groups[j])
             with torch.cuda.stream(self.copy_stream):
-                db = dev.DeviceBatch(view, self.device, non_blocking=True, defer_unpack=True, skip_quals=skip_q)
+                db = dev.DeviceBatch(batch.region_range_view(*groups[j]), self.device, non_blocking=True, defer_unpack=True,
+                                     skip_quals=skip_q)
                 self.last_h2d_bytes += db.h2d_bytes
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
-            if slot is not None:
-                packer.uploaded(slot, ev)
             return db, ev
 
-        run = HotPath._Run()
-        self._acc_buffer(self.infer_batch * 2)
         # uploads are queued `ahead` groups in front of the kernels: the copy stream never waits for the host (which
         # blocks on every group's candidate count), so the copies run back to back at PCIe speed
         # building a group's upload costs the host ~0.5 ms: the first group's kernels are launched as soon as two uploads
         # are queued, the look-ahead fills up (two more per group) while the GPU already works
-        queue = [upload(j) for j in range(min(1 if packing else 2, ahead, len(groups)))]
+        queue = [upload(j) for j in range(min(2, ahead, len(groups)))]
         nxt = len(queue)
         for i, g in enumerate(groups):
-            if not queue:                         # (inline packing) the group's packing job is the pace setter: wait for it
-                queue.append(upload(nxt)); nxt += 1
             db, ev = queue.pop(0)
             main.wait_event(ev)
             db.unpack()                           # compact wire forms -> plain arrays, on the compute stream
             self._ensure_workspaces(db)
             h = self._launch_summary(db, 0)
             for _ in range(2):                    # host work while the GPU runs the group
-                if nxt < len(groups) and nxt <= i + ahead and ready(nxt):
+                if nxt < len(groups) and nxt <= i + ahead:
                     queue.append(upload(nxt)); nxt += 1
             ws, k = self._collect_summary(h)
             self._push(run, ws, k, region_offset + g[0])
@@ -452,6 +433,67 @@ class HotPath:
             # (smaller passes, a little less efficient) instead of letting full passes pile up behind the last upload;
             # the small groups of the taper share one last pass (a pass costs >= 66 launch latencies however small)
             if i == len(groups) - 1:
+                self._drain(run, final=True)
+            elif i < n_body:
+                self._drain(run, final=False, aligned=True)
+            db.record_stream(main)
+        return self._finish(run, True)
+
+    def _run_host_packing(self, batch, groups, n_body, region_offset, run, main, skip_q):
+        """run_host with inline transport packing: the packing threads set the pace (a group of 48 regions is packed in ~3 ms,
+        uploaded in 2.3, summarised and inferred in ~2.5), so everything else is arranged around them. Two worker threads take
+        the groups in turn: each packs its group (one packing job at a time inside pv_pack_group) and then queues the group's
+        upload on the copy stream ITSELF -- the wire starts the moment the bytes exist, and the other worker is already
+        packing the next group meanwhile. The calling thread only consumes finished uploads: expansion + summary kernels,
+        inference in whole waves of the step kernels while full groups arrive (one host round trip per group is what the
+        calling thread can afford), everything that is waiting with the last full group, so that behind the last packing job
+        only the small groups of the taper remain."""
+        in_flight = self.host_ahead + 2
+        nslots = in_flight + 2
+        if self._packer is None or len(self._packer.slots) < nslots:
+            self._packer = _GroupPacker(self.pack_threads, nslots, pack_cigar=self.pack_cigar)
+        packer = self._packer
+
+        import threading
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        turn = threading.Condition()
+        state = {"next": 0, "submitted": 0}
+
+        def job(j):
+            with turn:                                     # groups are packed in order, whichever worker holds them
+                turn.wait_for(lambda: state["next"] == j)
+            try:
+                torch.cuda.set_device(dev_index)          # the current device is per thread
+                view, slot = packer._pack(batch, groups[j], j % nslots)
+            finally:
+                with turn:
+                    state["next"] = j + 1
+                    turn.notify_all()
+            with torch.cuda.stream(self.copy_stream):
+                db = dev.DeviceBatch(view, self.device, non_blocking=True, defer_unpack=True, skip_quals=skip_q)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            if slot is not None:
+                packer.uploaded(slot, ev)
+            return db, ev
+
+        futs = {}
+
+        def request(upto):
+            while state["submitted"] < min(len(groups), upto):
+                futs[state["submitted"]] = packer.pool.submit(job, state["submitted"])
+                state["submitted"] += 1
+        request(in_flight)
+        for i, g in enumerate(groups):
+            db, ev = futs.pop(i).result()
+            request(i + 1 + in_flight)
+            self.last_h2d_bytes += db.h2d_bytes
+            main.wait_event(ev)
+            db.unpack()
+            self._ensure_workspaces(db)
+            ws, k = self._collect_summary(self._launch_summary(db, 0))
+            self._push(run, ws, k, region_offset + g[0])
+            if i == n_body - 1 or i == len(groups) - 1:
                 self._drain(run, final=True)
             elif i < n_body:
                 self._drain(run, final=False, aligned=True)

@@ -9,7 +9,7 @@ import pytest
 from pepper_thesis_b200 import capi, pipeline, synth
 
 
-def _pack_group(bases, cigar, threads, cap=1 << 14, misalign=(17, 3)):
+def _pack_group(bases, cigar, threads, cap=1 << 18, misalign=(17, 3)):
     lib = capi.load()
     n = bases.size
     out2 = np.full(n // 4 + 64, 0xEE, np.uint8)[misalign[0]:misalign[0] + n // 4]
@@ -33,7 +33,7 @@ def _numpy_forms(bases, cigar):
     return p, exc, cigar.astype(np.uint16), int(not (cigar >> 16).any()) if cigar.size else 1
 
 
-@pytest.mark.parametrize("n", [0, 4, 124, 128, 132, 1000, 4096 + 12, 300000])
+@pytest.mark.parametrize("n", [0, 4, 124, 128, 132, 1000, 4096 + 12, 300000, 5 * (1 << 20) + 12])
 @pytest.mark.parametrize("threads", [1, 3, 8])
 def test_pack_group_matches_the_documented_forms(n, threads):
     rng = np.random.default_rng(n + threads)
