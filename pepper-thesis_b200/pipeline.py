@@ -96,17 +96,67 @@ class _GroupPacker:
         self.pack_cigar = pack_cigar
         # two workers take turns: while one queues its group's upload (Python, ~0.5 ms) the other one is already packing
         # (the C call is threaded itself, admits one job at a time and releases the GIL)
-        self.pool = ThreadPoolExecutor(max_workers=2)
+        self.pool = ThreadPoolExecutor(max_workers=4)       # (as many as groups in flight: a plain group must not queue behind waiting packers)
         self.slots = [dict(b2=None, c16=None, exc=None, ev=None) for _ in range(slots)]
         self.lib = None
+        # the mix of packed and plain groups (choose_plain): running estimates of the two rates that decide it
+        self.pack_s_per_base = None         # seconds of packing per base (this rank's threads, as contended as they are)
+        self.wire_s_per_byte = None         # seconds per uploaded byte (this rank's share of the host's H2D bandwidth)
+        self._uploads = []                  # (start event, end event, bytes) of uploads not yet measured
+        import threading
+        self._uploads_lock = threading.Lock()
+        self._plain_acc = 0.0
+        self.n_plain = self.n_packed = 0
+
+    def note_upload(self, e0, e1, nbytes):
+        with self._uploads_lock:
+            self._uploads.append((e0, e1, nbytes))
+
+    def _poll_uploads(self):
+        with self._uploads_lock:
+            pending, self._uploads = self._uploads, []
+        keep = []
+        for e0, e1, nbytes in pending:
+            if e1.query():
+                t = e0.elapsed_time(e1) * 1e-3 / max(1, nbytes)
+                self.wire_s_per_byte = t if self.wire_s_per_byte is None else 0.7 * self.wire_s_per_byte + 0.3 * t
+            else:
+                keep.append((e0, e1, nbytes))
+        with self._uploads_lock:
+            self._uploads = keep + self._uploads
+
+    def choose_plain(self, n_bases: int, other_bytes: int) -> bool:
+        """Should this group travel plain? Packing costs host time (T_p), the wire carries a packed group in T_wp and a plain
+        one in T_wl. With a share x of the groups plain the packing threads are busy (1 - x) T_p per group and the wire
+        (1 - x) T_wp + x T_wl; both finish together at x = (T_p - T_wp) / (T_p - T_wp + T_wl) (0 when the wire is the slower
+        one anyway). With 7 threads per GPU that is one group in four, with 3 threads one in two (measured on one B200, ms per
+        64 Mbp: 7 threads 53 mixed / 66 all packed / 76 all plain; 3 threads 69 / 124 / 76; with ONE thread the mix loses to
+        the plain upload, 93 against 76 -- the caller should not ask for inline packing then, and bench.py times both). The rates are measured
+        as the run goes (packing: host clock around the call; wire: events around every upload), so the mix follows the
+        cores and the H2D bandwidth this rank really gets. Groups are dealt out like Bresenham's line."""
+        self._poll_uploads()
+        if self.pack_s_per_base is None or self.wire_s_per_byte is None or os.environ.get("PV_PACK_MIX", "1") != "1":
+            return False
+        t_p = n_bases * self.pack_s_per_base
+        t_wp = (n_bases // 4 + other_bytes) * self.wire_s_per_byte
+        t_wl = (n_bases + other_bytes) * self.wire_s_per_byte
+        x = 0.0 if t_p <= t_wp else (t_p - t_wp) / (t_p - t_wp + t_wl)
+        if x < 0.2:         # nearly balanced already: a plain group then costs more (its 5.8 ms on the wire delay the packed
+            return False    # groups behind it) than it saves -- measured with 15 threads: 48.8 against 45.8 ms per 64 Mbp
+        self._plain_acc += x
+        if self._plain_acc >= 1.0:
+            self._plain_acc -= 1.0
+            return True
+        return False
 
     @staticmethod
     def _pinned(nbytes):
         # (page-locked whenever there is a device to upload to; the packing itself is host work and is unit-tested without one)
         return torch.empty(max(64, int(nbytes * 1.1) + 4096), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
 
-    def _pack(self, batch: ReadBatch, g, slot_i: int):
+    def _pack(self, batch: ReadBatch, g, slot_i: int, plain: bool = False):
         import ctypes as C
+        import time
         from . import capi
         if self.lib is None:
             self.lib = capi.load()
@@ -114,6 +164,11 @@ class _GroupPacker:
         nb, no = view.n_bases, view.n_ops
         if nb == 0 or nb % 16 or no == 0:
             return view, None
+        if plain:
+            self.n_plain += 1
+            return view, None
+        self.n_packed += 1
+        t0 = time.perf_counter()
         sl = self.slots[slot_i]
         if sl["ev"] is not None:
             sl["ev"].synchronize()
@@ -139,6 +194,8 @@ class _GroupPacker:
             view.base_exceptions = sl["exc"].numpy()[:n_exc.value * 8].view(np.uint64)
         if fits.value and self.pack_cigar:
             view.cigar16 = sl["c16"].numpy()[:no * 2].view(np.uint16)
+        t = (time.perf_counter() - t0) / nb
+        self.pack_s_per_base = t if self.pack_s_per_base is None else 0.7 * self.pack_s_per_base + 0.3 * t
         return view, slot_i
 
     def submit(self, batch, g, j):
@@ -457,31 +514,46 @@ class HotPath:
         import threading
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         turn = threading.Condition()
-        state = {"next": 0, "submitted": 0}
+        state = {"next": 0, "submitted": 0, "tickets": 0}
 
-        def job(j):
-            with turn:                                     # groups are packed in order, whichever worker holds them
-                turn.wait_for(lambda: state["next"] == j)
-            try:
-                torch.cuda.set_device(dev_index)          # the current device is per thread
-                view, slot = packer._pack(batch, groups[j], j % nslots)
-            finally:
-                with turn:
-                    state["next"] = j + 1
-                    turn.notify_all()
+        def job(j, plain, ticket):
+            torch.cuda.set_device(dev_index)              # the current device is per thread
+            if plain:                                      # travels as it is: straight to the wire, past the packing jobs
+                view, slot = packer._pack(batch, groups[j], j % nslots, plain=True)
+            else:
+                with turn:                                 # groups are packed in order, whichever worker holds them
+                    turn.wait_for(lambda: state["next"] == ticket)
+                try:
+                    view, slot = packer._pack(batch, groups[j], j % nslots)
+                finally:
+                    with turn:
+                        state["next"] = ticket + 1
+                        turn.notify_all()
             with torch.cuda.stream(self.copy_stream):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(self.copy_stream)
                 db = dev.DeviceBatch(view, self.device, non_blocking=True, defer_unpack=True, skip_quals=skip_q)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=True)
                 ev.record(self.copy_stream)
+            packer.note_upload(e0, ev, db.h2d_bytes)
             if slot is not None:
                 packer.uploaded(slot, ev)
             return db, ev
 
         futs = {}
 
+        rb, bo, co = batch.region_read_begin, batch.read_base_off, batch.read_cigar_off
+
         def request(upto):
             while state["submitted"] < min(len(groups), upto):
-                futs[state["submitted"]] = packer.pool.submit(job, state["submitted"])
+                j = state["submitted"]
+                r0, r1 = int(rb[groups[j][0]]), int(rb[groups[j][1]])
+                n_b = int(bo[r1] - bo[r0]) if r1 < len(bo) else int(batch.n_bases - bo[r0]) if r0 < len(bo) else 0
+                n_o = int(co[r1] - co[r0]) if r1 < len(co) else int(batch.n_ops - co[r0]) if r0 < len(co) else 0
+                plain = packer.choose_plain(n_b, 4 * n_o + 100000 * (groups[j][1] - groups[j][0]))
+                futs[j] = packer.pool.submit(job, j, plain, state["tickets"])
+                if not plain:
+                    state["tickets"] += 1
                 state["submitted"] += 1
         request(in_flight)
         for i, g in enumerate(groups):

@@ -12,22 +12,30 @@ batch.scan_min_qual(16)
 batch.pin_plain(with_quals=False)
 thr = synth.PROFILES["ont_r9"].thresholds
 model = models.TransducerGRU(26, 1, 256, 28, 3, True).load_state_dict(models.random_variant_state_dict(0))
-def make(g, threads, ahead=2, taper=True):
-    return pipeline.HotPath(model, thr, "cuda:0", group_regions=g, pack_inline=True, pack_threads=threads, taper=taper, host_ahead=ahead)
-configs = [(48, 14, "1", "5000"), (48, 14, "0", "5000"), (48, 14, "1", "200"), (48, 14, "0", "200"), (48, 15, "1", "200"), (48, 15, "0", "200"), (64, 14, "1", "200"), (64, 14, "0", "200"), (48, 13, "0", "200")]
+def make(g, threads, ahead=2, taper=True, inline=True):
+    return pipeline.HotPath(model, thr, "cuda:0", group_regions=g, pack_inline=inline, pack_threads=threads, taper=taper, host_ahead=ahead)
+configs = [(48, 15, "1"), (48, 15, "0"), (48, 14, "1"), (48, 7, "1"), (48, 7, "0"), (48, 3, "1"), (48, 3, "0"), (48, 1, "1"), (32, 7, "1"), (64, 7, "1")]
 hps = {c: make(c[0], c[1]) for c in configs}
 res = {c: [] for c in configs}
 def call(c):
-    os.environ["PV_EV_BLOCKING"] = c[2]; os.environ["PV_SWITCH_US"] = c[3]
+    os.environ["PV_PACK_MIX"] = c[2]
     hps[c].run_host(batch)
 for c in configs:
-    for _ in range(3):
+    for _ in range(4):
         call(c)
-for rnd in range(3):
+for rnd in range(2):
     for c in configs:
         for _ in range(4):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             call(c)
             torch.cuda.synchronize(); res[c].append((time.perf_counter() - t0) * 1e3)
 for c in configs:
-    print("group %3d threads %2d blocking-event %s switch %s us: median %.1f ms  (%s)" % (c[0], c[1], c[2], c[3], statistics.median(res[c]), " ".join("%.0f" % t for t in res[c])), flush=True)
+    pk = hps[c]._packer
+    print("group %3d threads %2d mix %s: median %.1f ms  (%s)  plain %d packed %d  pack %.2f ns/base wire %.3f ns/B  h2d %.2f GB" % (
+        c[0], c[1], c[2], statistics.median(res[c]), " ".join("%.0f" % t for t in res[c]), pk.n_plain, pk.n_packed,
+        (pk.pack_s_per_base or 0) * 1e9, (pk.wire_s_per_byte or 0) * 1e9, hps[c].last_h2d_bytes / 1e9), flush=True)
+hp0 = make(128, 1, ahead=4, inline=False)
+ts = []
+for _ in range(8):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); hp0.run_host(batch); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+print("plain upload, groups of 128: median %.1f ms" % statistics.median(ts[3:]))
