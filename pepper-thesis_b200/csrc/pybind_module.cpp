@@ -419,7 +419,14 @@ PYBIND11_MODULE(PEPPER_VARIANT, m) {
         .def("get_chromosome_sequence_length", &FASTA_handler::get_chromosome_sequence_length)
         .def("get_chromosome_names", &FASTA_handler::get_chromosome_names);
 
-    out_of_scope(m, "SummaryGenerator", "legacy per-position generator, not called by call_variant");
+    // The legacy per-position generator (pybind_api.h:24-43; not called by call_variant) lives in Python on top of the
+    // polisher's summary kernels: pepper_thesis_b200/legacy_summary.py. Forwarded lazily (the import pulls in torch).
+    for (const char* name : {"SummaryGenerator", "ImageSummary"}) {
+        string n = name;
+        m.attr(name) = py::cpp_function([n](py::args a, py::kwargs k) -> py::object {
+            return py::module_::import("pepper_thesis_b200.legacy_summary").attr(n.c_str())(*a, **k);
+        });
+    }
     out_of_scope(m, "RegionalSummaryGeneratorHP", "haplotype-aware variant, -hp flag only");
     out_of_scope(m, "CandidateFinder", "legacy C++ candidate finder, unreachable from call_variant");
     out_of_scope(m, "CandidateFinderHP", "legacy C++ candidate finder, unreachable from call_variant");

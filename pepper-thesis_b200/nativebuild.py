@@ -123,7 +123,8 @@ def build_oracle(force=False, verbose=False):
     ref_dir = os.path.join(odir, "_ref")
     if os.path.isdir("/root/reference/pepper_variant/modules/cpp"):
         have = os.listdir(ref_dir) if os.path.isdir(ref_dir) else []
-        shims = {"pv_ref_oracle": "ref_shim.cpp", "pv_ref_polisher": "ref_shim_polisher.cpp", "pv_ref_bam": "ref_shim_bam.cpp"}
+        shims = {"pv_ref_oracle": "ref_shim.cpp", "pv_ref_polisher": "ref_shim_polisher.cpp", "pv_ref_bam": "ref_shim_bam.cpp",
+                 "pv_ref_legacy": "ref_shim_legacy.cpp"}
         stale = False
         for mod, shim in shims.items():
             so = [os.path.join(ref_dir, f) for f in have if f.startswith(mod)]

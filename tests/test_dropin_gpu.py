@@ -103,7 +103,12 @@ def test_alignment_summarizer_mirror():
 def test_out_of_scope_names_raise():
     pv = _pv()
     with pytest.raises(RuntimeError, match="outside the B200 hot path"):
-        pv.SummaryGenerator("ACGT", "c", 0, 3)
+        pv.RegionalSummaryGeneratorHP("c", 0, 3, "ACGT")
+    # the legacy per-position generator is built (legacy_summary.py): the module forwards the name
+    lg = pv.SummaryGenerator("ACGT", "c", 0, 3)
+    lg.generate_summary([H.Read(0, "ACGT", [(0, 4)])], 0, 3)
+    assert lg.genomic_pos == [(0, 0), (1, 0), (2, 0), (3, 0)] and lg.ref_image == [1, 2, 3, 4] and lg.image[0][4] == 254
+    assert pv.ImageSummary().chunk_ids == []
     g = pv.RegionalSummaryGenerator("c", 0, 3, "ACGT")
     with pytest.raises(RuntimeError):
         g.generate_summary([], 1, 1, .1, .1, .1, 1, .1, .1, 1, False, 0, 3, 32, 26, True)
