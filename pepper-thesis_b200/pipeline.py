@@ -209,6 +209,10 @@ def default_pack_threads() -> int:
     """Host threads one rank may spend on packing: its share of the cores, less one for the Python thread that drives the
     GPU."""
     cores = os.cpu_count() or 1
+    try:
+        cores = min(cores, len(os.sched_getaffinity(0)))       # the cores this process may run on
+    except (AttributeError, OSError):
+        pass
     local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
     return int(os.environ.get("PV_PACK_THREADS", max(1, min(32, cores // max(1, local) - 1))))
 
