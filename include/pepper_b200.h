@@ -275,7 +275,7 @@ typedef struct PvLstmModel PvLstmModel;
 int pv_lstm_create(const PvLstmWeights* host_weights, PvLstmModel** model);
 void pv_lstm_destroy(PvLstmModel* model);
 int64_t pv_lstm_workspace_bytes(int64_t max_windows);
-/* windows_dev int16 [n][33][26]; probs_dev float [n][3] (softmax); argmax_dev uint8 [n] (may be NULL).
+/* windows_dev int16 [n][33][26] (4-byte aligned); probs_dev float [n][3] (softmax); argmax_dev uint8 [n] (may be NULL).
  * wrap_int8 != 0 reproduces the reference pipeline's int8 HDF5 round trip (DataStore.py:68,
  * dataloader_predict.py:90): the value fed to the network is (int8_t)window value. */
 int pv_lstm_infer(PvLstmModel* model, const int16_t* windows_dev, int64_t n, int32_t wrap_int8,

@@ -205,26 +205,31 @@ struct SeluEpilogue {
 // windows int16 [n][33][26] -> xhl bf16 [n][33][128]: cols 0..25 = x_hi, 26..51 = x_lo (x == x_hi + x_lo exactly; both
 // meet bf16(W_ih)), cols 64..89 = x_hi again (meets the bf16 remainder of W_ih), rest 0
 __global__ void prep_input_kernel(const int16_t* __restrict__ win, __nv_bfloat16* __restrict__ xhl, int64_t n, int wrap_int8) {
-    // a thread writes 8 consecutive output columns (one 16-byte store); 16 threads share one 52-byte input row
+    // a thread writes 8 consecutive output columns (one 16-byte store); 16 threads share one 52-byte input row. The column
+    // blocks change their source at even columns only (26, 52, 64, 90) and a row starts 4-byte aligned (52 bytes per row), so
+    // a thread reads its features as pairs: four 32-bit loads instead of eight 16-bit ones
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over n*33*16
     if (i >= n * T * (XK / 8)) return;
     const int c0 = (int)(i & (XK / 8 - 1)) * 8;
     const int64_t rt = i / (XK / 8);
+    const uint32_t* row = (const uint32_t*)(win + rt * F);
     uint32_t o[4];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 8; k += 2) {
         const int col = c0 + k;
         const int f = col < 2 * F ? (col < F ? col : col - F) : (col >= 64 && col < 64 + F ? col - 64 : -1);
-        float v = 0.f;
+        uint32_t b2 = 0u;
         if (f >= 0) {
-            int x = __ldg(win + rt * F + f);
-            if (wrap_int8) x = (int)(int8_t)x;                                  // DataStore.py:68 int8 round trip
-            const float xf = (float)x;
-            const float hi = __bfloat162float(__float2bfloat16_rn(xf));
-            v = (col >= F && col < 2 * F) ? xf - hi : hi;
+            const uint32_t pair = __ldg(row + (f >> 1));
+            int x0 = (int)(int16_t)(pair & 0xffffu), x1 = (int)(int16_t)(pair >> 16);
+            if (wrap_int8) { x0 = (int)(int8_t)x0; x1 = (int)(int8_t)x1; }      // DataStore.py:68 int8 round trip
+            const float f0 = (float)x0, f1 = (float)x1;
+            const float h0 = __bfloat162float(__float2bfloat16_rn(f0)), h1 = __bfloat162float(__float2bfloat16_rn(f1));
+            const bool lo = col >= F && col < 2 * F;
+            const __nv_bfloat162 v = __floats2bfloat162_rn(lo ? f0 - h0 : h0, lo ? f1 - h1 : h1);
+            b2 = *(const uint32_t*)&v;
         }
-        const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
-        if (k & 1) o[k >> 1] |= b << 16; else o[k >> 1] = b;
+        o[k >> 1] = b2;
     }
     *(uint4*)(xhl + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -393,6 +398,7 @@ int lstm_run(PvLstmModel* m, const int16_t* windows, int64_t n, int32_t wrap_int
 extern "C" int pv_lstm_infer(PvLstmModel* m, const int16_t* windows, int64_t n, int32_t wrap_int8, float* probs,
                              uint8_t* argmax, void* workspace, int64_t workspace_bytes, void* stream_) {
     if (!m || !windows || !probs || !workspace) return pv::set_error(PV_EINVAL, "null argument");
+    if ((uintptr_t)windows & 3) return pv::set_error(PV_EINVAL, "pv_lstm_infer: windows must be 4-byte aligned (a window is 1716 bytes, so any whole-window offset into an aligned array is)");
     if (n <= 0) return PV_OK;
     cudaStream_t st = (cudaStream_t)stream_;
     static int use_graph = -1;
