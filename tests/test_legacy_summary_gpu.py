@@ -72,6 +72,24 @@ def check(b, r=0, chunk=(1000, 50)):
     return g
 
 
+def test_product_matches_the_committed_golden_vectors():
+    """tests/golden/legacy_summary.json (written by the compiled reference, tests/golden/make_legacy_golden.py)"""
+    import json
+    import legacy_cases as LC
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "legacy_summary.json")))
+    for name, (b, chunk) in LC.cases().items():
+        ref = bytes(b.ref[int(b.region_ref_off[0]):int(b.region_ref_off[0]) + int(b.region_ref_len[0])]).decode()
+        start, end = int(b.region_ref_start[0]), int(b.region_ref_end[0])
+        g = legacy_summary.SummaryGenerator(ref, "c", start, end)
+        g.generate_summary([_Read(b, i) for i in range(b.n_reads)], start, end)
+        w = gold[name]
+        assert g.image == w["image"] and [list(p) for p in g.genomic_pos] == w["genomic_pos"] and g.ref_image == w["ref_image"]
+        assert {str(k): v for k, v in g.longest_insert_count.items()} == w["longest_insert_count"]
+        s = g.chunk_image(chunk[0], chunk[1], 10)
+        assert s.images == w["chunk_images"] and [[list(p) for p in c] for c in s.positions] == w["chunk_positions"]
+        assert s.refs == w["chunk_refs"] and s.labels == w["chunk_labels"] and s.chunk_ids == w["chunk_ids"]
+
+
 def test_hand_built_counts_mapq0_reads():
     ref = "ACGTNacgt" + "ACGT" * 8
     reads = [H.Read(0, "ACGTACGTAC", [(0, 10)]),
