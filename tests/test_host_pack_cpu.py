@@ -79,3 +79,39 @@ def test_group_packer_equals_the_per_array_packers_on_views():
         assert np.array_equal(view.base_exceptions, want.base_exceptions)
         assert np.array_equal(view.cigar16, want.cigar16)
         assert np.array_equal(view.bases, want.bases) and view.n_reads == want.n_reads
+
+
+def test_mix_of_packed_and_plain_groups_follows_the_measured_rates(monkeypatch):
+    """_GroupPacker.choose_plain: x = (T_p - T_wp) / (T_p - T_wp + T_wl) of the groups travel plain, dealt out evenly; nothing
+    before both rates are known; nothing while the two sides are nearly balanced (x < 0.2)."""
+    pk = pipeline._GroupPacker(threads=2, slots=2)
+    n_b, other = 240_000_000, 60_000_000
+    assert not pk.choose_plain(n_b, other)                        # no measurements yet
+    pk.wire_s_per_byte = 0.02e-9                                  # 50 GB/s
+    t_wp, t_wl = (n_b // 4 + other) * 0.02e-9, (n_b + other) * 0.02e-9
+    for t_p_ms, want in [(2.0, 0.0), (3.0, 0.0), (6.4, None), (15.0, None), (45.0, None)]:
+        pk.pack_s_per_base, pk._plain_acc = t_p_ms * 1e-3 / n_b, 0.0
+        t_p = t_p_ms * 1e-3
+        x = 0.0 if t_p <= t_wp else (t_p - t_wp) / (t_p - t_wp + t_wl)
+        picks = [pk.choose_plain(n_b, other) for _ in range(200)]
+        if want == 0.0 or x < 0.2:
+            assert not any(picks)
+        else:
+            assert abs(sum(picks) / 200.0 - x) < 0.02
+            runs = "".join("1" if p else "0" for p in picks)
+            assert "1111" not in runs or x > 0.75                  # spread out, not bunched
+    monkeypatch.setenv("PV_PACK_MIX", "0")
+    pk.pack_s_per_base = 45e-3 / n_b
+    assert not any(pk.choose_plain(n_b, other) for _ in range(20))
+
+
+def test_default_pack_threads_is_this_ranks_share_of_the_cores(monkeypatch):
+    import os
+    cores = min(os.cpu_count() or 1, len(os.sched_getaffinity(0)))
+    monkeypatch.delenv("PV_PACK_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert pipeline.default_pack_threads() == max(1, min(32, cores - 1))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    assert pipeline.default_pack_threads() == max(1, min(32, cores // 4 - 1))
+    monkeypatch.setenv("PV_PACK_THREADS", "5")
+    assert pipeline.default_pack_threads() == 5
