@@ -36,6 +36,8 @@ class CallOptions:
     group_mbp: float = 32.0                     # contig span decoded per device call (a BGZF block takes ~10 ms: large calls amortise that)
     threads: int = 0
     filter: candidate_filter.FilterOptions = field(default_factory=candidate_filter.FilterOptions)
+    predictions_hdf: Optional[str] = None       # leave the reference's stage-2 file (DataStorePredict.py:49-66) beside the run:
+                                                # one batch per decoded group; rank r of a multi-rank job writes <path>.<r>
 
 
 def contig_intervals(fasta: ingest.FASTAHandler, regions: Optional[Sequence] = None, region_size: int = 100000) -> List[Tuple[str, int, int]]:
@@ -84,6 +86,10 @@ def call_candidates(bam_path: str, fasta_path: str, hot: HotPath, regions: Optio
     phasing, variant = {}, {}
     contigs: List[str] = []
     stats = dict(intervals=len(mine), candidates=0, reads=0, compressed_bytes=0)
+    store, batch_no = None, 0
+    if opt.predictions_hdf:
+        from . import datastore
+        store = datastore.DataStorePredict(opt.predictions_hdf if world == 1 else "%s.%d" % (opt.predictions_hdf, rank), "w")
     for name, ivs in by_contig.items():
         ivs.sort()
         groups = [([s for s, _ in ivs[i:i + per_group]], [e for _, e in ivs[i:i + per_group]]) for i in range(0, len(ivs), per_group)]
@@ -95,6 +101,9 @@ def call_candidates(bam_path: str, fasta_path: str, hot: HotPath, regions: Optio
                 continue
             pred = hot.run_device(got.batch, to_host=True)
             stats["candidates"] += len(pred)
+            if store is not None and len(pred):
+                datastore.write_prediction_batch(store, batch_no, pred, list(got.batch.host.contigs))
+                batch_no += 1
             c, p, v = candidate_filter.find_candidates(pred, _RegionView(got.batch), opt.filter)
             for k, lst in p.items():
                 phasing.setdefault(k, []).extend(lst)
@@ -103,6 +112,8 @@ def call_candidates(bam_path: str, fasta_path: str, hot: HotPath, regions: Optio
             for x in c:
                 if x not in contigs:
                     contigs.append(x)
+    if store is not None:
+        store.close()
     return gather_candidates((contigs, phasing, variant, stats), rank, world, group)
 
 

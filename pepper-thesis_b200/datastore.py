@@ -1,0 +1,84 @@
+"""The reference's HDF5 hand-off files, written without h5py (hdf5_lite.py): the image file of stage 1
+(/root/reference/pepper_variant/modules/python/DataStore.py:54-71: ``summaries/<name>/{contigs 'S', positions int32, depths
+uint8, candidates vlen str, candidate_frequency uint8, images int8}``) and the prediction file of stage 2
+(DataStorePredict.py:49-66: ``predictions/batch_<n>/{contigs, positions, depths, candidates, candidate_frequency,
+base_prediction float64}``). The B200 path itself hands tensors from stage to stage (pipeline.HotPath); these writers exist so
+that a run can leave the files the reference's own stage 2 / stage 3 tools read. Same method names and argument order as the
+reference classes; the int8 cast of the images (DataStore.py:68) wraps like numpy's."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import hdf5_lite
+
+
+class _Store:
+    def __init__(self, filename, mode="w"):
+        if mode not in ("w", "x"):
+            raise ValueError("only writing is supported (mode 'w'); read the files with h5py or hdf5_lite.Reader")
+        self.filename, self.mode = filename, mode
+        self.file_handler = None
+        self._names = set()
+
+    def __enter__(self):
+        self.file_handler = hdf5_lite.Writer(self.filename)
+        return self
+
+    def __exit__(self, *args):
+        self.close()
+
+    def close(self):
+        if self.file_handler is not None:
+            self.file_handler.close()
+            self.file_handler = None
+
+    def _put(self, path, name, contigs, positions, depths, candidates, candidate_frequency):
+        f = self.file_handler
+        f["%s/%s/contigs" % (path, name)] = np.array(contigs, dtype="S")
+        f["%s/%s/positions" % (path, name)] = np.array(positions, dtype=np.int32)
+        f["%s/%s/depths" % (path, name)] = np.array(depths, dtype=np.int64).astype(np.uint8)
+        f["%s/%s/candidates" % (path, name)] = hdf5_lite.VlenStr(candidates)
+        f["%s/%s/candidate_frequency" % (path, name)] = np.array(candidate_frequency, dtype=np.int64).astype(np.uint8)
+
+
+class DataStore(_Store):
+    """DataStore.py:7-71 (writing side)"""
+    _summary_path_ = "summaries"
+
+    def write_summary(self, summary_name, contigs, positions, depths, all_candidates, all_candidate_frequency, all_images,
+                      all_base_labels=None, all_type_label=None, train_mode=False):
+        if self.file_handler is None:
+            self.__enter__()
+        if summary_name in self._names:
+            return
+        self._names.add(summary_name)
+        self._put(self._summary_path_, summary_name, contigs, positions, depths, all_candidates, all_candidate_frequency)
+        images = np.asarray(all_images)
+        self.file_handler["%s/%s/images" % (self._summary_path_, summary_name)] = images.astype(np.int64).astype(np.int8)   # :68
+        if train_mode:
+            self.file_handler["%s/%s/base_labels" % (self._summary_path_, summary_name)] = np.array(all_base_labels, dtype=np.uint8)
+            self.file_handler["%s/%s/type_label" % (self._summary_path_, summary_name)] = np.array(all_type_label, dtype=np.uint8)
+
+
+class DataStorePredict(_Store):
+    """DataStorePredict.py:6-66 (writing side)"""
+    _prediction_path_ = "predictions"
+
+    def write_prediction(self, batch_no, contigs, positions, depths, candidates, candidate_frequencies, base_predictions):
+        if self.file_handler is None:
+            self.__enter__()
+        name = "batch_" + str(batch_no)
+        if name in self._names:
+            return
+        self._names.add(name)
+        self._put(self._prediction_path_, name, contigs, positions, depths, candidates, candidate_frequencies)
+        self.file_handler["%s/%s/base_prediction" % (self._prediction_path_, name)] = np.array(base_predictions, dtype=np.float64)   # :66
+
+
+def write_prediction_batch(store: DataStorePredict, batch_no: int, pred, contigs_of_region) -> None:
+    """One ``pipeline.Predictions`` as one ``predictions/batch_<n>`` group: what predict_distributed_gpu.py:82-93 hands to
+    ``write_prediction`` per batch -- contig, position, depth, [candidate allele], [its frequency], the three genotype
+    probabilities -- for every candidate."""
+    contigs = [contigs_of_region[int(r)] for r in pred.region]
+    store.write_prediction(batch_no, contigs, pred.position, np.minimum(pred.depth, 255), [[a.decode("latin-1")] for a in pred.alleles()],
+                           [[int(min(f, 255))] for f in pred.frequency], pred.probs.astype(np.float64))

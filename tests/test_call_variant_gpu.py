@@ -60,8 +60,15 @@ def test_bam_to_vcf_equals_host_ingest_chain(files, tmp_path, group_mbp):
     assert stats["intervals"] == 12 + 1 and stats["candidates"] > 200 and len(variant) > 20
     _same(phasing, want_p)
     _same(variant, want_v)
+    opt.predictions_hdf = str(tmp_path / "predictions.hdf")          # the reference's stage-2 file beside the run (datastore.py)
     counts, stats2, paths = CV.call_variant(files["bam"], files["fa"], _hot(), str(tmp_path / "out"), "HG002", regions, opt)
     assert counts[0] == len(_records(paths["full"])) > 0 and counts[0] == counts[1] + counts[2]
+    from pepper_thesis_b200 import hdf5_lite
+    rd = hdf5_lite.Reader(opt.predictions_hdf)
+    batches = rd.keys("predictions")
+    n_pred = sum(rd["predictions/%s/positions" % b].shape[0] for b in batches)
+    assert n_pred == stats2["candidates"] and rd["predictions/%s/base_prediction" % batches[0]].shape[1] == 3
+    assert set(rd["predictions/%s/contigs" % batches[0]].tolist()) == {b"chrS"}
     assert all(os.path.exists(p + ".tbi") for p in paths.values())
     # the same records as the writer produces from the host chain's candidates
     from pepper_thesis_b200.vcf_writer import VCFWriter, VcfOptions
