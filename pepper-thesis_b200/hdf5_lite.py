@@ -47,8 +47,10 @@ def _pad8(n: int) -> int:
 # ---------------------------------------------------------------------------------------------------------------------
 def _datatype_message(dt: Union[np.dtype, str]) -> bytes:
     if isinstance(dt, str) and dt == "vlen_str":
-        # class 9 (variable length), version 1; bits: type 1 = string, padding 0 (null terminated), character set 1 (UTF-8)
-        base = struct.pack("<BBBBI", 0x13, 0x10, 0x00, 0x00, 1)       # base type: 1-byte string, null terminated, UTF-8
+        # class 9 (variable length), version 1; bits: type 1 = string, padding 0 (null terminated), character set 1 (UTF-8:
+        # h5py's str). The base type is the library's H5T_C_S1 as it stands (1 byte, null terminated, ASCII): setting the
+        # size of a string type to "variable" wraps that type, the character set lives on the variable-length level.
+        base = struct.pack("<BBBBI", 0x13, 0x00, 0x00, 0x00, 1)
         return struct.pack("<BBBBI", 0x19, 0x01, 0x01, 0x00, 16) + base
     dt = np.dtype(dt)
     if dt.kind in "iu":
@@ -175,9 +177,17 @@ class Writer:
         i = 0
         while i < len(values):
             # fill one collection: 16 bytes of header, objects of 16 + padded size, room for the free-space object 0
-            objs, used = [], 16
+            # (an empty string is a null heap id -- length 0, address 0, index 0 -- like the library's "set null")
+            objs, used, slots = [], 16, []
             while i < len(values) and (not objs or used + 16 + _pad8(len(values[i])) + 16 <= GCOL_MIN):
-                objs.append(values[i]); used += 16 + _pad8(len(values[i])); i += 1
+                if len(values[i]):
+                    objs.append(values[i]); used += 16 + _pad8(len(values[i])); slots.append(len(objs))
+                else:
+                    slots.append(0)
+                i += 1
+            if not objs:
+                out += b"".join(struct.pack("<IQI", 0, 0, 0) for _ in slots)
+                continue
             size = max(GCOL_MIN, _pad8(used + 16))
             col = bytearray(b"GCOL" + struct.pack("<B3xQ", 1, size))
             for k, v in enumerate(objs):
@@ -185,8 +195,8 @@ class Writer:
             free = size - len(col)
             col += struct.pack("<HH4xQ", 0, 0, free) + b"\0" * (free - 16)      # object 0: the free space (size includes its header)
             addr = self._alloc(bytes(col))
-            for k, v in enumerate(objs):
-                out += struct.pack("<IQI", len(v), addr, k + 1)
+            for k in slots:
+                out += struct.pack("<IQI", len(objs[k - 1]), addr, k) if k else struct.pack("<IQI", 0, 0, 0)
         return bytes(out)
 
     def _write_group(self, g: _Group) -> Tuple[int, int, int]:
@@ -457,7 +467,7 @@ class Reader:
             out = []
             for k in range(n):
                 ln, col, idx = struct.unpack_from("<IQI", raw, 16 * k)
-                out.append(self._global_heap_object(col, idx)[:ln].decode("utf-8"))
+                out.append(self._global_heap_object(col, idx)[:ln].decode("utf-8") if ln else "")
             return out[0] if not shape else np.array(out, dtype=object).reshape(shape)
         else:
             raise FormatError("datatype class %d not handled" % cls)

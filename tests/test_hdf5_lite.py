@@ -71,7 +71,8 @@ def test_round_trip_of_every_type_and_of_large_groups(tmp_path):
         want["t/S"] = np.array(["chr20", "chrX", ""], dtype="S")
         for k in ("t/i8", "t/u8", "t/i64", "t/f64", "t/f32", "t/S"):
             w[k] = want[k]
-        strs = [["1" + "ACGT"[i % 4] * (i % 70)] for i in range(700)]     # ~30 KB of strings: several global heap collections
+        strs = [["1" + "ACGT"[i % 4] * (i % 70) if i % 50 else ""] for i in range(700)]     # ~30 KB of strings: several global heap
+        # collections; the empty ones are null heap ids
         w["t/vlen"] = H.VlenStr(strs)
         w["meta/yaml"] = "summaries: !!set {a: null}\n"
         w["t/empty"] = np.zeros((0, 33, 26), np.int8)
@@ -87,6 +88,7 @@ def test_round_trip_of_every_type_and_of_large_groups(tmp_path):
     assert r["t/empty"].shape == (0, 33, 26)
     d = r.describe("t/vlen")
     assert d["type_class"] == 9 and d["type_size"] == 16 and d["type_bits"][:2] == (0x01, 0x01)
+    assert d["type_props"][:8] == bytes([0x13, 0, 0, 0, 1, 0, 0, 0])          # base type: H5T_C_S1 (1 byte, null terminated, ASCII)
     assert r.describe("t/i8")["type_bits"][0] & 8 and not r.describe("t/u8")["type_bits"][0] & 8
     # every structure starts 8-byte aligned and lies inside the file
     raw = open(p, "rb").read()
