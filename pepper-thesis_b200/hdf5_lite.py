@@ -224,7 +224,7 @@ class Writer:
         # symbol-table nodes of up to 2K entries each (allocated at full size, as the library does), then the B-tree
         per = 2 * GROUP_LEAF_K
         leaves = []
-        for i in range(0, max(1, len(entries)), per):
+        for i in range(0, len(entries), per):
             chunk = entries[i:i + per]
             node = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(chunk)))
             for n, hdr, cache, scratch in chunk:
@@ -239,6 +239,8 @@ class Writer:
         """children: (address, heap offset of the largest name below it). Nodes of up to 2K children; returns the root."""
         per = 2 * GROUP_INTERNAL_K
         nodes = []
+        if not children:                                                         # an empty group: a leaf-level node without entries
+            return self._alloc(b"TREE" + struct.pack("<BBH", 0, 0, 0) + struct.pack("<QQ", UNDEF, UNDEF) + b"\0" * (8 + 16 * per))
         groups = [children[i:i + per] for i in range(0, len(children), per)]
         addrs = []
         for gi, grp in enumerate(groups):
