@@ -82,3 +82,16 @@ def write_prediction_batch(store: DataStorePredict, batch_no: int, pred, contigs
     contigs = [contigs_of_region[int(r)] for r in pred.region]
     store.write_prediction(batch_no, contigs, pred.position, np.minimum(pred.depth, 255), [[a.decode("latin-1")] for a in pred.alleles()],
                            [[int(min(f, 255))] for f in pred.frequency], pred.probs.astype(np.float64))
+
+
+def write_summary_from_workspace(store: DataStore, summary_name: str, ws, k: int, contigs_of_region) -> None:
+    """The first ``k`` candidates of a summary workspace (device.SummaryWorkspace after pv_summary_regions) as one
+    ``summaries/<name>`` group: what ImageGenerationUI.py:236-256 hands to ``write_summary`` -- the windows go to disk as int8
+    (DataStore.py:68: values beyond [-128, 127] wrap, which the ``wrap_int8`` flag of the inference kernels reproduces)."""
+    region = ws.region[:k].cpu().numpy()
+    alleles = ws.allele[:k].cpu().numpy()
+    lens = ws.allele_len[:k].cpu().numpy()
+    store.write_summary(summary_name, [contigs_of_region[int(r)] for r in region], ws.position[:k].cpu().numpy(),
+                        np.minimum(ws.depth[:k].cpu().numpy(), 255),
+                        [[bytes(alleles[i, :lens[i]]).decode("latin-1")] for i in range(k)],
+                        [[int(min(f, 255))] for f in ws.frequency[:k].cpu().numpy()], ws.windows[:k].cpu().numpy())

@@ -173,3 +173,25 @@ def test_inline_packing_of_plain_batches_does_not_change_results():
     hp2.pack_inline = True
     v = hp2.run_host(q)
     assert len(w) > 50 and np.array_equal(w.position, v.position) and w.alleles() == v.alleles() and np.array_equal(w.probs, v.probs)
+
+
+def test_image_file_of_a_summary_has_the_reference_schema(tmp_path):
+    """datastore.write_summary_from_workspace: the candidates of a group as ``summaries/<name>`` of the reference's image file
+    (DataStore.py:54-71), windows wrapped to int8 like np.int8 does."""
+    from pepper_thesis_b200 import datastore, hdf5_lite
+    b = H.kat_clamp()                                             # 300x coverage: window values reach -300
+    hp, _ = _hot_path("ont_r9", group=1)
+    ws, k = hp.summarize(dev.DeviceBatch(b))
+    assert k > 0
+    p = str(tmp_path / "images.hdf")
+    with datastore.DataStore(p, "w") as ds:
+        datastore.write_summary_from_workspace(ds, "c_0_100", ws, k, ["c"])
+    r = hdf5_lite.Reader(p)
+    g = "summaries/c_0_100/"
+    win = ws.windows[:k].cpu().numpy()
+    assert win.min() < -128                                        # the wrap is exercised
+    assert r[g + "images"].dtype == np.int8 and np.array_equal(r[g + "images"], win.astype(np.int8))
+    assert np.array_equal(r[g + "positions"], ws.position[:k].cpu().numpy().astype(np.int32))
+    o = O.port_summary(b, 0, H.R9)
+    assert [x[0].encode("latin-1") for x in r[g + "candidates"].tolist()] == list(o["alleles"])
+    assert r[g + "contigs"].tolist() == [b"c"] * k
