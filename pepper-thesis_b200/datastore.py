@@ -95,3 +95,31 @@ def write_summary_from_workspace(store: DataStore, summary_name: str, ws, k: int
                         np.minimum(ws.depth[:k].cpu().numpy(), 255),
                         [[bytes(alleles[i, :lens[i]]).decode("latin-1")] for i in range(k)],
                         [[int(min(f, 255))] for f in ws.frequency[:k].cpu().numpy()], ws.windows[:k].cpu().numpy())
+
+
+def predict_hdf5(image_hdf: str, output_hdf: str, model, device="cuda", pass_windows: int = 32768) -> int:
+    """Stage 2 of ``pepper_variant call_variant`` as the reference runs it from files (predict_distributed_gpu.py:48-96 +
+    dataloader_predict.py:82-93): every ``summaries/<name>`` group of an image file -- written by the reference's DataStore
+    through h5py in the classic layout, or by ``DataStore`` above -- goes through the tcgen05 LSTM model, the genotype
+    probabilities leave as ``predictions/batch_<n>`` groups (one per pass instead of one per 512 windows). The int8 values of
+    the file are what the network sees, exactly like the reference's ``images.type(torch.FloatTensor)``. Returns the number of
+    candidates predicted."""
+    import torch
+    rd = hdf5_lite.Reader(image_hdf)
+    names = rd.keys(DataStore._summary_path_) if DataStore._summary_path_ in rd.keys("/") else []
+    total, batch_no = 0, 0
+    with DataStorePredict(output_hdf, "w") as out:
+        for name in names:
+            g = "%s/%s/" % (DataStore._summary_path_, name)
+            images = rd[g + "images"]
+            contigs, positions, depths = rd[g + "contigs"], rd[g + "positions"], rd[g + "depths"]
+            cands, freqs = rd[g + "candidates"], rd[g + "candidate_frequency"]
+            for lo in range(0, images.shape[0], pass_windows):
+                hi = min(images.shape[0], lo + pass_windows)
+                x = torch.from_numpy(np.ascontiguousarray(images[lo:hi]).astype(np.int16)).to(device)
+                probs, _ = model.infer_windows(x, wrap_int8=False)          # the file already holds the wrapped values
+                out.write_prediction(batch_no, [c.decode("latin-1") for c in contigs[lo:hi].tolist()], positions[lo:hi],
+                                     depths[lo:hi], cands[lo:hi].tolist(), freqs[lo:hi].tolist(), probs.cpu().numpy())
+                batch_no += 1
+                total += hi - lo
+    return total

@@ -195,3 +195,25 @@ def test_image_file_of_a_summary_has_the_reference_schema(tmp_path):
     o = O.port_summary(b, 0, H.R9)
     assert [x[0].encode("latin-1") for x in r[g + "candidates"].tolist()] == list(o["alleles"])
     assert r[g + "contigs"].tolist() == [b"c"] * k
+
+
+def test_stage2_from_an_image_file_equals_the_tensor_hand_off(tmp_path):
+    """datastore.predict_hdf5: image file in, prediction file out (the reference's file-based stage 2) gives the probabilities
+    of the in-memory path with the int8 wrap switched on."""
+    from pepper_thesis_b200 import datastore, hdf5_lite
+    b = synth.generate("ont_r9", 320000, 20.0, seed=31)           # 3 regions
+    hp, sd = _hot_path("ont_r9", wrap=True, group=3)
+    want = hp.run_host(b)
+    p, q = str(tmp_path / "images.hdf"), str(tmp_path / "pred.hdf")
+    with datastore.DataStore(p, "w") as ds:
+        for r in range(b.n_regions):
+            ws, k = hp.summarize(dev.DeviceBatch(b.region_range_view(r, r + 1)))
+            datastore.write_summary_from_workspace(ds, "chr_%d" % r, ws, k, ["chr"])
+    n = datastore.predict_hdf5(p, q, hp.model, pass_windows=500)
+    rd = hdf5_lite.Reader(q)
+    batches = sorted(rd.keys("predictions"), key=lambda s: int(s.split("_")[1]))
+    probs = np.concatenate([rd["predictions/%s/base_prediction" % x] for x in batches])
+    pos = np.concatenate([rd["predictions/%s/positions" % x] for x in batches])
+    assert n == len(want) == probs.shape[0] > 300 and len(batches) >= 3
+    assert np.array_equal(pos, want.position.astype(np.int32))
+    assert np.abs(probs - want.probs.astype(np.float64)).max() < 1e-6
