@@ -80,8 +80,10 @@ def write_prediction_batch(store: DataStorePredict, batch_no: int, pred, contigs
     ``write_prediction`` per batch -- contig, position, depth, [candidate allele], [its frequency], the three genotype
     probabilities -- for every candidate."""
     contigs = [contigs_of_region[int(r)] for r in pred.region]
-    store.write_prediction(batch_no, contigs, pred.position, np.minimum(pred.depth, 255), [[a.decode("latin-1")] for a in pred.alleles()],
-                           [[int(min(f, 255))] for f in pred.frequency], pred.probs.astype(np.float64))
+    # depths and frequencies go through the reference's uint8 casts as they are (DataStorePredict.py:63,65: a frequency above 255
+    # wraps in the file, exactly as it does there; depths are at most 125, region_summary.cpp:682)
+    store.write_prediction(batch_no, contigs, pred.position, pred.depth, [[a.decode("latin-1")] for a in pred.alleles()],
+                           [[int(f)] for f in pred.frequency], pred.probs.astype(np.float64))
 
 
 def write_summary_from_workspace(store: DataStore, summary_name: str, ws, k: int, contigs_of_region) -> None:
@@ -92,9 +94,9 @@ def write_summary_from_workspace(store: DataStore, summary_name: str, ws, k: int
     alleles = ws.allele[:k].cpu().numpy()
     lens = ws.allele_len[:k].cpu().numpy()
     store.write_summary(summary_name, [contigs_of_region[int(r)] for r in region], ws.position[:k].cpu().numpy(),
-                        np.minimum(ws.depth[:k].cpu().numpy(), 255),
+                        ws.depth[:k].cpu().numpy(),
                         [[bytes(alleles[i, :lens[i]]).decode("latin-1")] for i in range(k)],
-                        [[int(min(f, 255))] for f in ws.frequency[:k].cpu().numpy()], ws.windows[:k].cpu().numpy())
+                        [[int(f)] for f in ws.frequency[:k].cpu().numpy()], ws.windows[:k].cpu().numpy())
 
 
 def predict_hdf5(image_hdf: str, output_hdf: str, model, device="cuda", pass_windows: int = 32768) -> int:
@@ -123,3 +125,57 @@ def predict_hdf5(image_hdf: str, output_hdf: str, model, device="cuda", pass_win
                 batch_no += 1
                 total += hi - lo
     return total
+
+
+def find_candidates_hdf5(prediction_hdf: str, fasta_path: str, options=None):
+    """Stage 3 from the prediction FILE (FindCandidates.py:150-184 -> CandidateFinder.find_candidates, :532-581): every
+    ``predictions/batch_<n>`` group of the file and the FASTA go through the device filter (candidate_filter.cu); returns
+    ``(contigs, phasing_dict, variant_calling_dict)`` like the reference. The reference context of a contig's candidates is
+    fetched once per contig (FASTA_handler.get_reference_sequence) instead of once per candidate."""
+    from . import candidate_filter, ingest
+    from .pipeline import Predictions
+    rd = hdf5_lite.Reader(prediction_hdf)
+    path = DataStorePredict._prediction_path_
+    batches = sorted(rd.keys(path), key=lambda s: int(s.split("_")[1])) if path in rd.keys("/") else []
+    if not batches:
+        return [], {}, {}
+    col = {k: [] for k in ("contigs", "positions", "depths", "candidates", "candidate_frequency", "base_prediction")}
+    for b in batches:
+        for k in col:
+            col[k].append(rd["%s/%s/%s" % (path, b, k)])
+    contigs = [c.decode("latin-1") for a in col["contigs"] for c in a.tolist()]
+    pos = np.concatenate(col["positions"]).astype(np.int64)
+    depth = np.concatenate(col["depths"]).astype(np.int32)
+    freq = np.concatenate([a.reshape(a.shape[0], -1)[:, 0] for a in col["candidate_frequency"]]).astype(np.int32)
+    probs = np.concatenate(col["base_prediction"]).astype(np.float32)
+    cands = [row[0] if isinstance(row, (list, np.ndarray)) else row for a in col["candidates"] for row in a.tolist()]
+    n = len(pos)
+    allele = np.zeros((n, 64), np.uint8)
+    allele_len = np.zeros(n, np.uint8)
+    for i, c in enumerate(cands):
+        b = c.encode("latin-1")[:64]
+        allele[i, :len(b)] = np.frombuffer(b, np.uint8)
+        allele_len[i] = len(b)
+    names = list(dict.fromkeys(contigs))
+    index = {c: i for i, c in enumerate(names)}
+    region = np.array([index[c] for c in contigs], np.int32)
+    fasta = ingest.FASTAHandler(fasta_path)
+
+    class _View:
+        pass
+    v = _View()
+    v.n_regions, v.contigs = len(names), names
+    starts, offs, lens, clen, refs = [], [], [], [], []
+    at = 0
+    for i, c in enumerate(names):
+        p = pos[region == i]
+        total = int(fasta.get_chromosome_sequence_length(c))
+        lo, hi = max(0, int(p.min()) - 32), min(total, int(p.max()) + 128)
+        seq = fasta.get_reference_sequence(c, lo, hi).encode("latin-1")
+        starts.append(lo); offs.append(at); lens.append(len(seq)); clen.append(total); refs.append(np.frombuffer(seq, np.uint8))
+        at += len(seq)
+    v.region_ref_start, v.region_ref_off = np.array(starts, np.int64), np.array(offs, np.int64)
+    v.region_ref_len, v.region_contig_len = np.array(lens, np.int64), np.array(clen, np.int64)
+    v.ref = np.ascontiguousarray(np.concatenate(refs))
+    pred = Predictions(region, pos, depth, freq, allele, allele_len, probs, probs.argmax(1).astype(np.uint8))
+    return candidate_filter.find_candidates(pred, v, options or candidate_filter.FilterOptions())

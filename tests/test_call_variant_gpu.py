@@ -69,6 +69,11 @@ def test_bam_to_vcf_equals_host_ingest_chain(files, tmp_path, group_mbp):
     n_pred = sum(rd["predictions/%s/positions" % b].shape[0] for b in batches)
     assert n_pred == stats2["candidates"] and rd["predictions/%s/base_prediction" % batches[0]].shape[1] == 3
     assert set(rd["predictions/%s/contigs" % batches[0]].tolist()) == {b"chrS"}
+    # stage 3 from that FILE + the FASTA (the reference's FindCandidates route) selects the candidates of the in-memory route
+    from pepper_thesis_b200 import datastore
+    c3, p3, v3 = datastore.find_candidates_hdf5(opt.predictions_hdf, files["fa"], opt.filter)
+    _same(p3, want_p)
+    _same(v3, want_v)
     assert all(os.path.exists(p + ".tbi") for p in paths.values())
     # the same records as the writer produces from the host chain's candidates
     from pepper_thesis_b200.vcf_writer import VCFWriter, VcfOptions
