@@ -304,8 +304,12 @@ class Reader:
             raise FormatError("object header version %d at %d" % (ver, addr))
         blocks = [(p + 16, size)]
         out = []
+        n_blocks = 0
         while blocks and len(out) < n_msgs:
             q, left = blocks.pop(0)
+            n_blocks += 1
+            if n_blocks > 64 or q + left > len(self.d):
+                raise FormatError("object header at %d: continuation blocks" % addr)
             while left >= 8 and len(out) < n_msgs:
                 mtype, msize, flags = struct.unpack_from("<HHB", self.d, q)
                 data = self.d[q + 8:q + 8 + msize]
@@ -330,9 +334,10 @@ class Reader:
         seg = self.d[q:q + size]
         if len(seg) != size:
             raise FormatError("local heap data segment")
-        f = free
+        f, steps = free, 0
         while f != 1:                                                            # walk the free list (1 = end of list)
-            if f + 16 > size:
+            steps += 1
+            if f + 16 > size or steps > size // 16 + 1:                          # (a cyclic list never ends)
                 raise FormatError("local heap free block at %d" % f)
             f, fsz = struct.unpack_from("<QQ", seg, f)
             if fsz < 16:
@@ -343,13 +348,15 @@ class Reader:
         end = heap.index(b"\0", off)
         return heap[off:end].decode("utf-8")
 
-    def _btree_leaves(self, addr: int, heap: bytes, prev_key=None):
+    def _btree_leaves(self, addr: int, heap: bytes, want_level=None):
         p = self._at(addr)
         if self.d[p:p + 4] != b"TREE":
             raise FormatError("B-tree node at %d" % addr)
         ntype, level, used = struct.unpack_from("<BBH", self.d, p + 4)
         if ntype != 0 or used > 2 * self.int_k:
             raise FormatError("group B-tree node type %d with %d entries" % (ntype, used))
+        if (want_level is not None and level != want_level) or level > 16:       # levels count down to the leaves: no cycles
+            raise FormatError("B-tree node at %d has level %d" % (addr, level))
         keys = [struct.unpack_from("<Q", self.d, p + 24 + 16 * i)[0] for i in range(used + 1)]
         kids = [struct.unpack_from("<Q", self.d, p + 32 + 16 * i)[0] for i in range(used)]
         names = [self._name(heap, k) for k in keys]
@@ -357,7 +364,7 @@ class Reader:
             raise FormatError("B-tree keys out of order at %d" % addr)
         out = []
         for i, c in enumerate(kids):
-            out += [(c, names[i], names[i + 1])] if level == 0 else self._btree_leaves(c, heap)
+            out += [(c, names[i], names[i + 1])] if level == 0 else self._btree_leaves(c, heap, level - 1)
         return out
 
     def _read_group(self, hdr_addr: int):
@@ -393,7 +400,7 @@ class Reader:
 
     def _resolve_group(self, path: str):
         g = self.root
-        for p in [p for p in path.split("/") if p]:
+        for p in [p for p in path.split("/") if p][:64]:
             if p not in g:
                 raise KeyError(path)
             g = self._read_group(g[p])
@@ -448,8 +455,15 @@ class Reader:
 
     def __getitem__(self, path: str):
         i = self.describe(path)
+        for need in ("shape", "type_class", "layout_class"):
+            if need not in i:
+                raise FormatError("%s: no %s message" % (path, need.split("_")[0]))
         shape = i["shape"]
-        n = int(np.prod(shape)) if shape else 1
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if n > len(self.d):                                       # more elements than the file has bytes
+            raise FormatError("%s: %d elements in a file of %d bytes" % (path, n, len(self.d)))
         if i["layout_class"] == 1:
             if i["size"] is None:
                 i["size"] = n * i["type_size"]
@@ -459,6 +473,8 @@ class Reader:
         else:
             raise FormatError("chunked datasets are not handled")
         cls, size, bits = i["type_class"], i["type_size"], i["type_bits"]
+        if (cls == 0 and size not in (1, 2, 4, 8)) or (cls == 1 and size not in (4, 8)) or (cls == 3 and not 0 < size <= (1 << 24)):
+            raise FormatError("%s: datatype class %d of %d bytes" % (path, cls, size))
         if cls == 0:
             dt = np.dtype("%s%d" % ("i" if bits[0] & 8 else "u", size)).newbyteorder(">" if bits[0] & 1 else "<")
         elif cls == 1:

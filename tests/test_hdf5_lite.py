@@ -162,3 +162,45 @@ def test_predictions_as_the_reference_stage2_file(tmp_path):
     assert np.array_equal(r[g + "positions"], pred.position.astype(np.int32)) and np.array_equal(r[g + "depths"], pred.depth.astype(np.uint8))
     assert [x[0].encode("latin-1") for x in r[g + "candidates"].tolist()] == pred.alleles()
     assert np.array_equal(r[g + "base_prediction"], probs.astype(np.float64))
+
+
+def test_reader_fails_cleanly_on_corrupted_files(tmp_path):
+    """single-byte and truncation damage: every read either succeeds or raises an ordinary exception -- no hang (cyclic free
+    lists, B-tree cycles), no crash"""
+    p = str(tmp_path / "ok.h5")
+    with H.Writer(p) as w:
+        for i in range(20):
+            w["g/sub%02d/x" % i] = np.arange(i + 1, dtype=np.int32)
+        w["g/v"] = H.VlenStr([["1A"], [""], ["2ACGT"]])
+        w["s"] = "text"
+    raw = bytearray(open(p, "rb").read())
+    rng = np.random.default_rng(5)
+
+    def read_all(path):
+        r = H.Reader(path)
+        def walk(prefix, depth=0):
+            for k in r.keys(prefix):
+                q = prefix.rstrip("/") + "/" + k
+                if r.is_group(q):
+                    if depth < 4:
+                        walk(q, depth + 1)
+                else:
+                    r[q]
+        walk("/")
+    read_all(p)
+    survived = 0
+    for trial in range(400):
+        bad = bytearray(raw)
+        if trial % 8 == 7:
+            bad = bad[:int(rng.integers(8, len(bad)))]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+        q = str(tmp_path / "bad.h5")
+        open(q, "wb").write(bad)
+        try:
+            read_all(q)
+            survived += 1
+        except (H.FormatError, KeyError, ValueError, IndexError, struct.error, UnicodeDecodeError, OverflowError, MemoryError):
+            pass
+    assert survived < 400
