@@ -105,7 +105,9 @@ class Writer:
         elif isinstance(value, (str, bytes)):
             g.children[parts[-1]] = ("vlen", VlenStr([value], shape=()))       # h5py stores a Python str as a scalar vlen string
         else:
-            a = np.ascontiguousarray(value)
+            a = np.asarray(value)
+            if a.ndim:                                                        # (ascontiguousarray would turn a scalar into [1])
+                a = np.ascontiguousarray(a)
             if a.dtype.kind == "U":
                 a = a.astype("S")
             if a.dtype.byteorder == ">":
@@ -123,16 +125,20 @@ class Writer:
         if self._closed:
             return
         self._closed = True
-        self.buf = bytearray(96)                       # superblock (56 bytes + the 40-byte root entry), filled in last
-        root_hdr, root_btree, root_heap = self._write_group(self.root)
-        eof = len(self.buf)
-        sb = SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, GROUP_LEAF_K, GROUP_INTERNAL_K, 0)
-        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
-        sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_btree, root_heap)
-        assert len(sb) == 96
-        self.buf[0:96] = sb
+        # structures are streamed to the file as they are laid out (a whole-genome image file is gigabytes); the superblock
+        # (56 bytes + the 40-byte root entry) and the B-tree sibling pointers are patched in afterwards
         with open(self.path, "wb") as f:
-            f.write(self.buf)
+            self._f, self._pos = f, 96
+            f.write(bytes(96))
+            root_hdr, root_btree, root_heap = self._write_group(self.root)
+            eof = self._pos
+            sb = SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, GROUP_LEAF_K, GROUP_INTERNAL_K, 0)
+            sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+            sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_btree, root_heap)
+            assert len(sb) == 96
+            f.seek(0)
+            f.write(sb)
+        self._f = None
 
     def __enter__(self):
         return self
@@ -141,11 +147,19 @@ class Writer:
         self.close()
 
     def _alloc(self, data: bytes) -> int:
-        while len(self.buf) % 8:
-            self.buf.append(0)
-        at = len(self.buf)
-        self.buf += data
+        pad = (-self._pos) % 8
+        if pad:
+            self._f.write(bytes(pad))
+            self._pos += pad
+        at = self._pos
+        self._f.write(data)
+        self._pos += len(data)
         return at
+
+    def _patch(self, at: int, data: bytes):
+        self._f.seek(at)
+        self._f.write(data)
+        self._f.seek(self._pos)
 
     @staticmethod
     def _object_header(messages: List[Tuple[int, bytes, int]]) -> bytes:
@@ -161,7 +175,7 @@ class Writer:
             shape, raw = value.shape, self._write_vlen(value.values)
             dtype_msg = _datatype_message("vlen_str")
         else:
-            shape, raw, dtype_msg = value.shape, value.tobytes(), _datatype_message(value.dtype)
+            shape, raw, dtype_msg = value.shape, (memoryview(value).cast("B") if value.ndim else value.tobytes()) if value.size else b"", _datatype_message(value.dtype)
         addr = self._alloc(raw) if raw else UNDEF
         msgs = [(MSG_DATASPACE, _dataspace_message(shape), 0),
                 (MSG_DATATYPE, dtype_msg, 1),                                   # flag bit 0: constant message
@@ -256,7 +270,8 @@ class Writer:
         for gi, a in enumerate(addrs):                                           # sibling pointers
             left = addrs[gi - 1] if gi > 0 else UNDEF
             right = addrs[gi + 1] if gi + 1 < len(addrs) else UNDEF
-            self.buf[a + 8:a + 24] = struct.pack("<QQ", left, right)
+            if left != UNDEF or right != UNDEF:
+                self._patch(a + 8, struct.pack("<QQ", left, right))
         return nodes[0][0] if len(nodes) == 1 else self._btree_level(nodes, level + 1)
 
 

@@ -204,3 +204,11 @@ def test_reader_fails_cleanly_on_corrupted_files(tmp_path):
         except (H.FormatError, KeyError, ValueError, IndexError, struct.error, UnicodeDecodeError, OverflowError, MemoryError):
             pass
     assert survived < 400
+
+
+def test_scalars_keep_rank_zero(tmp_path):
+    p = str(tmp_path / "s.h5")
+    with H.Writer(p) as w:
+        w["f"] = np.float64(3.5); w["i"] = np.int32(-7); w["s"] = np.array(b"abc")
+    r = H.Reader(p)
+    assert r.describe("f")["shape"] == () and float(r["f"]) == 3.5 and int(r["i"]) == -7 and r["s"].item() == b"abc"
